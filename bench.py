@@ -1,0 +1,323 @@
+"""bench.py -- cPongDouble env-steps/s at 84x84x4 observations (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu E] [--impl ours|reference]
+
+One "step" = one vec-env step of the whole shard: every env advances 4 game frames and both
+agents' (4, 84, 84) uint8 observations are produced (56 448 B per env-step).  Workload =
+BASELINE config 3: 65 536 envs per GPU, device-side random actions, device-side serve RNG.
+For N > 1 the driver launches one rank per GPU with torch.distributed.run; envs shard by
+index, no collective on the step path ("scaling": "weak").
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port of the
+reference's path (the reference is Python + un-installable wheels and cannot travel to the
+GPU box) with all host threads on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_ENV_STEP = 2 * 4 * 84 * 84          # 56 448 B written per env-step
+METRIC = "cPongDouble env-steps/sec at 84x84x4 obs"
+UNIT = "env-steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--envs-per-gpu", type=int, default=65536)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--cpu-sample-envs", type=int, default=256)
+    ap.add_argument("--cpu-sample-steps", type=int, default=0, help="0 = auto (about 10-20 s of CPU work)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------- CPU baseline
+def cpu_baseline(sample_envs, sample_steps, threads):
+    """The oracle port of the reference's path (oracle/pong_oracle.c: renders all four 210x160x3
+    frames per env-step like the reference, max-pool, cv2-exact gray+area, per-agent 4-stack),
+    envs split over `threads` host threads the way SubprocVecEnv splits them over processes."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import pong_oracle
+    atlas = np.load(os.path.join(ROOT, "competitive-rl_b200", "data", "scoreboard_atlas.npz"))["strips"]
+    pong_oracle.set_threads(threads)
+    v = pong_oracle.PongOracleVec("cPongDouble-v0", sample_envs, 84, 4, 21, atlas, None, seed=1)
+    v.reset()
+    rng = np.random.default_rng(0)
+    acts = rng.integers(0, 3, (64, sample_envs, 2)).astype(np.int32)
+    for t in range(3):
+        v.step(acts[t])
+    if sample_steps <= 0:
+        t0 = time.perf_counter()
+        for t in range(4):
+            v.step(acts[t])
+        per = (time.perf_counter() - t0) / 4
+        sample_steps = int(max(8, min(4000, 12.0 / max(per, 1e-6))))
+    t0 = time.perf_counter()
+    for t in range(sample_steps):
+        v.step(acts[t % 64])
+    dt = time.perf_counter() - t0
+    v.close()
+    return {
+        "value": sample_envs * sample_steps / dt, "unit": UNIT, "cores": threads, "kind": "port",
+        "sample": "%d envs x %d vec-steps of cPongDouble 84x84x4, random actions, oracle/pong_oracle.c, %.1f s"
+                  % (sample_envs, sample_steps, dt),
+    }
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        self._t.join(timeout=6)
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from competitive_rl_b200 import _native, make_envs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus > 1 and world == 1:   # plain `python bench.py --gpus N`: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    N = a.envs_per_gpu
+    lib = _native.load()
+    envs = make_envs("cPongDouble-v0", seed=1000, log_dir=None, num_envs=N, asynchronous=True, resized_dim=84,
+                     frame_stack=4, first_env=rank * N, n_buffers=1)
+    envs.reset()
+    h = envs._h
+    stream = torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    actions = torch.zeros((N, 2), dtype=torch.int32, device=dev)
+    obs0, obs1 = envs._obs
+    rew, done, steps_t, real = envs._rew, envs._done, envs._steps, envs._real
+    act_seed = 1000 + rank
+
+    def one_step(t, ev=None):
+        _native.check(lib.crl_pong_random_actions(P(actions), 2 * N, act_seed, t, sp))
+        _native.check(lib.crl_pong_step_state(h, P(actions), P(rew), P(done), P(steps_t), P(real), sp))
+        if ev is not None:
+            ev[0].record(stream)
+        _native.check(lib.crl_pong_render_obs(h, P(obs0), P(obs1), sp))
+        if ev is not None:
+            ev[1].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    t = 0
+    for _ in range(max(3, a.warmup)):
+        one_step(t)
+        t += 1
+    # ---- timed region: device-resident inputs, CUDA events on the launching stream ----
+    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = _native.launch_count()
+    e0.record(stream)
+    for k in range(a.steps):
+        one_step(t, kern_ev[k])
+        t += 1
+    e1.record(stream)
+    barrier()
+    launches = _native.launch_count() - l0
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    raster_ms = sum(x.elapsed_time(y) for x, y in kern_ev) / a.steps
+    episodes = None
+
+    # ---- e2e: through the host-buffer C-ABI call (pinned host memory, copies inside the timed region) ----
+    K2 = max(10, min(a.steps, 200))
+    rng = np.random.default_rng(1000 + rank)
+    h_act = torch.from_numpy(rng.integers(0, 3, (N, 2)).astype(np.int32)).pin_memory()
+    h_rew = torch.zeros((N, 2), dtype=torch.float32).pin_memory()
+    h_done = torch.zeros((N,), dtype=torch.uint8).pin_memory()
+    h_steps = torch.zeros((N,), dtype=torch.int32).pin_memory()
+    h_real = torch.zeros((N, 2), dtype=torch.float32).pin_memory()
+
+    def host_step():
+        _native.check(lib.crl_pong_step_host(h, P(h_act), P(obs0), P(obs1), None, None, P(h_rew), P(h_done),
+                                             P(h_steps), P(h_real), sp))
+    for _ in range(3):
+        host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K2):
+        host_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = h_act.numel() * 4
+    d2h = h_rew.numel() * 4 + h_done.numel() + h_steps.numel() * 4 + h_real.numel() * 4
+
+    # ---- optional: the numpy-style call that also brings both observation stacks to the host ----
+    K3 = 3
+    h_o0 = torch.empty(obs0.shape, dtype=torch.uint8).pin_memory()
+    h_o1 = torch.empty(obs1.shape, dtype=torch.uint8).pin_memory()
+    _native.check(lib.crl_pong_step_host(h, P(h_act), P(obs0), P(obs1), P(h_o0), P(h_o1), P(h_rew), P(h_done),
+                                         P(h_steps), P(h_real), sp))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K3):
+        _native.check(lib.crl_pong_step_host(h, P(h_act), P(obs0), P(obs1), P(h_o0), P(h_o1), P(h_rew), P(h_done),
+                                             P(h_steps), P(h_real), sp))
+    barrier()
+    e2e_obs_s = time.perf_counter() - t0
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([ms, raster_ms, e2e_s, e2e_obs_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, raster_ms, e2e_s, e2e_obs_s = [float(x) for x in tt.tolist()]
+    total_envs = N * world
+    value = total_envs * a.steps / (ms / 1e3)
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_ENV_STEP * N / (raster_ms / 1e3) / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 obs / int32+f64 game state / f32 area-resize", "data": "synthetic",
+        "config": {"workload": "cPongDouble-v0, %d envs per GPU x %d GPU(s), frameskip 4, 84x84x4 uint8 obs per agent, "
+                               "device-side random actions (Philox) and serve RNG, auto-reset" % (N, world),
+                   "envs_per_gpu": N, "bytes_per_env_step": BYTES_PER_ENV_STEP,
+                   "l2": "each step writes %.2f GB per GPU (>> 126 MB L2); no flush needed"
+                         % (BYTES_PER_ENV_STEP * N / 1e9)},
+        "roofline": {"bound": "hbm", "kernel": "pong_raster_kernel<16>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "avg_launch_ms": raster_ms, "bytes_per_launch": BYTES_PER_ENV_STEP * N},
+        "e2e": {"value": total_envs * K2 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+                "d2h_bytes_per_step": d2h * world,
+                "note": "crl_pong_step_host: pinned host actions in, rew/done/num_steps/real_reward out; "
+                        "observations stay in HBM (the API returns device tensors)"},
+        "e2e_host_obs": {"value": total_envs * K3 / e2e_obs_s, "unit": UNIT,
+                         "d2h_bytes_per_step": (d2h + 2 * obs0.numel()) * world,
+                         "note": "same call with both observation stacks copied to pinned host memory (PCIe-bound)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if rank == 0 and not a.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = cpu_baseline(a.cpu_sample_envs, a.cpu_sample_steps, host_threads())
+    envs.close()
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    # one "step" here = one vec-step of the bounded sample; K steps timed after W warm-up
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import pong_oracle
+    atlas = np.load(os.path.join(ROOT, "competitive-rl_b200", "data", "scoreboard_atlas.npz"))["strips"]
+    pong_oracle.set_threads(threads)
+    E = a.cpu_sample_envs
+    v = pong_oracle.PongOracleVec("cPongDouble-v0", E, 84, 4, 21, atlas, None, seed=1)
+    v.reset()
+    rng = np.random.default_rng(0)
+    acts = rng.integers(0, 3, (64, E, 2)).astype(np.int32)
+    for t in range(max(3, a.warmup)):
+        v.step(acts[t % 64])
+    steps = a.steps
+    t0 = time.perf_counter()
+    for t in range(steps):
+        v.step(acts[t % 64])
+        if time.perf_counter() - t0 > 150:   # bounded: stop early, report what ran
+            steps = t + 1
+            break
+    dt = time.perf_counter() - t0
+    val = E * steps / dt
+    cb = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+          "sample": "%d envs x %d vec-steps of cPongDouble 84x84x4 (oracle/pong_oracle.c, all host threads)" % (E, steps)}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": max(3, a.warmup), "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8 obs / int32+f64 game state / f32 area-resize", "data": "synthetic",
+        "config": {"workload": "cPongDouble-v0 frameskip 4, 84x84x4 uint8 obs per agent, random actions; CPU sample of "
+                               "%d envs per vec-step on %d host threads" % (E, threads)},
+        "cpu_baseline": cb,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+if __name__ == "__main__":
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -1,0 +1,85 @@
+"""ctypes binding of libcrl_b200.so (include/crl_b200.h).
+
+There is deliberately no fallback: if the CUDA library has not been built or
+cannot be loaded, importing the simulator fails loudly.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcrl_b200.so")
+
+CRL_OK = 0
+ATLAS_SHAPE = (22, 22, 34, 160, 3)
+DEFAULT_ATLAS = os.path.join(_HERE, "data", "scoreboard_atlas.npz")
+
+EXPORTS = [
+    "crl_abi_version", "crl_last_error", "crl_pong_create", "crl_pong_destroy", "crl_pong_load_atlas",
+    "crl_pong_inject_serves", "crl_pong_seed", "crl_pong_reset", "crl_pong_step", "crl_pong_step_state",
+    "crl_pong_render_obs", "crl_pong_render_obs_generic", "crl_pong_terminal_obs", "crl_pong_step_host",
+    "crl_pong_get_state", "crl_pong_set_state", "crl_pong_render_raw", "crl_pong_random_actions",
+    "crl_launch_count", "crl_pong_check",
+]
+
+
+class PongConfig(ctypes.Structure):
+    _fields_ = [
+        ("num_envs", ctypes.c_int32), ("n_agents", ctypes.c_int32), ("resized_dim", ctypes.c_int32),
+        ("frame_stack", ctypes.c_int32), ("max_num_rounds", ctypes.c_int32), ("device", ctypes.c_int32),
+        ("seed", ctypes.c_uint64), ("first_env", ctypes.c_int64),
+    ]
+
+
+class CrlError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the C-ABI library; raises if it is missing (build with build.py / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s not found: the CUDA extension is not built. Run `python competitive-rl_b200/build.py` "
+            "(there is no CPU fallback)." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64
+    L.crl_abi_version.restype = ctypes.c_int
+    L.crl_last_error.restype = ctypes.c_char_p
+    L.crl_launch_count.restype = u64
+    L.crl_pong_create.argtypes = [ctypes.POINTER(PongConfig), ctypes.POINTER(vp)]
+    L.crl_pong_destroy.argtypes = [vp]
+    L.crl_pong_load_atlas.argtypes = [vp, vp, ctypes.c_size_t, vp]
+    L.crl_pong_inject_serves.argtypes = [vp, vp, i32, vp]
+    L.crl_pong_seed.argtypes = [vp, u64]
+    L.crl_pong_reset.argtypes = [vp, vp, vp, vp]
+    L.crl_pong_step.argtypes = [vp] * 9
+    L.crl_pong_step_state.argtypes = [vp] * 7
+    L.crl_pong_render_obs.argtypes = [vp] * 4
+    L.crl_pong_render_obs_generic.argtypes = [vp] * 4
+    L.crl_pong_terminal_obs.argtypes = [vp] * 5
+    L.crl_pong_step_host.argtypes = [vp] * 11
+    L.crl_pong_get_state.argtypes = [vp, vp, vp]
+    L.crl_pong_set_state.argtypes = [vp, vp, vp]
+    L.crl_pong_render_raw.argtypes = [vp, i32, vp, vp, vp]
+    L.crl_pong_random_actions.argtypes = [vp, i32, u64, u64, vp]
+    L.crl_pong_check.argtypes = [vp, vp]
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("crl_last_error", "crl_launch_count"):
+            fn.restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != CRL_OK:
+        raise CrlError("crl error %d: %s" % (rc, load().crl_last_error().decode()))
+
+
+def launch_count():
+    return int(load().crl_launch_count())

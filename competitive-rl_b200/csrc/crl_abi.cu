@@ -1,0 +1,366 @@
+// crl_abi.cu -- C ABI (include/crl_b200.h) over the Pong kernels.  Host-side only:
+// allocation, table setup, launch sequencing.  No CPU fallback exists: every entry
+// point needs a CUDA device.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "../../include/crl_b200.h"
+#include "pong_common.cuh"
+
+using namespace crl;
+
+namespace crl {
+cudaError_t pong_raster_init();
+}
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) return fail(CRL_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));      \
+    } while (0)
+
+#define LAUNCH(expr)     \
+    do {                 \
+        CUDA_TRY(expr);  \
+        g_launches += 1; \
+    } while (0)
+
+struct crl_pong {
+    crl_pong_config cfg;
+    PongDev dev;
+    std::vector<void*> allocs;
+    double* serves_dev = nullptr;
+    uint8_t* atlas_dev = nullptr;
+    uint8_t* text_tab_dev = nullptr;
+    uint8_t* tmpl_dev = nullptr;
+    AreaTabs* tabs_dev = nullptr;
+    int32_t* actions_stage = nullptr;   // device staging for crl_pong_step_host
+    float* rew_stage = nullptr;
+    uint8_t* done_stage = nullptr;
+    int32_t* steps_stage = nullptr;
+    float* real_stage = nullptr;
+    bool atlas_loaded = false;
+    bool was_reset = false;
+};
+
+// OpenCV computeResizeAreaTab: scale and cell in double, alpha stored as float.
+static bool build_axis(int ssize, int dsize, uint8_t* src0, uint8_t* cnt, float (*alpha)[MAX_TAPS], uint8_t* first,
+                       uint8_t* last) {
+    const double scale = (double)ssize / dsize;
+    for (int s = 0; s < ssize; ++s) { first[s] = 255; last[s] = 0; }
+    for (int dx = 0; dx < dsize; ++dx) {
+        const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+        const double cell = fmin(scale, ssize - fsx1);
+        int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+        sx2 = sx2 < ssize - 1 ? sx2 : ssize - 1;
+        sx1 = sx1 < sx2 ? sx1 : sx2;
+        int n = 0, s0 = -1;
+        auto emit = [&](int s, float a) -> bool {
+            if (n == 0) s0 = s;
+            if (n >= MAX_TAPS || s != s0 + n) return false;
+            alpha[dx][n++] = a;
+            if (first[s] == 255) first[s] = (uint8_t)dx;
+            last[s] = (uint8_t)dx;
+            return true;
+        };
+        if (sx1 - fsx1 > 1e-3 && !emit(sx1 - 1, (float)((sx1 - fsx1) / cell))) return false;
+        for (int sx = sx1; sx < sx2; ++sx)
+            if (!emit(sx, (float)(1.0 / cell))) return false;
+        if (fsx2 - sx2 > 1e-3 && !emit(sx2, (float)(fmin(fmin(fsx2 - sx2, 1.0), cell) / cell))) return false;
+        if (n == 0) return false;
+        src0[dx] = (uint8_t)s0;
+        cnt[dx] = (uint8_t)n;
+        for (int k = n; k < MAX_TAPS; ++k) alpha[dx][k] = 0.f;
+    }
+    for (int s = 0; s < ssize; ++s)
+        if (first[s] == 255) return false;   // every source index must feed some destination
+    return true;
+}
+
+static bool build_tabs(int dim, AreaTabs* t) {
+    memset(t, 0, sizeof *t);
+    t->dim = dim;
+    if (!build_axis(SCREEN_W, dim, t->x_src0, t->x_n, t->x_a, t->x_first, t->x_last)) return false;
+    if (!build_axis(SCREEN_H, dim, t->y_src0, t->y_n, t->y_b, t->y_first, t->y_last)) return false;
+    for (int dx = 0; dx < dim; ++dx)
+        for (int k = 0; k < MAX_TAPS; ++k) {
+            volatile float pa = 255.0f * t->x_a[dx][k];   // fl(fl(255) * alpha), single rounding in fp32
+            t->x_pa[dx][k] = pa;
+        }
+    t->text_rows = t->y_last[ARENA_TOP - 1] + 1;
+    return true;
+}
+
+template <typename T>
+static cudaError_t dev_alloc(crl_pong* h, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (e != cudaSuccess) return e;
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return cudaMemset(q, 0, count * sizeof(T) + 16);
+}
+
+extern "C" {
+
+int crl_abi_version(void) { return CRL_ABI_VERSION; }
+const char* crl_last_error(void) { return g_err; }
+uint64_t crl_launch_count(void) { return g_launches.load(); }
+
+int crl_pong_destroy(crl_pong* h) {
+    if (!h) return CRL_OK;
+    cudaSetDevice(h->cfg.device);
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+    return CRL_OK;
+}
+
+int crl_pong_create(const crl_pong_config* cfg, crl_pong** out) {
+    if (!cfg || !out) return fail(CRL_E_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->num_envs <= 0) return fail(CRL_E_INVALID, "num_envs must be positive");
+    if (cfg->n_agents != 1 && cfg->n_agents != 2) return fail(CRL_E_INVALID, "n_agents must be 1 or 2");
+    if (cfg->resized_dim < 8 || cfg->resized_dim > MAX_DIM || cfg->resized_dim % 2)
+        return fail(CRL_E_INVALID, "resized_dim must be even and in [8, %d]", MAX_DIM);
+    if (cfg->frame_stack < 0 || cfg->frame_stack > MAX_STACK)
+        return fail(CRL_E_INVALID, "frame_stack must be in [0, %d]", MAX_STACK);
+    if (cfg->max_num_rounds < 1 || cfg->max_num_rounds > ATLAS_SCORES - 1)
+        return fail(CRL_E_INVALID, "max_num_rounds must be in [1, %d] (scoreboard atlas range)", ATLAS_SCORES - 1);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(CRL_E_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                    cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(CRL_E_INVALID, "device %d out of range", cfg->device);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    AreaTabs tabs;
+    if (!build_tabs(cfg->resized_dim, &tabs))
+        return fail(CRL_E_INVALID, "resized_dim %d needs more than %d taps per pixel", cfg->resized_dim, MAX_TAPS);
+
+    crl_pong* h = new crl_pong();
+    h->cfg = *cfg;
+    PongDev& d = h->dev;
+    memset(&d, 0, sizeof d);
+    const size_t n = (size_t)cfg->num_envs;
+    d.n = cfg->num_envs;
+    d.n_agents = cfg->n_agents;
+    d.dim = cfg->resized_dim;
+    d.c = cfg->frame_stack > 0 ? cfg->frame_stack : 1;
+    d.max_rounds = cfg->max_num_rounds;
+    d.first_env = cfg->first_env;
+    d.seed = cfg->seed;
+    const int dd = d.dim * d.dim;
+    d.text_stride = ((tabs.text_rows * d.dim + 15) / 16) * 16;
+    if (d.text_stride > ((dd + 15) / 16) * 16) d.text_stride = ((dd + 15) / 16) * 16;
+#define ALLOC(ptr, count)                                                        \
+    do {                                                                         \
+        cudaError_t _e = dev_alloc(h, &(ptr), (count));                          \
+        if (_e != cudaSuccess) {                                                 \
+            crl_pong_destroy(h);                                                 \
+            return fail(CRL_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(_e));   \
+        }                                                                        \
+    } while (0)
+    ALLOC(d.ball, n); ALLOC(d.vx, n); ALLOC(d.vy, n); ALLOC(d.bats, n); ALLOC(d.score, n);
+    ALLOC(d.num_steps, n); ALLOC(d.clip_steps, n); ALLOC(d.serve_count, n);
+    ALLOC(d.skipbuf, 2 * n); ALLOC(d.hist, d.c * n); ALLOC(d.term_hist, d.c * n);
+    ALLOC(d.serve_overrun, 1);
+    ALLOC(h->tabs_dev, 1);
+    ALLOC(h->atlas_dev, (size_t)CRL_PONG_ATLAS_BYTES);
+    ALLOC(h->text_tab_dev, (size_t)ATLAS_SCORES * ATLAS_SCORES * 3 * 2 * d.text_stride);
+    ALLOC(h->tmpl_dev, (size_t)((dd + 15) / 16) * 16);
+    ALLOC(h->actions_stage, 2 * n); ALLOC(h->rew_stage, 2 * n); ALLOC(h->done_stage, n);
+    ALLOC(h->steps_stage, n); ALLOC(h->real_stage, 2 * n);
+#undef ALLOC
+    d.tabs = h->tabs_dev;
+    d.atlas = h->atlas_dev;
+    d.text_tab = h->text_tab_dev;
+    d.tmpl = h->tmpl_dev;
+    e = cudaMemcpy(h->tabs_dev, &tabs, sizeof tabs, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = pong_raster_init();
+    if (e == cudaSuccess) e = launch_pong_construct(d, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        crl_pong_destroy(h);
+        return fail(CRL_E_CUDA, "construct: %s", cudaGetErrorString(e));
+    }
+    g_launches += 1;
+    *out = h;
+    return CRL_OK;
+}
+
+#define CHECK_HANDLE(h)                                        \
+    do {                                                       \
+        if (!(h)) return fail(CRL_E_INVALID, "null handle");   \
+        CUDA_TRY(cudaSetDevice((h)->cfg.device));              \
+    } while (0)
+
+int crl_pong_load_atlas(crl_pong* h, const uint8_t* strips_host, size_t bytes, void* stream) {
+    CHECK_HANDLE(h);
+    if (!strips_host || bytes != (size_t)CRL_PONG_ATLAS_BYTES)
+        return fail(CRL_E_INVALID, "atlas must be %d bytes ([22][22][34][160][3] uint8)", CRL_PONG_ATLAS_BYTES);
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(h->atlas_dev, strips_host, bytes, cudaMemcpyHostToDevice, s));
+    LAUNCH(launch_pong_build_tables(h->dev, h->text_tab_dev, h->tmpl_dev, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    h->atlas_loaded = true;
+    return CRL_OK;
+}
+
+int crl_pong_inject_serves(crl_pong* h, const double* serves_host, int32_t k, void* stream) {
+    CHECK_HANDLE(h);
+    if (!serves_host || k < 3) return fail(CRL_E_INVALID, "serve table needs k >= 3 entries per env");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* buf = nullptr;
+    CUDA_TRY(dev_alloc(h, &buf, (size_t)h->dev.n * k * 2));
+    CUDA_TRY(cudaMemcpyAsync(buf, serves_host, (size_t)h->dev.n * k * 2 * sizeof(double), cudaMemcpyHostToDevice, s));
+    h->serves_dev = buf;
+    h->dev.serves = buf;
+    h->dev.serves_k = k;
+    LAUNCH(launch_pong_construct(h->dev, s));   // constructors re-run: serves 0 and 1 from the table
+    CUDA_TRY(cudaStreamSynchronize(s));
+    h->was_reset = false;
+    return CRL_OK;
+}
+
+int crl_pong_seed(crl_pong* h, uint64_t seed) {
+    CHECK_HANDLE(h);
+    h->dev.seed = seed;
+    return CRL_OK;
+}
+
+static int need_ready(crl_pong* h, bool need_reset) {
+    if (!h->atlas_loaded) return fail(CRL_E_STATE, "crl_pong_load_atlas must be called before reset/step");
+    if (need_reset && !h->was_reset) return fail(CRL_E_STATE, "reset must be called before step");
+    return CRL_OK;
+}
+
+int crl_pong_render_obs(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (int r = need_ready(h, true)) return r;
+    if (!obs0_dev || (h->dev.n_agents == 2 && !obs1_dev)) return fail(CRL_E_INVALID, "null observation buffer");
+    if (h->dev.n_agents == 1) obs1_dev = obs0_dev;
+    LAUNCH(launch_pong_raster(h->dev, h->dev.hist, obs0_dev, obs1_dev, (cudaStream_t)stream));
+    return CRL_OK;
+}
+
+int crl_pong_render_obs_generic(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (int r = need_ready(h, true)) return r;
+    if (!obs0_dev || (h->dev.n_agents == 2 && !obs1_dev)) return fail(CRL_E_INVALID, "null observation buffer");
+    LAUNCH(launch_pong_raster_generic(h->dev, h->dev.hist, nullptr, obs0_dev, obs1_dev, (cudaStream_t)stream));
+    return CRL_OK;
+}
+
+int crl_pong_reset(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (int r = need_ready(h, false)) return r;
+    LAUNCH(launch_pong_reset(h->dev, (cudaStream_t)stream));
+    h->was_reset = true;
+    return crl_pong_render_obs(h, obs0_dev, obs1_dev, stream);
+}
+
+int crl_pong_step_state(crl_pong* h, const int32_t* actions_dev, float* rew_dev, uint8_t* done_dev,
+                        int32_t* num_steps_dev, float* real_reward_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (int r = need_ready(h, true)) return r;
+    if (!actions_dev || !rew_dev || !done_dev || !num_steps_dev || !real_reward_dev)
+        return fail(CRL_E_INVALID, "null step buffer");
+    LAUNCH(launch_pong_step(h->dev, actions_dev, rew_dev, done_dev, num_steps_dev, real_reward_dev,
+                            (cudaStream_t)stream));
+    return CRL_OK;
+}
+
+int crl_pong_step(crl_pong* h, const int32_t* actions_dev, uint8_t* obs0_dev, uint8_t* obs1_dev, float* rew_dev,
+                  uint8_t* done_dev, int32_t* num_steps_dev, float* real_reward_dev, void* stream) {
+    if (int r = crl_pong_step_state(h, actions_dev, rew_dev, done_dev, num_steps_dev, real_reward_dev, stream))
+        return r;
+    return crl_pong_render_obs(h, obs0_dev, obs1_dev, stream);
+}
+
+int crl_pong_terminal_obs(crl_pong* h, const uint8_t* done_dev, uint8_t* term0_dev, uint8_t* term1_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (int r = need_ready(h, true)) return r;
+    if (!done_dev || !term0_dev || (h->dev.n_agents == 2 && !term1_dev)) return fail(CRL_E_INVALID, "null buffer");
+    LAUNCH(launch_pong_raster_generic(h->dev, h->dev.term_hist, done_dev, term0_dev, term1_dev, (cudaStream_t)stream));
+    return CRL_OK;
+}
+
+int crl_pong_step_host(crl_pong* h, const int32_t* actions_host, uint8_t* obs0_dev, uint8_t* obs1_dev,
+                       uint8_t* obs0_host, uint8_t* obs1_host, float* rew_host, uint8_t* done_host,
+                       int32_t* num_steps_host, float* real_reward_host, void* stream) {
+    CHECK_HANDLE(h);
+    if (!actions_host || !rew_host || !done_host) return fail(CRL_E_INVALID, "null host buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)h->dev.n;
+    const size_t aw = h->dev.n_agents == 2 ? 2 : 1;
+    CUDA_TRY(cudaMemcpyAsync(h->actions_stage, actions_host, n * aw * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (int r = crl_pong_step(h, h->actions_stage, obs0_dev, obs1_dev, h->rew_stage, h->done_stage, h->steps_stage,
+                              h->real_stage, stream))
+        return r;
+    CUDA_TRY(cudaMemcpyAsync(rew_host, h->rew_stage, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(done_host, h->done_stage, n, cudaMemcpyDeviceToHost, s));
+    if (num_steps_host)
+        CUDA_TRY(cudaMemcpyAsync(num_steps_host, h->steps_stage, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (real_reward_host)
+        CUDA_TRY(cudaMemcpyAsync(real_reward_host, h->real_stage, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    const size_t ob = n * h->dev.c * h->dev.dim * h->dev.dim;
+    if (obs0_host) CUDA_TRY(cudaMemcpyAsync(obs0_host, obs0_dev, ob, cudaMemcpyDeviceToHost, s));
+    if (obs1_host && h->dev.n_agents == 2) CUDA_TRY(cudaMemcpyAsync(obs1_host, obs1_dev, ob, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return CRL_OK;
+}
+
+int crl_pong_get_state(crl_pong* h, double* state_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (!state_dev) return fail(CRL_E_INVALID, "null buffer");
+    LAUNCH(launch_pong_get_state(h->dev, state_dev, (cudaStream_t)stream));
+    return CRL_OK;
+}
+
+int crl_pong_set_state(crl_pong* h, const double* state_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (!state_dev) return fail(CRL_E_INVALID, "null buffer");
+    LAUNCH(launch_pong_set_state(h->dev, state_dev, (cudaStream_t)stream));
+    return CRL_OK;
+}
+
+int crl_pong_render_raw(crl_pong* h, int32_t env, uint8_t* rgb0_dev, uint8_t* rgb1_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (int r = need_ready(h, false)) return r;
+    if (env < 0 || env >= h->dev.n || !rgb0_dev) return fail(CRL_E_INVALID, "bad env index or null buffer");
+    LAUNCH(launch_pong_raw_frame(h->dev, env, rgb0_dev, rgb1_dev, (cudaStream_t)stream));
+    return CRL_OK;
+}
+
+int crl_pong_random_actions(int32_t* actions_dev, int32_t n_values, uint64_t seed, uint64_t step, void* stream) {
+    if (!actions_dev || n_values <= 0) return fail(CRL_E_INVALID, "bad arguments");
+    LAUNCH(launch_pong_random_actions(actions_dev, n_values, seed, step, (cudaStream_t)stream));
+    return CRL_OK;
+}
+
+int crl_pong_check(crl_pong* h, void* stream) {
+    CHECK_HANDLE(h);
+    int32_t flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, h->dev.serve_overrun, sizeof flag, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    if (flag) return fail(CRL_E_SERVES, "injected serve table exhausted");
+    return CRL_OK;
+}
+
+}  // extern "C"

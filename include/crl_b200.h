@@ -1,0 +1,141 @@
+/*
+ * crl_b200.h -- C ABI of the B200-native batched simulator for competitive-rl's
+ * vectorised env-stepping path.
+ *
+ * The reference (ucla-rlcourse/competitive-rl) is pure Python and has no FFI; the
+ * boundary it exposes for this path is the vec-env protocol returned by
+ *   make_envs(env_id, seed, log_dir, num_envs, asynchronous, resized_dim, frame_stack,
+ *             action_repeat)                       competitive_rl/make_envs.py:67-118
+ *   VecEnv.reset / step_async / step_wait / seed   competitive_rl/utils/base_vec_env.py:63-252
+ * implemented by DummyVecEnv (utils/dummy_vec_env.py:27-75) and SubprocVecEnv
+ * (utils/subproc_vec_env.py:81-129).  Each entry point below names the reference
+ * interface it replaces.  INTEGRATION.md shows the ctypes binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in the signatures
+ *     (`stream` is a cudaStream_t passed as void*, NULL = legacy default stream);
+ *   - every call returns 0 on success or a negative CRL_E_* code; crl_last_error()
+ *     returns a thread-local message; no exceptions cross the ABI;
+ *   - calls are stream-ordered and never synchronise the host unless stated;
+ *   - `*_dev` pointers are device memory owned by the CALLER (e.g. torch tensors);
+ *     `*_host` pointers are host memory; a handle is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef CRL_B200_H
+#define CRL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRL_OK 0
+#define CRL_E_INVALID (-1)   /* bad argument / unsupported configuration */
+#define CRL_E_CUDA (-2)      /* a CUDA runtime call failed (message has the detail) */
+#define CRL_E_STATE (-3)     /* call order violated (e.g. step before atlas/reset) */
+#define CRL_E_SERVES (-4)    /* injected serve table exhausted */
+
+#define CRL_ABI_VERSION 1
+#define CRL_PONG_ATLAS_BYTES (22 * 22 * 34 * 160 * 3)
+#define CRL_PONG_STATE_DOUBLES 10
+
+typedef struct crl_pong crl_pong; /* opaque handle: one shard of envs on one GPU */
+
+typedef struct crl_pong_config {
+    int32_t num_envs;       /* envs in this shard (make_envs num_envs) */
+    int32_t n_agents;       /* 1 = "cPong-v0" (built-in right bat), 2 = "cPongDouble-v0" */
+    int32_t resized_dim;    /* make_envs resized_dim: 84 or 42 */
+    int32_t frame_stack;    /* make_envs frame_stack; 0 = None (one channel) */
+    int32_t max_num_rounds; /* gym registry kwarg, pong/register.py:13-22 (21) */
+    int32_t device;         /* CUDA device ordinal */
+    uint64_t seed;          /* serve RNG seed (Philox); ignored once serves are injected */
+    int64_t first_env;      /* global index of env 0 of this shard: RNG streams are keyed by
+                               global env index, so results do not depend on the sharding */
+} crl_pong_config;
+
+int crl_abi_version(void);
+const char* crl_last_error(void);
+
+/* Construct the shard == running the num_envs thunks of make_env_a2c_atari
+ * (utils/atari_wrappers.py:40-53): every PongGame constructor consumes two serves
+ * (pong/base_pong_env.py:211, 312). */
+int crl_pong_create(const crl_pong_config* cfg, crl_pong** out);
+int crl_pong_destroy(crl_pong* h);
+
+/* Scoreboard atlas: rows 0..33 of the 210x160x3 frame for every score pair,
+ * uint8 [22][22][34][160][3] (what Scoreboard.draw, pong/base_pong_env.py:474-487,
+ * leaves on the surface).  Builds the preprocessed-scoreboard tables on the device.
+ * Must be called once before reset/step.  Synchronises the stream. */
+int crl_pong_load_atlas(crl_pong* h, const uint8_t* strips_host, size_t bytes, void* stream);
+
+/* Validation mode: replace the serve RNG by a table, serves_host[num_envs][k][2] =
+ * (vx, vy) of the k-th serve each env consumes since construction (the reference
+ * draws them from stdlib `random`, pong/base_pong_env.py:314-320).  Re-runs the
+ * constructors so serves 0 and 1 come from the table.  Synchronises. */
+int crl_pong_inject_serves(crl_pong* h, const double* serves_host, int32_t k, void* stream);
+
+/* VecEnv.seed(seed) (base_vec_env.py:163-176): the reference Pong envs ignore seeds
+ * (pong/base_pong_env.py:38-39); here it re-keys the serve RNG for FUTURE serves. */
+int crl_pong_seed(crl_pong* h, uint64_t seed);
+
+/* VecEnv.reset(): obs{0,1}_dev receive uint8 [num_envs][C][dim][dim] per agent
+ * (obs1_dev is ignored for n_agents == 1). */
+int crl_pong_reset(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_dev, void* stream);
+
+/* VecEnv.step(actions) == step_async + step_wait with auto-reset on done.
+ *   actions_dev      int32 [num_envs][2] (Double; 0/1/2 or 999 = built-in rule-based bat,
+ *                    pong/base_pong_env.py:116-134) or int32 [num_envs] (single)
+ *   rew_dev          float32 [num_envs][2]  np.sign of the frameskip reward sum (ClipRewardEnv)
+ *   done_dev         uint8   [num_envs]
+ *   num_steps_dev    int32   [num_envs]     info["num_steps"]
+ *   real_reward_dev  float32 [num_envs][2]  info["real_reward"]
+ * Observations of envs that finished are already those of the auto-reset. */
+int crl_pong_step(crl_pong* h, const int32_t* actions_dev, uint8_t* obs0_dev, uint8_t* obs1_dev, float* rew_dev,
+                  uint8_t* done_dev, int32_t* num_steps_dev, float* real_reward_dev, void* stream);
+
+/* The two halves of crl_pong_step, for callers that want to overlap or time them:
+ * game core only (one thread per env), then the fused rasteriser+preprocessing. */
+int crl_pong_step_state(crl_pong* h, const int32_t* actions_dev, float* rew_dev, uint8_t* done_dev,
+                        int32_t* num_steps_dev, float* real_reward_dev, void* stream);
+int crl_pong_render_obs(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_dev, void* stream);
+/* same output through the one-thread-per-pixel reference rasteriser (cross-check) */
+int crl_pong_render_obs_generic(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_dev, void* stream);
+
+/* info["terminal_observation"] of the LAST step: writes, for every env whose
+ * done_dev[i] != 0, the stacked observation the episode ended with into
+ * term{0,1}_dev[i] (same layout as obs); other envs' slots are left untouched. */
+int crl_pong_terminal_obs(crl_pong* h, const uint8_t* done_dev, uint8_t* term0_dev, uint8_t* term1_dev, void* stream);
+
+/* Host-buffer form of step (what a numpy caller of the reference's VecEnv.step sees):
+ * copies actions host->device, steps, copies rew/done/num_steps/real_reward back and,
+ * when obs*_host are non-NULL, the observations too.  Synchronises the stream.
+ * Host buffers should be pinned for full PCIe bandwidth.  obs*_dev are still required
+ * (device staging owned by the caller). */
+int crl_pong_step_host(crl_pong* h, const int32_t* actions_host, uint8_t* obs0_dev, uint8_t* obs1_dev,
+                       uint8_t* obs0_host, uint8_t* obs1_host, float* rew_host, uint8_t* done_host,
+                       int32_t* num_steps_host, float* real_reward_host, void* stream);
+
+/* Game state, float64 [num_envs][10]: ball_x, ball_y, vx, vy, left_y, right_y,
+ * score_left, score_right, num_rounds, num_steps (PongGame fields). */
+int crl_pong_get_state(crl_pong* h, double* state_dev, void* stream);
+int crl_pong_set_state(crl_pong* h, const double* state_dev, void* stream);
+
+/* VecEnv.get_images()/render (base_vec_env.py:189-216): raw 210x160x3 uint8 frame of
+ * env `env` as agent 0 sees it, and (rgb1_dev may be NULL) agent 1's mirrored copy. */
+int crl_pong_render_raw(crl_pong* h, int32_t env, uint8_t* rgb0_dev, uint8_t* rgb1_dev, void* stream);
+
+/* Synthetic rollout driver: uniform actions in {0,1,2}, Philox keyed by (seed, step). */
+int crl_pong_random_actions(int32_t* actions_dev, int32_t n_values, uint64_t seed, uint64_t step, void* stream);
+
+/* Number of kernel launches this library has issued from this process (bench.py's
+ * gpu_launches) and a checked flag for serve-table overrun (synchronises). */
+uint64_t crl_launch_count(void);
+int crl_pong_check(crl_pong* h, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRL_B200_H */
