@@ -14,10 +14,6 @@
 
 using namespace crl;
 
-namespace crl {
-cudaError_t pong_raster_init();
-}
-
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 
@@ -50,6 +46,8 @@ struct crl_pong {
     uint8_t* text_tab_dev = nullptr;
     uint8_t* tmpl_dev = nullptr;
     AreaTabs* tabs_dev = nullptr;
+    AreaTabs tabs_host;
+    uint8_t* fast_tabs_dev = nullptr;
     int32_t* actions_stage = nullptr;   // device staging for crl_pong_step_host
     float* rew_stage = nullptr;
     uint8_t* done_stage = nullptr;
@@ -186,11 +184,24 @@ int crl_pong_create(const crl_pong_config* cfg, crl_pong** out) {
     ALLOC(h->tmpl_dev, (size_t)((dd + 15) / 16) * 16);
     ALLOC(h->actions_stage, 2 * n); ALLOC(h->rew_stage, 2 * n); ALLOC(h->done_stage, n);
     ALLOC(h->steps_stage, n); ALLOC(h->real_stage, 2 * n);
-#undef ALLOC
+    h->tabs_host = tabs;
+    const size_t ftb = pong_fast_supported(tabs) ? pong_fast_tabs_bytes(d.dim) : 0;
+    if (ftb) {
+        ALLOC(h->fast_tabs_dev, ftb);
+        std::vector<uint8_t> img(ftb);
+        pong_fast_tabs_fill(tabs, img.data());
+        cudaError_t _e = cudaMemcpy(h->fast_tabs_dev, img.data(), ftb, cudaMemcpyHostToDevice);
+        if (_e != cudaSuccess) {
+            crl_pong_destroy(h);
+            return fail(CRL_E_CUDA, "fast tabs upload: %s", cudaGetErrorString(_e));
+        }
+        d.fast_tabs = h->fast_tabs_dev;
+    }
     d.tabs = h->tabs_dev;
     d.atlas = h->atlas_dev;
     d.text_tab = h->text_tab_dev;
     d.tmpl = h->tmpl_dev;
+#undef ALLOC
     e = cudaMemcpy(h->tabs_dev, &tabs, sizeof tabs, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = pong_raster_init();
     if (e == cudaSuccess) e = launch_pong_construct(d, 0);
@@ -215,6 +226,21 @@ int crl_pong_load_atlas(crl_pong* h, const uint8_t* strips_host, size_t bytes, v
     if (!strips_host || bytes != (size_t)CRL_PONG_ATLAS_BYTES)
         return fail(CRL_E_INVALID, "atlas must be %d bytes ([22][22][34][160][3] uint8)", CRL_PONG_ATLAS_BYTES);
     cudaStream_t s = (cudaStream_t)stream;
+    // The hot kernel treats source rows above the arena that share a destination row with arena
+    // rows as pure white (true for any scoreboard that stays clear of the arena edge); otherwise
+    // every frame takes the exact one-thread-per-pixel rasteriser.
+    {
+        const AreaTabs& t = h->tabs_host;
+        const int first = t.y_src0[t.text_rows - 1];
+        bool white = true;
+        for (int pair = 0; pair < ATLAS_SCORES * ATLAS_SCORES && white; ++pair)
+            for (int r = first; r < ATLAS_ROWS && white; ++r) {
+                const uint8_t* row = strips_host + ((size_t)pair * ATLAS_ROWS + r) * SCREEN_W * 3;
+                for (int i = 0; i < SCREEN_W * 3; ++i)
+                    if (row[i] != 255) { white = false; break; }
+            }
+        h->dev.fast_ok = white ? 1 : 0;
+    }
     CUDA_TRY(cudaMemcpyAsync(h->atlas_dev, strips_host, bytes, cudaMemcpyHostToDevice, s));
     LAUNCH(launch_pong_build_tables(h->dev, h->text_tab_dev, h->tmpl_dev, s));
     CUDA_TRY(cudaStreamSynchronize(s));

@@ -99,6 +99,8 @@ struct PongDev {
     const uint8_t* text_tab;   // [22*22*3][2 agents][text_stride] preprocessed rows above the arena
     const uint8_t* tmpl;       // [dim*dim (+pad)] rect-free frame (score 0:0)
     int text_stride;           // bytes per text_tab entry (multiple of 16)
+    const void* fast_tabs;     // FastTabs<dim> image for the hot kernel (nullptr: dim not specialised)
+    int fast_ok;               // atlas rows sharing a dst row with the arena are pure white
 };
 
 // ---- Philox4x32-10 (counter-based; streams keyed by seed and global env index) ----
@@ -131,6 +133,10 @@ cudaError_t launch_pong_build_tables(const PongDev& p, uint8_t* text_tab, uint8_
 cudaError_t launch_pong_raster(const PongDev& p, const FrameSpec* hist, uint8_t* obs0, uint8_t* obs1, cudaStream_t s);
 cudaError_t launch_pong_raster_generic(const PongDev& p, const FrameSpec* hist, const uint8_t* only_done,
                                        uint8_t* obs0, uint8_t* obs1, cudaStream_t s);
+cudaError_t pong_raster_init();
+size_t pong_fast_tabs_bytes(int dim);
+bool pong_fast_supported(const AreaTabs& a);
+void pong_fast_tabs_fill(const AreaTabs& a, void* host_buf);
 cudaError_t launch_pong_raw_frame(const PongDev& p, int env, uint8_t* rgb0, uint8_t* rgb1, cudaStream_t s);
 
 }  // namespace crl
