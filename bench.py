@@ -32,8 +32,8 @@ UNIT = "env-steps/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--envs-per-gpu", type=int, default=65536)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cpu-sample-envs", type=int, default=256)
@@ -95,37 +95,60 @@ def host_threads():
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler(object):
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi -lms loop running across the timed region; samples are filtered to the
+    [mark_start, mark_stop] wall-clock window (B200_PROFILING.md clocks line)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index):
-        self.index, self.samples, self._stop = index, [], threading.Event()
-        self._t = threading.Thread(target=self._run, daemon=True)
-
-    def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                f = [x.strip() for x in out.stdout.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
-            except Exception:  # noqa: BLE001
-                pass
-            self._stop.wait(0.2)
+        self.index, self.proc, self.t0, self.t1 = index, None, None, None
 
     def start(self):
-        self._t.start()
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
 
     def stop(self):
-        self._stop.set()
-        self._t.join(timeout=6)
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        import datetime
+        lines = []
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+                lines = out.strip().splitlines()
+            except Exception:  # noqa: BLE001
+                self.proc.kill()
+        inside, every = [], []
+        for ln in lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7 or not f[1].isdigit():
+                continue
+            every.append(f)
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                continue
+            if self.t0 is not None and self.t0 - 0.05 <= ts <= self.t1 + 0.05:
+                inside.append(f)
+        use = inside if inside else every
+        sm = sorted(int(s[1]) for s in use)
+        mx = [int(s[2]) for s in use if s[2].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for s in use for n, v in zip(names, s[3:7]) if v.lower().startswith("active")})
+        pw = [float(s[7]) for s in use if len(s) > 7 and s[7].replace(".", "", 1).isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(use), "samples_in_timed_region": len(inside),
+                "power_w_max": max(pw) if pw else None}
 
 
 # --------------------------------------------------------------------------- our arm
@@ -176,6 +199,8 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     t = 0
     for _ in range(max(3, a.warmup)):
         one_step(t)
@@ -183,9 +208,8 @@ def run_ours(a):
     # ---- timed region: device-resident inputs, CUDA events on the launching stream ----
     kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark_start()
     l0 = _native.launch_count()
     e0.record(stream)
     for k in range(a.steps):
@@ -193,6 +217,7 @@ def run_ours(a):
         t += 1
     e1.record(stream)
     barrier()
+    sampler.mark_stop()
     launches = _native.launch_count() - l0
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
@@ -254,7 +279,7 @@ def run_ours(a):
                    "envs_per_gpu": N, "bytes_per_env_step": BYTES_PER_ENV_STEP,
                    "l2": "each step writes %.2f GB per GPU (>> 126 MB L2); no flush needed"
                          % (BYTES_PER_ENV_STEP * N / 1e9)},
-        "roofline": {"bound": "hbm", "kernel": "pong_raster_kernel<16>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "pong_raster_fast_kernel<84>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                      "avg_launch_ms": raster_ms, "bytes_per_launch": BYTES_PER_ENV_STEP * N},
         "e2e": {"value": total_envs * K2 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,

@@ -18,7 +18,7 @@ EXPORTS = [
     "crl_pong_inject_serves", "crl_pong_seed", "crl_pong_reset", "crl_pong_step", "crl_pong_step_state",
     "crl_pong_render_obs", "crl_pong_render_obs_generic", "crl_pong_terminal_obs", "crl_pong_step_host",
     "crl_pong_get_state", "crl_pong_set_state", "crl_pong_render_raw", "crl_pong_random_actions",
-    "crl_launch_count", "crl_pong_check",
+    "crl_launch_count", "crl_pong_check", "crl_pong_get_stats",
 ]
 
 
@@ -68,6 +68,7 @@ def load():
     L.crl_pong_render_raw.argtypes = [vp, i32, vp, vp, vp]
     L.crl_pong_random_actions.argtypes = [vp, i32, u64, u64, vp]
     L.crl_pong_check.argtypes = [vp, vp]
+    L.crl_pong_get_stats.argtypes = [vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("crl_last_error", "crl_launch_count"):

@@ -178,6 +178,7 @@ int crl_pong_create(const crl_pong_config* cfg, crl_pong** out) {
     ALLOC(d.num_steps, n); ALLOC(d.clip_steps, n); ALLOC(d.serve_count, n);
     ALLOC(d.skipbuf, 2 * n); ALLOC(d.hist, d.c * n); ALLOC(d.term_hist, d.c * n);
     ALLOC(d.serve_overrun, 1);
+    ALLOC(d.stats, 8);
     ALLOC(h->tabs_dev, 1);
     ALLOC(h->atlas_dev, (size_t)CRL_PONG_ATLAS_BYTES);
     ALLOC(h->text_tab_dev, (size_t)ATLAS_SCORES * ATLAS_SCORES * 3 * 2 * d.text_stride);
@@ -377,6 +378,16 @@ int crl_pong_render_raw(crl_pong* h, int32_t env, uint8_t* rgb0_dev, uint8_t* rg
 int crl_pong_random_actions(int32_t* actions_dev, int32_t n_values, uint64_t seed, uint64_t step, void* stream) {
     if (!actions_dev || n_values <= 0) return fail(CRL_E_INVALID, "bad arguments");
     LAUNCH(launch_pong_random_actions(actions_dev, n_values, seed, step, (cudaStream_t)stream));
+    return CRL_OK;
+}
+
+int crl_pong_get_stats(crl_pong* h, uint64_t* stats_host, void* stream) {
+    CHECK_HANDLE(h);
+    if (!stats_host) return fail(CRL_E_INVALID, "null buffer");
+    unsigned long long raw[8];
+    CUDA_TRY(cudaMemcpyAsync(raw, h->dev.stats, sizeof raw, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int i = 0; i < 8; ++i) stats_host[i] = raw[i];
     return CRL_OK;
 }
 

@@ -93,6 +93,9 @@ struct PongDev {
     const double* serves;   // [n][K][2] (vx, vy) or nullptr
     int serves_k;
     int32_t* serve_overrun; // device flag
+    // episode statistics, accumulated on done: [0] episodes, [1] sum of episode lengths (env-steps),
+    // [2] left wins, [3] right wins, [4] draws, [5] sum of (score_left - score_right) + 64*episodes
+    unsigned long long* stats;
     // --- renderer data ---
     const AreaTabs* tabs;
     const uint8_t* atlas;      // [22][22][34][160][3] RGB

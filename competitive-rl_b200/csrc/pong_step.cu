@@ -277,6 +277,10 @@ pong_step_kernel(PongDev p, const int32_t* __restrict__ actions, float* __restri
         make_float2((float)((total0 > 0) - (total0 < 0)), (float)((total1 > 0) - (total1 < 0)));
     done_out[e] = done ? 1 : 0;
     if (done) {   // vec-env auto-reset: keep the terminal deque, then env.reset()
+        atomicAdd(&p.stats[0], 1ull);
+        atomicAdd(&p.stats[1], (unsigned long long)steps);
+        atomicAdd(&p.stats[g.score_left > g.score_right ? 2 : (g.score_left < g.score_right ? 3 : 4)], 1ull);
+        atomicAdd(&p.stats[5], (unsigned long long)(g.score_left - g.score_right + 64));
 #pragma unroll
         for (int k = 0; k < MAX_STACK; ++k)
             if (k + 1 < p.c) p.term_hist[(size_t)k * p.n + e] = h[k];

@@ -407,6 +407,13 @@ class CudaPongVecEnv(VecEnv):
         """Raise if a device-side error flag (serve table overrun) is set. Synchronises."""
         _native.check(self._lib.crl_pong_check(self._h, self._stream()))
 
+    def episode_stats(self):
+        """Device-accumulated episode statistics of this shard as a dict (synchronises)."""
+        raw = (ctypes.c_uint64 * 8)()
+        _native.check(self._lib.crl_pong_get_stats(self._h, raw, self._stream()))
+        from .distributed import stats_from_raw
+        return stats_from_raw(list(raw))
+
     def render_obs_generic(self):
         """Observations through the one-thread-per-pixel reference rasteriser (cross-check)."""
         out = [torch.empty_like(o) for o in self._obs]

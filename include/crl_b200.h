@@ -130,6 +130,14 @@ int crl_pong_render_raw(crl_pong* h, int32_t env, uint8_t* rgb0_dev, uint8_t* rg
 /* Synthetic rollout driver: uniform actions in {0,1,2}, Philox keyed by (seed, step). */
 int crl_pong_random_actions(int32_t* actions_dev, int32_t n_values, uint64_t seed, uint64_t step, void* stream);
 
+/* Episode statistics accumulated on the device since construction (for the optional
+ * end-of-run gather across GPUs; the reference tallies these on the host in
+ * pong/evaluate.py:53-88 and utils/utils.py:23-60).  stats_host[8] (uint64):
+ * [0] finished episodes, [1] sum of episode lengths in env-steps, [2] episodes won by the
+ * left agent, [3] by the right agent, [4] draws, [5] sum over episodes of
+ * (score_left - score_right + 64), [6..7] reserved.  Synchronises the stream. */
+int crl_pong_get_stats(crl_pong* h, uint64_t* stats_host, void* stream);
+
 /* Number of kernel launches this library has issued from this process (bench.py's
  * gpu_launches) and a checked flag for serve-table overrun (synchronises). */
 uint64_t crl_launch_count(void);
