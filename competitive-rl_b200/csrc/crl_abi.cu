@@ -186,17 +186,20 @@ int crl_pong_create(const crl_pong_config* cfg, crl_pong** out) {
     ALLOC(h->actions_stage, 2 * n); ALLOC(h->rew_stage, 2 * n); ALLOC(h->done_stage, n);
     ALLOC(h->steps_stage, n); ALLOC(h->real_stage, 2 * n);
     h->tabs_host = tabs;
-    const size_t ftb = pong_fast_supported(tabs) ? pong_fast_tabs_bytes(d.dim) : 0;
+    const size_t ftb = pong_fast_tabs_bytes(d.dim);
     if (ftb) {
-        ALLOC(h->fast_tabs_dev, ftb);
         std::vector<uint8_t> img(ftb);
-        pong_fast_tabs_fill(tabs, img.data());
-        cudaError_t _e = cudaMemcpy(h->fast_tabs_dev, img.data(), ftb, cudaMemcpyHostToDevice);
-        if (_e != cudaSuccess) {
-            crl_pong_destroy(h);
-            return fail(CRL_E_CUDA, "fast tabs upload: %s", cudaGetErrorString(_e));
+        if (pong_fast_tabs_fill(tabs, d.text_stride, img.data())) {
+            ALLOC(h->fast_tabs_dev, ftb);
+            cudaError_t _e = cudaMemcpy(h->fast_tabs_dev, img.data(), ftb, cudaMemcpyHostToDevice);
+            if (_e == cudaSuccess) _e = launch_pong_build_bat_lut(d.dim, h->fast_tabs_dev, 0);
+            if (_e != cudaSuccess) {
+                crl_pong_destroy(h);
+                return fail(CRL_E_CUDA, "fast tabs upload: %s", cudaGetErrorString(_e));
+            }
+            g_launches += 1;
+            d.fast_tabs = h->fast_tabs_dev;
         }
-        d.fast_tabs = h->fast_tabs_dev;
     }
     d.tabs = h->tabs_dev;
     d.atlas = h->atlas_dev;

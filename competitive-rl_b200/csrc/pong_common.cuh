@@ -138,8 +138,8 @@ cudaError_t launch_pong_raster_generic(const PongDev& p, const FrameSpec* hist, 
                                        uint8_t* obs0, uint8_t* obs1, cudaStream_t s);
 cudaError_t pong_raster_init();
 size_t pong_fast_tabs_bytes(int dim);
-bool pong_fast_supported(const AreaTabs& a);
-void pong_fast_tabs_fill(const AreaTabs& a, void* host_buf);
+bool pong_fast_tabs_fill(const AreaTabs& a, int text_stride, void* host_buf);   // false: geometry not supported
+cudaError_t launch_pong_build_bat_lut(int dim, void* fast_tabs_dev, cudaStream_t s);
 cudaError_t launch_pong_raw_frame(const PongDev& p, int env, uint8_t* rgb0, uint8_t* rgb1, cudaStream_t s);
 
 }  // namespace crl

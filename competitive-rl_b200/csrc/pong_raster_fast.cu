@@ -8,14 +8,22 @@
 //
 // Shape of the work (84x84): a preprocessed frame is 7 056 bytes of which ~100 depend on
 // the ball and bats; the rest is the scoreboard rows (table lookup by score pair) and a
-// constant template.  So each warp keeps the TEMPLATE resident in its shared-memory
-// frame buffer and, per frame,
-//   1. copies the scoreboard rows for this frame's score pair(s) into the buffer,
-//   2. evaluates -- exactly, with cv2's un-fused fp32 order -- only the destination
-//      pixels whose source footprint touches a rectangle (one pixel per lane),
-//   3. streams the buffer to HBM with coalesced 16-byte st.global.cs,
-//   4. restores the patched pixels, so the buffer is the template again.
-// HBM traffic = the observation bytes, written once; no reads beyond ~100 B/env of state.
+// constant template.  Each warp keeps the TEMPLATE resident in its shared-memory frame
+// buffer and, per frame,
+//   A. computes in registers what differs from the template:
+//        - bat columns: a bat always covers the same source columns, so a destination row of
+//          the 4-column bat strip is a pure function of (row, which of its vertical taps are
+//          inside a bat) -> one 32-bit LUT word per row, one lane per row;
+//        - ball: the <=4x4 destination pixels of each of the two pooled ball positions are
+//          evaluated exactly (cv2's un-fused fp32 order), one pixel per lane, taking nearby
+//          bats into account;
+//        - the scoreboard rows for this frame's score pair(s) (only when they changed);
+//   B. waits until the TMA engine has finished READING the previous frame out of the buffer,
+//      restores the bytes that frame had patched, writes this frame's patches,
+//   C. hands the buffer to the TMA engine: one cp.async.bulk shared->global of 7 056 bytes
+//      (fence.proxy.async first), so the drain costs one instruction and overlaps step A of
+//      the next frame.
+// HBM traffic = the observation bytes, written once; ~100 B/env of state are read.
 // The grid is persistent: SMs x resident CTAs, warps stride over the stacks.
 #include "pong_raster_dev.cuh"
 
@@ -30,16 +38,16 @@ template <int DIM> struct FastCfg;
 template <> struct FastCfg<84> { static constexpr int TAPS = 3, VEC = 16; };
 template <> struct FastCfg<42> { static constexpr int TAPS = 5, VEC = 4; };
 
-constexpr int FAST_WARPS = 4;
+constexpr int FAST_WARPS = 8;
 constexpr int FIRST_PAD = 224;   // y_first/y_last padded to a multiple of 16 bytes
+constexpr int BAT_ROWS = 8;      // destination rows one bat can touch (checked on the host)
 
 template <int DIM> struct alignas(16) FastTabs {
     TapEnt<FastCfg<DIM>::TAPS> xe[DIM], ye[DIM];
+    uint32_t bat_lut[2][DIM][1 << FastCfg<DIM>::TAPS];   // [view side][dst row][vertical tap bits] -> 4 pixels
     uint8_t x_first[SCREEN_W], x_last[SCREEN_W], y_first[FIRST_PAD], y_last[FIRST_PAD];
+    uint32_t bat_c0[2], pad[2];                           // first of the 4 destination columns per side
 };
-
-struct alignas(16) RectS { uint32_t xy, mx8, my8, pad; };          // x0 | y0<<16, (1<<w)-1 << 8, (1<<h)-1 << 8
-struct alignas(16) RegionS { uint32_t geom, start, recip, mask; };  // x0 | y0<<8 | w<<16
 
 template <int VEC> struct VecT;
 template <> struct VecT<16> { typedef uint4 type; };
@@ -53,30 +61,30 @@ __device__ __forceinline__ void st_stream(uint32_t* ptr, const uint32_t v) {
     asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(ptr), "r"(v) : "memory");
 }
 
+// ---- TMA bulk store (shared::cta -> global), bulk_group completion ----
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // bits of v (<= 5) moved to positions 0, 6, 12, 18, 24
 __device__ __forceinline__ uint32_t spread6(uint32_t v) { return (v * 0x108421u) & 0x1041041u; }
 
-// mask8 = rect extent mask << 8; returns the tap bits covered by a rect starting at r0 when
-// the taps start at s0
+// mask8 = extent mask << 8 of a rect starting at r0; returns which of the taps starting at s0 it covers
 __device__ __forceinline__ uint32_t tap_bits(uint32_t mask8, int r0, int s0) {
     const int sh = min(max(8 - (r0 - s0), 0), 31);
     return mask8 >> sh;
 }
 
+// cv2 INTER_AREA float sequence for one destination pixel given, per vertical tap t (6-bit
+// field t of `pat`), which horizontal taps are white.  X.w = fl(255*alpha), Y.w = beta.
 template <int TAPS>
-__device__ __forceinline__ uint32_t eval_fast(const TapEnt<TAPS>& X, const TapEnt<TAPS>& Y, const RectS* rects,
-                                              uint32_t infl) {
-    const int sx0 = X.meta & 255u, sy0 = Y.meta & 255u;
-    const uint32_t xmask = (X.meta >> 8) & 255u, ymask = (Y.meta >> 8) & 255u;
-    uint32_t pat = xmask * spread6((Y.meta >> 16) & 255u);   // border rows: every tap white
-    while (infl) {
-        const int k = __ffs(infl) - 1;
-        infl &= infl - 1;
-        const RectS r = rects[k];
-        const uint32_t hb = tap_bits(r.mx8, (int)(r.xy & 0xffffu), sx0) & xmask;
-        const uint32_t vb = tap_bits(r.my8, (int)(r.xy >> 16), sy0) & ymask;
-        pat |= hb * spread6(vb);
-    }
+__device__ __forceinline__ uint32_t eval_from_pat(const TapEnt<TAPS>& X, const TapEnt<TAPS>& Y, uint32_t pat) {
     float sum = 0.f;
 #pragma unroll
     for (int t = 0; t < TAPS; ++t) {
@@ -87,34 +95,82 @@ __device__ __forceinline__ uint32_t eval_fast(const TapEnt<TAPS>& X, const TapEn
         const float term = __fmul_rn(Y.w[t], buf);           // padded taps have weight 0
         sum = (t == 0) ? term : __fadd_rn(sum, term);
     }
-    const int v = __float2int_rn(sum);
+    const int v = __float2int_rn(sum);                       // cvRound: half to even
     return (uint32_t)min(max(v, 0), 255);
 }
 
+// One 4-pixel LUT word per (view side, destination row, vertical tap bits).
 template <int DIM>
-__global__ void __launch_bounds__(FAST_WARPS * 32)
+__global__ void pong_build_bat_lut_kernel(FastTabs<DIM>* T) {
+    constexpr int TAPS = FastCfg<DIM>::TAPS, NP = 1 << TAPS;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * DIM * NP) return;
+    const int vp = i % NP, dy = (i / NP) % DIM, side = i / (NP * DIM);
+    const TapEnt<TAPS> Y = T->ye[dy];
+    const uint32_t ymask = (Y.meta >> 8) & 255u;
+    uint32_t word = 0u;
+    for (int j = 0; j < 4; ++j) {
+        const int dx = (int)T->bat_c0[side] + j;
+        uint32_t v = 0u;
+        if (dx < DIM) {
+            const TapEnt<TAPS> X = T->xe[dx];
+            const uint32_t xmask = (X.meta >> 8) & 255u;
+            const uint32_t hb = tap_bits(((1u << BAT_W) - 1u) << 8, side ? RIGHT_BAT_X : LEFT_BAT_X, X.meta & 255u) & xmask;
+            const uint32_t pat = xmask * spread6((Y.meta >> 16) & 255u) | hb * spread6((uint32_t)vp & ymask);
+            v = eval_from_pat<TAPS>(X, Y, pat);
+        }
+        word |= v << (8 * j);
+    }
+    T->bat_lut[side][dy][vp] = word;
+}
+
+// Exact generic evaluation of a whole frame into the staged buffer, plain drain, template refill.
+// Kept out of line so its registers do not count against the hot loop.
+template <int DIM>
+__device__ __noinline__ void slow_frame(const AreaTabs* __restrict__ tabs, const uint8_t* __restrict__ atlas,
+                                        const uint8_t* __restrict__ tmpl, const FrameSpec g, const int agent,
+                                        uint8_t* sm8, uint8_t* out8, const int lane) {
+    constexpr int VEC = FastCfg<DIM>::VEC, DD = DIM * DIM, FB = ((DD + 15) / 16) * 16, NCH = DD / VEC;
+    typedef typename VecT<VEC>::type V;
+    const FrameCtx c = make_ctx(g, agent);
+    for (int i = lane; i < DD; i += 32)
+        sm8[i] = c.any_valid ? eval_pixel(tabs, c, atlas, i / DIM, i % DIM) : (uint8_t)0;
+    __syncwarp();
+    V* out = reinterpret_cast<V*>(out8);
+    const V* sm = reinterpret_cast<const V*>(sm8);
+    for (int k = lane; k < NCH; k += 32) st_stream(out + k, sm[k]);
+    __syncwarp();
+    const uint4* tm = reinterpret_cast<const uint4*>(tmpl);
+    uint4* fb = reinterpret_cast<uint4*>(sm8);
+    for (int i = lane; i < FB / 16; i += 32) fb[i] = tm[i];
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(FAST_WARPS * 32, 3)
 pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* __restrict__ obs0,
                         uint8_t* __restrict__ obs1, const FastTabs<DIM>* __restrict__ gtabs) {
     constexpr int TAPS = FastCfg<DIM>::TAPS, VEC = FastCfg<DIM>::VEC;
     constexpr int DD = DIM * DIM, FB = ((DD + 15) / 16) * 16, NCH = DD / VEC;
+#ifndef CRL_RASTER_TMA
+#define CRL_RASTER_TMA 0
+#endif
+    constexpr bool USE_TMA = (DD % 16 == 0) && (CRL_RASTER_TMA != 0);
+    constexpr int TEXT_ITERS = 3;   // text_stride <= 96 vectors (checked on the host)
     typedef typename VecT<VEC>::type V;
     typedef FastTabs<DIM> Tabs;
     static_assert(DD % VEC == 0, "frame must be a whole number of store vectors");
 
     extern __shared__ uint4 smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(smem_raw);
-    Tabs* T = reinterpret_cast<Tabs*>(smem);
+    const Tabs* T = reinterpret_cast<const Tabs*>(smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t* warp_base = smem + sizeof(Tabs) + (size_t)warp * (FB + 6 * sizeof(RectS) + 4 * sizeof(RegionS));
-    uint8_t* sm8 = warp_base;
+    uint8_t* sm8 = smem + sizeof(Tabs) + (size_t)warp * FB;
     V* sm = reinterpret_cast<V*>(sm8);
-    RectS* rects = reinterpret_cast<RectS*>(warp_base + FB);
-    RegionS* regions = reinterpret_cast<RegionS*>(warp_base + FB + 6 * sizeof(RectS));
 
-    // ---- CTA prologue: tap tables into shared memory, template into every warp's frame buffer ----
+    // ---- CTA prologue: tables into shared memory, template into every warp's frame buffer ----
     {
         const uint4* src = reinterpret_cast<const uint4*>(gtabs);
-        uint4* dst = reinterpret_cast<uint4*>(T);
+        uint4* dst = reinterpret_cast<uint4*>(smem);
         for (int i = threadIdx.x; i < (int)(sizeof(Tabs) / 16); i += blockDim.x) dst[i] = src[i];
         const uint4* tm = reinterpret_cast<const uint4*>(p.tmpl);
         uint4* f = reinterpret_cast<uint4*>(sm8);
@@ -123,6 +179,16 @@ pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
     __syncthreads();
 
     const int text_chunks = p.text_stride / VEC;
+    const int cL = (int)T->bat_c0[0], cR = (int)T->bat_c0[1];
+    // lane roles
+    const int b_side = lane >> 4, b_which = (lane >> 3) & 1, b_row = lane & 7;   // bat strip rows
+    const int p_which = lane >> 4, p_col = lane & 3, p_row = (lane >> 2) & 3;    // ball pixels
+    // what the previous frame left patched in the buffer (restored before the next write)
+    int prev_bat_off = -1, prev_ball_off = -1;
+    uint32_t prev_bat_rest = 0u, prev_ball_old = 0u;
+    int cur_text = -1;          // text_tab entry whose rows are in the buffer (-1: template's)
+    bool pending = false;       // a bulk store may still be reading the buffer
+
     const long long n_stacks = (long long)p.n * p.n_agents;
     for (long long s = (long long)blockIdx.x * FAST_WARPS + warp; s < n_stacks; s += (long long)gridDim.x * FAST_WARPS) {
         const int env = (int)(s / p.n_agents), agent = (int)(s % p.n_agents);
@@ -136,7 +202,7 @@ pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
             f.y = __shfl_sync(0xffffffffu, my_spec.y, slot);
             f.z = __shfl_sync(0xffffffffu, my_spec.z, slot);
             f.w = __shfl_sync(0xffffffffu, my_spec.w, slot);
-            V* out = reinterpret_cast<V*>(out_stack + (size_t)slot * DD);
+            uint8_t* out8 = out_stack + (size_t)slot * DD;
 
             // ---- frame context (warp-uniform) ----
             const bool va = (f.y >> 16) & 1u, vb = (f.w >> 16) & 1u;
@@ -156,175 +222,176 @@ pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
             }
 
             if (!(va || vb) || !text_ok) {
-                // ---- slow frame (never reached in normal play): both pool buffers still zero, or a
-                // score combination outside the table.  Exact generic evaluation, then template refill.
-                FrameSpec g = f;
-                if (!(va || vb)) g = make_uint4(0u, 0u, 0u, 0u);
-                const FrameCtx c = make_ctx(g, agent);
-                for (int i = lane; i < DD; i += 32)
-                    sm8[i] = c.any_valid ? eval_pixel(p.tabs, c, p.atlas, i / DIM, i % DIM) : (uint8_t)0;
-                __syncwarp();
-                for (int k = lane; k < NCH; k += 32) st_stream(out + k, sm[k]);
-                __syncwarp();
-                const uint4* tm = reinterpret_cast<const uint4*>(p.tmpl);
-                uint4* fb = reinterpret_cast<uint4*>(sm8);
-                for (int i = lane; i < FB / 16; i += 32) fb[i] = tm[i];
+                // ---- slow frame (not reached in normal play): both pool buffers still zero, or a score
+                // combination outside the table.  Exact generic evaluation, then template refill.
+                if (pending) {
+                    if (lane == 0) bulk_wait_read();
+                    __syncwarp();
+                    pending = false;
+                }
+                slow_frame<DIM>(p.tabs, p.atlas, p.tmpl, (va || vb) ? f : make_uint4(0u, 0u, 0u, 0u), agent, sm8, out8, lane);
+                prev_bat_off = prev_ball_off = -1;
+                cur_text = -1;
                 __syncwarp();
                 continue;
             }
 
-            // ---- rectangles: lane k < 6 owns rect k (ball, left bat, right bat of frame A, then B) ----
-            uint32_t fp = 0u;         // dst footprint x0 | x1<<8 | y0<<16 | y1<<24 (inclusive), valid iff nonempty
-            bool nonempty = false;
-            if (lane < 6) {
-                const bool second = lane >= 3;
-                const uint32_t sx = second ? f.z : f.x;
-                const int which = second ? lane - 3 : lane;
-                int x0, y0, w, h;
-                if (which == 0) { x0 = sx & 255u; y0 = (sx >> 8) & 255u; w = BALL_SIZE; h = BALL_SIZE; }
-                else if (which == 1) { x0 = LEFT_BAT_X; y0 = (sx >> 16) & 255u; w = BAT_W; h = BAT_H; }
-                else { x0 = RIGHT_BAT_X; y0 = sx >> 24; w = BAT_W; h = BAT_H; }
-                int x1 = min(x0 + w, SCREEN_W), y1 = min(y0 + h, ARENA_BOTTOM);
-                x0 = max(x0, 0);
-                y0 = max(y0, ARENA_TOP);   // white on white outside the arena rows
-                nonempty = x1 > x0 && y1 > y0 && !(second && f.x == f.z);
-                if (nonempty) {
-                    if (agent) { const int t = SCREEN_W - x1; x1 = SCREEN_W - x0; x0 = t; }   // mirrored view
-                    RectS r;
-                    r.xy = (uint32_t)x0 | ((uint32_t)y0 << 16);
-                    r.mx8 = ((1u << (x1 - x0)) - 1u) << 8;
-                    r.my8 = ((1u << (y1 - y0)) - 1u) << 8;
-                    r.pad = 0u;
-                    rects[lane] = r;
-                    fp = (uint32_t)T->x_first[x0] | ((uint32_t)T->x_last[x1 - 1] << 8) |
-                         ((uint32_t)T->y_first[y0] << 16) | ((uint32_t)T->y_last[y1 - 1] << 24);
-                }
-            }
-            const uint32_t ne_mask = __ballot_sync(0xffffffffu, nonempty);
+            // ======== A. everything that differs from the template, in registers ========
+            const bool same = (f.x == f.z);
+            // view coordinates: agent 1 sees the arena mirrored in x, so the view-left bat strip
+            // shows the game's right bat
+            const int lyA = (f.x >> 16) & 255u, ryA = f.x >> 24, lyB = (f.z >> 16) & 255u, ryB = f.z >> 24;
+            const int vlA = agent ? ryA : lyA, vrA = agent ? lyA : ryA;
+            const int vlB = agent ? ryB : lyB, vrB = agent ? lyB : ryB;
 
-            // ---- regions: lane g < 4 owns region g = footprint bbox of {left bats, right bats, ball A, ball B} ----
-            const int ra = (lane == 0) ? 1 : (lane == 1) ? 2 : (lane == 2) ? 0 : 3;
-            const int rb = (lane == 0) ? 4 : (lane == 1) ? 5 : ra;
-            const uint32_t fa = __shfl_sync(0xffffffffu, fp, ra & 31), fb2 = __shfl_sync(0xffffffffu, fp, rb & 31);
-            int gx0 = 0, gx1 = -1, gy0 = 0, gy1 = -1;
-            if (lane < 4) {
-                const bool ea = (ne_mask >> ra) & 1u, eb = (ne_mask >> rb) & 1u;
-                if (ea) { gx0 = fa & 255u; gx1 = (fa >> 8) & 255u; gy0 = (fa >> 16) & 255u; gy1 = fa >> 24; }
-                if (eb) {
-                    const int bx0 = fb2 & 255u, bx1 = (fb2 >> 8) & 255u, by0 = (fb2 >> 16) & 255u, by1 = fb2 >> 24;
-                    if (ea) { gx0 = min(gx0, bx0); gx1 = max(gx1, bx1); gy0 = min(gy0, by0); gy1 = max(gy1, by1); }
-                    else { gx0 = bx0; gx1 = bx1; gy0 = by0; gy1 = by1; }
-                }
-            }
-            const int gw = gx1 - gx0 + 1, gh = gy1 - gy0 + 1;
-            int cnt = (lane < 4 && gx1 >= gx0) ? gw * gh : 0;
-            // which rects can influence pixels of this region: footprint bbox intersects region bbox
-            uint32_t infl = 0u;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                const uint32_t fk = __shfl_sync(0xffffffffu, fp, k);
-                const bool hit = ((ne_mask >> k) & 1u) && (int)(fk & 255u) <= gx1 && (int)((fk >> 8) & 255u) >= gx0 &&
-                                 (int)((fk >> 16) & 255u) <= gy1 && (int)(fk >> 24) >= gy0;
-                infl |= hit ? (1u << k) : 0u;
-            }
-            // exclusive prefix of cnt over lanes 0..3
-            int incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 4; d <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += v;
-            }
-            if (lane < 4) {
-                RegionS R;
-                R.geom = (uint32_t)gx0 | ((uint32_t)gy0 << 8) | ((uint32_t)max(gw, 1) << 16);
-                R.start = (uint32_t)(incl - cnt);
-                R.recip = (65536u + (uint32_t)max(gw, 1) - 1u) / (uint32_t)max(gw, 1);
-                R.mask = infl;
-                regions[lane] = R;
-            }
-            // a rect that is not one of the region's own reaches into it -> two regions may share pixels
-            const uint32_t own = (lane == 0) ? 0x12u : (lane == 1) ? 0x24u : (lane == 2) ? 0x01u : 0x08u;
-            const bool shared_px = __ballot_sync(0xffffffffu, lane < 4 && (infl & ~own) != 0u) != 0u;
-            const int s1 = __shfl_sync(0xffffffffu, incl, 0), s2 = __shfl_sync(0xffffffffu, incl, 1),
-                      s3 = __shfl_sync(0xffffffffu, incl, 2), total = __shfl_sync(0xffffffffu, incl, 3);
+            // ---- A1. scoreboard rows (only when the buffer holds another score pair's) ----
+            const int text_id = (base * 3 + kind) * 2 + agent;
+            const bool reload_text = text_id != cur_text;
+            const uint8_t* __restrict__ te8 = p.text_tab + (size_t)text_id * p.text_stride;
+            if (reload_text && lane * 128 < p.text_stride)   // pull the entry's lines L2 -> L1 now, copy in phase B
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(te8 + lane * 128));
 
-            // ---- 1. scoreboard rows for this frame's score pair(s) ----
+            // ---- A2. bat strips: lane = (view side, frame A|B, row); one LUT word per row ----
+            int bat_off = -1;
+            uint32_t bat_val = 0u, bat_rest = 0u;
             {
-                const V* __restrict__ te =
-                    reinterpret_cast<const V*>(p.text_tab + (size_t)((base * 3 + kind) * 2 + agent) * p.text_stride);
-                for (int k = lane; k < text_chunks; k += 32) sm[k] = te[k];
+                const int yA = b_side ? vrA : vlA, yB = b_side ? vrB : vlB;
+                const int y0 = b_which ? yB : yA;
+                const int c0 = max(y0, ARENA_TOP), c1 = min(y0 + BAT_H, ARENA_BOTTOM);   // white on white outside
+                if (c1 > c0 && !(b_which && same)) {
+                    const int dy = (int)T->y_first[c0] + b_row;
+                    if (dy <= (int)T->y_last[c1 - 1]) {
+                        const uint32_t meta = T->ye[dy].meta;
+                        const int sy0 = meta & 255u;
+                        const int a0 = max(yA, ARENA_TOP), a1 = min(yA + BAT_H, ARENA_BOTTOM);
+                        const int b0 = max(yB, ARENA_TOP), b1 = min(yB + BAT_H, ARENA_BOTTOM);
+                        uint32_t vbits = 0u;
+                        if (a1 > a0) vbits |= tap_bits(((1u << (a1 - a0)) - 1u) << 8, a0, sy0);
+                        if (b1 > b0) vbits |= tap_bits(((1u << (b1 - b0)) - 1u) << 8, b0, sy0);
+                        vbits &= (meta >> 8) & 255u;
+                        bat_val = T->bat_lut[b_side][dy][vbits];
+                        bat_rest = T->bat_lut[b_side][dy][0];
+                        bat_off = dy * DIM + (b_side ? cR : cL);
+                    }
+                }
             }
-            __syncwarp();
 
-            // ---- 2. evaluate the pixels whose footprint touches a rectangle ----
-            uint32_t offs[4], olds = 0u;
+            // ---- A3. ball pixels: lane = (frame A|B, 4x4 window position), exact evaluation ----
+            int ball_off = -1;
+            uint32_t ball_val = 0u;
+            {
+                // both balls in view coordinates, clipped to the arena rows (white on white outside)
+                int ax0 = f.x & 255u, ax1 = min(ax0 + BALL_SIZE, SCREEN_W);
+                int ay0 = (f.x >> 8) & 255u, ay1 = min(ay0 + BALL_SIZE, ARENA_BOTTOM);
+                ay0 = max(ay0, ARENA_TOP);
+                int bx0 = f.z & 255u, bx1 = min(bx0 + BALL_SIZE, SCREEN_W);
+                int by0 = (f.z >> 8) & 255u, by1 = min(by0 + BALL_SIZE, ARENA_BOTTOM);
+                by0 = max(by0, ARENA_TOP);
+                if (agent) {
+                    int t = SCREEN_W - ax1; ax1 = SCREEN_W - ax0; ax0 = t;
+                    t = SCREEN_W - bx1; bx1 = SCREEN_W - bx0; bx0 = t;
+                }
+                const bool ea = ax1 > ax0 && ay1 > ay0, eb = bx1 > bx0 && by1 > by0 && !same;
+                const int mx0 = p_which ? bx0 : ax0, mx1 = p_which ? bx1 : ax1;
+                const int my0 = p_which ? by0 : ay0, my1 = p_which ? by1 : ay1;
+                if (p_which ? eb : ea) {
+                    const int dx = (int)T->x_first[mx0] + p_col, dy = (int)T->y_first[my0] + p_row;
+                    if (dx <= (int)T->x_last[mx1 - 1] && dy <= (int)T->y_last[my1 - 1]) {
+                        const TapEnt<TAPS> X = T->xe[dx], Y = T->ye[dy];
+                        const int sx0 = X.meta & 255u, sy0 = Y.meta & 255u;
+                        const uint32_t xmask = (X.meta >> 8) & 255u, ymask = (Y.meta >> 8) & 255u;
+                        uint32_t pat = xmask * spread6((Y.meta >> 16) & 255u);   // border rows: all white
+                        if (ea)
+                            pat |= (tap_bits(((1u << (ax1 - ax0)) - 1u) << 8, ax0, sx0) & xmask) *
+                                   spread6(tap_bits(((1u << (ay1 - ay0)) - 1u) << 8, ay0, sy0) & ymask);
+                        if (eb)
+                            pat |= (tap_bits(((1u << (bx1 - bx0)) - 1u) << 8, bx0, sx0) & xmask) *
+                                   spread6(tap_bits(((1u << (by1 - by0)) - 1u) << 8, by0, sy0) & ymask);
+                        // a bat strip under this pixel: both frames' bats of that side
+                        const bool nl = (unsigned)(dx - cL) < 4u, nr = (unsigned)(dx - cR) < 4u;
+                        if (nl || nr) {
+                            const int yA = nr ? vrA : vlA, yB = nr ? vrB : vlB;
+                            const int a0 = max(yA, ARENA_TOP), a1 = min(yA + BAT_H, ARENA_BOTTOM);
+                            const int b0 = max(yB, ARENA_TOP), b1 = min(yB + BAT_H, ARENA_BOTTOM);
+                            uint32_t vbits = 0u;
+                            if (a1 > a0) vbits |= tap_bits(((1u << (a1 - a0)) - 1u) << 8, a0, sy0);
+                            if (b1 > b0) vbits |= tap_bits(((1u << (b1 - b0)) - 1u) << 8, b0, sy0);
+                            const uint32_t hb = tap_bits(((1u << BAT_W) - 1u) << 8, nr ? RIGHT_BAT_X : LEFT_BAT_X, sx0);
+                            pat |= (hb & xmask) * spread6(vbits & ymask);
+                        }
+                        ball_val = eval_from_pat<TAPS>(X, Y, pat);
+                        ball_off = dy * DIM + dx;
+                    }
+                }
+            }
+
+            // ======== B. the buffer: wait for the previous drain, restore, patch ========
+            if (pending) {
+                if (lane == 0) bulk_wait_read();
+                __syncwarp();
+            }
+            if (prev_bat_off >= 0) {
+                if (DIM % 4 == 0) {
+                    *reinterpret_cast<uint32_t*>(sm8 + prev_bat_off) = prev_bat_rest;
+                } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                offs[j] = 0xffffffffu;
-                const int q = lane + 32 * j;
-                if (q < total) {
-                    const int g = (q >= s1) + (q >= s2) + (q >= s3);
-                    const RegionS R = regions[g];
-                    const int local = q - (int)R.start, w = (R.geom >> 16) & 255u;
-                    const int row = (int)(((uint32_t)local * R.recip) >> 16), col = local - row * w;
-                    const int dy = (int)((R.geom >> 8) & 255u) + row, dx = (int)(R.geom & 255u) + col;
-                    const uint32_t v = eval_fast<TAPS>(T->xe[dx], T->ye[dy], rects, R.mask);
-                    const int off = dy * DIM + dx;
-                    offs[j] = (uint32_t)off;
-                    olds |= (uint32_t)sm8[off] << (8 * j);
-                    sm8[off] = (uint8_t)v;
-                }
-            }
-            if (total > 128) {   // more than 4 pixels per lane (not reachable with 4x4 / 5x15 sprites)
-                for (int q = lane + 128; q < total; q += 32) {
-                    const int g = (q >= s1) + (q >= s2) + (q >= s3);
-                    const RegionS R = regions[g];
-                    const int local = q - (int)R.start, w = (R.geom >> 16) & 255u;
-                    const int row = (int)(((uint32_t)local * R.recip) >> 16), col = local - row * w;
-                    const int dy = (int)((R.geom >> 8) & 255u) + row, dx = (int)(R.geom & 255u) + col;
-                    sm8[dy * DIM + dx] = (uint8_t)eval_fast<TAPS>(T->xe[dx], T->ye[dy], rects, R.mask);
+                    for (int j = 0; j < 4; ++j) sm8[prev_bat_off + j] = (uint8_t)(prev_bat_rest >> (8 * j));
                 }
             }
             __syncwarp();
-
-            // ---- 3. stream the frame out ----
-#pragma unroll 4
-            for (int k = lane; k < NCH; k += 32) st_stream(out + k, sm[k]);
+            if (prev_ball_off >= 0) sm8[prev_ball_off] = (uint8_t)prev_ball_old;   // after the bats: a ball pixel may lie on a strip
             __syncwarp();
-
-            // ---- 4. restore the template under the patched pixels ----
-            // Two regions may overlap (ball next to a bat): both lanes saved a value for that byte and
-            // one of them saved the other's patch, so restore from the template instead of `olds`.
-            if (total > 128 || shared_px) {
-                // generic restore: template bytes (text rows are rewritten next frame anyway)
+            if (reload_text) {
+                const V* __restrict__ te = reinterpret_cast<const V*>(te8);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (offs[j] != 0xffffffffu) sm8[offs[j]] = p.tmpl[offs[j]];
-                for (int q = lane + 128; q < total; q += 32) {
-                    const int g = (q >= s1) + (q >= s2) + (q >= s3);
-                    const RegionS R = regions[g];
-                    const int local = q - (int)R.start, w = (R.geom >> 16) & 255u;
-                    const int row = (int)(((uint32_t)local * R.recip) >> 16), col = local - row * w;
-                    const int off = ((int)((R.geom >> 8) & 255u) + row) * DIM + (int)(R.geom & 255u) + col;
-                    sm8[off] = p.tmpl[off];
+                for (int j = 0; j < TEXT_ITERS; ++j)
+                    if (lane + 32 * j < text_chunks) sm[lane + 32 * j] = te[lane + 32 * j];
+                cur_text = text_id;
+                __syncwarp();
+            }
+            uint32_t ball_old = 0u;
+            if (ball_off >= 0) ball_old = sm8[ball_off];      // template / scoreboard value under the ball
+            __syncwarp();
+            if (bat_off >= 0) {
+                if (DIM % 4 == 0) {
+                    *reinterpret_cast<uint32_t*>(sm8 + bat_off) = bat_val;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) sm8[bat_off + j] = (uint8_t)(bat_val >> (8 * j));
                 }
+            }
+            __syncwarp();
+            if (ball_off >= 0) sm8[ball_off] = (uint8_t)ball_val;   // overrides the strip LUT where the ball is near
+            prev_bat_off = bat_off; prev_bat_rest = bat_rest;
+            prev_ball_off = ball_off; prev_ball_old = ball_old;
+
+            // ======== C. drain ========
+            if (USE_TMA) {
+                fence_proxy_async_smem();    // generic-proxy writes -> visible to the async proxy
+                __syncwarp();
+                if (lane == 0) bulk_store(out8, sm8, DD);
+                pending = true;
             } else {
+                __syncwarp();
+                V* out = reinterpret_cast<V*>(out8);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (offs[j] != 0xffffffffu) sm8[offs[j]] = (uint8_t)(olds >> (8 * j));
+                for (int j = 0; j < (NCH + 31) / 32; ++j)
+                    if ((j + 1) * 32 <= NCH || lane + 32 * j < NCH) st_stream(out + lane + 32 * j, sm[lane + 32 * j]);
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
+    if (USE_TMA && lane == 0) bulk_wait_all();   // the buffer must outlive the last drain
 }
 
 // ---------------------------------------------------------------------------------
 // host side
 template <int DIM>
-static void fill_fast_tabs(const AreaTabs& a, FastTabs<DIM>* t) {
+static bool fill_fast_tabs(const AreaTabs& a, FastTabs<DIM>* t) {
     constexpr int TAPS = FastCfg<DIM>::TAPS;
     memset(t, 0, sizeof *t);
     for (int i = 0; i < DIM; ++i) {
+        if (a.x_n[i] > TAPS || a.y_n[i] > TAPS) return false;
         t->xe[i].meta = (uint32_t)a.x_src0[i] | (((1u << a.x_n[i]) - 1u) << 8);
         uint32_t white = 0u;
         for (int k = 0; k < a.y_n[i]; ++k) {
@@ -341,29 +408,50 @@ static void fill_fast_tabs(const AreaTabs& a, FastTabs<DIM>* t) {
     memcpy(t->x_last, a.x_last, SCREEN_W);
     memcpy(t->y_first, a.y_first, SCREEN_H);
     memcpy(t->y_last, a.y_last, SCREEN_H);
+    // geometry the lane mapping relies on
+    for (int side = 0; side < 2; ++side) {   // bat strip: 4 destination columns starting at a multiple of 4
+        const int x0 = side ? RIGHT_BAT_X : LEFT_BAT_X;
+        const int c0 = (a.x_first[x0] / 4) * 4;
+        if (a.x_last[x0 + BAT_W - 1] > c0 + 3 || c0 + 3 >= DIM) return false;
+        t->bat_c0[side] = (uint32_t)c0;
+    }
+    for (int y = ARENA_TOP; y + 1 <= ARENA_BOTTOM; ++y) {   // a (clipped) bat touches <= BAT_ROWS rows
+        const int y1 = y + BAT_H < ARENA_BOTTOM ? y + BAT_H : ARENA_BOTTOM;
+        if (a.y_last[y1 - 1] - a.y_first[y] + 1 > BAT_ROWS) return false;
+    }
+    for (int x = 0; x < SCREEN_W; ++x) {                    // a ball touches <= 4x4 destination pixels
+        const int x1 = x + BALL_SIZE < SCREEN_W ? x + BALL_SIZE : SCREEN_W;
+        if (a.x_last[x1 - 1] - a.x_first[x] + 1 > 4) return false;
+    }
+    for (int y = ARENA_TOP; y < ARENA_BOTTOM; ++y) {
+        const int y1 = y + BALL_SIZE < ARENA_BOTTOM ? y + BALL_SIZE : ARENA_BOTTOM;
+        if (a.y_last[y1 - 1] - a.y_first[y] + 1 > 4) return false;
+    }
+    return true;
 }
 
 template <int DIM>
 static size_t fast_smem_bytes() {
     constexpr int FB = ((DIM * DIM + 15) / 16) * 16;
-    return sizeof(FastTabs<DIM>) + (size_t)FAST_WARPS * (FB + 6 * sizeof(RectS) + 4 * sizeof(RegionS));
+    return sizeof(FastTabs<DIM>) + (size_t)FAST_WARPS * FB;
 }
 
 size_t pong_fast_tabs_bytes(int dim) {
     return dim == 84 ? sizeof(FastTabs<84>) : dim == 42 ? sizeof(FastTabs<42>) : 0;
 }
 
-bool pong_fast_supported(const AreaTabs& a) {
-    int mx = 0;
-    for (int i = 0; i < a.dim; ++i) mx = max(mx, max((int)a.x_n[i], (int)a.y_n[i]));
-    if (a.dim == 84) return mx <= 3;
-    if (a.dim == 42) return mx <= 5;
+bool pong_fast_tabs_fill(const AreaTabs& a, int text_stride, void* host_buf) {
+    if (a.dim == 84) return text_stride <= 96 * 16 && fill_fast_tabs<84>(a, reinterpret_cast<FastTabs<84>*>(host_buf));
+    if (a.dim == 42) return text_stride <= 96 * 4 && fill_fast_tabs<42>(a, reinterpret_cast<FastTabs<42>*>(host_buf));
     return false;
 }
 
-void pong_fast_tabs_fill(const AreaTabs& a, void* host_buf) {
-    if (a.dim == 84) fill_fast_tabs<84>(a, reinterpret_cast<FastTabs<84>*>(host_buf));
-    else if (a.dim == 42) fill_fast_tabs<42>(a, reinterpret_cast<FastTabs<42>*>(host_buf));
+cudaError_t launch_pong_build_bat_lut(int dim, void* fast_tabs_dev, cudaStream_t s) {
+    if (dim == 84)
+        pong_build_bat_lut_kernel<84><<<(2 * 84 * 8 + 127) / 128, 128, 0, s>>>(reinterpret_cast<FastTabs<84>*>(fast_tabs_dev));
+    else if (dim == 42)
+        pong_build_bat_lut_kernel<42><<<(2 * 42 * 32 + 127) / 128, 128, 0, s>>>(reinterpret_cast<FastTabs<42>*>(fast_tabs_dev));
+    return cudaGetLastError();
 }
 
 static int g_grid[2] = {0, 0};
