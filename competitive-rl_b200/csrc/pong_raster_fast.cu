@@ -124,25 +124,33 @@ __global__ void pong_build_bat_lut_kernel(FastTabs<DIM>* T) {
     T->bat_lut[side][dy][vp] = word;
 }
 
-// Exact generic evaluation of a whole frame into the staged buffer, plain drain, template refill.
-// Kept out of line so its registers do not count against the hot loop.
-template <int DIM>
-__device__ __noinline__ void slow_frame(const AreaTabs* __restrict__ tabs, const uint8_t* __restrict__ atlas,
-                                        const uint8_t* __restrict__ tmpl, const FrameSpec g, const int agent,
-                                        uint8_t* sm8, uint8_t* out8, const int lane) {
-    constexpr int VEC = FastCfg<DIM>::VEC, DD = DIM * DIM, FB = ((DD + 15) / 16) * 16, NCH = DD / VEC;
-    typedef typename VecT<VEC>::type V;
-    const FrameCtx c = make_ctx(g, agent);
-    for (int i = lane; i < DD; i += 32)
-        sm8[i] = c.any_valid ? eval_pixel(tabs, c, atlas, i / DIM, i % DIM) : (uint8_t)0;
-    __syncwarp();
-    V* out = reinterpret_cast<V*>(out8);
-    const V* sm = reinterpret_cast<const V*>(sm8);
-    for (int k = lane; k < NCH; k += 32) st_stream(out + k, sm[k]);
-    __syncwarp();
-    const uint4* tm = reinterpret_cast<const uint4*>(tmpl);
-    uint4* fb = reinterpret_cast<uint4*>(sm8);
-    for (int i = lane; i < FB / 16; i += 32) fb[i] = tm[i];
+// Scoreboard rows for a score combination that is not in text_tab (the two pooled frames differ by
+// more than one point: only reachable through crl_pong_set_state): exact evaluation straight from
+// the atlas.  Arena taps count as black here; pixels that also see a rectangle are overwritten by
+// the bat/ball patches, which (fast_ok) treat the atlas rows they share a destination row with as white.
+__device__ __forceinline__ uint8_t eval_text_pixel(const AreaTabs* __restrict__ T, const uint8_t* __restrict__ atlas,
+                                                   int pairA, int pairB, bool mirror, int dy, int dx) {
+    const int sx0 = T->x_src0[dx], nx = T->x_n[dx], sy0 = T->y_src0[dy], ny = T->y_n[dy];
+    float sum = 0.f;
+    for (int ty = 0; ty < ny; ++ty) {
+        const int sy = sy0 + ty;
+        float buf = 0.f;
+        for (int tx = 0; tx < nx; ++tx) {
+            int g = 0;
+            if (sy < ARENA_TOP) {
+                const int sx = sx0 + tx;
+                const int ax = (mirror && sy >= MIRROR_ROW) ? (SCREEN_W - 1 - sx) : sx;
+                const uint8_t* pa = atlas + ((size_t)(pairA * ATLAS_ROWS + sy) * SCREEN_W + ax) * 3;
+                const uint8_t* pb = atlas + ((size_t)(pairB * ATLAS_ROWS + sy) * SCREEN_W + ax) * 3;
+                g = (max((int)pa[0], (int)pb[0]) * 9798 + max((int)pa[1], (int)pb[1]) * 19235 +
+                     max((int)pa[2], (int)pb[2]) * 3735 + 16384) >> 15;
+            }
+            buf = __fadd_rn(buf, __fmul_rn((float)g, T->x_a[dx][tx]));
+        }
+        const float term = __fmul_rn(T->y_b[dy][ty], buf);
+        sum = (ty == 0) ? term : __fadd_rn(sum, term);
+    }
+    return (uint8_t)min(max(__float2int_rn(sum), 0), 255);
 }
 
 template <int DIM>
@@ -221,18 +229,13 @@ pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
                 else text_ok = false;
             }
 
-            if (!(va || vb) || !text_ok) {
-                // ---- slow frame (not reached in normal play): both pool buffers still zero, or a score
-                // combination outside the table.  Exact generic evaluation, then template refill.
-                if (pending) {
-                    if (lane == 0) bulk_wait_read();
-                    __syncwarp();
-                    pending = false;
-                }
-                slow_frame<DIM>(p.tabs, p.atlas, p.tmpl, (va || vb) ? f : make_uint4(0u, 0u, 0u, 0u), agent, sm8, out8, lane);
-                prev_bat_off = prev_ball_off = -1;
-                cur_text = -1;
-                __syncwarp();
+            if (!(va || vb)) {
+                // both MaxAndSkip buffers still np.zeros (a done on the very first sub-steps after
+                // construction; not reachable in play): the frame is all zeros.  The staged buffer is untouched.
+                V z;
+                memset(&z, 0, sizeof z);
+                V* out = reinterpret_cast<V*>(out8);
+                for (int k = lane; k < NCH; k += 32) st_stream(out + k, z);
                 continue;
             }
 
@@ -245,10 +248,10 @@ pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
             const int vlB = agent ? ryB : lyB, vrB = agent ? lyB : ryB;
 
             // ---- A1. scoreboard rows (only when the buffer holds another score pair's) ----
-            const int text_id = (base * 3 + kind) * 2 + agent;
-            const bool reload_text = text_id != cur_text;
+            const int text_id = text_ok ? (base * 3 + kind) * 2 + agent : -2;
+            const bool reload_text = text_id != cur_text || !text_ok;
             const uint8_t* __restrict__ te8 = p.text_tab + (size_t)text_id * p.text_stride;
-            if (reload_text && lane * 128 < p.text_stride)   // pull the entry's lines L2 -> L1 now, copy in phase B
+            if (reload_text && text_ok && lane * 128 < p.text_stride)   // pull the entry's lines L2 -> L1 now, copy in phase B
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(te8 + lane * 128));
 
             // ---- A2. bat strips: lane = (view side, frame A|B, row); one LUT word per row ----
@@ -342,10 +345,16 @@ pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
             if (prev_ball_off >= 0) sm8[prev_ball_off] = (uint8_t)prev_ball_old;   // after the bats: a ball pixel may lie on a strip
             __syncwarp();
             if (reload_text) {
-                const V* __restrict__ te = reinterpret_cast<const V*>(te8);
+                if (text_ok) {
+                    const V* __restrict__ te = reinterpret_cast<const V*>(te8);
 #pragma unroll
-                for (int j = 0; j < TEXT_ITERS; ++j)
-                    if (lane + 32 * j < text_chunks) sm[lane + 32 * j] = te[lane + 32 * j];
+                    for (int j = 0; j < TEXT_ITERS; ++j)
+                        if (lane + 32 * j < text_chunks) sm[lane + 32 * j] = te[lane + 32 * j];
+                } else {   // score combination outside the table: exact rows straight from the atlas
+                    const int n_text = p.tabs->text_rows * DIM;
+                    for (int i = lane; i < n_text; i += 32)
+                        sm8[i] = eval_text_pixel(p.tabs, p.atlas, pairA, pairB, agent != 0, i / DIM, i % DIM);
+                }
                 cur_text = text_id;
                 __syncwarp();
             }
