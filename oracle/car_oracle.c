@@ -1,0 +1,1067 @@
+/*
+ * car_oracle.c -- CPU restatement of the reference's cCarRacing stepping path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/pong_oracle.c for the rules).
+ *
+ * What is restated from WHICH source (paths relative to /root/reference/competitive_rl/):
+ *   car_racing/car_dynamics.py            Car.__init__ (55-129), gas/brake/steer (131-157), step (159-234)
+ *   car_racing/car_racing_multi_players.py  FrictionDetector._contact (111-153), _create_track (262-452),
+ *                                         reset (454-525), process_action (527-540), step (542-620),
+ *                                         get_observation (622-634), render_indicators_for_pygame (645-670),
+ *                                         render_road_for_observation_map (732-755), camera_view (764-789),
+ *                                         camera_update (791-812), render "internal_rgb_array" (857-863)
+ *   car_racing/pygame_rendering.py        vertical_ind / horiz_ind / draw_text (8-18)
+ * and, because the reference's native arithmetic lives in box2d-py ~=2.3.5 (setup.py:14), which is
+ * NOT in /root/reference and not installable here, the published Box2D 2.3 algorithms restated
+ * from memory: b2PolygonShape::ComputeMass, b2Body::ResetMassData, b2World::Step / b2Island::Solve
+ * (force integration, warm-started sequential impulses, 180 velocity + 60 position iterations,
+ * translation/rotation clamps, island sleeping), b2RevoluteJoint (motor + limit + point),
+ * sensor overlap for tile contacts.  PARITY UNPINNED for that part: no Box2D run is available to
+ * check it against.  The Python-level logic IS pinned: oracle/ref_car_loader.py runs
+ * the reference's own car_dynamics.py / car_racing_multi_players.py on top of a Box2D stand-in
+ * that calls this file's solver, and tests/test_oracle_car.py compares.
+ *
+ * Deliberate simplifications (stated, tested as such):
+ *   - car-car collisions are not modelled (each car is its own island; cCarRacingDouble cars
+ *     pass through each other);
+ *   - a sensor contact exists exactly while the wheel polygon and the tile polygon are closer
+ *     than 2*b2_polygonRadius by the separating-axis measure, evaluated at the start of
+ *     world.Step (Box2D: b2TestOverlap on contacts whose fat AABBs overlap);
+ *   - the renderer samples the analytic scene at destination pixel centres instead of
+ *     re-creating pygame's polygon scan conversion and rotozoom (see render_obs below).
+ *
+ * Build: gcc -O2 -ffp-contract=off -pthread -shared -fPIC (oracle/Makefile).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------ */
+/* constants                                                                                   */
+
+#define STATE_W 96
+#define STATE_H 96
+#define SCALE 6.0
+#define TRACK_RAD (900.0 / SCALE)
+#define PLAYFIELD (2000.0 / SCALE)
+#define FPS 50
+#define TRACK_DETAIL_STEP (21.0 / SCALE)
+#define TRACK_TURN_RATE 0.31
+#define TRACK_WIDTH (40.0 / SCALE)
+#define BORDER (8.0 / SCALE)
+#define BORDER_MIN_COUNT 4
+#define CHECKPOINTS 12
+#define MAX_TRACK 512
+#define MAX_TRACK_RAW 2600
+#define MAX_CARS 2
+
+#define SIZE 0.02
+#define ENGINE_POWER (100000000 * SIZE * SIZE)
+#define WHEEL_MOMENT_OF_INERTIA (4000 * SIZE * SIZE)
+#define FRICTION_LIMIT (1000000 * SIZE * SIZE)
+#define WHEEL_R 27
+#define WHEEL_W 14
+
+/* Box2D 2.3 b2Settings.h */
+#define B2_LINEAR_SLOP 0.005f
+#define B2_ANGULAR_SLOP (2.0f / 180.0f * 3.14159265359f)
+#define B2_POLYGON_RADIUS (2.0f * B2_LINEAR_SLOP)
+#define B2_MAX_ANGULAR_CORRECTION (8.0f / 180.0f * 3.14159265359f)
+#define B2_MAX_TRANSLATION 2.0f
+#define B2_MAX_ROTATION (0.5f * 3.14159265359f)
+#define B2_TIME_TO_SLEEP 0.5f
+#define B2_LINEAR_SLEEP_TOL 0.01f
+#define B2_ANGULAR_SLEEP_TOL (2.0f / 180.0f * 3.14159265359f)
+
+typedef struct { float x, y; } V2;
+typedef struct { float s, c; } Rot;
+
+static V2 v2(float x, float y) { V2 r = {x, y}; return r; }
+static V2 vadd(V2 a, V2 b) { return v2(a.x + b.x, a.y + b.y); }
+static V2 vsub(V2 a, V2 b) { return v2(a.x - b.x, a.y - b.y); }
+static V2 vscale(float s, V2 a) { return v2(s * a.x, s * a.y); }
+static float vdot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
+static float vcross(V2 a, V2 b) { return a.x * b.y - a.y * b.x; }
+static V2 cross_sv(float s, V2 a) { return v2(-s * a.y, s * a.x); }
+static Rot rot(float a) { Rot r = {sinf(a), cosf(a)}; return r; }
+static V2 rmul(Rot q, V2 v) { return v2(q.c * v.x - q.s * v.y, q.s * v.x + q.c * v.y); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* mini Box2D: bodies, polygon mass, revolute joints                                           */
+
+typedef struct {
+    V2 p; Rot q;                 /* m_xf */
+    V2 local_center, c0, c;      /* m_sweep */
+    float a0, a;
+    V2 v; float w;
+    V2 force; float torque;
+    float mass, inv_mass, I, inv_I;
+    int awake; float sleep_time;
+} Body;
+
+typedef struct {
+    int a, b;                    /* body indices */
+    V2 local_anchor_a, local_anchor_b;
+    float reference_angle;
+    int enable_motor, enable_limit;
+    float max_motor_torque, motor_speed, lower, upper;
+    /* solver state (b2RevoluteJoint members) */
+    float impulse[3], motor_impulse;
+    int limit_state;             /* 0 inactive, 1 atLower, 2 atUpper, 3 equal */
+    V2 rA, rB, lcA, lcB;
+    float mA, mB, iA, iB;
+    float K[3][3];               /* K[col][row] like b2Mat33 ex, ey, ez */
+    float motor_mass;
+} RevJoint;
+
+/* b2PolygonShape::ComputeMass (2.3) for a convex polygon given in CCW order */
+static void polygon_mass(const V2* vs, int n, float density, float* mass, V2* center, float* I) {
+    V2 c = v2(0.f, 0.f), s = v2(0.f, 0.f);
+    float area = 0.f, inertia = 0.f;
+    const float inv3 = 1.0f / 3.0f;
+    for (int i = 0; i < n; ++i) s = vadd(s, vs[i]);
+    s = vscale(1.0f / n, s);
+    for (int i = 0; i < n; ++i) {
+        V2 e1 = vsub(vs[i], s), e2 = vsub(vs[(i + 1) % n], s);
+        float D = vcross(e1, e2);
+        float tri = 0.5f * D;
+        area += tri;
+        c = vadd(c, vscale(tri * inv3, vadd(e1, e2)));
+        float intx2 = e1.x * e1.x + e2.x * e1.x + e2.x * e2.x;
+        float inty2 = e1.y * e1.y + e2.y * e1.y + e2.y * e2.y;
+        inertia += (0.25f * inv3 * D) * (intx2 + inty2);
+    }
+    *mass = density * area;
+    c = vscale(1.0f / area, c);
+    *center = vadd(c, s);
+    *I = density * inertia;
+    *I += *mass * (vdot(*center, *center) - vdot(c, c));
+}
+
+/* b2Body::ResetMassData over a list of polygons attached to the body */
+static void body_set_mass(Body* b, const V2* polys, const int* counts, const float* density, int n_polys) {
+    float mass = 0.f, I = 0.f;
+    V2 lc = v2(0.f, 0.f);
+    const V2* p = polys;
+    for (int k = 0; k < n_polys; ++k) {
+        float m, i;
+        V2 c;
+        polygon_mass(p, counts[k], density[k], &m, &c, &i);
+        mass += m;
+        lc = vadd(lc, vscale(m, c));
+        I += i;
+        p += counts[k];
+    }
+    b->mass = mass;
+    b->inv_mass = 1.0f / mass;
+    lc = vscale(b->inv_mass, lc);
+    I -= mass * vdot(lc, lc);
+    b->I = I;
+    b->inv_I = 1.0f / I;
+    b->local_center = lc;
+    b->c = b->c0 = vadd(rmul(b->q, lc), b->p);
+}
+
+static void body_init(Body* b, float x, float y, float angle) {
+    memset(b, 0, sizeof *b);
+    b->p = v2(x, y);
+    b->q = rot(angle);
+    b->a = b->a0 = angle;
+    b->awake = 1;
+}
+
+static void body_set_awake(Body* b, int flag) {
+    if (flag) {
+        if (!b->awake) { b->awake = 1; b->sleep_time = 0.f; }
+    } else {
+        b->awake = 0; b->sleep_time = 0.f;
+        b->v = v2(0.f, 0.f); b->w = 0.f; b->force = v2(0.f, 0.f); b->torque = 0.f;
+    }
+}
+
+static float clampf(float a, float lo, float hi) { return a < lo ? lo : (a > hi ? hi : a); }
+
+/* b2Mat33::Solve33 / Solve22 with K stored as columns ex, ey, ez */
+static void solve33(float K[3][3], const float b[3], float out[3]) {
+    const float* ex = K[0]; const float* ey = K[1]; const float* ez = K[2];
+    /* det = dot(ex, cross(ey, ez)) */
+    float cx = ey[1] * ez[2] - ey[2] * ez[1], cy = ey[2] * ez[0] - ey[0] * ez[2], cz = ey[0] * ez[1] - ey[1] * ez[0];
+    float det = ex[0] * cx + ex[1] * cy + ex[2] * cz;
+    if (det != 0.0f) det = 1.0f / det;
+    /* x = det * dot(b, cross(ey, ez)) */
+    out[0] = det * (b[0] * cx + b[1] * cy + b[2] * cz);
+    /* y = det * dot(ex, cross(b, ez)) */
+    float bx = b[1] * ez[2] - b[2] * ez[1], by = b[2] * ez[0] - b[0] * ez[2], bz = b[0] * ez[1] - b[1] * ez[0];
+    out[1] = det * (ex[0] * bx + ex[1] * by + ex[2] * bz);
+    /* z = det * dot(ex, cross(ey, b)) */
+    float dx = ey[1] * b[2] - ey[2] * b[1], dy = ey[2] * b[0] - ey[0] * b[2], dz = ey[0] * b[1] - ey[1] * b[0];
+    out[2] = det * (ex[0] * dx + ex[1] * dy + ex[2] * dz);
+}
+
+static V2 solve22(float K[3][3], V2 b) {
+    float a11 = K[0][0], a12 = K[1][0], a21 = K[0][1], a22 = K[1][1];
+    float det = a11 * a22 - a12 * a21;
+    if (det != 0.0f) det = 1.0f / det;
+    return v2(det * (a22 * b.x - a12 * b.y), det * (a11 * b.y - a21 * b.x));
+}
+
+/* b2RevoluteJoint::InitVelocityConstraints */
+static void joint_init_velocity(RevJoint* j, const Body* bodies, V2* c, float* a, V2* v, float* w, float dt_ratio) {
+    const Body* A = &bodies[j->a]; const Body* B = &bodies[j->b];
+    j->lcA = A->local_center; j->lcB = B->local_center;
+    j->mA = A->inv_mass; j->mB = B->inv_mass; j->iA = A->inv_I; j->iB = B->inv_I;
+    float aA = a[j->a], aB = a[j->b];
+    V2 vA = v[j->a], vB = v[j->b];
+    float wA = w[j->a], wB = w[j->b];
+    (void)c;
+    Rot qA = rot(aA), qB = rot(aB);
+    j->rA = rmul(qA, vsub(j->local_anchor_a, j->lcA));
+    j->rB = rmul(qB, vsub(j->local_anchor_b, j->lcB));
+    float mA = j->mA, mB = j->mB, iA = j->iA, iB = j->iB;
+    int fixed_rotation = (iA + iB == 0.0f);
+    j->K[0][0] = mA + mB + j->rA.y * j->rA.y * iA + j->rB.y * j->rB.y * iB;
+    j->K[1][0] = -j->rA.y * j->rA.x * iA - j->rB.y * j->rB.x * iB;
+    j->K[2][0] = -j->rA.y * iA - j->rB.y * iB;
+    j->K[0][1] = j->K[1][0];
+    j->K[1][1] = mA + mB + j->rA.x * j->rA.x * iA + j->rB.x * j->rB.x * iB;
+    j->K[2][1] = j->rA.x * iA + j->rB.x * iB;
+    j->K[0][2] = j->K[2][0];
+    j->K[1][2] = j->K[2][1];
+    j->K[2][2] = iA + iB;
+    j->motor_mass = iA + iB;
+    if (j->motor_mass > 0.0f) j->motor_mass = 1.0f / j->motor_mass;
+    if (!j->enable_motor || fixed_rotation) j->motor_impulse = 0.0f;
+    if (j->enable_limit && !fixed_rotation) {
+        float joint_angle = aB - aA - j->reference_angle;
+        if (fabsf(j->upper - j->lower) < 2.0f * B2_ANGULAR_SLOP) {
+            j->limit_state = 3;
+        } else if (joint_angle <= j->lower) {
+            if (j->limit_state != 1) j->impulse[2] = 0.0f;
+            j->limit_state = 1;
+        } else if (joint_angle >= j->upper) {
+            if (j->limit_state != 2) j->impulse[2] = 0.0f;
+            j->limit_state = 2;
+        } else {
+            j->limit_state = 0;
+            j->impulse[2] = 0.0f;
+        }
+    } else {
+        j->limit_state = 0;
+    }
+    /* warm starting (always on in b2World::Step) */
+    j->impulse[0] *= dt_ratio; j->impulse[1] *= dt_ratio; j->impulse[2] *= dt_ratio;
+    j->motor_impulse *= dt_ratio;
+    V2 P = v2(j->impulse[0], j->impulse[1]);
+    vA = vsub(vA, vscale(mA, P));
+    wA -= iA * (vcross(j->rA, P) + j->motor_impulse + j->impulse[2]);
+    vB = vadd(vB, vscale(mB, P));
+    wB += iB * (vcross(j->rB, P) + j->motor_impulse + j->impulse[2]);
+    v[j->a] = vA; w[j->a] = wA; v[j->b] = vB; w[j->b] = wB;
+}
+
+/* b2RevoluteJoint::SolveVelocityConstraints */
+static void joint_solve_velocity(RevJoint* j, V2* v, float* w, float dt) {
+    V2 vA = v[j->a], vB = v[j->b];
+    float wA = w[j->a], wB = w[j->b];
+    float mA = j->mA, mB = j->mB, iA = j->iA, iB = j->iB;
+    int fixed_rotation = (iA + iB == 0.0f);
+    if (j->enable_motor && j->limit_state != 3 && !fixed_rotation) {
+        float Cdot = wB - wA - j->motor_speed;
+        float impulse = -j->motor_mass * Cdot;
+        float old = j->motor_impulse;
+        float max_impulse = dt * j->max_motor_torque;
+        j->motor_impulse = clampf(old + impulse, -max_impulse, max_impulse);
+        impulse = j->motor_impulse - old;
+        wA -= iA * impulse;
+        wB += iB * impulse;
+    }
+    if (j->enable_limit && j->limit_state != 0 && !fixed_rotation) {
+        V2 Cdot1 = vsub(vsub(vadd(vB, cross_sv(wB, j->rB)), vA), cross_sv(wA, j->rA));
+        float Cdot2 = wB - wA;
+        float rhs[3] = {Cdot1.x, Cdot1.y, Cdot2}, imp[3];
+        solve33(j->K, rhs, imp);
+        imp[0] = -imp[0]; imp[1] = -imp[1]; imp[2] = -imp[2];
+        if (j->limit_state == 3) {
+            j->impulse[0] += imp[0]; j->impulse[1] += imp[1]; j->impulse[2] += imp[2];
+        } else if (j->limit_state == 1) {
+            float ni = j->impulse[2] + imp[2];
+            if (ni < 0.0f) {
+                V2 r = v2(-Cdot1.x + j->impulse[2] * j->K[2][0], -Cdot1.y + j->impulse[2] * j->K[2][1]);
+                V2 red = solve22(j->K, r);
+                imp[0] = red.x; imp[1] = red.y; imp[2] = -j->impulse[2];
+                j->impulse[0] += red.x; j->impulse[1] += red.y; j->impulse[2] = 0.0f;
+            } else {
+                j->impulse[0] += imp[0]; j->impulse[1] += imp[1]; j->impulse[2] += imp[2];
+            }
+        } else {
+            float ni = j->impulse[2] + imp[2];
+            if (ni > 0.0f) {
+                V2 r = v2(-Cdot1.x + j->impulse[2] * j->K[2][0], -Cdot1.y + j->impulse[2] * j->K[2][1]);
+                V2 red = solve22(j->K, r);
+                imp[0] = red.x; imp[1] = red.y; imp[2] = -j->impulse[2];
+                j->impulse[0] += red.x; j->impulse[1] += red.y; j->impulse[2] = 0.0f;
+            } else {
+                j->impulse[0] += imp[0]; j->impulse[1] += imp[1]; j->impulse[2] += imp[2];
+            }
+        }
+        V2 P = v2(imp[0], imp[1]);
+        vA = vsub(vA, vscale(mA, P));
+        wA -= iA * (vcross(j->rA, P) + imp[2]);
+        vB = vadd(vB, vscale(mB, P));
+        wB += iB * (vcross(j->rB, P) + imp[2]);
+    } else {
+        V2 Cdot = vsub(vsub(vadd(vB, cross_sv(wB, j->rB)), vA), cross_sv(wA, j->rA));
+        V2 imp = solve22(j->K, v2(-Cdot.x, -Cdot.y));
+        j->impulse[0] += imp.x; j->impulse[1] += imp.y;
+        vA = vsub(vA, vscale(mA, imp));
+        wA -= iA * vcross(j->rA, imp);
+        vB = vadd(vB, vscale(mB, imp));
+        wB += iB * vcross(j->rB, imp);
+    }
+    v[j->a] = vA; w[j->a] = wA; v[j->b] = vB; w[j->b] = wB;
+}
+
+/* b2RevoluteJoint::SolvePositionConstraints */
+static int joint_solve_position(RevJoint* j, V2* c, float* a) {
+    V2 cA = c[j->a], cB = c[j->b];
+    float aA = a[j->a], aB = a[j->b];
+    float angular_error = 0.0f, position_error;
+    int fixed_rotation = (j->iA + j->iB == 0.0f);
+    if (j->enable_limit && j->limit_state != 0 && !fixed_rotation) {
+        float angle = aB - aA - j->reference_angle, limit_impulse = 0.0f;
+        if (j->limit_state == 3) {
+            float C = clampf(angle - j->lower, -B2_MAX_ANGULAR_CORRECTION, B2_MAX_ANGULAR_CORRECTION);
+            limit_impulse = -j->motor_mass * C;
+            angular_error = fabsf(C);
+        } else if (j->limit_state == 1) {
+            float C = angle - j->lower;
+            angular_error = -C;
+            C = clampf(C + B2_ANGULAR_SLOP, -B2_MAX_ANGULAR_CORRECTION, 0.0f);
+            limit_impulse = -j->motor_mass * C;
+        } else {
+            float C = angle - j->upper;
+            angular_error = C;
+            C = clampf(C - B2_ANGULAR_SLOP, 0.0f, B2_MAX_ANGULAR_CORRECTION);
+            limit_impulse = -j->motor_mass * C;
+        }
+        aA -= j->iA * limit_impulse;
+        aB += j->iB * limit_impulse;
+    }
+    {
+        Rot qA = rot(aA), qB = rot(aB);
+        V2 rA = rmul(qA, vsub(j->local_anchor_a, j->lcA));
+        V2 rB = rmul(qB, vsub(j->local_anchor_b, j->lcB));
+        V2 C = vsub(vsub(vadd(cB, rB), cA), rA);
+        position_error = sqrtf(vdot(C, C));
+        float mA = j->mA, mB = j->mB, iA = j->iA, iB = j->iB;
+        float K[3][3];
+        K[0][0] = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
+        K[0][1] = -iA * rA.x * rA.y - iB * rB.x * rB.y;
+        K[1][0] = K[0][1];
+        K[1][1] = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
+        V2 imp = solve22(K, C);
+        imp = v2(-imp.x, -imp.y);
+        cA = vsub(cA, vscale(mA, imp));
+        aA -= iA * vcross(rA, imp);
+        cB = vadd(cB, vscale(mB, imp));
+        aB += iB * vcross(rB, imp);
+    }
+    c[j->a] = cA; a[j->a] = aA; c[j->b] = cB; a[j->b] = aB;
+    return position_error <= B2_LINEAR_SLOP && angular_error <= B2_ANGULAR_SLOP;
+}
+
+/* One island = bodies[0..nb) joined by joints[0..nj) (already in island order).
+ * b2Island::Solve with gravity 0, no damping, no contacts. */
+static void island_solve(Body* bodies, int nb, RevJoint* joints, int nj, float h, float dt_ratio, int vel_iters,
+                         int pos_iters) {
+    V2 c[8], v[8];
+    float a[8], w[8];
+    for (int i = 0; i < nb; ++i) {
+        Body* b = &bodies[i];
+        b->c0 = b->c; b->a0 = b->a;
+        v[i] = vadd(b->v, vscale(h, vscale(b->inv_mass, b->force)));
+        w[i] = b->w + h * b->inv_I * b->torque;
+        v[i] = vscale(1.0f / (1.0f + h * 0.0f), v[i]);
+        w[i] *= 1.0f / (1.0f + h * 0.0f);
+        c[i] = b->c; a[i] = b->a;
+    }
+    for (int k = 0; k < nj; ++k) joint_init_velocity(&joints[k], bodies, c, a, v, w, dt_ratio);
+    for (int it = 0; it < vel_iters; ++it)
+        for (int k = 0; k < nj; ++k) joint_solve_velocity(&joints[k], v, w, h);
+    for (int i = 0; i < nb; ++i) {
+        V2 tr = vscale(h, v[i]);
+        if (vdot(tr, tr) > B2_MAX_TRANSLATION * B2_MAX_TRANSLATION) v[i] = vscale(B2_MAX_TRANSLATION / sqrtf(vdot(tr, tr)), v[i]);
+        float r = h * w[i];
+        if (r * r > B2_MAX_ROTATION * B2_MAX_ROTATION) w[i] *= B2_MAX_ROTATION / fabsf(r);
+        c[i] = vadd(c[i], vscale(h, v[i]));
+        a[i] += h * w[i];
+    }
+    int position_solved = 0;
+    for (int it = 0; it < pos_iters; ++it) {
+        int ok = 1;
+        for (int k = 0; k < nj; ++k) ok = joint_solve_position(&joints[k], c, a) && ok;
+        if (ok) { position_solved = 1; break; }
+    }
+    for (int i = 0; i < nb; ++i) {
+        Body* b = &bodies[i];
+        b->c = c[i]; b->a = a[i]; b->v = v[i]; b->w = w[i];
+        b->q = rot(b->a);
+        b->p = vsub(b->c, rmul(b->q, b->local_center));
+    }
+    /* sleeping (allowSleep defaults to true) */
+    float min_sleep = 3.4e38f;
+    for (int i = 0; i < nb; ++i) {
+        Body* b = &bodies[i];
+        if (b->w * b->w > B2_ANGULAR_SLEEP_TOL * B2_ANGULAR_SLEEP_TOL ||
+            vdot(b->v, b->v) > B2_LINEAR_SLEEP_TOL * B2_LINEAR_SLEEP_TOL) {
+            b->sleep_time = 0.0f;
+            min_sleep = 0.0f;
+        } else {
+            b->sleep_time += h;
+            if (b->sleep_time < min_sleep) min_sleep = b->sleep_time;
+        }
+    }
+    if (min_sleep >= B2_TIME_TO_SLEEP && position_solved)
+        for (int i = 0; i < nb; ++i) body_set_awake(&bodies[i], 0);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* exported low-level hooks for the Box2D stand-in (oracle/ref_shim/Box2D): it keeps the bodies
+ * and joints in flat arrays of these structs and calls back into the solver above.             */
+
+int car_oracle_sizeof_body(void) { return (int)sizeof(Body); }
+int car_oracle_sizeof_joint(void) { return (int)sizeof(RevJoint); }
+void car_oracle_body_init(Body* b, float x, float y, float angle) { body_init(b, x, y, angle); }
+void car_oracle_body_set_mass(Body* b, const float* polys_xy, const int* counts, const float* density, int n_polys) {
+    body_set_mass(b, (const V2*)polys_xy, counts, density, n_polys);
+}
+void car_oracle_island_solve(Body* bodies, int nb, RevJoint* joints, int nj, float h, float dt_ratio, int vel_iters,
+                             int pos_iters) {
+    island_solve(bodies, nb, joints, nj, h, dt_ratio, vel_iters, pos_iters);
+}
+
+/* max separation of convex polygon B from the faces of convex polygon A (both CCW, world coords) */
+static float max_separation(const V2* A, int na, const V2* B, int nb) {
+    float best = -3.4e38f;
+    for (int i = 0; i < na; ++i) {
+        V2 e = vsub(A[(i + 1) % na], A[i]);
+        float len = sqrtf(vdot(e, e));
+        if (len < 1e-12f) continue;
+        V2 n = v2(e.y / len, -e.x / len);   /* outward normal of a CCW polygon */
+        float mn = 3.4e38f;
+        for (int k = 0; k < nb; ++k) {
+            float d = vdot(n, vsub(B[k], A[i]));
+            if (d < mn) mn = d;
+        }
+        if (mn > best) best = mn;
+    }
+    return best;
+}
+
+/* sensor overlap used for wheel-tile contacts: polygons (with their b2_polygonRadius skins) touch */
+int car_oracle_polys_touch(const float* a_xy, int na, const float* b_xy, int nb) {
+    const V2* A = (const V2*)a_xy; const V2* B = (const V2*)b_xy;
+    float s1 = max_separation(A, na, B, nb), s2 = max_separation(B, nb, A, na);
+    float s = s1 > s2 ? s1 : s2;
+    return s < 2.0f * B2_POLYGON_RADIUS;
+}
+
+/* b2PolygonShape::Set: convex hull (gift wrapping) of up to 8 points, CCW; returns the count */
+int car_oracle_convex_hull(const float* in_xy, int n, float* out_xy) {
+    V2 ps[8];
+    int m = 0;
+    for (int i = 0; i < n && i < 8; ++i) {   /* weld points closer than 0.5 * linearSlop */
+        V2 p = v2(in_xy[2 * i], in_xy[2 * i + 1]);
+        int unique = 1;
+        for (int k = 0; k < m; ++k) {
+            V2 d = vsub(p, ps[k]);
+            if (vdot(d, d) < 0.5f * B2_LINEAR_SLOP * 0.5f * B2_LINEAR_SLOP) { unique = 0; break; }
+        }
+        if (unique) ps[m++] = p;
+    }
+    if (m < 3) return 0;
+    int i0 = 0;
+    for (int i = 1; i < m; ++i)
+        if (ps[i].x > ps[i0].x || (ps[i].x == ps[i0].x && ps[i].y < ps[i0].y)) i0 = i;
+    int hull[8], cnt = 0, ih = i0;
+    for (;;) {
+        hull[cnt] = ih;
+        int ie = 0;
+        for (int j = 1; j < m; ++j) {
+            if (ie == ih) { ie = j; continue; }
+            V2 r = vsub(ps[ie], ps[hull[cnt]]), v = vsub(ps[j], ps[hull[cnt]]);
+            float c = vcross(r, v);
+            if (c < 0.0f) ie = j;
+            if (c == 0.0f && vdot(v, v) > vdot(r, r)) ie = j;
+        }
+        ++cnt;
+        ih = ie;
+        if (ie == i0) break;
+    }
+    for (int i = 0; i < cnt; ++i) { out_xy[2 * i] = ps[hull[i]].x; out_xy[2 * i + 1] = ps[hull[i]].y; }
+    return cnt;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* track generator: CarRacing._create_track, car_racing_multi_players.py:262-452.  Pure float64  */
+/* Python math; `draws` are the 2*CHECKPOINTS np_random.uniform values of this attempt in draw   */
+/* order (noise_c, rad_c per checkpoint).  Returns the number of track points, 0 on failure.     */
+
+typedef struct { double alpha, beta, x, y; } TrackPt;
+
+int car_oracle_create_track(const double* draws, double* out /* [MAX_TRACK][4] */, int* border_out) {
+    double cp_alpha[CHECKPOINTS], cp_x[CHECKPOINTS], cp_y[CHECKPOINTS];
+    double start_alpha = 0.0;
+    for (int c = 0; c < CHECKPOINTS; ++c) {
+        double noise = draws[2 * c];
+        double alpha = 2 * M_PI * c / CHECKPOINTS + noise;
+        double rad = draws[2 * c + 1];
+        if (c == 0) { alpha = 0; rad = 1.5 * TRACK_RAD; }
+        if (c == CHECKPOINTS - 1) {
+            alpha = 2 * M_PI * c / CHECKPOINTS;
+            start_alpha = 2 * M_PI * (-0.5) / CHECKPOINTS;
+            rad = 1.5 * TRACK_RAD;
+        }
+        cp_alpha[c] = alpha; cp_x[c] = rad * cos(alpha); cp_y[c] = rad * sin(alpha);
+    }
+    static __thread TrackPt raw[MAX_TRACK_RAW];
+    int n_raw = 0;
+    double x = 1.5 * TRACK_RAD, y = 0, beta = 0;
+    int dest_i = 0, laps = 0, no_freeze = 2500, visited_other_side = 0;
+    for (;;) {
+        double alpha = atan2(y, x);
+        if (visited_other_side && alpha > 0) { laps += 1; visited_other_side = 0; }
+        if (alpha < 0) { visited_other_side = 1; alpha += 2 * M_PI; }
+        double dest_alpha, dest_x, dest_y;
+        for (;;) {
+            int failed = 1;
+            for (;;) {
+                dest_alpha = cp_alpha[dest_i % CHECKPOINTS]; dest_x = cp_x[dest_i % CHECKPOINTS]; dest_y = cp_y[dest_i % CHECKPOINTS];
+                if (alpha <= dest_alpha) { failed = 0; break; }
+                dest_i += 1;
+                if (dest_i % CHECKPOINTS == 0) break;
+            }
+            if (!failed) break;
+            alpha -= 2 * M_PI;
+        }
+        double r1x = cos(beta), r1y = sin(beta);
+        double p1x = -r1y, p1y = r1x;
+        double dest_dx = dest_x - x, dest_dy = dest_y - y;
+        double proj = r1x * dest_dx + r1y * dest_dy;
+        while (beta - alpha > 1.5 * M_PI) beta -= 2 * M_PI;
+        while (beta - alpha < -1.5 * M_PI) beta += 2 * M_PI;
+        double prev_beta = beta;
+        proj *= SCALE;
+        if (proj > 0.3) beta -= fmin(TRACK_TURN_RATE, fabs(0.001 * proj));
+        if (proj < -0.3) beta += fmin(TRACK_TURN_RATE, fabs(0.001 * proj));
+        x += p1x * TRACK_DETAIL_STEP;
+        y += p1y * TRACK_DETAIL_STEP;
+        if (n_raw >= MAX_TRACK_RAW) return 0;
+        raw[n_raw].alpha = alpha; raw[n_raw].beta = prev_beta * 0.5 + beta * 0.5; raw[n_raw].x = x; raw[n_raw].y = y;
+        n_raw++;
+        if (laps > 4) break;
+        no_freeze -= 1;
+        if (no_freeze == 0) break;
+    }
+    int i1 = -1, i2 = -1, i = n_raw;
+    for (;;) {
+        i -= 1;
+        if (i == 0) return 0;
+        int pass = raw[i].alpha > start_alpha && raw[i - 1].alpha <= start_alpha;
+        if (pass && i2 == -1) i2 = i;
+        else if (pass && i1 == -1) { i1 = i; break; }
+    }
+    int n = (i2 - 1) - i1;
+    if (n <= 0 || n > MAX_TRACK) return 0;
+    const TrackPt* t = raw + i1;
+    double fb = t[0].beta, fpx = cos(fb), fpy = sin(fb);
+    double dx = fpx * (t[0].x - t[n - 1].x), dy = fpy * (t[0].y - t[n - 1].y);
+    if (sqrt(dx * dx + dy * dy) > TRACK_DETAIL_STEP) return 0;
+    /* red-white border on hard turns */
+    int border[MAX_TRACK];
+    for (int k = 0; k < n; ++k) {
+        int good = 1, oneside = 0;
+        for (int neg = 0; neg < BORDER_MIN_COUNT; ++neg) {
+            double b1 = t[((k - neg - 0) % n + n) % n].beta, b2 = t[((k - neg - 1) % n + n) % n].beta;
+            good &= fabs(b1 - b2) > TRACK_TURN_RATE * 0.2;
+            oneside += (b1 - b2 > 0) - (b1 - b2 < 0);
+        }
+        good &= abs(oneside) == BORDER_MIN_COUNT;
+        border[k] = good;
+    }
+    for (int k = 0; k < n; ++k)
+        for (int neg = 0; neg < BORDER_MIN_COUNT; ++neg) border[((k - neg) % n + n) % n] |= border[k];
+    for (int k = 0; k < n; ++k) {
+        out[4 * k] = t[k].alpha; out[4 * k + 1] = t[k].beta; out[4 * k + 2] = t[k].x; out[4 * k + 3] = t[k].y;
+        if (border_out) border_out[k] = border[k];
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* car + env                                                                                    */
+
+static const float HULL_POLYS[4][8][2] = {
+    {{-60, +130}, {+60, +130}, {+60, +110}, {-60, +110}},
+    {{-15, +120}, {+15, +120}, {+20, +20}, {-20, 20}},
+    {{+25, +20}, {+50, -10}, {+50, -40}, {+20, -90}, {-20, -90}, {-50, -40}, {-50, -10}, {-25, +20}},
+    {{-50, -120}, {+50, -120}, {+50, -90}, {-50, -90}}};
+static const int HULL_COUNTS[4] = {4, 4, 8, 4};
+static const float WHEELPOS[4][2] = {{-55, +80}, {+55, +80}, {-55, -82}, {+55, -82}};
+
+typedef struct {
+    Body body[5];                /* island order: wheel3, hull, wheel0, wheel1, wheel2 (b2World::Solve DFS) */
+    RevJoint joint[4];           /* island order: joint3, joint2, joint1, joint0 */
+    double gas[4], brake[4], steer[4], phase[4], omega[4];
+    uint32_t touching[4][MAX_TRACK / 32];   /* wheel.tiles */
+    int n_touching[4];
+    uint32_t visited[MAX_TRACK / 32];       /* tile.road_visited[car] */
+    int last_block, has_block;              /* block_visited[car][-1] */
+    int tile_visited_count;
+    double reward, prev_reward;
+    int done;
+} Car;
+
+static const int BODY_OF_WHEEL[4] = {2, 3, 4, 0};   /* wheel k -> index in Car.body */
+#define HULL_BODY 1
+static const int JOINT_OF_WHEEL[4] = {3, 2, 1, 0};
+
+typedef struct {
+    int n_cars, action_repeat;
+    int n_track;
+    double track[MAX_TRACK][4];
+    int border[MAX_TRACK];
+    float tile_poly[MAX_TRACK][5][2]; int tile_n[MAX_TRACK];   /* convex hulls, CCW */
+    float tile_raw[MAX_TRACK][5][2];                            /* as listed (draw order) */
+    float tile_aabb[MAX_TRACK][4];
+    float kerb[MAX_TRACK][4][2];
+    Car car[MAX_CARS];
+    int step_count;
+    float inv_dt0;
+    uint8_t obs[MAX_CARS][STATE_H * STATE_W];
+    const uint8_t* glyphs;      /* [11][8][4] bitmaps of "0123456789-" (non-AA COMIC 5 px) then [11] advances; may be NULL */
+} CarEnv;
+
+static void wheel_world_poly(const Body* b, V2 out[4]) {
+    const float hw = WHEEL_W * (float)SIZE, hr = WHEEL_R * (float)SIZE;
+    /* CCW order */
+    V2 loc[4] = {{-hw, -hr}, {+hw, -hr}, {+hw, +hr}, {-hw, +hr}};
+    for (int i = 0; i < 4; ++i) out[i] = vadd(rmul(b->q, loc[i]), b->p);
+}
+
+/* Car.__init__, car_dynamics.py:55-129 */
+static void car_create(Car* c, double init_angle, double init_x, double init_y, int birth_place_index) {
+    memset(c, 0, sizeof *c);
+    init_x -= birth_place_index % 2 * 5;
+    init_y -= floor(birth_place_index / 2) * 10;
+    Body* hull = &c->body[HULL_BODY];
+    body_init(hull, (float)init_x, (float)init_y, (float)init_angle);
+    V2 polys[20];
+    float dens[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+    int at = 0, counts[4];
+    for (int k = 0; k < 4; ++k) {
+        float raw[16], hullpts[16];
+        for (int i = 0; i < HULL_COUNTS[k]; ++i) {
+            raw[2 * i] = (float)(HULL_POLYS[k][i][0] * SIZE);
+            raw[2 * i + 1] = (float)(HULL_POLYS[k][i][1] * SIZE);
+        }
+        int n = car_oracle_convex_hull(raw, HULL_COUNTS[k], hullpts);
+        for (int i = 0; i < n; ++i) polys[at + i] = v2(hullpts[2 * i], hullpts[2 * i + 1]);
+        counts[k] = n;
+        at += n;
+    }
+    body_set_mass(hull, polys, counts, dens, 4);
+    for (int k = 0; k < 4; ++k) {
+        Body* w = &c->body[BODY_OF_WHEEL[k]];
+        /* position = (init_x + wx*SIZE, init_y + wy*SIZE): NOT rotated by init_angle (car_dynamics.py:90) */
+        body_init(w, (float)(init_x + WHEELPOS[k][0] * SIZE), (float)(init_y + WHEELPOS[k][1] * SIZE), (float)init_angle);
+        const float hw = (float)(WHEEL_W * SIZE), hr = (float)(WHEEL_R * SIZE);
+        V2 box[4] = {{+hw, -hr}, {+hw, +hr}, {-hw, +hr}, {-hw, -hr}};   /* hull order of b2PolygonShape::Set */
+        float d = 0.1f;
+        int cnt = 4;
+        body_set_mass(w, box, &cnt, &d, 1);
+        RevJoint* j = &c->joint[JOINT_OF_WHEEL[k]];
+        memset(j, 0, sizeof *j);
+        j->a = HULL_BODY; j->b = BODY_OF_WHEEL[k];
+        j->local_anchor_a = v2((float)(WHEELPOS[k][0] * SIZE), (float)(WHEELPOS[k][1] * SIZE));
+        j->local_anchor_b = v2(0.f, 0.f);
+        j->enable_motor = 1; j->enable_limit = 1;
+        j->max_motor_torque = (float)(180 * 900 * SIZE * SIZE);
+        j->motor_speed = 0.f; j->lower = -0.4f; j->upper = +0.4f;
+        j->reference_angle = 0.f;
+    }
+    c->last_block = 0; c->has_block = 0;
+}
+
+static double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static double signd(double v) { return (v > 0) - (v < 0); }
+
+/* Car.gas / brake / steer, car_dynamics.py:131-157 */
+static void car_controls(Car* c, double steer, double gas, double brake) {
+    c->steer[0] = steer; c->steer[1] = steer;
+    gas = clipd(gas, 0, 1);
+    for (int k = 2; k < 4; ++k) {
+        double diff = gas - c->gas[k];
+        if (diff > 0.1) diff = 0.1;
+        c->gas[k] += diff;
+    }
+    for (int k = 0; k < 4; ++k) c->brake[k] = brake;
+}
+
+/* Car.step, car_dynamics.py:159-234 (skid particles are render-only and omitted) */
+static void car_step(Car* c, double dt) {
+    for (int k = 0; k < 4; ++k) {
+        Body* w = &c->body[BODY_OF_WHEEL[k]];
+        Body* hull = &c->body[HULL_BODY];
+        RevJoint* j = &c->joint[JOINT_OF_WHEEL[k]];
+        double joint_angle = (double)(w->a - hull->a - j->reference_angle);
+        double dir = signd(c->steer[k] - joint_angle);
+        double val = fabs(c->steer[k] - joint_angle);
+        j->motor_speed = (float)(dir * fmin(50.0 * val, 3.0));
+        /* joint.motorSpeed setter wakes both bodies (b2RevoluteJoint::SetMotorSpeed) */
+        body_set_awake(hull, 1); body_set_awake(w, 1);
+        double friction_limit = FRICTION_LIMIT * 0.6;
+        if (c->n_touching[k] > 0) friction_limit = fmax(friction_limit, FRICTION_LIMIT * 1.0);
+        V2 forw = rmul(w->q, v2(0.f, 1.f)), side = rmul(w->q, v2(1.f, 0.f));
+        double vx = w->v.x, vy = w->v.y;
+        double vf = (double)forw.x * vx + (double)forw.y * vy;
+        double vs = (double)side.x * vx + (double)side.y * vy;
+        c->omega[k] += dt * ENGINE_POWER * c->gas[k] / WHEEL_MOMENT_OF_INERTIA / (fabs(c->omega[k]) + 5.0);
+        if (c->brake[k] >= 0.9) {
+            c->omega[k] = 0;
+        } else if (c->brake[k] > 0) {
+            double bdir = -signd(c->omega[k]);
+            double bval = 15 * c->brake[k];
+            if (fabs(bval) > fabs(c->omega[k])) bval = fabs(c->omega[k]);
+            c->omega[k] += bdir * bval;
+        }
+        c->phase[k] += c->omega[k] * dt;
+        double vr = c->omega[k] * (WHEEL_R * SIZE);
+        double f_force = -vf + vr, p_force = -vs;
+        f_force *= 205000 * SIZE * SIZE;
+        p_force *= 205000 * SIZE * SIZE;
+        double force = sqrt(f_force * f_force + p_force * p_force);
+        if (fabs(force) > friction_limit) {
+            f_force /= force; p_force /= force;
+            force = friction_limit;
+            f_force *= force; p_force *= force;
+        }
+        c->omega[k] -= dt * f_force * (WHEEL_R * SIZE) / WHEEL_MOMENT_OF_INERTIA;
+        /* ApplyForceToCenter((..), True): python floats -> b2Vec2 float32 */
+        float fx = (float)(p_force * (double)side.x + f_force * (double)forw.x);
+        float fy = (float)(p_force * (double)side.y + f_force * (double)forw.y);
+        if (!w->awake) body_set_awake(w, 1);
+        w->force = vadd(w->force, v2(fx, fy));
+    }
+}
+
+/* FrictionDetector._contact (begin) for wheel k of car c touching tile t, :111-153 */
+static void contact_begin(CarEnv* e, Car* c, int k, int t) {
+    c->touching[k][t >> 5] |= 1u << (t & 31);
+    c->n_touching[k] += 1;
+    if (!((c->visited[t >> 5] >> (t & 31)) & 1u)) {
+        int last_blk = c->has_block ? c->last_block : 0;
+        if (t - last_blk < 50) {
+            c->last_block = t; c->has_block = 1;
+            c->reward += 1000.0 / e->n_track;
+        }
+        c->visited[t >> 5] |= 1u << (t & 31);
+        c->tile_visited_count += 1;
+    }
+}
+
+static void contact_end(Car* c, int k, int t) {
+    c->touching[k][t >> 5] &= ~(1u << (t & 31));
+    c->n_touching[k] -= 1;
+}
+
+/* b2ContactManager::Collide for the wheel-tile sensor pairs (see header for the simplification) */
+static void world_collide(CarEnv* e) {
+    for (int ci = 0; ci < e->n_cars; ++ci) {
+        Car* c = &e->car[ci];
+        for (int k = 0; k < 4; ++k) {
+            const Body* w = &c->body[BODY_OF_WHEEL[k]];
+            V2 wp[4];
+            wheel_world_poly(w, wp);
+            float minx = wp[0].x, maxx = wp[0].x, miny = wp[0].y, maxy = wp[0].y;
+            for (int i = 1; i < 4; ++i) {
+                if (wp[i].x < minx) minx = wp[i].x; if (wp[i].x > maxx) maxx = wp[i].x;
+                if (wp[i].y < miny) miny = wp[i].y; if (wp[i].y > maxy) maxy = wp[i].y;
+            }
+            const float m = 2.0f * B2_POLYGON_RADIUS;
+            for (int t = 0; t < e->n_track; ++t) {
+                int was = (c->touching[k][t >> 5] >> (t & 31)) & 1u;
+                int now = 0;
+                const float* bb = e->tile_aabb[t];
+                if (!(bb[0] > maxx + m || bb[2] < minx - m || bb[1] > maxy + m || bb[3] < miny - m))
+                    now = car_oracle_polys_touch((const float*)wp, 4, &e->tile_poly[t][0][0], e->tile_n[t]);
+                if (now && !was) contact_begin(e, c, k, t);
+                else if (!now && was) contact_end(c, k, t);
+            }
+        }
+    }
+}
+
+/* b2World::Step(1/FPS, 180, 60) */
+static void world_step(CarEnv* e, float dt) {
+    world_collide(e);
+    float dt_ratio = e->inv_dt0 * dt;
+    for (int ci = 0; ci < e->n_cars; ++ci) {
+        Car* c = &e->car[ci];
+        int any_awake = 0;
+        for (int i = 0; i < 5; ++i) any_awake |= c->body[i].awake;
+        if (any_awake) {
+            for (int i = 0; i < 5; ++i) body_set_awake(&c->body[i], 1);   /* island bodies are woken */
+            island_solve(c->body, 5, c->joint, 4, dt, dt_ratio, 6 * 30, 2 * 30);
+        }
+        for (int i = 0; i < 5; ++i) { c->body[i].force = v2(0.f, 0.f); c->body[i].torque = 0.f; }   /* ClearForces */
+    }
+    e->inv_dt0 = 1.0f / dt;
+}
+
+/* tiles from the track: _create_track tail, :399-445 */
+static void build_tiles(CarEnv* e) {
+    int n = e->n_track;
+    for (int i = 0; i < n; ++i) {
+        const double* p1 = e->track[i];
+        const double* p2 = e->track[(i - 1 + n) % n];
+        double b1 = p1[1], x1 = p1[2], y1 = p1[3], b2 = p2[1], x2 = p2[2], y2 = p2[3];
+        double v[5][2] = {
+            {x1 - TRACK_WIDTH * cos(b1), y1 - TRACK_WIDTH * sin(b1)},
+            {x1 - TRACK_WIDTH / 2 * cos(b1 - M_PI / 2), y1 - TRACK_WIDTH / 2 * sin(b1 - M_PI / 2)},
+            {x1 + TRACK_WIDTH * cos(b1), y1 + TRACK_WIDTH * sin(b1)},
+            {x2 + TRACK_WIDTH * cos(b2), y2 + TRACK_WIDTH * sin(b2)},
+            {x2 - TRACK_WIDTH * cos(b2), y2 - TRACK_WIDTH * sin(b2)}};
+        float raw[10], hull[16];
+        for (int k = 0; k < 5; ++k) {
+            raw[2 * k] = (float)v[k][0]; raw[2 * k + 1] = (float)v[k][1];
+            e->tile_raw[i][k][0] = raw[2 * k]; e->tile_raw[i][k][1] = raw[2 * k + 1];
+        }
+        int cnt = car_oracle_convex_hull(raw, 5, hull);
+        e->tile_n[i] = cnt;
+        float minx = 3e38f, miny = 3e38f, maxx = -3e38f, maxy = -3e38f;
+        for (int k = 0; k < cnt; ++k) {
+            e->tile_poly[i][k][0] = hull[2 * k]; e->tile_poly[i][k][1] = hull[2 * k + 1];
+            if (hull[2 * k] < minx) minx = hull[2 * k]; if (hull[2 * k] > maxx) maxx = hull[2 * k];
+            if (hull[2 * k + 1] < miny) miny = hull[2 * k + 1]; if (hull[2 * k + 1] > maxy) maxy = hull[2 * k + 1];
+        }
+        e->tile_aabb[i][0] = minx; e->tile_aabb[i][1] = miny; e->tile_aabb[i][2] = maxx; e->tile_aabb[i][3] = maxy;
+        if (e->border[i]) {
+            double side = signd(b2 - b1);
+            double kb[4][2] = {
+                {x1 + side * TRACK_WIDTH * cos(b1), y1 + side * TRACK_WIDTH * sin(b1)},
+                {x1 + side * (TRACK_WIDTH + BORDER) * cos(b1), y1 + side * (TRACK_WIDTH + BORDER) * sin(b1)},
+                {x2 + side * (TRACK_WIDTH + BORDER) * cos(b2), y2 + side * (TRACK_WIDTH + BORDER) * sin(b2)},
+                {x2 + side * TRACK_WIDTH * cos(b2), y2 + side * TRACK_WIDTH * sin(b2)}};
+            for (int k = 0; k < 4; ++k) { e->kerb[i][k][0] = (float)kb[k][0]; e->kerb[i][k][1] = (float)kb[k][1]; }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* renderer                                                                                     */
+
+/* Observation of player `pi` (get_observation :622-634).  Geometry follows the reference:
+ * camera = hull.position + R(angle)*(0,16), angle = hull.angle or atan2(-vx, vy) above 0.5 m/s
+ * (camera_update :791-812); the 96x96 window is the centre of the road map rotated by `angle`
+ * at obs_scale px per world unit (camera_view :764-789); cars' fixture polygons on top
+ * (Car.draw_for_pygame, car_dynamics.py:284-298); HUD bar and indicators (:645-670); gray =
+ * trunc(0.299 R + 0.587 G + 0.114 B) in float64 (:632-633).  Sampling rule (this restatement's
+ * own; pygame's scan conversion / rotate cannot be reproduced here): each destination pixel takes
+ * the colour of the analytic scene at its centre, polygons in the reference's paint order. */
+static int point_in_convex(const float (*poly)[2], int n, double px, double py) {
+    int pos = 0, neg = 0;
+    for (int i = 0; i < n; ++i) {
+        double ax = poly[i][0], ay = poly[i][1], bx = poly[(i + 1) % n][0], by = poly[(i + 1) % n][1];
+        double cr = (bx - ax) * (py - ay) - (by - ay) * (px - ax);
+        if (cr > 0) pos = 1; else if (cr < 0) neg = 1;
+        if (pos && neg) return 0;
+    }
+    return 1;
+}
+
+static uint8_t gray_of(double r, double g, double b) { return (uint8_t)(r * 0.299 + g * 0.587 + b * 0.114); }
+
+static void fill_rect_px(uint8_t* img, double x, double y, double w, double h, uint8_t val) {
+    /* pygame.draw.rect on (x, y, w, h): Rect truncates each float; a negative extent grows the other way */
+    int X = (int)x, Y = (int)y, W = (int)w, H = (int)h;
+    int x0 = W >= 0 ? X : X + W, x1 = W >= 0 ? X + W : X + 1;
+    int y0 = H >= 0 ? Y : Y + H, y1 = H >= 0 ? Y + H : Y + 1;
+    if (W == 0 || H == 0) return;
+    if (x0 < 0) x0 = 0; if (y0 < 0) y0 = 0; if (x1 > STATE_W) x1 = STATE_W; if (y1 > STATE_H) y1 = STATE_H;
+    for (int r = y0; r < y1; ++r)
+        for (int c = x0; c < x1; ++c) img[r * STATE_W + c] = val;
+}
+
+static void render_obs(CarEnv* e, int pi) {
+    const double obs_scale = (10.0 / (100.0 / sqrt(96.0))) * 1.8;
+    const Car* me = &e->car[pi];
+    const Body* hull = &me->body[HULL_BODY];
+    double angle = hull->a;
+    double vx = hull->v.x, vy = hull->v.y;
+    if (vx * vx + vy * vy > 0.5 * 0.5) angle = atan2(-vx, +vy);
+    float fa = (float)angle;                       /* tmp.angle = angle -> b2Rot float32 */
+    double sa = sinf(fa), ca = cosf(fa);
+    double camx = (double)hull->p.x + (double)(float)(ca * 0.0f - sa * 16.0f);
+    double camy = (double)hull->p.y + (double)(float)(sa * 0.0f + ca * 16.0f);
+    double s_rot = sin(angle), c_rot = cos(angle);
+    uint8_t* img = e->obs[pi];
+    const uint8_t g_grass = gray_of(0.4 * 255, 0.8 * 255, 0.4 * 255), g_check = gray_of((int)(0.4 * 255), (int)(0.9 * 255), (int)(0.4 * 255));
+    const double k = PLAYFIELD / 20.0;
+    /* candidate tiles: centre within the window's circumscribed circle */
+    static __thread int cand[MAX_TRACK];
+    int n_cand = 0;
+    const double reach = 48.0 * 1.4142135623730951 / obs_scale + 2.0 * TRACK_WIDTH + BORDER;
+    for (int t = e->n_track - 1; t >= 0; --t) {   /* paint order: tiles are created from i = n-1 down to 0 */
+        double dx = e->track[t][2] - camx, dy = e->track[t][3] - camy;
+        if (dx * dx + dy * dy <= (reach + TRACK_DETAIL_STEP) * (reach + TRACK_DETAIL_STEP)) cand[n_cand++] = t;
+    }
+    for (int r = 0; r < STATE_H; ++r) {
+        for (int c = 0; c < STATE_W; ++c) {
+            double dxp = c + 0.5 - STATE_W / 2.0, dyp = r + 0.5 - STATE_H / 2.0;   /* screen offset from centre */
+            double sx = dxp * c_rot - dyp * s_rot, sy = dxp * s_rot + dyp * c_rot;  /* un-rotate (y down) */
+            double wx = camx - sx / obs_scale, wy = camy - sy / obs_scale;
+            uint8_t val = g_grass;
+            {
+                double gx = floor(wx / k), gy = floor(wy / k);
+                if (gx >= -20 && gx < 20 && gy >= -20 && gy < 20 && ((long)gx % 2 == 0) && ((long)gy % 2 == 0)) val = g_check;
+            }
+            for (int q = 0; q < n_cand; ++q) {
+                int t = cand[q];
+                if (point_in_convex(e->tile_poly[t], e->tile_n[t], wx, wy)) {
+                    double col = (int)(255 * (0.4 + 0.01 * (t % 3)));
+                    val = gray_of(col, col, col);
+                }
+                if (e->border[t] && point_in_convex(e->kerb[t], 4, wx, wy))
+                    val = (t % 2 == 0) ? gray_of(255, 255, 255) : gray_of(255, 0, 0);
+            }
+            /* cars: for k in cars: wheels then hull (drawlist = wheels + [hull]) */
+            for (int ci = 0; ci < e->n_cars; ++ci) {
+                const Car* cr = &e->car[ci];
+                for (int wk = 0; wk < 4; ++wk) {
+                    V2 wp[4];
+                    wheel_world_poly(&cr->body[BODY_OF_WHEEL[wk]], wp);
+                    float pp[4][2];
+                    for (int i = 0; i < 4; ++i) { pp[i][0] = wp[i].x; pp[i][1] = wp[i].y; }
+                    if (point_in_convex(pp, 4, wx, wy)) val = gray_of(0, 0, 0);
+                }
+                const Body* h = &cr->body[HULL_BODY];
+                for (int f = 0; f < 4; ++f) {
+                    float pp[8][2];
+                    for (int i = 0; i < HULL_COUNTS[f]; ++i) {
+                        V2 p = vadd(rmul(h->q, v2((float)(HULL_POLYS[f][i][0] * SIZE), (float)(HULL_POLYS[f][i][1] * SIZE))), h->p);
+                        pp[i][0] = p.x; pp[i][1] = p.y;
+                    }
+                    if (point_in_convex(pp, HULL_COUNTS[f], wx, wy))
+                        val = (ci == pi) ? gray_of(0.8 * 255, 0, 0) : gray_of(0, 0, 255);
+                }
+            }
+            img[r * STATE_W + c] = val;
+        }
+    }
+    /* HUD: render_indicators_for_pygame(width=96, height=96, scale=5) */
+    const double W = STATE_W, H = STATE_H, s = W / 40.0, h = H / 40.0;
+    double true_speed = sqrt((double)hull->v.x * hull->v.x + (double)hull->v.y * hull->v.y);
+    fill_rect_px(img, 0, H - 4 * h, W, 4 * h * 1000, gray_of(0, 0, 0));
+    fill_rect_px(img, 5 * s, H - h, s, h * (-0.02 * true_speed), gray_of(0, 0, 255));
+    for (int wk = 0; wk < 4; ++wk)
+        fill_rect_px(img, (7 + wk) * s, H - h, s, h * (-0.01 * me->omega[wk]),
+                     wk < 2 ? gray_of(0, 0, 255) : gray_of(0.2 * 255, 0, 255));
+    {
+        const RevJoint* j0 = &me->joint[JOINT_OF_WHEEL[0]];
+        double ja = (double)(me->body[BODY_OF_WHEEL[0]].a - hull->a - j0->reference_angle);
+        fill_rect_px(img, 20 * s, H - 2 * h, s * (10.0 * ja), 2 * h, gray_of(0, 255, 0));
+        fill_rect_px(img, 30 * s, H - 2 * h, s * (0.8 * (double)hull->w), 2 * h, gray_of(255, 0, 0));
+    }
+    if (e->glyphs) {   /* draw_text("%05.0f" % reward) at (W/100, H - H/20), white, 5 px non-AA glyphs */
+        char txt[32];
+        double rv = me->reward;
+        /* "%05.0f": round-half-even to integer, zero padded to width 5 (sign counts) */
+        snprintf(txt, sizeof txt, "%05.0f", rv);
+        int pen = (int)(W / 100), y0 = (int)(H - H / 20);
+        for (int i = 0; txt[i]; ++i) {
+            int gi = txt[i] == '-' ? 10 : (txt[i] >= '0' && txt[i] <= '9' ? txt[i] - '0' : -1);
+            if (gi < 0) continue;
+            for (int gy = 0; gy < 8; ++gy)
+                for (int gx = 0; gx < 4; ++gx)
+                    if (e->glyphs[(gi * 8 + gy) * 4 + gx]) {
+                        int px = pen + gx, py = y0 + gy;
+                        if (px >= 0 && px < STATE_W && py >= 0 && py < STATE_H) img[py * STATE_W + px] = gray_of(255, 255, 255);
+                    }
+            pen += e->glyphs[11 * 8 * 4 + gi];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* env API (ctypes)                                                                             */
+
+CarEnv* car_oracle_create(int n_cars, int action_repeat, const uint8_t* glyphs) {
+    CarEnv* e = (CarEnv*)calloc(1, sizeof(CarEnv));
+    e->n_cars = n_cars;
+    e->action_repeat = action_repeat > 0 ? action_repeat : 1;
+    e->glyphs = glyphs;
+    return e;
+}
+void car_oracle_destroy(CarEnv* e) { free(e); }
+
+/* CarRacing.reset with an injected track ([n][4] alpha,beta,x,y as in the JSON track format
+ * :376-381) and birth-place permutation (np.random.shuffle(arange(num_player)), :508-509). */
+void car_oracle_reset(CarEnv* e, const double* track, const int* border, int n_track, const int* birth_place) {
+    e->n_track = n_track;
+    memcpy(e->track, track, sizeof(double) * 4 * (size_t)n_track);
+    memcpy(e->border, border, sizeof(int) * (size_t)n_track);
+    build_tiles(e);
+    for (int k = 0; k < e->n_cars; ++k)
+        car_create(&e->car[k], e->track[0][1], e->track[0][2], e->track[0][3], birth_place ? birth_place[k] : k);
+    e->step_count = 0;
+    e->inv_dt0 = 0.0f;
+    for (int k = 0; k < e->n_cars; ++k) render_obs(e, k);   /* return self.step(None)[0] */
+}
+
+/* CarRacing.step, :542-620.  actions [n_cars][2]; out: step_rewards[n_cars], done[n_cars] */
+void car_oracle_step(CarEnv* e, const double* actions, double* step_rewards, int* done, int* num_steps) {
+    for (int k = 0; k < e->n_cars; ++k) {   /* process_action, :527-540 */
+        double a0 = fmax(fmin(actions[2 * k], 1), -1), a1 = fmax(fmin(actions[2 * k + 1], 1), -1), a2;
+        if (a1 > 0) a2 = 0; else { a2 = a1; a1 = 0; }
+        car_controls(&e->car[k], -a0, fabs(a1), fabs(a2));
+        step_rewards[k] = 0.0;
+    }
+    for (int rep = 0; rep < e->action_repeat; ++rep) {
+        for (int k = 0; k < e->n_cars; ++k) {
+            Car* c = &e->car[k];
+            if (c->done) continue;
+            car_step(c, 1.0 / FPS);
+            c->reward -= 0.1 / e->action_repeat;
+            step_rewards[k] += c->reward - c->prev_reward;
+            c->prev_reward = c->reward;
+            double x = c->body[HULL_BODY].p.x, y = c->body[HULL_BODY].p.y;
+            if (c->tile_visited_count == e->n_track) c->done = 1;
+            if (fabs(x) > PLAYFIELD || fabs(y) > PLAYFIELD) c->done = 1;
+            if (e->step_count > 1000) c->done = 1;
+        }
+        world_step(e, 1.0f / FPS);
+        e->step_count += 1;
+    }
+    for (int k = 0; k < e->n_cars; ++k) { render_obs(e, k); done[k] = e->car[k].done; }
+    *num_steps = e->step_count;
+}
+
+const uint8_t* car_oracle_obs(const CarEnv* e, int player) { return e->obs[player]; }
+
+/* state[car][24]: hull x, y, angle, vx, vy, w; wheel k: angle_k, omega_k (python), gas_k ; reward; tiles; done */
+void car_oracle_get_state(const CarEnv* e, double* out) {
+    for (int k = 0; k < e->n_cars; ++k) {
+        const Car* c = &e->car[k];
+        const Body* h = &c->body[HULL_BODY];
+        double* s = out + 24 * k;
+        s[0] = h->p.x; s[1] = h->p.y; s[2] = h->a; s[3] = h->v.x; s[4] = h->v.y; s[5] = h->w;
+        for (int w = 0; w < 4; ++w) {
+            const Body* b = &c->body[BODY_OF_WHEEL[w]];
+            s[6 + 4 * w] = b->a - h->a; s[7 + 4 * w] = c->omega[w]; s[8 + 4 * w] = c->gas[w]; s[9 + 4 * w] = c->n_touching[w];
+        }
+        s[22] = c->reward; s[23] = c->tile_visited_count;
+    }
+}

@@ -14,7 +14,7 @@ in /root/reference (pygame is an un-vendored wheel):
 """
 import numpy as np
 
-from . import display, draw, font, sprite, surfarray  # noqa: F401
+from . import display, draw, font, image, sprite, surfarray, transform  # noqa: F401
 
 
 def init():
