@@ -19,6 +19,9 @@ EXPORTS = [
     "crl_pong_render_obs", "crl_pong_render_obs_generic", "crl_pong_terminal_obs", "crl_pong_step_host",
     "crl_pong_get_state", "crl_pong_set_state", "crl_pong_render_raw", "crl_pong_random_actions",
     "crl_launch_count", "crl_pong_check", "crl_pong_get_stats",
+    "crl_car_create", "crl_car_destroy", "crl_car_load_glyphs", "crl_car_inject_tracks", "crl_car_reset",
+    "crl_car_step", "crl_car_step_state", "crl_car_render_obs", "crl_car_get_state", "crl_car_get_track",
+    "crl_car_random_actions", "crl_car_get_stats", "crl_car_check",
 ]
 
 
@@ -28,6 +31,17 @@ class PongConfig(ctypes.Structure):
         ("frame_stack", ctypes.c_int32), ("max_num_rounds", ctypes.c_int32), ("device", ctypes.c_int32),
         ("seed", ctypes.c_uint64), ("first_env", ctypes.c_int64),
     ]
+
+
+class CarConfig(ctypes.Structure):
+    _fields_ = [
+        ("num_envs", ctypes.c_int32), ("num_players", ctypes.c_int32), ("frame_stack", ctypes.c_int32),
+        ("action_repeat", ctypes.c_int32), ("max_episode_steps", ctypes.c_int32), ("device", ctypes.c_int32),
+        ("seed", ctypes.c_uint64), ("first_env", ctypes.c_int64),
+    ]
+
+
+DEFAULT_CAR_GLYPHS = os.path.join(_HERE, "data", "car_hud_glyphs.npz")
 
 
 class CrlError(RuntimeError):
@@ -69,6 +83,19 @@ def load():
     L.crl_pong_random_actions.argtypes = [vp, i32, u64, u64, vp]
     L.crl_pong_check.argtypes = [vp, vp]
     L.crl_pong_get_stats.argtypes = [vp, vp, vp]
+    L.crl_car_create.argtypes = [ctypes.POINTER(CarConfig), ctypes.POINTER(vp)]
+    L.crl_car_destroy.argtypes = [vp]
+    L.crl_car_load_glyphs.argtypes = [vp, vp, ctypes.c_size_t, vp]
+    L.crl_car_inject_tracks.argtypes = [vp, vp, i32, vp, i32, vp]
+    L.crl_car_reset.argtypes = [vp, vp, vp]
+    L.crl_car_step.argtypes = [vp] * 9
+    L.crl_car_step_state.argtypes = [vp] * 7
+    L.crl_car_render_obs.argtypes = [vp] * 4
+    L.crl_car_get_state.argtypes = [vp, vp, vp]
+    L.crl_car_get_track.argtypes = [vp, i32, ctypes.POINTER(i32), vp, i32, vp]
+    L.crl_car_random_actions.argtypes = [vp, i32, u64, u64, vp]
+    L.crl_car_get_stats.argtypes = [vp, vp, vp]
+    L.crl_car_check.argtypes = [vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("crl_last_error", "crl_launch_count"):

@@ -1,0 +1,206 @@
+"""Vec-env front end of the CUDA car-racing simulator (cCarRacing-v0 / cCarRacingDouble-v0).
+
+Mirrors what make_envs builds for these ids (competitive_rl/make_envs.py:101-110):
+  single: gym.make (TimeLimit 1000) -> FrameStack(n) -> WrapPyTorch        obs (N, n, 96, 96)
+  Double: gym.make -> MultipleFrameStack(n) -> FlattenMultiAgentObservation -> WrapPyTorch
+          obs (N, 2n, 96, 96) (player 0's stack, then player 1's), reward = player 0's,
+          done = any car done (utils/atari_wrappers.py:308-334)
+stepped by a Dummy/Subproc vec-env with auto-reset (utils/dummy_vec_env.py:51-63).
+Car-car collisions are not modelled."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native, spaces
+from .vec_env import VecEnv, _EnvList
+
+
+class LazyCarInfos(object):
+    """infos[i] -> {"num_steps": ..} (single) or {player: {"num_steps": .., "reward": ..}} (Double),
+    plus "terminal_observation" / "TimeLimit.truncated" for finished envs."""
+
+    def __init__(self, env, num_steps, rewards, done, truncated, term):
+        self._env, self.num_steps, self.rewards, self.done, self.truncated = env, num_steps, rewards, done, truncated
+        self._term, self._host = term, None
+
+    def __len__(self):
+        return self._env.num_envs
+
+    def terminal_observation(self):
+        return self._term
+
+    def __getitem__(self, i):
+        if self._host is None:
+            self._host = (self.num_steps.cpu().numpy(), self.rewards.cpu().numpy(), self.done.cpu().numpy(),
+                          self.truncated.cpu().numpy())
+        steps, rew, done, trunc = self._host
+        if self._env.players == 1:
+            info = {"num_steps": int(steps[i])}
+        else:
+            info = {k: {"num_steps": int(steps[i]), "reward": float(rew[i, k])} for k in range(self._env.players)}
+        if done[i]:
+            info["terminal_observation"] = self._term[i]
+            if self._env.max_episode_steps:
+                info["TimeLimit.truncated"] = bool(trunc[i])
+        return info
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+
+class CudaCarVecEnv(VecEnv):
+    """actions: float (N, 2) for cCarRacing-v0, (N, 2, 2) for cCarRacingDouble-v0 (steer, gas/brake in [-1, 1]).
+    step -> (obs uint8 (N, players*C, 96, 96), rew float32, done bool (N,), infos)."""
+
+    def __init__(self, env_id="cCarRacing-v0", num_envs=1, frame_stack=4, action_repeat=None, seed=0,
+                 asynchronous=False, device=None, max_episode_steps=1000, first_env=0, track_draws=None, birth=None,
+                 glyphs="default", return_numpy=False, n_buffers=2):
+        if env_id not in ("cCarRacing-v0", "cCarRacingDouble-v0"):
+            raise ValueError("unsupported env id %r" % (env_id,))
+        if not torch.cuda.is_available():
+            raise RuntimeError("CudaCarVecEnv needs a CUDA device: this simulator has no CPU path")
+        self._lib = _native.load()
+        self.env_id, self.players = env_id, 2 if env_id == "cCarRacingDouble-v0" else 1
+        self.c = int(frame_stack) if frame_stack else 1
+        self.asynchronous, self.return_numpy = bool(asynchronous), bool(return_numpy)
+        self.max_episode_steps = int(max_episode_steps or 0)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        n = int(num_envs)
+        ch = self.players * self.c
+        obs_space = spaces.Box(0, 255, (ch, 96, 96), dtype=np.uint8)
+        act_space = spaces.Box(-1, 1, (2,) if self.players == 1 else (self.players, 2), dtype=np.float32)
+        VecEnv.__init__(self, n, obs_space, act_space)
+        cfg = _native.CarConfig(n, self.players, int(frame_stack or 0), int(action_repeat or 0), self.max_episode_steps,
+                                int(self.device.index), int(seed) & (2 ** 64 - 1), int(first_env))
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.crl_car_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h = h
+        if isinstance(glyphs, str) and glyphs == "default":
+            g = np.load(_native.DEFAULT_CAR_GLYPHS)
+            glyphs = np.concatenate([g["bitmaps"].reshape(-1), g["advance"].reshape(-1)]).astype(np.uint8)
+        if glyphs is not None:
+            glyphs = np.ascontiguousarray(glyphs, np.uint8)
+            _native.check(self._lib.crl_car_load_glyphs(self._h, glyphs.ctypes.data, glyphs.nbytes, self._stream()))
+        if track_draws is not None:
+            self.inject_tracks(track_draws, birth)
+        dev = self.device
+        self._sets = []
+        for _ in range(max(1, int(n_buffers))):
+            self._sets.append(dict(
+                obs=torch.empty((n, ch, 96, 96), dtype=torch.uint8, device=dev),
+                term=torch.zeros((n, ch, 96, 96), dtype=torch.uint8, device=dev),
+                rew=torch.zeros((n, self.players), dtype=torch.float32, device=dev),
+                done=torch.zeros((n,), dtype=torch.uint8, device=dev),
+                trunc=torch.zeros((n,), dtype=torch.uint8, device=dev),
+                steps=torch.zeros((n,), dtype=torch.int32, device=dev)))
+        self._cur = 0
+        self._actions = torch.zeros((n, self.players, 2), dtype=torch.float32, device=dev)
+        self._waiting, self.closed = False, False
+        self.envs = _EnvList(self)
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _ptr(t):
+        return ctypes.c_void_p(t.data_ptr())
+
+    def inject_tracks(self, draws, birth=None):
+        """Validation mode: draws (N, K, 24) = np_random.uniform values per _create_track attempt; birth
+        (N, Kb, players) = shuffled birth_place_indices per reset."""
+        d = np.ascontiguousarray(draws, np.float64)
+        assert d.ndim == 3 and d.shape[0] == self.num_envs and d.shape[2] == 24
+        b = None if birth is None else np.ascontiguousarray(birth, np.int32)
+        _native.check(self._lib.crl_car_inject_tracks(
+            self._h, d.ctypes.data, d.shape[1], None if b is None else b.ctypes.data, 0 if b is None else b.shape[1],
+            self._stream()))
+
+    def _out(self, t):
+        return t.cpu().numpy() if self.return_numpy else t
+
+    def reset(self):
+        self._cur = (self._cur + 1) % len(self._sets)
+        b = self._sets[self._cur]
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.crl_car_reset(self._h, self._ptr(b["obs"]), self._stream()))
+        self._waiting = False
+        return self._out(b["obs"])
+
+    def step_async(self, actions):
+        a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions, np.float32))
+        self._actions.copy_(a.reshape(self._actions.shape), non_blocking=True)
+        self._cur = (self._cur + 1) % len(self._sets)
+        b = self._sets[self._cur]
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.crl_car_step(
+                self._h, self._ptr(self._actions), self._ptr(b["obs"]), self._ptr(b["rew"]), self._ptr(b["done"]),
+                self._ptr(b["steps"]), self._ptr(b["trunc"]), self._ptr(b["term"]), self._stream()))
+        self._waiting = True
+
+    def step_wait(self):
+        self._waiting = False
+        b = self._sets[self._cur]
+        done = b["done"].bool()
+        rew = b["rew"][:, 0]          # FlattenMultiAgentObservation returns r[0]; single: the scalar reward
+        infos = LazyCarInfos(self, b["steps"], b["rew"], b["done"], b["trunc"], b["term"])
+        if not self.asynchronous:     # DummyVecEnv buffers: (N, 1)
+            rew, done = rew[:, None], done[:, None]
+        if self.return_numpy:
+            rew, done, infos = rew.cpu().numpy(), done.cpu().numpy(), list(infos)
+        return self._out(b["obs"]), rew, done, infos
+
+    def seed(self, seed=None):
+        return [[None if seed is None else seed + i] for i in range(self.num_envs)]
+
+    def get_state(self):
+        s = torch.empty((self.num_envs * self.players, 24), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.crl_car_get_state(self._h, self._ptr(s), self._stream()))
+        return s.reshape(self.num_envs, self.players, 24)
+
+    def get_track(self, env):
+        n = ctypes.c_int32(0)
+        pts = np.zeros((512, 3), np.float64)
+        _native.check(self._lib.crl_car_get_track(self._h, int(env), ctypes.byref(n), pts.ctypes.data, 512, self._stream()))
+        return pts[:n.value].copy()
+
+    def episode_stats(self):
+        raw = (ctypes.c_uint64 * 8)()
+        _native.check(self._lib.crl_car_get_stats(self._h, raw, self._stream()))
+        ep = int(raw[0])
+        return {"episodes": ep, "mean_length": raw[1] / ep if ep else 0.0, "mean_tiles": raw[2] / ep if ep else 0.0}
+
+    def check(self):
+        _native.check(self._lib.crl_car_check(self._h, self._stream()))
+
+    def close(self):
+        if not self.closed and self._h:
+            torch.cuda.synchronize(self.device)
+            self._lib.crl_car_destroy(self._h)
+            self._h = None
+        self.closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def get_images(self, indices=None, **kwargs):
+        b = self._sets[self._cur]
+        return [np.repeat(b["obs"][i, self.c - 1].cpu().numpy()[:, :, None], 3, axis=2) for i in self._get_indices(indices)]
+
+    def get_attr(self, attr_name, indices=None):
+        return [getattr(self.envs[i], attr_name) for i in self._get_indices(indices)]
+
+    def set_attr(self, attr_name, value, indices=None):
+        for i in self._get_indices(indices):
+            setattr(self.envs[i], attr_name, value)
+
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        return [getattr(self.envs[i], method_name)(*method_args, **method_kwargs) for i in self._get_indices(indices)]

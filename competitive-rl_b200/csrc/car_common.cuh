@@ -1,0 +1,95 @@
+// car_common.cuh -- device-side layout of the batched cCarRacing simulator (sm_100a).
+//
+// Reference path being replaced (paths relative to /root/reference/competitive_rl/):
+//   car_racing/car_dynamics.py              Car (hull + 4 wheels + 4 revolute joints), wheel model
+//   car_racing/car_racing_multi_players.py  CarRacing.step/reset, FrictionDetector, _create_track, renderer
+//   box2d-py ~=2.3.5 (un-vendored)          b2World.Step(1/50, 180, 60) for 5 bodies + 4 joints per car
+//
+// One thread per CAR runs the whole per-step pipeline (controls, wheel model, sensor contacts,
+// 180+60-iteration joint solver) with its island in registers; one CTA per (env, player) rasterises
+// the 96x96 observation.  Everything below is per shard (one crl_car handle, one GPU).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pong_common.cuh"   // philox4x32_10
+
+namespace crl {
+
+constexpr int CAR_W = 96, CAR_H = 96, CAR_PIX = CAR_W * CAR_H;
+constexpr int CAR_MAX_TRACK = 512;          // tiles per track (standard tracks: 230-330)
+constexpr int CAR_MAX_PLAYERS = 2;
+constexpr int CAR_CHECKPOINTS = 12;
+constexpr int CAR_DRAWS = 2 * CAR_CHECKPOINTS;   // np_random.uniform draws per _create_track attempt
+constexpr int CAR_SAMPLE_STRIDE = 8;        // every 8th track point feeds the contact prefilter
+constexpr int CAR_MAX_SAMPLES = CAR_MAX_TRACK / CAR_SAMPLE_STRIDE;
+constexpr int CAR_MAX_STACK = 8;
+constexpr int CAR_GLYPH_BYTES = 11 * 8 * 4 + 11;
+
+// A road tile: convex hull (CCW) of the reference's 5 listed vertices + its kerb, 80 bytes.
+struct CarTile {
+    float px[5], py[5];       // hull vertices (n of them)
+    float kx[4], ky[4];       // kerb quad (valid iff flags & 2)
+    uint8_t n, flags;         // flags: 1 = exists, 2 = has kerb, 4 = white kerb (block_id even)
+    uint16_t pad;
+    float cx, cy;             // track point (x, y): centre used for culling
+};
+
+struct CarHullConst {         // mass data of the car bodies (b2Body::ResetMassData), computed on the host
+    float hull_inv_mass, hull_inv_I, hull_lcx, hull_lcy;
+    float wheel_inv_mass, wheel_inv_I;
+    uint8_t gray[16];         // palette: see CarGray
+};
+enum CarGray { G_GRASS = 0, G_CHECK, G_ROAD0, G_ROAD1, G_ROAD2, G_KERB_W, G_KERB_R, G_WHEEL, G_OWN, G_OTHER, G_HUD,
+               G_BLUE, G_BLUE2, G_GREEN, G_RED, G_TEXT };
+
+struct CarDev {
+    int n;                    // envs in this shard
+    int players;              // 1 = cCarRacing-v0, 2 = cCarRacingDouble-v0
+    int c;                    // frames per player in the observation (frame_stack or 1)
+    int action_repeat;
+    int max_episode_steps;    // gym TimeLimit of the registry entry (1000); 0 = none
+    int64_t first_env;
+    uint64_t seed;
+    // ---- per env ----
+    int32_t* n_track;         // [n]
+    CarTile* tiles;           // [n][CAR_MAX_TRACK]
+    float2* samples;          // [CAR_MAX_SAMPLES][n] every 8th track point (transposed: coalesced per-thread scans)
+    double* start_pose;       // [n][3] beta, x, y of track[0]
+    int32_t* step_count;      // [n] CarRacing.step_count
+    int32_t* elapsed;         // [n] TimeLimit._elapsed_steps
+    int32_t* reset_count;     // [n] resets so far (RNG / injection cursor)
+    int32_t* attempt_count;   // [n] track attempts so far (injection cursor)
+    float* inv_dt0;           // [n] b2World::m_inv_dt0
+    uint8_t* env_done;        // [n] done flag of the LAST step (what the vec-env saw)
+    int32_t* ring_pos;        // [n] newest slot of the frame ring
+    // ---- per car (index = env * players + player), all [n*players] unless noted ----
+    float* body;              // [n*players][5][8]: cx, cy, a, vx, vy, w, sleep_time, awake   (0 = hull, 1..4 = wheels)
+    float* joint;             // [n*players][4][6]: impulse x, y, z, motor impulse, limit state, motor speed
+    double* wheel;            // [n*players][8]: omega[4], gas[2] (rear), brake, steer
+    double* reward;           // [n*players][2]: reward, prev_reward
+    int32_t* counters;        // [n*players][4]: tile_visited_count, last_block, has_block, done
+    uint32_t* touching;       // [n*players][4][16] wheel.tiles bitmasks
+    uint32_t* visited;        // [n*players][16] tile.road_visited[car]
+    // ---- observation ring: [n][players][c][CAR_PIX] ----
+    uint8_t* ring;
+    // ---- validation mode ----
+    const double* track_draws;   // [n][k_draws][CAR_DRAWS] or nullptr
+    int k_draws;
+    const int32_t* birth;        // [n][k_birth][players] or nullptr
+    int k_birth;
+    int32_t* overrun;            // device flag: an injection table ran out
+    // ---- constants ----
+    const CarHullConst* consts;
+    const uint8_t* glyphs;       // [CAR_GLYPH_BYTES]
+    unsigned long long* stats;   // [0] episodes, [1] sum length, [2] sum tiles visited (player 0)
+};
+
+cudaError_t launch_car_reset(const CarDev& p, int only_done, cudaStream_t s);
+cudaError_t launch_car_step(const CarDev& p, const float* actions, float* rew, uint8_t* done, int32_t* num_steps,
+                            uint8_t* truncated, cudaStream_t s);
+cudaError_t launch_car_render(const CarDev& p, int only_done, uint8_t* obs, uint8_t* term_obs, cudaStream_t s);
+cudaError_t launch_car_get_state(const CarDev& p, double* state, cudaStream_t s);
+cudaError_t launch_car_random_actions(float* actions, int n_values, uint64_t seed, uint64_t step, cudaStream_t s);
+
+}  // namespace crl

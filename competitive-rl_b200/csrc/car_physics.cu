@@ -1,0 +1,836 @@
+// car_physics.cu -- cCarRacing game core: track generation + reset (one thread per env) and the
+// per-step pipeline (one thread per car): action decode, wheel model, sensor contacts / tile
+// reward, Box2D-style joint solver, done / TimeLimit logic.
+//
+// Replaces (paths relative to /root/reference/competitive_rl/):
+//   car_racing/car_racing_multi_players.py  _create_track (262-452), reset (454-525), process_action (527-540),
+//                                           step (542-620), FrictionDetector._contact (111-153)
+//   car_racing/car_dynamics.py              Car.__init__ (55-129), gas/brake/steer (131-157), step (159-234)
+//   car_racing/register.py                  max_episode_steps=1000 (gym TimeLimit) (8-26)
+//   box2d-py 2.3 (un-vendored)              b2World::Step(1/50, 180, 60): b2Island::Solve + b2RevoluteJoint,
+//                                           polygon mass data, sensor overlap -- restated from the published
+//                                           algorithm (parity vs a real Box2D is unpinned)
+//
+// Arithmetic: solver in fp32 exactly as Box2D (b2 float32), un-fused (-fmad=false); the Python-level
+// wheel model and the track generator in fp64 like the reference's Python floats.
+#include <math.h>
+
+#include "car_common.cuh"
+
+namespace crl {
+
+// ---- constants (car_dynamics.py:17-41, car_racing_multi_players.py:54-72) ----
+#define CR_SIZE 0.02
+#define CR_ENGINE_POWER (100000000 * CR_SIZE * CR_SIZE)
+#define CR_WHEEL_MOI (4000 * CR_SIZE * CR_SIZE)
+#define CR_FRICTION_LIMIT (1000000 * CR_SIZE * CR_SIZE)
+#define CR_WHEEL_R 27
+#define CR_WHEEL_W 14
+#define CR_SCALE 6.0
+#define CR_TRACK_RAD (900.0 / CR_SCALE)
+#define CR_PLAYFIELD (2000.0 / CR_SCALE)
+#define CR_FPS 50
+#define CR_TRACK_DETAIL_STEP (21.0 / CR_SCALE)
+#define CR_TRACK_TURN_RATE 0.31
+#define CR_TRACK_WIDTH (40.0 / CR_SCALE)
+#define CR_BORDER (8.0 / CR_SCALE)
+#define CR_BORDER_MIN_COUNT 4
+#define CR_PI 3.141592653589793
+
+// Box2D 2.3 b2Settings.h
+#define B2_PI 3.14159265359f
+#define B2_LINEAR_SLOP 0.005f
+#define B2_ANGULAR_SLOP (2.0f / 180.0f * B2_PI)
+#define B2_POLYGON_RADIUS (2.0f * B2_LINEAR_SLOP)
+#define B2_MAX_ANGULAR_CORRECTION (8.0f / 180.0f * B2_PI)
+#define B2_MAX_TRANSLATION 2.0f
+#define B2_MAX_ROTATION (0.5f * B2_PI)
+#define B2_TIME_TO_SLEEP 0.5f
+#define B2_LINEAR_SLEEP_TOL 0.01f
+#define B2_ANGULAR_SLEEP_TOL (2.0f / 180.0f * B2_PI)
+
+__constant__ float c_wheelpos[4][2] = {{-55, +80}, {+55, +80}, {-55, -82}, {+55, -82}};
+
+struct F2 { float x, y; };
+__device__ __forceinline__ F2 f2(float x, float y) { F2 r; r.x = x; r.y = y; return r; }
+__device__ __forceinline__ F2 operator+(F2 a, F2 b) { return f2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ F2 operator-(F2 a, F2 b) { return f2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ F2 operator*(float s, F2 a) { return f2(s * a.x, s * a.y); }
+__device__ __forceinline__ float dot(F2 a, F2 b) { return a.x * b.x + a.y * b.y; }
+__device__ __forceinline__ float cross(F2 a, F2 b) { return a.x * b.y - a.y * b.x; }
+__device__ __forceinline__ F2 cross_sv(float s, F2 a) { return f2(-s * a.y, s * a.x); }
+struct Rot { float s, c; };
+__device__ __forceinline__ Rot make_rot(float a) { Rot r; sincosf(a, &r.s, &r.c); return r; }
+__device__ __forceinline__ F2 rmul(Rot q, F2 v) { return f2(q.c * v.x - q.s * v.y, q.s * v.x + q.c * v.y); }
+__device__ __forceinline__ float clampf(float a, float lo, float hi) { return a < lo ? lo : (a > hi ? hi : a); }
+__device__ __forceinline__ double signd(double v) { return (double)((v > 0) - (v < 0)); }
+
+// ------------------------------------------------------------------------------------------------
+// track generator (fp64): one walk of the curve follower; `emit_from/emit_to` select which raw points
+// are written out (second pass) -- the raw 2500-point walk is never stored.
+struct WalkResult { int n_raw, i1, i2; };
+
+__device__ WalkResult track_walk(const double* draws, int emit_from, int emit_to, double* out /* [][3] beta,x,y */) {
+    double cp_alpha[CAR_CHECKPOINTS], cp_x[CAR_CHECKPOINTS], cp_y[CAR_CHECKPOINTS];
+    double start_alpha = 0.0;
+    for (int c = 0; c < CAR_CHECKPOINTS; ++c) {
+        double alpha = 2 * CR_PI * c / CAR_CHECKPOINTS + draws[2 * c];
+        double rad = draws[2 * c + 1];
+        if (c == 0) { alpha = 0; rad = 1.5 * CR_TRACK_RAD; }
+        if (c == CAR_CHECKPOINTS - 1) {
+            alpha = 2 * CR_PI * c / CAR_CHECKPOINTS;
+            start_alpha = 2 * CR_PI * (-0.5) / CAR_CHECKPOINTS;
+            rad = 1.5 * CR_TRACK_RAD;
+        }
+        cp_alpha[c] = alpha; cp_x[c] = rad * cos(alpha); cp_y[c] = rad * sin(alpha);
+    }
+    double x = 1.5 * CR_TRACK_RAD, y = 0, beta = 0, prev_alpha = 0;
+    int dest_i = 0, laps = 0, no_freeze = 2500, visited_other_side = 0, n_raw = 0;
+    int last_cross = -1, prev_cross = -1;
+    for (;;) {
+        double alpha = atan2(y, x);
+        if (visited_other_side && alpha > 0) { laps += 1; visited_other_side = 0; }
+        if (alpha < 0) { visited_other_side = 1; alpha += 2 * CR_PI; }
+        double dest_x, dest_y;
+        for (;;) {
+            bool failed = true;
+            for (;;) {
+                const int k = dest_i % CAR_CHECKPOINTS;
+                dest_x = cp_x[k]; dest_y = cp_y[k];
+                if (alpha <= cp_alpha[k]) { failed = false; break; }
+                dest_i += 1;
+                if (dest_i % CAR_CHECKPOINTS == 0) break;
+            }
+            if (!failed) break;
+            alpha -= 2 * CR_PI;
+        }
+        const double r1x = cos(beta), r1y = sin(beta);
+        const double p1x = -r1y, p1y = r1x;
+        double proj = r1x * (dest_x - x) + r1y * (dest_y - y);
+        while (beta - alpha > 1.5 * CR_PI) beta -= 2 * CR_PI;
+        while (beta - alpha < -1.5 * CR_PI) beta += 2 * CR_PI;
+        const double prev_beta = beta;
+        proj *= CR_SCALE;
+        if (proj > 0.3) beta -= fmin(CR_TRACK_TURN_RATE, fabs(0.001 * proj));
+        if (proj < -0.3) beta += fmin(CR_TRACK_TURN_RATE, fabs(0.001 * proj));
+        x += p1x * CR_TRACK_DETAIL_STEP;
+        y += p1y * CR_TRACK_DETAIL_STEP;
+        // raw point n_raw = (alpha, prev_beta*0.5 + beta*0.5, x, y)
+        if (n_raw >= 1 && alpha > start_alpha && prev_alpha <= start_alpha) { prev_cross = last_cross; last_cross = n_raw; }
+        if (out != nullptr && n_raw >= emit_from && n_raw < emit_to) {
+            double* o = out + 3 * (n_raw - emit_from);
+            o[0] = prev_beta * 0.5 + beta * 0.5; o[1] = x; o[2] = y;
+        }
+        prev_alpha = alpha;
+        n_raw += 1;
+        if (laps > 4) break;
+        no_freeze -= 1;
+        if (no_freeze == 0) break;
+    }
+    WalkResult r;
+    r.n_raw = n_raw; r.i2 = last_cross; r.i1 = prev_cross;
+    return r;
+}
+
+// b2PolygonShape::Set hull of 5 points (gift wrapping, fp32)
+__device__ int convex_hull5(const float* px, const float* py, float* ox, float* oy) {
+    float qx[5], qy[5];
+    int m = 0;
+    for (int i = 0; i < 5; ++i) {
+        bool unique = true;
+        for (int k = 0; k < m; ++k) {
+            const float dx = px[i] - qx[k], dy = py[i] - qy[k];
+            if (dx * dx + dy * dy < 0.5f * B2_LINEAR_SLOP * 0.5f * B2_LINEAR_SLOP) { unique = false; break; }
+        }
+        if (unique) { qx[m] = px[i]; qy[m] = py[i]; ++m; }
+    }
+    if (m < 3) return 0;
+    int i0 = 0;
+    for (int i = 1; i < m; ++i)
+        if (qx[i] > qx[i0] || (qx[i] == qx[i0] && qy[i] < qy[i0])) i0 = i;
+    int hull[5], cnt = 0, ih = i0;
+    for (;;) {
+        hull[cnt] = ih;
+        int ie = 0;
+        for (int j = 1; j < m; ++j) {
+            if (ie == ih) { ie = j; continue; }
+            const float rx = qx[ie] - qx[hull[cnt]], ry = qy[ie] - qy[hull[cnt]];
+            const float vx = qx[j] - qx[hull[cnt]], vy = qy[j] - qy[hull[cnt]];
+            const float c = rx * vy - ry * vx;
+            if (c < 0.0f) ie = j;
+            if (c == 0.0f && vx * vx + vy * vy > rx * rx + ry * ry) ie = j;
+        }
+        ++cnt;
+        ih = ie;
+        if (ie == i0 || cnt >= 5) break;
+    }
+    for (int i = 0; i < cnt; ++i) { ox[i] = qx[hull[i]]; oy[i] = qy[hull[i]]; }
+    return cnt;
+}
+
+__device__ void car_body_reset(const CarDev& p, int ci, double init_angle, double init_x, double init_y, int birth) {
+    init_x -= birth % 2 * 5;
+    init_y -= floor((double)(birth / 2)) * 10;
+    float* b = p.body + (size_t)ci * 40;
+    const CarHullConst* K = p.consts;
+    const float a = (float)init_angle;
+    const Rot q = make_rot(a);
+    const F2 lc = rmul(q, f2(K->hull_lcx, K->hull_lcy));
+    b[0] = (float)init_x + lc.x; b[1] = (float)init_y + lc.y; b[2] = a; b[3] = b[4] = b[5] = 0.f; b[6] = 0.f; b[7] = 1.f;
+    for (int k = 0; k < 4; ++k) {   // wheels are NOT placed rotated (car_dynamics.py:90); the joints pull them in
+        float* w = b + 8 * (k + 1);
+        w[0] = (float)(init_x + c_wheelpos[k][0] * CR_SIZE); w[1] = (float)(init_y + c_wheelpos[k][1] * CR_SIZE);
+        w[2] = a; w[3] = w[4] = w[5] = 0.f; w[6] = 0.f; w[7] = 1.f;
+    }
+    float* j = p.joint + (size_t)ci * 24;
+    for (int i = 0; i < 24; ++i) j[i] = 0.f;
+    double* wd = p.wheel + (size_t)ci * 8;
+    for (int i = 0; i < 8; ++i) wd[i] = 0.0;
+    p.reward[2 * ci] = 0.0; p.reward[2 * ci + 1] = 0.0;
+    int32_t* cn = p.counters + 4 * ci;
+    cn[0] = cn[1] = cn[2] = cn[3] = 0;
+    for (int i = 0; i < 64; ++i) p.touching[(size_t)ci * 64 + i] = 0u;
+    for (int i = 0; i < 16; ++i) p.visited[(size_t)ci * 16 + i] = 0u;
+}
+
+// CarRacing.reset: new track (retry until an attempt succeeds, :499-507), cars at track[0] (:508-512)
+__global__ void car_reset_kernel(CarDev p, int only_done, double* track_scratch /* [n][MAX_TRACK][3] */) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n) return;
+    if (only_done && !p.env_done[e]) return;
+    double* pts = track_scratch + (size_t)e * CAR_MAX_TRACK * 3;
+    CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
+    const uint64_t gi = (uint64_t)(p.first_env + e);
+    int n = 0;
+    for (int guard = 0; guard < 64 && n == 0; ++guard) {
+        double draws[CAR_DRAWS];
+        const int att = p.attempt_count[e];
+        p.attempt_count[e] = att + 1;
+        if (p.track_draws != nullptr) {
+            int k = att;
+            if (k >= p.k_draws) { *p.overrun = 1; k = p.k_draws - 1; }
+            for (int i = 0; i < CAR_DRAWS; ++i) draws[i] = p.track_draws[((size_t)e * p.k_draws + k) * CAR_DRAWS + i];
+        } else {
+            for (int i = 0; i < CAR_DRAWS; i += 2) {   // noise ~ U(0, 2pi/12), rad ~ U(R/3, R), :268-270
+                uint32_t r[4];
+                philox4x32_10((uint32_t)att, (uint32_t)(i / 2), (uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)p.seed,
+                              (uint32_t)(p.seed >> 32) ^ 0xC0FFEEu, r);
+                const double u0 = (double)((((uint64_t)r[0] >> 5) << 26) | ((uint64_t)r[1] >> 6)) * (1.0 / 9007199254740992.0);
+                const double u1 = (double)((((uint64_t)r[2] >> 5) << 26) | ((uint64_t)r[3] >> 6)) * (1.0 / 9007199254740992.0);
+                draws[i] = 0.0 + (2 * CR_PI * 1 / CAR_CHECKPOINTS - 0.0) * u0;
+                draws[i + 1] = CR_TRACK_RAD / 3 + (CR_TRACK_RAD - CR_TRACK_RAD / 3) * u1;
+            }
+        }
+        const WalkResult w = track_walk(draws, 0, 0, nullptr);
+        if (w.i1 < 0 || w.i2 < 0) continue;               // "return False  # Failed"
+        const int cnt = (w.i2 - 1) - w.i1;                // track = track[i1:i2 - 1]
+        if (cnt <= 8 || cnt > CAR_MAX_TRACK) continue;
+        track_walk(draws, w.i1, w.i1 + cnt, pts);
+        const double fb = pts[0], fpx = cos(fb), fpy = sin(fb);
+        const double gx = fpx * (pts[1] - pts[3 * (cnt - 1) + 1]), gy = fpy * (pts[2] - pts[3 * (cnt - 1) + 2]);
+        if (sqrt(gx * gx + gy * gy) > CR_TRACK_DETAIL_STEP) continue;   // not well glued together
+        n = cnt;
+    }
+    if (n == 0) {   // cannot happen with sane draws; keep the env valid with a flagged error
+        *p.overrun = 2;
+        return;
+    }
+    p.n_track[e] = n;
+    // red-white border on hard turns (:383-397): border[] kept in tile.flags bit 1
+    for (int i = 0; i < n; ++i) tiles[i].flags = 1;
+    for (int i = 0; i < n; ++i) {
+        bool good = true;
+        int oneside = 0;
+        for (int neg = 0; neg < CR_BORDER_MIN_COUNT; ++neg) {
+            const double b1 = pts[3 * (((i - neg - 0) % n + n) % n)], b2 = pts[3 * (((i - neg - 1) % n + n) % n)];
+            good = good && fabs(b1 - b2) > CR_TRACK_TURN_RATE * 0.2;
+            oneside += (b1 - b2 > 0) - (b1 - b2 < 0);
+        }
+        good = good && abs(oneside) == CR_BORDER_MIN_COUNT;
+        if (good) tiles[i].flags |= 8;   // provisional mark
+    }
+    for (int i = 0; i < n; ++i)
+        if (tiles[i].flags & 8)
+            for (int neg = 0; neg < CR_BORDER_MIN_COUNT; ++neg) tiles[((i - neg) % n + n) % n].flags |= 2;
+    // tiles (:399-445)
+    for (int i = 0; i < n; ++i) {
+        const double* p1 = pts + 3 * i;
+        const double* p2 = pts + 3 * ((i - 1 + n) % n);
+        const double b1 = p1[0], x1 = p1[1], y1 = p1[2], b2 = p2[0], x2 = p2[1], y2 = p2[2];
+        float vx[5], vy[5];
+        vx[0] = (float)(x1 - CR_TRACK_WIDTH * cos(b1)); vy[0] = (float)(y1 - CR_TRACK_WIDTH * sin(b1));
+        vx[1] = (float)(x1 - CR_TRACK_WIDTH / 2 * cos(b1 - CR_PI / 2)); vy[1] = (float)(y1 - CR_TRACK_WIDTH / 2 * sin(b1 - CR_PI / 2));
+        vx[2] = (float)(x1 + CR_TRACK_WIDTH * cos(b1)); vy[2] = (float)(y1 + CR_TRACK_WIDTH * sin(b1));
+        vx[3] = (float)(x2 + CR_TRACK_WIDTH * cos(b2)); vy[3] = (float)(y2 + CR_TRACK_WIDTH * sin(b2));
+        vx[4] = (float)(x2 - CR_TRACK_WIDTH * cos(b2)); vy[4] = (float)(y2 - CR_TRACK_WIDTH * sin(b2));
+        CarTile t;
+        t.n = (uint8_t)convex_hull5(vx, vy, t.px, t.py);
+        for (int k = t.n; k < 5; ++k) { t.px[k] = t.px[0]; t.py[k] = t.py[0]; }
+        t.flags = (uint8_t)(1 | (tiles[i].flags & 2) | ((i % 2 == 0) ? 4 : 0));
+        t.pad = 0;
+        t.cx = (float)x1; t.cy = (float)y1;
+        const double side = signd(b2 - b1);
+        t.kx[0] = (float)(x1 + side * CR_TRACK_WIDTH * cos(b1)); t.ky[0] = (float)(y1 + side * CR_TRACK_WIDTH * sin(b1));
+        t.kx[1] = (float)(x1 + side * (CR_TRACK_WIDTH + CR_BORDER) * cos(b1)); t.ky[1] = (float)(y1 + side * (CR_TRACK_WIDTH + CR_BORDER) * sin(b1));
+        t.kx[2] = (float)(x2 + side * (CR_TRACK_WIDTH + CR_BORDER) * cos(b2)); t.ky[2] = (float)(y2 + side * (CR_TRACK_WIDTH + CR_BORDER) * sin(b2));
+        t.kx[3] = (float)(x2 + side * CR_TRACK_WIDTH * cos(b2)); t.ky[3] = (float)(y2 + side * CR_TRACK_WIDTH * sin(b2));
+        tiles[i] = t;
+    }
+    for (int i = n; i < CAR_MAX_TRACK; ++i) tiles[i].flags = 0;
+    for (int s = 0; s < CAR_MAX_SAMPLES; ++s) {
+        const int i = s * CAR_SAMPLE_STRIDE;
+        p.samples[(size_t)s * p.n + e] = (i < n) ? make_float2((float)pts[3 * i + 1], (float)pts[3 * i + 2])
+                                                 : make_float2(1e30f, 1e30f);
+    }
+    p.start_pose[3 * e] = pts[0]; p.start_pose[3 * e + 1] = pts[1]; p.start_pose[3 * e + 2] = pts[2];
+    // cars: birth_place_indices = shuffle(arange(num_player)) (:508-512)
+    const int rc = p.reset_count[e];
+    p.reset_count[e] = rc + 1;
+    int birth[CAR_MAX_PLAYERS] = {0, 1};
+    if (p.players == 2) {
+        if (p.birth != nullptr) {
+            int k = rc;
+            if (k >= p.k_birth) { *p.overrun = 1; k = p.k_birth - 1; }
+            birth[0] = p.birth[((size_t)e * p.k_birth + k) * 2]; birth[1] = p.birth[((size_t)e * p.k_birth + k) * 2 + 1];
+        } else {
+            uint32_t r[4];
+            philox4x32_10((uint32_t)rc, 0x5EEDu, (uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)p.seed,
+                          (uint32_t)(p.seed >> 32) ^ 0xB1A7u, r);
+            if (r[0] & 1u) { birth[0] = 1; birth[1] = 0; }
+        }
+    }
+    for (int k = 0; k < p.players; ++k) car_body_reset(p, e * p.players + k, pts[0], pts[1], pts[2], birth[k]);
+    p.step_count[e] = 0;
+    p.elapsed[e] = 0;
+    p.inv_dt0[e] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-step pipeline, one thread per car
+
+struct Joint {
+    F2 rA, rB;
+    float k00, k01, k02, k11, k12, k22;   // symmetric K (ex.x, ey.x, ez.x, ey.y, ez.y, ez.z)
+    float motor_mass;
+    float ix, iy, iz, motor_impulse, motor_speed;
+    int limit_state;
+};
+
+__device__ __forceinline__ void solve33(const Joint& j, float b0, float b1, float b2, float& o0, float& o1, float& o2) {
+    const float ex0 = j.k00, ex1 = j.k01, ex2 = j.k02, ey0 = j.k01, ey1 = j.k11, ey2 = j.k12, ez0 = j.k02, ez1 = j.k12, ez2 = j.k22;
+    const float cx = ey1 * ez2 - ey2 * ez1, cy = ey2 * ez0 - ey0 * ez2, cz = ey0 * ez1 - ey1 * ez0;
+    float det = ex0 * cx + ex1 * cy + ex2 * cz;
+    if (det != 0.0f) det = 1.0f / det;
+    o0 = det * (b0 * cx + b1 * cy + b2 * cz);
+    const float bx = b1 * ez2 - b2 * ez1, by = b2 * ez0 - b0 * ez2, bz = b0 * ez1 - b1 * ez0;
+    o1 = det * (ex0 * bx + ex1 * by + ex2 * bz);
+    const float dx = ey1 * b2 - ey2 * b1, dy = ey2 * b0 - ey0 * b2, dz = ey0 * b1 - ey1 * b0;
+    o2 = det * (ex0 * dx + ex1 * dy + ex2 * dz);
+}
+
+__device__ __forceinline__ F2 solve22(float a11, float a12, float a21, float a22, F2 b) {
+    float det = a11 * a22 - a12 * a21;
+    if (det != 0.0f) det = 1.0f / det;
+    return f2(det * (a22 * b.x - a12 * b.y), det * (a11 * b.y - a21 * b.x));
+}
+
+// polygons (with b2_polygonRadius skins) touch: max face separation below 2 * radius
+__device__ float max_separation(const float* ax, const float* ay, int na, const float* bx, const float* by, int nb) {
+    float best = -3.4e38f;
+    for (int i = 0; i < na; ++i) {
+        const int i2 = (i + 1 == na) ? 0 : i + 1;
+        const float ex = ax[i2] - ax[i], ey = ay[i2] - ay[i];
+        const float len = sqrtf(ex * ex + ey * ey);
+        if (len < 1e-12f) continue;
+        const float nx = ey / len, ny = -ex / len;
+        float mn = 3.4e38f;
+        for (int k = 0; k < nb; ++k) mn = fminf(mn, nx * (bx[k] - ax[i]) + ny * (by[k] - ay[i]));
+        best = fmaxf(best, mn);
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(64)
+car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__ rew, uint8_t* __restrict__ done_out,
+                int32_t* __restrict__ num_steps_out, uint8_t* __restrict__ truncated_out) {
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_cars = p.n * p.players;
+    const bool active = ci < n_cars;
+    const int e = active ? ci / p.players : 0, player = active ? ci % p.players : 0;
+    bool car_done = false;
+    double step_reward = 0.0;
+    int env_steps = 0;
+    if (active) {
+        const CarHullConst K = *p.consts;
+        // ---- load ----
+        F2 c[5], v[5];
+        float a[5], w[5], sleep_t[5];
+        bool awake[5];
+        {
+            const float* b = p.body + (size_t)ci * 40;
+            for (int i = 0; i < 5; ++i) {
+                c[i] = f2(b[8 * i], b[8 * i + 1]); a[i] = b[8 * i + 2]; v[i] = f2(b[8 * i + 3], b[8 * i + 4]);
+                w[i] = b[8 * i + 5]; sleep_t[i] = b[8 * i + 6]; awake[i] = b[8 * i + 7] != 0.f;
+            }
+        }
+        Joint J[4];
+        {
+            const float* j = p.joint + (size_t)ci * 24;
+            for (int k = 0; k < 4; ++k) {
+                J[k].ix = j[6 * k]; J[k].iy = j[6 * k + 1]; J[k].iz = j[6 * k + 2]; J[k].motor_impulse = j[6 * k + 3];
+                J[k].limit_state = (int)j[6 * k + 4]; J[k].motor_speed = j[6 * k + 5];
+            }
+        }
+        double omega[4], gas[2], brake, steer;
+        {
+            const double* wd = p.wheel + (size_t)ci * 8;
+            for (int k = 0; k < 4; ++k) omega[k] = wd[k];
+            gas[0] = wd[4]; gas[1] = wd[5]; brake = wd[6]; steer = wd[7];
+        }
+        double reward = p.reward[2 * ci], prev_reward = p.reward[2 * ci + 1];
+        int32_t* cn = p.counters + 4 * ci;
+        int tile_visited = cn[0], last_block = cn[1], has_block = cn[2];
+        car_done = cn[3] != 0;
+        uint32_t* touching = p.touching + (size_t)ci * 64;
+        uint32_t* visited = p.visited + (size_t)ci * 16;
+        const int n_track = p.n_track[e];
+        const CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
+        int step_count = p.step_count[e];
+        float inv_dt0 = p.inv_dt0[e];
+        const float hull_lcx = K.hull_lcx, hull_lcy = K.hull_lcy;
+
+        // ---- process_action (:527-540) + Car.steer(-a0) / gas / brake (car_dynamics.py:131-157) ----
+        {
+            const double in0 = (double)actions[2 * ci], in1 = (double)actions[2 * ci + 1];
+            const double a0 = fmax(fmin(in0, 1.0), -1.0);
+            double a1 = fmax(fmin(in1, 1.0), -1.0), a2;
+            if (a1 > 0) a2 = 0; else { a2 = a1; a1 = 0; }
+            steer = -a0;
+            const double g = fmin(fmax(fabs(a1), 0.0), 1.0);
+            for (int k = 0; k < 2; ++k) {
+                double diff = g - gas[k];
+                if (diff > 0.1) diff = 0.1;
+                gas[k] += diff;
+            }
+            brake = fabs(a2);
+        }
+
+        const double dt = 1.0 / CR_FPS;
+        const float h = 1.0f / CR_FPS;
+        for (int rep = 0; rep < p.action_repeat; ++rep) {
+            F2 force[5];
+            for (int i = 0; i < 5; ++i) force[i] = f2(0.f, 0.f);
+            int n_touch[4];
+            for (int k = 0; k < 4; ++k) {
+                int cnt = 0;
+                for (int wd = 0; wd < 16; ++wd) cnt += __popc(touching[16 * k + wd]);
+                n_touch[k] = cnt;
+            }
+            if (!car_done) {
+                // ---- Car.step(1/FPS), car_dynamics.py:159-234 ----
+                for (int k = 0; k < 4; ++k) {
+                    const int bi = k + 1;
+                    const double joint_angle = (double)(a[bi] - a[0] - 0.0f);
+                    const double st = (k < 2) ? steer : 0.0;
+                    const double dir = signd(st - joint_angle), val = fabs(st - joint_angle);
+                    J[k].motor_speed = (float)(dir * fmin(50.0 * val, 3.0));
+                    if (!awake[0]) { awake[0] = true; sleep_t[0] = 0.f; }      // SetMotorSpeed wakes both bodies
+                    if (!awake[bi]) { awake[bi] = true; sleep_t[bi] = 0.f; }
+                    double friction_limit = CR_FRICTION_LIMIT * 0.6;
+                    if (n_touch[k] > 0) friction_limit = fmax(friction_limit, CR_FRICTION_LIMIT * 1.0);
+                    const Rot q = make_rot(a[bi]);
+                    const F2 forw = rmul(q, f2(0.f, 1.f)), side = rmul(q, f2(1.f, 0.f));
+                    const double vf = (double)forw.x * (double)v[bi].x + (double)forw.y * (double)v[bi].y;
+                    const double vs = (double)side.x * (double)v[bi].x + (double)side.y * (double)v[bi].y;
+                    const double gk = (k >= 2) ? gas[k - 2] : 0.0;
+                    omega[k] += dt * CR_ENGINE_POWER * gk / CR_WHEEL_MOI / (fabs(omega[k]) + 5.0);
+                    if (brake >= 0.9) {
+                        omega[k] = 0;
+                    } else if (brake > 0) {
+                        const double bdir = -signd(omega[k]);
+                        double bval = 15 * brake;
+                        if (fabs(bval) > fabs(omega[k])) bval = fabs(omega[k]);
+                        omega[k] += bdir * bval;
+                    }
+                    const double vr = omega[k] * (CR_WHEEL_R * CR_SIZE);
+                    double f_force = -vf + vr, p_force = -vs;
+                    f_force *= 205000 * CR_SIZE * CR_SIZE;
+                    p_force *= 205000 * CR_SIZE * CR_SIZE;
+                    double frc = sqrt(f_force * f_force + p_force * p_force);
+                    if (fabs(frc) > friction_limit) {
+                        f_force /= frc; p_force /= frc;
+                        frc = friction_limit;
+                        f_force *= frc; p_force *= frc;
+                    }
+                    omega[k] -= dt * f_force * (CR_WHEEL_R * CR_SIZE) / CR_WHEEL_MOI;
+                    const float fx = (float)(p_force * (double)side.x + f_force * (double)forw.x);
+                    const float fy = (float)(p_force * (double)side.y + f_force * (double)forw.y);
+                    force[bi] = force[bi] + f2(fx, fy);   // ApplyForceToCenter(.., True): wheel is awake by now
+                }
+                // ---- CarRacing.step bookkeeping (:581-598) ----
+                reward -= 0.1 / p.action_repeat;
+                step_reward += reward - prev_reward;
+                prev_reward = reward;
+                {
+                    const Rot q = make_rot(a[0]);
+                    const F2 pos = c[0] - rmul(q, f2(hull_lcx, hull_lcy));
+                    if (tile_visited == n_track) car_done = true;
+                    if (fabs((double)pos.x) > CR_PLAYFIELD || fabs((double)pos.y) > CR_PLAYFIELD) car_done = true;
+                    if (step_count > 1000) car_done = true;
+                }
+            }
+            // ================= world.Step(1/FPS, 180, 60) =================
+            // ---- b2ContactManager::Collide: wheel-tile sensor contacts -> FrictionDetector._contact ----
+            {
+                // candidate tiles: prefilter on every 8th track point (transposed array: coalesced), then tile centres
+                const Rot qh = make_rot(a[0]);
+                const F2 hp = c[0] - rmul(qh, f2(hull_lcx, hull_lcy));
+                int cand[48], n_cand = 0;
+                const int n_samp = (n_track + CAR_SAMPLE_STRIDE - 1) / CAR_SAMPLE_STRIDE;
+                for (int s = 0; s < n_samp; ++s) {
+                    const float2 sp = p.samples[(size_t)s * p.n + e];
+                    const float dx = sp.x - hp.x, dy = sp.y - hp.y;
+                    if (dx * dx + dy * dy < 36.0f * 36.0f) {
+                        const int t1 = min(n_track, (s + 1) * CAR_SAMPLE_STRIDE);
+                        for (int t = s * CAR_SAMPLE_STRIDE; t < t1; ++t) {
+                            const float tx = tiles[t].cx - hp.x, ty = tiles[t].cy - hp.y;
+                            if (tx * tx + ty * ty < 11.5f * 11.5f && n_cand < 48) cand[n_cand++] = t;
+                        }
+                    }
+                }
+                for (int k = 0; k < 4; ++k) {
+                    const int bi = k + 1;
+                    const Rot q = make_rot(a[bi]);
+                    const float hw = (float)(CR_WHEEL_W * CR_SIZE), hr = (float)(CR_WHEEL_R * CR_SIZE);
+                    float wx[4], wy[4];
+                    {
+                        const F2 l0 = rmul(q, f2(-hw, -hr)) + c[bi], l1 = rmul(q, f2(+hw, -hr)) + c[bi];
+                        const F2 l2 = rmul(q, f2(+hw, +hr)) + c[bi], l3 = rmul(q, f2(-hw, +hr)) + c[bi];
+                        wx[0] = l0.x; wy[0] = l0.y; wx[1] = l1.x; wy[1] = l1.y; wx[2] = l2.x; wy[2] = l2.y; wx[3] = l3.x; wy[3] = l3.y;
+                    }
+                    uint32_t now[16];
+                    for (int wd = 0; wd < 16; ++wd) now[wd] = 0u;
+                    for (int q2 = 0; q2 < n_cand; ++q2) {
+                        const int t = cand[q2];
+                        const CarTile T = tiles[t];
+                        const float ddx = T.cx - c[bi].x, ddy = T.cy - c[bi].y;
+                        if (ddx * ddx + ddy * ddy > 9.0f * 9.0f) continue;
+                        const float s1 = max_separation(wx, wy, 4, T.px, T.py, T.n);
+                        const float s2 = max_separation(T.px, T.py, T.n, wx, wy, 4);
+                        if (fmaxf(s1, s2) < 2.0f * B2_POLYGON_RADIUS) now[t >> 5] |= 1u << (t & 31);
+                    }
+                    for (int wd = 0; wd < 16; ++wd) {
+                        const uint32_t was = touching[16 * k + wd];
+                        uint32_t begins = now[wd] & ~was;
+                        while (begins) {                                   // BeginContact, ascending block id
+                            const int bit = __ffs(begins) - 1;
+                            begins &= begins - 1;
+                            const int t = wd * 32 + bit;
+                            if (!((visited[wd] >> bit) & 1u)) {
+                                const int last_blk = has_block ? last_block : 0;
+                                if (t - last_blk < 50) {
+                                    last_block = t; has_block = 1;
+                                    reward += 1000.0 / n_track;
+                                }
+                                visited[wd] |= 1u << bit;
+                                tile_visited += 1;
+                            }
+                        }
+                        touching[16 * k + wd] = now[wd];                   // EndContact: tiles.remove
+                    }
+                }
+            }
+            // ---- b2Island::Solve for this car's island (bodies: hull + 4 wheels; joints relaxed in the
+            //      order wheel 3, 2, 1, 0 -- the island order b2World::Solve's DFS produces) ----
+            const bool any_awake = awake[0] || awake[1] || awake[2] || awake[3] || awake[4];
+            if (any_awake) {
+                for (int i = 0; i < 5; ++i)
+                    if (!awake[i]) { awake[i] = true; sleep_t[i] = 0.f; }
+                const float dt_ratio = inv_dt0 * h;
+                const float mA = K.hull_inv_mass, iA = K.hull_inv_I, mB = K.wheel_inv_mass, iB = K.wheel_inv_I;
+                const F2 c0h = c[0];
+                (void)c0h;
+                for (int i = 0; i < 5; ++i) {
+                    const float im = (i == 0) ? mA : mB;
+                    v[i] = v[i] + h * (im * force[i]);
+                    // torque is never applied; damping is 0: v *= 1/(1 + h*0)
+                    v[i] = (1.0f / (1.0f + h * 0.0f)) * v[i];
+                    w[i] *= 1.0f / (1.0f + h * 0.0f);
+                }
+                // InitVelocityConstraints (+ warm start), joints 3, 2, 1, 0
+                for (int kk = 3; kk >= 0; --kk) {
+                    Joint& j = J[kk];
+                    const int bi = kk + 1;
+                    const Rot qA = make_rot(a[0]), qB = make_rot(a[bi]);
+                    j.rA = rmul(qA, f2((float)(c_wheelpos[kk][0] * CR_SIZE), (float)(c_wheelpos[kk][1] * CR_SIZE)) - f2(hull_lcx, hull_lcy));
+                    j.rB = rmul(qB, f2(0.f, 0.f) - f2(0.f, 0.f));
+                    j.k00 = mA + mB + j.rA.y * j.rA.y * iA + j.rB.y * j.rB.y * iB;
+                    j.k01 = -j.rA.y * j.rA.x * iA - j.rB.y * j.rB.x * iB;
+                    j.k02 = -j.rA.y * iA - j.rB.y * iB;
+                    j.k11 = mA + mB + j.rA.x * j.rA.x * iA + j.rB.x * j.rB.x * iB;
+                    j.k12 = j.rA.x * iA + j.rB.x * iB;
+                    j.k22 = iA + iB;
+                    j.motor_mass = iA + iB;
+                    if (j.motor_mass > 0.0f) j.motor_mass = 1.0f / j.motor_mass;
+                    const float joint_angle = a[bi] - a[0] - 0.0f;
+                    const float lower = -0.4f, upper = +0.4f;
+                    if (joint_angle <= lower) {
+                        if (j.limit_state != 1) j.iz = 0.0f;
+                        j.limit_state = 1;
+                    } else if (joint_angle >= upper) {
+                        if (j.limit_state != 2) j.iz = 0.0f;
+                        j.limit_state = 2;
+                    } else {
+                        j.limit_state = 0;
+                        j.iz = 0.0f;
+                    }
+                    j.ix *= dt_ratio; j.iy *= dt_ratio; j.iz *= dt_ratio; j.motor_impulse *= dt_ratio;
+                    const F2 P = f2(j.ix, j.iy);
+                    v[0] = v[0] - mA * P;
+                    w[0] -= iA * (cross(j.rA, P) + j.motor_impulse + j.iz);
+                    v[bi] = v[bi] + mB * P;
+                    w[bi] += iB * (cross(j.rB, P) + j.motor_impulse + j.iz);
+                }
+                const float max_motor_impulse = h * (float)(180 * 900 * CR_SIZE * CR_SIZE);
+#pragma unroll 1
+                for (int it = 0; it < 6 * 30; ++it) {
+#pragma unroll
+                    for (int kk = 3; kk >= 0; --kk) {
+                        Joint& j = J[kk];
+                        const int bi = kk + 1;
+                        F2 vA = v[0], vB = v[bi];
+                        float wA = w[0], wB = w[bi];
+                        {   // motor
+                            const float Cdot = wB - wA - j.motor_speed;
+                            float impulse = -j.motor_mass * Cdot;
+                            const float old = j.motor_impulse;
+                            j.motor_impulse = clampf(old + impulse, -max_motor_impulse, max_motor_impulse);
+                            impulse = j.motor_impulse - old;
+                            wA -= iA * impulse;
+                            wB += iB * impulse;
+                        }
+                        if (j.limit_state != 0) {
+                            const F2 Cdot1 = ((vB + cross_sv(wB, j.rB)) - vA) - cross_sv(wA, j.rA);
+                            const float Cdot2 = wB - wA;
+                            float i0, i1, i2;
+                            solve33(j, Cdot1.x, Cdot1.y, Cdot2, i0, i1, i2);
+                            i0 = -i0; i1 = -i1; i2 = -i2;
+                            const float ni = j.iz + i2;
+                            const bool release = (j.limit_state == 1) ? (ni < 0.0f) : (ni > 0.0f);
+                            if (release) {
+                                const F2 rhs = f2(-Cdot1.x + j.iz * j.k02, -Cdot1.y + j.iz * j.k12);
+                                const F2 red = solve22(j.k00, j.k01, j.k01, j.k11, rhs);
+                                i0 = red.x; i1 = red.y; i2 = -j.iz;
+                                j.ix += red.x; j.iy += red.y; j.iz = 0.0f;
+                            } else {
+                                j.ix += i0; j.iy += i1; j.iz += i2;
+                            }
+                            const F2 P = f2(i0, i1);
+                            vA = vA - mA * P;
+                            wA -= iA * (cross(j.rA, P) + i2);
+                            vB = vB + mB * P;
+                            wB += iB * (cross(j.rB, P) + i2);
+                        } else {
+                            const F2 Cdot = ((vB + cross_sv(wB, j.rB)) - vA) - cross_sv(wA, j.rA);
+                            const F2 imp = solve22(j.k00, j.k01, j.k01, j.k11, f2(-Cdot.x, -Cdot.y));
+                            j.ix += imp.x; j.iy += imp.y;
+                            vA = vA - mA * imp;
+                            wA -= iA * cross(j.rA, imp);
+                            vB = vB + mB * imp;
+                            wB += iB * cross(j.rB, imp);
+                        }
+                        v[0] = vA; w[0] = wA; v[bi] = vB; w[bi] = wB;
+                    }
+                }
+                // integrate positions
+                for (int i = 0; i < 5; ++i) {
+                    const F2 tr = h * v[i];
+                    if (dot(tr, tr) > B2_MAX_TRANSLATION * B2_MAX_TRANSLATION) v[i] = (B2_MAX_TRANSLATION / sqrtf(dot(tr, tr))) * v[i];
+                    const float r = h * w[i];
+                    if (r * r > B2_MAX_ROTATION * B2_MAX_ROTATION) w[i] *= B2_MAX_ROTATION / fabsf(r);
+                    c[i] = c[i] + h * v[i];
+                    a[i] += h * w[i];
+                }
+                // position iterations
+                bool position_solved = false;
+#pragma unroll 1
+                for (int it = 0; it < 2 * 30; ++it) {
+                    bool ok = true;
+#pragma unroll
+                    for (int kk = 3; kk >= 0; --kk) {
+                        const Joint& j = J[kk];
+                        const int bi = kk + 1;
+                        F2 cA = c[0], cB = c[bi];
+                        float aA = a[0], aB = a[bi];
+                        float angular_error = 0.0f;
+                        if (j.limit_state != 0) {
+                            const float angle = aB - aA - 0.0f;
+                            float limit_impulse;
+                            if (j.limit_state == 1) {
+                                float C = angle - (-0.4f);
+                                angular_error = -C;
+                                C = clampf(C + B2_ANGULAR_SLOP, -B2_MAX_ANGULAR_CORRECTION, 0.0f);
+                                limit_impulse = -j.motor_mass * C;
+                            } else {
+                                float C = angle - 0.4f;
+                                angular_error = C;
+                                C = clampf(C - B2_ANGULAR_SLOP, 0.0f, B2_MAX_ANGULAR_CORRECTION);
+                                limit_impulse = -j.motor_mass * C;
+                            }
+                            aA -= iA * limit_impulse;
+                            aB += iB * limit_impulse;
+                        }
+                        const Rot qA = make_rot(aA), qB = make_rot(aB);
+                        const F2 rA = rmul(qA, f2((float)(c_wheelpos[kk][0] * CR_SIZE), (float)(c_wheelpos[kk][1] * CR_SIZE)) - f2(hull_lcx, hull_lcy));
+                        const F2 rB = rmul(qB, f2(0.f, 0.f) - f2(0.f, 0.f));
+                        const F2 C = ((cB + rB) - cA) - rA;
+                        const float position_error = sqrtf(dot(C, C));
+                        const float k00 = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
+                        const float k01 = -iA * rA.x * rA.y - iB * rB.x * rB.y;
+                        const float k11 = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
+                        F2 imp = solve22(k00, k01, k01, k11, C);
+                        imp = f2(-imp.x, -imp.y);
+                        cA = cA - mA * imp;
+                        aA -= iA * cross(rA, imp);
+                        cB = cB + mB * imp;
+                        aB += iB * cross(rB, imp);
+                        c[0] = cA; a[0] = aA; c[bi] = cB; a[bi] = aB;
+                        ok = (position_error <= B2_LINEAR_SLOP && angular_error <= B2_ANGULAR_SLOP) && ok;
+                    }
+                    if (ok) { position_solved = true; break; }
+                }
+                // sleeping
+                float min_sleep = 3.4e38f;
+                for (int i = 0; i < 5; ++i) {
+                    if (w[i] * w[i] > B2_ANGULAR_SLEEP_TOL * B2_ANGULAR_SLEEP_TOL || dot(v[i], v[i]) > B2_LINEAR_SLEEP_TOL * B2_LINEAR_SLEEP_TOL) {
+                        sleep_t[i] = 0.0f;
+                        min_sleep = 0.0f;
+                    } else {
+                        sleep_t[i] += h;
+                        min_sleep = fminf(min_sleep, sleep_t[i]);
+                    }
+                }
+                if (min_sleep >= B2_TIME_TO_SLEEP && position_solved)
+                    for (int i = 0; i < 5; ++i) { awake[i] = false; sleep_t[i] = 0.f; v[i] = f2(0.f, 0.f); w[i] = 0.f; }
+            }
+            inv_dt0 = 1.0f / h;
+            step_count += 1;
+            env_steps += 1;
+        }
+        // ---- store ----
+        {
+            float* b = p.body + (size_t)ci * 40;
+            for (int i = 0; i < 5; ++i) {
+                b[8 * i] = c[i].x; b[8 * i + 1] = c[i].y; b[8 * i + 2] = a[i]; b[8 * i + 3] = v[i].x; b[8 * i + 4] = v[i].y;
+                b[8 * i + 5] = w[i]; b[8 * i + 6] = sleep_t[i]; b[8 * i + 7] = awake[i] ? 1.f : 0.f;
+            }
+            float* j = p.joint + (size_t)ci * 24;
+            for (int k = 0; k < 4; ++k) {
+                j[6 * k] = J[k].ix; j[6 * k + 1] = J[k].iy; j[6 * k + 2] = J[k].iz; j[6 * k + 3] = J[k].motor_impulse;
+                j[6 * k + 4] = (float)J[k].limit_state; j[6 * k + 5] = J[k].motor_speed;
+            }
+            double* wd = p.wheel + (size_t)ci * 8;
+            for (int k = 0; k < 4; ++k) wd[k] = omega[k];
+            wd[4] = gas[0]; wd[5] = gas[1]; wd[6] = brake; wd[7] = steer;
+            p.reward[2 * ci] = reward; p.reward[2 * ci + 1] = prev_reward;
+            cn[0] = tile_visited; cn[1] = last_block; cn[2] = has_block; cn[3] = car_done ? 1 : 0;
+        }
+        rew[ci] = (float)step_reward;
+    }
+    // ---- env level: done = any(car done) (FlattenMultiAgentObservation.step, atari_wrappers.py:323-331),
+    //      gym TimeLimit (register.py:14,21) ----
+    bool any_done = car_done;
+    if (p.players == 2) any_done = any_done || __shfl_xor_sync(0xffffffffu, (int)car_done, 1) != 0;
+    if (active && player == 0) {
+        const int steps = p.step_count[e] + env_steps;
+        p.step_count[e] = steps;
+        p.inv_dt0[e] = 1.0f / (1.0f / CR_FPS);
+        int el = p.elapsed[e] + 1;
+        bool trunc = false;
+        if (p.max_episode_steps > 0 && el >= p.max_episode_steps) { trunc = !any_done; any_done = true; }
+        p.elapsed[e] = el;
+        done_out[e] = any_done ? 1 : 0;
+        truncated_out[e] = trunc ? 1 : 0;
+        num_steps_out[e] = steps;
+        p.env_done[e] = any_done ? 1 : 0;
+        if (any_done) {
+            atomicAdd(&p.stats[0], 1ull);
+            atomicAdd(&p.stats[1], (unsigned long long)el);
+            atomicAdd(&p.stats[2], (unsigned long long)p.counters[4 * ci]);
+        }
+    }
+}
+
+// state[car][24]: hull x, y, angle, vx, vy, w; wheel k: joint angle, omega, gas, #tiles; reward; tiles visited
+__global__ void car_get_state_kernel(CarDev p, double* state) {
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= p.n * p.players) return;
+    const float* b = p.body + (size_t)ci * 40;
+    const CarHullConst* K = p.consts;
+    double* s = state + (size_t)ci * 24;
+    const Rot q = make_rot(b[2]);
+    const F2 pos = f2(b[0], b[1]) - rmul(q, f2(K->hull_lcx, K->hull_lcy));
+    s[0] = pos.x; s[1] = pos.y; s[2] = b[2]; s[3] = b[3]; s[4] = b[4]; s[5] = b[5];
+    const double* wd = p.wheel + (size_t)ci * 8;
+    for (int k = 0; k < 4; ++k) {
+        int cnt = 0;
+        for (int i = 0; i < 16; ++i) cnt += __popc(p.touching[(size_t)ci * 64 + 16 * k + i]);
+        s[6 + 4 * k] = (double)(b[8 * (k + 1) + 2] - b[2]);
+        s[7 + 4 * k] = wd[k];
+        s[8 + 4 * k] = (k >= 2) ? wd[4 + k - 2] : 0.0;
+        s[9 + 4 * k] = cnt;
+    }
+    s[22] = p.reward[2 * ci];
+    s[23] = p.counters[4 * ci];
+}
+
+__global__ void car_random_actions_kernel(float* actions, int n_values, uint64_t seed, uint64_t step) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i * 4 >= n_values) return;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)i, 1u, (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    for (int k = 0; k < 4; ++k)
+        if (i * 4 + k < n_values) actions[i * 4 + k] = (float)r[k] * (2.0f / 4294967296.0f) - 1.0f;   // U[-1, 1)
+}
+
+static double* g_track_scratch = nullptr;
+static size_t g_track_scratch_envs = 0;
+
+cudaError_t car_track_scratch(const CarDev& p, double** out) {
+    if (g_track_scratch_envs < (size_t)p.n) {
+        if (g_track_scratch) cudaFree(g_track_scratch);
+        cudaError_t e = cudaMalloc(&g_track_scratch, (size_t)p.n * CAR_MAX_TRACK * 3 * sizeof(double));
+        if (e != cudaSuccess) { g_track_scratch = nullptr; g_track_scratch_envs = 0; return e; }
+        g_track_scratch_envs = (size_t)p.n;
+    }
+    *out = g_track_scratch;
+    return cudaSuccess;
+}
+
+cudaError_t launch_car_reset(const CarDev& p, int only_done, cudaStream_t s) {
+    double* scratch = nullptr;
+    cudaError_t e0 = car_track_scratch(p, &scratch);
+    if (e0 != cudaSuccess) return e0;
+    car_reset_kernel<<<(p.n + 63) / 64, 64, 0, s>>>(p, only_done, g_track_scratch);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_car_step(const CarDev& p, const float* actions, float* rew, uint8_t* done, int32_t* num_steps,
+                            uint8_t* truncated, cudaStream_t s) {
+    const int n_cars = p.n * p.players;
+    car_step_kernel<<<(n_cars + 63) / 64, 64, 0, s>>>(p, actions, rew, done, num_steps, truncated);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_car_get_state(const CarDev& p, double* state, cudaStream_t s) {
+    const int n_cars = p.n * p.players;
+    car_get_state_kernel<<<(n_cars + 127) / 128, 128, 0, s>>>(p, state);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_car_random_actions(float* actions, int n_values, uint64_t seed, uint64_t step, cudaStream_t s) {
+    car_random_actions_kernel<<<((n_values + 3) / 4 + 127) / 128, 128, 0, s>>>(actions, n_values, seed, step);
+    return cudaGetLastError();
+}
+
+}  // namespace crl

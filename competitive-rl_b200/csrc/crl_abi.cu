@@ -25,6 +25,15 @@ static int fail(int code, const char* fmt, ...) {
     return code;
 }
 
+int crl_set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+void crl_count_launch(int n) { g_launches += (uint64_t)n; }
+
 #define CUDA_TRY(expr)                                                                                \
     do {                                                                                              \
         cudaError_t _e = (expr);                                                                      \

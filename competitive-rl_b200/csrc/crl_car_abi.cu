@@ -1,0 +1,349 @@
+// crl_car_abi.cu -- C ABI (include/crl_b200.h, crl_car_*) over the car-racing kernels. Host side only.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/crl_b200.h"
+#include "car_common.cuh"
+
+using namespace crl;
+
+namespace crl {
+extern cudaError_t car_track_scratch(const CarDev& p, double** out);
+}
+
+extern "C" const char* crl_last_error(void);
+extern int crl_set_error(int code, const char* fmt, ...);
+extern void crl_count_launch(int n);
+
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) return crl_set_error(CRL_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+#define LAUNCH(expr, n)      \
+    do {                     \
+        CUDA_TRY(expr);      \
+        crl_count_launch(n); \
+    } while (0)
+
+struct crl_car {
+    crl_car_config cfg;
+    CarDev dev;
+    std::vector<void*> allocs;
+    bool was_reset = false;
+};
+
+// ---- car body mass data: b2PolygonShape::Set + ComputeMass + b2Body::ResetMassData, fp32 ----
+namespace {
+struct P2 { float x, y; };
+
+int hull_of(const P2* in, int n, P2* out) {   // gift wrapping exactly as b2PolygonShape::Set
+    P2 ps[8];
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        bool unique = true;
+        for (int k = 0; k < m; ++k) {
+            const float dx = in[i].x - ps[k].x, dy = in[i].y - ps[k].y;
+            if (dx * dx + dy * dy < 0.5f * 0.005f * 0.5f * 0.005f) { unique = false; break; }
+        }
+        if (unique) ps[m++] = in[i];
+    }
+    int i0 = 0;
+    for (int i = 1; i < m; ++i)
+        if (ps[i].x > ps[i0].x || (ps[i].x == ps[i0].x && ps[i].y < ps[i0].y)) i0 = i;
+    int idx[8], cnt = 0, ih = i0;
+    for (;;) {
+        idx[cnt] = ih;
+        int ie = 0;
+        for (int j = 1; j < m; ++j) {
+            if (ie == ih) { ie = j; continue; }
+            const float rx = ps[ie].x - ps[idx[cnt]].x, ry = ps[ie].y - ps[idx[cnt]].y;
+            const float vx = ps[j].x - ps[idx[cnt]].x, vy = ps[j].y - ps[idx[cnt]].y;
+            const float c = rx * vy - ry * vx;
+            if (c < 0.0f) ie = j;
+            if (c == 0.0f && vx * vx + vy * vy > rx * rx + ry * ry) ie = j;
+        }
+        ++cnt;
+        ih = ie;
+        if (ie == i0) break;
+    }
+    for (int i = 0; i < cnt; ++i) out[i] = ps[idx[i]];
+    return cnt;
+}
+
+void poly_mass(const P2* v, int n, float density, float* mass, P2* center, float* inertia) {
+    volatile float cx = 0.f, cy = 0.f, sx = 0.f, sy = 0.f, area = 0.f, I = 0.f;
+    const float inv3 = 1.0f / 3.0f;
+    for (int i = 0; i < n; ++i) { sx = sx + v[i].x; sy = sy + v[i].y; }
+    sx = (1.0f / n) * sx; sy = (1.0f / n) * sy;
+    for (int i = 0; i < n; ++i) {
+        const float e1x = v[i].x - sx, e1y = v[i].y - sy, e2x = v[(i + 1) % n].x - sx, e2y = v[(i + 1) % n].y - sy;
+        volatile float D = e1x * e2y - e1y * e2x;
+        volatile float tri = 0.5f * D;
+        area = area + tri;
+        volatile float k = tri * inv3;
+        cx = cx + k * (e1x + e2x); cy = cy + k * (e1y + e2y);
+        volatile float intx2 = e1x * e1x + e2x * e1x + e2x * e2x, inty2 = e1y * e1y + e2y * e1y + e2y * e2y;
+        volatile float q = 0.25f * inv3 * D;
+        I = I + q * (intx2 + inty2);
+    }
+    *mass = density * area;
+    volatile float ia = 1.0f / area;
+    cx = ia * cx; cy = ia * cy;
+    center->x = cx + sx; center->y = cy + sy;
+    volatile float in = density * I;
+    volatile float d1 = center->x * center->x + center->y * center->y, d2 = cx * cx + cy * cy;
+    *inertia = in + *mass * (d1 - d2);
+}
+
+uint8_t gray_of(double r, double g, double b) { return (uint8_t)(r * 0.299 + g * 0.587 + b * 0.114); }
+
+void car_constants(CarHullConst* K) {
+    static const float HP[4][8][2] = {
+        {{-60, +130}, {+60, +130}, {+60, +110}, {-60, +110}},
+        {{-15, +120}, {+15, +120}, {+20, +20}, {-20, 20}},
+        {{+25, +20}, {+50, -10}, {+50, -40}, {+20, -90}, {-20, -90}, {-50, -40}, {-50, -10}, {-25, +20}},
+        {{-50, -120}, {+50, -120}, {+50, -90}, {-50, -90}}};
+    static const int HC[4] = {4, 4, 8, 4};
+    float mass = 0.f, I = 0.f, lx = 0.f, ly = 0.f;
+    for (int k = 0; k < 4; ++k) {
+        P2 raw[8], hull[8];
+        for (int i = 0; i < HC[k]; ++i) { raw[i].x = (float)(HP[k][i][0] * 0.02); raw[i].y = (float)(HP[k][i][1] * 0.02); }
+        const int n = hull_of(raw, HC[k], hull);
+        float m, in;
+        P2 c;
+        poly_mass(hull, n, 1.0f, &m, &c, &in);
+        mass += m; lx += m * c.x; ly += m * c.y; I += in;
+    }
+    const float inv_mass = 1.0f / mass;
+    lx = inv_mass * lx; ly = inv_mass * ly;
+    I -= mass * (lx * lx + ly * ly);
+    K->hull_inv_mass = inv_mass; K->hull_inv_I = 1.0f / I; K->hull_lcx = lx; K->hull_lcy = ly;
+    {
+        const float hw = (float)(14 * 0.02), hr = (float)(27 * 0.02);
+        P2 box[4] = {{+hw, -hr}, {+hw, +hr}, {-hw, +hr}, {-hw, -hr}};
+        float m, in;
+        P2 c;
+        poly_mass(box, 4, 0.1f, &m, &c, &in);
+        const float wl = c.x * c.x + c.y * c.y;
+        K->wheel_inv_mass = 1.0f / m;
+        K->wheel_inv_I = 1.0f / (in - m * wl);
+    }
+    uint8_t* g = K->gray;
+    g[G_GRASS] = gray_of(0.4 * 255, 0.8 * 255, 0.4 * 255);
+    g[G_CHECK] = gray_of((int)(0.4 * 255), (int)(0.9 * 255), (int)(0.4 * 255));
+    for (int k = 0; k < 3; ++k) { const double c = (int)(255 * (0.4 + 0.01 * k)); g[G_ROAD0 + k] = gray_of(c, c, c); }
+    g[G_KERB_W] = gray_of(255, 255, 255); g[G_KERB_R] = gray_of(255, 0, 0);
+    g[G_WHEEL] = gray_of(0, 0, 0); g[G_OWN] = gray_of(0.8 * 255, 0, 0); g[G_OTHER] = gray_of(0, 0, 255);
+    g[G_HUD] = gray_of(0, 0, 0); g[G_BLUE] = gray_of(0, 0, 255); g[G_BLUE2] = gray_of(0.2 * 255, 0, 255);
+    g[G_GREEN] = gray_of(0, 255, 0); g[G_RED] = gray_of(255, 0, 0); g[G_TEXT] = gray_of(255, 255, 255);
+}
+
+template <typename T>
+cudaError_t car_alloc(crl_car* h, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (e != cudaSuccess) return e;
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return cudaMemset(q, 0, count * sizeof(T) + 16);
+}
+}  // namespace
+
+extern "C" {
+
+int crl_car_destroy(crl_car* h) {
+    if (!h) return CRL_OK;
+    cudaSetDevice(h->cfg.device);
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+    return CRL_OK;
+}
+
+int crl_car_create(const crl_car_config* cfg, crl_car** out) {
+    if (!cfg || !out) return crl_set_error(CRL_E_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->num_envs <= 0) return crl_set_error(CRL_E_INVALID, "num_envs must be positive");
+    if (cfg->num_players != 1 && cfg->num_players != 2) return crl_set_error(CRL_E_INVALID, "num_players must be 1 or 2");
+    if (cfg->frame_stack < 0 || cfg->frame_stack > CAR_MAX_STACK)
+        return crl_set_error(CRL_E_INVALID, "frame_stack must be in [0, %d]", CAR_MAX_STACK);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return crl_set_error(CRL_E_CUDA, "no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return crl_set_error(CRL_E_INVALID, "device %d out of range", cfg->device);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    crl_car* h = new crl_car();
+    h->cfg = *cfg;
+    CarDev& d = h->dev;
+    memset(&d, 0, sizeof d);
+    const size_t n = (size_t)cfg->num_envs, P = (size_t)cfg->num_players, nc = n * P;
+    d.n = cfg->num_envs; d.players = cfg->num_players; d.c = cfg->frame_stack > 0 ? cfg->frame_stack : 1;
+    d.action_repeat = cfg->action_repeat > 0 ? cfg->action_repeat : 1;
+    d.max_episode_steps = cfg->max_episode_steps;
+    d.first_env = cfg->first_env; d.seed = cfg->seed;
+#define ALLOC(ptr, count)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = car_alloc(h, &(ptr), (count));                                     \
+        if (_e != cudaSuccess) {                                                            \
+            crl_car_destroy(h);                                                             \
+            return crl_set_error(CRL_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(_e));      \
+        }                                                                                   \
+    } while (0)
+    ALLOC(d.n_track, n); ALLOC(d.tiles, n * CAR_MAX_TRACK); ALLOC(d.samples, n * CAR_MAX_SAMPLES);
+    ALLOC(d.start_pose, n * 3); ALLOC(d.step_count, n); ALLOC(d.elapsed, n); ALLOC(d.reset_count, n);
+    ALLOC(d.attempt_count, n); ALLOC(d.inv_dt0, n); ALLOC(d.env_done, n); ALLOC(d.ring_pos, n);
+    ALLOC(d.body, nc * 40); ALLOC(d.joint, nc * 24); ALLOC(d.wheel, nc * 8); ALLOC(d.reward, nc * 2);
+    ALLOC(d.counters, nc * 4); ALLOC(d.touching, nc * 64); ALLOC(d.visited, nc * 16);
+    ALLOC(d.ring, nc * d.c * CAR_PIX); ALLOC(d.overrun, 1); ALLOC(d.stats, 8);
+    CarHullConst* kdev = nullptr;
+    ALLOC(kdev, 1);
+#undef ALLOC
+    CarHullConst K;
+    memset(&K, 0, sizeof K);
+    car_constants(&K);
+    e = cudaMemcpy(kdev, &K, sizeof K, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d.ring_pos, 0xFF, n * sizeof(int32_t));
+    if (e != cudaSuccess) {
+        crl_car_destroy(h);
+        return crl_set_error(CRL_E_CUDA, "init: %s", cudaGetErrorString(e));
+    }
+    d.consts = kdev;
+    *out = h;
+    return CRL_OK;
+}
+
+#define CHECK_HANDLE(h)                                               \
+    do {                                                              \
+        if (!(h)) return crl_set_error(CRL_E_INVALID, "null handle"); \
+        CUDA_TRY(cudaSetDevice((h)->cfg.device));                     \
+    } while (0)
+
+int crl_car_load_glyphs(crl_car* h, const uint8_t* glyphs_host, size_t bytes, void* stream) {
+    CHECK_HANDLE(h);
+    if (!glyphs_host || bytes != (size_t)CRL_CAR_GLYPH_BYTES) return crl_set_error(CRL_E_INVALID, "glyph atlas must be %d bytes", CRL_CAR_GLYPH_BYTES);
+    uint8_t* g = nullptr;
+    CUDA_TRY(car_alloc(h, &g, bytes));
+    CUDA_TRY(cudaMemcpyAsync(g, glyphs_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    h->dev.glyphs = g;
+    return CRL_OK;
+}
+
+int crl_car_inject_tracks(crl_car* h, const double* draws_host, int32_t k_draws, const int32_t* birth_host,
+                          int32_t k_birth, void* stream) {
+    CHECK_HANDLE(h);
+    if (!draws_host || k_draws < 1) return crl_set_error(CRL_E_INVALID, "need at least one attempt of draws per env");
+    cudaStream_t s = (cudaStream_t)stream;
+    double* dd = nullptr;
+    const size_t cnt = (size_t)h->dev.n * k_draws * CAR_DRAWS;
+    CUDA_TRY(car_alloc(h, &dd, cnt));
+    CUDA_TRY(cudaMemcpyAsync(dd, draws_host, cnt * sizeof(double), cudaMemcpyHostToDevice, s));
+    h->dev.track_draws = dd; h->dev.k_draws = k_draws;
+    if (birth_host && k_birth > 0) {
+        int32_t* bb = nullptr;
+        const size_t bc = (size_t)h->dev.n * k_birth * h->dev.players;
+        CUDA_TRY(car_alloc(h, &bb, bc));
+        CUDA_TRY(cudaMemcpyAsync(bb, birth_host, bc * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+        h->dev.birth = bb; h->dev.k_birth = k_birth;
+    }
+    CUDA_TRY(cudaMemsetAsync(h->dev.attempt_count, 0, (size_t)h->dev.n * sizeof(int32_t), s));
+    CUDA_TRY(cudaMemsetAsync(h->dev.reset_count, 0, (size_t)h->dev.n * sizeof(int32_t), s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return CRL_OK;
+}
+
+int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(h->dev.ring_pos, 0xFF, (size_t)h->dev.n * sizeof(int32_t), s));
+    CUDA_TRY(cudaMemsetAsync(h->dev.env_done, 0, (size_t)h->dev.n, s));
+    LAUNCH(launch_car_reset(h->dev, 0, s), 1);
+    LAUNCH(launch_car_render(h->dev, 0, obs_dev, nullptr, s), 2);
+    h->was_reset = true;
+    return CRL_OK;
+}
+
+int crl_car_step_state(crl_car* h, const float* actions_dev, float* rew_dev, uint8_t* done_dev,
+                       int32_t* num_steps_dev, uint8_t* truncated_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
+    if (!actions_dev || !rew_dev || !done_dev || !num_steps_dev || !truncated_dev) return crl_set_error(CRL_E_INVALID, "null step buffer");
+    LAUNCH(launch_car_step(h->dev, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, (cudaStream_t)stream), 1);
+    return CRL_OK;
+}
+
+int crl_car_render_obs(crl_car* h, uint8_t* obs_dev, uint8_t* term_obs_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
+    if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    LAUNCH(launch_car_render(h->dev, 0, obs_dev, term_obs_dev, s), 2);   // post-step frame (terminal obs of finished envs)
+    LAUNCH(launch_car_reset(h->dev, 1, s), 1);                           // auto-reset of finished envs
+    LAUNCH(launch_car_render(h->dev, 1, obs_dev, nullptr, s), 2);        // their reset observation
+    return CRL_OK;
+}
+
+int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* rew_dev, uint8_t* done_dev,
+                 int32_t* num_steps_dev, uint8_t* truncated_dev, uint8_t* term_obs_dev, void* stream) {
+    if (int r = crl_car_step_state(h, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, stream)) return r;
+    return crl_car_render_obs(h, obs_dev, term_obs_dev, stream);
+}
+
+int crl_car_get_state(crl_car* h, double* state_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (!state_dev) return crl_set_error(CRL_E_INVALID, "null buffer");
+    LAUNCH(launch_car_get_state(h->dev, state_dev, (cudaStream_t)stream), 1);
+    return CRL_OK;
+}
+
+int crl_car_get_track(crl_car* h, int32_t env, int32_t* n_out, double* pts_host, int32_t max_points, void* stream) {
+    CHECK_HANDLE(h);
+    if (env < 0 || env >= h->dev.n || !n_out) return crl_set_error(CRL_E_INVALID, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    int32_t n = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n, h->dev.n_track + env, sizeof n, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *n_out = n;
+    if (pts_host) {
+        double* scratch = nullptr;
+        CUDA_TRY(car_track_scratch(h->dev, &scratch));
+        const int m = n < max_points ? n : max_points;
+        if (scratch && m > 0)
+            CUDA_TRY(cudaMemcpy(pts_host, scratch + (size_t)env * CAR_MAX_TRACK * 3, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return CRL_OK;
+}
+
+int crl_car_random_actions(float* actions_dev, int32_t n_values, uint64_t seed, uint64_t step, void* stream) {
+    if (!actions_dev || n_values <= 0) return crl_set_error(CRL_E_INVALID, "bad arguments");
+    LAUNCH(launch_car_random_actions(actions_dev, n_values, seed, step, (cudaStream_t)stream), 1);
+    return CRL_OK;
+}
+
+int crl_car_get_stats(crl_car* h, uint64_t* stats_host, void* stream) {
+    CHECK_HANDLE(h);
+    if (!stats_host) return crl_set_error(CRL_E_INVALID, "null buffer");
+    unsigned long long raw[8];
+    CUDA_TRY(cudaMemcpyAsync(raw, h->dev.stats, sizeof raw, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int i = 0; i < 8; ++i) stats_host[i] = raw[i];
+    return CRL_OK;
+}
+
+int crl_car_check(crl_car* h, void* stream) {
+    CHECK_HANDLE(h);
+    int32_t flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, h->dev.overrun, sizeof flag, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    if (flag == 1) return crl_set_error(CRL_E_SERVES, "injected track-draw / birth-place table exhausted");
+    if (flag == 2) return crl_set_error(CRL_E_STATE, "track generation failed 64 times in a row");
+    return CRL_OK;
+}
+
+}  // extern "C"

@@ -54,6 +54,8 @@ def make_envs(env_id="cPong-v0", seed=0, log_dir="data", num_envs=3, asynchronou
         return CudaPongVecEnv(env_id, num_envs, resized_dim=resized_dim, frame_stack=frame_stack, seed=seed,
                               asynchronous=asynchronous, max_num_rounds=s["kwargs"]["max_num_rounds"], **kwargs)
     if env_id in ("cCarRacing-v0", "cCarRacingDouble-v0"):
-        raise NotImplementedError(
-            "%s: the CUDA car-racing path is not built yet (SURVEY.md section 8 rows a13-a18)" % env_id)
+        from .car_vec_env import CudaCarVecEnv
+        s = spec(env_id)
+        return CudaCarVecEnv(env_id, num_envs, frame_stack=frame_stack, action_repeat=action_repeat, seed=seed,
+                             asynchronous=asynchronous, max_episode_steps=s.get("max_episode_steps", 1000), **kwargs)
     raise ValueError("unknown environment id %r" % (env_id,))

@@ -143,6 +143,74 @@ int crl_pong_get_stats(crl_pong* h, uint64_t* stats_host, void* stream);
 uint64_t crl_launch_count(void);
 int crl_pong_check(crl_pong* h, void* stream);
 
+/* ======================================================================================
+ * cCarRacing-v0 / cCarRacingDouble-v0
+ * Replaces the env stack built by make_car_racing / make_car_racing_double
+ * (car_racing/register.py:29-53): gym.make(id) [TimeLimit(1000)] -> FrameStack |
+ * MultipleFrameStack + FlattenMultiAgentObservation -> WrapPyTorch, stepped by a vec-env.
+ * ====================================================================================== */
+#define CRL_CAR_DRAWS 24          /* np_random.uniform draws of one _create_track attempt */
+#define CRL_CAR_STATE_DOUBLES 24
+#define CRL_CAR_GLYPH_BYTES (11 * 8 * 4 + 11)
+
+typedef struct crl_car crl_car;
+
+typedef struct crl_car_config {
+    int32_t num_envs;
+    int32_t num_players;        /* 1 = "cCarRacing-v0", 2 = "cCarRacingDouble-v0" */
+    int32_t frame_stack;        /* make_envs frame_stack; 0 = None */
+    int32_t action_repeat;      /* CarRacing(action_repeat=...), 0/None = 1 */
+    int32_t max_episode_steps;  /* gym registry TimeLimit (car_racing/register.py:14,21): 1000; 0 = off */
+    int32_t device;
+    uint64_t seed;              /* track / birth-place RNG (Philox) */
+    int64_t first_env;          /* global index of env 0 of this shard */
+} crl_car_config;
+
+int crl_car_create(const crl_car_config* cfg, crl_car** out);
+int crl_car_destroy(crl_car* h);
+
+/* HUD glyphs: the reward text "%05.0f" is drawn into every observation with COMIC.TTF 5 px,
+ * non-antialiased (car_racing_multi_players.py:225-229, 669).  uint8 [11][8][4] bitmaps of
+ * "0123456789-" followed by [11] advances.  Optional: without it no text is drawn. */
+int crl_car_load_glyphs(crl_car* h, const uint8_t* glyphs_host, size_t bytes, void* stream);
+
+/* Validation mode: draws_host[num_envs][k_draws][24] = the np_random.uniform values of the k-th
+ * _create_track attempt of each env (car_racing_multi_players.py:268-270), birth_host
+ * [num_envs][k_birth][num_players] = the shuffled birth_place_indices of the k-th reset
+ * (:508-509; may be NULL).  Synchronises. */
+int crl_car_inject_tracks(crl_car* h, const double* draws_host, int32_t k_draws, const int32_t* birth_host,
+                          int32_t k_birth, void* stream);
+
+/* VecEnv.reset(): obs_dev uint8 [num_envs][num_players * C][96][96]. */
+int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream);
+
+/* VecEnv.step with auto-reset.
+ *   actions_dev     float32 [num_envs][num_players][2]  (steer, gas/brake), clipped like process_action
+ *   rew_dev         float32 [num_envs][num_players]     per-car step reward (the Double wrapper returns [:, 0])
+ *   done_dev        uint8   [num_envs]                  any car done, or TimeLimit
+ *   num_steps_dev   int32   [num_envs]                  info["num_steps"]
+ *   truncated_dev   uint8   [num_envs]                  info["TimeLimit.truncated"]
+ *   term_obs_dev    may be NULL; else same layout as obs: rows of finished envs receive
+ *                   info["terminal_observation"]. */
+int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* rew_dev, uint8_t* done_dev,
+                 int32_t* num_steps_dev, uint8_t* truncated_dev, uint8_t* term_obs_dev, void* stream);
+
+/* the two halves of crl_car_step: game core (no rendering, no auto-reset), then
+ * render + auto-reset + render of the reset envs */
+int crl_car_step_state(crl_car* h, const float* actions_dev, float* rew_dev, uint8_t* done_dev,
+                       int32_t* num_steps_dev, uint8_t* truncated_dev, void* stream);
+int crl_car_render_obs(crl_car* h, uint8_t* obs_dev, uint8_t* term_obs_dev, void* stream);
+
+/* float64 [num_envs * num_players][24]: hull x, y, angle, vx, vy, w; per wheel: joint angle,
+ * omega, gas, #tiles touched; reward; tiles visited. */
+int crl_car_get_state(crl_car* h, double* state_dev, void* stream);
+/* number of tiles of env `env`'s current track, and (if non-NULL) its track points float64 [n][3] beta, x, y */
+int crl_car_get_track(crl_car* h, int32_t env, int32_t* n_out, double* pts_host, int32_t max_points, void* stream);
+
+int crl_car_random_actions(float* actions_dev, int32_t n_values, uint64_t seed, uint64_t step, void* stream);
+int crl_car_get_stats(crl_car* h, uint64_t* stats_host, void* stream);   /* [0] episodes [1] sum length [2] sum tiles */
+int crl_car_check(crl_car* h, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,157 @@
+"""CUDA car-racing path (through the C ABI) against the CPU oracle and against fixtures recorded
+by running the reference's own car Python on the stand-in Box2D.
+
+Stated tolerances (fp32 solver on both sides; the only arithmetic differences are CUDA vs glibc
+sinf/cosf/sin/cos/atan2 in the last ulp, which a 240-iteration solver amplifies slowly):
+  * generated track points: |d| <= 1e-9 (fp64 libm differences)
+  * hull pose over 200 steps of moderate driving: position <= 0.02 units, angle <= 0.01 rad
+  * per-step rewards: <= 1e-4; tiles visited and done flags: identical
+  * observations: mean pixel mismatch per frame <= 0.1 %, worst frame <= 2 %
+Once a car spins (full throttle + steering) the dynamics are chaotic and trajectories separate;
+the tests therefore drive moderately."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _make(env_id, n, **kw):
+    from competitive_rl_b200 import make_envs
+    kw.setdefault("frame_stack", 4)
+    return make_envs(env_id, num_envs=n, log_dir=None, **kw)
+
+
+@pytest.mark.parametrize("name", ["car_single_seed123", "car_single_seed5_rep2", "car_double"])
+def test_track_generator_matches_reference_fixture(name):
+    g = load_golden(name)
+    P = int(g["n_players"])
+    draws = g["all_draws"].reshape(1, -1, 24)
+    envs = _make("cCarRacing-v0" if P == 1 else "cCarRacingDouble-v0", 1, track_draws=draws,
+                 birth=g["birth"].reshape(1, 1, P).astype(np.int32), action_repeat=int(g["action_repeat"]))
+    envs.reset()
+    tr = envs.get_track(0)
+    assert tr.shape[0] == g["track"].shape[0]
+    assert np.abs(tr - g["track"][:, 1:]).max() <= 1e-9
+    # and the first steps of the reference rollout (before any chaotic separation)
+    s0 = envs.get_state().cpu().numpy()[0]
+    assert np.abs(s0[:, :6] - g["state0"][:, :6]).max() <= 1e-5
+    T = 60
+    for t in range(T):
+        a = g["actions"][t].astype(np.float32)
+        obs, r, d, info = envs.step(a[None] if P == 2 else a)
+        s = envs.get_state().cpu().numpy()[0]
+        assert np.abs(s[:, :2] - g["states"][t][:, :2]).max() <= 0.02, (name, t)
+        assert np.abs(s[:, 2] - g["states"][t][:, 2]).max() <= 0.01, (name, t)
+        assert np.abs(info.rewards.cpu().numpy()[0] - g["rewards"][t]).max() <= 1e-4, (name, t)
+        assert np.array_equal(s[:, 23], g["states"][t][:, 23]), (name, t)
+    envs.check()
+    envs.close()
+
+
+@pytest.mark.parametrize("P,N,T", [(1, 32, 200), (2, 16, 150)])
+def test_rollout_and_pixels_vs_oracle(P, N, T):
+    import car_oracle as C
+    from competitive_rl_b200 import _native
+    rng = np.random.RandomState(11)
+    draws = np.zeros((N, 4, 24))
+    tracks = []
+    for e in range(N):
+        tr, bd, d = C.make_track(rng)
+        draws[e, :] = d
+        tracks.append((tr, bd))
+    birth = np.tile(np.arange(P)[None, None], (N, 4, 1)).astype(np.int32)
+    envs = _make("cCarRacing-v0" if P == 1 else "cCarRacingDouble-v0", N, track_draws=draws, birth=birth)
+    glyphs = C.load_glyphs(_native.DEFAULT_CAR_GLYPHS)
+    orcs = [C.CarOracleEnv(P, 1, glyphs) for _ in range(N)]
+    og = envs.reset().cpu().numpy()
+    oo = [o.reset(*tracks[e], list(range(P))) for e, o in enumerate(orcs)]
+    for e in range(N):
+        for p in range(P):
+            assert np.array_equal(og[e, p * 4 + 3], oo[e][p]) and np.array_equal(og[e, p * 4], oo[e][p])
+    arng = np.random.default_rng(1)
+    steer = np.zeros((N, P))
+    mism = []
+    for t in range(T):
+        if t % 25 == 0:
+            steer = arng.uniform(-0.25, 0.25, (N, P))
+        gas = 0.5 if (t // 60) % 2 == 0 else -0.3
+        a = np.stack([steer, np.full((N, P), gas)], axis=-1).astype(np.float32)
+        obs, r, d, info = envs.step(a if P == 2 else a[:, 0])
+        sg = envs.get_state().cpu().numpy()
+        rg = info.rewards.cpu().numpy()
+        og = obs.cpu().numpy()
+        dg = d.cpu().numpy().reshape(N)
+        for e in range(N):
+            oo_e, ro, do, ns = orcs[e].step(a[e].astype(np.float64))
+            so = orcs[e].get_state()
+            assert np.abs(sg[e][:, :2] - so[:, :2]).max() <= 0.02, (t, e)
+            assert np.abs(sg[e][:, 2] - so[:, 2]).max() <= 0.01, (t, e)
+            assert np.abs(rg[e] - ro).max() <= 1e-4, (t, e)
+            assert np.array_equal(sg[e][:, 23], so[:, 23]), (t, e)
+            assert bool(dg[e]) == bool(do.any()), (t, e)
+            if t % 10 == 0:
+                for p in range(P):
+                    mism.append(float((og[e, p * 4 + 3] != oo_e[p]).mean()))
+    assert np.mean(mism) <= 1e-3, np.mean(mism)
+    assert np.max(mism) <= 2e-2, np.max(mism)
+    envs.check()
+    envs.close()
+
+
+def test_autoreset_timelimit_and_stack_layout():
+    N = 8
+    envs = _make("cCarRacingDouble-v0", N, seed=5, max_episode_steps=30)
+    o = envs.reset()
+    assert tuple(o.shape) == (N, 8, 96, 96) and o.dtype == torch.uint8
+    assert torch.equal(o[:, 0], o[:, 3]) and torch.equal(o[:, 4], o[:, 7])     # FrameStack.reset: n copies
+    assert not torch.equal(o[:, 0], o[:, 4])                                     # the two players' views differ
+    tracks0 = [envs.get_track(e) for e in range(N)]
+    a = torch.zeros((N, 2, 2), device="cuda")
+    a[:, :, 1] = 0.4
+    prev = o.clone()
+    for t in range(30):
+        o, r, d, info = envs.step(a)
+        if t < 29:
+            assert not bool(d.any())
+            assert torch.equal(o[:, 0:3], prev[:, 1:4]) and torch.equal(o[:, 4:7], prev[:, 5:8])   # deque shift
+            assert torch.equal(r[:, 0], info.rewards[:, 0])
+        prev = o.clone()
+    assert bool(d.all())                                                         # TimeLimit(30)
+    assert bool(info.truncated.bool().all())
+    assert int(info.num_steps[0]) == 30
+    term = info.terminal_observation()
+    assert torch.equal(o[:, 0], o[:, 3])                                         # already the reset observation
+    assert not torch.equal(term[:, 3], o[:, 3])
+    assert any(len(envs.get_track(e)) != len(tracks0[e]) or not np.array_equal(envs.get_track(e), tracks0[e])
+               for e in range(N))                                                # a new random track per reset
+    i0 = info[0]
+    assert i0[0]["num_steps"] == 30 and "terminal_observation" in i0 and i0["TimeLimit.truncated"] is True
+    envs.check()
+    envs.close()
+
+
+def test_1024_envs_properties():
+    """BASELINE config 4 size: cCarRacing-v0, 1024 envs."""
+    N = 1024
+    envs = _make("cCarRacing-v0", N, seed=3)
+    o = envs.reset()
+    assert tuple(o.shape) == (N, 4, 96, 96)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    total = torch.zeros(N, device="cuda")
+    for t in range(120):
+        a = torch.rand((N, 2), generator=gen, device="cuda") * 2 - 1
+        a[:, 1] = a[:, 1].abs() * 0.6
+        a[:, 0] *= 0.2
+        o, r, d, info = envs.step(a)
+        total += r[:, 0]
+        assert int(o[:, 3, 88:, 40:44].max()) == 0          # HUD bar is black between the indicators
+    s = envs.get_state().cpu().numpy()[:, 0]
+    assert (s[:, 23] >= 3).mean() > 0.9                     # nearly every car collected tiles
+    assert float(total.mean()) > 0
+    lens = np.array([len(envs.get_track(e)) for e in range(0, N, 64)])
+    assert lens.min() > 150 and lens.max() <= 512
+    envs.check()
+    envs.close()
