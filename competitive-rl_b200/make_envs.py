@@ -56,6 +56,7 @@ def make_envs(env_id="cPong-v0", seed=0, log_dir="data", num_envs=3, asynchronou
     if env_id in ("cCarRacing-v0", "cCarRacingDouble-v0"):
         from .car_vec_env import CudaCarVecEnv
         s = spec(env_id)
+        kwargs.setdefault("max_episode_steps", s.get("max_episode_steps", 1000))   # gym TimeLimit of the registry entry
         return CudaCarVecEnv(env_id, num_envs, frame_stack=frame_stack, action_repeat=action_repeat, seed=seed,
-                             asynchronous=asynchronous, max_episode_steps=s.get("max_episode_steps", 1000), **kwargs)
+                             asynchronous=asynchronous, **kwargs)
     raise ValueError("unknown environment id %r" % (env_id,))
