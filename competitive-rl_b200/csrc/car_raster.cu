@@ -239,17 +239,17 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
         hud_rect(img, 30 * s, H - 2 * h, s * (0.8 * hud_vals[6]), 2 * h, G[G_RED], tid);
         __syncthreads();
         if (tid == 0 && p.glyphs != nullptr) {     // draw_text("%05.0f" % reward) at (W/100, H - H/20)
+            // "%05.0f": round half to even, sign kept for negative values, zero padded to width 5
             const double rv = hud_vals[7];
-            double mag = rint(fabs(rv));             // "%.0f": round half to even
-            const bool negative = rv < 0 && !(mag == 0 && false);
+            double mag = rint(fabs(rv));
             char digits[24];
             int nd = 0;
             if (mag == 0) digits[nd++] = 0;
             while (mag >= 1 && nd < 20) { const double qd = floor(mag / 10.0); digits[nd++] = (char)(mag - qd * 10.0); mag = qd; }
-            const int width = 5, body = nd + (negative || (rv < 0) ? 1 : 0);
+            const int body = nd + (rv < 0 ? 1 : 0);
             int pen = (int)(W / 100);
             const int y0 = (int)(H - H / 20);
-            const int pad = width > body ? width - body : 0;
+            const int pad = 5 > body ? 5 - body : 0;
             for (int i = 0; i < body + pad; ++i) {
                 int gi;
                 if (rv < 0 && i == 0) gi = 10;
