@@ -48,27 +48,54 @@ __device__ __forceinline__ void to_screen(const Cam& cm, double wx, double wy, f
     sy = (float)(-mx * cm.s_rot + my * cm.c_rot + CAR_H / 2.0);
 }
 
-// fill a convex polygon given in screen space into the key buffer; `lanes` threads cooperate
-__device__ void fill_poly(unsigned int* keys, const float* sx, const float* sy, int n, unsigned int key, int lane, int lanes) {
-    float minx = sx[0], maxx = sx[0], miny = sy[0], maxy = sy[0];
-    for (int i = 1; i < n; ++i) {
+constexpr int KEY_STRIDE = CAR_W + 1;   // padded row stride: lanes work on different rows of the same columns
+
+// Fill a convex polygon given in screen space into the key buffer: the warp sweeps the polygon's
+// bounding box (32 pixels per pass, shaped 1x32, 2x16 or 4x8 to suit the box width) and every lane
+// evaluates the edge functions at its pixel centre.  Covered = all cross products >= 0 (or all <= 0).
+template <int N>
+__device__ __forceinline__ void fill_poly_n(unsigned int* keys, const float* sx, const float* sy, unsigned int key, int lane) {
+    float minx = sx[0], maxx = sx[0], miny = sy[0], maxy = sy[0], area2 = 0.f;
+    float ex[N], ey[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int i2 = (i + 1 == N) ? 0 : i + 1;
         minx = fminf(minx, sx[i]); maxx = fmaxf(maxx, sx[i]); miny = fminf(miny, sy[i]); maxy = fmaxf(maxy, sy[i]);
+        area2 += sx[i] * sy[i2] - sx[i2] * sy[i];
+        ex[i] = sx[i2] - sx[i]; ey[i] = sy[i2] - sy[i];
     }
-    const int x0 = max(0, (int)floorf(minx - 0.5f)), x1 = min(CAR_W - 1, (int)ceilf(maxx - 0.5f));
     const int y0 = max(0, (int)floorf(miny - 0.5f)), y1 = min(CAR_H - 1, (int)ceilf(maxy - 0.5f));
+    const int x0 = max(0, (int)floorf(minx - 0.5f)), x1 = min(CAR_W - 1, (int)ceilf(maxx - 0.5f));
     if (x1 < x0 || y1 < y0) return;
-    const int bw = x1 - x0 + 1, total = bw * (y1 - y0 + 1);
-    for (int q = lane; q < total; q += lanes) {
-        const int py = y0 + q / bw, px = x0 + q % bw;
-        const float cx = px + 0.5f, cy = py + 0.5f;
-        bool pos = false, neg = false;
-        for (int i = 0; i < n; ++i) {
-            const int i2 = (i + 1 == n) ? 0 : i + 1;
-            const float cr = (sx[i2] - sx[i]) * (cy - sy[i]) - (sy[i2] - sy[i]) * (cx - sx[i]);
-            pos = pos || cr > 0.f;
-            neg = neg || cr < 0.f;
+    const bool ccw = area2 >= 0.f;
+    const int bw = x1 - x0 + 1;
+    const int lw = (bw <= 8) ? 3 : (bw <= 16) ? 4 : 5;          // log2 of the pass width
+    const int lx = lane & ((1 << lw) - 1), ly = lane >> lw, rows_per_pass = 32 >> lw;
+    for (int yb = y0; yb <= y1; yb += rows_per_pass) {
+        const int y = yb + ly;
+        const float cy = y + 0.5f;
+        for (int xb = x0; xb <= x1; xb += (1 << lw)) {
+            const int x = xb + lx;
+            const float cx = x + 0.5f;
+            bool pos = false, neg = false;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const float cr = ex[i] * (cy - sy[i]) - ey[i] * (cx - sx[i]);
+                pos = pos || cr > 0.f;
+                neg = neg || cr < 0.f;
+            }
+            if ((ccw ? !neg : !pos) && y <= y1 && x <= x1) atomicMax(&keys[y * KEY_STRIDE + x], key);
         }
-        if (!(pos && neg)) atomicMax(&keys[py * CAR_W + px], key);
+    }
+}
+
+__device__ __forceinline__ void fill_poly(unsigned int* keys, const float* sx, const float* sy, int n, unsigned int key, int lane) {
+    switch (n) {
+        case 3: fill_poly_n<3>(keys, sx, sy, key, lane); break;
+        case 4: fill_poly_n<4>(keys, sx, sy, key, lane); break;
+        case 5: fill_poly_n<5>(keys, sx, sy, key, lane); break;
+        case 8: fill_poly_n<8>(keys, sx, sy, key, lane); break;
+        default: break;
     }
 }
 
@@ -86,7 +113,7 @@ __device__ __forceinline__ void hud_rect(uint8_t* img, double x, double y, doubl
 
 __global__ void __launch_bounds__(RASTER_THREADS)
 car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* __restrict__ term_obs) {
-    __shared__ unsigned int keys[CAR_PIX];
+    __shared__ unsigned int keys[CAR_H * KEY_STRIDE];
     __shared__ __align__(16) uint8_t img[CAR_PIX];
     __shared__ int cand[MAX_CAND];
     __shared__ int n_cand;
@@ -134,17 +161,26 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
     const int n_track = p.n_track[e];
     const CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
 
-    // ---- background: grass + checker squares, evaluated per pixel centre ----
+    // ---- background: grass + checker squares at pixel centres.  fp64 only for the per-row terms; the
+    //      per-pixel increment runs in fp32 on values bounded by +-24 (checker grid units), error ~1e-6 ----
     {
         const double kq = CR_PLAYFIELD / 20.0;
-        for (int q = tid; q < CAR_PIX; q += RASTER_THREADS) {
-            const int r = q / CAR_W, c = q % CAR_W;
-            const double dxp = c + 0.5 - CAR_W / 2.0, dyp = r + 0.5 - CAR_H / 2.0;
-            const double sx = dxp * cm.c_rot - dyp * cm.s_rot, sy = dxp * cm.s_rot + dyp * cm.c_rot;
-            const double wx = cm.camx - sx / cm.k, wy = cm.camy - sy / cm.k;
-            const double gx = floor(wx / kq), gy = floor(wy / kq);
-            const bool chk = gx >= -20 && gx < 20 && gy >= -20 && gy < 20 && (((long long)gx) % 2 == 0) && (((long long)gy) % 2 == 0);
-            keys[q] = chk ? G[G_CHECK] : G[G_GRASS];
+        const double inv = 1.0 / (cm.k * kq), ax = cm.camx / kq, ay = cm.camy / kq;
+        const float cinv = (float)(cm.c_rot * inv), sinv = (float)(cm.s_rot * inv);
+        for (int r = warp; r < CAR_H; r += RASTER_THREADS / 32) {
+            const double dyp = r + 0.5 - CAR_H / 2.0;
+            // g(c) = a - (dxp*c_rot - dyp*s_rot)*inv  with dxp = c + 0.5 - 48
+            const double gx0d = ax + dyp * cm.s_rot * inv + (CAR_W / 2.0 - 0.5) * cm.c_rot * inv;
+            const double gy0d = ay - dyp * cm.c_rot * inv + (CAR_W / 2.0 - 0.5) * cm.s_rot * inv;
+            // keep magnitudes small for fp32: subtract the integer part of the row origin
+            const double bx = floor(gx0d), by = floor(gy0d);
+            const float fx0 = (float)(gx0d - bx), fy0 = (float)(gy0d - by);
+            const int ibx = (int)fmax(fmin(bx, 1e6), -1e6), iby = (int)fmax(fmin(by, 1e6), -1e6);
+            for (int c = lane; c < CAR_W; c += 32) {
+                const int gx = ibx + (int)floorf(fx0 - (float)c * cinv), gy = iby + (int)floorf(fy0 - (float)c * sinv);
+                const bool chk = gx >= -20 && gx < 20 && gy >= -20 && gy < 20 && !(gx & 1) && !(gy & 1);
+                keys[r * KEY_STRIDE + c] = chk ? G[G_CHECK] : G[G_GRASS];
+            }
         }
     }
     // ---- cull: tiles whose track point lies within the window's circumscribed circle (ordered by index) ----
@@ -174,13 +210,13 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
             const CarTile T = tiles[cand[q]];
             const int t = cand[q];
             const unsigned int order = 2u * (unsigned)(n_track - 1 - t) + 1u;
-            float sx[5], sy[5];
+            float sx[8], sy[8];
             for (int i = 0; i < T.n; ++i) to_screen(cm, (double)T.px[i], (double)T.py[i], sx[i], sy[i]);
             const uint8_t g = G[G_ROAD0 + t % 3];
-            fill_poly(keys, sx, sy, T.n, (order << 8) | g, lane, 32);
+            fill_poly(keys, sx, sy, T.n, (order << 8) | g, lane);
             if (T.flags & 2) {
                 for (int i = 0; i < 4; ++i) to_screen(cm, (double)T.kx[i], (double)T.ky[i], sx[i], sy[i]);
-                fill_poly(keys, sx, sy, 4, ((order + 1u) << 8) | ((T.flags & 4) ? G[G_KERB_W] : G[G_KERB_R]), lane, 32);
+                fill_poly(keys, sx, sy, 4, ((order + 1u) << 8) | ((T.flags & 4) ? G[G_KERB_W] : G[G_KERB_R]), lane);
             }
         }
     }
@@ -217,11 +253,12 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
                 }
                 g = (ck == pi) ? G[G_OWN] : G[G_OTHER];
             }
-            fill_poly(keys, sx, sy, n, (order << 8) | g, lane, 32);
+            fill_poly(keys, sx, sy, n, (order << 8) | g, lane);
         }
     }
     __syncthreads();
-    for (int q = tid; q < CAR_PIX; q += RASTER_THREADS) img[q] = (uint8_t)(keys[q] & 255u);
+    for (int r = warp; r < CAR_H; r += RASTER_THREADS / 32)
+        for (int c = lane; c < CAR_W; c += 32) img[r * CAR_W + c] = (uint8_t)(keys[r * KEY_STRIDE + c] & 255u);
     __syncthreads();
     // ---- HUD (painted after the scene) ----
     {
