@@ -280,7 +280,10 @@ def run_ours(a):
                    "l2": "each step writes %.2f GB per GPU (>> 126 MB L2); no flush needed"
                          % (BYTES_PER_ENV_STEP * N / 1e9)},
         "roofline": {"bound": "hbm", "kernel": "pong_raster_fast_kernel<84>", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this workload, from the
+                     # committed ncu --set full capture (profiles/r01_ncu_raster_fast_v3_summary.txt)
+                     "traffic": (3.678e9 + 4.8e6) if N == 65536 else None, "peak_source": peak_src,
                      "avg_launch_ms": raster_ms, "bytes_per_launch": BYTES_PER_ENV_STEP * N},
         "e2e": {"value": total_envs * K2 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h * world,
