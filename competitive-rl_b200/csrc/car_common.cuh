@@ -26,19 +26,24 @@ constexpr int CAR_MAX_SAMPLES = CAR_MAX_TRACK / CAR_SAMPLE_STRIDE;
 constexpr int CAR_MAX_STACK = 8;
 constexpr int CAR_GLYPH_BYTES = 11 * 8 * 4 + 11;
 
-// A road tile: convex hull (CCW) of the reference's 5 listed vertices + its kerb, 80 bytes.
+// A road tile, 116 bytes: for the physics the convex hull (CCW, fp32) of the reference's 5 listed
+// vertices; for the renderer the listed vertices and the kerb quad in ROAD-MAP PIXELS, i.e.
+// (int)(obs_scale * -v + 5000) of the fp64 vertex as pygame truncates it (render_road_for_observation_map).
 struct CarTile {
     float px[5], py[5];       // hull vertices (n of them)
-    float kx[4], ky[4];       // kerb quad (valid iff flags & 2)
+    float kx[4], ky[4];       // kerb quad in world units (valid iff flags & 2)
     uint8_t n, flags;         // flags: 1 = exists, 2 = has kerb, 4 = white kerb (block_id even)
     uint16_t pad;
     float cx, cy;             // track point (x, y): centre used for culling
+    int16_t mx[5], my[5];     // listed vertices l1, m, r1, r2, l2 in road-map pixels
+    int16_t kmx[4], kmy[4];   // kerb quad in road-map pixels
 };
 
 struct CarHullConst {         // mass data of the car bodies (b2Body::ResetMassData), computed on the host
     float hull_inv_mass, hull_inv_I, hull_lcx, hull_lcy;
     float wheel_inv_mass, wheel_inv_I;
     uint8_t gray[16];         // palette: see CarGray
+    int checker[80];          // [axis][20][lo, hi]: road-map pixel bounds of the checker squares (car_checker_table)
 };
 enum CarGray { G_GRASS = 0, G_CHECK, G_ROAD0, G_ROAD1, G_ROAD2, G_KERB_W, G_KERB_R, G_WHEEL, G_OWN, G_OTHER, G_HUD,
                G_BLUE, G_BLUE2, G_GREEN, G_RED, G_TEXT };
@@ -56,6 +61,7 @@ struct CarDev {
     CarTile* tiles;           // [n][CAR_MAX_TRACK]
     float2* samples;          // [CAR_MAX_SAMPLES][n] every 8th track point (transposed: coalesced per-thread scans)
     double* start_pose;       // [n][3] beta, x, y of track[0]
+    double* track_pts;        // [n][CAR_MAX_TRACK][3] beta, x, y of the current track (fp64, as generated)
     int32_t* step_count;      // [n] CarRacing.step_count
     int32_t* elapsed;         // [n] TimeLimit._elapsed_steps
     int32_t* reset_count;     // [n] resets so far (RNG / injection cursor)
@@ -89,6 +95,8 @@ cudaError_t launch_car_reset(const CarDev& p, int only_done, cudaStream_t s);
 cudaError_t launch_car_step(const CarDev& p, const float* actions, float* rew, uint8_t* done, int32_t* num_steps,
                             uint8_t* truncated, cudaStream_t s);
 cudaError_t launch_car_render(const CarDev& p, int only_done, uint8_t* obs, uint8_t* term_obs, cudaStream_t s);
+cudaError_t car_raster_init();
+void car_checker_table(int* out);
 cudaError_t launch_car_get_state(const CarDev& p, double* state, cudaStream_t s);
 cudaError_t launch_car_random_actions(float* actions, int n_values, uint64_t seed, uint64_t step, cudaStream_t s);
 

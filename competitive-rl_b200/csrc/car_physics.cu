@@ -194,11 +194,11 @@ __device__ void car_body_reset(const CarDev& p, int ci, double init_angle, doubl
 }
 
 // CarRacing.reset: new track (retry until an attempt succeeds, :499-507), cars at track[0] (:508-512)
-__global__ void car_reset_kernel(CarDev p, int only_done, double* track_scratch /* [n][MAX_TRACK][3] */) {
+__global__ void car_reset_kernel(CarDev p, int only_done) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.n) return;
     if (only_done && !p.env_done[e]) return;
-    double* pts = track_scratch + (size_t)e * CAR_MAX_TRACK * 3;
+    double* pts = p.track_pts + (size_t)e * CAR_MAX_TRACK * 3;
     CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
     const uint64_t gi = (uint64_t)(p.first_env + e);
     int n = 0;
@@ -264,6 +264,17 @@ __global__ void car_reset_kernel(CarDev p, int only_done, double* track_scratch 
         vx[3] = (float)(x2 + CR_TRACK_WIDTH * cos(b2)); vy[3] = (float)(y2 + CR_TRACK_WIDTH * sin(b2));
         vx[4] = (float)(x2 - CR_TRACK_WIDTH * cos(b2)); vy[4] = (float)(y2 - CR_TRACK_WIDTH * sin(b2));
         CarTile t;
+        {   // road-map pixels of the listed (fp64) vertices: obs_scale * -v + world_size / 2, truncated
+            const double osc = (10 / (100 / sqrt(96.0))) * 1.8;
+            const double dvx[5] = {x1 - CR_TRACK_WIDTH * cos(b1), x1 - CR_TRACK_WIDTH / 2 * cos(b1 - CR_PI / 2),
+                                   x1 + CR_TRACK_WIDTH * cos(b1), x2 + CR_TRACK_WIDTH * cos(b2), x2 - CR_TRACK_WIDTH * cos(b2)};
+            const double dvy[5] = {y1 - CR_TRACK_WIDTH * sin(b1), y1 - CR_TRACK_WIDTH / 2 * sin(b1 - CR_PI / 2),
+                                   y1 + CR_TRACK_WIDTH * sin(b1), y2 + CR_TRACK_WIDTH * sin(b2), y2 - CR_TRACK_WIDTH * sin(b2)};
+            for (int k = 0; k < 5; ++k) {
+                t.mx[k] = (int16_t)(int)(osc * -dvx[k] + 5000.0);
+                t.my[k] = (int16_t)(int)(osc * -dvy[k] + 5000.0);
+            }
+        }
         t.n = (uint8_t)convex_hull5(vx, vy, t.px, t.py);
         for (int k = t.n; k < 5; ++k) { t.px[k] = t.px[0]; t.py[k] = t.py[0]; }
         t.flags = (uint8_t)(1 | (tiles[i].flags & 2) | ((i % 2 == 0) ? 4 : 0));
@@ -274,6 +285,17 @@ __global__ void car_reset_kernel(CarDev p, int only_done, double* track_scratch 
         t.kx[1] = (float)(x1 + side * (CR_TRACK_WIDTH + CR_BORDER) * cos(b1)); t.ky[1] = (float)(y1 + side * (CR_TRACK_WIDTH + CR_BORDER) * sin(b1));
         t.kx[2] = (float)(x2 + side * (CR_TRACK_WIDTH + CR_BORDER) * cos(b2)); t.ky[2] = (float)(y2 + side * (CR_TRACK_WIDTH + CR_BORDER) * sin(b2));
         t.kx[3] = (float)(x2 + side * CR_TRACK_WIDTH * cos(b2)); t.ky[3] = (float)(y2 + side * CR_TRACK_WIDTH * sin(b2));
+        {
+            const double osc = (10 / (100 / sqrt(96.0))) * 1.8;
+            const double kdx[4] = {x1 + side * CR_TRACK_WIDTH * cos(b1), x1 + side * (CR_TRACK_WIDTH + CR_BORDER) * cos(b1),
+                                   x2 + side * (CR_TRACK_WIDTH + CR_BORDER) * cos(b2), x2 + side * CR_TRACK_WIDTH * cos(b2)};
+            const double kdy[4] = {y1 + side * CR_TRACK_WIDTH * sin(b1), y1 + side * (CR_TRACK_WIDTH + CR_BORDER) * sin(b1),
+                                   y2 + side * (CR_TRACK_WIDTH + CR_BORDER) * sin(b2), y2 + side * CR_TRACK_WIDTH * sin(b2)};
+            for (int k = 0; k < 4; ++k) {
+                t.kmx[k] = (int16_t)(int)(osc * -kdx[k] + 5000.0);
+                t.kmy[k] = (int16_t)(int)(osc * -kdy[k] + 5000.0);
+            }
+        }
         tiles[i] = t;
     }
     for (int i = n; i < CAR_MAX_TRACK; ++i) tiles[i].flags = 0;
@@ -793,25 +815,8 @@ __global__ void car_random_actions_kernel(float* actions, int n_values, uint64_t
         if (i * 4 + k < n_values) actions[i * 4 + k] = (float)r[k] * (2.0f / 4294967296.0f) - 1.0f;   // U[-1, 1)
 }
 
-static double* g_track_scratch = nullptr;
-static size_t g_track_scratch_envs = 0;
-
-cudaError_t car_track_scratch(const CarDev& p, double** out) {
-    if (g_track_scratch_envs < (size_t)p.n) {
-        if (g_track_scratch) cudaFree(g_track_scratch);
-        cudaError_t e = cudaMalloc(&g_track_scratch, (size_t)p.n * CAR_MAX_TRACK * 3 * sizeof(double));
-        if (e != cudaSuccess) { g_track_scratch = nullptr; g_track_scratch_envs = 0; return e; }
-        g_track_scratch_envs = (size_t)p.n;
-    }
-    *out = g_track_scratch;
-    return cudaSuccess;
-}
-
 cudaError_t launch_car_reset(const CarDev& p, int only_done, cudaStream_t s) {
-    double* scratch = nullptr;
-    cudaError_t e0 = car_track_scratch(p, &scratch);
-    if (e0 != cudaSuccess) return e0;
-    car_reset_kernel<<<(p.n + 63) / 64, 64, 0, s>>>(p, only_done, g_track_scratch);
+    car_reset_kernel<<<(p.n + 63) / 64, 64, 0, s>>>(p, only_done);
     return cudaGetLastError();
 }
 

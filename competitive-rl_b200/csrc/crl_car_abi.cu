@@ -11,10 +11,6 @@
 
 using namespace crl;
 
-namespace crl {
-extern cudaError_t car_track_scratch(const CarDev& p, double** out);
-}
-
 extern "C" const char* crl_last_error(void);
 extern int crl_set_error(int code, const char* fmt, ...);
 extern void crl_count_launch(int n);
@@ -134,12 +130,12 @@ void car_constants(CarHullConst* K) {
         K->wheel_inv_I = 1.0f / (in - m * wl);
     }
     uint8_t* g = K->gray;
-    g[G_GRASS] = gray_of(0.4 * 255, 0.8 * 255, 0.4 * 255);
+    g[G_GRASS] = gray_of((int)(0.4 * 255), (int)(0.8 * 255), (int)(0.4 * 255));
     g[G_CHECK] = gray_of((int)(0.4 * 255), (int)(0.9 * 255), (int)(0.4 * 255));
     for (int k = 0; k < 3; ++k) { const double c = (int)(255 * (0.4 + 0.01 * k)); g[G_ROAD0 + k] = gray_of(c, c, c); }
     g[G_KERB_W] = gray_of(255, 255, 255); g[G_KERB_R] = gray_of(255, 0, 0);
-    g[G_WHEEL] = gray_of(0, 0, 0); g[G_OWN] = gray_of(0.8 * 255, 0, 0); g[G_OTHER] = gray_of(0, 0, 255);
-    g[G_HUD] = gray_of(0, 0, 0); g[G_BLUE] = gray_of(0, 0, 255); g[G_BLUE2] = gray_of(0.2 * 255, 0, 255);
+    g[G_WHEEL] = gray_of(0, 0, 0); g[G_OWN] = gray_of((int)(0.8 * 255), 0, 0); g[G_OTHER] = gray_of(0, 0, 255);
+    g[G_HUD] = gray_of(0, 0, 0); g[G_BLUE] = gray_of(0, 0, 255); g[G_BLUE2] = gray_of((int)(0.2 * 255), 0, 255);
     g[G_GREEN] = gray_of(0, 255, 0); g[G_RED] = gray_of(255, 0, 0); g[G_TEXT] = gray_of(255, 255, 255);
 }
 
@@ -195,7 +191,7 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
         }                                                                                   \
     } while (0)
     ALLOC(d.n_track, n); ALLOC(d.tiles, n * CAR_MAX_TRACK); ALLOC(d.samples, n * CAR_MAX_SAMPLES);
-    ALLOC(d.start_pose, n * 3); ALLOC(d.step_count, n); ALLOC(d.elapsed, n); ALLOC(d.reset_count, n);
+    ALLOC(d.start_pose, n * 3); ALLOC(d.track_pts, n * CAR_MAX_TRACK * 3); ALLOC(d.step_count, n); ALLOC(d.elapsed, n); ALLOC(d.reset_count, n);
     ALLOC(d.attempt_count, n); ALLOC(d.inv_dt0, n); ALLOC(d.env_done, n); ALLOC(d.ring_pos, n);
     ALLOC(d.body, nc * 40); ALLOC(d.joint, nc * 24); ALLOC(d.wheel, nc * 8); ALLOC(d.reward, nc * 2);
     ALLOC(d.counters, nc * 4); ALLOC(d.touching, nc * 64); ALLOC(d.visited, nc * 16);
@@ -206,8 +202,10 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     CarHullConst K;
     memset(&K, 0, sizeof K);
     car_constants(&K);
+    car_checker_table(K.checker);
     e = cudaMemcpy(kdev, &K, sizeof K, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemset(d.ring_pos, 0xFF, n * sizeof(int32_t));
+    if (e == cudaSuccess) e = car_raster_init();
     if (e != cudaSuccess) {
         crl_car_destroy(h);
         return crl_set_error(CRL_E_CUDA, "init: %s", cudaGetErrorString(e));
@@ -311,11 +309,9 @@ int crl_car_get_track(crl_car* h, int32_t env, int32_t* n_out, double* pts_host,
     CUDA_TRY(cudaStreamSynchronize(s));
     *n_out = n;
     if (pts_host) {
-        double* scratch = nullptr;
-        CUDA_TRY(car_track_scratch(h->dev, &scratch));
         const int m = n < max_points ? n : max_points;
-        if (scratch && m > 0)
-            CUDA_TRY(cudaMemcpy(pts_host, scratch + (size_t)env * CAR_MAX_TRACK * 3, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+        if (m > 0)
+            CUDA_TRY(cudaMemcpy(pts_host, h->dev.track_pts + (size_t)env * CAR_MAX_TRACK * 3, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost));
     }
     return CRL_OK;
 }

@@ -27,8 +27,8 @@
  *   - a sensor contact exists exactly while the wheel polygon and the tile polygon are closer
  *     than 2*b2_polygonRadius by the separating-axis measure, evaluated at the start of
  *     world.Step (Box2D: b2TestOverlap on contacts whose fat AABBs overlap);
- *   - the renderer samples the analytic scene at destination pixel centres instead of
- *     re-creating pygame's polygon scan conversion and rotozoom (see render_obs below).
+ *   - the renderer evaluates the reference's paint-crop-rotate-blit pipeline per destination pixel
+ *     with pygame 1.9's polygon fill / rotate rules restated from memory (see render_obs below).
  *
  * Build: gcc -O2 -ffp-contract=off -pthread -shared -fPIC (oracle/Makefile).
  */
@@ -56,6 +56,7 @@
 #define MAX_TRACK 512
 #define MAX_TRACK_RAW 2600
 #define MAX_CARS 2
+#define OBS_SCALE ((10 / (100 / sqrt(96.0))) * 1.8)   /* CarRacing.obs_scale, :211 */
 
 #define SIZE 0.02
 #define ENGINE_POWER (100000000 * SIZE * SIZE)
@@ -637,10 +638,12 @@ typedef struct {
     float tile_raw[MAX_TRACK][5][2];                            /* as listed (draw order) */
     float tile_aabb[MAX_TRACK][4];
     float kerb[MAX_TRACK][4][2];
+    int tile_map[MAX_TRACK][5][2], kerb_map[MAX_TRACK][4][2];   /* road-map pixel coordinates (int-truncated) */
     Car car[MAX_CARS];
     int step_count;
     float inv_dt0;
     uint8_t obs[MAX_CARS][STATE_H * STATE_W];
+    int lazy_render;            /* 1: step/reset do not render; car_oracle_obs renders on demand */
     const uint8_t* glyphs;      /* [11][8][4] bitmaps of "0123456789-" (non-AA COMIC 5 px) then [11] advances; may be NULL */
 } CarEnv;
 
@@ -838,6 +841,9 @@ static void build_tiles(CarEnv* e) {
         for (int k = 0; k < 5; ++k) {
             raw[2 * k] = (float)v[k][0]; raw[2 * k + 1] = (float)v[k][1];
             e->tile_raw[i][k][0] = raw[2 * k]; e->tile_raw[i][k][1] = raw[2 * k + 1];
+            /* render_road_for_observation_map :749-753: (obs_scale * -v + world_size/2), int-truncated by pygame */
+            e->tile_map[i][k][0] = (int)(OBS_SCALE * -v[k][0] + 5000.0);
+            e->tile_map[i][k][1] = (int)(OBS_SCALE * -v[k][1] + 5000.0);
         }
         int cnt = car_oracle_convex_hull(raw, 5, hull);
         e->tile_n[i] = cnt;
@@ -855,7 +861,11 @@ static void build_tiles(CarEnv* e) {
                 {x1 + side * (TRACK_WIDTH + BORDER) * cos(b1), y1 + side * (TRACK_WIDTH + BORDER) * sin(b1)},
                 {x2 + side * (TRACK_WIDTH + BORDER) * cos(b2), y2 + side * (TRACK_WIDTH + BORDER) * sin(b2)},
                 {x2 + side * TRACK_WIDTH * cos(b2), y2 + side * TRACK_WIDTH * sin(b2)}};
-            for (int k = 0; k < 4; ++k) { e->kerb[i][k][0] = (float)kb[k][0]; e->kerb[i][k][1] = (float)kb[k][1]; }
+            for (int k = 0; k < 4; ++k) {
+                e->kerb[i][k][0] = (float)kb[k][0]; e->kerb[i][k][1] = (float)kb[k][1];
+                e->kerb_map[i][k][0] = (int)(OBS_SCALE * -kb[k][0] + 5000.0);
+                e->kerb_map[i][k][1] = (int)(OBS_SCALE * -kb[k][1] + 5000.0);
+            }
         }
     }
 }
@@ -863,123 +873,182 @@ static void build_tiles(CarEnv* e) {
 /* ------------------------------------------------------------------------------------------ */
 /* renderer                                                                                     */
 
-/* Observation of player `pi` (get_observation :622-634).  Geometry follows the reference:
- * camera = hull.position + R(angle)*(0,16), angle = hull.angle or atan2(-vx, vy) above 0.5 m/s
- * (camera_update :791-812); the 96x96 window is the centre of the road map rotated by `angle`
- * at obs_scale px per world unit (camera_view :764-789); cars' fixture polygons on top
- * (Car.draw_for_pygame, car_dynamics.py:284-298); HUD bar and indicators (:645-670); gray =
- * trunc(0.299 R + 0.587 G + 0.114 B) in float64 (:632-633).  Sampling rule (this restatement's
- * own; pygame's scan conversion / rotate cannot be reproduced here): each destination pixel takes
- * the colour of the analytic scene at its centre, polygons in the reference's paint order. */
-static int point_in_convex(const float (*poly)[2], int n, double px, double py) {
-    int pos = 0, neg = 0;
-    for (int i = 0; i < n; ++i) {
-        double ax = poly[i][0], ay = poly[i][1], bx = poly[(i + 1) % n][0], by = poly[(i + 1) % n][1];
-        double cr = (bx - ax) * (py - ay) - (by - ay) * (px - ax);
-        if (cr > 0) pos = 1; else if (cr < 0) neg = 1;
-        if (pos && neg) return 0;
+/* Observation of player `pi`: get_observation (:622-634) -> camera_update("rgb_array") (:791-812) ->
+ * render(mode="internal_rgb_array") (:857-863) = camera_view (:764-789) + Car.draw_for_pygame
+ * (car_dynamics.py:284-298) + render_indicators_for_pygame (:645-670); gray = trunc(0.299 R + 0.587 G +
+ * 0.114 B) in float64.
+ *
+ * The reference paints the whole road once per reset into a 10 000 x 10 000 surface at obs_scale px/unit
+ * (render_road_for_observation_map :732-755), crops 192 x 192 around the camera, rotates the crop
+ * (pygame.transform.rotate) and centre-blits it onto the 96 x 96 screen.  This function evaluates the same
+ * pipeline per destination pixel: screen pixel -> rotated-surface pixel -> (16.16 fixed point) source pixel
+ * -> road-map pixel (U, V), whose colour is the last polygon in paint order that pygame's scanline fill
+ * would have covered it with.  The third-party pieces restated here (pygame 1.9 draw_fillpoly, draw.rect
+ * via polygon, transform.rotate, int truncation of float coordinates) are the same restatements as in
+ * oracle/ref_shim/pygame, against which tests/golden/car_frames.npz pins this function bit for bit. */
+typedef struct { int n; int vx[8], vy[8]; } IPoly;
+
+/* pygame 1.9 draw_fillpoly: is pixel (U, V) filled? */
+static int ipoly_covers(const IPoly* p, int U, int V) {
+    int miny = p->vy[0], maxy = p->vy[0];
+    for (int i = 1; i < p->n; ++i) { if (p->vy[i] < miny) miny = p->vy[i]; if (p->vy[i] > maxy) maxy = p->vy[i]; }
+    if (V < miny || V > maxy) return 0;
+    int xs[8], m = 0;
+    for (int i = 0; i < p->n; ++i) {
+        int i1 = i ? i - 1 : p->n - 1;
+        int y1 = p->vy[i1], y2 = p->vy[i], x1 = p->vx[i1], x2 = p->vx[i];
+        if (y1 > y2) { int t = y1; y1 = y2; y2 = t; t = x1; x1 = x2; x2 = t; }
+        else if (y1 == y2) continue;
+        if ((V >= y1 && V < y2) || (V == maxy && V > y1 && V <= y2)) xs[m++] = (V - y1) * (x2 - x1) / (y2 - y1) + x1;
     }
-    return 1;
+    for (int i = 1; i < m; ++i) { int k = xs[i], j = i - 1; while (j >= 0 && xs[j] > k) { xs[j + 1] = xs[j]; --j; } xs[j + 1] = k; }
+    for (int k = 0; k + 1 < m; k += 2) if (U >= xs[k] && U <= xs[k + 1]) return 1;
+    return 0;
 }
 
 static uint8_t gray_of(double r, double g, double b) { return (uint8_t)(r * 0.299 + g * 0.587 + b * 0.114); }
 
-static void fill_rect_px(uint8_t* img, double x, double y, double w, double h, uint8_t val) {
-    /* pygame.draw.rect on (x, y, w, h): Rect truncates each float; a negative extent grows the other way */
-    int X = (int)x, Y = (int)y, W = (int)w, H = (int)h;
-    int x0 = W >= 0 ? X : X + W, x1 = W >= 0 ? X + W : X + 1;
-    int y0 = H >= 0 ? Y : Y + H, y1 = H >= 0 ? Y + H : Y + 1;
-    if (W == 0 || H == 0) return;
-    if (x0 < 0) x0 = 0; if (y0 < 0) y0 = 0; if (x1 > STATE_W) x1 = STATE_W; if (y1 > STATE_H) y1 = STATE_H;
-    for (int r = y0; r < y1; ++r)
-        for (int c = x0; c < x1; ++c) img[r * STATE_W + c] = val;
+static void fill_ipoly(uint8_t* img, const IPoly* p, uint8_t val) {
+    for (int y = 0; y < STATE_H; ++y)
+        for (int x = 0; x < STATE_W; ++x)
+            if (ipoly_covers(p, x, y)) img[y * STATE_W + x] = val;
 }
 
+/* pygame.draw.rect(screen, color, (x, y, w, h)): Rect truncates the floats; 1.9 draws it as the polygon
+ * (l, t), (r, t), (r, b), (l, b) with r = x + w - 1, b = y + h - 1 */
+static void draw_rect(uint8_t* img, double x, double y, double w, double h, uint8_t val) {
+    int X = (int)x, Y = (int)y, W = (int)w, H = (int)h;
+    IPoly p;
+    p.n = 4;
+    p.vx[0] = X; p.vy[0] = Y; p.vx[1] = X + W - 1; p.vy[1] = Y; p.vx[2] = X + W - 1; p.vy[2] = Y + H - 1; p.vx[3] = X; p.vy[3] = Y + H - 1;
+    fill_ipoly(img, &p, val);
+}
+
+static float f32(double v) { return (float)v; }
+
 static void render_obs(CarEnv* e, int pi) {
-    const double obs_scale = (10.0 / (100.0 / sqrt(96.0))) * 1.8;
+    const double obs_scale = OBS_SCALE;
     const Car* me = &e->car[pi];
     const Body* hull = &me->body[HULL_BODY];
+    /* camera_update("rgb_array") */
     double angle = hull->a;
     double vx = hull->v.x, vy = hull->v.y;
     if (vx * vx + vy * vy > 0.5 * 0.5) angle = atan2(-vx, +vy);
-    float fa = (float)angle;                       /* tmp.angle = angle -> b2Rot float32 */
-    double sa = sinf(fa), ca = cosf(fa);
-    double camx = (double)hull->p.x + (double)(float)(ca * 0.0f - sa * 16.0f);
-    double camy = (double)hull->p.y + (double)(float)(sa * 0.0f + ca * 16.0f);
-    double s_rot = sin(angle), c_rot = cos(angle);
+    float fa = (float)angle, fs = sinf(fa), fc = cosf(fa);
+    float camx = hull->p.x + (fc * 0.0f - fs * 16.0f), camy = hull->p.y + (fs * 0.0f + fc * 16.0f);   /* b2Vec2 arithmetic */
+    /* camera_view(mode="rgb_array") */
+    double pos0 = obs_scale * -(double)camx + 5000.0, pos1 = obs_scale * -(double)camy + 5000.0;
+    int rx = (int)(pos0 - STATE_W), ry = (int)(pos1 - STATE_H);
+    const int sw = 2 * STATE_W, sh = 2 * STATE_H;
+    /* pygame.transform.rotate(view, 57.295779513 * angle) */
+    double rad = (57.295779513 * angle) * .01745329251994329;
+    double sangle = sin(rad), cangle = cos(rad);
+    double cx = cangle * sw, cy = cangle * sh, sx = sangle * sw, sy = sangle * sh;
+    double m1 = fmax(fmax(fmax(fabs(cx + sy), fabs(cx - sy)), fabs(-cx + sy)), fabs(-cx - sy));
+    double m2 = fmax(fmax(fmax(fabs(sx + cy), fabs(sx - cy)), fabs(-sx + cy)), fabs(-sx - cy));
+    int nx = (int)m1, ny = (int)m2;
+    int cyi = ny / 2, xd = (sw - nx) * 32768, yd = (sh - ny) * 32768;
+    int isin = (int)(sangle * 65536), icos = (int)(cangle * 65536);
+    int ax = (nx * 32768) - (int)(cangle * (double)((nx - 1) * 32768));
+    int ay = (ny * 32768) - (int)(sangle * (double)((nx - 1) * 32768));
+    int xmaxval = (sw << 16) - 1, ymaxval = (sh << 16) - 1;
+    int bx = -(nx >> 1) + STATE_W / 2, by = -(ny >> 1) + STATE_H / 2;   /* blit position of the rotated surface */
     uint8_t* img = e->obs[pi];
-    const uint8_t g_grass = gray_of(0.4 * 255, 0.8 * 255, 0.4 * 255), g_check = gray_of((int)(0.4 * 255), (int)(0.9 * 255), (int)(0.4 * 255));
+    const uint8_t g_grass = gray_of((int)(0.4 * 255), (int)(0.8 * 255), (int)(0.4 * 255));
+    const uint8_t g_check = gray_of((int)(0.4 * 255), (int)(0.9 * 255), (int)(0.4 * 255));
     const double k = PLAYFIELD / 20.0;
-    /* candidate tiles: centre within the window's circumscribed circle */
+    /* candidate tiles: anything that can reach the visible window (central 96 x 96 of the rotated crop) */
     static __thread int cand[MAX_TRACK];
     int n_cand = 0;
-    const double reach = 48.0 * 1.4142135623730951 / obs_scale + 2.0 * TRACK_WIDTH + BORDER;
+    const double reach = (48.0 * 1.4142135623730951 + 4.0) / obs_scale + 2.0 * TRACK_WIDTH + BORDER + TRACK_DETAIL_STEP;
     for (int t = e->n_track - 1; t >= 0; --t) {   /* paint order: tiles are created from i = n-1 down to 0 */
         double dx = e->track[t][2] - camx, dy = e->track[t][3] - camy;
-        if (dx * dx + dy * dy <= (reach + TRACK_DETAIL_STEP) * (reach + TRACK_DETAIL_STEP)) cand[n_cand++] = t;
+        if (dx * dx + dy * dy <= reach * reach) cand[n_cand++] = t;
     }
-    for (int r = 0; r < STATE_H; ++r) {
-        for (int c = 0; c < STATE_W; ++c) {
-            double dxp = c + 0.5 - STATE_W / 2.0, dyp = r + 0.5 - STATE_H / 2.0;   /* screen offset from centre */
-            double sx = dxp * c_rot - dyp * s_rot, sy = dxp * s_rot + dyp * c_rot;  /* un-rotate (y down) */
-            double wx = camx - sx / obs_scale, wy = camy - sy / obs_scale;
-            uint8_t val = g_grass;
-            {
-                double gx = floor(wx / k), gy = floor(wy / k);
-                if (gx >= -20 && gx < 20 && gy >= -20 && gy < 20 && ((long)gx % 2 == 0) && ((long)gy % 2 == 0)) val = g_check;
-            }
-            for (int q = 0; q < n_cand; ++q) {
-                int t = cand[q];
-                if (point_in_convex(e->tile_poly[t], e->tile_n[t], wx, wy)) {
-                    double col = (int)(255 * (0.4 + 0.01 * (t % 3)));
-                    val = gray_of(col, col, col);
-                }
-                if (e->border[t] && point_in_convex(e->kerb[t], 4, wx, wy))
-                    val = (t % 2 == 0) ? gray_of(255, 255, 255) : gray_of(255, 0, 0);
-            }
-            /* cars: for k in cars: wheels then hull (drawlist = wheels + [hull]) */
-            for (int ci = 0; ci < e->n_cars; ++ci) {
-                const Car* cr = &e->car[ci];
-                for (int wk = 0; wk < 4; ++wk) {
-                    V2 wp[4];
-                    wheel_world_poly(&cr->body[BODY_OF_WHEEL[wk]], wp);
-                    float pp[4][2];
-                    for (int i = 0; i < 4; ++i) { pp[i][0] = wp[i].x; pp[i][1] = wp[i].y; }
-                    if (point_in_convex(pp, 4, wx, wy)) val = gray_of(0, 0, 0);
-                }
-                const Body* h = &cr->body[HULL_BODY];
-                for (int f = 0; f < 4; ++f) {
-                    float pp[8][2];
-                    for (int i = 0; i < HULL_COUNTS[f]; ++i) {
-                        V2 p = vadd(rmul(h->q, v2((float)(HULL_POLYS[f][i][0] * SIZE), (float)(HULL_POLYS[f][i][1] * SIZE))), h->p);
-                        pp[i][0] = p.x; pp[i][1] = p.y;
+    for (int Y = 0; Y < STATE_H; ++Y) {
+        for (int X = 0; X < STATE_W; ++X) {
+            int x = X - bx, y = Y - by;    /* pixel of the rotated surface under this screen pixel */
+            uint8_t val = 0;               /* surfaces start black */
+            if (x >= 0 && y >= 0 && x < nx && y < ny) {
+                int dx = (ax + (isin * (cyi - y))) + xd + icos * x;
+                int dy = (ay - (icos * (cyi - y))) + yd + isin * x;
+                if (!(dx < 0 || dy < 0 || dx > xmaxval || dy > ymaxval)) {
+                    int U = rx + (dx >> 16), V = ry + (dy >> 16);
+                    val = g_grass;
+                    for (int gx = -20; gx < 20; gx += 2)       /* checker squares, :735-746 */
+                        for (int gy = -20; gy < 20; gy += 2) {
+                            IPoly q;
+                            q.n = 4;
+                            double qx[4] = {k * gx + k, k * gx + 0, k * gx + 0, k * gx + k};
+                            double qy[4] = {k * gy + 0, k * gy + 0, k * gy + k, k * gy + k};
+                            for (int i = 0; i < 4; ++i) { q.vx[i] = (int)(obs_scale * -qx[i] + 5000.0); q.vy[i] = (int)(obs_scale * -qy[i] + 5000.0); }
+                            if (U < q.vx[0] - 1 || U > q.vx[1] + 1 || V < q.vy[2] - 1 || V > q.vy[0] + 1) continue;
+                            if (ipoly_covers(&q, U, V)) val = g_check;
+                        }
+                    for (int c = 0; c < n_cand; ++c) {
+                        int t = cand[c];
+                        IPoly q;
+                        q.n = 5;
+                        for (int i = 0; i < 5; ++i) { q.vx[i] = e->tile_map[t][i][0]; q.vy[i] = e->tile_map[t][i][1]; }
+                        if (ipoly_covers(&q, U, V)) { double col = (int)(255 * (0.4 + 0.01 * (t % 3))); val = gray_of(col, col, col); }
+                        if (e->border[t]) {
+                            q.n = 4;
+                            for (int i = 0; i < 4; ++i) { q.vx[i] = e->kerb_map[t][i][0]; q.vy[i] = e->kerb_map[t][i][1]; }
+                            if (ipoly_covers(&q, U, V)) val = (t % 2 == 0) ? gray_of(255, 255, 255) : gray_of(255, 0, 0);
+                        }
                     }
-                    if (point_in_convex(pp, HULL_COUNTS[f], wx, wy))
-                        val = (ci == pi) ? gray_of(0.8 * 255, 0, 0) : gray_of(0, 0, 255);
                 }
             }
-            img[r * STATE_W + c] = val;
+            img[Y * STATE_W + X] = val;
+        }
+    }
+    /* cars: for k in cars: for obj in wheels + [hull]: for f in obj.fixtures: polygon (draw_for_pygame) */
+    {
+        float ta = f32(-angle), ts = sinf(ta), tc = cosf(ta);     /* tmp.angle = -angle */
+        for (int ci = 0; ci < e->n_cars; ++ci) {
+            const Car* cr = &e->car[ci];
+            for (int part = 0; part < 8; ++part) {
+                const Body* b = part < 4 ? &cr->body[BODY_OF_WHEEL[part]] : &cr->body[HULL_BODY];
+                IPoly q;
+                float lv[8][2];
+                if (part < 4) {
+                    const float hw = (float)(WHEEL_W * SIZE), hr = (float)(WHEEL_R * SIZE);
+                    float box[4][2] = {{+hw, -hr}, {+hw, +hr}, {-hw, +hr}, {-hw, -hr}};
+                    q.n = 4;
+                    memcpy(lv, box, sizeof box);
+                } else {
+                    int f = part - 4;
+                    q.n = HULL_COUNTS[f];
+                    for (int i = 0; i < q.n; ++i) { lv[i][0] = (float)(HULL_POLYS[f][i][0] * SIZE); lv[i][1] = (float)(HULL_POLYS[f][i][1] * SIZE); }
+                }
+                for (int i = 0; i < q.n; ++i) {
+                    float wx = (b->q.c * lv[i][0] - b->q.s * lv[i][1]) + b->p.x, wy = (b->q.s * lv[i][0] + b->q.c * lv[i][1]) + b->p.y;
+                    float ox = wx - camx, oy = wy - camy;
+                    float rx2 = (tc * ox - ts * oy) + 0.0f, ry2 = (ts * ox + tc * oy) + 0.0f;
+                    float px = f32((double)rx2 * -obs_scale) + (float)(STATE_W / 2.0), py = f32((double)ry2 * -obs_scale) + (float)(STATE_H / 2.0);
+                    q.vx[i] = (int)px; q.vy[i] = (int)py;
+                }
+                uint8_t col = part < 4 ? gray_of(0, 0, 0) : (ci == pi ? gray_of(0.8 * 255, 0, 0) : gray_of(0, 0, 255));
+                fill_ipoly(img, &q, col);
+            }
         }
     }
     /* HUD: render_indicators_for_pygame(width=96, height=96, scale=5) */
     const double W = STATE_W, H = STATE_H, s = W / 40.0, h = H / 40.0;
     double true_speed = sqrt((double)hull->v.x * hull->v.x + (double)hull->v.y * hull->v.y);
-    fill_rect_px(img, 0, H - 4 * h, W, 4 * h * 1000, gray_of(0, 0, 0));
-    fill_rect_px(img, 5 * s, H - h, s, h * (-0.02 * true_speed), gray_of(0, 0, 255));
+    draw_rect(img, 0, H - 4 * h, W, 4 * h * 1000, gray_of(0, 0, 0));
+    draw_rect(img, 5 * s, H - h, s, h * (-0.02 * true_speed), gray_of(0, 0, 255));
     for (int wk = 0; wk < 4; ++wk)
-        fill_rect_px(img, (7 + wk) * s, H - h, s, h * (-0.01 * me->omega[wk]),
-                     wk < 2 ? gray_of(0, 0, 255) : gray_of(0.2 * 255, 0, 255));
+        draw_rect(img, (7 + wk) * s, H - h, s, h * (-0.01 * me->omega[wk]), wk < 2 ? gray_of(0.0, 0, 255) : gray_of((int)(0.2 * 255), 0, 255));
     {
         const RevJoint* j0 = &me->joint[JOINT_OF_WHEEL[0]];
-        double ja = (double)(me->body[BODY_OF_WHEEL[0]].a - hull->a - j0->reference_angle);
-        fill_rect_px(img, 20 * s, H - 2 * h, s * (10.0 * ja), 2 * h, gray_of(0, 255, 0));
-        fill_rect_px(img, 30 * s, H - 2 * h, s * (0.8 * (double)hull->w), 2 * h, gray_of(255, 0, 0));
+        double ja = (double)((me->body[BODY_OF_WHEEL[0]].a - hull->a) - j0->reference_angle);
+        draw_rect(img, 20 * s, H - 2 * h, s * (10.0 * ja), 2 * h, gray_of(0, 255, 0));
+        draw_rect(img, 30 * s, H - 2 * h, s * (0.8 * (double)hull->w), 2 * h, gray_of(255, 0, 0));
     }
     if (e->glyphs) {   /* draw_text("%05.0f" % reward) at (W/100, H - H/20), white, 5 px non-AA glyphs */
         char txt[32];
-        double rv = me->reward;
-        /* "%05.0f": round-half-even to integer, zero padded to width 5 (sign counts) */
-        snprintf(txt, sizeof txt, "%05.0f", rv);
+        snprintf(txt, sizeof txt, "%05.0f", me->reward);
         int pen = (int)(W / 100), y0 = (int)(H - H / 20);
         for (int i = 0; txt[i]; ++i) {
             int gi = txt[i] == '-' ? 10 : (txt[i] >= '0' && txt[i] <= '9' ? txt[i] - '0' : -1);
@@ -1018,7 +1087,7 @@ void car_oracle_reset(CarEnv* e, const double* track, const int* border, int n_t
         car_create(&e->car[k], e->track[0][1], e->track[0][2], e->track[0][3], birth_place ? birth_place[k] : k);
     e->step_count = 0;
     e->inv_dt0 = 0.0f;
-    for (int k = 0; k < e->n_cars; ++k) render_obs(e, k);   /* return self.step(None)[0] */
+    if (!e->lazy_render) for (int k = 0; k < e->n_cars; ++k) render_obs(e, k);   /* return self.step(None)[0] */
 }
 
 /* CarRacing.step, :542-620.  actions [n_cars][2]; out: step_rewards[n_cars], done[n_cars] */
@@ -1045,11 +1114,15 @@ void car_oracle_step(CarEnv* e, const double* actions, double* step_rewards, int
         world_step(e, 1.0f / FPS);
         e->step_count += 1;
     }
-    for (int k = 0; k < e->n_cars; ++k) { render_obs(e, k); done[k] = e->car[k].done; }
+    for (int k = 0; k < e->n_cars; ++k) { if (!e->lazy_render) render_obs(e, k); done[k] = e->car[k].done; }
     *num_steps = e->step_count;
 }
 
-const uint8_t* car_oracle_obs(const CarEnv* e, int player) { return e->obs[player]; }
+void car_oracle_set_lazy_render(CarEnv* e, int lazy) { e->lazy_render = lazy; }
+const uint8_t* car_oracle_obs(CarEnv* e, int player) {
+    if (e->lazy_render) render_obs(e, player);
+    return e->obs[player];
+}
 
 /* state[car][24]: hull x, y, angle, vx, vy, w; wheel k: angle_k, omega_k (python), gas_k ; reward; tiles; done */
 void car_oracle_get_state(const CarEnv* e, double* out) {

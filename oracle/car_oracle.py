@@ -34,6 +34,7 @@ def lib():
         L.car_oracle_obs.restype = ctypes.POINTER(ctypes.c_uint8)
         L.car_oracle_obs.argtypes = [vp, ctypes.c_int]
         L.car_oracle_get_state.argtypes = [vp, vp]
+        L.car_oracle_set_lazy_render.argtypes = [vp, ctypes.c_int]
         L.car_oracle_create_track.argtypes = [vp, vp, vp]
         L.car_oracle_create_track.restype = ctypes.c_int
         L.car_oracle_polys_touch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int]
@@ -86,10 +87,14 @@ def make_track(rng):
 class CarOracleEnv(object):
     """One cCarRacing env (1 or 2 cars): reset(track, border) -> obs list; step(actions (n_cars, 2))."""
 
-    def __init__(self, n_cars=1, action_repeat=1, glyphs=None):
+    def __init__(self, n_cars=1, action_repeat=1, glyphs=None, render=True):
+        """render=False: reset()/step() return obs=None and frames are drawn only by observe() (the faithful
+        per-pixel renderer costs ~0.1 s per frame)."""
         self.n_cars = n_cars
+        self.render = bool(render)
         self._glyphs = None if glyphs is None else np.ascontiguousarray(glyphs, np.uint8)
         self._h = lib().car_oracle_create(n_cars, action_repeat, _p(self._glyphs))
+        lib().car_oracle_set_lazy_render(self._h, 0 if self.render else 1)
 
     def close(self):
         if self._h:
@@ -102,7 +107,13 @@ class CarOracleEnv(object):
         except Exception:
             pass
 
+    def observe(self):
+        """Render (if lazy) and return the current observation of every player."""
+        return [np.ctypeslib.as_array(lib().car_oracle_obs(self._h, k), shape=(96, 96)).copy() for k in range(self.n_cars)]
+
     def _obs(self):
+        if not self.render:
+            return None
         return [np.ctypeslib.as_array(lib().car_oracle_obs(self._h, k), shape=(96, 96)).copy() for k in range(self.n_cars)]
 
     def reset(self, track, border, birth_place=None):

@@ -66,7 +66,47 @@ def run(name, n_players, seed, T, action_repeat=None, amp=0.6):
         name, len(track), n_attempts, len(kerbs), states[-1, :, 23], rewards.sum(0).round(2), os.path.getsize(path) // 1024))
 
 
+def run_frames(name, cases, T=60, every=12):
+    """Observation fixtures: the reference's OWN renderer (get_observation and everything under it) run on the
+    pygame stand-in.  Pins camera, scales, colours, paint order, car polygons and HUD of the observation."""
+    M = RC.load_car_racing(render=True)
+    out = {}
+    for ci, (n_players, seed) in enumerate(cases):
+        env = M.CarRacing(num_player=n_players, verbose=0)
+        env.seed(seed)
+        rec = RC.RecordingRandom(env.np_random)
+        env.np_random = rec
+        np.random.seed(seed)
+        o = env.reset()
+        np.random.seed(seed)
+        birth = np.arange(n_players)
+        np.random.shuffle(birth)
+
+        def frames_of(o):
+            return np.stack([o[:, :, 0]] if n_players == 1 else [o[k][:, :, 0] for k in range(n_players)])
+        frames, steps = [frames_of(o)], [-1]
+        actions = np.zeros((T, n_players, 2))
+        for t in range(T):
+            for k in range(n_players):
+                actions[t, k] = (0.3 * np.sin(t / 9.0 + seed + k), 0.6 if (t // 25) % 2 == 0 else -0.4)
+            o, r, d, info = env.step(actions[t, 0] if n_players == 1 else {k: actions[t, k] for k in range(n_players)})
+            if t % every == every - 1:
+                frames.append(frames_of(o))
+                steps.append(t)
+        out["c%d_players" % ci] = n_players
+        out["c%d_draws" % ci] = np.array(rec.draws[-24:])
+        out["c%d_birth" % ci] = birth
+        out["c%d_actions" % ci] = actions
+        out["c%d_frames" % ci] = np.array(frames, np.uint8)
+        out["c%d_steps" % ci] = np.array(steps)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, n_cases=len(cases), **out)
+    print("%-22s cases=%d  %d KiB" % (name, len(cases), os.path.getsize(path) // 1024))
+    RC.load_car_racing(render=False)
+
+
 if __name__ == "__main__":
+    run_frames("car_frames", [(1, 123), (1, 31), (2, 12)])
     run("car_single_seed123", 1, 123, 400)
     run("car_single_seed5_rep2", 1, 5, 150, action_repeat=2)
     # The reference raises AttributeError inside FrictionDetector._contact (it reads self.verbose,

@@ -29,12 +29,22 @@ def install():
     pkg.car_racing = cr
 
 
-def load_car_racing():
+def load_car_racing(render=False):
+    """render=False: get_observation is stubbed (fast; logic fixtures).  render=True: the reference's own
+    renderer runs on the pygame stand-in (polygon fill / rotate / rect restated from pygame 1.9, see
+    oracle/ref_shim/pygame); slow (a 10 000 x 10 000 road map per reset) but it pins the camera, scales,
+    colours, paint order and HUD layout of the observation."""
     install()
     import competitive_rl.car_racing.car_racing_multi_players as M
-    # observation rendering is not run under the stand-ins (see module docstring)
-    M.CarRacing.get_observation = lambda self, i: np.zeros((96, 96, 1), np.uint8)
-    M.CarRacing.render_road_for_observation_map = lambda self, screen: screen
+    if not hasattr(M.CarRacing, "_orig_get_observation"):
+        M.CarRacing._orig_get_observation = M.CarRacing.get_observation
+        M.CarRacing._orig_render_road = M.CarRacing.render_road_for_observation_map
+    if render:
+        M.CarRacing.get_observation = M.CarRacing._orig_get_observation
+        M.CarRacing.render_road_for_observation_map = M.CarRacing._orig_render_road
+    else:
+        M.CarRacing.get_observation = lambda self, i: np.zeros((96, 96, 1), np.uint8)
+        M.CarRacing.render_road_for_observation_map = lambda self, screen: screen
     return M
 
 

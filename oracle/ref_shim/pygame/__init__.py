@@ -56,6 +56,7 @@ class Rect(object):
     h = property(lambda s: s._h)
     centerx = property(lambda s: s._x + (s._w >> 1))
     centery = property(lambda s: s._y + (s._h >> 1))
+    center = property(lambda s: (s._x + (s._w >> 1), s._y + (s._h >> 1)))
 
     def _set_topleft(self, v):
         self._x, self._y = _trunc(v[0]), _trunc(v[1])
@@ -92,9 +93,18 @@ class Surface(object):
 
     def fill(self, color, rect=None):
         if rect is None:
-            self.rgb[:, :] = color[:3]
+            self.rgb[:, :] = [int(c) for c in color[:3]]
         else:
             draw.rect(self, color, rect)
+
+    def subsurface(self, rect):
+        x, y, w, h = (int(v) for v in rect)
+        assert 0 <= x and 0 <= y and x + w <= self._w and y + h <= self._h, "subsurface rectangle outside surface area"
+        sub = Surface.__new__(Surface)
+        sub._w, sub._h = w, h
+        sub.rgb = self.rgb[y:y + h, x:x + w]
+        sub.alpha = None
+        return sub
 
     def blit(self, source, dest):
         if isinstance(dest, Rect):
@@ -111,6 +121,9 @@ class Surface(object):
         s = source.rgb[sy0:sy1, sx0:sx1].astype(np.int32)
         if source.alpha is None:
             out = s
+        elif getattr(source, "colorkey", False):   # non-antialiased text: 8-bit surface with a colorkey, exact copy
+            m = (source.alpha[sy0:sy1, sx0:sx1] > 0)[:, :, None]
+            out = np.where(m, s, d)
         else:
             a = source.alpha[sy0:sy1, sx0:sx1].astype(np.int32)[:, :, None]
             out = d + (((s - d) * a) >> 8)  # SDL 1.2 ALPHA_BLEND, arithmetic shift
