@@ -21,7 +21,7 @@ EXPORTS = [
     "crl_launch_count", "crl_pong_check", "crl_pong_get_stats",
     "crl_car_create", "crl_car_destroy", "crl_car_load_glyphs", "crl_car_inject_tracks", "crl_car_reset",
     "crl_car_step", "crl_car_step_state", "crl_car_render_obs", "crl_car_get_state", "crl_car_get_track",
-    "crl_car_random_actions", "crl_car_get_stats", "crl_car_check",
+    "crl_car_random_actions", "crl_car_get_stats", "crl_car_get_contacts", "crl_car_check",
 ]
 
 
@@ -95,6 +95,7 @@ def load():
     L.crl_car_get_track.argtypes = [vp, i32, ctypes.POINTER(i32), vp, i32, vp]
     L.crl_car_random_actions.argtypes = [vp, i32, u64, u64, vp]
     L.crl_car_get_stats.argtypes = [vp, vp, vp]
+    L.crl_car_get_contacts.argtypes = [vp, vp, vp, vp]
     L.crl_car_check.argtypes = [vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcrl_b200.so")
 SOURCES = ["crl_abi.cu", "pong_step.cu", "pong_raster.cu", "pong_raster_fast.cu", "crl_car_abi.cu",
            "car_physics.cu", "car_raster.cu"]
-HEADERS = ["pong_common.cuh", "pong_raster_dev.cuh", "car_common.cuh", os.path.join("..", "..", "include", "crl_b200.h")]
+HEADERS = ["pong_common.cuh", "pong_raster_dev.cuh", "car_common.cuh", "car_contact.cuh", os.path.join("..", "..", "include", "crl_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false",            # cv2's area resize and the fp64 ball physics are un-fused mul/add

@@ -175,6 +175,13 @@ class CudaCarVecEnv(VecEnv):
         ep = int(raw[0])
         return {"episodes": ep, "mean_length": raw[1] / ep if ep else 0.0, "mean_tiles": raw[2] / ep if ep else 0.0}
 
+    def get_contacts(self):
+        """(int32 [num_envs] touching car-car fixture pairs after the last step, contacts dropped so far)."""
+        counts = np.zeros((self.num_envs,), np.int32)
+        over = ctypes.c_int32(0)
+        _native.check(self._lib.crl_car_get_contacts(self._h, counts.ctypes.data, ctypes.byref(over), self._stream()))
+        return counts, int(over.value)
+
     def check(self):
         _native.check(self._lib.crl_car_check(self._h, self._stream()))
 

@@ -25,6 +25,7 @@ constexpr int CAR_SAMPLE_STRIDE = 8;        // every 8th track point feeds the c
 constexpr int CAR_MAX_SAMPLES = CAR_MAX_TRACK / CAR_SAMPLE_STRIDE;
 constexpr int CAR_MAX_STACK = 8;
 constexpr int CAR_GLYPH_BYTES = 11 * 8 * 4 + 11;
+constexpr int CAR_MAX_CONTACTS = 8;         // touching car-car fixture pairs kept per env (of 48 possible)
 
 // A road tile, 116 bytes: for the physics the convex hull (CCW, fp32) of the reference's 5 listed
 // vertices; for the renderer the listed vertices and the kerb quad in ROAD-MAP PIXELS, i.e.
@@ -39,9 +40,29 @@ struct CarTile {
     int16_t kmx[4], kmy[4];   // kerb quad in road-map pixels
 };
 
+// One touching fixture pair between the two cars of an env (b2Contact + its solver constraints), 144 bytes.
+// The manifold part and the accumulated impulses persist between steps (warm start); the rest is per-step scratch.
+struct CarContact {
+    uint8_t pair, count, type, vcount;   // canonical pair index (0..47), manifold points, 0 = e_faceA / 1 = e_faceB, solver points
+    uint8_t ia, ib, pad0, pad1;          // bodies: 0..4 = car 0 (hull, wheels 0..3), 5..9 = car 1
+    uint32_t id[2];                      // b2ContactFeature keys
+    float lnx, lny, lpx, lpy;            // manifold.localNormal, manifold.localPoint
+    float px[2], py[2];                  // manifold.points[].localPoint
+    float ni[2], ti[2];                  // normal / tangent impulses
+    float nx, ny;                        // world normal
+    float rAx[2], rAy[2], rBx[2], rBy[2];
+    float nmass[2], tmass[2];
+    float k11, k12, k22, nm00, nm01, nm10, nm11;
+};
+
 struct CarHullConst {         // mass data of the car bodies (b2Body::ResetMassData), computed on the host
     float hull_inv_mass, hull_inv_I, hull_lcx, hull_lcy;
     float wheel_inv_mass, wheel_inv_I;
+    // body-local fixture polygons as b2PolygonShape::Set leaves them (hull order, edge normals, centroid):
+    // 0..3 = the hull's four polygons, 4 = the wheel box; radius = farthest vertex from the body origin
+    int fix_n[5];
+    float fix_vx[5][8], fix_vy[5][8], fix_nx[5][8], fix_ny[5][8];
+    float fix_cx[5], fix_cy[5], fix_radius[5], fix_cradius[5];   // cradius = farthest vertex from the centroid
     uint8_t gray[16];         // palette: see CarGray
     int checker[80];          // [axis][20][lo, hi]: road-map pixel bounds of the checker squares (car_checker_table)
 };
@@ -77,6 +98,10 @@ struct CarDev {
     int32_t* counters;        // [n*players][4]: tile_visited_count, last_block, has_block, done
     uint32_t* touching;       // [n*players][4][16] wheel.tiles bitmasks
     uint32_t* visited;        // [n*players][16] tile.road_visited[car]
+    // ---- car-car contacts (players == 2): [n][CAR_MAX_CONTACTS] records, [n] counts, one overflow counter ----
+    CarContact* contacts;
+    int32_t* n_contacts;
+    int32_t* contact_overflow;
     // ---- observation ring: [n][players][c][CAR_PIX] ----
     uint8_t* ring;
     // ---- validation mode ----

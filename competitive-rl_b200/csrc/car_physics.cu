@@ -65,6 +65,10 @@ __device__ __forceinline__ F2 rmul(Rot q, F2 v) { return f2(q.c * v.x - q.s * v.
 __device__ __forceinline__ float clampf(float a, float lo, float hi) { return a < lo ? lo : (a > hi ? hi : a); }
 __device__ __forceinline__ double signd(double v) { return (double)((v > 0) - (v < 0)); }
 
+}  // namespace crl
+#include "car_contact.cuh"
+namespace crl {
+
 // ------------------------------------------------------------------------------------------------
 // track generator (fp64): one walk of the curve follower; `emit_from/emit_to` select which raw points
 // are written out (second pass) -- the raw 2500-point walk is never stored.
@@ -325,6 +329,7 @@ __global__ void car_reset_kernel(CarDev p, int only_done) {
     p.step_count[e] = 0;
     p.elapsed[e] = 0;
     p.inv_dt0[e] = 0.f;
+    if (p.n_contacts != nullptr) p.n_contacts[e] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -382,6 +387,13 @@ car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__
     bool car_done = false;
     double step_reward = 0.0;
     int env_steps = 0;
+    // two-car envs: the cars of an env sit on adjacent lanes (blockDim is even, ci = 2 * env + player) and exchange
+    // their bodies through these blocks when they touch (car_contact.cuh)
+    __shared__ float sh_pose[32][10][3];
+    __shared__ float sh_vel[32][10][3];
+    const unsigned pair_mask = 3u << (threadIdx.x & 30);
+    float (*pose)[3] = sh_pose[threadIdx.x >> 1];
+    float (*vel)[3] = sh_vel[threadIdx.x >> 1];
     if (active) {
         const CarHullConst K = *p.consts;
         // ---- load ----
@@ -562,9 +574,46 @@ car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__
                     }
                 }
             }
+            // ---- b2ContactManager::Collide: car-car contacts (two-car envs).  n_con > 0 merges both cars into one island. ----
+            int n_con = 0;
+            CarContact* recs = nullptr;
+            if (p.players == 2) {
+                for (int i = 0; i < 5; ++i) { pose[player * 5 + i][0] = c[i].x; pose[player * 5 + i][1] = c[i].y; pose[player * 5 + i][2] = a[i]; }
+                __syncwarp(pair_mask);
+                recs = p.contacts + (size_t)e * CAR_MAX_CONTACTS;
+                // gate: the two cars as oriented boxes in their hull frames (hull polygons span x +-1.2, y -2.4..2.6; wheels
+                // reach x +-1.71 at any steering angle; 0.3 of slack for skins and joint error) -- separated boxes, no contact
+                bool near_each_other;
+                {
+                    const Rot qa = make_rot(pose[0][2]), qb = make_rot(pose[5][2]);
+                    const F2 pa = f2(pose[0][0], pose[0][1]) + rmul(qa, f2(-hull_lcx, 0.1f - hull_lcy));
+                    const F2 pb = f2(pose[5][0], pose[5][1]) + rmul(qb, f2(-hull_lcx, 0.1f - hull_lcy));
+                    const F2 t = pb - pa;
+                    const float ex = 2.01f, ey = 2.8f;
+                    const float cxx = fabsf(qa.c * qb.c + qa.s * qb.s), cxy = fabsf(qa.s * qb.c - qa.c * qb.s);   // |ax.bx|, |ax.by| (= |ay.bx|)
+                    const float tax = fabsf(t.x * qa.c + t.y * qa.s), tay = fabsf(-t.x * qa.s + t.y * qa.c);
+                    const float tbx = fabsf(t.x * qb.c + t.y * qb.s), tby = fabsf(-t.x * qb.s + t.y * qb.c);
+                    const bool separated = tax > ex + ex * cxx + ey * cxy || tay > ey + ex * cxy + ey * cxx ||
+                                           tbx > ex + ex * cxx + ey * cxy || tby > ey + ex * cxy + ey * cxx;
+                    // right after a reset the wheels are not yet where the joints want them (Car.__init__ places them
+                    // un-rotated, car_dynamics.py:90): plain distance gate for the first steps
+                    near_each_other = (step_count < 4) ? (t.x * t.x + t.y * t.y < 8.0f * 8.0f) : !separated;
+                }
+                if (near_each_other) {
+                    if (player == 0) {
+                        n_con = car_contacts_collide(p.consts, pose, recs, p.n_contacts[e], p.contact_overflow);
+                        p.n_contacts[e] = n_con;
+                    }
+                    n_con = __shfl_sync(pair_mask, n_con, threadIdx.x & 30);
+                } else if (player == 0) {
+                    p.n_contacts[e] = 0;
+                }
+            }
+            const bool merged = n_con > 0;
             // ---- b2Island::Solve for this car's island (bodies: hull + 4 wheels; joints relaxed in the
             //      order wheel 3, 2, 1, 0 -- the island order b2World::Solve's DFS produces) ----
-            const bool any_awake = awake[0] || awake[1] || awake[2] || awake[3] || awake[4];
+            bool any_awake = awake[0] || awake[1] || awake[2] || awake[3] || awake[4];
+            if (merged) any_awake = any_awake || __shfl_xor_sync(pair_mask, (int)any_awake, 1) != 0;
             if (any_awake) {
                 for (int i = 0; i < 5; ++i)
                     if (!awake[i]) { awake[i] = true; sleep_t[i] = 0.f; }
@@ -578,6 +627,13 @@ car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__
                     // torque is never applied; damping is 0: v *= 1/(1 + h*0)
                     v[i] = (1.0f / (1.0f + h * 0.0f)) * v[i];
                     w[i] *= 1.0f / (1.0f + h * 0.0f);
+                }
+                if (merged) {   // contact constraints are initialised and warm-started before the joints (b2Island::Solve)
+                    for (int i = 0; i < 5; ++i) { vel[player * 5 + i][0] = v[i].x; vel[player * 5 + i][1] = v[i].y; vel[player * 5 + i][2] = w[i]; }
+                    __syncwarp(pair_mask);
+                    if (player == 0) car_contacts_init(p.consts, recs, n_con, pose, vel, dt_ratio);
+                    __syncwarp(pair_mask);
+                    for (int i = 0; i < 5; ++i) { v[i] = f2(vel[player * 5 + i][0], vel[player * 5 + i][1]); w[i] = vel[player * 5 + i][2]; }
                 }
                 // InitVelocityConstraints (+ warm start), joints 3, 2, 1, 0
                 for (int kk = 3; kk >= 0; --kk) {
@@ -663,6 +719,13 @@ car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__
                         }
                         v[0] = vA; w[0] = wA; v[bi] = vB; w[bi] = wB;
                     }
+                    if (merged) {   // contacts after the joints of both cars
+                        for (int i = 0; i < 5; ++i) { vel[player * 5 + i][0] = v[i].x; vel[player * 5 + i][1] = v[i].y; vel[player * 5 + i][2] = w[i]; }
+                        __syncwarp(pair_mask);
+                        if (player == 0) car_contacts_solve_velocity(p.consts, recs, n_con, vel);
+                        __syncwarp(pair_mask);
+                        for (int i = 0; i < 5; ++i) { v[i] = f2(vel[player * 5 + i][0], vel[player * 5 + i][1]); w[i] = vel[player * 5 + i][2]; }
+                    }
                 }
                 // integrate positions
                 for (int i = 0; i < 5; ++i) {
@@ -678,6 +741,15 @@ car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__
 #pragma unroll 1
                 for (int it = 0; it < 2 * 30; ++it) {
                     bool ok = true;
+                    if (merged) {   // contacts before the joints
+                        for (int i = 0; i < 5; ++i) { pose[player * 5 + i][0] = c[i].x; pose[player * 5 + i][1] = c[i].y; pose[player * 5 + i][2] = a[i]; }
+                        __syncwarp(pair_mask);
+                        int cok = 1;
+                        if (player == 0) cok = car_contacts_solve_position(p.consts, recs, n_con, pose) ? 1 : 0;
+                        __syncwarp(pair_mask);
+                        ok = __shfl_sync(pair_mask, cok, threadIdx.x & 30) != 0;
+                        for (int i = 0; i < 5; ++i) { c[i] = f2(pose[player * 5 + i][0], pose[player * 5 + i][1]); a[i] = pose[player * 5 + i][2]; }
+                    }
 #pragma unroll
                     for (int kk = 3; kk >= 0; --kk) {
                         const Joint& j = J[kk];
@@ -719,6 +791,7 @@ car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__
                         c[0] = cA; a[0] = aA; c[bi] = cB; a[bi] = aB;
                         ok = (position_error <= B2_LINEAR_SLOP && angular_error <= B2_ANGULAR_SLOP) && ok;
                     }
+                    if (merged) ok = __shfl_xor_sync(pair_mask, (int)ok, 1) != 0 && ok;
                     if (ok) { position_solved = true; break; }
                 }
                 // sleeping
@@ -732,6 +805,7 @@ car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__
                         min_sleep = fminf(min_sleep, sleep_t[i]);
                     }
                 }
+                if (merged) min_sleep = fminf(min_sleep, __shfl_xor_sync(pair_mask, min_sleep, 1));
                 if (min_sleep >= B2_TIME_TO_SLEEP && position_solved)
                     for (int i = 0; i < 5; ++i) { awake[i] = false; sleep_t[i] = 0.f; v[i] = f2(0.f, 0.f); w[i] = 0.f; }
             }

@@ -96,6 +96,43 @@ void poly_mass(const P2* v, int n, float density, float* mass, P2* center, float
     *inertia = in + *mass * (d1 - d2);
 }
 
+// b2PolygonShape::Set after the hull: edge normals (b2Cross(edge, 1) normalised) and ComputeCentroid (pRef = origin)
+void fixture_polygon(CarHullConst* K, int s, const P2* v, int n) {
+    K->fix_n[s] = n;
+    volatile float cx = 0.f, cy = 0.f, area = 0.f, r2 = 0.f;
+    const float inv3 = 1.0f / 3.0f;
+    for (int i = 0; i < n; ++i) {
+        const P2 a = v[i], b = v[i + 1 < n ? i + 1 : 0];
+        K->fix_vx[s][i] = a.x; K->fix_vy[s][i] = a.y;
+        volatile float ex = b.x - a.x, ey = b.y - a.y;
+        volatile float nx = 1.0f * ey, ny = -1.0f * ex;
+        volatile float l2 = nx * nx, l2b = ny * ny;
+        volatile float len = sqrtf(l2 + l2b);
+        if (!(len < 1.1920929e-07f)) { volatile float inv = 1.0f / len; nx = nx * inv; ny = ny * inv; }
+        K->fix_nx[s][i] = nx; K->fix_ny[s][i] = ny;
+        volatile float t1 = a.x * b.y, t2 = a.y * b.x;
+        volatile float D = t1 - t2;
+        volatile float tri = 0.5f * D;
+        area = area + tri;
+        volatile float k = tri * inv3;
+        volatile float sx = (0.0f + a.x) + b.x, sy = (0.0f + a.y) + b.y;
+        volatile float kx = k * sx, ky = k * sy;
+        cx = cx + kx; cy = cy + ky;
+        volatile float q1 = a.x * a.x, q2 = a.y * a.y;
+        volatile float d2 = q1 + q2;
+        if (d2 > r2) r2 = d2;
+    }
+    volatile float ia = 1.0f / area;
+    K->fix_cx[s] = ia * cx; K->fix_cy[s] = ia * cy;
+    K->fix_radius[s] = sqrtf(r2);
+    float c2 = 0.f;
+    for (int i = 0; i < n; ++i) {
+        const float dx = v[i].x - K->fix_cx[s], dy = v[i].y - K->fix_cy[s];
+        if (dx * dx + dy * dy > c2) c2 = dx * dx + dy * dy;
+    }
+    K->fix_cradius[s] = sqrtf(c2) * 1.0001f;
+}
+
 uint8_t gray_of(double r, double g, double b) { return (uint8_t)(r * 0.299 + g * 0.587 + b * 0.114); }
 
 void car_constants(CarHullConst* K) {
@@ -110,6 +147,7 @@ void car_constants(CarHullConst* K) {
         P2 raw[8], hull[8];
         for (int i = 0; i < HC[k]; ++i) { raw[i].x = (float)(HP[k][i][0] * 0.02); raw[i].y = (float)(HP[k][i][1] * 0.02); }
         const int n = hull_of(raw, HC[k], hull);
+        fixture_polygon(K, k, hull, n);
         float m, in;
         P2 c;
         poly_mass(hull, n, 1.0f, &m, &c, &in);
@@ -122,6 +160,7 @@ void car_constants(CarHullConst* K) {
     {
         const float hw = (float)(14 * 0.02), hr = (float)(27 * 0.02);
         P2 box[4] = {{+hw, -hr}, {+hw, +hr}, {-hw, +hr}, {-hw, -hr}};
+        fixture_polygon(K, 4, box, 4);
         float m, in;
         P2 c;
         poly_mass(box, 4, 0.1f, &m, &c, &in);
@@ -196,6 +235,8 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     ALLOC(d.body, nc * 40); ALLOC(d.joint, nc * 24); ALLOC(d.wheel, nc * 8); ALLOC(d.reward, nc * 2);
     ALLOC(d.counters, nc * 4); ALLOC(d.touching, nc * 64); ALLOC(d.visited, nc * 16);
     ALLOC(d.ring, nc * d.c * CAR_PIX); ALLOC(d.overrun, 1); ALLOC(d.stats, 8);
+    ALLOC(d.contact_overflow, 1);
+    if (P == 2) { ALLOC(d.contacts, n * CAR_MAX_CONTACTS); ALLOC(d.n_contacts, n); }
     CarHullConst* kdev = nullptr;
     ALLOC(kdev, 1);
 #undef ALLOC
@@ -329,6 +370,18 @@ int crl_car_get_stats(crl_car* h, uint64_t* stats_host, void* stream) {
     CUDA_TRY(cudaMemcpyAsync(raw, h->dev.stats, sizeof raw, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     for (int i = 0; i < 8; ++i) stats_host[i] = raw[i];
+    return CRL_OK;
+}
+
+int crl_car_get_contacts(crl_car* h, int32_t* counts_host, int32_t* overflow_host, void* stream) {
+    CHECK_HANDLE(h);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (counts_host) {
+        if (h->dev.n_contacts) CUDA_TRY(cudaMemcpyAsync(counts_host, h->dev.n_contacts, (size_t)h->dev.n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        else memset(counts_host, 0, (size_t)h->dev.n * sizeof(int32_t));
+    }
+    if (overflow_host) CUDA_TRY(cudaMemcpyAsync(overflow_host, h->dev.contact_overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     return CRL_OK;
 }
 

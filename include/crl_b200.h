@@ -209,6 +209,10 @@ int crl_car_get_track(crl_car* h, int32_t env, int32_t* n_out, double* pts_host,
 
 int crl_car_random_actions(float* actions_dev, int32_t n_values, uint64_t seed, uint64_t step, void* stream);
 int crl_car_get_stats(crl_car* h, uint64_t* stats_host, void* stream);   /* [0] episodes [1] sum length [2] sum tiles */
+/* car-car contacts of cCarRacingDouble (what box2d-py's b2World::Step resolves between the fixtures of the two
+ * cars, car_dynamics.py:63-68,94-96): int32 [num_envs] touching fixture pairs per env after the last step, and the
+ * number of contacts dropped so far because an env had more than 8 touching pairs at once (either may be NULL). */
+int crl_car_get_contacts(crl_car* h, int32_t* counts_host, int32_t* overflow_host, void* stream);
 int crl_car_check(crl_car* h, void* stream);
 
 #ifdef __cplusplus

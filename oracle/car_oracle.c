@@ -22,8 +22,8 @@
  * that calls this file's solver, and tests/test_oracle_car.py compares.
  *
  * Deliberate simplifications (stated, tested as such):
- *   - car-car collisions are not modelled (each car is its own island; cCarRacingDouble cars
- *     pass through each other);
+ *   - car-car contacts (cCarRacingDouble) are evaluated for every allowed fixture pair each Step and
+ *     enter the island in a canonical order (see "mini Box2D, part 2" below);
  *   - a sensor contact exists exactly while the wheel polygon and the tile polygon are closer
  *     than 2*b2_polygonRadius by the separating-axis measure, evaluated at the start of
  *     world.Step (Box2D: b2TestOverlap on contacts whose fat AABBs overlap);
@@ -429,6 +429,523 @@ static void island_solve(Body* bodies, int nb, RevJoint* joints, int nj, float h
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* mini Box2D, part 2: polygon-polygon contacts between the two cars of cCarRacingDouble        */
+/*                                                                                              */
+/* Restated from the published Box2D 2.3.0 algorithm (from memory; PARITY UNPINNED like the     */
+/* rest of the mini Box2D): b2PolygonShape::Set (normals, centroid), b2CollidePolygons with     */
+/* b2FindMaxSeparation's hill climb / b2FindIncidentEdge / b2ClipSegmentToLine, b2Contact::     */
+/* Update (impulses carried over by contact-feature id), b2ContactSolver (warm start, friction  */
+/* then normal, 2-point block solver, Baumgarte position correction) and the merged island in   */
+/* b2Island::Solve (joints before contacts in the velocity loop, contacts before joints in the  */
+/* position loop).                                                                              */
+/*                                                                                              */
+/* Fixtures of a car: 0..3 = hull polygons (car_dynamics.py:63-68, category 0x0001 mask 0xFFFF),*/
+/* 4..7 = wheels 0..3 (:94-96, category 0x0020 mask 0x001).  b2ContactFilter::ShouldCollide     */
+/* therefore allows hull-hull and wheel-hull between the two cars but not wheel-wheel; fixtures  */
+/* of one car never collide (wheels: mask; hull-wheel: joined with collideConnected = false).   */
+/* All fixtures: friction 0.2 (b2FixtureDef default), restitution 0 -> b2MixFriction =          */
+/* sqrt(0.2 * 0.2), b2MixRestitution = 0.                                                       */
+/*                                                                                              */
+/* Stated deviations from a real Box2D world: (1) a b2Contact object exists in Box2D only while */
+/* the fat AABBs of two fixtures overlap; its manifold is empty unless the polygons are within  */
+/* 2 * b2_polygonRadius, and an empty manifold carries no impulses, so evaluating the manifold  */
+/* of every allowed pair at the start of each Step gives the same constraints.  (2) The order   */
+/* of contacts inside the island follows the order in which Box2D's broad phase happened to     */
+/* create them (proxy ids, move buffer); here it is canonical: fixture of car 0 major, fixture  */
+/* of car 1 minor, and fixtureA is always car 0's.  (3) Merged-island joint order is car 1's    */
+/* joints (3, 2, 1, 0) then car 0's (3, 2, 1, 0); Box2D's depth-first search can put one joint  */
+/* of the second car first when it enters that car through a wheel contact.  Joints of the two  */
+/* cars share no body, so only the position of that one joint relative to its siblings differs. */
+
+#define CAR_FIXTURES 8
+#define CAR_PAIRS 48                       /* 8 x 8 minus the 16 wheel-wheel pairs */
+#define B2_VELOCITY_THRESHOLD 1.0f
+#define B2_BAUMGARTE 0.2f
+#define B2_MAX_LINEAR_CORRECTION 0.2f
+#define B2_EPSILON 1.1920929e-07f
+
+typedef struct { int n; V2 v[8], nrm[8]; V2 centroid; } Poly;
+typedef struct { V2 p; Rot q; } Xf;
+
+typedef struct {
+    V2 local_point;
+    float normal_impulse, tangent_impulse;
+    uint32_t id;                 /* b2ContactFeature: indexA | indexB << 8 | typeA << 16 | typeB << 24 */
+} MPoint;
+typedef struct {
+    MPoint pt[2];
+    V2 local_normal, local_point;
+    int type;                    /* 0 = e_faceA, 1 = e_faceB */
+    int count;
+} Manifold;
+typedef struct { Manifold m[CAR_PAIRS]; } ContactStore;
+
+static V2 vneg(V2 a) { return v2(-a.x, -a.y); }
+static V2 xf_mul(Xf t, V2 v) { return v2((t.q.c * v.x - t.q.s * v.y) + t.p.x, (t.q.s * v.x + t.q.c * v.y) + t.p.y); }
+static V2 xf_mulT(Xf t, V2 v) {
+    float px = v.x - t.p.x, py = v.y - t.p.y;
+    return v2(t.q.c * px + t.q.s * py, -t.q.s * px + t.q.c * py);
+}
+static V2 rmulT(Rot q, V2 v) { return v2(q.c * v.x + q.s * v.y, -q.s * v.x + q.c * v.y); }
+static V2 cross_vs(V2 a, float s) { return v2(s * a.y, -s * a.x); }
+static V2 normalized(V2 a) {
+    float len = sqrtf(a.x * a.x + a.y * a.y);
+    if (len < B2_EPSILON) return a;
+    float inv = 1.0f / len;
+    return v2(a.x * inv, a.y * inv);
+}
+
+/* b2PolygonShape::Set after the hull: edge normals and ComputeCentroid (pRef = origin) */
+static void poly_set(Poly* p, const float* hull_xy, int n) {
+    p->n = n;
+    for (int i = 0; i < n; ++i) p->v[i] = v2(hull_xy[2 * i], hull_xy[2 * i + 1]);
+    for (int i = 0; i < n; ++i) {
+        V2 e = vsub(p->v[i + 1 < n ? i + 1 : 0], p->v[i]);
+        p->nrm[i] = normalized(cross_vs(e, 1.0f));
+    }
+    V2 c = v2(0.f, 0.f);
+    float area = 0.f;
+    const float inv3 = 1.0f / 3.0f;
+    for (int i = 0; i < n; ++i) {
+        V2 p2 = p->v[i], p3 = p->v[i + 1 < n ? i + 1 : 0];
+        float D = vcross(p2, p3);
+        float tri = 0.5f * D;
+        area += tri;
+        c = vadd(c, vscale(tri * inv3, vadd(vadd(v2(0.f, 0.f), p2), p3)));
+    }
+    p->centroid = vscale(1.0f / area, c);
+}
+
+static float edge_separation(const Poly* p1, Xf xf1, int edge1, const Poly* p2, Xf xf2) {
+    V2 n1w = rmul(xf1.q, p1->nrm[edge1]);
+    V2 n1 = rmulT(xf2.q, n1w);
+    int index = 0;
+    float min_dot = 3.402823466e+38f;
+    for (int i = 0; i < p2->n; ++i) {
+        float d = vdot(p2->v[i], n1);
+        if (d < min_dot) { min_dot = d; index = i; }
+    }
+    V2 v1 = xf_mul(xf1, p1->v[edge1]), v2w = xf_mul(xf2, p2->v[index]);
+    return vdot(vsub(v2w, v1), n1w);
+}
+
+/* b2FindMaxSeparation (2.3.0): start at the edge most aligned with the centroid offset, climb */
+static float find_max_separation(int* edge_index, const Poly* p1, Xf xf1, const Poly* p2, Xf xf2) {
+    int count1 = p1->n;
+    V2 d = vsub(xf_mul(xf2, p2->centroid), xf_mul(xf1, p1->centroid));
+    V2 d_local1 = rmulT(xf1.q, d);
+    int edge = 0;
+    float max_dot = -3.402823466e+38f;
+    for (int i = 0; i < count1; ++i) {
+        float dt = vdot(p1->nrm[i], d_local1);
+        if (dt > max_dot) { max_dot = dt; edge = i; }
+    }
+    float s = edge_separation(p1, xf1, edge, p2, xf2);
+    int prev_edge = edge - 1 >= 0 ? edge - 1 : count1 - 1;
+    float s_prev = edge_separation(p1, xf1, prev_edge, p2, xf2);
+    int next_edge = edge + 1 < count1 ? edge + 1 : 0;
+    float s_next = edge_separation(p1, xf1, next_edge, p2, xf2);
+    int best_edge, increment;
+    float best_sep;
+    if (s_prev > s && s_prev > s_next) { increment = -1; best_edge = prev_edge; best_sep = s_prev; }
+    else if (s_next > s) { increment = 1; best_edge = next_edge; best_sep = s_next; }
+    else { *edge_index = edge; return s; }
+    for (;;) {
+        if (increment == -1) edge = best_edge - 1 >= 0 ? best_edge - 1 : count1 - 1;
+        else edge = best_edge + 1 < count1 ? best_edge + 1 : 0;
+        s = edge_separation(p1, xf1, edge, p2, xf2);
+        if (s > best_sep) { best_edge = edge; best_sep = s; } else break;
+    }
+    *edge_index = best_edge;
+    return best_sep;
+}
+
+typedef struct { V2 v; uint32_t id; } ClipVertex;
+#define CF_ID(ia, ib, ta, tb) ((uint32_t)(ia) | ((uint32_t)(ib) << 8) | ((uint32_t)(ta) << 16) | ((uint32_t)(tb) << 24))
+#define CF_VERTEX 0
+#define CF_FACE 1
+
+static int clip_segment_to_line(ClipVertex out[2], const ClipVertex in[2], V2 normal, float offset, int vertex_index_a) {
+    int n_out = 0;
+    float d0 = vdot(normal, in[0].v) - offset, d1 = vdot(normal, in[1].v) - offset;
+    if (d0 <= 0.0f) out[n_out++] = in[0];
+    if (d1 <= 0.0f) out[n_out++] = in[1];
+    if (d0 * d1 < 0.0f) {
+        float interp = d0 / (d0 - d1);
+        out[n_out].v = vadd(in[0].v, vscale(interp, vsub(in[1].v, in[0].v)));
+        out[n_out].id = CF_ID(vertex_index_a, (in[0].id >> 8) & 0xff, CF_VERTEX, CF_FACE);
+        ++n_out;
+    }
+    return n_out;
+}
+
+/* b2CollidePolygons (2.3.0) */
+static void collide_polygons(Manifold* m, const Poly* pa, Xf xfa, const Poly* pb, Xf xfb) {
+    m->count = 0;
+    const float total_radius = B2_POLYGON_RADIUS + B2_POLYGON_RADIUS;
+    int edge_a = 0, edge_b = 0;
+    float sep_a = find_max_separation(&edge_a, pa, xfa, pb, xfb);
+    if (sep_a > total_radius) return;
+    float sep_b = find_max_separation(&edge_b, pb, xfb, pa, xfa);
+    if (sep_b > total_radius) return;
+    const Poly *p1, *p2;
+    Xf xf1, xf2;
+    int edge1, flip;
+    const float k_rel = 0.98f, k_abs = 0.001f;
+    if (sep_b > k_rel * sep_a + k_abs) { p1 = pb; p2 = pa; xf1 = xfb; xf2 = xfa; edge1 = edge_b; m->type = 1; flip = 1; }
+    else { p1 = pa; p2 = pb; xf1 = xfa; xf2 = xfb; edge1 = edge_a; m->type = 0; flip = 0; }
+    /* b2FindIncidentEdge */
+    ClipVertex incident[2];
+    {
+        V2 n1 = rmulT(xf2.q, rmul(xf1.q, p1->nrm[edge1]));
+        int index = 0;
+        float min_dot = 3.402823466e+38f;
+        for (int i = 0; i < p2->n; ++i) {
+            float d = vdot(n1, p2->nrm[i]);
+            if (d < min_dot) { min_dot = d; index = i; }
+        }
+        int i1 = index, i2 = i1 + 1 < p2->n ? i1 + 1 : 0;
+        incident[0].v = xf_mul(xf2, p2->v[i1]); incident[0].id = CF_ID(edge1, i1, CF_FACE, CF_VERTEX);
+        incident[1].v = xf_mul(xf2, p2->v[i2]); incident[1].id = CF_ID(edge1, i2, CF_FACE, CF_VERTEX);
+    }
+    int iv1 = edge1, iv2 = edge1 + 1 < p1->n ? edge1 + 1 : 0;
+    V2 v11 = p1->v[iv1], v12 = p1->v[iv2];
+    V2 local_tangent = normalized(vsub(v12, v11));
+    V2 local_normal = cross_vs(local_tangent, 1.0f);
+    V2 plane_point = vscale(0.5f, vadd(v11, v12));
+    V2 tangent = rmul(xf1.q, local_tangent);
+    V2 normal = cross_vs(tangent, 1.0f);
+    v11 = xf_mul(xf1, v11); v12 = xf_mul(xf1, v12);
+    float front_offset = vdot(normal, v11);
+    float side_offset1 = -vdot(tangent, v11) + total_radius;
+    float side_offset2 = vdot(tangent, v12) + total_radius;
+    ClipVertex clip1[2], clip2[2];
+    if (clip_segment_to_line(clip1, incident, vneg(tangent), side_offset1, iv1) < 2) return;
+    if (clip_segment_to_line(clip2, clip1, tangent, side_offset2, iv2) < 2) return;
+    m->local_normal = local_normal;
+    m->local_point = plane_point;
+    int count = 0;
+    for (int i = 0; i < 2; ++i) {
+        float separation = vdot(normal, clip2[i].v) - front_offset;
+        if (separation <= total_radius) {
+            MPoint* cp = &m->pt[count];
+            cp->local_point = xf_mulT(xf2, clip2[i].v);
+            uint32_t id = clip2[i].id;
+            if (flip) id = CF_ID((id >> 8) & 0xff, id & 0xff, (id >> 24) & 0xff, (id >> 16) & 0xff);
+            cp->id = id;
+            ++count;
+        }
+    }
+    m->count = count;
+}
+
+/* b2Contact::Update for one pair: new manifold, impulses carried over by feature id.  Returns touching. */
+static int contact_update(Manifold* m, const Poly* pa, Xf xfa, const Poly* pb, Xf xfb, int* touching_changed) {
+    Manifold old = *m;
+    int was = old.count > 0;
+    collide_polygons(m, pa, xfa, pb, xfb);
+    for (int i = 0; i < m->count; ++i) {
+        MPoint* mp2 = &m->pt[i];
+        mp2->normal_impulse = 0.0f; mp2->tangent_impulse = 0.0f;
+        for (int j = 0; j < old.count; ++j)
+            if (old.pt[j].id == mp2->id) {
+                mp2->normal_impulse = old.pt[j].normal_impulse;
+                mp2->tangent_impulse = old.pt[j].tangent_impulse;
+                break;
+            }
+    }
+    *touching_changed = (m->count > 0) != was;
+    return m->count > 0;
+}
+
+/* b2ContactVelocityConstraint + b2ContactPositionConstraint of one touching pair */
+typedef struct {
+    int ia, ib;                  /* island body indices */
+    Manifold* man;
+    int point_count;             /* velocity constraint count (may drop to 1: ill-conditioned block) */
+    V2 normal;
+    V2 rA[2], rB[2];
+    float normal_impulse[2], tangent_impulse[2], normal_mass[2], tangent_mass[2], velocity_bias[2];
+    float K[2][2], NM[2][2];     /* [col][row] */
+    float friction, restitution;
+    float mA, mB, iA, iB;
+    V2 lcA, lcB;
+} ContactC;
+
+static Xf xf_of(V2 c, float a, V2 local_center) {
+    Xf t;
+    t.q = rot(a);
+    t.p = vsub(c, rmul(t.q, local_center));
+    return t;
+}
+
+/* b2WorldManifold::Initialize */
+static void world_manifold(const Manifold* m, Xf xfa, Xf xfb, V2* normal, V2 points[2]) {
+    const float ra = B2_POLYGON_RADIUS, rb = B2_POLYGON_RADIUS;
+    if (m->type == 0) {
+        *normal = rmul(xfa.q, m->local_normal);
+        V2 plane = xf_mul(xfa, m->local_point);
+        for (int i = 0; i < m->count; ++i) {
+            V2 clip = xf_mul(xfb, m->pt[i].local_point);
+            V2 ca = vadd(clip, vscale(ra - vdot(vsub(clip, plane), *normal), *normal));
+            V2 cb = vsub(clip, vscale(rb, *normal));
+            points[i] = vscale(0.5f, vadd(ca, cb));
+        }
+    } else {
+        *normal = rmul(xfb.q, m->local_normal);
+        V2 plane = xf_mul(xfb, m->local_point);
+        for (int i = 0; i < m->count; ++i) {
+            V2 clip = xf_mul(xfa, m->pt[i].local_point);
+            V2 cb = vadd(clip, vscale(rb - vdot(vsub(clip, plane), *normal), *normal));
+            V2 ca = vsub(clip, vscale(ra, *normal));
+            points[i] = vscale(0.5f, vadd(ca, cb));
+        }
+        *normal = vneg(*normal);
+    }
+}
+
+/* b2ContactSolver constructor + InitializeVelocityConstraints + WarmStart for one contact */
+static void contact_init(ContactC* cc, const V2* c, const float* a, V2* v, float* w, float dt_ratio) {
+    const Manifold* m = cc->man;
+    cc->point_count = m->count;
+    for (int j = 0; j < m->count; ++j) {
+        cc->normal_impulse[j] = dt_ratio * m->pt[j].normal_impulse;
+        cc->tangent_impulse[j] = dt_ratio * m->pt[j].tangent_impulse;
+    }
+    const float mA = cc->mA, mB = cc->mB, iA = cc->iA, iB = cc->iB;
+    V2 cA = c[cc->ia], cB = c[cc->ib];
+    V2 vA = v[cc->ia], vB = v[cc->ib];
+    float wA = w[cc->ia], wB = w[cc->ib];
+    Xf xfa = xf_of(cA, a[cc->ia], cc->lcA), xfb = xf_of(cB, a[cc->ib], cc->lcB);
+    V2 pts[2];
+    world_manifold(m, xfa, xfb, &cc->normal, pts);
+    for (int j = 0; j < cc->point_count; ++j) {
+        cc->rA[j] = vsub(pts[j], cA);
+        cc->rB[j] = vsub(pts[j], cB);
+        float rnA = vcross(cc->rA[j], cc->normal), rnB = vcross(cc->rB[j], cc->normal);
+        float k_normal = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+        cc->normal_mass[j] = k_normal > 0.0f ? 1.0f / k_normal : 0.0f;
+        V2 tangent = cross_vs(cc->normal, 1.0f);
+        float rtA = vcross(cc->rA[j], tangent), rtB = vcross(cc->rB[j], tangent);
+        float k_tangent = mA + mB + iA * rtA * rtA + iB * rtB * rtB;
+        cc->tangent_mass[j] = k_tangent > 0.0f ? 1.0f / k_tangent : 0.0f;
+        cc->velocity_bias[j] = 0.0f;
+        float v_rel = vdot(cc->normal, vsub(vsub(vadd(vB, cross_sv(wB, cc->rB[j])), vA), cross_sv(wA, cc->rA[j])));
+        if (v_rel < -B2_VELOCITY_THRESHOLD) cc->velocity_bias[j] = -cc->restitution * v_rel;
+    }
+    if (cc->point_count == 2) {
+        float rn1A = vcross(cc->rA[0], cc->normal), rn1B = vcross(cc->rB[0], cc->normal);
+        float rn2A = vcross(cc->rA[1], cc->normal), rn2B = vcross(cc->rB[1], cc->normal);
+        float k11 = mA + mB + iA * rn1A * rn1A + iB * rn1B * rn1B;
+        float k22 = mA + mB + iA * rn2A * rn2A + iB * rn2B * rn2B;
+        float k12 = mA + mB + iA * rn1A * rn2A + iB * rn1B * rn2B;
+        const float k_max_cond = 1000.0f;
+        if (k11 * k11 < k_max_cond * (k11 * k22 - k12 * k12)) {
+            cc->K[0][0] = k11; cc->K[0][1] = k12; cc->K[1][0] = k12; cc->K[1][1] = k22;
+            float A = k11, B = k12, C = k12, D = k22;   /* a = ex.x, b = ey.x, c = ex.y, d = ey.y */
+            float det = A * D - B * C;
+            if (det != 0.0f) det = 1.0f / det;
+            cc->NM[0][0] = det * D; cc->NM[1][0] = -det * B; cc->NM[0][1] = -det * C; cc->NM[1][1] = det * A;
+        } else {
+            cc->point_count = 1;
+        }
+    }
+    /* WarmStart */
+    V2 tangent = cross_vs(cc->normal, 1.0f);
+    for (int j = 0; j < cc->point_count; ++j) {
+        V2 P = vadd(vscale(cc->normal_impulse[j], cc->normal), vscale(cc->tangent_impulse[j], tangent));
+        wA -= iA * vcross(cc->rA[j], P);
+        vA = vsub(vA, vscale(mA, P));
+        wB += iB * vcross(cc->rB[j], P);
+        vB = vadd(vB, vscale(mB, P));
+    }
+    v[cc->ia] = vA; w[cc->ia] = wA; v[cc->ib] = vB; w[cc->ib] = wB;
+}
+
+/* the constructor and InitializeVelocityConstraints run over ALL contacts before WarmStart runs over all
+ * of them; InitializeVelocityConstraints reads velocities only for the restitution bias, which is zero
+ * here (restitution 0), so doing init + warm start contact by contact gives the same numbers. */
+
+/* b2ContactSolver::SolveVelocityConstraints for one contact */
+static void contact_solve_velocity(ContactC* cc, V2* v, float* w) {
+    const float mA = cc->mA, mB = cc->mB, iA = cc->iA, iB = cc->iB;
+    V2 vA = v[cc->ia], vB = v[cc->ib];
+    float wA = w[cc->ia], wB = w[cc->ib];
+    V2 normal = cc->normal, tangent = cross_vs(normal, 1.0f);
+    for (int j = 0; j < cc->point_count; ++j) {
+        V2 dv = vsub(vsub(vadd(vB, cross_sv(wB, cc->rB[j])), vA), cross_sv(wA, cc->rA[j]));
+        float vt = vdot(dv, tangent) - 0.0f;
+        float lambda = cc->tangent_mass[j] * (-vt);
+        float max_friction = cc->friction * cc->normal_impulse[j];
+        float new_impulse = clampf(cc->tangent_impulse[j] + lambda, -max_friction, max_friction);
+        lambda = new_impulse - cc->tangent_impulse[j];
+        cc->tangent_impulse[j] = new_impulse;
+        V2 P = vscale(lambda, tangent);
+        vA = vsub(vA, vscale(mA, P));
+        wA -= iA * vcross(cc->rA[j], P);
+        vB = vadd(vB, vscale(mB, P));
+        wB += iB * vcross(cc->rB[j], P);
+    }
+    if (cc->point_count == 1) {
+        V2 dv = vsub(vsub(vadd(vB, cross_sv(wB, cc->rB[0])), vA), cross_sv(wA, cc->rA[0]));
+        float vn = vdot(dv, normal);
+        float lambda = -cc->normal_mass[0] * (vn - cc->velocity_bias[0]);
+        float new_impulse = cc->normal_impulse[0] + lambda;
+        if (!(new_impulse > 0.0f)) new_impulse = 0.0f;
+        lambda = new_impulse - cc->normal_impulse[0];
+        cc->normal_impulse[0] = new_impulse;
+        V2 P = vscale(lambda, normal);
+        vA = vsub(vA, vscale(mA, P));
+        wA -= iA * vcross(cc->rA[0], P);
+        vB = vadd(vB, vscale(mB, P));
+        wB += iB * vcross(cc->rB[0], P);
+    } else {
+        V2 a = v2(cc->normal_impulse[0], cc->normal_impulse[1]);
+        V2 dv1 = vsub(vsub(vadd(vB, cross_sv(wB, cc->rB[0])), vA), cross_sv(wA, cc->rA[0]));
+        V2 dv2 = vsub(vsub(vadd(vB, cross_sv(wB, cc->rB[1])), vA), cross_sv(wA, cc->rA[1]));
+        float vn1 = vdot(dv1, normal), vn2 = vdot(dv2, normal);
+        V2 b = v2(vn1 - cc->velocity_bias[0], vn2 - cc->velocity_bias[1]);
+        b = vsub(b, v2(cc->K[0][0] * a.x + cc->K[1][0] * a.y, cc->K[0][1] * a.x + cc->K[1][1] * a.y));
+        V2 x;
+        int solved = 0;
+        for (;;) {
+            x = vneg(v2(cc->NM[0][0] * b.x + cc->NM[1][0] * b.y, cc->NM[0][1] * b.x + cc->NM[1][1] * b.y));
+            if (x.x >= 0.0f && x.y >= 0.0f) { solved = 1; break; }
+            x.x = -cc->normal_mass[0] * b.x; x.y = 0.0f;
+            vn1 = 0.0f; vn2 = cc->K[0][1] * x.x + b.y;
+            if (x.x >= 0.0f && vn2 >= 0.0f) { solved = 1; break; }
+            x.x = 0.0f; x.y = -cc->normal_mass[1] * b.y;
+            vn1 = cc->K[1][0] * x.y + b.x; vn2 = 0.0f;
+            if (x.y >= 0.0f && vn1 >= 0.0f) { solved = 1; break; }
+            x.x = 0.0f; x.y = 0.0f;
+            vn1 = b.x; vn2 = b.y;
+            if (vn1 >= 0.0f && vn2 >= 0.0f) { solved = 1; break; }
+            break;
+        }
+        if (solved) {
+            V2 d = vsub(x, a);
+            V2 P1 = vscale(d.x, normal), P2 = vscale(d.y, normal);
+            vA = vsub(vA, vscale(mA, vadd(P1, P2)));
+            wA -= iA * (vcross(cc->rA[0], P1) + vcross(cc->rA[1], P2));
+            vB = vadd(vB, vscale(mB, vadd(P1, P2)));
+            wB += iB * (vcross(cc->rB[0], P1) + vcross(cc->rB[1], P2));
+            cc->normal_impulse[0] = x.x; cc->normal_impulse[1] = x.y;
+        }
+    }
+    v[cc->ia] = vA; w[cc->ia] = wA; v[cc->ib] = vB; w[cc->ib] = wB;
+}
+
+/* b2ContactSolver::SolvePositionConstraints for one contact; returns its min separation */
+static float contact_solve_position(const ContactC* cc, V2* c, float* a) {
+    const Manifold* m = cc->man;
+    const float mA = cc->mA, mB = cc->mB, iA = cc->iA, iB = cc->iB;
+    V2 cA = c[cc->ia], cB = c[cc->ib];
+    float aA = a[cc->ia], aB = a[cc->ib];
+    float min_sep = 0.0f;
+    for (int j = 0; j < m->count; ++j) {
+        Xf xfa = xf_of(cA, aA, cc->lcA), xfb = xf_of(cB, aB, cc->lcB);
+        V2 normal, point;
+        float separation;
+        if (m->type == 0) {
+            normal = rmul(xfa.q, m->local_normal);
+            V2 plane = xf_mul(xfa, m->local_point);
+            V2 clip = xf_mul(xfb, m->pt[j].local_point);
+            separation = vdot(vsub(clip, plane), normal) - B2_POLYGON_RADIUS - B2_POLYGON_RADIUS;
+            point = clip;
+        } else {
+            normal = rmul(xfb.q, m->local_normal);
+            V2 plane = xf_mul(xfb, m->local_point);
+            V2 clip = xf_mul(xfa, m->pt[j].local_point);
+            separation = vdot(vsub(clip, plane), normal) - B2_POLYGON_RADIUS - B2_POLYGON_RADIUS;
+            point = clip;
+            normal = vneg(normal);
+        }
+        V2 rA = vsub(point, cA), rB = vsub(point, cB);
+        if (separation < min_sep) min_sep = separation;
+        float C = clampf(B2_BAUMGARTE * (separation + B2_LINEAR_SLOP), -B2_MAX_LINEAR_CORRECTION, 0.0f);
+        float rnA = vcross(rA, normal), rnB = vcross(rB, normal);
+        float K = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+        float impulse = K > 0.0f ? -C / K : 0.0f;
+        V2 P = vscale(impulse, normal);
+        cA = vsub(cA, vscale(mA, P));
+        aA -= iA * vcross(rA, P);
+        cB = vadd(cB, vscale(mB, P));
+        aB += iB * vcross(rB, P);
+    }
+    c[cc->ia] = cA; a[cc->ia] = aA; c[cc->ib] = cB; a[cc->ib] = aB;
+    return min_sep;
+}
+
+/* b2Island::Solve over bodies[0..nb) (pointers), joints (indices into the island) and contacts */
+static void island_solve_ex(Body** bodies, int nb, RevJoint** joints, int nj, ContactC* contacts, int nc, float h,
+                            float dt_ratio, int vel_iters, int pos_iters) {
+    V2 c[16], v[16];
+    float a[16], w[16];
+    Body flat[16];
+    for (int i = 0; i < nb; ++i) {
+        Body* b = bodies[i];
+        b->c0 = b->c; b->a0 = b->a;
+        v[i] = vadd(b->v, vscale(h, vscale(b->inv_mass, b->force)));
+        w[i] = b->w + h * b->inv_I * b->torque;
+        v[i] = vscale(1.0f / (1.0f + h * 0.0f), v[i]);
+        w[i] *= 1.0f / (1.0f + h * 0.0f);
+        c[i] = b->c; a[i] = b->a;
+        flat[i] = *b;
+    }
+    for (int k = 0; k < nc; ++k) contact_init(&contacts[k], c, a, v, w, dt_ratio);
+    for (int k = 0; k < nj; ++k) joint_init_velocity(joints[k], flat, c, a, v, w, dt_ratio);
+    for (int it = 0; it < vel_iters; ++it) {
+        for (int k = 0; k < nj; ++k) joint_solve_velocity(joints[k], v, w, h);
+        for (int k = 0; k < nc; ++k) contact_solve_velocity(&contacts[k], v, w);
+    }
+    for (int k = 0; k < nc; ++k)       /* StoreImpulses */
+        for (int j = 0; j < contacts[k].point_count; ++j) {
+            contacts[k].man->pt[j].normal_impulse = contacts[k].normal_impulse[j];
+            contacts[k].man->pt[j].tangent_impulse = contacts[k].tangent_impulse[j];
+        }
+    for (int i = 0; i < nb; ++i) {
+        V2 tr = vscale(h, v[i]);
+        if (vdot(tr, tr) > B2_MAX_TRANSLATION * B2_MAX_TRANSLATION) v[i] = vscale(B2_MAX_TRANSLATION / sqrtf(vdot(tr, tr)), v[i]);
+        float r = h * w[i];
+        if (r * r > B2_MAX_ROTATION * B2_MAX_ROTATION) w[i] *= B2_MAX_ROTATION / fabsf(r);
+        c[i] = vadd(c[i], vscale(h, v[i]));
+        a[i] += h * w[i];
+    }
+    int position_solved = 0;
+    for (int it = 0; it < pos_iters; ++it) {
+        float min_sep = 0.0f;
+        for (int k = 0; k < nc; ++k) {
+            float s = contact_solve_position(&contacts[k], c, a);
+            if (s < min_sep) min_sep = s;
+        }
+        int contacts_ok = min_sep >= -3.0f * B2_LINEAR_SLOP;
+        int joints_ok = 1;
+        for (int k = 0; k < nj; ++k) joints_ok = joint_solve_position(joints[k], c, a) && joints_ok;
+        if (contacts_ok && joints_ok) { position_solved = 1; break; }
+    }
+    float min_sleep = 3.4e38f;
+    for (int i = 0; i < nb; ++i) {
+        Body* b = bodies[i];
+        b->c = c[i]; b->a = a[i]; b->v = v[i]; b->w = w[i];
+        b->q = rot(b->a);
+        b->p = vsub(b->c, rmul(b->q, b->local_center));
+    }
+    for (int i = 0; i < nb; ++i) {
+        Body* b = bodies[i];
+        if (b->w * b->w > B2_ANGULAR_SLEEP_TOL * B2_ANGULAR_SLEEP_TOL ||
+            vdot(b->v, b->v) > B2_LINEAR_SLEEP_TOL * B2_LINEAR_SLEEP_TOL) {
+            b->sleep_time = 0.0f;
+            min_sleep = 0.0f;
+        } else {
+            b->sleep_time += h;
+            if (b->sleep_time < min_sleep) min_sleep = b->sleep_time;
+        }
+    }
+    if (min_sleep >= B2_TIME_TO_SLEEP && position_solved)
+        for (int i = 0; i < nb; ++i) body_set_awake(bodies[i], 0);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* exported low-level hooks for the Box2D stand-in (oracle/ref_shim/Box2D): it keeps the bodies
  * and joints in flat arrays of these structs and calls back into the solver above.             */
 
@@ -629,6 +1146,124 @@ static const int BODY_OF_WHEEL[4] = {2, 3, 4, 0};   /* wheel k -> index in Car.b
 #define HULL_BODY 1
 static const int JOINT_OF_WHEEL[4] = {3, 2, 1, 0};
 
+/* ---- two-car world: fixtures, b2ContactManager::Collide for the car-car pairs, b2World::Solve ---- */
+
+static Poly g_fix_poly[CAR_FIXTURES];        /* body-local polygons: 0..3 hull (of the hull body), 4..7 wheel box */
+static float g_fix_radius[CAR_FIXTURES];     /* bounding radius about the body origin (quick reject only) */
+static int g_fix_ready = 0;
+
+static void fixtures_init(void) {
+    if (g_fix_ready) return;
+    for (int k = 0; k < 4; ++k) {
+        float raw[16], hull[16];
+        for (int i = 0; i < HULL_COUNTS[k]; ++i) {
+            raw[2 * i] = (float)(HULL_POLYS[k][i][0] * SIZE);
+            raw[2 * i + 1] = (float)(HULL_POLYS[k][i][1] * SIZE);
+        }
+        int n = car_oracle_convex_hull(raw, HULL_COUNTS[k], hull);
+        poly_set(&g_fix_poly[k], hull, n);
+    }
+    {
+        const float wp[4][2] = {{-WHEEL_W, +WHEEL_R}, {+WHEEL_W, +WHEEL_R}, {+WHEEL_W, -WHEEL_R}, {-WHEEL_W, -WHEEL_R}};
+        float raw[8], hull[16];
+        for (int i = 0; i < 4; ++i) { raw[2 * i] = (float)(wp[i][0] * 1.0 * SIZE); raw[2 * i + 1] = (float)(wp[i][1] * 1.0 * SIZE); }
+        int n = car_oracle_convex_hull(raw, 4, hull);
+        for (int k = 4; k < 8; ++k) poly_set(&g_fix_poly[k], hull, n);
+    }
+    for (int k = 0; k < CAR_FIXTURES; ++k) {
+        float r2 = 0.f;
+        for (int i = 0; i < g_fix_poly[k].n; ++i) {
+            float d = vdot(g_fix_poly[k].v[i], g_fix_poly[k].v[i]);
+            if (d > r2) r2 = d;
+        }
+        g_fix_radius[k] = sqrtf(r2);
+    }
+    g_fix_ready = 1;
+}
+
+static int body_of_fixture(int f) { return f < 4 ? HULL_BODY : BODY_OF_WHEEL[f - 4]; }
+
+/* b2World::Step (collide + solve) for the dynamic bodies of a two-car world.  b0/j0 = bodies and joints
+ * of car 0 (created first) in island order, b1/j1 = car 1.  Tile sensors are handled by the caller. */
+static void world_step_two(Body* b0, RevJoint* j0, Body* b1, RevJoint* j1, ContactStore* cs, float h, float dt_ratio,
+                           int vel_iters, int pos_iters) {
+    fixtures_init();
+    int touching = 0, pair = 0;
+    for (int fa = 0; fa < CAR_FIXTURES; ++fa)
+        for (int fb = 0; fb < CAR_FIXTURES; ++fb) {
+            if (fa >= 4 && fb >= 4) continue;
+            Body* A = &b0[body_of_fixture(fa)];
+            Body* B = &b1[body_of_fixture(fb)];
+            Manifold* m = &cs->m[pair++];
+            V2 d = vsub(B->p, A->p);
+            float reach = g_fix_radius[fa] + g_fix_radius[fb] + 0.1f;
+            int changed = 0, t = 0;
+            if (vdot(d, d) > reach * reach) {           /* certainly separated: empty manifold */
+                changed = m->count > 0;
+                m->count = 0;
+            } else {
+                Xf xa = {A->p, A->q}, xb = {B->p, B->q};
+                t = contact_update(m, &g_fix_poly[fa], xa, &g_fix_poly[fb], xb, &changed);
+            }
+            if (changed) { body_set_awake(A, 1); body_set_awake(B, 1); }
+            touching |= t;
+        }
+    if (!touching) {
+        for (int ci = 1; ci >= 0; --ci) {
+            Body* b = ci ? b1 : b0;
+            RevJoint* j = ci ? j1 : j0;
+            int any_awake = 0;
+            for (int i = 0; i < 5; ++i) any_awake |= b[i].awake;
+            if (any_awake) {
+                for (int i = 0; i < 5; ++i) body_set_awake(&b[i], 1);
+                island_solve(b, 5, j, 4, h, dt_ratio, vel_iters, pos_iters);
+            }
+        }
+        return;
+    }
+    int any_awake = 0;
+    for (int i = 0; i < 5; ++i) any_awake |= b0[i].awake | b1[i].awake;
+    if (!any_awake) return;
+    Body* bodies[10];
+    RevJoint* joints[8];
+    for (int i = 0; i < 5; ++i) { bodies[i] = &b1[i]; bodies[5 + i] = &b0[i]; body_set_awake(&b1[i], 1); body_set_awake(&b0[i], 1); }
+    for (int k = 0; k < 4; ++k) { joints[k] = &j1[k]; joints[4 + k] = &j0[k]; j0[k].a += 5; j0[k].b += 5; }
+    ContactC cc[CAR_PAIRS];
+    int nc = 0;
+    pair = 0;
+    for (int fa = 0; fa < CAR_FIXTURES; ++fa)
+        for (int fb = 0; fb < CAR_FIXTURES; ++fb) {
+            if (fa >= 4 && fb >= 4) continue;
+            Manifold* m = &cs->m[pair++];
+            if (m->count == 0) continue;
+            ContactC* c = &cc[nc++];
+            memset(c, 0, sizeof *c);
+            c->man = m;
+            c->ia = 5 + body_of_fixture(fa);
+            c->ib = body_of_fixture(fb);
+            const Body* A = bodies[c->ia]; const Body* B = bodies[c->ib];
+            c->mA = A->inv_mass; c->iA = A->inv_I; c->lcA = A->local_center;
+            c->mB = B->inv_mass; c->iB = B->inv_I; c->lcB = B->local_center;
+            c->friction = sqrtf(0.2f * 0.2f);
+            c->restitution = 0.0f;
+        }
+    island_solve_ex(bodies, 10, joints, 8, cc, nc, h, dt_ratio, vel_iters, pos_iters);
+    for (int k = 0; k < 4; ++k) { j0[k].a -= 5; j0[k].b -= 5; }
+}
+
+int car_oracle_sizeof_contact_store(void) { return (int)sizeof(ContactStore); }
+void car_oracle_world_step_two(Body* b0, RevJoint* j0, Body* b1, RevJoint* j1, ContactStore* cs, float h, float dt_ratio,
+                               int vel_iters, int pos_iters) {
+    world_step_two(b0, j0, b1, j1, cs, h, dt_ratio, vel_iters, pos_iters);
+}
+/* number of touching car-car contacts / manifold points in the store (diagnostics for the tests) */
+int car_oracle_contact_count(const ContactStore* cs, int* n_points) {
+    int nc = 0, np = 0;
+    for (int i = 0; i < CAR_PAIRS; ++i) { nc += cs->m[i].count > 0; np += cs->m[i].count; }
+    if (n_points) *n_points = np;
+    return nc;
+}
+
 typedef struct {
     int n_cars, action_repeat;
     int n_track;
@@ -640,6 +1275,7 @@ typedef struct {
     float kerb[MAX_TRACK][4][2];
     int tile_map[MAX_TRACK][5][2], kerb_map[MAX_TRACK][4][2];   /* road-map pixel coordinates (int-truncated) */
     Car car[MAX_CARS];
+    ContactStore contacts;      /* car-car manifolds (two-car worlds) */
     int step_count;
     float inv_dt0;
     uint8_t obs[MAX_CARS][STATE_H * STATE_W];
@@ -811,16 +1447,22 @@ static void world_collide(CarEnv* e) {
 static void world_step(CarEnv* e, float dt) {
     world_collide(e);
     float dt_ratio = e->inv_dt0 * dt;
-    for (int ci = 0; ci < e->n_cars; ++ci) {
-        Car* c = &e->car[ci];
-        int any_awake = 0;
-        for (int i = 0; i < 5; ++i) any_awake |= c->body[i].awake;
-        if (any_awake) {
-            for (int i = 0; i < 5; ++i) body_set_awake(&c->body[i], 1);   /* island bodies are woken */
-            island_solve(c->body, 5, c->joint, 4, dt, dt_ratio, 6 * 30, 2 * 30);
+    if (e->n_cars == 2) {
+        world_step_two(e->car[0].body, e->car[0].joint, e->car[1].body, e->car[1].joint, &e->contacts, dt, dt_ratio,
+                       6 * 30, 2 * 30);
+    } else {
+        for (int ci = 0; ci < e->n_cars; ++ci) {
+            Car* c = &e->car[ci];
+            int any_awake = 0;
+            for (int i = 0; i < 5; ++i) any_awake |= c->body[i].awake;
+            if (any_awake) {
+                for (int i = 0; i < 5; ++i) body_set_awake(&c->body[i], 1);   /* island bodies are woken */
+                island_solve(c->body, 5, c->joint, 4, dt, dt_ratio, 6 * 30, 2 * 30);
+            }
         }
-        for (int i = 0; i < 5; ++i) { c->body[i].force = v2(0.f, 0.f); c->body[i].torque = 0.f; }   /* ClearForces */
     }
+    for (int ci = 0; ci < e->n_cars; ++ci)
+        for (int i = 0; i < 5; ++i) { e->car[ci].body[i].force = v2(0.f, 0.f); e->car[ci].body[i].torque = 0.f; }   /* ClearForces */
     e->inv_dt0 = 1.0f / dt;
 }
 
@@ -867,6 +1509,71 @@ static void build_tiles(CarEnv* e) {
                 e->kerb_map[i][k][1] = (int)(OBS_SCALE * -kb[k][1] + 5000.0);
             }
         }
+    }
+}
+
+
+/* ---- test hooks for the contact restatement (tests/test_oracle_car_contacts.py) ---- */
+
+/* b2CollidePolygons + b2WorldManifold for fixture fa of a body at (xa, ya, angle aa) against fixture fb of a body at
+ * (xb, yb, ab); fixtures 0..3 = hull polygons, 4 = wheel box.  out: count, type, normal xy, world points (2 x xy),
+ * ids (2).  Returns the point count. */
+int car_oracle_collide_fixtures(int fa, float xa, float ya, float aa, int fb, float xb, float yb, float ab, double* out) {
+    fixtures_init();
+    Xf ta, tb;
+    ta.p = v2(xa, ya); ta.q = rot(aa); tb.p = v2(xb, yb); tb.q = rot(ab);
+    Manifold m;
+    memset(&m, 0, sizeof m);
+    collide_polygons(&m, &g_fix_poly[fa], ta, &g_fix_poly[fb], tb);
+    V2 normal = v2(0.f, 0.f), pts[2] = {{0.f, 0.f}, {0.f, 0.f}};
+    if (m.count) world_manifold(&m, ta, tb, &normal, pts);
+    out[0] = m.count; out[1] = m.type; out[2] = normal.x; out[3] = normal.y;
+    out[4] = pts[0].x; out[5] = pts[0].y; out[6] = pts[1].x; out[7] = pts[1].y;
+    out[8] = m.pt[0].id; out[9] = m.pt[1].id;
+    return m.count;
+}
+
+/* vertices of fixture f (body-local, hull order); returns the count */
+int car_oracle_fixture_polygon(int f, float* out_xy) {
+    fixtures_init();
+    for (int i = 0; i < g_fix_poly[f].n; ++i) { out_xy[2 * i] = g_fix_poly[f].v[i].x; out_xy[2 * i + 1] = g_fix_poly[f].v[i].y; }
+    return g_fix_poly[f].n;
+}
+
+/* Two cars in free flight (no wheel forces, no tiles): car k starts at pose[k] = (x, y, angle) with every body
+ * moving at vel[k] = (vx, vy); `steps` world steps.  out[t] = total linear momentum (2, float64 sums of m * v),
+ * total angular momentum about the origin, touching contacts, manifold points, the two hull positions (4) -> [steps][9]. */
+void car_oracle_free_collision(const double* pose, const double* vel, int steps, double* out) {
+    Car car[2];
+    ContactStore cs;
+    memset(&cs, 0, sizeof cs);
+    for (int k = 0; k < 2; ++k) {
+        car_create(&car[k], pose[3 * k + 2], pose[3 * k], pose[3 * k + 1], 0);
+        Body* hull = &car[k].body[HULL_BODY];
+        for (int w = 0; w < 4; ++w) {       /* put the wheels where the joints want them (Car.__init__ does not rotate them) */
+            Body* b = &car[k].body[BODY_OF_WHEEL[w]];
+            V2 anchor = vadd(rmul(hull->q, v2((float)(WHEELPOS[w][0] * SIZE), (float)(WHEELPOS[w][1] * SIZE))), hull->p);
+            b->p = anchor; b->c = b->c0 = vadd(rmul(b->q, b->local_center), b->p);
+        }
+        for (int i = 0; i < 5; ++i) car[k].body[i].v = v2((float)vel[2 * k], (float)vel[2 * k + 1]);
+    }
+    float inv_dt0 = 0.0f;
+    const float dt = 1.0f / FPS;
+    for (int t = 0; t < steps; ++t) {
+        world_step_two(car[0].body, car[0].joint, car[1].body, car[1].joint, &cs, dt, inv_dt0 * dt, 6 * 30, 2 * 30);
+        inv_dt0 = 1.0f / dt;
+        double px = 0, py = 0, L = 0;
+        for (int k = 0; k < 2; ++k)
+            for (int i = 0; i < 5; ++i) {
+                const Body* b = &car[k].body[i];
+                px += (double)b->mass * b->v.x; py += (double)b->mass * b->v.y;
+                L += (double)b->mass * ((double)b->c.x * b->v.y - (double)b->c.y * b->v.x) + (double)b->I * b->w;
+            }
+        int np = 0;
+        double* o = out + 9 * t;
+        o[0] = px; o[1] = py; o[2] = L; o[3] = car_oracle_contact_count(&cs, &np); o[4] = np;
+        o[5] = car[0].body[HULL_BODY].p.x; o[6] = car[0].body[HULL_BODY].p.y;
+        o[7] = car[1].body[HULL_BODY].p.x; o[8] = car[1].body[HULL_BODY].p.y;
     }
 }
 
@@ -1087,6 +1794,7 @@ void car_oracle_reset(CarEnv* e, const double* track, const int* border, int n_t
         car_create(&e->car[k], e->track[0][1], e->track[0][2], e->track[0][3], birth_place ? birth_place[k] : k);
     e->step_count = 0;
     e->inv_dt0 = 0.0f;
+    memset(&e->contacts, 0, sizeof e->contacts);
     if (!e->lazy_render) for (int k = 0; k < e->n_cars; ++k) render_obs(e, k);   /* return self.step(None)[0] */
 }
 
@@ -1119,6 +1827,8 @@ void car_oracle_step(CarEnv* e, const double* actions, double* step_rewards, int
 }
 
 void car_oracle_set_lazy_render(CarEnv* e, int lazy) { e->lazy_render = lazy; }
+/* touching car-car contacts / manifold points after the last step (diagnostics for the tests) */
+int car_oracle_env_contacts(const CarEnv* e, int* n_points) { return car_oracle_contact_count(&e->contacts, n_points); }
 const uint8_t* car_oracle_obs(CarEnv* e, int player) {
     if (e->lazy_render) render_obs(e, player);
     return e->obs[player];

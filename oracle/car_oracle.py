@@ -35,6 +35,11 @@ def lib():
         L.car_oracle_obs.argtypes = [vp, ctypes.c_int]
         L.car_oracle_get_state.argtypes = [vp, vp]
         L.car_oracle_set_lazy_render.argtypes = [vp, ctypes.c_int]
+        L.car_oracle_env_contacts.argtypes = [vp, vp]
+        f = ctypes.c_float
+        L.car_oracle_collide_fixtures.argtypes = [ctypes.c_int, f, f, f, ctypes.c_int, f, f, f, vp]
+        L.car_oracle_fixture_polygon.argtypes = [ctypes.c_int, vp]
+        L.car_oracle_free_collision.argtypes = [vp, vp, ctypes.c_int, vp]
         L.car_oracle_create_track.argtypes = [vp, vp, vp]
         L.car_oracle_create_track.restype = ctypes.c_int
         L.car_oracle_polys_touch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int]
@@ -84,6 +89,30 @@ def make_track(rng):
             return t[0], t[1], d
 
 
+def collide_fixtures(fa, pose_a, fb, pose_b):
+    """b2CollidePolygons + world manifold of two car fixtures (0..3 hull polygons, 4 wheel box) on bodies at
+    pose = (x, y, angle).  -> dict(count, type, normal (2,), points (count, 2), ids (count,))."""
+    out = np.zeros(10, np.float64)
+    n = lib().car_oracle_collide_fixtures(fa, pose_a[0], pose_a[1], pose_a[2], fb, pose_b[0], pose_b[1], pose_b[2], _p(out))
+    return {"count": n, "type": int(out[1]), "normal": out[2:4].copy(), "points": out[4:8].reshape(2, 2)[:n].copy(),
+            "ids": out[8:10][:n].astype(np.int64)}
+
+
+def fixture_polygon(f):
+    xy = np.zeros((8, 2), np.float32)
+    n = lib().car_oracle_fixture_polygon(f, _p(xy))
+    return xy[:n].copy()
+
+
+def free_collision(pose, vel, steps):
+    """Two cars in free flight; -> (steps, 9): momentum x, y, angular momentum, contacts, points, hull positions."""
+    pose = np.ascontiguousarray(pose, np.float64)
+    vel = np.ascontiguousarray(vel, np.float64)
+    out = np.zeros((steps, 9), np.float64)
+    lib().car_oracle_free_collision(_p(pose), _p(vel), steps, _p(out))
+    return out
+
+
 class CarOracleEnv(object):
     """One cCarRacing env (1 or 2 cars): reset(track, border) -> obs list; step(actions (n_cars, 2))."""
 
@@ -106,6 +135,12 @@ class CarOracleEnv(object):
             self.close()
         except Exception:
             pass
+
+    def contacts(self):
+        """(touching car-car contacts, manifold points) after the last step."""
+        n = ctypes.c_int(0)
+        c = lib().car_oracle_env_contacts(self._h, ctypes.byref(n))
+        return int(c), int(n.value)
 
     def observe(self):
         """Render (if lazy) and return the current observation of every player."""

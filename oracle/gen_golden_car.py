@@ -29,7 +29,7 @@ def actions_for(T, n, seed, amp=0.6):
     return a
 
 
-def run(name, n_players, seed, T, action_repeat=None, amp=0.6):
+def run(name, n_players, seed, T, action_repeat=None, amp=0.6, actions=None, min_contact_steps=0):
     M = RC.load_car_racing()
     env = M.CarRacing(num_player=n_players, verbose=0, action_repeat=action_repeat)
     env.seed(seed)
@@ -45,7 +45,9 @@ def run(name, n_players, seed, T, action_repeat=None, amp=0.6):
     track = np.array(env.track)
     kerbs = np.array([np.array(p).reshape(-1) for p, c in env.road_poly if len(p) == 4])
     tiles = np.array([np.array(p).reshape(-1) for p, c in env.road_poly if len(p) == 5])
-    actions = actions_for(T, n_players, seed + 1, amp)
+    if actions is None:
+        actions = actions_for(T, n_players, seed + 1, amp)
+    contacts = np.zeros((T,), np.int32)
     states = np.zeros((T, n_players, 24))
     rewards = np.zeros((T, n_players))
     dones = np.zeros((T, n_players), bool)
@@ -53,17 +55,38 @@ def run(name, n_players, seed, T, action_repeat=None, amp=0.6):
     for t in range(T):
         a = actions[t, 0] if n_players == 1 else {k: actions[t, k] for k in range(n_players)}
         o, r, d, info = env.step(a)
+        contacts[t] = env.world.contact_count()
         for k in range(n_players):
             states[t, k] = RC.car_state(env, k)
             rewards[t, k] = r if n_players == 1 else r[k]
             dones[t, k] = d if n_players == 1 else d[k]
+    if (contacts > 0).sum() < min_contact_steps:
+        return False
     path = os.path.join(OUT, name + ".npz")
-    np.savez_compressed(path, n_players=n_players, seed=seed, draws=draws, all_draws=np.array(rec.draws),
+    np.savez_compressed(path, n_players=n_players, seed=seed, draws=draws, all_draws=np.array(rec.draws), contacts=contacts,
                         n_attempts=n_attempts, track=track, kerbs=kerbs, tiles=tiles, birth=birth, actions=actions,
                         state0=state0, states=states, rewards=rewards, dones=dones,
                         action_repeat=action_repeat or 1)
     print("%-22s track=%d attempts=%d kerbs=%d tiles_visited=%s return=%s  %d KiB" % (
         name, len(track), n_attempts, len(kerbs), states[-1, :, 23], rewards.sum(0).round(2), os.path.getsize(path) // 1024))
+    return True
+
+
+def run_collision(name, seed, T):
+    """Two cars steered into each other (the cars spawn 5 units apart side by side): the car-car contact
+    path of world.Step under the reference's own CarRacing.step.  The steering sign that closes the gap depends
+    on which car got which birth place, so both are tried."""
+    for sign in (+1.0, -1.0):
+        a = np.zeros((T, 2, 2))
+        a[:, 0] = (sign * 0.3, 0.5)
+        a[:, 1] = (-sign * 0.3, 0.5)
+        a[T // 2:, :, 0] *= -0.5      # later pull apart again
+        try:
+            if run(name, 2, seed, T, actions=a, min_contact_steps=20):
+                return True
+        except AttributeError as exc:
+            print("seed", seed, "-> reference crashed:", exc)
+    return False
 
 
 def run_frames(name, cases, T=60, every=12):
@@ -112,6 +135,9 @@ if __name__ == "__main__":
     # The reference raises AttributeError inside FrictionDetector._contact (it reads self.verbose,
     # :146) when a car touches a tile >= 50 blocks ahead of its last one, e.g. after spinning back
     # over the start line; fixtures must stay clear of that crash, so the two-car run steers gently.
+    for seed in range(3, 40):
+        if run_collision("car_double_collision", seed, 120):
+            break
     for seed in range(7, 40):
         try:
             run("car_double", 2, seed, 300, amp=0.15)

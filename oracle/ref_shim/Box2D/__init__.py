@@ -11,7 +11,8 @@ Restated pybox2d/Box2D behaviour: bodies and joints are prepended to the world l
 are built by depth-first search from awake bodies (b2World::Solve), which fixes the order in which
 the joints of a car are relaxed; ApplyForceToCenter / joint.motorSpeed wake bodies; forces are
 cleared after every Step; sensor contacts fire Begin/EndContact inside Step before the solve.
-Not modelled: collisions between non-sensor fixtures (car-car contact).
+Collisions between non-sensor fixtures exist only between the two cars of a two-car world; they go
+through car_oracle.c's contact restatement (car_oracle_world_step_two), which owns the manifolds.
 """
 import ctypes
 import math
@@ -58,6 +59,9 @@ _L.car_oracle_body_set_mass.argtypes = [ctypes.POINTER(_CBody), ctypes.c_void_p,
                                         ctypes.c_int]
 _L.car_oracle_island_solve.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_float,
                                        ctypes.c_float, ctypes.c_int, ctypes.c_int]
+_L.car_oracle_world_step_two.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_void_p, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_int]
+_L.car_oracle_contact_count.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 
 
 class b2Vec2(object):
@@ -285,6 +289,7 @@ class b2World(object):
         self.joints = []
         self._touching = {}
         self._inv_dt0 = 0.0
+        self._contact_store = ctypes.create_string_buffer(_L.car_oracle_sizeof_contact_store())
 
     def CreateDynamicBody(self, position=(0, 0), angle=0.0, fixtures=None, **kw):
         b = _Body(self, True, position, angle, fixtures)
@@ -345,15 +350,54 @@ class b2World(object):
                     self._listener.EndContact(_Contact(statics[t].fixtures[0], f))
                 self._touching[f] = now
 
-    def Step(self, dt, velocity_iterations, position_iterations):
-        dt = float(_f32(dt))
-        if self._listener is not None:
-            self._collide()
-        dt_ratio = float(_f32(self._inv_dt0) * _f32(dt))
-        for b in self.bodies:
-            b._island = False
-        for j in self.joints:
-            j._island = False
+    def _joint_groups(self):
+        """Bodies and joints of every joint-connected group in b2World::Solve's depth-first order
+        (seeds in body-list order, joint edges most recent first), regardless of the awake state."""
+        seen_b, seen_j, groups = set(), set(), []
+        for seed in self.bodies:
+            if not seed._dynamic or id(seed) in seen_b:
+                continue
+            gb, gj, stack = [], [], [seed]
+            seen_b.add(id(seed))
+            while stack:
+                b = stack.pop()
+                gb.append(b)
+                for j, other in b._joints:
+                    if id(j) in seen_j:
+                        continue
+                    gj.append(j)
+                    seen_j.add(id(j))
+                    if id(other) in seen_b:
+                        continue
+                    stack.append(other)
+                    seen_b.add(id(other))
+            groups.append((gb, gj))
+        return groups
+
+    def _step_two_cars(self, groups, dt, dt_ratio, vi, pi):
+        """Two cars: collide + solve in C (car 0 = created first = LAST group of the body list)."""
+        (b1, j1), (b0, j0) = groups
+        arrs = []
+        for gb, gj in ((b0, j0), (b1, j1)):
+            cb = (_CBody * 5)(*[b._c for b in gb])
+            idx = {id(b): i for i, b in enumerate(gb)}
+            for j in gj:
+                j._c.a, j._c.b = idx[id(j.bodyA)], idx[id(j.bodyB)]
+            cj = (_CJoint * 4)(*[j._c for j in gj])
+            arrs.append((cb, cj))
+        _L.car_oracle_world_step_two(ctypes.cast(arrs[0][0], ctypes.c_void_p), ctypes.cast(arrs[0][1], ctypes.c_void_p),
+                                     ctypes.cast(arrs[1][0], ctypes.c_void_p), ctypes.cast(arrs[1][1], ctypes.c_void_p),
+                                     ctypes.cast(self._contact_store, ctypes.c_void_p), dt, dt_ratio, vi, pi)
+        for (gb, gj), (cb, cj) in zip(((b0, j0), (b1, j1)), arrs):
+            for i, b in enumerate(gb):
+                ctypes.memmove(ctypes.byref(b._c), ctypes.byref(cb[i]), ctypes.sizeof(_CBody))
+            for i, j in enumerate(gj):
+                ctypes.memmove(ctypes.byref(j._c), ctypes.byref(cj[i]), ctypes.sizeof(_CJoint))
+
+    def contact_count(self):
+        return int(_L.car_oracle_contact_count(ctypes.cast(self._contact_store, ctypes.c_void_p), None))
+
+    def _step_islands(self, dt, dt_ratio, velocity_iterations, position_iterations):
         for seed in self.bodies:                    # b2World::Solve
             if seed._island or not seed._dynamic or not seed.awake:
                 continue
@@ -384,6 +428,22 @@ class b2World(object):
                 ctypes.memmove(ctypes.byref(b._c), ctypes.byref(cb[i]), ctypes.sizeof(_CBody))
             for i, j in enumerate(island_j):
                 ctypes.memmove(ctypes.byref(j._c), ctypes.byref(cj[i]), ctypes.sizeof(_CJoint))
+
+    def Step(self, dt, velocity_iterations, position_iterations):
+        dt = float(_f32(dt))
+        if self._listener is not None:
+            self._collide()
+        dt_ratio = float(_f32(self._inv_dt0) * _f32(dt))
+        for b in self.bodies:
+            b._island = False
+        for j in self.joints:
+            j._island = False
+        groups = self._joint_groups()
+        if len(groups) == 2 and all(len(gb) == 5 and len(gj) == 4 for gb, gj in groups):
+            self._step_two_cars(groups, dt, dt_ratio, velocity_iterations, position_iterations)
+        else:
+            assert len([b for b in self.bodies if b._dynamic]) <= 5, "contacts are restated for two-car worlds only"
+            self._step_islands(dt, dt_ratio, velocity_iterations, position_iterations)
         for b in self.bodies:                       # ClearForces
             if b._dynamic:
                 b._c.force.x = b._c.force.y = b._c.torque = 0.0

@@ -8,6 +8,10 @@ sinf/cosf/sin/cos/atan2 in the last ulp, which a 240-iteration solver amplifies 
   * per-step rewards: <= 1e-4; tiles visited and done flags: identical
   * observations: identical pixel rules (integer pipeline), so frames differ only where the ~1e-3 state
     deviation moves an integer-truncated coordinate: mean mismatch per frame <= 0.5 %, worst frame <= 5 %
+  * car-car collisions (cCarRacingDouble): first contact on the same step, the same number of touching fixture
+    pairs on >= 95 % of the steps, hull pose within 0.02 units / rad over the 30 steps after the first contact
+    and within 0.1 over 90 steps (a contact is a discontinuity: one ulp decides which step a manifold point
+    appears on, so the bound after a long scrape is looser than in free driving)
 Once a car spins (full throttle + steering) the dynamics are chaotic and trajectories separate;
 the tests therefore drive moderately."""
 import numpy as np
@@ -158,5 +162,96 @@ def test_1024_envs_properties():
     assert float(total.mean()) > 0
     lens = np.array([len(envs.get_track(e)) for e in range(0, N, 64)])
     assert lens.min() > 150 and lens.max() <= 512
+    envs.check()
+    envs.close()
+
+
+COLLISION_SCENARIOS = [(-0.35, 0.35, 0.5, 0.5), (-0.2, 0.3, 0.6, 0.4), (-0.5, 0.0, 0.5, 0.3), (0.0, 0.45, 0.3, 0.6),
+                       (-0.3, 0.3, 0.8, 0.8), (-0.15, 0.15, 0.4, 0.4), (-0.4, 0.1, 0.7, 0.2), (-0.1, 0.4, 0.2, 0.7)]
+
+
+def test_car_car_collisions_vs_oracle():
+    """Two cars steered into each other: contacts (b2CollidePolygons + contact solver in the merged island)."""
+    import car_oracle as C
+    N, T = len(COLLISION_SCENARIOS), 90
+    rng = np.random.RandomState(5)
+    draws, tracks = np.zeros((N, 4, 24)), []
+    for e in range(N):
+        tr, bd, d = C.make_track(rng)
+        draws[e, :] = d
+        tracks.append((tr, bd))
+    birth = np.tile(np.arange(2)[None, None], (N, 4, 1)).astype(np.int32)
+    envs = _make("cCarRacingDouble-v0", N, track_draws=draws, birth=birth)
+    orcs = [C.CarOracleEnv(2, 1, None, render=False) for _ in range(N)]
+    envs.reset()
+    for e, o in enumerate(orcs):
+        o.reset(*tracks[e], [0, 1])
+    a = np.array([[[s[0], s[2]], [s[1], s[3]]] for s in COLLISION_SCENARIOS], np.float32)
+    dev, cg, co = np.zeros((T, N)), np.zeros((T, N), int), np.zeros((T, N), int)
+    for t in range(T):
+        envs.step(a)
+        sg = envs.get_state().cpu().numpy()
+        cg[t], over = envs.get_contacts()
+        assert over == 0
+        for e in range(N):
+            orcs[e].step(a[e].astype(np.float64))
+            dev[t, e] = np.abs(sg[e, :, :3] - orcs[e].get_state()[:, :3]).max()
+            co[t, e] = orcs[e].contacts()[0]
+    for e in range(N):
+        assert (co[:, e] > 0).sum() >= 20, e                       # the scenario does collide
+        first = int(np.argmax(co[:, e] > 0))
+        assert int(np.argmax(cg[:, e] > 0)) == first, e
+        assert (cg[:, e] != co[:, e]).mean() <= 0.05, e
+        assert dev[:first + 30, e].max() <= 0.02, (e, dev[:first + 30, e].max())
+        assert dev[:, e].max() <= 0.1, (e, dev[:, e].max())
+    print("collision parity: max dev +30 %.2e, end %.2e" % (max(dev[:int(np.argmax(co[:, e] > 0)) + 30, e].max() for e in range(N)), dev.max()))
+    envs.close()
+
+
+def test_collision_fixture_from_reference_python():
+    """tests/golden/car_double_collision.npz: the reference's own CarRacing.step with two cars steered into each other."""
+    g = load_golden("car_double_collision")
+    draws = g["all_draws"].reshape(1, -1, 24)
+    envs = _make("cCarRacingDouble-v0", 1, track_draws=draws, birth=g["birth"].reshape(1, 1, 2).astype(np.int32))
+    envs.reset()
+    first = int(np.argmax(g["contacts"] > 0))
+    T = min(len(g["actions"]), first + 40)
+    same = 0
+    for t in range(T):
+        obs, r, d, info = envs.step(g["actions"][t].astype(np.float32)[None])
+        s = envs.get_state().cpu().numpy()[0]
+        cnt, over = envs.get_contacts()
+        same += int(cnt[0] == g["contacts"][t])
+        assert np.abs(s[:, :3] - g["states"][t][:, :3]).max() <= 0.02, t
+        assert np.abs(info.rewards.cpu().numpy()[0] - g["rewards"][t]).max() <= 1e-4, t
+        if t <= first:
+            assert (cnt[0] > 0) == (g["contacts"][t] > 0), t
+    assert same >= 0.95 * T
+    envs.close()
+
+
+def test_double_cars_never_pass_through_each_other():
+    """512 two-car envs on random tracks, cars steered at each other with random strength."""
+    N = 512
+    envs = _make("cCarRacingDouble-v0", N, seed=9)
+    envs.reset()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    steer = 0.15 + 0.35 * torch.rand((N,), generator=gen, device="cuda")
+    gas = 0.3 + 0.5 * torch.rand((N, 2), generator=gen, device="cuda")
+    a = torch.zeros((N, 2, 2), device="cuda")
+    a[:, 0, 0], a[:, 1, 0] = -steer, steer
+    a[:, :, 1] = gas
+    dmin = torch.full((N,), 1e9, device="cuda", dtype=torch.float64)
+    touched = np.zeros((N,), bool)
+    for t in range(100):
+        o, r, d, info = envs.step(a)
+        s = envs.get_state()
+        dist = torch.hypot(s[:, 0, 0] - s[:, 1, 0], s[:, 0, 1] - s[:, 1, 1])
+        dmin = torch.minimum(dmin, torch.where(d.bool(), dmin, dist))     # a reset respawns the cars 5 apart
+        cnt, over = envs.get_contacts()
+        touched |= cnt > 0
+    assert over == 0
+    assert touched.mean() > 0.3         # birth places are shuffled: about half of the pairs steer towards each other
+    assert float(dmin.min()) > 1.9      # hull half-widths 1.2 + 1.2 side by side (2.4 minus skins and slop); through = ~0
     envs.check()
     envs.close()
