@@ -109,7 +109,8 @@ struct CarDev {
     int k_draws;
     const int32_t* birth;        // [n][k_birth][players] or nullptr
     int k_birth;
-    int32_t* overrun;            // device flag: an injection table ran out
+    int32_t* overrun;            // [0] device flag: an injection table ran out; [1] frames whose rasteriser dropped polygons;
+                                 // [2] frames rasterised on the exact slow path (a cell list overflowed)
     // ---- constants ----
     const CarHullConst* consts;
     const uint8_t* glyphs;       // [CAR_GLYPH_BYTES]

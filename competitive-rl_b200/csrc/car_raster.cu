@@ -11,10 +11,12 @@
 // nearest neighbour) and centre-blits it to the 96x96 screen, then draws the cars' fixture polygons and the
 // HUD.  No map is ever built here: every destination pixel is mapped through the same integer pipeline
 // (screen -> rotated surface -> source crop -> road-map pixel (U, V)) and coloured by the last polygon in
-// paint order whose pygame scanline fill covers (U, V).  Per polygon one warp builds the scanline span table
-// (pygame 1.9 draw_fillpoly: C integer division per edge) in shared memory and sweeps the polygon's screen
-// bounding box; atomicMax on (paint order << 8 | gray) lets all polygons fill in parallel while the
-// reference's painter's order decides each pixel.  pygame's integer rules are restated from memory exactly
+// paint order whose pygame scanline fill covers (U, V).  Every polygon that can reach the window (road tiles and
+// kerbs in road-map pixels, car fixtures in screen pixels) gets its scanline span table (pygame 1.9
+// draw_fillpoly: C integer division per edge) in one shared-memory pool and is binned, by the screen bounding
+// box of its vertices, into 8x8-pixel cells; a warp then walks a cell with two pixels per lane and tests only
+// that cell's polygons, keeping the largest (paint order << 8 | gray) -- the reference's painter's order --
+// per pixel in registers.  pygame's integer rules are restated from memory exactly
 // as in oracle/ref_shim/pygame, under which the reference's own renderer reproduces these frames bit for bit
 // (tests/golden/car_frames.npz); parity against a real pygame build is unpinned.
 #include <math.h>
@@ -31,9 +33,12 @@ namespace crl {
 
 constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
-constexpr int MAX_CAND = 192;
-constexpr int KEY_STRIDE = CAR_W + 1;      // padded: lanes of a pass touch different rows of the same columns
-constexpr int SPAN_ROWS = 64;              // scanlines of one polygon (road tiles need <= ~30)
+constexpr int MAX_CAND = 176;              // road tiles that can reach the visible window
+constexpr int MAX_POLY = 232;              // tiles + kerbs + 16 car polygons of one frame (ids fit a byte)
+constexpr int POOL_ROWS = 2304;            // scanline span table shared by all polygons of a frame
+constexpr int CELL = 8, CELLS_X = CAR_W / CELL, N_CELLS = CELLS_X * (CAR_H / CELL);
+constexpr int CELL_CAP = 40;               // polygons binned to one 8x8 screen cell (more: exact slow path)
+constexpr unsigned short NO_TABLE = 0xFFFFu;
 
 __constant__ float c_hull_poly[4][8][2] = {
     {{-60, +130}, {+60, +130}, {+60, +110}, {-60, +110}},
@@ -81,9 +86,17 @@ __device__ __forceinline__ void map_to_screen(const FrameMap& m, float u, float 
     Y = (-(float)m.isin * dx + (float)m.icos * dy) * m.inv_det + (float)m.by;
 }
 
+// C integer division a / b (b > 0, truncation towards zero).  For |a| < 2^24 the correctly rounded float quotient of
+// two integers truncates to the exact answer (a non-integer quotient is at least 1/b away from an integer, the
+// rounding error is below |a/b| * 2^-24), which is several times cheaper than the emulated 32-bit division.
+__device__ __forceinline__ int cdiv_trunc(int a, int b) {
+    if (abs(a) < (1 << 24)) return (int)__fdiv_rn((float)a, (float)b);
+    return a / b;
+}
+
 // pygame 1.9 draw_fillpoly, one scanline: x spans (inclusive) of polygon (vx, vy)[n] at row V.
 // Up to two spans (outlines with <= 8 vertices used here never give more); empty span = (1, 0).
-__device__ __forceinline__ int4 scanline_spans(const int* vx, const int* vy, int n, int V, int maxy) {
+__device__ __forceinline__ short4 scanline_spans(const short* vx, const short* vy, int n, int V, int maxy) {
     int xs[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
     int m = 0;
 #pragma unroll
@@ -93,7 +106,7 @@ __device__ __forceinline__ int4 scanline_spans(const int* vx, const int* vy, int
             int y1 = vy[i1], y2 = vy[i], x1 = vx[i1], x2 = vx[i];
             if (y1 > y2) { int t = y1; y1 = y2; y2 = t; t = x1; x1 = x2; x2 = t; }
             if (y1 != y2 && ((V >= y1 && V < y2) || (V == maxy && V > y1 && V <= y2))) {
-                const int x = (V - y1) * (x2 - x1) / (y2 - y1) + x1;      // C integer division
+                const int x = cdiv_trunc((V - y1) * (x2 - x1), y2 - y1) + x1;      // C integer division
                 if (m == 0) xs[0] = x; else if (m == 1) xs[1] = x; else if (m == 2) xs[2] = x; else if (m == 3) xs[3] = x;
                 ++m;
             }
@@ -104,29 +117,54 @@ __device__ __forceinline__ int4 scanline_spans(const int* vx, const int* vy, int
     CSWAP(0, 1) CSWAP(2, 3) CSWAP(0, 2) CSWAP(1, 3) CSWAP(1, 2)
 #undef CSWAP
     m = min(m, 4);
-    int4 r = make_int4(1, 0, 1, 0);
-    if (m >= 2) { r.x = xs[0]; r.y = xs[1]; }
-    if (m >= 4) { r.z = xs[2]; r.w = xs[3]; }
+    short4 r = make_short4(1, 0, 1, 0);
+    if (m >= 2) { r.x = (short)xs[0]; r.y = (short)xs[1]; }
+    if (m >= 4) { r.z = (short)xs[2]; r.w = (short)xs[3]; }
     return r;
 }
 
-// Fill polygon (vx, vy)[n] given in the coordinate system `MAPPED ? road map : screen` into the key buffer.
-template <bool MAPPED>
-__device__ void fill_ipoly(unsigned int* keys, int4* spans, const FrameMap& fm, const int* vx, const int* vy, int n,
-                           unsigned int key, int lane) {
+// pygame.draw.rect(screen, color, (x, y, w, h)) = polygon (l, t), (r, t), (r, b), (l, b), r = x + w - 1, b = y + h - 1
+__device__ __forceinline__ void hud_rect(uint8_t* img, double x, double y, double w, double h, uint8_t val, int tid, int nthreads) {
+    const int X = (int)x, Y = (int)y, W = (int)w, H = (int)h;
+    const int l = X, r = X + W - 1, t = Y, b = Y + H - 1;
+    if (t == b) return;                                   // every edge horizontal or degenerate: nothing is filled
+    const int x0 = max(min(l, r), 0), x1 = min(max(l, r), CAR_W - 1), y0 = max(min(t, b), 0), y1 = min(max(t, b), CAR_H - 1);
+    const int bw = x1 - x0 + 1, total = bw * (y1 - y0 + 1);
+    if (bw <= 0 || total <= 0) return;
+    for (int q = tid; q < total; q += nthreads) img[(y0 + q / bw) * CAR_W + x0 + q % bw] = val;
+}
+
+// one polygon of the frame: rows [miny, miny + rows) of its span table start at spans[off] (NO_TABLE: the pool was
+// full, spans are recomputed per pixel); screen = 1: vertices are screen pixels (cars), else road-map pixels
+struct __align__(16) PolyMeta { short miny, rows; unsigned short off; unsigned char n, screen; unsigned int key; unsigned int pad; };
+
+struct RasterSmem {
+    uint8_t img[CAR_PIX];
+    short4 spans[POOL_ROWS];
+    uint8_t row_owner[POOL_ROWS];
+    short pvx[MAX_POLY][8], pvy[MAX_POLY][8];
+    PolyMeta meta[MAX_POLY];
+    uint8_t cell_list[N_CELLS][CELL_CAP];
+    int cell_count[N_CELLS];
+    int cand[MAX_CAND];
+    uint8_t chk_x[2 * CAR_W], chk_y[2 * CAR_H];   // is road-map column rx + i / row ry + i inside a checker square
+    float car_body[CAR_MAX_PLAYERS][40];
+    double hud_vals[8];
+    FrameMap fm;
+    int n_cand, n_poly, pool_used, overflow;
+};
+
+// Register polygon (vx, vy)[n] of the frame: id, span-table rows, cell bins.  One thread per polygon.
+__device__ void add_polygon(RasterSmem& S, const FrameMap& fm, const int* vx, const int* vy, int n, unsigned int key, bool screen) {
     int minx = vx[0], maxx = vx[0], miny = vy[0], maxy = vy[0];
 #pragma unroll
     for (int i = 1; i < 8; ++i)
         if (i < n) { minx = min(minx, vx[i]); maxx = max(maxx, vx[i]); miny = min(miny, vy[i]); maxy = max(maxy, vy[i]); }
     const int rows = maxy - miny + 1;
-    if (rows > SPAN_ROWS || rows <= 0) return;            // not reachable for this geometry
-    for (int r = lane; r < rows; r += 32) spans[r] = scanline_spans(vx, vy, n, miny + r, maxy);
-    __syncwarp();
     int X0, X1, Y0, Y1;
-    if (MAPPED) {
-        // Every covered map pixel lies within one pixel of the polygon's hull, so the screen hull of the
-        // (mapped) vertices, grown by the truncations along the way, bounds the sweep far tighter than the
-        // rotated map-space box would.
+    if (!screen) {
+        // Every covered map pixel lies within one pixel of the polygon's hull, so the screen hull of the (mapped)
+        // vertices, grown by the truncations along the way, bounds the covered screen pixels.
         float fx0 = 1e9f, fx1 = -1e9f, fy0 = 1e9f, fy1 = -1e9f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -141,50 +179,73 @@ __device__ void fill_ipoly(unsigned int* keys, int4* spans, const FrameMap& fm, 
     } else {
         X0 = max(0, minx); X1 = min(CAR_W - 1, maxx); Y0 = max(0, miny); Y1 = min(CAR_H - 1, maxy);
     }
-    if (X1 >= X0 && Y1 >= Y0) {
-        const int bw = X1 - X0 + 1;
-        const int lw = (bw <= 8) ? 3 : (bw <= 16) ? 4 : 5;          // pass shape 4x8, 2x16 or 1x32
-        const int lx = lane & ((1 << lw) - 1), ly = lane >> lw, rows_per_pass = 32 >> lw;
-        for (int yb = Y0; yb <= Y1; yb += rows_per_pass) {
-            const int Y = yb + ly;
-            for (int xb = X0; xb <= X1; xb += (1 << lw)) {
-                const int X = xb + lx;
-                int U = X, V = Y;
-                bool ok = (Y <= Y1) && (X <= X1);
-                if (MAPPED) map_pixel_nocheck(fm, X, Y, U, V);
-                const int r = V - miny;
-                if (ok && r >= 0 && r < rows) {
-                    const int4 sp = spans[r];
-                    if ((U >= sp.x && U <= sp.y) || (U >= sp.z && U <= sp.w)) atomicMax(&keys[Y * KEY_STRIDE + X], key);
-                }
+    if (X1 < X0 || Y1 < Y0 || rows <= 0) return;          // cannot touch the window
+    const int id = atomicAdd(&S.n_poly, 1);
+    if (id >= MAX_POLY) { S.overflow = 2; return; }       // polygon dropped (reported through crl_car_check)
+    int off = atomicAdd(&S.pool_used, rows);
+    if (off + rows > POOL_ROWS) { off = NO_TABLE; S.overflow = 1; }
+    else for (int r = 0; r < rows; ++r) S.row_owner[off + r] = (uint8_t)id;
+    PolyMeta m;
+    m.miny = (short)miny; m.rows = (short)rows; m.off = (unsigned short)off; m.n = (unsigned char)n; m.screen = screen ? 1 : 0; m.key = key; m.pad = 0u;
+    S.meta[id] = m;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { S.pvx[id][i] = (short)max(-32000, min(32000, vx[i])); S.pvy[id][i] = (short)max(-32000, min(32000, vy[i])); }
+    for (int cy = Y0 / CELL; cy <= Y1 / CELL; ++cy)
+        for (int cx = X0 / CELL; cx <= X1 / CELL; ++cx) {
+            const int slot = atomicAdd(&S.cell_count[cy * CELLS_X + cx], 1);
+            if (slot < CELL_CAP) S.cell_list[cy * CELLS_X + cx][slot] = (uint8_t)id;
+            else S.overflow = 1;                            // that frame walks all polygons per pixel instead
+        }
+}
+
+// Pixels of the frame: a warp walks one 8x8 cell at a time, lane = (x, y) and (x, y + 4).  Background: black outside
+// the source crop, else grass / checker by road-map pixel; then the polygons binned to the cell, largest key wins.
+// SLOW (a cell list or the span pool overflowed): every polygon of the frame is tested, spans recomputed if needed.
+template <bool SLOW>
+__device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, unsigned int g_grass, unsigned int g_check,
+                                           int warp, int lane) {
+    uint8_t* img = S.img;
+    const int n_poly = min(S.n_poly, MAX_POLY);
+    const int lx = lane & 7, ly = lane >> 3;
+    // dx = cx0 + icos * x - isin * y, dy = cy0 + isin * x + icos * y with (x, y) = (X - bx, Y - by): affine in the lane
+    const int ldx = fm.cx0 + fm.icos * (lx - fm.bx) - fm.isin * (ly - fm.by);
+    const int ldy = fm.cy0 + fm.isin * (lx - fm.bx) + fm.icos * (ly - fm.by);
+    const int lim = (2 * CAR_W << 16) - 1;
+    for (int cell = warp; cell < N_CELLS; cell += RASTER_WARPS) {
+        const int cx = (cell % CELLS_X) * CELL, cy = (cell / CELLS_X) * CELL;
+        const int X = cx + lx, Ya = cy + ly, Yb = Ya + 4;
+        const int dxa = ldx + fm.icos * cx - fm.isin * cy, dya = ldy + fm.isin * cx + fm.icos * cy;
+        const int dxb = dxa - 4 * fm.isin, dyb = dya + 4 * fm.icos;
+        int Ua = -30000, Va = -30000, Ub = -30000, Vb = -30000;
+        unsigned int ka = 0u, kb = 0u;      // surfaces start black
+        if ((unsigned)dxa <= (unsigned)lim && (unsigned)dya <= (unsigned)lim) {
+            Ua = fm.rx + (dxa >> 16); Va = fm.ry + (dya >> 16);
+            ka = (S.chk_x[dxa >> 16] & S.chk_y[dya >> 16]) ? g_check : g_grass;
+        }
+        if ((unsigned)dxb <= (unsigned)lim && (unsigned)dyb <= (unsigned)lim) {
+            Ub = fm.rx + (dxb >> 16); Vb = fm.ry + (dyb >> 16);
+            kb = (S.chk_x[dxb >> 16] & S.chk_y[dyb >> 16]) ? g_check : g_grass;
+        }
+        const int cnt = SLOW ? n_poly : min(S.cell_count[cell], CELL_CAP);
+        for (int k = 0; k < cnt; ++k) {
+            const int id = SLOW ? k : S.cell_list[cell][k];
+            const PolyMeta m = S.meta[id];
+            if (m.key < ka && m.key < kb) continue;
+            const int xa = m.screen ? X : Ua, ya = m.screen ? Ya : Va, xb = m.screen ? X : Ub, yb = m.screen ? Yb : Vb;
+            const int ra = ya - m.miny, rb = yb - m.miny;
+            if ((unsigned)ra < (unsigned)m.rows && m.key > ka) {
+                const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + ra] : scanline_spans(S.pvx[id], S.pvy[id], m.n, ya, m.miny + m.rows - 1);
+                if ((xa >= sp.x && xa <= sp.y) || (xa >= sp.z && xa <= sp.w)) ka = m.key;
+            }
+            if ((unsigned)rb < (unsigned)m.rows && m.key > kb) {
+                const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + rb] : scanline_spans(S.pvx[id], S.pvy[id], m.n, yb, m.miny + m.rows - 1);
+                if ((xb >= sp.x && xb <= sp.y) || (xb >= sp.z && xb <= sp.w)) kb = m.key;
             }
         }
+        img[Ya * CAR_W + X] = (uint8_t)(ka & 255u);
+        img[Yb * CAR_W + X] = (uint8_t)(kb & 255u);
     }
-    __syncwarp();
 }
-
-// pygame.draw.rect(screen, color, (x, y, w, h)) = polygon (l, t), (r, t), (r, b), (l, b), r = x + w - 1, b = y + h - 1
-__device__ __forceinline__ void hud_rect(uint8_t* img, double x, double y, double w, double h, uint8_t val, int tid) {
-    const int X = (int)x, Y = (int)y, W = (int)w, H = (int)h;
-    const int l = X, r = X + W - 1, t = Y, b = Y + H - 1;
-    if (t == b) return;                                   // every edge horizontal or degenerate: nothing is filled
-    const int x0 = max(min(l, r), 0), x1 = min(max(l, r), CAR_W - 1), y0 = max(min(t, b), 0), y1 = min(max(t, b), CAR_H - 1);
-    const int bw = x1 - x0 + 1, total = bw * (y1 - y0 + 1);
-    if (bw <= 0 || total <= 0) return;
-    for (int q = tid; q < total; q += RASTER_THREADS) img[(y0 + q / bw) * CAR_W + x0 + q % bw] = val;
-}
-
-struct RasterSmem {
-    unsigned int keys[CAR_H * KEY_STRIDE];
-    uint8_t img[CAR_PIX];
-    int4 spans[RASTER_WARPS][SPAN_ROWS];
-    int cand[MAX_CAND];
-    uint8_t chk_x[2 * CAR_W], chk_y[2 * CAR_H];   // is road-map column rx + i / row ry + i inside a checker square
-    float car_body[CAR_MAX_PLAYERS][40];
-    double hud_vals[8];
-    FrameMap fm;
-    int n_cand;
-};
 
 __global__ void __launch_bounds__(RASTER_THREADS)
 car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* __restrict__ term_obs) {
@@ -199,6 +260,8 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
     const int* checker = K->checker;
 
     if (tid < p.players * 40) S.car_body[tid / 40][tid % 40] = p.body[((size_t)e * p.players + tid / 40) * 40 + tid % 40];
+    if (tid < (2 * CAR_W + 2 * CAR_H) / 4) reinterpret_cast<uint32_t*>(S.chk_x)[tid] = 0u;     // chk_x and chk_y are adjacent
+    if (tid >= 96 && tid < 96 + N_CELLS) S.cell_count[tid - 96] = 0;
     __syncthreads();
     if (tid == 0) {
         // ---- camera_update("rgb_array"): hull.position + R(angle) * (0, 16) ----
@@ -237,7 +300,7 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
         const float ta = (float)(-angle);
         sincosf(ta, &m.ts, &m.tc);
         S.fm = m;
-        S.n_cand = 0;
+        S.n_cand = 0; S.n_poly = 0; S.pool_used = 0; S.overflow = 0;
         // HUD inputs (render_indicators_for_pygame :645-670)
         const double* wd = p.wheel + ((size_t)e * p.players + pi) * 8;
         S.hud_vals[0] = sqrt(vx * vx + vy * vy);
@@ -250,72 +313,57 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
     const FrameMap fm = S.fm;
     const int n_track = p.n_track[e];
     const CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
-    unsigned int* keys = S.keys;
 
-    // ---- background: black outside the source, else grass / checker squares (:733-746) by road-map pixel.
-    //      The squares are axis-aligned in the road map: tabulate per crop column / row whether it lies in one. ----
-    for (int i = tid; i < 2 * CAR_W + 2 * CAR_H; i += RASTER_THREADS) {
-        const bool is_y = i >= 2 * CAR_W;
-        const int v = is_y ? fm.ry + (i - 2 * CAR_W) : fm.rx + i;
-        const int* tab = checker + (is_y ? 40 : 0);
-        bool in = false;
-#pragma unroll 4
-        for (int c = 0; c < 20; ++c) in = in || (v >= tab[2 * c] && v <= tab[2 * c + 1]);
-        if (is_y) S.chk_y[i - 2 * CAR_W] = in; else S.chk_x[i] = in;
+    // ---- checker squares (:733-746) are axis-aligned in the road map: mark the crop columns / rows that lie in one
+    //      (20 squares per axis, each ~29 px wide; the tables were cleared above) ----
+    if (tid >= 64 && tid < 64 + 40) {
+        const int q = tid - 64, is_y = q >= 20;
+        const int lo = checker[2 * q], hi = checker[2 * q + 1], base = is_y ? fm.ry : fm.rx;
+        uint8_t* tab = is_y ? S.chk_y : S.chk_x;
+        for (int v = max(lo - base, 0); v <= min(hi - base, 2 * CAR_W - 1); ++v) tab[v] = 1;
     }
-    __syncthreads();
-    for (int Y = warp; Y < CAR_H; Y += RASTER_WARPS) {
-        for (int X = lane; X < CAR_W; X += 32) {
-            int U, V;
-            unsigned int key = 0u;    // surfaces start black
-            if (map_pixel(fm, X, Y, U, V)) key = (S.chk_x[U - fm.rx] && S.chk_y[V - fm.ry]) ? G[G_CHECK] : G[G_GRASS];
-            keys[Y * KEY_STRIDE + X] = key;
-        }
-    }
-    // ---- cull: tiles that can reach the visible window (the central 96x96 of the rotated crop; ordered by index) ----
+    // ---- cull: road tiles whose centre, mapped to the screen, lies within the window grown by the tile's reach
+    //      (farthest kerb corner 8.7 units = 15.4 px, plus the slack of the integer pipeline); ordered by index ----
     if (warp == 0) {
-        const double reach = (48.0 * 1.4142135623730951 + 4.0) / fm.obs_scale + 2.0 * CR_TRACK_WIDTH + CR_BORDER + CR_TRACK_DETAIL_STEP;
-        const float r2 = (float)(reach * reach);
+        const float reach = 20.0f;
         int base = 0;
         for (int t0 = 0; t0 < n_track; t0 += 32) {
             const int t = t0 + lane;
             bool in = false;
             if (t < n_track) {
-                const float dx = tiles[t].cx - fm.camx, dy = tiles[t].cy - fm.camy;
-                in = dx * dx + dy * dy <= r2;
+                const float u = (float)(fm.obs_scale * -(double)tiles[t].cx + 5000.0), v = (float)(fm.obs_scale * -(double)tiles[t].cy + 5000.0);
+                float X, Y;
+                map_to_screen(fm, u, v, X, Y);
+                in = X > -reach && X < CAR_W + reach && Y > -reach && Y < CAR_H + reach;
             }
             const unsigned m = __ballot_sync(0xffffffffu, in);
             const int pos = base + __popc(m & ((1u << lane) - 1u));
             if (in && pos < MAX_CAND) S.cand[pos] = t;
             base += __popc(m);
         }
-        if (lane == 0) S.n_cand = min(base, MAX_CAND);
+        if (lane == 0) { S.n_cand = min(base, MAX_CAND); if (base > MAX_CAND) atomicAdd(p.overrun + 1, 1); }   // tiles dropped: crl_car_check reports it
     }
     __syncthreads();
-    // ---- road: paint order is tile n-1 .. 0, each followed by its kerb (:399-445); higher key wins ----
+    // ---- polygons of the frame, one thread each.  Road: paint order is tile n-1 .. 0, each followed by its kerb
+    //      (:399-445).  Cars (Car.draw_for_pygame): for k in cars: wheels, then hull fixtures; b2Vec2 fp32 arithmetic:
+    //      path = -scale * (tmp * ((trans * v) - offset)) + (W/2, H/2), truncated to int by pygame.  Higher key wins. ----
     {
-        const int nc = S.n_cand;
-        for (int q = warp; q < nc; q += RASTER_WARPS) {
-            const int t = S.cand[q];
+        const int nc = S.n_cand, per_car = 8;   // 4 wheels + 4 hull fixtures
+        if (tid < nc) {
+            const int t = S.cand[tid];
             const CarTile T = tiles[t];
             const unsigned int order = 2u * (unsigned)(n_track - 1 - t) + 1u;
             int vx[8], vy[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { vx[i] = (i < 5) ? T.mx[i] : 0; vy[i] = (i < 5) ? T.my[i] : 0; }
-            fill_ipoly<true>(keys, S.spans[warp], fm, vx, vy, 5, (order << 8) | G[G_ROAD0 + t % 3], lane);
+            add_polygon(S, fm, vx, vy, 5, (order << 8) | G[G_ROAD0 + t % 3], false);
             if (T.flags & 2) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { vx[i] = T.kmx[i]; vy[i] = T.kmy[i]; }
-                fill_ipoly<true>(keys, S.spans[warp], fm, vx, vy, 4, ((order + 1u) << 8) | ((T.flags & 4) ? G[G_KERB_W] : G[G_KERB_R]), lane);
+                add_polygon(S, fm, vx, vy, 4, ((order + 1u) << 8) | ((T.flags & 4) ? G[G_KERB_W] : G[G_KERB_R]), false);
             }
-        }
-    }
-    __syncthreads();
-    // ---- cars (Car.draw_for_pygame): for k in cars: wheels, then hull fixtures; b2Vec2 fp32 arithmetic:
-    //      path = -scale * (tmp * ((trans * v) - offset)) + (W/2, H/2), truncated to int by pygame ----
-    {
-        const int per_car = 8;   // 4 wheels + 4 hull fixtures
-        for (int q = warp; q < p.players * per_car; q += RASTER_WARPS) {
+        } else if (tid >= RASTER_THREADS - p.players * per_car) {
+            const int q = RASTER_THREADS - 1 - tid;
             const int ck = q / per_car, part = q % per_car;
             const float* b = S.car_body[ck];
             const unsigned int order = 2048u + (unsigned)(ck * per_car + part);
@@ -343,29 +391,45 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
                 }
             }
             const uint8_t g = (part < 4) ? G[G_WHEEL] : ((ck == pi) ? G[G_OWN] : G[G_OTHER]);
-            fill_ipoly<false>(keys, S.spans[warp], fm, vx, vy, n, (order << 8) | g, lane);
+            add_polygon(S, fm, vx, vy, n, (order << 8) | g, true);
         }
     }
     __syncthreads();
-    uint8_t* img = S.img;
-    for (int r = warp; r < CAR_H; r += RASTER_WARPS)
-        for (int c = lane; c < CAR_W; c += 32) img[r * CAR_W + c] = (uint8_t)(keys[r * KEY_STRIDE + c] & 255u);
+    if (tid == 0 && S.overflow != 0) atomicAdd(p.overrun + (S.overflow == 2 ? 1 : 2), 1);   // [1] polygons dropped, [2] frames on the slow path
+    // ---- span tables: one (polygon, row) per thread and pass ----
+    {
+        const int total = min(S.pool_used, POOL_ROWS);
+        for (int i = tid; i < total; i += RASTER_THREADS) {
+            const int id = S.row_owner[i];
+            const PolyMeta m = S.meta[id];
+            if (m.off == NO_TABLE || i < (int)m.off || i >= (int)m.off + m.rows) continue;   // tail of a polygon that did not fit
+            S.spans[i] = scanline_spans(S.pvx[id], S.pvy[id], m.n, m.miny + (i - (int)m.off), m.miny + m.rows - 1);
+        }
+    }
     __syncthreads();
-    // ---- HUD (painted after the scene) ----
+    // ---- pixels ----
+    uint8_t* img = S.img;
+    if (S.overflow == 0) walk_cells<false>(S, fm, G[G_GRASS], G[G_CHECK], warp, lane);
+    else walk_cells<true>(S, fm, G[G_GRASS], G[G_CHECK], warp, lane);
+    __syncthreads();
+    // ---- HUD (painted after the scene): the black bar by the whole CTA, the small indicators and the text, which
+    //      overlap and are painted in order, by warp 0 ----
     {
         const double W = CAR_W, H = CAR_H, s = W / 40.0, h = H / 40.0;
-        hud_rect(img, 0, H - 4 * h, W, 4 * h * 1000, G[G_HUD], tid);
+        hud_rect(img, 0, H - 4 * h, W, 4 * h * 1000, G[G_HUD], tid, RASTER_THREADS);
         __syncthreads();
-        hud_rect(img, 5 * s, H - h, s, h * (-0.02 * S.hud_vals[0]), G[G_BLUE], tid);
-        __syncthreads();
-        for (int k = 0; k < 4; ++k) {
-            hud_rect(img, (7 + k) * s, H - h, s, h * (-0.01 * S.hud_vals[1 + k]), k < 2 ? G[G_BLUE] : G[G_BLUE2], tid);
-            __syncthreads();
+        if (warp == 0) {
+            hud_rect(img, 5 * s, H - h, s, h * (-0.02 * S.hud_vals[0]), G[G_BLUE], lane, 32);
+            __syncwarp();
+            for (int k = 0; k < 4; ++k) {
+                hud_rect(img, (7 + k) * s, H - h, s, h * (-0.01 * S.hud_vals[1 + k]), k < 2 ? G[G_BLUE] : G[G_BLUE2], lane, 32);
+                __syncwarp();
+            }
+            hud_rect(img, 20 * s, H - 2 * h, s * (10.0 * S.hud_vals[5]), 2 * h, G[G_GREEN], lane, 32);
+            __syncwarp();
+            hud_rect(img, 30 * s, H - 2 * h, s * (0.8 * S.hud_vals[6]), 2 * h, G[G_RED], lane, 32);
+            __syncwarp();
         }
-        hud_rect(img, 20 * s, H - 2 * h, s * (10.0 * S.hud_vals[5]), 2 * h, G[G_GREEN], tid);
-        __syncthreads();
-        hud_rect(img, 30 * s, H - 2 * h, s * (0.8 * S.hud_vals[6]), 2 * h, G[G_RED], tid);
-        __syncthreads();
         if (tid == 0 && p.glyphs != nullptr) {     // draw_text("%05.0f" % reward) at (W/100, H - H/20)
             // "%05.0f": round half to even, sign kept for negative values, zero padded to width 5
             const double rv = S.hud_vals[7];

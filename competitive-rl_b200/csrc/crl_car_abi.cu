@@ -234,7 +234,7 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     ALLOC(d.attempt_count, n); ALLOC(d.inv_dt0, n); ALLOC(d.env_done, n); ALLOC(d.ring_pos, n);
     ALLOC(d.body, nc * 40); ALLOC(d.joint, nc * 24); ALLOC(d.wheel, nc * 8); ALLOC(d.reward, nc * 2);
     ALLOC(d.counters, nc * 4); ALLOC(d.touching, nc * 64); ALLOC(d.visited, nc * 16);
-    ALLOC(d.ring, nc * d.c * CAR_PIX); ALLOC(d.overrun, 1); ALLOC(d.stats, 8);
+    ALLOC(d.ring, nc * d.c * CAR_PIX); ALLOC(d.overrun, 4); ALLOC(d.stats, 8);
     ALLOC(d.contact_overflow, 1);
     if (P == 2) { ALLOC(d.contacts, n * CAR_MAX_CONTACTS); ALLOC(d.n_contacts, n); }
     CarHullConst* kdev = nullptr;
@@ -387,9 +387,11 @@ int crl_car_get_contacts(crl_car* h, int32_t* counts_host, int32_t* overflow_hos
 
 int crl_car_check(crl_car* h, void* stream) {
     CHECK_HANDLE(h);
-    int32_t flag = 0;
-    CUDA_TRY(cudaMemcpyAsync(&flag, h->dev.overrun, sizeof flag, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    int32_t flags[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(flags, h->dev.overrun, sizeof flags, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    const int32_t flag = flags[0];
+    if (flags[1] != 0) return crl_set_error(CRL_E_STATE, "rasteriser dropped polygons in %d frame(s) (more road tiles in view than its tables hold)", flags[1]);
     if (flag == 1) return crl_set_error(CRL_E_SERVES, "injected track-draw / birth-place table exhausted");
     if (flag == 2) return crl_set_error(CRL_E_STATE, "track generation failed 64 times in a row");
     return CRL_OK;

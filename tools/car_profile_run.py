@@ -1,0 +1,20 @@
+"""Short cCarRacingDouble run for ncu captures: 16384 envs, a few steps (tools/bench_car.py is the timed one)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from competitive_rl_b200 import make_envs
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 60
+envs = make_envs("cCarRacingDouble-v0", num_envs=n, frame_stack=4, log_dir=None, seed=1, n_buffers=1)
+envs.reset()
+gen = torch.Generator(device="cuda").manual_seed(0)
+for t in range(steps):
+    a = torch.rand((n, 2, 2), generator=gen, device="cuda") * 2 - 1
+    a[:, :, 0] *= 0.3
+    envs.step(a)
+torch.cuda.synchronize()
+cnt, over = envs.get_contacts()
+print("envs in contact: %.3f, overflow %d" % ((cnt > 0).mean(), over))
+envs.check()
