@@ -25,6 +25,7 @@ constexpr int CAR_SAMPLE_STRIDE = 8;        // every 8th track point feeds the c
 constexpr int CAR_MAX_SAMPLES = CAR_MAX_TRACK / CAR_SAMPLE_STRIDE;
 constexpr int CAR_MAX_STACK = 8;
 constexpr int CAR_GLYPH_BYTES = 11 * 8 * 4 + 11;
+constexpr int CAR_MAX_CAND = 176;           // road tiles of one frame that can reach the 96x96 window
 constexpr int CAR_MAX_CONTACTS = 8;         // touching car-car fixture pairs kept per env (of 48 possible)
 
 // A road tile, 116 bytes: for the physics the convex hull (CCW, fp32) of the reference's 5 listed
@@ -69,6 +70,8 @@ struct CarHullConst {         // mass data of the car bodies (b2Body::ResetMassD
 enum CarGray { G_GRASS = 0, G_CHECK, G_ROAD0, G_ROAD1, G_ROAD2, G_KERB_W, G_KERB_R, G_WHEEL, G_OWN, G_OTHER, G_HUD,
                G_BLUE, G_BLUE2, G_GREEN, G_RED, G_TEXT };
 
+struct FrameMap;              // per-frame camera / screen -> road-map mapping (car_raster.cu)
+
 struct CarDev {
     int n;                    // envs in this shard
     int players;              // 1 = cCarRacing-v0, 2 = cCarRacingDouble-v0
@@ -102,6 +105,10 @@ struct CarDev {
     CarContact* contacts;
     int32_t* n_contacts;
     int32_t* contact_overflow;
+    // ---- per frame (env * players + player): written by car_frame_setup_kernel, read by car_render_kernel ----
+    FrameMap* frame_map;      // [n*players]
+    uint16_t* frame_cand;     // [n*players][CAR_MAX_CAND] road tiles that can reach the window
+    int32_t* frame_ncand;     // [n*players]
     // ---- observation ring: [n][players][c][CAR_PIX] ----
     uint8_t* ring;
     // ---- validation mode ----
@@ -122,6 +129,7 @@ cudaError_t launch_car_step(const CarDev& p, const float* actions, float* rew, u
                             uint8_t* truncated, cudaStream_t s);
 cudaError_t launch_car_render(const CarDev& p, int only_done, uint8_t* obs, uint8_t* term_obs, cudaStream_t s);
 cudaError_t car_raster_init();
+size_t car_frame_map_bytes();
 void car_checker_table(int* out);
 cudaError_t launch_car_get_state(const CarDev& p, double* state, cudaStream_t s);
 cudaError_t launch_car_random_actions(float* actions, int n_values, uint64_t seed, uint64_t step, cudaStream_t s);

@@ -33,12 +33,12 @@ namespace crl {
 
 constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
-constexpr int MAX_CAND = 176;              // road tiles that can reach the visible window
 constexpr int MAX_POLY = 232;              // tiles + kerbs + 16 car polygons of one frame (ids fit a byte)
 constexpr int POOL_ROWS = 2304;            // scanline span table shared by all polygons of a frame
 constexpr int CELL = 8, CELLS_X = CAR_W / CELL, N_CELLS = CELLS_X * (CAR_H / CELL);
 constexpr int CELL_CAP = 40;               // polygons binned to one 8x8 screen cell (more: exact slow path)
 constexpr unsigned short NO_TABLE = 0xFFFFu;
+constexpr int HUD_TOP = 86;                // (int)(H - 4 * (H / 40.0)) = (int)86.4: first row of the black HUD bar
 
 __constant__ float c_hull_poly[4][8][2] = {
     {{-60, +130}, {+60, +130}, {+60, +110}, {-60, +110}},
@@ -57,8 +57,8 @@ struct FrameMap {
     float inv_det;         // 1 / (icos^2 + isin^2), for the inverse mapping used to bound sweeps
     float camx, camy;      // camera_offset (b2Vec2)
     float ts, tc;          // sin/cos of tmp.angle = -camera_angle (fp32, b2Rot)
-    double obs_scale;
 };
+__device__ __forceinline__ double car_obs_scale() { return (10 / (100 / sqrt(96.0))) * 1.8; }   // CarRacing.obs_scale, :215
 
 // road-map pixel under screen pixel (X, Y); false: outside the rotated surface / source crop (black)
 __device__ __forceinline__ bool map_pixel(const FrameMap& m, int X, int Y, int& U, int& V) {
@@ -146,12 +146,11 @@ struct RasterSmem {
     PolyMeta meta[MAX_POLY];
     uint8_t cell_list[N_CELLS][CELL_CAP];
     int cell_count[N_CELLS];
-    int cand[MAX_CAND];
     uint8_t chk_x[2 * CAR_W], chk_y[2 * CAR_H];   // is road-map column rx + i / row ry + i inside a checker square
     float car_body[CAR_MAX_PLAYERS][40];
     double hud_vals[8];
     FrameMap fm;
-    int n_cand, n_poly, pool_used, overflow;
+    int n_poly, pool_used, overflow;
 };
 
 // Register polygon (vx, vy)[n] of the frame: id, span-table rows, cell bins.  One thread per polygon.
@@ -203,7 +202,7 @@ __device__ void add_polygon(RasterSmem& S, const FrameMap& fm, const int* vx, co
 // SLOW (a cell list or the span pool overflowed): every polygon of the frame is tested, spans recomputed if needed.
 template <bool SLOW>
 __device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, unsigned int g_grass, unsigned int g_check,
-                                           int warp, int lane) {
+                                           unsigned int g_hud, int warp, int lane) {
     uint8_t* img = S.img;
     const int n_poly = min(S.n_poly, MAX_POLY);
     const int lx = lane & 7, ly = lane >> 3;
@@ -218,6 +217,8 @@ __device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, un
         const int dxb = dxa - 4 * fm.isin, dyb = dya + 4 * fm.icos;
         int Ua = -30000, Va = -30000, Ub = -30000, Vb = -30000;
         unsigned int ka = 0u, kb = 0u;      // surfaces start black
+        // the HUD bar (render_indicators_for_pygame :651, painted after the scene) covers every row from HUD_TOP down
+        if (cy >= HUD_TOP) { img[Ya * CAR_W + X] = (uint8_t)g_hud; img[Yb * CAR_W + X] = (uint8_t)g_hud; continue; }   // whole cell under the bar
         if ((unsigned)dxa <= (unsigned)lim && (unsigned)dya <= (unsigned)lim) {
             Ua = fm.rx + (dxa >> 16); Va = fm.ry + (dya >> 16);
             ka = (S.chk_x[dxa >> 16] & S.chk_y[dya >> 16]) ? g_check : g_grass;
@@ -242,30 +243,26 @@ __device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, un
                 if ((xb >= sp.x && xb <= sp.y) || (xb >= sp.z && xb <= sp.w)) kb = m.key;
             }
         }
-        img[Ya * CAR_W + X] = (uint8_t)(ka & 255u);
-        img[Yb * CAR_W + X] = (uint8_t)(kb & 255u);
+        img[Ya * CAR_W + X] = (uint8_t)((Ya >= HUD_TOP) ? g_hud : (ka & 255u));
+        img[Yb * CAR_W + X] = (uint8_t)((Yb >= HUD_TOP) ? g_hud : (kb & 255u));
     }
 }
 
+// Per-frame setup, one warp per (env, player) frame: camera and the integer screen -> road-map mapping (lane 0), then
+// the cull of the road tiles against the visible window (all lanes).  Kept out of the render kernel, where these
+// serial steps would stall a whole CTA.
 __global__ void __launch_bounds__(RASTER_THREADS)
-car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* __restrict__ term_obs) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
-    const int frame = blockIdx.x;                     // env * players + player
-    const int e = frame / p.players, pi = frame % p.players;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+car_frame_setup_kernel(CarDev p, int only_done) {
+    __shared__ FrameMap s_fm[RASTER_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int frame = blockIdx.x * RASTER_WARPS + warp;            // env * players + player
+    if (frame >= p.n * p.players) return;
+    const int e = frame / p.players;
     if (only_done && !p.env_done[e]) return;
     const CarHullConst* K = p.consts;
-    const uint8_t* G = K->gray;
-    const int* checker = K->checker;
-
-    if (tid < p.players * 40) S.car_body[tid / 40][tid % 40] = p.body[((size_t)e * p.players + tid / 40) * 40 + tid % 40];
-    if (tid < (2 * CAR_W + 2 * CAR_H) / 4) reinterpret_cast<uint32_t*>(S.chk_x)[tid] = 0u;     // chk_x and chk_y are adjacent
-    if (tid >= 96 && tid < 96 + N_CELLS) S.cell_count[tid - 96] = 0;
-    __syncthreads();
-    if (tid == 0) {
+    if (lane == 0) {
         // ---- camera_update("rgb_array"): hull.position + R(angle) * (0, 16) ----
-        const float* b = S.car_body[pi];
+        const float* b = p.body + (size_t)frame * 40;
         float hs, hc;
         sincosf(b[2], &hs, &hc);
         const float hx = b[0] - (hc * K->hull_lcx - hs * K->hull_lcy), hy = b[1] - (hs * K->hull_lcx + hc * K->hull_lcy);
@@ -276,11 +273,11 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
         float fs, fc;
         sincosf(fa, &fs, &fc);
         FrameMap m;
-        m.obs_scale = (10 / (100 / sqrt(96.0))) * 1.8;
+        const double obs_scale = car_obs_scale();
         m.camx = hx + (fc * 0.0f - fs * 16.0f);
         m.camy = hy + (fs * 0.0f + fc * 16.0f);
         // ---- camera_view: crop rectangle, rotation, blit ----
-        const double pos0 = m.obs_scale * -(double)m.camx + 5000.0, pos1 = m.obs_scale * -(double)m.camy + 5000.0;
+        const double pos0 = obs_scale * -(double)m.camx + 5000.0, pos1 = obs_scale * -(double)m.camy + 5000.0;
         m.rx = (int)(pos0 - CAR_W); m.ry = (int)(pos1 - CAR_H);
         const int sw = 2 * CAR_W, sh = 2 * CAR_H;
         const double rad = (57.295779513 * angle) * .01745329251994329;
@@ -299,58 +296,87 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
         m.inv_det = 1.0f / ((float)m.icos * (float)m.icos + (float)m.isin * (float)m.isin);
         const float ta = (float)(-angle);
         sincosf(ta, &m.ts, &m.tc);
-        S.fm = m;
-        S.n_cand = 0; S.n_poly = 0; S.pool_used = 0; S.overflow = 0;
-        // HUD inputs (render_indicators_for_pygame :645-670)
-        const double* wd = p.wheel + ((size_t)e * p.players + pi) * 8;
-        S.hud_vals[0] = sqrt(vx * vx + vy * vy);
-        for (int k = 0; k < 4; ++k) S.hud_vals[1 + k] = wd[k];
-        S.hud_vals[5] = (double)(b[8 + 2] - b[2]);     // wheels[0].joint.angle
-        S.hud_vals[6] = (double)b[5];                   // hull.angularVelocity
-        S.hud_vals[7] = p.reward[2 * ((size_t)e * p.players + pi)];
+        s_fm[warp] = m;
+        p.frame_map[frame] = m;
     }
-    __syncthreads();
-    const FrameMap fm = S.fm;
+    __syncwarp();
+    const FrameMap fm = s_fm[warp];
+    // ---- cull: road tiles whose centre, mapped to the screen, lies within the window grown by the tile's reach
+    //      (farthest kerb corner 8.7 units = 15.4 px, plus the slack of the integer pipeline) ----
+    const int n_track = p.n_track[e];
+    const CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
+    uint16_t* cand = p.frame_cand + (size_t)frame * CAR_MAX_CAND;
+    const double obs_scale = car_obs_scale();
+    const float reach = 20.0f;
+    int base = 0;
+    for (int t0 = 0; t0 < n_track; t0 += 32) {
+        const int t = t0 + lane;
+        bool in = false;
+        if (t < n_track) {
+            const float u = (float)(obs_scale * -(double)tiles[t].cx + 5000.0), v = (float)(obs_scale * -(double)tiles[t].cy + 5000.0);
+            float X, Y;
+            map_to_screen(fm, u, v, X, Y);
+            in = X > -reach && X < CAR_W + reach && Y > -reach && Y < CAR_H + reach;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, in);
+        const int pos = base + __popc(m & ((1u << lane) - 1u));
+        if (in && pos < CAR_MAX_CAND) cand[pos] = (uint16_t)t;
+        base += __popc(m);
+    }
+    if (lane == 0) {
+        p.frame_ncand[frame] = min(base, CAR_MAX_CAND);
+        if (base > CAR_MAX_CAND) atomicAdd(p.overrun + 1, 1);   // tiles dropped: crl_car_check reports it
+    }
+}
+
+__global__ void __launch_bounds__(RASTER_THREADS)
+car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* __restrict__ term_obs) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
+    const int frame = blockIdx.x;                     // env * players + player
+    const int e = frame / p.players, pi = frame % p.players;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (only_done && !p.env_done[e]) return;
+    const CarHullConst* K = p.consts;
+    const uint8_t* G = K->gray;
+    const int* checker = K->checker;
+    const FrameMap fm = p.frame_map[frame];           // written by car_frame_setup_kernel
+    const double obs_scale = car_obs_scale();
     const int n_track = p.n_track[e];
     const CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
 
+    if (tid < p.players * 40) S.car_body[tid / 40][tid % 40] = p.body[((size_t)e * p.players + tid / 40) * 40 + tid % 40];
+    if (tid < (2 * CAR_W + 2 * CAR_H) / 4) reinterpret_cast<uint32_t*>(S.chk_x)[tid] = 0u;     // chk_x and chk_y are adjacent
+    if (tid >= 96 && tid < 96 + N_CELLS) S.cell_count[tid - 96] = 0;
+    if (tid == 255) { S.n_poly = 0; S.pool_used = 0; S.overflow = 0; }
+    if (tid >= 240 && tid < 248) {      // HUD inputs (render_indicators_for_pygame :645-670)
+        const int k = tid - 240;
+        const float* b = p.body + (size_t)frame * 40;
+        const double* wd = p.wheel + (size_t)frame * 8;
+        double v;
+        if (k == 0) { const double vx = (double)b[3], vy = (double)b[4]; v = sqrt(vx * vx + vy * vy); }
+        else if (k <= 4) v = wd[k - 1];
+        else if (k == 5) v = (double)(b[8 + 2] - b[2]);     // wheels[0].joint.angle
+        else if (k == 6) v = (double)b[5];                  // hull.angularVelocity
+        else v = p.reward[2 * (size_t)frame];
+        S.hud_vals[k] = v;
+    }
+    __syncthreads();
     // ---- checker squares (:733-746) are axis-aligned in the road map: mark the crop columns / rows that lie in one
     //      (20 squares per axis, each ~29 px wide; the tables were cleared above) ----
-    if (tid >= 64 && tid < 64 + 40) {
-        const int q = tid - 64, is_y = q >= 20;
+    if (tid >= 192 && tid < 192 + 40) {
+        const int q = tid - 192, is_y = q >= 20;
         const int lo = checker[2 * q], hi = checker[2 * q + 1], base = is_y ? fm.ry : fm.rx;
         uint8_t* tab = is_y ? S.chk_y : S.chk_x;
         for (int v = max(lo - base, 0); v <= min(hi - base, 2 * CAR_W - 1); ++v) tab[v] = 1;
     }
-    // ---- cull: road tiles whose centre, mapped to the screen, lies within the window grown by the tile's reach
-    //      (farthest kerb corner 8.7 units = 15.4 px, plus the slack of the integer pipeline); ordered by index ----
-    if (warp == 0) {
-        const float reach = 20.0f;
-        int base = 0;
-        for (int t0 = 0; t0 < n_track; t0 += 32) {
-            const int t = t0 + lane;
-            bool in = false;
-            if (t < n_track) {
-                const float u = (float)(fm.obs_scale * -(double)tiles[t].cx + 5000.0), v = (float)(fm.obs_scale * -(double)tiles[t].cy + 5000.0);
-                float X, Y;
-                map_to_screen(fm, u, v, X, Y);
-                in = X > -reach && X < CAR_W + reach && Y > -reach && Y < CAR_H + reach;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, in);
-            const int pos = base + __popc(m & ((1u << lane) - 1u));
-            if (in && pos < MAX_CAND) S.cand[pos] = t;
-            base += __popc(m);
-        }
-        if (lane == 0) { S.n_cand = min(base, MAX_CAND); if (base > MAX_CAND) atomicAdd(p.overrun + 1, 1); }   // tiles dropped: crl_car_check reports it
-    }
-    __syncthreads();
     // ---- polygons of the frame, one thread each.  Road: paint order is tile n-1 .. 0, each followed by its kerb
     //      (:399-445).  Cars (Car.draw_for_pygame): for k in cars: wheels, then hull fixtures; b2Vec2 fp32 arithmetic:
     //      path = -scale * (tmp * ((trans * v) - offset)) + (W/2, H/2), truncated to int by pygame.  Higher key wins. ----
     {
-        const int nc = S.n_cand, per_car = 8;   // 4 wheels + 4 hull fixtures
+        const int nc = p.frame_ncand[frame], per_car = 8;   // 4 wheels + 4 hull fixtures
         if (tid < nc) {
-            const int t = S.cand[tid];
+            const int t = p.frame_cand[(size_t)frame * CAR_MAX_CAND + tid];
             const CarTile T = tiles[t];
             const unsigned int order = 2u * (unsigned)(n_track - 1 - t) + 1u;
             int vx[8], vy[8];
@@ -385,8 +411,8 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
                     const float wx = (bc * lx - bs * ly) + px, wy = (bs * lx + bc * ly) + py;
                     const float ox = wx - fm.camx, oy = wy - fm.camy;
                     const float rx2 = (fm.tc * ox - fm.ts * oy) + 0.0f, ry2 = (fm.ts * ox + fm.tc * oy) + 0.0f;
-                    const float sxp = (float)((double)rx2 * -fm.obs_scale) + (float)(CAR_W / 2.0);
-                    const float syp = (float)((double)ry2 * -fm.obs_scale) + (float)(CAR_H / 2.0);
+                    const float sxp = (float)((double)rx2 * -obs_scale) + (float)(CAR_W / 2.0);
+                    const float syp = (float)((double)ry2 * -obs_scale) + (float)(CAR_H / 2.0);
                     vx[i] = (int)sxp; vy[i] = (int)syp;
                 }
             }
@@ -409,28 +435,34 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
     __syncthreads();
     // ---- pixels ----
     uint8_t* img = S.img;
-    if (S.overflow == 0) walk_cells<false>(S, fm, G[G_GRASS], G[G_CHECK], warp, lane);
-    else walk_cells<true>(S, fm, G[G_GRASS], G[G_CHECK], warp, lane);
+    if (S.overflow == 0) walk_cells<false>(S, fm, G[G_GRASS], G[G_CHECK], G[G_HUD], warp, lane);
+    else walk_cells<true>(S, fm, G[G_GRASS], G[G_CHECK], G[G_HUD], warp, lane);
     __syncthreads();
-    // ---- HUD (painted after the scene): the black bar by the whole CTA, the small indicators and the text, which
-    //      overlap and are painted in order, by warp 0 ----
-    {
+    // ---- HUD indicators and text (painted after the scene, in order, on top of the black bar that the pixel pass already
+    //      laid down) by warp 0, while the other warps copy the older frames of the stack ----
+    // FrameStack: the new frame enters the ring; the observation is the ring oldest -> newest.  After a reset
+    // (only_done pass, or the very first render) every slot holds the reset frame.
+    // output layout: [env][players * C][96][96]: player-major channel blocks (FlattenMultiAgentObservation
+    // concatenates the players' stacks on the channel axis), oldest frame first within a player
+    const int C = p.c;
+    uint8_t* ring = p.ring + (size_t)frame * C * CAR_PIX;
+    const bool fill_all = only_done != 0 || p.ring_pos[e] < 0;
+    const int newest = fill_all ? C - 1 : (p.ring_pos[e] + 1) % C;
+    uint8_t* out = obs + (size_t)frame * C * CAR_PIX;
+    uint8_t* tout = (term_obs != nullptr && !only_done && p.env_done[e]) ? term_obs + (size_t)frame * C * CAR_PIX : nullptr;
+    if (warp == 0) {
         const double W = CAR_W, H = CAR_H, s = W / 40.0, h = H / 40.0;
-        hud_rect(img, 0, H - 4 * h, W, 4 * h * 1000, G[G_HUD], tid, RASTER_THREADS);
-        __syncthreads();
-        if (warp == 0) {
-            hud_rect(img, 5 * s, H - h, s, h * (-0.02 * S.hud_vals[0]), G[G_BLUE], lane, 32);
-            __syncwarp();
-            for (int k = 0; k < 4; ++k) {
-                hud_rect(img, (7 + k) * s, H - h, s, h * (-0.01 * S.hud_vals[1 + k]), k < 2 ? G[G_BLUE] : G[G_BLUE2], lane, 32);
-                __syncwarp();
-            }
-            hud_rect(img, 20 * s, H - 2 * h, s * (10.0 * S.hud_vals[5]), 2 * h, G[G_GREEN], lane, 32);
-            __syncwarp();
-            hud_rect(img, 30 * s, H - 2 * h, s * (0.8 * S.hud_vals[6]), 2 * h, G[G_RED], lane, 32);
+        hud_rect(img, 5 * s, H - h, s, h * (-0.02 * S.hud_vals[0]), G[G_BLUE], lane, 32);
+        __syncwarp();
+        for (int k = 0; k < 4; ++k) {
+            hud_rect(img, (7 + k) * s, H - h, s, h * (-0.01 * S.hud_vals[1 + k]), k < 2 ? G[G_BLUE] : G[G_BLUE2], lane, 32);
             __syncwarp();
         }
-        if (tid == 0 && p.glyphs != nullptr) {     // draw_text("%05.0f" % reward) at (W/100, H - H/20)
+        hud_rect(img, 20 * s, H - 2 * h, s * (10.0 * S.hud_vals[5]), 2 * h, G[G_GREEN], lane, 32);
+        __syncwarp();
+        hud_rect(img, 30 * s, H - 2 * h, s * (0.8 * S.hud_vals[6]), 2 * h, G[G_RED], lane, 32);
+        __syncwarp();
+        if (p.glyphs != nullptr) {     // draw_text("%05.0f" % reward) at (W/100, H - H/20): lane = one pixel of the 4x8 glyph cell
             // "%05.0f": round half to even, sign kept for negative values, zero padded to width 5
             const double rv = S.hud_vals[7];
             double mag = rint(fabs(rv));
@@ -443,50 +475,48 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
             int pen = (int)(W / 100);
             const int y0 = (int)(H - H / 20);
             const int pad = 5 > body ? 5 - body : 0;
+            const int gx = lane & 3, gy = lane >> 2;
             for (int i = 0; i < body + pad; ++i) {
                 int gi;
                 if (neg && i == 0) gi = 10;
                 else if (i < neg + pad) gi = 0;
                 else gi = digits[nd - 1 - (i - neg - pad)];
-                for (int gy = 0; gy < 8; ++gy)
-                    for (int gx = 0; gx < 4; ++gx)
-                        if (p.glyphs[(gi * 8 + gy) * 4 + gx]) {
-                            const int px = pen + gx, py = y0 + gy;
-                            if (px >= 0 && px < CAR_W && py >= 0 && py < CAR_H) img[py * CAR_W + px] = G[G_TEXT];
-                        }
+                if (p.glyphs[(gi * 8 + gy) * 4 + gx]) {
+                    const int px = pen + gx, py = y0 + gy;
+                    if (px >= 0 && px < CAR_W && py >= 0 && py < CAR_H) img[py * CAR_W + px] = G[G_TEXT];
+                }
                 pen += p.glyphs[11 * 8 * 4 + gi];
+                __syncwarp();
             }
         }
-        __syncthreads();
+    } else if (!fill_all) {
+        for (int sl = 0; sl < C - 1; ++sl) {                      // the C - 1 older frames, oldest first
+            const int rs = (newest + 1 + sl) % C;
+            const uint4* rsrc = reinterpret_cast<const uint4*>(ring + (size_t)rs * CAR_PIX);
+            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)sl * CAR_PIX);
+            uint4* tdst = tout ? reinterpret_cast<uint4*>(tout + (size_t)sl * CAR_PIX) : nullptr;
+            for (int q = tid - 32; q < CAR_PIX / 16; q += RASTER_THREADS - 32) {
+                const uint4 vv = rsrc[q];
+                dst[q] = vv;
+                if (tdst) tdst[q] = vv;
+            }
+        }
     }
-    // ---- FrameStack: the new frame enters the ring; the observation is the ring oldest -> newest.
-    //      After a reset (only_done pass, or the very first render) every slot holds the reset frame. ----
-    const int C = p.c;
-    uint8_t* ring = p.ring + ((size_t)e * p.players + pi) * C * CAR_PIX;
-    const bool fill_all = only_done != 0 || p.ring_pos[e] < 0;
-    const int newest = fill_all ? C - 1 : (p.ring_pos[e] + 1) % C;
+    __syncthreads();
     const uint4* src = reinterpret_cast<const uint4*>(img);
     if (fill_all) {
         for (int sl = 0; sl < C; ++sl) {
-            uint4* dst = reinterpret_cast<uint4*>(ring + (size_t)sl * CAR_PIX);
-            for (int q = tid; q < CAR_PIX / 16; q += RASTER_THREADS) dst[q] = src[q];
+            uint4* rdst = reinterpret_cast<uint4*>(ring + (size_t)sl * CAR_PIX);
+            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)sl * CAR_PIX);
+            for (int q = tid; q < CAR_PIX / 16; q += RASTER_THREADS) { const uint4 vv = src[q]; rdst[q] = vv; dst[q] = vv; }
         }
     } else {
-        uint4* dst = reinterpret_cast<uint4*>(ring + (size_t)newest * CAR_PIX);
-        for (int q = tid; q < CAR_PIX / 16; q += RASTER_THREADS) dst[q] = src[q];
-    }
-    __syncthreads();
-    // output layout: [env][players * C][96][96]: player-major channel blocks (FlattenMultiAgentObservation
-    // concatenates the players' stacks on the channel axis), oldest frame first within a player
-    uint8_t* out = obs + ((size_t)e * p.players + pi) * C * CAR_PIX;
-    uint8_t* tout = (term_obs != nullptr && !only_done && p.env_done[e]) ? term_obs + ((size_t)e * p.players + pi) * C * CAR_PIX : nullptr;
-    for (int sl = 0; sl < C; ++sl) {
-        const int rs = fill_all ? sl : (newest + 1 + sl) % C;     // oldest first
-        const uint4* rsrc = (rs == newest || fill_all) ? src : reinterpret_cast<const uint4*>(ring + (size_t)rs * CAR_PIX);
-        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)sl * CAR_PIX);
-        uint4* tdst = tout ? reinterpret_cast<uint4*>(tout + (size_t)sl * CAR_PIX) : nullptr;
+        uint4* rdst = reinterpret_cast<uint4*>(ring + (size_t)newest * CAR_PIX);
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(C - 1) * CAR_PIX);
+        uint4* tdst = tout ? reinterpret_cast<uint4*>(tout + (size_t)(C - 1) * CAR_PIX) : nullptr;
         for (int q = tid; q < CAR_PIX / 16; q += RASTER_THREADS) {
-            const uint4 vv = rsrc[q];
+            const uint4 vv = src[q];
+            rdst[q] = vv;
             dst[q] = vv;
             if (tdst) tdst[q] = vv;
         }
@@ -516,13 +546,18 @@ void car_checker_table(int* out /* [2][20][2] */) {
         }
 }
 
+size_t car_frame_map_bytes() { return sizeof(FrameMap); }
+
 cudaError_t car_raster_init() {
     return cudaFuncSetAttribute(car_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterSmem));
 }
 
 cudaError_t launch_car_render(const CarDev& p, int only_done, uint8_t* obs, uint8_t* term_obs, cudaStream_t s) {
-    car_render_kernel<<<p.n * p.players, RASTER_THREADS, sizeof(RasterSmem), s>>>(p, only_done, obs, term_obs);
+    car_frame_setup_kernel<<<(p.n * p.players + RASTER_WARPS - 1) / RASTER_WARPS, RASTER_THREADS, 0, s>>>(p, only_done);
     cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    car_render_kernel<<<p.n * p.players, RASTER_THREADS, sizeof(RasterSmem), s>>>(p, only_done, obs, term_obs);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     car_ring_advance_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p, only_done);
     return cudaGetLastError();

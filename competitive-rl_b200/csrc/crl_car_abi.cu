@@ -236,6 +236,12 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     ALLOC(d.counters, nc * 4); ALLOC(d.touching, nc * 64); ALLOC(d.visited, nc * 16);
     ALLOC(d.ring, nc * d.c * CAR_PIX); ALLOC(d.overrun, 4); ALLOC(d.stats, 8);
     ALLOC(d.contact_overflow, 1);
+    {
+        uint8_t* fmraw = nullptr;
+        ALLOC(fmraw, nc * car_frame_map_bytes());
+        d.frame_map = reinterpret_cast<FrameMap*>(fmraw);
+    }
+    ALLOC(d.frame_cand, nc * CAR_MAX_CAND); ALLOC(d.frame_ncand, nc);
     if (P == 2) { ALLOC(d.contacts, n * CAR_MAX_CONTACTS); ALLOC(d.n_contacts, n); }
     CarHullConst* kdev = nullptr;
     ALLOC(kdev, 1);
@@ -303,7 +309,7 @@ int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream) {
     CUDA_TRY(cudaMemsetAsync(h->dev.ring_pos, 0xFF, (size_t)h->dev.n * sizeof(int32_t), s));
     CUDA_TRY(cudaMemsetAsync(h->dev.env_done, 0, (size_t)h->dev.n, s));
     LAUNCH(launch_car_reset(h->dev, 0, s), 1);
-    LAUNCH(launch_car_render(h->dev, 0, obs_dev, nullptr, s), 2);
+    LAUNCH(launch_car_render(h->dev, 0, obs_dev, nullptr, s), 3);
     h->was_reset = true;
     return CRL_OK;
 }
@@ -322,9 +328,9 @@ int crl_car_render_obs(crl_car* h, uint8_t* obs_dev, uint8_t* term_obs_dev, void
     if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
     if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
     cudaStream_t s = (cudaStream_t)stream;
-    LAUNCH(launch_car_render(h->dev, 0, obs_dev, term_obs_dev, s), 2);   // post-step frame (terminal obs of finished envs)
+    LAUNCH(launch_car_render(h->dev, 0, obs_dev, term_obs_dev, s), 3);   // post-step frame (terminal obs of finished envs)
     LAUNCH(launch_car_reset(h->dev, 1, s), 1);                           // auto-reset of finished envs
-    LAUNCH(launch_car_render(h->dev, 1, obs_dev, nullptr, s), 2);        // their reset observation
+    LAUNCH(launch_car_render(h->dev, 1, obs_dev, nullptr, s), 3);        // their reset observation
     return CRL_OK;
 }
 
