@@ -117,7 +117,7 @@ struct CarDev {
     const int32_t* birth;        // [n][k_birth][players] or nullptr
     int k_birth;
     int32_t* overrun;            // [0] device flag: an injection table ran out; [1] frames whose rasteriser dropped polygons;
-                                 // [2] frames rasterised on the exact slow path (a cell list overflowed)
+                                 // [2] frames rasterised on the exact slow path (span pool full)
     // ---- constants ----
     const CarHullConst* consts;
     const uint8_t* glyphs;       // [CAR_GLYPH_BYTES]

@@ -311,7 +311,7 @@ __device__ __noinline__ void car_contacts_init(const CarHullConst* K, CarContact
 
 // b2ContactSolver::SolveVelocityConstraints over all contacts of the env (one velocity iteration)
 __device__ __noinline__ void car_contacts_solve_velocity(const CarHullConst* K, CarContact* recs, int n, float (*vel)[3]) {
-    const float friction = sqrtf(0.2f * 0.2f);   // b2MixFriction of two default fixtures
+    const float friction = 0.2f;   // b2MixFriction of two default fixtures: sqrtf(0.2f * 0.2f) == 0.2f in fp32
     for (int k = 0; k < n; ++k) {
         CarContact& c = recs[k];
         const int ia = c.ia, ib = c.ib;

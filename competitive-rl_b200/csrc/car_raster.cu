@@ -34,9 +34,9 @@ namespace crl {
 constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 constexpr int MAX_POLY = 232;              // tiles + kerbs + 16 car polygons of one frame (ids fit a byte)
-constexpr int POOL_ROWS = 2304;            // scanline span table shared by all polygons of a frame
+constexpr int POOL_ROWS = 2048;            // scanline span table shared by all polygons of a frame
 constexpr int CELL = 8, CELLS_X = CAR_W / CELL, N_CELLS = CELLS_X * (CAR_H / CELL);
-constexpr int CELL_CAP = 40;               // polygons binned to one 8x8 screen cell (more: exact slow path)
+constexpr int MASK_WORDS = (MAX_POLY + 31) / 32;   // per-cell bitmask over the polygon ids
 constexpr unsigned short NO_TABLE = 0xFFFFu;
 constexpr int HUD_TOP = 86;                // (int)(H - 4 * (H / 40.0)) = (int)86.4: first row of the black HUD bar
 
@@ -144,8 +144,7 @@ struct RasterSmem {
     uint8_t row_owner[POOL_ROWS];
     short pvx[MAX_POLY][8], pvy[MAX_POLY][8];
     PolyMeta meta[MAX_POLY];
-    uint8_t cell_list[N_CELLS][CELL_CAP];
-    int cell_count[N_CELLS];
+    uint32_t cell_mask[N_CELLS][MASK_WORDS];      // polygons whose screen bounding box touches the cell
     uint8_t chk_x[2 * CAR_W], chk_y[2 * CAR_H];   // is road-map column rx + i / row ry + i inside a checker square
     float car_body[CAR_MAX_PLAYERS][40];
     double hud_vals[8];
@@ -189,22 +188,19 @@ __device__ void add_polygon(RasterSmem& S, const FrameMap& fm, const int* vx, co
     S.meta[id] = m;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { S.pvx[id][i] = (short)max(-32000, min(32000, vx[i])); S.pvy[id][i] = (short)max(-32000, min(32000, vy[i])); }
-    for (int cy = Y0 / CELL; cy <= Y1 / CELL; ++cy)
-        for (int cx = X0 / CELL; cx <= X1 / CELL; ++cx) {
-            const int slot = atomicAdd(&S.cell_count[cy * CELLS_X + cx], 1);
-            if (slot < CELL_CAP) S.cell_list[cy * CELLS_X + cx][slot] = (uint8_t)id;
-            else S.overflow = 1;                            // that frame walks all polygons per pixel instead
-        }
+    const uint32_t bit = 1u << (id & 31);
+    for (int cy = Y0 / CELL; cy <= min(Y1, HUD_TOP - 1) / CELL; ++cy)      // rows under the HUD bar are never walked
+        for (int cx = X0 / CELL; cx <= X1 / CELL; ++cx) atomicOr(&S.cell_mask[cy * CELLS_X + cx][id >> 5], bit);
 }
 
 // Pixels of the frame: a warp walks one 8x8 cell at a time, lane = (x, y) and (x, y + 4).  Background: black outside
 // the source crop, else grass / checker by road-map pixel; then the polygons binned to the cell, largest key wins.
-// SLOW (a cell list or the span pool overflowed): every polygon of the frame is tested, spans recomputed if needed.
+// SLOW (the span pool overflowed): polygons without a table get their spans recomputed per pixel.
 template <bool SLOW>
 __device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, unsigned int g_grass, unsigned int g_check,
                                            unsigned int g_hud, int warp, int lane) {
     uint8_t* img = S.img;
-    const int n_poly = min(S.n_poly, MAX_POLY);
+    const int n_words = (min(S.n_poly, MAX_POLY) + 31) >> 5;
     const int lx = lane & 7, ly = lane >> 3;
     // dx = cx0 + icos * x - isin * y, dy = cy0 + isin * x + icos * y with (x, y) = (X - bx, Y - by): affine in the lane
     const int ldx = fm.cx0 + fm.icos * (lx - fm.bx) - fm.isin * (ly - fm.by);
@@ -227,20 +223,23 @@ __device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, un
             Ub = fm.rx + (dxb >> 16); Vb = fm.ry + (dyb >> 16);
             kb = (S.chk_x[dxb >> 16] & S.chk_y[dyb >> 16]) ? g_check : g_grass;
         }
-        const int cnt = SLOW ? n_poly : min(S.cell_count[cell], CELL_CAP);
-        for (int k = 0; k < cnt; ++k) {
-            const int id = SLOW ? k : S.cell_list[cell][k];
-            const PolyMeta m = S.meta[id];
-            if (m.key < ka && m.key < kb) continue;
-            const int xa = m.screen ? X : Ua, ya = m.screen ? Ya : Va, xb = m.screen ? X : Ub, yb = m.screen ? Yb : Vb;
-            const int ra = ya - m.miny, rb = yb - m.miny;
-            if ((unsigned)ra < (unsigned)m.rows && m.key > ka) {
-                const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + ra] : scanline_spans(S.pvx[id], S.pvy[id], m.n, ya, m.miny + m.rows - 1);
-                if ((xa >= sp.x && xa <= sp.y) || (xa >= sp.z && xa <= sp.w)) ka = m.key;
-            }
-            if ((unsigned)rb < (unsigned)m.rows && m.key > kb) {
-                const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + rb] : scanline_spans(S.pvx[id], S.pvy[id], m.n, yb, m.miny + m.rows - 1);
-                if ((xb >= sp.x && xb <= sp.y) || (xb >= sp.z && xb <= sp.w)) kb = m.key;
+        for (int w = 0; w < n_words; ++w) {
+            unsigned int bits = S.cell_mask[cell][w];
+            while (bits) {
+                const int id = w * 32 + __ffs(bits) - 1;
+                bits &= bits - 1u;
+                const PolyMeta m = S.meta[id];
+                if (m.key < ka && m.key < kb) continue;
+                const int xa = m.screen ? X : Ua, ya = m.screen ? Ya : Va, xb = m.screen ? X : Ub, yb = m.screen ? Yb : Vb;
+                const int ra = ya - m.miny, rb = yb - m.miny;
+                if ((unsigned)ra < (unsigned)m.rows && m.key > ka) {
+                    const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + ra] : scanline_spans(S.pvx[id], S.pvy[id], m.n, ya, m.miny + m.rows - 1);
+                    if ((xa >= sp.x && xa <= sp.y) || (xa >= sp.z && xa <= sp.w)) ka = m.key;
+                }
+                if ((unsigned)rb < (unsigned)m.rows && m.key > kb) {
+                    const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + rb] : scanline_spans(S.pvx[id], S.pvy[id], m.n, yb, m.miny + m.rows - 1);
+                    if ((xb >= sp.x && xb <= sp.y) || (xb >= sp.z && xb <= sp.w)) kb = m.key;
+                }
             }
         }
         img[Ya * CAR_W + X] = (uint8_t)((Ya >= HUD_TOP) ? g_hud : (ka & 255u));
@@ -329,7 +328,7 @@ car_frame_setup_kernel(CarDev p, int only_done) {
     }
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS)
+__global__ void __launch_bounds__(RASTER_THREADS, 5)
 car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* __restrict__ term_obs) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
@@ -347,7 +346,7 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
 
     if (tid < p.players * 40) S.car_body[tid / 40][tid % 40] = p.body[((size_t)e * p.players + tid / 40) * 40 + tid % 40];
     if (tid < (2 * CAR_W + 2 * CAR_H) / 4) reinterpret_cast<uint32_t*>(S.chk_x)[tid] = 0u;     // chk_x and chk_y are adjacent
-    if (tid >= 96 && tid < 96 + N_CELLS) S.cell_count[tid - 96] = 0;
+    for (int i = tid; i < N_CELLS * MASK_WORDS; i += RASTER_THREADS) (&S.cell_mask[0][0])[i] = 0u;
     if (tid == 255) { S.n_poly = 0; S.pool_used = 0; S.overflow = 0; }
     if (tid >= 240 && tid < 248) {      // HUD inputs (render_indicators_for_pygame :645-670)
         const int k = tid - 240;
@@ -421,7 +420,7 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
         }
     }
     __syncthreads();
-    if (tid == 0 && S.overflow != 0) atomicAdd(p.overrun + (S.overflow == 2 ? 1 : 2), 1);   // [1] polygons dropped, [2] frames on the slow path
+    if (tid == 0 && S.overflow != 0) atomicAdd(p.overrun + (S.overflow == 2 ? 1 : 2), 1);   // [1] polygons dropped, [2] frames with a full span pool (slow path)
     // ---- span tables: one (polygon, row) per thread and pass ----
     {
         const int total = min(S.pool_used, POOL_ROWS);
