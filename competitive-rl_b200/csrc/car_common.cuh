@@ -41,9 +41,9 @@ struct CarTile {
     int16_t kmx[4], kmy[4];   // kerb quad in road-map pixels
 };
 
-// One touching fixture pair between the two cars of an env (b2Contact + its solver constraints), 144 bytes.
+// One touching fixture pair between the two cars of an env (b2Contact + its solver constraints), 160 bytes.
 // The manifold part and the accumulated impulses persist between steps (warm start); the rest is per-step scratch.
-struct CarContact {
+struct __align__(16) CarContact {
     uint8_t pair, count, type, vcount;   // canonical pair index (0..47), manifold points, 0 = e_faceA / 1 = e_faceB, solver points
     uint8_t ia, ib, pad0, pad1;          // bodies: 0..4 = car 0 (hull, wheels 0..3), 5..9 = car 1
     uint32_t id[2];                      // b2ContactFeature keys

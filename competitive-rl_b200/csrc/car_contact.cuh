@@ -309,35 +309,54 @@ __device__ __noinline__ void car_contacts_init(const CarHullConst* K, CarContact
     }
 }
 
+// A contact record by value: ten 16-byte loads issued back to back.  (Field-by-field access through the pointer makes
+// every load wait for the previous store: the compiler cannot rule out that `vel` / `pose` alias the record.)
+__device__ __forceinline__ CarContact load_contact(const CarContact* src) {
+    static_assert(sizeof(CarContact) == 160, "CarContact is ten uint4");
+    CarContact c;
+    uint4* d = reinterpret_cast<uint4*>(&c);
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) d[i] = s4[i];
+    return c;
+}
+
+// one friction (tangent) constraint of point J
+template <int J>
+__device__ __forceinline__ void contact_tangent(CarContact& c, F2 tangent, float friction, float mA, float iA, float mB, float iB,
+                                                F2& vA, float& wA, F2& vB, float& wB) {
+    const F2 rA = f2(c.rAx[J], c.rAy[J]), rB = f2(c.rBx[J], c.rBy[J]);
+    const F2 dv = ((vB + cross_sv(wB, rB)) - vA) - cross_sv(wA, rA);
+    const float vt = dot(dv, tangent) - 0.0f;
+    float lambda = c.tmass[J] * (-vt);
+    const float max_friction = friction * c.ni[J];
+    const float new_impulse = clampf(c.ti[J] + lambda, -max_friction, max_friction);
+    lambda = new_impulse - c.ti[J];
+    c.ti[J] = new_impulse;
+    const F2 P = lambda * tangent;
+    vA = vA - mA * P;
+    wA -= iA * cross(rA, P);
+    vB = vB + mB * P;
+    wB += iB * cross(rB, P);
+}
+
 // b2ContactSolver::SolveVelocityConstraints over all contacts of the env (one velocity iteration)
 __device__ __noinline__ void car_contacts_solve_velocity(const CarHullConst* K, CarContact* recs, int n, float (*vel)[3]) {
     const float friction = 0.2f;   // b2MixFriction of two default fixtures: sqrtf(0.2f * 0.2f) == 0.2f in fp32
+    const float mH = K->hull_inv_mass, iH = K->hull_inv_I, mW = K->wheel_inv_mass, iW = K->wheel_inv_I;
     for (int k = 0; k < n; ++k) {
-        CarContact& c = recs[k];
+        CarContact c = load_contact(recs + k);
         const int ia = c.ia, ib = c.ib;
-        const float mA = body_inv_mass(K, ia), iA = body_inv_I(K, ia), mB = body_inv_mass(K, ib), iB = body_inv_I(K, ib);
+        const float mA = (ia == 0) ? mH : mW, iA = (ia == 0) ? iH : iW, mB = (ib == 5) ? mH : mW, iB = (ib == 5) ? iH : iW;
         F2 vA = f2(vel[ia][0], vel[ia][1]), vB = f2(vel[ib][0], vel[ib][1]);
         float wA = vel[ia][2], wB = vel[ib][2];
         const F2 normal = f2(c.nx, c.ny), tangent = cross_vs(normal, 1.0f);
         const int vcount = c.vcount;
-        F2 rA[2], rB[2];
-        for (int j = 0; j < 2; ++j) { rA[j] = f2(c.rAx[j], c.rAy[j]); rB[j] = f2(c.rBx[j], c.rBy[j]); }
-        for (int j = 0; j < vcount; ++j) {
-            const F2 dv = ((vB + cross_sv(wB, rB[j])) - vA) - cross_sv(wA, rA[j]);
-            const float vt = dot(dv, tangent) - 0.0f;
-            float lambda = c.tmass[j] * (-vt);
-            const float max_friction = friction * c.ni[j];
-            const float new_impulse = clampf(c.ti[j] + lambda, -max_friction, max_friction);
-            lambda = new_impulse - c.ti[j];
-            c.ti[j] = new_impulse;
-            const F2 P = lambda * tangent;
-            vA = vA - mA * P;
-            wA -= iA * cross(rA[j], P);
-            vB = vB + mB * P;
-            wB += iB * cross(rB[j], P);
-        }
+        contact_tangent<0>(c, tangent, friction, mA, iA, mB, iB, vA, wA, vB, wB);
+        if (vcount == 2) contact_tangent<1>(c, tangent, friction, mA, iA, mB, iB, vA, wA, vB, wB);
+        const F2 rA0 = f2(c.rAx[0], c.rAy[0]), rB0 = f2(c.rBx[0], c.rBy[0]);
         if (vcount == 1) {
-            const F2 dv = ((vB + cross_sv(wB, rB[0])) - vA) - cross_sv(wA, rA[0]);
+            const F2 dv = ((vB + cross_sv(wB, rB0)) - vA) - cross_sv(wA, rA0);
             const float vn = dot(dv, normal);
             float lambda = -c.nmass[0] * (vn - 0.0f);
             float new_impulse = c.ni[0] + lambda;
@@ -346,13 +365,14 @@ __device__ __noinline__ void car_contacts_solve_velocity(const CarHullConst* K, 
             c.ni[0] = new_impulse;
             const F2 P = lambda * normal;
             vA = vA - mA * P;
-            wA -= iA * cross(rA[0], P);
+            wA -= iA * cross(rA0, P);
             vB = vB + mB * P;
-            wB += iB * cross(rB[0], P);
+            wB += iB * cross(rB0, P);
         } else {
+            const F2 rA1 = f2(c.rAx[1], c.rAy[1]), rB1 = f2(c.rBx[1], c.rBy[1]);
             const F2 a = f2(c.ni[0], c.ni[1]);
-            const F2 dv1 = ((vB + cross_sv(wB, rB[0])) - vA) - cross_sv(wA, rA[0]);
-            const F2 dv2 = ((vB + cross_sv(wB, rB[1])) - vA) - cross_sv(wA, rA[1]);
+            const F2 dv1 = ((vB + cross_sv(wB, rB0)) - vA) - cross_sv(wA, rA0);
+            const F2 dv2 = ((vB + cross_sv(wB, rB1)) - vA) - cross_sv(wA, rA1);
             float vn1 = dot(dv1, normal), vn2 = dot(dv2, normal);
             F2 b = f2(vn1 - 0.0f, vn2 - 0.0f);
             b = b - f2(c.k11 * a.x + c.k12 * a.y, c.k12 * a.x + c.k22 * a.y);
@@ -376,56 +396,62 @@ __device__ __noinline__ void car_contacts_solve_velocity(const CarHullConst* K, 
                 const F2 d = x - a;
                 const F2 P1 = d.x * normal, P2 = d.y * normal;
                 vA = vA - mA * (P1 + P2);
-                wA -= iA * (cross(rA[0], P1) + cross(rA[1], P2));
+                wA -= iA * (cross(rA0, P1) + cross(rA1, P2));
                 vB = vB + mB * (P1 + P2);
-                wB += iB * (cross(rB[0], P1) + cross(rB[1], P2));
+                wB += iB * (cross(rB0, P1) + cross(rB1, P2));
                 c.ni[0] = x.x; c.ni[1] = x.y;
             }
         }
         vel[ia][0] = vA.x; vel[ia][1] = vA.y; vel[ia][2] = wA;
         vel[ib][0] = vB.x; vel[ib][1] = vB.y; vel[ib][2] = wB;
+        *reinterpret_cast<float4*>(recs[k].ni) = make_float4(c.ni[0], c.ni[1], c.ti[0], c.ti[1]);   // ni[2], ti[2] are adjacent
     }
 }
 
 // b2ContactSolver::SolvePositionConstraints over all contacts; true when minSeparation >= -3 * linearSlop
 __device__ __noinline__ bool car_contacts_solve_position(const CarHullConst* K, const CarContact* recs, int n, float (*pose)[3]) {
     float min_sep = 0.0f;
+    const float mH = K->hull_inv_mass, iH = K->hull_inv_I, mW = K->wheel_inv_mass, iW = K->wheel_inv_I;
+    const F2 lcH = f2(K->hull_lcx, K->hull_lcy);
     for (int k = 0; k < n; ++k) {
-        const CarContact& c = recs[k];
+        const CarContact c = load_contact(recs + k);
         const int ia = c.ia, ib = c.ib;
-        const float mA = body_inv_mass(K, ia), iA = body_inv_I(K, ia), mB = body_inv_mass(K, ib), iB = body_inv_I(K, ib);
-        const F2 lcA = body_lc(K, ia), lcB = body_lc(K, ib);
+        const float mA = (ia == 0) ? mH : mW, iA = (ia == 0) ? iH : iW, mB = (ib == 5) ? mH : mW, iB = (ib == 5) ? iH : iW;
+        const F2 lcA = (ia == 0) ? lcH : f2(0.f, 0.f), lcB = (ib == 5) ? lcH : f2(0.f, 0.f);
         F2 cA = f2(pose[ia][0], pose[ia][1]), cB = f2(pose[ib][0], pose[ib][1]);
         float aA = pose[ia][2], aB = pose[ib][2];
-        for (int j = 0; j < c.count; ++j) {
-            const Xf xfa = xf_of(cA, aA, lcA), xfb = xf_of(cB, aB, lcB);
-            F2 normal, point;
-            float separation;
-            if (c.type == 0) {
-                normal = rmul(xfa.q, f2(c.lnx, c.lny));
-                const F2 plane = xf_mul(xfa, f2(c.lpx, c.lpy));
-                const F2 clip = xf_mul(xfb, f2(c.px[j], c.py[j]));
-                separation = dot(clip - plane, normal) - B2_POLYGON_RADIUS - B2_POLYGON_RADIUS;
-                point = clip;
-            } else {
-                normal = rmul(xfb.q, f2(c.lnx, c.lny));
-                const F2 plane = xf_mul(xfb, f2(c.lpx, c.lpy));
-                const F2 clip = xf_mul(xfa, f2(c.px[j], c.py[j]));
-                separation = dot(clip - plane, normal) - B2_POLYGON_RADIUS - B2_POLYGON_RADIUS;
-                point = clip;
-                normal = neg(normal);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (j < c.count) {
+                const Xf xfa = xf_of(cA, aA, lcA), xfb = xf_of(cB, aB, lcB);
+                F2 normal, point;
+                float separation;
+                if (c.type == 0) {
+                    normal = rmul(xfa.q, f2(c.lnx, c.lny));
+                    const F2 plane = xf_mul(xfa, f2(c.lpx, c.lpy));
+                    const F2 clip = xf_mul(xfb, f2(c.px[j], c.py[j]));
+                    separation = dot(clip - plane, normal) - B2_POLYGON_RADIUS - B2_POLYGON_RADIUS;
+                    point = clip;
+                } else {
+                    normal = rmul(xfb.q, f2(c.lnx, c.lny));
+                    const F2 plane = xf_mul(xfb, f2(c.lpx, c.lpy));
+                    const F2 clip = xf_mul(xfa, f2(c.px[j], c.py[j]));
+                    separation = dot(clip - plane, normal) - B2_POLYGON_RADIUS - B2_POLYGON_RADIUS;
+                    point = clip;
+                    normal = neg(normal);
+                }
+                const F2 rA = point - cA, rB = point - cB;
+                if (separation < min_sep) min_sep = separation;
+                const float C = clampf(B2_BAUMGARTE * (separation + B2_LINEAR_SLOP), -B2_MAX_LINEAR_CORRECTION, 0.0f);
+                const float rnA = cross(rA, normal), rnB = cross(rB, normal);
+                const float Km = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
+                const float impulse = Km > 0.0f ? -C / Km : 0.0f;
+                const F2 P = impulse * normal;
+                cA = cA - mA * P;
+                aA -= iA * cross(rA, P);
+                cB = cB + mB * P;
+                aB += iB * cross(rB, P);
             }
-            const F2 rA = point - cA, rB = point - cB;
-            if (separation < min_sep) min_sep = separation;
-            const float C = clampf(B2_BAUMGARTE * (separation + B2_LINEAR_SLOP), -B2_MAX_LINEAR_CORRECTION, 0.0f);
-            const float rnA = cross(rA, normal), rnB = cross(rB, normal);
-            const float Km = mA + mB + iA * rnA * rnA + iB * rnB * rnB;
-            const float impulse = Km > 0.0f ? -C / Km : 0.0f;
-            const F2 P = impulse * normal;
-            cA = cA - mA * P;
-            aA -= iA * cross(rA, P);
-            cB = cB + mB * P;
-            aB += iB * cross(rB, P);
         }
         pose[ia][0] = cA.x; pose[ia][1] = cA.y; pose[ia][2] = aA;
         pose[ib][0] = cB.x; pose[ib][1] = cB.y; pose[ib][2] = aB;

@@ -383,6 +383,7 @@ car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__
     const int ci = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_cars = p.n * p.players;
     const bool active = ci < n_cars;
+    const unsigned warp_lanes = __ballot_sync(0xffffffffu, active);   // the lanes that run the per-car pipeline
     const int e = active ? ci / p.players : 0, player = active ? ci % p.players : 0;
     bool car_done = false;
     double step_reward = 0.0;
@@ -614,6 +615,9 @@ car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__
             //      order wheel 3, 2, 1, 0 -- the island order b2World::Solve's DFS produces) ----
             bool any_awake = awake[0] || awake[1] || awake[2] || awake[3] || awake[4];
             if (merged) any_awake = any_awake || __shfl_xor_sync(pair_mask, (int)any_awake, 1) != 0;
+            // The lanes arrive here diverged (different numbers of candidate tiles, contact events, gate outcomes); left
+            // alone, each group would run the 180-iteration solver loops on its own.  Reconverge the warp first.
+            __syncwarp(warp_lanes);
             if (any_awake) {
                 for (int i = 0; i < 5; ++i)
                     if (!awake[i]) { awake[i] = true; sleep_t[i] = 0.f; }
