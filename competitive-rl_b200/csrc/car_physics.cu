@@ -533,31 +533,59 @@ car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__
                         }
                     }
                 }
+                // wheel boxes in world coordinates
+                float wx[4][4], wy[4][4];
                 for (int k = 0; k < 4; ++k) {
                     const int bi = k + 1;
                     const Rot q = make_rot(a[bi]);
                     const float hw = (float)(CR_WHEEL_W * CR_SIZE), hr = (float)(CR_WHEEL_R * CR_SIZE);
-                    float wx[4], wy[4];
+                    const F2 l0 = rmul(q, f2(-hw, -hr)) + c[bi], l1 = rmul(q, f2(+hw, -hr)) + c[bi];
+                    const F2 l2 = rmul(q, f2(+hw, +hr)) + c[bi], l3 = rmul(q, f2(-hw, +hr)) + c[bi];
+                    wx[k][0] = l0.x; wy[k][0] = l0.y; wx[k][1] = l1.x; wy[k][1] = l1.y;
+                    wx[k][2] = l2.x; wy[k][2] = l2.y; wx[k][3] = l3.x; wy[k][3] = l3.y;
+                }
+                // overlap tests, tile-major: each candidate tile is fetched once and tested against the four wheels
+                uint32_t now[4][16];
+                for (int k = 0; k < 4; ++k)
+                    for (int wd = 0; wd < 16; ++wd) now[k][wd] = 0u;
+                for (int q2 = 0; q2 < n_cand; ++q2) {
+                    const int t = cand[q2];
+                    const CarTile* Tp = tiles + t;
+                    const float tcx = Tp->cx, tcy = Tp->cy;
+                    bool near_w[4], any_near = false;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float ddx = tcx - c[k + 1].x, ddy = tcy - c[k + 1].y;
+                        near_w[k] = ddx * ddx + ddy * ddy <= 9.0f * 9.0f;
+                        any_near = any_near || near_w[k];
+                    }
+                    if (!any_near) continue;
+                    float tpx[5], tpy[5];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) { tpx[i] = Tp->px[i]; tpy[i] = Tp->py[i]; }
+                    const int tn = Tp->n;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (!near_w[k]) continue;
+                        const float s1 = max_separation(wx[k], wy[k], 4, tpx, tpy, tn);
+                        const float s2 = max_separation(tpx, tpy, tn, wx[k], wy[k], 4);
+                        if (fmaxf(s1, s2) < 2.0f * B2_POLYGON_RADIUS) now[k][t >> 5] |= 1u << (t & 31);
+                    }
+                }
+                // contact events wheel by wheel (FrictionDetector._contact), BeginContact in ascending block id
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t was_w[16];
                     {
-                        const F2 l0 = rmul(q, f2(-hw, -hr)) + c[bi], l1 = rmul(q, f2(+hw, -hr)) + c[bi];
-                        const F2 l2 = rmul(q, f2(+hw, +hr)) + c[bi], l3 = rmul(q, f2(-hw, +hr)) + c[bi];
-                        wx[0] = l0.x; wy[0] = l0.y; wx[1] = l1.x; wy[1] = l1.y; wx[2] = l2.x; wy[2] = l2.y; wx[3] = l3.x; wy[3] = l3.y;
+                        const uint4* tw = reinterpret_cast<const uint4*>(touching + 16 * k);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { const uint4 q4 = tw[i]; was_w[4 * i] = q4.x; was_w[4 * i + 1] = q4.y; was_w[4 * i + 2] = q4.z; was_w[4 * i + 3] = q4.w; }
                     }
-                    uint32_t now[16];
-                    for (int wd = 0; wd < 16; ++wd) now[wd] = 0u;
-                    for (int q2 = 0; q2 < n_cand; ++q2) {
-                        const int t = cand[q2];
-                        const CarTile T = tiles[t];
-                        const float ddx = T.cx - c[bi].x, ddy = T.cy - c[bi].y;
-                        if (ddx * ddx + ddy * ddy > 9.0f * 9.0f) continue;
-                        const float s1 = max_separation(wx, wy, 4, T.px, T.py, T.n);
-                        const float s2 = max_separation(T.px, T.py, T.n, wx, wy, 4);
-                        if (fmaxf(s1, s2) < 2.0f * B2_POLYGON_RADIUS) now[t >> 5] |= 1u << (t & 31);
-                    }
+#pragma unroll
                     for (int wd = 0; wd < 16; ++wd) {
-                        const uint32_t was = touching[16 * k + wd];
-                        uint32_t begins = now[wd] & ~was;
-                        while (begins) {                                   // BeginContact, ascending block id
+                        const uint32_t was = was_w[wd], now_w = now[k][wd];
+                        if (now_w == was) continue;                        // nothing begins or ends in these 32 tiles
+                        uint32_t begins = now_w & ~was;
+                        while (begins) {
                             const int bit = __ffs(begins) - 1;
                             begins &= begins - 1;
                             const int t = wd * 32 + bit;
@@ -571,7 +599,7 @@ car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__
                                 tile_visited += 1;
                             }
                         }
-                        touching[16 * k + wd] = now[wd];                   // EndContact: tiles.remove
+                        touching[16 * k + wd] = now_w;                     // EndContact: tiles.remove
                     }
                 }
             }
