@@ -33,10 +33,12 @@ namespace crl {
 
 constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
-constexpr int MAX_POLY = 232;              // tiles + kerbs + 16 car polygons of one frame (ids fit a byte)
+constexpr int MAX_POLY = 240;              // 224 road polygons (tiles + kerbs) + 16 car fixtures of one frame (ids fit a byte)
 constexpr int POOL_ROWS = 2048;            // scanline span table shared by all polygons of a frame
 constexpr int CELL = 8, CELLS_X = CAR_W / CELL, N_CELLS = CELLS_X * (CAR_H / CELL);
 constexpr int MASK_WORDS = (MAX_POLY + 31) / 32;   // per-cell bitmask over the polygon ids
+constexpr int CAR_WORD = MASK_WORDS - 1;   // ids CAR_WORD * 32 .. are the car fixtures (screen space); below: road (map space)
+constexpr int MAX_ROAD_POLY = CAR_WORD * 32;
 constexpr unsigned short NO_TABLE = 0xFFFFu;
 constexpr int HUD_TOP = 86;                // (int)(H - 4 * (H / 40.0)) = (int)86.4: first row of the black HUD bar
 
@@ -153,7 +155,8 @@ struct RasterSmem {
 };
 
 // Register polygon (vx, vy)[n] of the frame: id, span-table rows, cell bins.  One thread per polygon.
-__device__ void add_polygon(RasterSmem& S, const FrameMap& fm, const int* vx, const int* vy, int n, unsigned int key, bool screen) {
+__device__ void add_polygon(RasterSmem& S, const FrameMap& fm, const int* vx, const int* vy, int n, unsigned int key, bool screen,
+                            int car_slot) {
     int minx = vx[0], maxx = vx[0], miny = vy[0], maxy = vy[0];
 #pragma unroll
     for (int i = 1; i < 8; ++i)
@@ -178,8 +181,8 @@ __device__ void add_polygon(RasterSmem& S, const FrameMap& fm, const int* vx, co
         X0 = max(0, minx); X1 = min(CAR_W - 1, maxx); Y0 = max(0, miny); Y1 = min(CAR_H - 1, maxy);
     }
     if (X1 < X0 || Y1 < Y0 || rows <= 0) return;          // cannot touch the window
-    const int id = atomicAdd(&S.n_poly, 1);
-    if (id >= MAX_POLY) { S.overflow = 2; return; }       // polygon dropped (reported through crl_car_check)
+    const int id = screen ? MAX_ROAD_POLY + car_slot : atomicAdd(&S.n_poly, 1);
+    if (!screen && id >= MAX_ROAD_POLY) { S.overflow = 2; return; }       // polygon dropped (reported through crl_car_check)
     int off = atomicAdd(&S.pool_used, rows);
     if (off + rows > POOL_ROWS) { off = NO_TABLE; S.overflow = 1; }
     else for (int r = 0; r < rows; ++r) S.row_owner[off + r] = (uint8_t)id;
@@ -196,54 +199,69 @@ __device__ void add_polygon(RasterSmem& S, const FrameMap& fm, const int* vx, co
 // Pixels of the frame: a warp walks one 8x8 cell at a time, lane = (x, y) and (x, y + 4).  Background: black outside
 // the source crop, else grass / checker by road-map pixel; then the polygons binned to the cell, largest key wins.
 // SLOW (the span pool overflowed): polygons without a table get their spans recomputed per pixel.
+// one polygon against the two pixels of a lane; (xa, ya) / (xb, yb) in the polygon's coordinate system
+template <bool SLOW>
+__device__ __forceinline__ void test_polygon(const RasterSmem& S, int id, int xa, int ya, int xb, int yb, unsigned int& ka,
+                                             unsigned int& kb) {
+    const PolyMeta m = S.meta[id];
+    if (m.key < ka && m.key < kb) return;
+    const int ra = ya - m.miny, rb = yb - m.miny;
+    if ((unsigned)ra < (unsigned)m.rows && m.key > ka) {
+        const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + ra] : scanline_spans(S.pvx[id], S.pvy[id], m.n, ya, m.miny + m.rows - 1);
+        if ((xa >= sp.x && xa <= sp.y) || (xa >= sp.z && xa <= sp.w)) ka = m.key;
+    }
+    if ((unsigned)rb < (unsigned)m.rows && m.key > kb) {
+        const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + rb] : scanline_spans(S.pvx[id], S.pvy[id], m.n, yb, m.miny + m.rows - 1);
+        if ((xb >= sp.x && xb <= sp.y) || (xb >= sp.z && xb <= sp.w)) kb = m.key;
+    }
+}
+
 template <bool SLOW>
 __device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, unsigned int g_grass, unsigned int g_check,
                                            unsigned int g_hud, int warp, int lane) {
     uint8_t* img = S.img;
-    const int n_words = (min(S.n_poly, MAX_POLY) + 31) >> 5;
+    const int n_words = (min(S.n_poly, MAX_ROAD_POLY) + 31) >> 5;
     const int lx = lane & 7, ly = lane >> 3;
-    // dx = cx0 + icos * x - isin * y, dy = cy0 + isin * x + icos * y with (x, y) = (X - bx, Y - by): affine in the lane
+    // dx = cx0 + icos * x - isin * y, dy = cy0 + isin * x + icos * y with (x, y) = (X - bx, Y - by): affine in the lane and
+    // in the cell.  No bounds test: the 96x96 window is the centre of the rotated 192x192 crop, whose inscribed circle
+    // (radius 96) contains it (half diagonal 68), so every screen pixel samples inside the crop.
     const int ldx = fm.cx0 + fm.icos * (lx - fm.bx) - fm.isin * (ly - fm.by);
     const int ldy = fm.cy0 + fm.isin * (lx - fm.bx) + fm.icos * (ly - fm.by);
-    const int lim = (2 * CAR_W << 16) - 1;
-    for (int cell = warp; cell < N_CELLS; cell += RASTER_WARPS) {
-        const int cx = (cell % CELLS_X) * CELL, cy = (cell / CELLS_X) * CELL;
+    // cells warp, warp + 8, ...: 12 cells per row of cells, so +8 cells = +64 px in x, wrapping into the next row
+    int cx = warp * CELL, cy = 0;
+    for (int cell = warp; cell < N_CELLS; cell += RASTER_WARPS, cx += RASTER_WARPS * CELL) {
+        if (cx >= CAR_W) { cx -= CAR_W; cy += CELL; }
         const int X = cx + lx, Ya = cy + ly, Yb = Ya + 4;
+        uint8_t* pa = img + Ya * CAR_W + X;
+        if (cy >= HUD_TOP) { pa[0] = (uint8_t)g_hud; pa[4 * CAR_W] = (uint8_t)g_hud; continue; }   // whole cell under the HUD bar
         const int dxa = ldx + fm.icos * cx - fm.isin * cy, dya = ldy + fm.isin * cx + fm.icos * cy;
         const int dxb = dxa - 4 * fm.isin, dyb = dya + 4 * fm.icos;
-        int Ua = -30000, Va = -30000, Ub = -30000, Vb = -30000;
-        unsigned int ka = 0u, kb = 0u;      // surfaces start black
-        // the HUD bar (render_indicators_for_pygame :651, painted after the scene) covers every row from HUD_TOP down
-        if (cy >= HUD_TOP) { img[Ya * CAR_W + X] = (uint8_t)g_hud; img[Yb * CAR_W + X] = (uint8_t)g_hud; continue; }   // whole cell under the bar
-        if ((unsigned)dxa <= (unsigned)lim && (unsigned)dya <= (unsigned)lim) {
-            Ua = fm.rx + (dxa >> 16); Va = fm.ry + (dya >> 16);
-            ka = (S.chk_x[dxa >> 16] & S.chk_y[dya >> 16]) ? g_check : g_grass;
-        }
-        if ((unsigned)dxb <= (unsigned)lim && (unsigned)dyb <= (unsigned)lim) {
-            Ub = fm.rx + (dxb >> 16); Vb = fm.ry + (dyb >> 16);
-            kb = (S.chk_x[dxb >> 16] & S.chk_y[dyb >> 16]) ? g_check : g_grass;
-        }
-        for (int w = 0; w < n_words; ++w) {
+        const int ua = (dxa >> 16) & 255, va = (dya >> 16) & 255, ub = (dxb >> 16) & 255, vb = (dyb >> 16) & 255;   // 0..191 (see above)
+        const int Ua = fm.rx + ua, Va = fm.ry + va, Ub = fm.rx + ub, Vb = fm.ry + vb;
+        unsigned int ka = (S.chk_x[ua] & S.chk_y[va]) ? g_check : g_grass;
+        unsigned int kb = (S.chk_x[ub] & S.chk_y[vb]) ? g_check : g_grass;
+        for (int w = 0; w < n_words; ++w) {                 // road tiles and kerbs: road-map coordinates
             unsigned int bits = S.cell_mask[cell][w];
             while (bits) {
                 const int id = w * 32 + __ffs(bits) - 1;
                 bits &= bits - 1u;
-                const PolyMeta m = S.meta[id];
-                if (m.key < ka && m.key < kb) continue;
-                const int xa = m.screen ? X : Ua, ya = m.screen ? Ya : Va, xb = m.screen ? X : Ub, yb = m.screen ? Yb : Vb;
-                const int ra = ya - m.miny, rb = yb - m.miny;
-                if ((unsigned)ra < (unsigned)m.rows && m.key > ka) {
-                    const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + ra] : scanline_spans(S.pvx[id], S.pvy[id], m.n, ya, m.miny + m.rows - 1);
-                    if ((xa >= sp.x && xa <= sp.y) || (xa >= sp.z && xa <= sp.w)) ka = m.key;
-                }
-                if ((unsigned)rb < (unsigned)m.rows && m.key > kb) {
-                    const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + rb] : scanline_spans(S.pvx[id], S.pvy[id], m.n, yb, m.miny + m.rows - 1);
-                    if ((xb >= sp.x && xb <= sp.y) || (xb >= sp.z && xb <= sp.w)) kb = m.key;
-                }
+                test_polygon<SLOW>(S, id, Ua, Va, Ub, Vb, ka, kb);
             }
         }
-        img[Ya * CAR_W + X] = (uint8_t)((Ya >= HUD_TOP) ? g_hud : (ka & 255u));
-        img[Yb * CAR_W + X] = (uint8_t)((Yb >= HUD_TOP) ? g_hud : (kb & 255u));
+        {                                                   // car fixtures: screen coordinates
+            unsigned int bits = S.cell_mask[cell][CAR_WORD];
+            while (bits) {
+                const int id = CAR_WORD * 32 + __ffs(bits) - 1;
+                bits &= bits - 1u;
+                test_polygon<SLOW>(S, id, X, Ya, X, Yb, ka, kb);
+            }
+        }
+        if (cy + CELL > HUD_TOP) {                          // the row of cells the HUD bar starts in
+            if (Ya >= HUD_TOP) ka = g_hud;
+            if (Yb >= HUD_TOP) kb = g_hud;
+        }
+        pa[0] = (uint8_t)(ka & 255u);
+        pa[4 * CAR_W] = (uint8_t)(kb & 255u);
     }
 }
 
@@ -381,11 +399,11 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
             int vx[8], vy[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { vx[i] = (i < 5) ? T.mx[i] : 0; vy[i] = (i < 5) ? T.my[i] : 0; }
-            add_polygon(S, fm, vx, vy, 5, (order << 8) | G[G_ROAD0 + t % 3], false);
+            add_polygon(S, fm, vx, vy, 5, (order << 8) | G[G_ROAD0 + t % 3], false, 0);
             if (T.flags & 2) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { vx[i] = T.kmx[i]; vy[i] = T.kmy[i]; }
-                add_polygon(S, fm, vx, vy, 4, ((order + 1u) << 8) | ((T.flags & 4) ? G[G_KERB_W] : G[G_KERB_R]), false);
+                add_polygon(S, fm, vx, vy, 4, ((order + 1u) << 8) | ((T.flags & 4) ? G[G_KERB_W] : G[G_KERB_R]), false, 0);
             }
         } else if (tid >= RASTER_THREADS - p.players * per_car) {
             const int q = RASTER_THREADS - 1 - tid;
@@ -416,7 +434,7 @@ car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* _
                 }
             }
             const uint8_t g = (part < 4) ? G[G_WHEEL] : ((ck == pi) ? G[G_OWN] : G[G_OTHER]);
-            add_polygon(S, fm, vx, vy, n, (order << 8) | g, true);
+            add_polygon(S, fm, vx, vy, n, (order << 8) | g, true, q);
         }
     }
     __syncthreads();
