@@ -287,8 +287,9 @@ def run_ours(a):
                      "avg_launch_ms": raster_ms, "bytes_per_launch": BYTES_PER_ENV_STEP * N},
         "e2e": {"value": total_envs * K2 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h * world,
-                "note": "crl_pong_step_host: pinned host actions in, rew/done/num_steps/real_reward out; "
-                        "observations stay in HBM (the API returns device tensors)"},
+                "note": "crl_pong_step_host: pinned host actions in, rew/done/num_steps/real_reward out (copied on a "
+                        "side stream behind the rasteriser, joined before the call returns); observations stay in "
+                        "HBM (the API returns device tensors)"},
         "e2e_host_obs": {"value": total_envs * K3 / e2e_obs_s, "unit": UNIT,
                          "d2h_bytes_per_step": (d2h + 2 * obs0.numel()) * world,
                          "note": "same call with both observation stacks copied to pinned host memory (PCIe-bound)"},

@@ -64,6 +64,9 @@ struct crl_pong {
     float* real_stage = nullptr;
     bool atlas_loaded = false;
     bool was_reset = false;
+    // crl_pong_step_host: the small results go back to the host on a side stream while the rasteriser runs
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_state = nullptr, ev_copied = nullptr;
 };
 
 // OpenCV computeResizeAreaTab: scale and cell in double, alpha stored as float.
@@ -134,6 +137,9 @@ int crl_pong_destroy(crl_pong* h) {
     if (!h) return CRL_OK;
     cudaSetDevice(h->cfg.device);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->ev_state) cudaEventDestroy(h->ev_state);
+    if (h->ev_copied) cudaEventDestroy(h->ev_copied);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
     return CRL_OK;
 }
@@ -348,16 +354,28 @@ int crl_pong_step_host(crl_pong* h, const int32_t* actions_host, uint8_t* obs0_d
     cudaStream_t s = (cudaStream_t)stream;
     const size_t n = (size_t)h->dev.n;
     const size_t aw = h->dev.n_agents == 2 ? 2 : 1;
+    if (!h->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_state, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copied, cudaEventDisableTiming));
+    }
     CUDA_TRY(cudaMemcpyAsync(h->actions_stage, actions_host, n * aw * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    if (int r = crl_pong_step(h, h->actions_stage, obs0_dev, obs1_dev, h->rew_stage, h->done_stage, h->steps_stage,
-                              h->real_stage, stream))
+    if (int r = crl_pong_step_state(h, h->actions_stage, h->rew_stage, h->done_stage, h->steps_stage, h->real_stage, stream))
         return r;
-    CUDA_TRY(cudaMemcpyAsync(rew_host, h->rew_stage, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(done_host, h->done_stage, n, cudaMemcpyDeviceToHost, s));
+    // rewards / dones / counters are final once the game-core kernel has run: copy them out on the side stream,
+    // behind the rasteriser (which is the whole cost of the step)
+    CUDA_TRY(cudaEventRecord(h->ev_state, s));
+    CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_state, 0));
+    cudaStream_t cs = h->copy_stream;
+    CUDA_TRY(cudaMemcpyAsync(rew_host, h->rew_stage, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaMemcpyAsync(done_host, h->done_stage, n, cudaMemcpyDeviceToHost, cs));
     if (num_steps_host)
-        CUDA_TRY(cudaMemcpyAsync(num_steps_host, h->steps_stage, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(num_steps_host, h->steps_stage, n * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
     if (real_reward_host)
-        CUDA_TRY(cudaMemcpyAsync(real_reward_host, h->real_stage, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(real_reward_host, h->real_stage, n * 2 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaEventRecord(h->ev_copied, cs));
+    if (int r = crl_pong_render_obs(h, obs0_dev, obs1_dev, stream)) return r;
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_copied, 0));
     const size_t ob = n * h->dev.c * h->dev.dim * h->dev.dim;
     if (obs0_host) CUDA_TRY(cudaMemcpyAsync(obs0_host, obs0_dev, ob, cudaMemcpyDeviceToHost, s));
     if (obs1_host && h->dev.n_agents == 2) CUDA_TRY(cudaMemcpyAsync(obs1_host, obs1_dev, ob, cudaMemcpyDeviceToHost, s));

@@ -112,6 +112,8 @@ int crl_pong_terminal_obs(crl_pong* h, const uint8_t* done_dev, uint8_t* term0_d
 /* Host-buffer form of step (what a numpy caller of the reference's VecEnv.step sees):
  * copies actions host->device, steps, copies rew/done/num_steps/real_reward back and,
  * when obs*_host are non-NULL, the observations too.  Synchronises the stream.
+ * The small results leave on an internal side stream as soon as the game-core kernel has
+ * produced them, i.e. behind the rasteriser; the side stream is joined before the call returns.
  * Host buffers should be pinned for full PCIe bandwidth.  obs*_dev are still required
  * (device staging owned by the caller). */
 int crl_pong_step_host(crl_pong* h, const int32_t* actions_host, uint8_t* obs0_dev, uint8_t* obs1_dev,

@@ -97,3 +97,42 @@ def test_tournament_wrapper_and_framestack_tensor():
         stacked = fst.update(o, mask=1.0 - d.float())
     assert tuple(stacked.shape) == (N, 4, 42, 42) and torch.equal(stacked[:, -1], o[:, 0].float())
     t.close()
+
+
+def test_step_host_matches_device_step():
+    """crl_pong_step_host (pinned host actions in, rewards / dones / counters out on a side stream behind the
+    rasteriser, optional host copies of the observations) against the device-pointer call on a twin env."""
+    from competitive_rl_b200 import _native, make_envs
+    lib = _native.load()
+    N, T = 512, 150
+    kw = dict(seed=11, log_dir=None, num_envs=N, resized_dim=84, frame_stack=4, n_buffers=1)
+    ea, eb = make_envs("cPongDouble-v0", **kw), make_envs("cPongDouble-v0", **kw)
+    ea.reset(); eb.reset()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    h_act = torch.zeros((N, 2), dtype=torch.int32).pin_memory()
+    h_rew = torch.zeros((N, 2), dtype=torch.float32).pin_memory()
+    h_done = torch.zeros((N,), dtype=torch.uint8).pin_memory()
+    h_steps = torch.zeros((N,), dtype=torch.int32).pin_memory()
+    h_real = torch.zeros((N, 2), dtype=torch.float32).pin_memory()
+    h_o0 = torch.zeros((N, 4, 84, 84), dtype=torch.uint8).pin_memory()
+    h_o1 = torch.zeros((N, 4, 84, 84), dtype=torch.uint8).pin_memory()
+    o0, o1 = eb._obs
+    sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rng = np.random.default_rng(3)
+    dones = 0
+    for t in range(T):
+        a = rng.integers(0, 3, (N, 2)).astype(np.int32)
+        a[rng.random((N, 2)) < 0.2] = 999
+        obs, rew, done, info = ea.step(torch.from_numpy(a).cuda())
+        h_act.copy_(torch.from_numpy(a))
+        with_obs = t % 25 == 0
+        _native.check(lib.crl_pong_step_host(eb._h, p(h_act), p(o0), p(o1), p(h_o0) if with_obs else None,
+                                             p(h_o1) if with_obs else None, p(h_rew), p(h_done), p(h_steps), p(h_real), sp))
+        # the call returns with every host buffer filled: no further synchronisation here
+        assert np.array_equal(h_rew.numpy(), rew.cpu().numpy()) and np.array_equal(h_done.numpy() != 0, done.cpu().numpy().astype(bool).reshape(N, -1)[:, 0])
+        assert np.array_equal(h_steps.numpy(), info.num_steps.cpu().numpy()) and np.array_equal(h_real.numpy(), info.real_reward.cpu().numpy())
+        assert torch.equal(o0, obs[0]) and torch.equal(o1, obs[1])
+        if with_obs:
+            assert torch.equal(h_o0, obs[0].cpu()) and torch.equal(h_o1, obs[1].cpu())
+        dones += int(h_done.sum())
+    ea.close(); eb.close()
