@@ -105,6 +105,10 @@ struct CarDev {
     CarContact* contacts;
     int32_t* n_contacts;
     int32_t* contact_overflow;
+    // two-pass stepping of two-car envs (car_step_kernel modes 1 / 2): envs whose cars are near each other
+    int32_t* slow_list;       // [n]
+    int32_t* slow_count;      // [1]
+    uint8_t* deferred;        // [n] 1 = on the slow list this step
     // ---- per frame (env * players + player): written by car_frame_setup_kernel, read by car_render_kernel ----
     FrameMap* frame_map;      // [n*players]
     uint16_t* frame_cand;     // [n*players][CAR_MAX_CAND] road tiles that can reach the window
@@ -125,9 +129,10 @@ struct CarDev {
 };
 
 cudaError_t launch_car_reset(const CarDev& p, int only_done, cudaStream_t s);
-cudaError_t launch_car_step(const CarDev& p, const float* actions, float* rew, uint8_t* done, int32_t* num_steps,
+cudaError_t launch_car_step(const CarDev& p, int mode, const float* actions, float* rew, uint8_t* done, int32_t* num_steps,
                             uint8_t* truncated, cudaStream_t s);
-cudaError_t launch_car_render(const CarDev& p, int only_done, uint8_t* obs, uint8_t* term_obs, cudaStream_t s);
+// which: 0 = every frame, 1 = envs not deferred to the slow stepping pass, 2 = deferred envs only; advance: move the frame ring on
+cudaError_t launch_car_render(const CarDev& p, int only_done, int which, int advance, uint8_t* obs, uint8_t* term_obs, cudaStream_t s);
 cudaError_t car_raster_init();
 size_t car_frame_map_bytes();
 void car_checker_table(int* out);

@@ -377,13 +377,39 @@ __device__ float max_separation(const float* ax, const float* ay, int na, const 
     return best;
 }
 
+// Can any fixture pair of the two cars be within contact reach?  The cars as oriented boxes in their hull frames (hull
+// polygons span x +-1.2, y -2.4..2.6; wheels reach x +-1.71 at any steering angle; 0.3 of slack for skins and joint
+// error): separated boxes, no contact.  pose[0] / pose[5] = (cx, cy, angle) of the two hulls.  Right after a reset the
+// wheels are not yet where the joints want them (Car.__init__ places them un-rotated, car_dynamics.py:90): plain
+// distance gate for the first steps.
+__device__ __forceinline__ bool cars_near(const float (*pose)[3], float hull_lcx, float hull_lcy, int step_count) {
+    const Rot qa = make_rot(pose[0][2]), qb = make_rot(pose[5][2]);
+    const F2 pa = f2(pose[0][0], pose[0][1]) + rmul(qa, f2(-hull_lcx, 0.1f - hull_lcy));
+    const F2 pb = f2(pose[5][0], pose[5][1]) + rmul(qb, f2(-hull_lcx, 0.1f - hull_lcy));
+    const F2 t = pb - pa;
+    const float ex = 2.01f, ey = 2.8f;
+    const float cxx = fabsf(qa.c * qb.c + qa.s * qb.s), cxy = fabsf(qa.s * qb.c - qa.c * qb.s);   // |ax.bx|, |ax.by| (= |ay.bx|)
+    const float tax = fabsf(t.x * qa.c + t.y * qa.s), tay = fabsf(-t.x * qa.s + t.y * qa.c);
+    const float tbx = fabsf(t.x * qb.c + t.y * qb.s), tby = fabsf(-t.x * qb.s + t.y * qb.c);
+    const bool separated = tax > ex + ex * cxx + ey * cxy || tay > ey + ex * cxy + ey * cxx ||
+                           tbx > ex + ex * cxx + ey * cxy || tby > ey + ex * cxy + ey * cxx;
+    return (step_count < 4) ? (t.x * t.x + t.y * t.y < 8.0f * 8.0f) : !separated;
+}
+
+// mode 0: every car.  mode 1 (fast pass): two-car envs whose cars are near each other are only put on p.slow_list
+// (p.deferred[env] = 1) -- their contact solve is several times longer than a plain step and would hold up the whole
+// single-wave launch.  mode 2 (slow pass): the envs on p.slow_list, two lanes each.
 __global__ void __launch_bounds__(64)
-car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__ rew, uint8_t* __restrict__ done_out,
+car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __restrict__ rew, uint8_t* __restrict__ done_out,
                 int32_t* __restrict__ num_steps_out, uint8_t* __restrict__ truncated_out) {
-    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_cars = p.n * p.players;
-    const bool active = ci < n_cars;
-    const unsigned warp_lanes = __ballot_sync(0xffffffffu, active);   // the lanes that run the per-car pipeline
+    int ci = gtid;
+    bool active = ci < n_cars;
+    if (mode == 2) {                 // slow pass: lane pair i takes env slow_list[i]
+        active = (gtid >> 1) < *p.slow_count;
+        ci = active ? p.slow_list[gtid >> 1] * 2 + (gtid & 1) : 0;
+    }
     const int e = active ? ci / p.players : 0, player = active ? ci % p.players : 0;
     bool car_done = false;
     double step_reward = 0.0;
@@ -395,6 +421,20 @@ car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__
     const unsigned pair_mask = 3u << (threadIdx.x & 30);
     float (*pose)[3] = sh_pose[threadIdx.x >> 1];
     float (*vel)[3] = sh_vel[threadIdx.x >> 1];
+    bool deferred = false;
+    if (active && p.players == 2 && mode != 2) {
+        if (mode == 1) {
+            const float* hb = p.body + (size_t)ci * 40;
+            pose[player * 5][0] = hb[0]; pose[player * 5][1] = hb[1]; pose[player * 5][2] = hb[2];
+            __syncwarp(pair_mask);
+            deferred = cars_near(pose, p.consts->hull_lcx, p.consts->hull_lcy, p.step_count[e]);
+            if (deferred && player == 0) p.slow_list[atomicAdd(p.slow_count, 1)] = e;
+            __syncwarp(pair_mask);
+        }
+        if (player == 0) p.deferred[e] = deferred ? 1 : 0;
+    }
+    active = active && !deferred;
+    const unsigned warp_lanes = __ballot_sync(0xffffffffu, active);   // the lanes that run the per-car pipeline
     if (active) {
         const CarHullConst K = *p.consts;
         // ---- load ----
@@ -610,24 +650,7 @@ car_step_kernel(CarDev p, const float* __restrict__ actions, float* __restrict__
                 for (int i = 0; i < 5; ++i) { pose[player * 5 + i][0] = c[i].x; pose[player * 5 + i][1] = c[i].y; pose[player * 5 + i][2] = a[i]; }
                 __syncwarp(pair_mask);
                 recs = p.contacts + (size_t)e * CAR_MAX_CONTACTS;
-                // gate: the two cars as oriented boxes in their hull frames (hull polygons span x +-1.2, y -2.4..2.6; wheels
-                // reach x +-1.71 at any steering angle; 0.3 of slack for skins and joint error) -- separated boxes, no contact
-                bool near_each_other;
-                {
-                    const Rot qa = make_rot(pose[0][2]), qb = make_rot(pose[5][2]);
-                    const F2 pa = f2(pose[0][0], pose[0][1]) + rmul(qa, f2(-hull_lcx, 0.1f - hull_lcy));
-                    const F2 pb = f2(pose[5][0], pose[5][1]) + rmul(qb, f2(-hull_lcx, 0.1f - hull_lcy));
-                    const F2 t = pb - pa;
-                    const float ex = 2.01f, ey = 2.8f;
-                    const float cxx = fabsf(qa.c * qb.c + qa.s * qb.s), cxy = fabsf(qa.s * qb.c - qa.c * qb.s);   // |ax.bx|, |ax.by| (= |ay.bx|)
-                    const float tax = fabsf(t.x * qa.c + t.y * qa.s), tay = fabsf(-t.x * qa.s + t.y * qa.c);
-                    const float tbx = fabsf(t.x * qb.c + t.y * qb.s), tby = fabsf(-t.x * qb.s + t.y * qb.c);
-                    const bool separated = tax > ex + ex * cxx + ey * cxy || tay > ey + ex * cxy + ey * cxx ||
-                                           tbx > ex + ex * cxx + ey * cxy || tby > ey + ex * cxy + ey * cxx;
-                    // right after a reset the wheels are not yet where the joints want them (Car.__init__ places them
-                    // un-rotated, car_dynamics.py:90): plain distance gate for the first steps
-                    near_each_other = (step_count < 4) ? (t.x * t.x + t.y * t.y < 8.0f * 8.0f) : !separated;
-                }
+                const bool near_each_other = cars_near(pose, hull_lcx, hull_lcy, step_count);
                 if (near_each_other) {
                     if (player == 0) {
                         n_con = car_contacts_collide(p.consts, pose, recs, p.n_contacts[e], p.contact_overflow);
@@ -926,10 +949,10 @@ cudaError_t launch_car_reset(const CarDev& p, int only_done, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-cudaError_t launch_car_step(const CarDev& p, const float* actions, float* rew, uint8_t* done, int32_t* num_steps,
+cudaError_t launch_car_step(const CarDev& p, int mode, const float* actions, float* rew, uint8_t* done, int32_t* num_steps,
                             uint8_t* truncated, cudaStream_t s) {
     const int n_cars = p.n * p.players;
-    car_step_kernel<<<(n_cars + 63) / 64, 64, 0, s>>>(p, actions, rew, done, num_steps, truncated);
+    car_step_kernel<<<(n_cars + 63) / 64, 64, 0, s>>>(p, mode, actions, rew, done, num_steps, truncated);
     return cudaGetLastError();
 }
 

@@ -269,13 +269,14 @@ __device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, un
 // the cull of the road tiles against the visible window (all lanes).  Kept out of the render kernel, where these
 // serial steps would stall a whole CTA.
 __global__ void __launch_bounds__(RASTER_THREADS)
-car_frame_setup_kernel(CarDev p, int only_done) {
+car_frame_setup_kernel(CarDev p, int only_done, int which) {
     __shared__ FrameMap s_fm[RASTER_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int frame = blockIdx.x * RASTER_WARPS + warp;            // env * players + player
     if (frame >= p.n * p.players) return;
     const int e = frame / p.players;
     if (only_done && !p.env_done[e]) return;
+    if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
     const CarHullConst* K = p.consts;
     if (lane == 0) {
         // ---- camera_update("rgb_array"): hull.position + R(angle) * (0, 16) ----
@@ -347,13 +348,14 @@ car_frame_setup_kernel(CarDev p, int only_done) {
 }
 
 __global__ void __launch_bounds__(RASTER_THREADS, 5)
-car_render_kernel(CarDev p, int only_done, uint8_t* __restrict__ obs, uint8_t* __restrict__ term_obs) {
+car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs, uint8_t* __restrict__ term_obs) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
     const int frame = blockIdx.x;                     // env * players + player
     const int e = frame / p.players, pi = frame % p.players;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (only_done && !p.env_done[e]) return;
+    if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
     const CarHullConst* K = p.consts;
     const uint8_t* G = K->gray;
     const int* checker = K->checker;
@@ -569,13 +571,13 @@ cudaError_t car_raster_init() {
     return cudaFuncSetAttribute(car_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterSmem));
 }
 
-cudaError_t launch_car_render(const CarDev& p, int only_done, uint8_t* obs, uint8_t* term_obs, cudaStream_t s) {
-    car_frame_setup_kernel<<<(p.n * p.players + RASTER_WARPS - 1) / RASTER_WARPS, RASTER_THREADS, 0, s>>>(p, only_done);
+cudaError_t launch_car_render(const CarDev& p, int only_done, int which, int advance, uint8_t* obs, uint8_t* term_obs, cudaStream_t s) {
+    car_frame_setup_kernel<<<(p.n * p.players + RASTER_WARPS - 1) / RASTER_WARPS, RASTER_THREADS, 0, s>>>(p, only_done, which);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    car_render_kernel<<<p.n * p.players, RASTER_THREADS, sizeof(RasterSmem), s>>>(p, only_done, obs, term_obs);
+    car_render_kernel<<<p.n * p.players, RASTER_THREADS, sizeof(RasterSmem), s>>>(p, only_done, which, obs, term_obs);
     e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess || !advance) return e;
     car_ring_advance_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p, only_done);
     return cudaGetLastError();
 }

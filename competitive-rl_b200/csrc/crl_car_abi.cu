@@ -30,6 +30,9 @@ struct crl_car {
     crl_car_config cfg;
     CarDev dev;
     std::vector<void*> allocs;
+    // crl_car_step of two-car envs: envs whose cars touch are stepped on a side stream while the others render
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fast = nullptr, ev_slow = nullptr;
     bool was_reset = false;
 };
 
@@ -195,6 +198,9 @@ int crl_car_destroy(crl_car* h) {
     if (!h) return CRL_OK;
     cudaSetDevice(h->cfg.device);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->ev_fast) cudaEventDestroy(h->ev_fast);
+    if (h->ev_slow) cudaEventDestroy(h->ev_slow);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
     delete h;
     return CRL_OK;
 }
@@ -242,7 +248,8 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
         d.frame_map = reinterpret_cast<FrameMap*>(fmraw);
     }
     ALLOC(d.frame_cand, nc * CAR_MAX_CAND); ALLOC(d.frame_ncand, nc);
-    if (P == 2) { ALLOC(d.contacts, n * CAR_MAX_CONTACTS); ALLOC(d.n_contacts, n); }
+    if (P == 2) { ALLOC(d.contacts, n * CAR_MAX_CONTACTS); ALLOC(d.n_contacts, n); ALLOC(d.slow_list, n); ALLOC(d.slow_count, 1); }
+    ALLOC(d.deferred, n);
     CarHullConst* kdev = nullptr;
     ALLOC(kdev, 1);
 #undef ALLOC
@@ -309,7 +316,7 @@ int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream) {
     CUDA_TRY(cudaMemsetAsync(h->dev.ring_pos, 0xFF, (size_t)h->dev.n * sizeof(int32_t), s));
     CUDA_TRY(cudaMemsetAsync(h->dev.env_done, 0, (size_t)h->dev.n, s));
     LAUNCH(launch_car_reset(h->dev, 0, s), 1);
-    LAUNCH(launch_car_render(h->dev, 0, obs_dev, nullptr, s), 3);
+    LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, nullptr, s), 3);
     h->was_reset = true;
     return CRL_OK;
 }
@@ -319,7 +326,7 @@ int crl_car_step_state(crl_car* h, const float* actions_dev, float* rew_dev, uin
     CHECK_HANDLE(h);
     if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
     if (!actions_dev || !rew_dev || !done_dev || !num_steps_dev || !truncated_dev) return crl_set_error(CRL_E_INVALID, "null step buffer");
-    LAUNCH(launch_car_step(h->dev, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, (cudaStream_t)stream), 1);
+    LAUNCH(launch_car_step(h->dev, 0, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, (cudaStream_t)stream), 1);
     return CRL_OK;
 }
 
@@ -328,16 +335,45 @@ int crl_car_render_obs(crl_car* h, uint8_t* obs_dev, uint8_t* term_obs_dev, void
     if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
     if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
     cudaStream_t s = (cudaStream_t)stream;
-    LAUNCH(launch_car_render(h->dev, 0, obs_dev, term_obs_dev, s), 3);   // post-step frame (terminal obs of finished envs)
-    LAUNCH(launch_car_reset(h->dev, 1, s), 1);                           // auto-reset of finished envs
-    LAUNCH(launch_car_render(h->dev, 1, obs_dev, nullptr, s), 3);        // their reset observation
+    LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, term_obs_dev, s), 3);   // post-step frame (terminal obs of finished envs)
+    LAUNCH(launch_car_reset(h->dev, 1, s), 1);                                 // auto-reset of finished envs
+    LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 3);        // their reset observation
     return CRL_OK;
 }
 
 int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* rew_dev, uint8_t* done_dev,
                  int32_t* num_steps_dev, uint8_t* truncated_dev, uint8_t* term_obs_dev, void* stream) {
-    if (int r = crl_car_step_state(h, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, stream)) return r;
-    return crl_car_render_obs(h, obs_dev, term_obs_dev, stream);
+    CHECK_HANDLE(h);
+    if (h->dev.players == 1) {
+        if (int r = crl_car_step_state(h, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, stream)) return r;
+        return crl_car_render_obs(h, obs_dev, term_obs_dev, stream);
+    }
+    // Two-car envs.  The step kernel is one wave of latency-bound threads; lane pairs whose cars touch run the sequential
+    // contact solver and take several times longer than the rest.  So: fast pass over the envs whose cars are apart
+    // (the others are only listed), then the listed envs on a side stream WHILE the main stream renders the fast ones,
+    // then the frames of the listed envs.  Per env nothing changes; only the launch schedule does.
+    if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
+    if (!actions_dev || !obs_dev || !rew_dev || !done_dev || !num_steps_dev || !truncated_dev) return crl_set_error(CRL_E_INVALID, "null step buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!h->side_stream) {
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, hi));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fast, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_slow, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaMemsetAsync(h->dev.slow_count, 0, sizeof(int32_t), s));
+    LAUNCH(launch_car_step(h->dev, 1, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, s), 1);
+    CUDA_TRY(cudaEventRecord(h->ev_fast, s));
+    CUDA_TRY(cudaStreamWaitEvent(h->side_stream, h->ev_fast, 0));
+    LAUNCH(launch_car_step(h->dev, 2, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, h->side_stream), 1);
+    CUDA_TRY(cudaEventRecord(h->ev_slow, h->side_stream));
+    LAUNCH(launch_car_render(h->dev, 0, 1, 0, obs_dev, term_obs_dev, s), 2);   // frames of the envs stepped by the fast pass
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_slow, 0));
+    LAUNCH(launch_car_render(h->dev, 0, 2, 1, obs_dev, term_obs_dev, s), 3);   // frames of the listed envs; ring moves on
+    LAUNCH(launch_car_reset(h->dev, 1, s), 1);                                 // auto-reset of finished envs
+    LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 3);        // their reset observation
+    return CRL_OK;
 }
 
 int crl_car_get_state(crl_car* h, double* state_dev, void* stream) {

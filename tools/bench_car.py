@@ -35,9 +35,14 @@ def run(env_id, n, steps, warmup, cpu_envs=0):
     actions = torch.zeros((n, P, 2), dtype=torch.float32, device=dev)
     h = envs._h
 
-    def one(t, ev=None):
+    def one_combined(t):      # the call the vec-env makes: crl_car_step (two-car envs: touching cars on a side stream)
         _native.check(lib.crl_car_random_actions(ptr(actions), actions.numel(), 7, t, sp))
         actions[:, :, 0].mul_(0.3)   # keep cars on the road for a realistic mix (still random)
+        _native.check(lib.crl_car_step(h, ptr(actions), ptr(b["obs"]), ptr(b["rew"]), ptr(b["done"]), ptr(b["steps"]), ptr(b["trunc"]), None, sp))
+
+    def one(t, ev=None):      # the two halves separately, for the per-kernel split
+        _native.check(lib.crl_car_random_actions(ptr(actions), actions.numel(), 7, t, sp))
+        actions[:, :, 0].mul_(0.3)
         if ev:
             ev[0].record(stream)
         _native.check(lib.crl_car_step_state(h, ptr(actions), ptr(b["rew"]), ptr(b["done"]), ptr(b["steps"]), ptr(b["trunc"]), sp))
@@ -54,18 +59,22 @@ def run(env_id, n, steps, warmup, cpu_envs=0):
 
     t = 0
     for _ in range(warmup):
-        one(t)
+        one_combined(t)
         t += 1
     barrier()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for k in range(steps):
-        one(t, evs[k])
+        one_combined(t)
         t += 1
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    for k in range(steps):
+        one(t, evs[k])
+        t += 1
+    barrier()
     phys = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
     rend = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
     if world > 1:
@@ -78,7 +87,8 @@ def run(env_id, n, steps, warmup, cpu_envs=0):
         "metric": "%s env-steps/sec at 96x96x%d obs" % (env_id, 4 * P), "value": n * world * steps / (ms / 1e3), "unit": "env-steps/s",
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "scaling": "weak",
         "config": {"workload": "%s, %d envs per GPU x %d GPU(s), frame_stack 4, random actions (steer scaled 0.3)" % (env_id, n, world)},
-        "kernel_ms": {"car_step_kernel": phys, "render+autoreset": rend},
+        "kernel_ms": {"car_step_kernel": phys, "render+autoreset": rend,
+                      "note": "the two halves run back to back (crl_car_step_state, crl_car_render_obs); value / ms_per_step time crl_car_step"},
         "roofline": {"bound": "latency (serial 180+60-iteration joint solver per car); HBM shown for reference",
                      "achieved": bytes_per_step * n / (rend / 1e3) / 1e9, "unit": "GB/s", "peak": 6539.2,
                      "frac": bytes_per_step * n / (rend / 1e3) / 1e9 / 6539.2},
