@@ -1,0 +1,125 @@
+// Store-pattern ceiling for the Pong rasteriser: the same grid / warp-per-stack mapping / 16-byte streaming stores of
+// 7056-byte frames out of shared memory, with no rasterisation work at all.  Variants: from shared memory (like the
+// kernel) or straight from registers; st.global.cs or plain st.global.
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o raster_store_probe raster_store_probe.cu && ./raster_store_probe
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+constexpr int DD = 84 * 84, NCH = DD / 16, FRAMES = 4;
+
+template <bool CS> __device__ __forceinline__ void st16(uint4* p, uint4 v) {
+    if (CS) asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else *p = v;
+}
+
+template <int WARPS, bool FROM_SMEM, bool CS>
+__global__ void __launch_bounds__(WARPS * 32) probe(uint8_t* obs, long long n_stacks) {
+    extern __shared__ uint4 smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* sm = smem + (size_t)warp * NCH;
+    for (int i = lane; i < NCH; i += 32) sm[i] = make_uint4(i, i, i, i);
+    __syncthreads();
+    for (long long s = (long long)blockIdx.x * WARPS + warp; s < n_stacks; s += (long long)gridDim.x * WARPS) {
+        uint4* out = reinterpret_cast<uint4*>(obs + (size_t)s * FRAMES * DD);
+        for (int f = 0; f < FRAMES; ++f) {
+#pragma unroll
+            for (int j = 0; j < (NCH + 31) / 32; ++j) {
+                const int c = lane + 32 * j;
+                if (c < NCH) st16<CS>(out + (size_t)f * NCH + c, FROM_SMEM ? sm[c] : make_uint4(c, f, j, lane));
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// plain grid-stride fill of the same buffer: the sustained pure-write rate of the device in this harness
+template <bool CS>
+__global__ void __launch_bounds__(256) fill(uint4* out, long long n16) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) st16<CS>(out + i, make_uint4((unsigned)i, 1u, 2u, 3u));
+}
+
+template <bool CS>
+void run_fill(const char* name, uint8_t* obs, long long bytes, int ctas_per_sm) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = 148 * ctas_per_sm;
+    for (int i = 0; i < 5; ++i) fill<CS><<<grid, 256>>>(reinterpret_cast<uint4*>(obs), bytes / 16);
+    const int reps = 50;
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i) fill<CS><<<grid, 256>>>(reinterpret_cast<uint4*>(obs), bytes / 16);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("%-44s %d CTAs/SM x  8 warps: %.3f ms/launch  %.0f GB/s  (%s)\n", name, ctas_per_sm, ms / reps, (double)bytes / (ms / reps) / 1e6,
+           cudaGetErrorString(cudaGetLastError()));
+}
+
+// like probe<>, but the 8 warps of a CTA write ONE frame together (warp w takes chunks w, w + 8, ... of the frame's
+// 32-chunk groups), so a CTA's stores in flight cover one contiguous 7 KB frame instead of eight frames 28 KB apart
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) probe_cta_frame(uint8_t* obs, long long n_stacks) {
+    const long long n_frames = n_stacks * FRAMES;
+    for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        uint4* out = reinterpret_cast<uint4*>(obs + (size_t)f * DD);
+        for (int c = threadIdx.x; c < NCH; c += WARPS * 32) st16<true>(out + c, make_uint4(c, 1u, 2u, 3u));
+    }
+}
+
+template <int WARPS>
+void run_cta_frame(const char* name, uint8_t* obs, long long n_stacks, int ctas_per_sm) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = 148 * ctas_per_sm;
+    for (int i = 0; i < 5; ++i) probe_cta_frame<WARPS><<<grid, WARPS * 32>>>(obs, n_stacks);
+    const int reps = 50;
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i) probe_cta_frame<WARPS><<<grid, WARPS * 32>>>(obs, n_stacks);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("%-44s %d CTAs/SM x %2d warps: %.3f ms/launch  %.0f GB/s  (%s)\n", name, ctas_per_sm, WARPS, ms / reps,
+           (double)n_stacks * FRAMES * DD / (ms / reps) / 1e6, cudaGetErrorString(cudaGetLastError()));
+}
+
+template <int WARPS, bool FROM_SMEM, bool CS>
+void run(const char* name, uint8_t* obs, long long n_stacks, int ctas_per_sm) {
+    const size_t smem = (size_t)WARPS * NCH * 16;
+    cudaFuncSetAttribute(probe<WARPS, FROM_SMEM, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = 148 * ctas_per_sm;
+    for (int i = 0; i < 5; ++i) probe<WARPS, FROM_SMEM, CS><<<grid, WARPS * 32, smem>>>(obs, n_stacks);
+    const int reps = 50;
+    cudaEventRecord(e0);
+    for (int i = 0; i < reps; ++i) probe<WARPS, FROM_SMEM, CS><<<grid, WARPS * 32, smem>>>(obs, n_stacks);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double bytes = (double)n_stacks * FRAMES * DD;
+    printf("%-44s %d CTAs/SM x %2d warps: %.3f ms/launch  %.0f GB/s  (%s)\n", name, ctas_per_sm, WARPS, ms / reps,
+           bytes / (ms / reps) / 1e6, cudaGetErrorString(cudaGetLastError()));
+}
+
+int main() {
+    const long long n_stacks = 65536LL * 2;
+    uint8_t* obs;
+    cudaMalloc(&obs, (size_t)n_stacks * FRAMES * DD);
+    run<8, true, true>("smem -> st.global.cs (the kernel's drain)", obs, n_stacks, 3);
+    run<8, true, false>("smem -> st.global", obs, n_stacks, 3);
+    run<8, false, true>("registers -> st.global.cs", obs, n_stacks, 3);
+    run<8, false, false>("registers -> st.global", obs, n_stacks, 3);
+    run<8, false, false>("registers -> st.global", obs, n_stacks, 8);
+    run<14, true, true>("smem -> st.global.cs", obs, n_stacks, 2);
+    run<4, true, true>("smem -> st.global.cs", obs, n_stacks, 7);
+    run_fill<false>("grid-stride fill, st.global", obs, n_stacks * FRAMES * DD, 8);
+    run_fill<true>("grid-stride fill, st.global.cs", obs, n_stacks * FRAMES * DD, 8);
+    run_fill<false>("grid-stride fill, st.global", obs, n_stacks * FRAMES * DD, 4);
+    run_cta_frame<8>("CTA writes one frame at a time (cs)", obs, n_stacks, 8);
+    run_cta_frame<4>("CTA writes one frame at a time (cs)", obs, n_stacks, 16);
+    return 0;
+}
