@@ -261,6 +261,22 @@ def run_ours(a):
     barrier()
     e2e_obs_s = time.perf_counter() - t0
 
+    # ---- context for the roofline: what a plain fill of the same observation buffers sustains on this GPU (the path
+    #      writes and never reads, so the pure-write rate, not the read+write copy rate, is its physical ceiling) ----
+    fill_views = [obs0.view(torch.int32), obs1.view(torch.int32)]
+    for _ in range(3):
+        for v in fill_views:
+            v.fill_(0)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    f0.record(stream)
+    for _ in range(25):
+        for v in fill_views:
+            v.fill_(0)
+    f1.record(stream)
+    torch.cuda.synchronize(dev)
+    fill_gbps = 25 * 2 * obs0.numel() / (f0.elapsed_time(f1) / 1e3) / 1e9
+
     # max over ranks
     if world > 1:
         tt = torch.tensor([ms, raster_ms, e2e_s, e2e_obs_s], dtype=torch.float64, device=dev)
@@ -284,7 +300,11 @@ def run_ours(a):
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this workload, from the
                      # committed ncu --set full capture (profiles/r01_ncu_raster_fast_v3_summary.txt)
                      "traffic": (3.678e9 + 4.8e6) if N == 65536 else None, "peak_source": peak_src,
-                     "avg_launch_ms": raster_ms, "bytes_per_launch": BYTES_PER_ENV_STEP * N},
+                     "avg_launch_ms": raster_ms, "bytes_per_launch": BYTES_PER_ENV_STEP * N,
+                     "sustained_fill_GBps": fill_gbps, "frac_of_sustained_fill": achieved / fill_gbps,
+                     "note": "peak = read+write copy rate (MEASURED_PEAKS.json); sustained_fill = torch fill_ of the same "
+                             "observation buffers, 25 back-to-back passes, measured in this run: the pure-write rate "
+                             "a write-only path is bounded by (see profiles/r01_store_pattern_probe.txt)"},
         "e2e": {"value": total_envs * K2 / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                 "d2h_bytes_per_step": d2h * world,
                 "note": "crl_pong_step_host: pinned host actions in, rew/done/num_steps/real_reward out (copied on a "

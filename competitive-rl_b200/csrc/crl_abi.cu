@@ -194,6 +194,7 @@ int crl_pong_create(const crl_pong_config* cfg, crl_pong** out) {
     ALLOC(d.skipbuf, 2 * n); ALLOC(d.hist, d.c * n); ALLOC(d.term_hist, d.c * n);
     ALLOC(d.serve_overrun, 1);
     ALLOC(d.stats, 8);
+    ALLOC(d.work_counter, 2);
     ALLOC(h->tabs_dev, 1);
     ALLOC(h->atlas_dev, (size_t)CRL_PONG_ATLAS_BYTES);
     ALLOC(h->text_tab_dev, (size_t)ATLAS_SCORES * ATLAS_SCORES * 3 * 2 * d.text_stride);

