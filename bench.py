@@ -298,8 +298,8 @@ def run_ours(a):
         "roofline": {"bound": "hbm", "kernel": "pong_raster_fast_kernel<84>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this workload, from the
-                     # committed ncu --set full capture (profiles/r01_ncu_raster_fast_v3_summary.txt)
-                     "traffic": (3.678e9 + 4.8e6) if N == 65536 else None, "peak_source": peak_src,
+                     # committed ncu --set full capture (profiles/r01_ncu_raster_fast_v4_summary.txt)
+                     "traffic": (3.642e9 + 4.7e6) if N == 65536 else None, "peak_source": peak_src,
                      "avg_launch_ms": raster_ms, "bytes_per_launch": BYTES_PER_ENV_STEP * N,
                      "sustained_fill_GBps": fill_gbps, "frac_of_sustained_fill": achieved / fill_gbps,
                      "note": "peak = read+write copy rate (MEASURED_PEAKS.json); sustained_fill = torch fill_ of the same "

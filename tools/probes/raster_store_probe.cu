@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(WARPS * 32) probe_cta_drain(uint8_t* obs, long
 
 // persistent, warp per stack like the kernel, but the next stack comes from a global counter (the GPU as a whole
 // sweeps the buffer front to back, like the hardware CTA dispatcher does for a non-persistent launch)
-template <int WARPS, bool PER_CTA>
-__global__ void __launch_bounds__(WARPS * 32) probe_dynamic(uint8_t* obs, long long n_stacks, unsigned long long* counter) {
+template <int WARPS, bool PER_CTA, int UNIT = FRAMES>
+__global__ void __launch_bounds__(WARPS * 32) probe_dynamic(uint8_t* obs, long long n_stacks_in, unsigned long long* counter) {
+    const long long n_stacks = n_stacks_in * (FRAMES / UNIT);      // tickets of UNIT frames
     extern __shared__ uint4 smem[];
     __shared__ long long s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -157,8 +158,8 @@ __global__ void __launch_bounds__(WARPS * 32) probe_dynamic(uint8_t* obs, long l
             s = (long long)__shfl_sync(0xffffffffu, t, 0);
         }
         if (s >= n_stacks) { if (PER_CTA) continue; else break; }
-        uint4* out = reinterpret_cast<uint4*>(obs + (size_t)s * FRAMES * DD);
-        for (int f = 0; f < FRAMES; ++f) {
+        uint4* out = reinterpret_cast<uint4*>(obs + (size_t)s * UNIT * DD);
+        for (int f = 0; f < UNIT; ++f) {
 #pragma unroll
             for (int j = 0; j < (NCH + 31) / 32; ++j) {
                 const int c = lane + 32 * j;
@@ -169,10 +170,10 @@ __global__ void __launch_bounds__(WARPS * 32) probe_dynamic(uint8_t* obs, long l
     }
 }
 
-template <int WARPS, bool PER_CTA>
+template <int WARPS, bool PER_CTA, int UNIT = FRAMES>
 void run_dynamic(const char* name, uint8_t* obs, long long n_stacks, int ctas_per_sm) {
     const size_t smem = (size_t)WARPS * NCH * 16;
-    cudaFuncSetAttribute(probe_dynamic<WARPS, PER_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(probe_dynamic<WARPS, PER_CTA, UNIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     unsigned long long* counter;
     cudaMalloc(&counter, 8);
     cudaEvent_t e0, e1;
@@ -181,7 +182,56 @@ void run_dynamic(const char* name, uint8_t* obs, long long n_stacks, int ctas_pe
     for (int i = 0; i < reps + 5; ++i) {
         if (i == 5) cudaEventRecord(e0);
         cudaMemsetAsync(counter, 0, 8);
-        probe_dynamic<WARPS, PER_CTA><<<grid, WARPS * 32, smem>>>(obs, n_stacks, counter);
+        probe_dynamic<WARPS, PER_CTA, UNIT><<<grid, WARPS * 32, smem>>>(obs, n_stacks, counter);
+    }
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("%-44s %d CTAs/SM x %2d warps: %.3f ms/launch  %.0f GB/s  (%s)\n", name, ctas_per_sm, WARPS, ms / reps,
+           (double)n_stacks * FRAMES * DD / (ms / reps) / 1e6, cudaGetErrorString(cudaGetLastError()));
+}
+
+// persistent, CTA ticket = WARPS / FRAMES consecutive stacks; warp w writes frame (w % FRAMES) of stack (w / FRAMES):
+// the CTA's warps write one contiguous WARPS * 7 KB region at a time
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) probe_dynamic_split(uint8_t* obs, long long n_stacks, unsigned long long* counter) {
+    extern __shared__ uint4 smem[];
+    __shared__ long long s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4* sm = smem + (size_t)warp * NCH;
+    for (int i = lane; i < NCH; i += 32) sm[i] = make_uint4(i, i, i, i);
+    __syncthreads();
+    constexpr int SPC = WARPS / FRAMES;      // stacks per CTA ticket
+    for (;;) {
+        if (threadIdx.x == 0) s_base = (long long)atomicAdd(counter, (unsigned long long)SPC);
+        __syncthreads();
+        const long long s = s_base + warp / FRAMES;
+        __syncthreads();
+        if (s_base >= n_stacks) break;
+        if (s >= n_stacks) continue;
+        uint4* out = reinterpret_cast<uint4*>(obs + ((size_t)s * FRAMES + warp % FRAMES) * DD);
+#pragma unroll
+        for (int j = 0; j < (NCH + 31) / 32; ++j) {
+            const int c = lane + 32 * j;
+            if (c < NCH) st16<true>(out + c, sm[c]);
+        }
+    }
+}
+
+template <int WARPS>
+void run_dynamic_split(const char* name, uint8_t* obs, long long n_stacks, int ctas_per_sm) {
+    const size_t smem = (size_t)WARPS * NCH * 16;
+    cudaFuncSetAttribute(probe_dynamic_split<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    unsigned long long* counter;
+    cudaMalloc(&counter, 8);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = 148 * ctas_per_sm, reps = 50;
+    for (int i = 0; i < reps + 5; ++i) {
+        if (i == 5) cudaEventRecord(e0);
+        cudaMemsetAsync(counter, 0, 8);
+        probe_dynamic_split<WARPS><<<grid, WARPS * 32, smem>>>(obs, n_stacks, counter);
     }
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
@@ -271,6 +321,15 @@ int main() {
     run_fill_tiled<8, true>("tiled fill, varying data", obs, n_stacks * FRAMES * DD);
     run_dynamic<8, false>("persistent, next stack from a counter (warp)", obs, n_stacks, 3);
     run_dynamic<8, true>("persistent, next 8 stacks from a counter (CTA)", obs, n_stacks, 3);
+    run_dynamic_split<8>("CTA ticket = 2 stacks, warp = one frame", obs, n_stacks, 3);
+    run_dynamic_split<4>("CTA ticket = 1 stack, warp = one frame", obs, n_stacks, 7);
+    run_dynamic_split<16>("CTA ticket = 4 stacks, warp = one frame", obs, n_stacks, 1);
+    run_dynamic<8, false, 1>("persistent, next FRAME from a counter (warp)", obs, n_stacks, 3);
+    run_dynamic<8, false, 2>("persistent, next 2 frames from a counter", obs, n_stacks, 3);
+    run_dynamic<8, false>("persistent, next stack from a counter (warp)", obs, n_stacks, 4);
+    run_dynamic<8, false>("persistent, next stack from a counter (warp)", obs, n_stacks, 2);
+    run_dynamic<4, false>("persistent, next stack from a counter (warp)", obs, n_stacks, 7);
+    run_dynamic<4, false>("persistent, next stack from a counter (warp)", obs, n_stacks, 5);
     run_frames<8, 0>("persistent, warp per frame, adjacent frames", obs, n_stacks, 3);
     run_frames<8, 1>("persistent, CTA-cooperative drain of 8 frames", obs, n_stacks, 3);
     run_frames<4, 1>("persistent, CTA-cooperative drain of 4 frames", obs, n_stacks, 7);
