@@ -201,13 +201,21 @@ pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
     // compact window of the observation buffers that advances front to back, like the CTA dispatcher of a non-persistent
     // launch would make them.  Measured with the drain alone (tools/probes/raster_store_probe.cu): 6.8 TB/s against
     // 5.8-5.9 TB/s for the static stride.
+    // A ticket covers ~4 frames (one stack of 4, or 4 stacks of 1): one atomic per 28 KB written; one per 7 KB frame
+    // makes the counter itself the bottleneck (2.7 TB/s in the probe).
     const long long n_stacks = (long long)p.n * p.n_agents;
+    const int per_ticket = max(1, 4 / p.c);
+    long long s = 0, s_end = 0;
     for (;;) {
-        unsigned long long ticket = 0ull;
-        if (lane == 0) ticket = atomicAdd(p.work_counter, 1ull);
-        const long long s = (long long)__shfl_sync(0xffffffffu, ticket, 0);
-        if (s >= n_stacks) break;
-        const int env = (int)(s / p.n_agents), agent = (int)(s % p.n_agents);
+        if (s >= s_end) {
+            unsigned long long ticket = 0ull;
+            if (lane == 0) ticket = atomicAdd(p.work_counter, (unsigned long long)per_ticket);
+            s = (long long)__shfl_sync(0xffffffffu, ticket, 0);
+            s_end = min(s + per_ticket, n_stacks);
+            if (s >= n_stacks) break;
+        }
+        const long long s_cur = s++;
+        const int env = (int)(s_cur / p.n_agents), agent = (int)(s_cur % p.n_agents);
         uint8_t* out_stack = (agent ? obs1 : obs0) + (size_t)env * p.c * DD;
         FrameSpec my_spec = make_uint4(0u, 0u, 0u, 0u);
         if (lane < p.c) my_spec = hist[(size_t)lane * p.n + env];
