@@ -62,24 +62,10 @@ struct FrameMap {
 };
 __device__ __forceinline__ double car_obs_scale() { return (10 / (100 / sqrt(96.0))) * 1.8; }   // CarRacing.obs_scale, :215
 
-// road-map pixel under screen pixel (X, Y); false: outside the rotated surface / source crop (black)
-__device__ __forceinline__ bool map_pixel(const FrameMap& m, int X, int Y, int& U, int& V) {
-    const int x = X - m.bx, y = Y - m.by;
-    if (x < 0 || y < 0 || x >= m.nx || y >= m.ny) return false;
-    const int dx = m.cx0 + m.icos * x - m.isin * y, dy = m.cy0 + m.isin * x + m.icos * y;
-    if (dx < 0 || dy < 0 || dx > (2 * CAR_W << 16) - 1 || dy > (2 * CAR_H << 16) - 1) return false;
-    U = m.rx + (dx >> 16);
-    V = m.ry + (dy >> 16);
-    return true;
-}
-
-// Same without the bounds tests: the visible 96x96 window is the centre of the rotated 192x192 crop, whose
-// inscribed circle (radius 96) always contains it (half diagonal 68), so every screen pixel has a source.
-__device__ __forceinline__ void map_pixel_nocheck(const FrameMap& m, int X, int Y, int& U, int& V) {
-    const int x = X - m.bx, y = Y - m.by;
-    U = m.rx + ((m.cx0 + m.icos * x - m.isin * y) >> 16);
-    V = m.ry + ((m.cy0 + m.isin * x + m.icos * y) >> 16);
-}
+// Screen pixel (X, Y) -> road-map pixel: with (x, y) = (X - bx, Y - by), dx = cx0 + icos * x - isin * y and
+// dy = cy0 + isin * x + icos * y in 16.16 fixed point, (U, V) = (rx + (dx >> 16), ry + (dy >> 16)) -- evaluated
+// incrementally in walk_cells.  The visible 96x96 window is the centre of the rotated 192x192 crop, whose inscribed
+// circle (radius 96) always contains it (half diagonal 68), so every screen pixel has a source inside the crop.
 
 // approximate screen position of road-map point (u, v), to bound sweeps
 __device__ __forceinline__ void map_to_screen(const FrameMap& m, float u, float v, float& X, float& Y) {
