@@ -1426,8 +1426,10 @@ static void world_collide(CarEnv* e) {
             wheel_world_poly(w, wp);
             float minx = wp[0].x, maxx = wp[0].x, miny = wp[0].y, maxy = wp[0].y;
             for (int i = 1; i < 4; ++i) {
-                if (wp[i].x < minx) minx = wp[i].x; if (wp[i].x > maxx) maxx = wp[i].x;
-                if (wp[i].y < miny) miny = wp[i].y; if (wp[i].y > maxy) maxy = wp[i].y;
+                if (wp[i].x < minx) minx = wp[i].x;
+                if (wp[i].x > maxx) maxx = wp[i].x;
+                if (wp[i].y < miny) miny = wp[i].y;
+                if (wp[i].y > maxy) maxy = wp[i].y;
             }
             const float m = 2.0f * B2_POLYGON_RADIUS;
             for (int t = 0; t < e->n_track; ++t) {
@@ -1492,8 +1494,10 @@ static void build_tiles(CarEnv* e) {
         float minx = 3e38f, miny = 3e38f, maxx = -3e38f, maxy = -3e38f;
         for (int k = 0; k < cnt; ++k) {
             e->tile_poly[i][k][0] = hull[2 * k]; e->tile_poly[i][k][1] = hull[2 * k + 1];
-            if (hull[2 * k] < minx) minx = hull[2 * k]; if (hull[2 * k] > maxx) maxx = hull[2 * k];
-            if (hull[2 * k + 1] < miny) miny = hull[2 * k + 1]; if (hull[2 * k + 1] > maxy) maxy = hull[2 * k + 1];
+            if (hull[2 * k] < minx) minx = hull[2 * k];
+            if (hull[2 * k] > maxx) maxx = hull[2 * k];
+            if (hull[2 * k + 1] < miny) miny = hull[2 * k + 1];
+            if (hull[2 * k + 1] > maxy) maxy = hull[2 * k + 1];
         }
         e->tile_aabb[i][0] = minx; e->tile_aabb[i][1] = miny; e->tile_aabb[i][2] = maxx; e->tile_aabb[i][3] = maxy;
         if (e->border[i]) {
