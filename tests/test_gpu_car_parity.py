@@ -255,3 +255,41 @@ def test_double_cars_never_pass_through_each_other():
     assert float(dmin.min()) > 1.9      # hull half-widths 1.2 + 1.2 side by side (2.4 minus skins and slop); through = ~0
     envs.check()
     envs.close()
+
+
+def test_16384_double_envs_properties():
+    """BASELINE config 5 size: cCarRacingDouble-v0, 16384 envs on one GPU -- size-independent properties."""
+    N = 16384
+    envs = _make("cCarRacingDouble-v0", N, seed=21)
+    o = envs.reset()
+    assert tuple(o.shape) == (N, 8, 96, 96) and o.dtype == torch.uint8
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    prev, tiles_prev = o.clone(), envs.get_state()[:, :, 23].clone()
+    ret = torch.zeros((N, 2), device="cuda")
+    touched = np.zeros((N,), bool)
+    for t in range(40):
+        a = torch.rand((N, 2, 2), generator=gen, device="cuda") * 2 - 1
+        a[:, :, 0] *= 0.3
+        o, r, d, info = envs.step(a)
+        assert not bool(d.any())                                             # nobody finishes or leaves the field this early
+        assert torch.equal(o[:, 0:3], prev[:, 1:4]) and torch.equal(o[:, 4:7], prev[:, 5:8])   # FrameStack shift, both players
+        assert int(o[:, [3, 7], 88:, :].max()) <= 255 and int(o[:, 3, 86:88].max()) == 0       # HUD bar rows
+        rew = info.rewards
+        assert bool(torch.isfinite(rew).all()) and float(rew.min()) >= -0.1 - 1e-6           # -0.1 per step, + tiles
+        ret += rew
+        s = envs.get_state()
+        assert bool((s[:, :, 23] >= tiles_prev).all())                       # tiles visited never decreases
+        tiles_prev = s[:, :, 23].clone()
+        cnt, over = envs.get_contacts()
+        assert over == 0 and cnt.max() <= 8
+        touched |= cnt > 0
+        prev = o.clone()
+    s = envs.get_state().cpu().numpy()
+    assert np.isfinite(s).all()
+    # reward bookkeeping: return = 1000 / len(track) per visited tile - 0.1 per step (tile credit is lagged by one sub-step)
+    assert float(ret.max()) < 200 and float(ret.mean()) > -4.0 - 1e-3
+    assert 0.0 < touched.mean() < 0.6                                         # some pairs touch (in-line spawns), most do not
+    dist = np.hypot(s[:, 0, 0] - s[:, 1, 0], s[:, 0, 1] - s[:, 1, 1])
+    assert dist.min() > 1.9                                                   # and none has gone through the other
+    envs.check()
+    envs.close()
