@@ -87,17 +87,18 @@ __device__ __forceinline__ int cdiv_trunc(int a, int b) {
 __device__ __forceinline__ short4 scanline_spans(const short* vx, const short* vy, int n, int V, int maxy) {
     int xs[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
     int m = 0;
+    int yp = vy[n - 1], xp = vx[n - 1];                   // previous vertex (edge i runs from vertex i - 1 to vertex i)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        if (i < n) {
-            const int i1 = i ? i - 1 : n - 1;
-            int y1 = vy[i1], y2 = vy[i], x1 = vx[i1], x2 = vx[i];
-            if (y1 > y2) { int t = y1; y1 = y2; y2 = t; t = x1; x1 = x2; x2 = t; }
-            if (y1 != y2 && ((V >= y1 && V < y2) || (V == maxy && V > y1 && V <= y2))) {
-                const int x = cdiv_trunc((V - y1) * (x2 - x1), y2 - y1) + x1;      // C integer division
-                if (m == 0) xs[0] = x; else if (m == 1) xs[1] = x; else if (m == 2) xs[2] = x; else if (m == 3) xs[3] = x;
-                ++m;
-            }
+        if (i >= n) break;
+        const int yc = vy[i], xc = vx[i];
+        int y1 = yp, y2 = yc, x1 = xp, x2 = xc;
+        yp = yc; xp = xc;
+        if (y1 > y2) { int t = y1; y1 = y2; y2 = t; t = x1; x1 = x2; x2 = t; }
+        if (y1 != y2 && ((V >= y1 && V < y2) || (V == maxy && V > y1 && V <= y2))) {
+            const int x = cdiv_trunc((V - y1) * (x2 - x1), y2 - y1) + x1;      // C integer division
+            if (m == 0) xs[0] = x; else if (m == 1) xs[1] = x; else if (m == 2) xs[2] = x; else if (m == 3) xs[3] = x;
+            ++m;
         }
     }
     // sort (unused slots hold INT_MAX): 4-element network
