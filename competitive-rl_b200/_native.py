@@ -19,7 +19,7 @@ EXPORTS = [
     "crl_pong_render_obs", "crl_pong_render_obs_generic", "crl_pong_terminal_obs", "crl_pong_step_host",
     "crl_pong_get_state", "crl_pong_set_state", "crl_pong_render_raw", "crl_pong_random_actions",
     "crl_launch_count", "crl_pong_check", "crl_pong_get_stats",
-    "crl_car_create", "crl_car_destroy", "crl_car_load_glyphs", "crl_car_inject_tracks", "crl_car_reset",
+    "crl_car_create", "crl_car_destroy", "crl_car_load_glyphs", "crl_car_inject_tracks", "crl_car_load_tracks", "crl_car_reset",
     "crl_car_step", "crl_car_step_state", "crl_car_render_obs", "crl_car_get_state", "crl_car_get_track",
     "crl_car_random_actions", "crl_car_get_stats", "crl_car_get_contacts", "crl_car_check",
 ]
@@ -87,6 +87,7 @@ def load():
     L.crl_car_destroy.argtypes = [vp]
     L.crl_car_load_glyphs.argtypes = [vp, vp, ctypes.c_size_t, vp]
     L.crl_car_inject_tracks.argtypes = [vp, vp, i32, vp, i32, vp]
+    L.crl_car_load_tracks.argtypes = [vp, vp, vp, i32, vp]
     L.crl_car_reset.argtypes = [vp, vp, vp]
     L.crl_car_step.argtypes = [vp] * 9
     L.crl_car_step_state.argtypes = [vp] * 7

@@ -123,6 +123,40 @@ class CudaCarVecEnv(VecEnv):
     def _out(self, t):
         return t.cpu().numpy() if self.return_numpy else t
 
+    def load_tracks(self, tracks):
+        """CarRacing.reset(use_local_track=...) (car_racing_multi_players.py:376-381) for the whole vec-env: `tracks` is a
+        list of recorded tracks, each a JSON path or an (n, 4) [alpha, beta, x, y] / (n, 3) [beta, x, y] array; from the
+        next reset on env i replays track i % len(tracks) at every reset.  An empty list returns to generated tracks."""
+        arrs = []
+        for t in tracks:
+            if isinstance(t, str):
+                import json
+                with open(t, "r", encoding="utf-8") as f:
+                    t = json.load(f)
+            t = np.asarray(t, np.float64)
+            arrs.append(t[:, 1:4] if t.shape[1] == 4 else t)
+        pts = np.zeros((max(len(arrs), 1), 512, 3), np.float64)
+        counts = np.zeros((max(len(arrs), 1),), np.int32)
+        for k, t in enumerate(arrs):
+            assert 9 <= len(t) <= 512, "a track has 9..512 points"
+            pts[k, :len(t)] = t
+            counts[k] = len(t)
+        _native.check(self._lib.crl_car_load_tracks(self._h, pts.ctypes.data, counts.ctypes.data, len(arrs), self._stream()))
+
+    def record_track(self, env, path=None):
+        """CarRacing.reset(record_track_to=...) (:447-451): the current track of `env` in the reference's JSON format
+        [[alpha, beta, x, y], ...].  alpha (the polar angle the generator was at when it emitted the point, unused by
+        every consumer of the file) is recomputed as atan2 of the previous point.  Returns the list; writes `path` if given."""
+        t = self.get_track(env)
+        prev = np.roll(t, 1, axis=0)
+        alpha = np.mod(np.arctan2(prev[:, 2], prev[:, 1]), 2 * np.pi)
+        rows = [[float(alpha[i]), float(t[i, 0]), float(t[i, 1]), float(t[i, 2])] for i in range(len(t))]
+        if path is not None:
+            import json
+            with open(path, "w", encoding="utf-8") as f:
+                json.dump(rows, f)
+        return rows
+
     def reset(self):
         self._cur = (self._cur + 1) % len(self._sets)
         b = self._sets[self._cur]

@@ -120,6 +120,11 @@ struct CarDev {
     int k_draws;
     const int32_t* birth;        // [n][k_birth][players] or nullptr
     int k_birth;
+    // fixed tracks (CarRacing.reset(use_local_track=...), car_racing_multi_players.py:376-381): env e replays track
+    // e % n_fixed at every reset instead of generating one
+    const double* fixed_tracks;  // [n_fixed][CAR_MAX_TRACK][3] beta, x, y or nullptr
+    const int32_t* fixed_counts; // [n_fixed]
+    int n_fixed;
     int32_t* overrun;            // [0] device flag: an injection table ran out; [1] frames whose rasteriser dropped polygons;
                                  // [2] frames rasterised on the exact slow path (span pool full)
     // ---- constants ----

@@ -206,6 +206,12 @@ __global__ void car_reset_kernel(CarDev p, int only_done) {
     CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
     const uint64_t gi = (uint64_t)(p.first_env + e);
     int n = 0;
+    if (p.fixed_tracks != nullptr && p.n_fixed > 0) {       // replay of a recorded track: no generation, no draws consumed
+        const int k = (int)(gi % (uint64_t)p.n_fixed);
+        n = min(max(p.fixed_counts[k], 0), CAR_MAX_TRACK);
+        const double* src = p.fixed_tracks + (size_t)k * CAR_MAX_TRACK * 3;
+        for (int i = 0; i < 3 * n; ++i) pts[i] = src[i];
+    }
     for (int guard = 0; guard < 64 && n == 0; ++guard) {
         double draws[CAR_DRAWS];
         const int att = p.attempt_count[e];
@@ -251,10 +257,12 @@ __global__ void car_reset_kernel(CarDev p, int only_done) {
             oneside += (b1 - b2 > 0) - (b1 - b2 < 0);
         }
         good = good && abs(oneside) == CR_BORDER_MIN_COUNT;
-        if (good) tiles[i].flags |= 8;   // provisional mark
+        if (good) tiles[i].flags |= 2;
     }
+    // "border[i - neg] |= border[i]" in place, i ascending (:394-396): the marks i = 0..2 put on the last tiles through the
+    // negative indices are seen again when the loop gets there, exactly like the reference's list
     for (int i = 0; i < n; ++i)
-        if (tiles[i].flags & 8)
+        if (tiles[i].flags & 2)
             for (int neg = 0; neg < CR_BORDER_MIN_COUNT; ++neg) tiles[((i - neg) % n + n) % n].flags |= 2;
     // tiles (:399-445)
     for (int i = 0; i < n; ++i) {

@@ -309,6 +309,28 @@ int crl_car_inject_tracks(crl_car* h, const double* draws_host, int32_t k_draws,
     return CRL_OK;
 }
 
+int crl_car_load_tracks(crl_car* h, const double* pts_host, const int32_t* counts_host, int32_t n_tracks, void* stream) {
+    CHECK_HANDLE(h);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_tracks <= 0) {                       // back to generated tracks
+        h->dev.fixed_tracks = nullptr; h->dev.fixed_counts = nullptr; h->dev.n_fixed = 0;
+        return CRL_OK;
+    }
+    if (!pts_host || !counts_host) return crl_set_error(CRL_E_INVALID, "null track buffer");
+    for (int k = 0; k < n_tracks; ++k)
+        if (counts_host[k] < 9 || counts_host[k] > CAR_MAX_TRACK)
+            return crl_set_error(CRL_E_INVALID, "track %d has %d points; need 9..%d", k, counts_host[k], CAR_MAX_TRACK);
+    double* dp = nullptr;
+    int32_t* dc = nullptr;
+    CUDA_TRY(car_alloc(h, &dp, (size_t)n_tracks * CAR_MAX_TRACK * 3));
+    CUDA_TRY(car_alloc(h, &dc, (size_t)n_tracks));
+    CUDA_TRY(cudaMemcpyAsync(dp, pts_host, (size_t)n_tracks * CAR_MAX_TRACK * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(dc, counts_host, (size_t)n_tracks * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    h->dev.fixed_tracks = dp; h->dev.fixed_counts = dc; h->dev.n_fixed = n_tracks;
+    return CRL_OK;
+}
+
 int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream) {
     CHECK_HANDLE(h);
     if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");

@@ -184,6 +184,11 @@ int crl_car_inject_tracks(crl_car* h, const double* draws_host, int32_t k_draws,
                           int32_t k_birth, void* stream);
 
 /* VecEnv.reset(): obs_dev uint8 [num_envs][num_players * C][96][96]. */
+/* CarRacing.reset(use_local_track=<json>) (car_racing_multi_players.py:376-381): replay recorded tracks instead of
+ * generating them.  pts_host: float64 [n_tracks][CRL_CAR_MAX_TRACK][3] = (beta, x, y) of every track point (the JSON
+ * rows are [alpha, beta, x, y]; alpha is not used downstream), counts_host: int32 [n_tracks] points per track.  From the
+ * next reset on, env i (global index) uses track i % n_tracks at every reset.  n_tracks = 0 returns to generated tracks. */
+int crl_car_load_tracks(crl_car* h, const double* pts_host, const int32_t* counts_host, int32_t n_tracks, void* stream);
 int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream);
 
 /* VecEnv.step with auto-reset.

@@ -1029,6 +1029,28 @@ int car_oracle_convex_hull(const float* in_xy, int n, float* out_xy) {
 
 typedef struct { double alpha, beta, x, y; } TrackPt;
 
+/* red-white border on hard turns, car_racing_multi_players.py:383-397 (also run on a track loaded from JSON, :376-381) */
+static void track_border(const double* beta, int n, int* border) {
+    for (int k = 0; k < n; ++k) {
+        int good = 1, oneside = 0;
+        for (int neg = 0; neg < BORDER_MIN_COUNT; ++neg) {
+            double b1 = beta[((k - neg - 0) % n + n) % n], b2 = beta[((k - neg - 1) % n + n) % n];
+            good &= fabs(b1 - b2) > TRACK_TURN_RATE * 0.2;
+            oneside += (b1 - b2 > 0) - (b1 - b2 < 0);
+        }
+        good &= abs(oneside) == BORDER_MIN_COUNT;
+        border[k] = good;
+    }
+    for (int k = 0; k < n; ++k)
+        for (int neg = 0; neg < BORDER_MIN_COUNT; ++neg) border[((k - neg) % n + n) % n] |= border[k];
+}
+/* border flags of a given track [n][4] (alpha, beta, x, y) */
+void car_oracle_track_border(const double* track, int n, int* border_out) {
+    double betas[MAX_TRACK];
+    for (int k = 0; k < n && k < MAX_TRACK; ++k) betas[k] = track[4 * k + 1];
+    track_border(betas, n < MAX_TRACK ? n : MAX_TRACK, border_out);
+}
+
 int car_oracle_create_track(const double* draws, double* out /* [MAX_TRACK][4] */, int* border_out) {
     double cp_alpha[CHECKPOINTS], cp_x[CHECKPOINTS], cp_y[CHECKPOINTS];
     double start_alpha = 0.0;
@@ -1099,18 +1121,9 @@ int car_oracle_create_track(const double* draws, double* out /* [MAX_TRACK][4] *
     if (sqrt(dx * dx + dy * dy) > TRACK_DETAIL_STEP) return 0;
     /* red-white border on hard turns */
     int border[MAX_TRACK];
-    for (int k = 0; k < n; ++k) {
-        int good = 1, oneside = 0;
-        for (int neg = 0; neg < BORDER_MIN_COUNT; ++neg) {
-            double b1 = t[((k - neg - 0) % n + n) % n].beta, b2 = t[((k - neg - 1) % n + n) % n].beta;
-            good &= fabs(b1 - b2) > TRACK_TURN_RATE * 0.2;
-            oneside += (b1 - b2 > 0) - (b1 - b2 < 0);
-        }
-        good &= abs(oneside) == BORDER_MIN_COUNT;
-        border[k] = good;
-    }
-    for (int k = 0; k < n; ++k)
-        for (int neg = 0; neg < BORDER_MIN_COUNT; ++neg) border[((k - neg) % n + n) % n] |= border[k];
+    double betas[MAX_TRACK];
+    for (int k = 0; k < n; ++k) betas[k] = t[k].beta;
+    track_border(betas, n, border);
     for (int k = 0; k < n; ++k) {
         out[4 * k] = t[k].alpha; out[4 * k + 1] = t[k].beta; out[4 * k + 2] = t[k].x; out[4 * k + 3] = t[k].y;
         if (border_out) border_out[k] = border[k];

@@ -42,6 +42,7 @@ def lib():
         L.car_oracle_free_collision.argtypes = [vp, vp, ctypes.c_int, vp]
         L.car_oracle_create_track.argtypes = [vp, vp, vp]
         L.car_oracle_create_track.restype = ctypes.c_int
+        L.car_oracle_track_border.argtypes = [vp, ctypes.c_int, vp]
         L.car_oracle_polys_touch.argtypes = [vp, ctypes.c_int, vp, ctypes.c_int]
         L.car_oracle_convex_hull.argtypes = [vp, ctypes.c_int, vp]
         L.car_oracle_sizeof_body.restype = ctypes.c_int
@@ -78,6 +79,14 @@ def create_track(draws):
     if n <= 0:
         return None
     return out[:n].copy(), border[:n].copy()
+
+
+def track_border(track):
+    """Kerb flags (:383-397) of a given track (n, 4) [alpha, beta, x, y], e.g. one loaded from the reference's JSON."""
+    track = np.ascontiguousarray(track, np.float64)
+    border = np.zeros((len(track),), np.int32)
+    lib().car_oracle_track_border(_p(track), len(track), _p(border))
+    return border
 
 
 def make_track(rng):

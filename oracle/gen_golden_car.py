@@ -72,6 +72,36 @@ def run(name, n_players, seed, T, action_repeat=None, amp=0.6, actions=None, min
     return True
 
 
+def run_replay(name, seed_track, seed_env, T):
+    """reset(record_track_to=...) of one env, then reset(use_local_track=<that json>) of another (:376-381, 447-451)."""
+    import glob
+    import json
+    import tempfile
+    M = RC.load_car_racing()
+    rec_env = M.CarRacing(num_player=1, verbose=0)
+    rec_env.seed(seed_track)
+    np.random.seed(seed_track)
+    with tempfile.TemporaryDirectory() as d:
+        rec_env.reset(record_track_to=d)
+        path = glob.glob(os.path.join(d, "*_track.json"))[0]
+        rows = np.array(json.load(open(path)), np.float64)
+        assert np.array_equal(rows, np.array(rec_env.track))
+        env = M.CarRacing(num_player=1, verbose=0)
+        env.seed(seed_env)
+        np.random.seed(seed_env)
+        env.reset(use_local_track=path)
+    assert np.array_equal(np.array(env.track), rows)
+    actions = actions_for(T, 1, seed_env + 1, 0.4)
+    states, rewards = np.zeros((T, 1, 24)), np.zeros((T, 1))
+    state0 = np.array([RC.car_state(env, 0)])
+    for t in range(T):
+        o, r, dn, info = env.step(actions[t, 0])
+        states[t, 0], rewards[t, 0] = RC.car_state(env, 0), r
+    out = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(out, track_json=rows, actions=actions[:, 0], state0=state0, states=states, rewards=rewards)
+    print("%-22s track=%d tiles_visited=%s return=%.2f  %d KiB" % (name, len(rows), states[-1, :, 23], rewards.sum(), os.path.getsize(out) // 1024))
+
+
 def run_collision(name, seed, T):
     """Two cars steered into each other (the cars spawn 5 units apart side by side): the car-car contact
     path of world.Step under the reference's own CarRacing.step.  The steering sign that closes the gap depends
@@ -130,6 +160,7 @@ def run_frames(name, cases, T=60, every=12):
 
 if __name__ == "__main__":
     run_frames("car_frames", [(1, 123), (1, 31), (2, 12)])
+    run_replay("car_replay", 31, 4, 80)
     run("car_single_seed123", 1, 123, 400)
     run("car_single_seed5_rep2", 1, 5, 150, action_repeat=2)
     # The reference raises AttributeError inside FrictionDetector._contact (it reads self.verbose,

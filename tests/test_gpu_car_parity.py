@@ -293,3 +293,52 @@ def test_16384_double_envs_properties():
     assert dist.min() > 1.9                                                   # and none has gone through the other
     envs.check()
     envs.close()
+
+
+def test_track_record_and_replay(tmp_path):
+    """CarRacing.reset(record_track_to=..., use_local_track=...) (car_racing_multi_players.py:376-381, 447-451): the JSON
+    written for a generated track, loaded into another vec-env, reproduces the same tiles, spawn and rollout."""
+    import json
+    a_env = _make("cCarRacing-v0", 3, seed=77)
+    a_env.reset()
+    paths = []
+    for e in range(3):
+        p = str(tmp_path / ("track%d.json" % e))
+        rows = a_env.record_track(e, p)
+        assert len(rows) == len(a_env.get_track(e)) and len(rows[0]) == 4
+        paths.append(p)
+    b_env = _make("cCarRacing-v0", 6, seed=5)           # other seed: its own tracks would differ
+    b_env.load_tracks(paths)
+    b_env.reset()
+    for e in range(6):
+        assert np.array_equal(b_env.get_track(e), a_env.get_track(e % 3))
+    sa, sb = a_env.get_state().cpu().numpy(), b_env.get_state().cpu().numpy()
+    assert np.array_equal(sb[:3, :, :6], sa[:, :, :6]) and np.array_equal(sb[3:, :, :6], sa[:, :, :6])
+    act = torch.tensor([[0.1, 0.6]], device="cuda")
+    for t in range(40):
+        o1, r1, d1, _ = a_env.step(act.repeat(3, 1))
+        o2, r2, d2, _ = b_env.step(act.repeat(6, 1))
+        assert torch.equal(o2[:3], o1) and torch.equal(o2[3:], o1) and torch.equal(r2[:3], r1)
+    assert np.allclose(np.array(json.load(open(paths[0])))[:, 1:], a_env.get_track(0), rtol=0, atol=0)
+    b_env.load_tracks([])                                # back to generated tracks
+    b_env.reset()
+    assert not np.array_equal(b_env.get_track(0), a_env.get_track(0))
+    a_env.close(); b_env.close()
+
+
+def test_replayed_track_matches_reference_fixture():
+    """tests/golden/car_replay.npz: the reference's own reset(use_local_track=<json>) + 80 steps on the stand-in Box2D."""
+    g = load_golden("car_replay")
+    envs = _make("cCarRacing-v0", 1, seed=3)
+    envs.load_tracks([g["track_json"]])
+    envs.reset()
+    assert np.array_equal(envs.get_track(0), g["track_json"][:, 1:])
+    s0 = envs.get_state().cpu().numpy()[0]
+    assert np.abs(s0[:, :6] - g["state0"][:, :6]).max() <= 1e-5
+    for t in range(len(g["actions"])):
+        obs, r, d, info = envs.step(g["actions"][t].astype(np.float32))
+        s = envs.get_state().cpu().numpy()[0]
+        assert np.abs(s[:, :2] - g["states"][t][:, :2]).max() <= 0.02 and np.abs(s[:, 2] - g["states"][t][:, 2]).max() <= 0.01, t
+        assert np.abs(info.rewards.cpu().numpy()[0] - g["rewards"][t]).max() <= 1e-4, t
+        assert np.array_equal(s[:, 23], g["states"][t][:, 23]), t
+    envs.close()

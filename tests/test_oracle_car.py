@@ -94,3 +94,16 @@ def test_render_is_deterministic_and_plausible():
     for _ in range(5):
         o, r, d, _ = env.step(np.array([[0.0, 0.5]]))
     assert not np.array_equal(o[0], o0)
+
+
+def test_replayed_track_matches_reference():
+    """reset(use_local_track=<json>) (car_racing_multi_players.py:376-381): the reference's own replay run on the stand-in."""
+    g = load_golden("car_replay")
+    track = g["track_json"]
+    env = C.CarOracleEnv(1, 1, None, render=False)
+    env.reset(track, C.track_border(track), [0])
+    assert np.array_equal(env.get_state(), g["state0"])
+    for t, a in enumerate(g["actions"]):
+        _, rew, done, _ = env.step(a[None])
+        assert np.array_equal(env.get_state(), g["states"][t]), t
+        assert np.array_equal(rew, g["rewards"][t]), t
