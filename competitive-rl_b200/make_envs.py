@@ -45,8 +45,9 @@ def make_envs(env_id="cPong-v0", seed=0, log_dir="data", num_envs=3, asynchronou
     env_id = _verify_env_id(env_id)
     if env_id == "cPongTournament-v0":
         from .tournament import TournamentEnvWrapper
+        resource_dir = kwargs.pop("resource_dir", None)     # where the reference's checkpoint-*.pkl files are (optional)
         envs = make_envs("cPongDouble-v0", seed, log_dir, num_envs, asynchronous, resized_dim, None, **kwargs)
-        return TournamentEnvWrapper(envs, num_envs)
+        return TournamentEnvWrapper(envs, num_envs, resource_dir)
     if log_dir:
         os.makedirs(log_dir, exist_ok=True)
     if env_id in ("cPong-v0", "cPongDouble-v0"):

@@ -1,22 +1,30 @@
-"""TournamentEnvWrapper: single-agent view of a Double vec-env whose agent 1 is played by a
-built-in opponent (competitive_rl/pong/competitive_pong_env.py:9-53).  Only the opponents that
-need no network are available on the device: RULE_BASED (the env's own action 999,
-pong/base_pong_env.py:116-134) and RANDOM."""
+"""TournamentEnvWrapper: single-agent view of a Double vec-env whose agent 1 is played by a built-in opponent
+(competitive_rl/pong/competitive_pong_env.py:9-53).  The opponent acts on the device (builtin_policies.py): its
+observation, frame stack and action never visit the host.  Available opponents: RANDOM, RULE_BASED and every
+network agent whose checkpoint file can be found (the reference ships WEAK and MEDIUM)."""
 import numpy as np
 import torch
 
-from .vec_env import CHEAT_CODES
+from .builtin_policies import get_builtin_agent_names, get_compute_action_function
 
 
 class TournamentEnvWrapper(object):
-    def __init__(self, env, num_envs):
+    def __init__(self, env, num_envs, resource_dir=None):
         self.env = env
-        self.agent_names = ["RANDOM", "RULE_BASED"]
+        self.num_envs = num_envs
+        self._resource_dir = resource_dir
+        self.agent_names = [n for n in get_builtin_agent_names(resource_dir) if n != "ALPHA_PONG"]
+        self.agents = {}                      # built on first use: a network agent allocates its stack and weights
         self.current_agent_name = "RULE_BASED"
+        self.current_agent = self._agent("RULE_BASED")
         self.observation_space = env.observation_space[0]
         self.action_space = env.action_space[0]
-        self.num_envs = num_envs
         self.prev_opponent_obs = None
+
+    def _agent(self, name):
+        if name not in self.agents:
+            self.agents[name] = get_compute_action_function(name, self.num_envs, self.env.device, self._resource_dir)
+        return self.agents[name]
 
     def get_agent_names(self):
         return self.agent_names
@@ -26,16 +34,12 @@ class TournamentEnvWrapper(object):
             agent_name = self.agent_names[int(np.random.randint(len(self.agent_names)))]
         assert agent_name in self.agent_names, self.agent_names
         self.current_agent_name = agent_name
-
-    def _opponent_actions(self, n, device):
-        if self.current_agent_name == "RULE_BASED":
-            return torch.full((n,), CHEAT_CODES, dtype=torch.int32, device=device)
-        return torch.randint(0, 3, (n,), dtype=torch.int32, device=device)
+        self.current_agent = self._agent(agent_name)
 
     def step(self, action):
         a = torch.as_tensor(np.asarray(action) if not isinstance(action, torch.Tensor) else action)
         a = a.reshape(-1).to(self.env.device, dtype=torch.int32)
-        both = torch.stack([a, self._opponent_actions(a.shape[0], a.device)], dim=1)
+        both = torch.stack([a, self.current_agent(self.prev_opponent_obs).reshape(-1)], dim=1)
         obs, rew, done, info = self.env.step(both)
         self.prev_opponent_obs = obs[1]
         if done.ndim == 2:
