@@ -136,3 +136,38 @@ def test_step_host_matches_device_step():
             assert torch.equal(h_o0, obs[0].cpu()) and torch.equal(h_o1, obs[1].cpu())
         dones += int(h_done.sum())
     ea.close(); eb.close()
+
+
+def test_evaluate_two_policies_in_batch_matches_host_bookkeeping():
+    """Device-side evaluate_two_policies_in_batch against the reference's per-env Python bookkeeping
+    (pong/evaluate.py:53-88) replayed on a twin env."""
+    from competitive_rl_b200 import make_envs
+    from competitive_rl_b200.evaluate import evaluate_two_policies_in_batch
+    from competitive_rl_b200.builtin_policies import get_compute_action_function
+    N, EPISODES = 128, 200
+    kw = dict(num_envs=N, resized_dim=42, frame_stack=None, log_dir=None, seed=9, asynchronous=True)
+
+    def lazy(obs):                      # deterministic opponent: always "stay"
+        return torch.ones((N,), dtype=torch.int32, device="cuda")
+    rule = get_compute_action_function("RULE_BASED", N, "cuda")
+    g0, g1 = evaluate_two_policies_in_batch(rule, lazy, make_envs("cPongDouble-v0", **kw), EPISODES)
+    # the reference's loop, on the host, over an identically seeded env
+    envs = make_envs("cPongDouble-v0", **kw)
+    r0, r1 = [0] * 4, [0] * 4
+    ep = np.zeros((N, 2))
+    total = 0
+    obs = envs.reset()
+    while total < EPISODES:
+        a = torch.stack([rule(obs[0]), lazy(obs[1])], dim=1)
+        obs, rew, done, _ = envs.step(a)
+        ep += rew.cpu().numpy()
+        for i, dn in enumerate(done.cpu().numpy().reshape(N, -1).all(axis=1)):
+            if dn:
+                k = 0 if ep[i, 0] > 0 else (1 if ep[i, 0] == 0 else 2)
+                r0[k] += 1; r1[2 - k] += 1
+                r0[3] += ep[i, 0]; r1[3] += ep[i, 1]
+                total += 1
+                ep[i] = 0
+    assert g0 == r0 and g1 == r1
+    assert g0[0] + g0[1] + g0[2] >= EPISODES and g0[0] > g0[2]      # the rule-based bat beats a bat that never moves
+    envs.close()
