@@ -45,6 +45,7 @@ constexpr int BAT_ROWS = 8;      // destination rows one bat can touch (checked 
 template <int DIM> struct alignas(16) FastTabs {
     TapEnt<FastCfg<DIM>::TAPS> xe[DIM], ye[DIM];
     uint32_t bat_lut[2][DIM][1 << FastCfg<DIM>::TAPS];   // [view side][dst row][vertical tap bits] -> 4 pixels
+    float xlut[DIM][1 << FastCfg<DIM>::TAPS];            // [dst column][white horizontal taps] -> cv2's row sum (eval_from_pat's buf)
     uint8_t x_first[SCREEN_W], x_last[SCREEN_W], y_first[FIRST_PAD], y_last[FIRST_PAD];
     uint32_t bat_c0[2], pad[2];                           // first of the 4 destination columns per side
 };
@@ -97,6 +98,32 @@ __device__ __forceinline__ uint32_t eval_from_pat(const TapEnt<TAPS>& X, const T
     }
     const int v = __float2int_rn(sum);                       // cvRound: half to even
     return (uint32_t)min(max(v, 0), 255);
+}
+
+// eval_from_pat with the horizontal sums looked up: xl = T->xlut[dx] holds, for every subset of white horizontal taps, the
+// float the sequential additions of eval_from_pat arrive at (built with the same __fadd_rn chain, so bit-identical).
+template <int TAPS>
+__device__ __forceinline__ uint32_t eval_from_pat_lut(const float* __restrict__ xl, const TapEnt<TAPS>& Y, uint32_t pat) {
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+        const float term = __fmul_rn(Y.w[t], xl[(pat >> (6 * t)) & ((1u << TAPS) - 1u)]);
+        sum = (t == 0) ? term : __fadd_rn(sum, term);
+    }
+    const int v = __float2int_rn(sum);
+    return (uint32_t)min(max(v, 0), 255);
+}
+
+template <int DIM>
+__global__ void pong_build_xlut_kernel(FastTabs<DIM>* T) {
+    constexpr int TAPS = FastCfg<DIM>::TAPS, NP = 1 << TAPS;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= DIM * NP) return;
+    const int bits = i % NP, dx = i / NP;
+    const TapEnt<TAPS> X = T->xe[dx];
+    float buf = (bits & 1) ? X.w[0] : 0.f;
+    for (int u = 1; u < TAPS; ++u) buf = __fadd_rn(buf, ((bits >> u) & 1) ? X.w[u] : 0.f);
+    T->xlut[dx][bits] = buf;
 }
 
 // One 4-pixel LUT word per (view side, destination row, vertical tap bits).
@@ -338,7 +365,7 @@ pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
                             const uint32_t hb = tap_bits(((1u << BAT_W) - 1u) << 8, nr ? RIGHT_BAT_X : LEFT_BAT_X, sx0);
                             pat |= (hb & xmask) * spread6(vbits & ymask);
                         }
-                        ball_val = eval_from_pat<TAPS>(X, Y, pat);
+                        ball_val = eval_from_pat_lut<TAPS>(T->xlut[dx], Y, pat);
                         ball_off = dy * DIM + dx;
                     }
                 }
@@ -472,10 +499,13 @@ bool pong_fast_tabs_fill(const AreaTabs& a, int text_stride, void* host_buf) {
 }
 
 cudaError_t launch_pong_build_bat_lut(int dim, void* fast_tabs_dev, cudaStream_t s) {
-    if (dim == 84)
+    if (dim == 84) {
         pong_build_bat_lut_kernel<84><<<(2 * 84 * 8 + 127) / 128, 128, 0, s>>>(reinterpret_cast<FastTabs<84>*>(fast_tabs_dev));
-    else if (dim == 42)
+        pong_build_xlut_kernel<84><<<(84 * 8 + 127) / 128, 128, 0, s>>>(reinterpret_cast<FastTabs<84>*>(fast_tabs_dev));
+    } else if (dim == 42) {
         pong_build_bat_lut_kernel<42><<<(2 * 42 * 32 + 127) / 128, 128, 0, s>>>(reinterpret_cast<FastTabs<42>*>(fast_tabs_dev));
+        pong_build_xlut_kernel<42><<<(42 * 32 + 127) / 128, 128, 0, s>>>(reinterpret_cast<FastTabs<42>*>(fast_tabs_dev));
+    }
     return cudaGetLastError();
 }
 
