@@ -322,6 +322,8 @@ int main() {
     run_dynamic<8, false>("persistent, next stack from a counter (warp)", obs, n_stacks, 3);
     run_dynamic<8, true>("persistent, next 8 stacks from a counter (CTA)", obs, n_stacks, 3);
     run_dynamic_split<8>("CTA ticket = 2 stacks, warp = one frame", obs, n_stacks, 3);
+    run_dynamic_split<8>("CTA ticket = 2 stacks, warp = one frame", obs, n_stacks, 2);
+    run_dynamic_split<8>("CTA ticket = 2 stacks, warp = one frame", obs, n_stacks, 4);
     run_dynamic_split<4>("CTA ticket = 1 stack, warp = one frame", obs, n_stacks, 7);
     run_dynamic_split<16>("CTA ticket = 4 stacks, warp = one frame", obs, n_stacks, 1);
     run_dynamic<8, false, 1>("persistent, next FRAME from a counter (warp)", obs, n_stacks, 3);
