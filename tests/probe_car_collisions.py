@@ -1,6 +1,7 @@
-"""Exploratory: cCarRacingDouble car-car collisions, CUDA path vs the C oracle (states, contact counts)."""
+"""Exploratory (not collected by pytest; run by hand on a GPU box): cCarRacingDouble car-car collisions, CUDA path vs
+the C oracle (states, contact counts).  Lives under tests/ because it uses the oracle."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this file lives in tests/)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 import car_oracle as C

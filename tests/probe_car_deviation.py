@@ -1,6 +1,7 @@
-"""Exploratory: deviation of the CUDA car path from the C oracle (states, rewards, pixels)."""
+"""Exploratory (not collected by pytest; run by hand on a GPU box): deviation of the CUDA car path from the C oracle
+(states, rewards, pixels).  Lives under tests/ because it uses the oracle."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this file lives in tests/)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np, torch
 import car_oracle as C
