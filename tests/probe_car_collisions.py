@@ -10,6 +10,7 @@ from competitive_rl_b200 import make_envs
 SCEN = [(-0.35, 0.35, 0.5, 0.5), (-0.2, 0.3, 0.6, 0.4), (-0.5, 0.0, 0.5, 0.3), (0.0, 0.45, 0.3, 0.6),
         (-0.3, 0.3, 0.8, 0.8), (-0.15, 0.15, 0.4, 0.4), (-0.4, 0.1, 0.7, 0.2), (-0.1, 0.4, 0.2, 0.7)]
 N, T = len(SCEN), int(sys.argv[1]) if len(sys.argv) > 1 else 90
+REP = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 rng = np.random.RandomState(5)
 draws = np.zeros((N, 4, 24)); tracks = []
 for e in range(N):
@@ -17,8 +18,8 @@ for e in range(N):
     draws[e, :] = d
     tracks.append((tr, bd))
 birth = np.tile(np.arange(2)[None, None], (N, 4, 1)).astype(np.int32)
-envs = make_envs("cCarRacingDouble-v0", num_envs=N, frame_stack=4, log_dir=None, track_draws=draws, birth=birth)
-orcs = [C.CarOracleEnv(2, 1, None, render=False) for _ in range(N)]
+envs = make_envs("cCarRacingDouble-v0", num_envs=N, frame_stack=4, log_dir=None, track_draws=draws, birth=birth, action_repeat=REP)
+orcs = [C.CarOracleEnv(2, REP, None, render=False) for _ in range(N)]
 envs.reset()
 for e, o in enumerate(orcs):
     o.reset(*tracks[e], [0, 1])

@@ -170,10 +170,12 @@ COLLISION_SCENARIOS = [(-0.35, 0.35, 0.5, 0.5), (-0.2, 0.3, 0.6, 0.4), (-0.5, 0.
                        (-0.3, 0.3, 0.8, 0.8), (-0.15, 0.15, 0.4, 0.4), (-0.4, 0.1, 0.7, 0.2), (-0.1, 0.4, 0.2, 0.7)]
 
 
-def test_car_car_collisions_vs_oracle():
-    """Two cars steered into each other: contacts (b2CollidePolygons + contact solver in the merged island)."""
+@pytest.mark.parametrize("action_repeat", [1, 2])
+def test_car_car_collisions_vs_oracle(action_repeat):
+    """Two cars steered into each other: contacts (b2CollidePolygons + contact solver in the merged island).  With
+    action_repeat = 2 the second sub-step of a pair that only gets near there is solved inline by the fast pass."""
     import car_oracle as C
-    N, T = len(COLLISION_SCENARIOS), 90
+    N, T = len(COLLISION_SCENARIOS), 90 // action_repeat
     rng = np.random.RandomState(5)
     draws, tracks = np.zeros((N, 4, 24)), []
     for e in range(N):
@@ -181,8 +183,8 @@ def test_car_car_collisions_vs_oracle():
         draws[e, :] = d
         tracks.append((tr, bd))
     birth = np.tile(np.arange(2)[None, None], (N, 4, 1)).astype(np.int32)
-    envs = _make("cCarRacingDouble-v0", N, track_draws=draws, birth=birth)
-    orcs = [C.CarOracleEnv(2, 1, None, render=False) for _ in range(N)]
+    envs = _make("cCarRacingDouble-v0", N, track_draws=draws, birth=birth, action_repeat=action_repeat)
+    orcs = [C.CarOracleEnv(2, action_repeat, None, render=False) for _ in range(N)]
     envs.reset()
     for e, o in enumerate(orcs):
         o.reset(*tracks[e], [0, 1])
@@ -198,12 +200,14 @@ def test_car_car_collisions_vs_oracle():
             dev[t, e] = np.abs(sg[e, :, :3] - orcs[e].get_state()[:, :3]).max()
             co[t, e] = orcs[e].contacts()[0]
     for e in range(N):
-        assert (co[:, e] > 0).sum() >= 20, e                       # the scenario does collide
+        assert (co[:, e] > 0).sum() >= 20 // action_repeat, e      # the scenario does collide
         first = int(np.argmax(co[:, e] > 0))
         assert int(np.argmax(cg[:, e] > 0)) == first, e
         assert (cg[:, e] != co[:, e]).mean() <= 0.05, e
-        assert dev[:first + 30, e].max() <= 0.02, (e, dev[:first + 30, e].max())
-        assert dev[:, e].max() <= 0.1, (e, dev[:, e].max())
+        assert dev[:first + 30 // action_repeat, e].max() <= 0.02, (e, dev[:first + 30 // action_repeat, e].max())
+        # after a long high-speed scrape one manifold point appearing a sub-step apart is enough for the two runs to drift
+        # (measured: <= 5e-3 with action_repeat 1, 0.11 in the fastest scenario with action_repeat 2)
+        assert dev[:, e].max() <= (0.1 if action_repeat == 1 else 0.25), (e, dev[:, e].max())
     print("collision parity: max dev +30 %.2e, end %.2e" % (max(dev[:int(np.argmax(co[:, e] > 0)) + 30, e].max() for e in range(N)), dev.max()))
     envs.close()
 
