@@ -26,6 +26,9 @@ constexpr int CAR_MAX_SAMPLES = CAR_MAX_TRACK / CAR_SAMPLE_STRIDE;
 constexpr int CAR_MAX_STACK = 8;
 constexpr int CAR_GLYPH_BYTES = 11 * 8 * 4 + 11;
 constexpr int CAR_MAX_CAND = 176;           // road tiles of one frame that can reach the 96x96 window
+constexpr int CAR_SPAN_TILE_ROWS = 32;      // cached scanline rows per road tile polygon ...
+constexpr int CAR_SPAN_KERB_ROWS = 16;      // ... and per kerb quad (larger polygons are scanned in the render kernel)
+constexpr int CAR_SPAN_ROWS = CAR_SPAN_TILE_ROWS + CAR_SPAN_KERB_ROWS;
 constexpr int CAR_MAX_CONTACTS = 8;         // touching car-car fixture pairs kept per env (of 48 possible)
 
 // A road tile, 116 bytes: for the physics the convex hull (CCW, fp32) of the reference's 5 listed
@@ -109,6 +112,9 @@ struct CarDev {
     int32_t* slow_list;       // [n]
     int32_t* slow_count;      // [1]
     uint8_t* deferred;        // [n] 1 = on the slow list this step
+    // ---- per env: scanline span tables of the road polygons in road-map pixels (they depend on the track only, so they
+    //      are built once per reset by car_tile_spans_kernel instead of once per frame): [n][CAR_MAX_TRACK][CAR_SPAN_ROWS] ----
+    short4* tile_spans;
     // ---- per frame (env * players + player): written by car_frame_setup_kernel, read by car_render_kernel ----
     FrameMap* frame_map;      // [n*players]
     uint16_t* frame_cand;     // [n*players][CAR_MAX_CAND] road tiles that can reach the window
@@ -139,6 +145,7 @@ cudaError_t launch_car_step(const CarDev& p, int mode, const float* actions, flo
 // which: 0 = every frame, 1 = envs not deferred to the slow stepping pass, 2 = deferred envs only; advance: move the frame ring on
 cudaError_t launch_car_render(const CarDev& p, int only_done, int which, int advance, uint8_t* obs, uint8_t* term_obs, cudaStream_t s);
 cudaError_t car_raster_init();
+cudaError_t launch_car_tile_spans(const CarDev& p, cudaStream_t s);   // after a full launch_car_reset (auto-reset: see car_frame_setup_kernel)
 size_t car_frame_map_bytes();
 void car_checker_table(int* out);
 cudaError_t launch_car_get_state(const CarDev& p, double* state, cudaStream_t s);

@@ -142,8 +142,9 @@ struct RasterSmem {
 };
 
 // Register polygon (vx, vy)[n] of the frame: id, span-table rows, cell bins.  One thread per polygon.
+// `cache` = 0x80000000 | kind << 16 | tile for a road polygon whose span table is in CarDev::tile_spans, else 0.
 __device__ void add_polygon(RasterSmem& S, const FrameMap& fm, const int* vx, const int* vy, int n, unsigned int key, bool screen,
-                            int car_slot) {
+                            int car_slot, unsigned int cache) {
     int minx = vx[0], maxx = vx[0], miny = vy[0], maxy = vy[0];
 #pragma unroll
     for (int i = 1; i < 8; ++i)
@@ -174,7 +175,8 @@ __device__ void add_polygon(RasterSmem& S, const FrameMap& fm, const int* vx, co
     if (off + rows > POOL_ROWS) { off = NO_TABLE; S.overflow = 1; }
     else for (int r = 0; r < rows; ++r) S.row_owner[off + r] = (uint8_t)id;
     PolyMeta m;
-    m.miny = (short)miny; m.rows = (short)rows; m.off = (unsigned short)off; m.n = (unsigned char)n; m.screen = screen ? 1 : 0; m.key = key; m.pad = 0u;
+    m.miny = (short)miny; m.rows = (short)rows; m.off = (unsigned short)off; m.n = (unsigned char)n; m.screen = screen ? 1 : 0; m.key = key;
+    m.pad = (cache != 0u && rows <= (((cache >> 16) & 1u) ? CAR_SPAN_KERB_ROWS : CAR_SPAN_TILE_ROWS)) ? cache : 0u;
     S.meta[id] = m;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { S.pvx[id][i] = (short)max(-32000, min(32000, vx[i])); S.pvy[id][i] = (short)max(-32000, min(32000, vy[i])); }
@@ -252,6 +254,35 @@ __device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, un
     }
 }
 
+// Scanline span tables of every road polygon (tile, kerb) of env e's track, in road-map pixels: they depend on the track
+// only, so they are scanned once per reset rather than once per frame in the render kernel.  `nthreads` threads, thread
+// `tid` of them; one (tile, table row) per thread and pass.
+__device__ void build_tile_spans(const CarDev& p, int e, int tid, int nthreads) {
+    const int n_track = p.n_track[e];
+    const CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
+    short4* out = p.tile_spans + (size_t)e * CAR_MAX_TRACK * CAR_SPAN_ROWS;
+    for (int item = tid; item < n_track * CAR_SPAN_ROWS; item += nthreads) {
+        const int t = item / CAR_SPAN_ROWS, slot = item % CAR_SPAN_ROWS;
+        const bool kerb = slot >= CAR_SPAN_TILE_ROWS;
+        const int r = kerb ? slot - CAR_SPAN_TILE_ROWS : slot;
+        const CarTile* T = tiles + t;
+        if (kerb && !(T->flags & 2)) continue;
+        const short* vx = kerb ? T->kmx : T->mx;
+        const short* vy = kerb ? T->kmy : T->my;
+        const int n = kerb ? 4 : 5;
+        int miny = vy[0], maxy = vy[0];
+        for (int i = 1; i < n; ++i) { miny = min(miny, (int)vy[i]); maxy = max(maxy, (int)vy[i]); }
+        if (r > maxy - miny) continue;
+        out[(size_t)t * CAR_SPAN_ROWS + slot] = scanline_spans(vx, vy, n, miny + r, maxy);
+    }
+}
+
+// all envs of the shard (crl_car_reset); the auto-reset pass builds the tables of the finished envs in
+// car_frame_setup_kernel instead (no extra launch on the step path)
+__global__ void __launch_bounds__(256) car_tile_spans_kernel(CarDev p) {
+    for (int e = blockIdx.x; e < p.n; e += gridDim.x) build_tile_spans(p, e, threadIdx.x, blockDim.x);
+}
+
 // Per-frame setup, one warp per (env, player) frame: camera and the integer screen -> road-map mapping (lane 0), then
 // the cull of the road tiles against the visible window (all lanes).  Kept out of the render kernel, where these
 // serial steps would stall a whole CTA.
@@ -264,6 +295,7 @@ car_frame_setup_kernel(CarDev p, int only_done, int which) {
     const int e = frame / p.players;
     if (only_done && !p.env_done[e]) return;
     if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
+    if (only_done && frame % p.players == 0) build_tile_spans(p, e, lane, 32);   // the env was just reset: new track
     const CarHullConst* K = p.consts;
     if (lane == 0) {
         // ---- camera_update("rgb_array"): hull.position + R(angle) * (0, 16) ----
@@ -388,11 +420,11 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
             int vx[8], vy[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { vx[i] = (i < 5) ? T.mx[i] : 0; vy[i] = (i < 5) ? T.my[i] : 0; }
-            add_polygon(S, fm, vx, vy, 5, (order << 8) | G[G_ROAD0 + t % 3], false, 0);
+            add_polygon(S, fm, vx, vy, 5, (order << 8) | G[G_ROAD0 + t % 3], false, 0, 0x80000000u | (unsigned)t);
             if (T.flags & 2) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { vx[i] = T.kmx[i]; vy[i] = T.kmy[i]; }
-                add_polygon(S, fm, vx, vy, 4, ((order + 1u) << 8) | ((T.flags & 4) ? G[G_KERB_W] : G[G_KERB_R]), false, 0);
+                add_polygon(S, fm, vx, vy, 4, ((order + 1u) << 8) | ((T.flags & 4) ? G[G_KERB_W] : G[G_KERB_R]), false, 0, 0x80010000u | (unsigned)t);
             }
         } else if (tid >= RASTER_THREADS - p.players * per_car) {
             const int q = RASTER_THREADS - 1 - tid;
@@ -423,7 +455,7 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
                 }
             }
             const uint8_t g = (part < 4) ? G[G_WHEEL] : ((ck == pi) ? G[G_OWN] : G[G_OTHER]);
-            add_polygon(S, fm, vx, vy, n, (order << 8) | g, true, q);
+            add_polygon(S, fm, vx, vy, n, (order << 8) | g, true, q, 0u);
         }
     }
     __syncthreads();
@@ -435,7 +467,13 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
             const int id = S.row_owner[i];
             const PolyMeta m = S.meta[id];
             if (m.off == NO_TABLE || i < (int)m.off || i >= (int)m.off + m.rows) continue;   // tail of a polygon that did not fit
-            S.spans[i] = scanline_spans(S.pvx[id], S.pvy[id], m.n, m.miny + (i - (int)m.off), m.miny + m.rows - 1);
+            const int r = i - (int)m.off;
+            if (m.pad & 0x80000000u) {      // road polygon: its rows were scanned once per reset (car_tile_spans_kernel)
+                const size_t base = ((size_t)e * CAR_MAX_TRACK + (m.pad & 0xFFFFu)) * CAR_SPAN_ROWS + (((m.pad >> 16) & 1u) ? CAR_SPAN_TILE_ROWS : 0);
+                S.spans[i] = p.tile_spans[base + r];
+            } else {
+                S.spans[i] = scanline_spans(S.pvx[id], S.pvy[id], m.n, m.miny + r, m.miny + m.rows - 1);
+            }
         }
     }
     __syncthreads();
@@ -527,6 +565,11 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
             if (tdst) tdst[q] = vv;
         }
     }
+}
+
+cudaError_t launch_car_tile_spans(const CarDev& p, cudaStream_t s) {
+    car_tile_spans_kernel<<<min(p.n, 148 * 8), 256, 0, s>>>(p);
+    return cudaGetLastError();
 }
 
 __global__ void car_ring_advance_kernel(CarDev p, int only_done) {

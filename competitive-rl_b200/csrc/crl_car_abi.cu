@@ -248,6 +248,7 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
         d.frame_map = reinterpret_cast<FrameMap*>(fmraw);
     }
     ALLOC(d.frame_cand, nc * CAR_MAX_CAND); ALLOC(d.frame_ncand, nc);
+    ALLOC(d.tile_spans, n * CAR_MAX_TRACK * CAR_SPAN_ROWS);
     if (P == 2) { ALLOC(d.contacts, n * CAR_MAX_CONTACTS); ALLOC(d.n_contacts, n); ALLOC(d.slow_list, n); ALLOC(d.slow_count, 1); }
     ALLOC(d.deferred, n);
     CarHullConst* kdev = nullptr;
@@ -338,6 +339,7 @@ int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream) {
     CUDA_TRY(cudaMemsetAsync(h->dev.ring_pos, 0xFF, (size_t)h->dev.n * sizeof(int32_t), s));
     CUDA_TRY(cudaMemsetAsync(h->dev.env_done, 0, (size_t)h->dev.n, s));
     LAUNCH(launch_car_reset(h->dev, 0, s), 1);
+    LAUNCH(launch_car_tile_spans(h->dev, s), 1);
     LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, nullptr, s), 3);
     h->was_reset = true;
     return CRL_OK;

@@ -346,3 +346,34 @@ def test_replayed_track_matches_reference_fixture():
         assert np.abs(info.rewards.cpu().numpy()[0] - g["rewards"][t]).max() <= 1e-4, t
         assert np.array_equal(s[:, 23], g["states"][t][:, 23]), t
     envs.close()
+
+
+def test_autoreset_frame_matches_oracle():
+    """The observation an env shows right after its auto-reset (new track, new span tables) against the oracle's
+    rendering of that new track -- and the frames of the following steps."""
+    import car_oracle as C
+    from competitive_rl_b200 import _native
+    N = 4
+    envs = _make("cCarRacing-v0", N, seed=13, max_episode_steps=12)
+    envs.reset()
+    a = torch.zeros((N, 2), device="cuda")
+    a[:, 1] = 0.5
+    for t in range(12):
+        o, r, d, info = envs.step(a)
+    assert bool(d.all())                                             # TimeLimit(12): every env was reset inside this step
+    glyphs = C.load_glyphs(_native.DEFAULT_CAR_GLYPHS)
+    orcs = []
+    for e in range(N):
+        tr = envs.get_track(e)
+        track = np.concatenate([np.zeros((len(tr), 1)), tr], axis=1)
+        orc = C.CarOracleEnv(1, 1, glyphs, render=False)
+        orc.reset(track, C.track_border(track), [0])
+        assert np.array_equal(o[e, 3].cpu().numpy(), orc.observe()[0]), e   # reset observation on the NEW track
+        assert np.array_equal(o[e, 0].cpu().numpy(), orc.observe()[0]), e   # FrameStack.reset: every slot
+        orcs.append(orc)
+    for t in range(6):
+        o, r, d, info = envs.step(a)
+        for e in range(N):
+            orcs[e].step(np.array([[0.0, 0.5]]))
+            assert (o[e, 3].cpu().numpy() != orcs[e].observe()[0]).mean() <= 5e-2, (t, e)
+    envs.close()
