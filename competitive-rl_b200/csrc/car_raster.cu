@@ -131,7 +131,9 @@ struct RasterSmem {
     uint8_t img[CAR_PIX];
     short4 spans[POOL_ROWS];
     uint8_t row_owner[POOL_ROWS];
-    short pvx[MAX_POLY][8], pvy[MAX_POLY][8];
+    short pvx[MAX_POLY - MAX_ROAD_POLY][8], pvy[MAX_POLY - MAX_ROAD_POLY][8];   // vertices of the car polygons (road: CarTile)
+    const CarTile* tiles;                          // the env's tiles (road polygon vertices) and their span tables
+    const short4* env_spans;
     PolyMeta meta[MAX_POLY];
     uint32_t cell_mask[N_CELLS][MASK_WORDS];      // polygons whose screen bounding box touches the cell
     uint8_t chk_x[2 * CAR_W], chk_y[2 * CAR_H];   // is road-map column rx + i / row ry + i inside a checker square
@@ -142,7 +144,8 @@ struct RasterSmem {
 };
 
 // Register polygon (vx, vy)[n] of the frame: id, span-table rows, cell bins.  One thread per polygon.
-// `cache` = 0x80000000 | kind << 16 | tile for a road polygon whose span table is in CarDev::tile_spans, else 0.
+// `cache` = 0x40000000 | kind << 16 | tile for a road polygon (its vertices live in CarTile; bit 31 is added here when its
+// span table fits CarDev::tile_spans), 0 for a car polygon (vertices kept in shared memory).
 __device__ void add_polygon(RasterSmem& S, const FrameMap& fm, const int* vx, const int* vy, int n, unsigned int key, bool screen,
                             int car_slot, unsigned int cache) {
     int minx = vx[0], maxx = vx[0], miny = vy[0], maxy = vy[0];
@@ -176,13 +179,28 @@ __device__ void add_polygon(RasterSmem& S, const FrameMap& fm, const int* vx, co
     else for (int r = 0; r < rows; ++r) S.row_owner[off + r] = (uint8_t)id;
     PolyMeta m;
     m.miny = (short)miny; m.rows = (short)rows; m.off = (unsigned short)off; m.n = (unsigned char)n; m.screen = screen ? 1 : 0; m.key = key;
-    m.pad = (cache != 0u && rows <= (((cache >> 16) & 1u) ? CAR_SPAN_KERB_ROWS : CAR_SPAN_TILE_ROWS)) ? cache : 0u;
+    m.pad = cache | ((cache != 0u && rows <= (((cache >> 16) & 1u) ? CAR_SPAN_KERB_ROWS : CAR_SPAN_TILE_ROWS)) ? 0x80000000u : 0u);
     S.meta[id] = m;
+    if (screen) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { S.pvx[id][i] = (short)max(-32000, min(32000, vx[i])); S.pvy[id][i] = (short)max(-32000, min(32000, vy[i])); }
+        for (int i = 0; i < 8; ++i) { S.pvx[car_slot][i] = (short)max(-32000, min(32000, vx[i])); S.pvy[car_slot][i] = (short)max(-32000, min(32000, vy[i])); }
+    }
     const uint32_t bit = 1u << (id & 31);
     for (int cy = Y0 / CELL; cy <= min(Y1, HUD_TOP - 1) / CELL; ++cy)      // rows under the HUD bar are never walked
         for (int cx = X0 / CELL; cx <= X1 / CELL; ++cx) atomicOr(&S.cell_mask[cy * CELLS_X + cx][id >> 5], bit);
+}
+
+// spans of row V of polygon `id` without the pooled table: from the per-reset cache, or scanned from the vertices
+__device__ __forceinline__ short4 poly_row_spans(const RasterSmem& S, int id, const PolyMeta& m, int V) {
+    const int r = V - m.miny;
+    if (m.pad & 0x80000000u)
+        return S.env_spans[(size_t)(m.pad & 0xFFFFu) * CAR_SPAN_ROWS + (((m.pad >> 16) & 1u) ? CAR_SPAN_TILE_ROWS : 0) + r];
+    if (m.pad & 0x40000000u) {
+        const CarTile* T = S.tiles + (m.pad & 0xFFFFu);
+        const bool kerb = (m.pad >> 16) & 1u;
+        return scanline_spans(kerb ? T->kmx : T->mx, kerb ? T->kmy : T->my, m.n, V, m.miny + m.rows - 1);
+    }
+    return scanline_spans(S.pvx[id - MAX_ROAD_POLY], S.pvy[id - MAX_ROAD_POLY], m.n, V, m.miny + m.rows - 1);
 }
 
 // Pixels of the frame: a warp walks one 8x8 cell at a time, lane = (x, y) and (x, y + 4).  Background: black outside
@@ -196,11 +214,11 @@ __device__ __forceinline__ void test_polygon(const RasterSmem& S, int id, int xa
     if (m.key < ka && m.key < kb) return;
     const int ra = ya - m.miny, rb = yb - m.miny;
     if ((unsigned)ra < (unsigned)m.rows && m.key > ka) {
-        const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + ra] : scanline_spans(S.pvx[id], S.pvy[id], m.n, ya, m.miny + m.rows - 1);
+        const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + ra] : poly_row_spans(S, id, m, ya);
         if ((xa >= sp.x && xa <= sp.y) || (xa >= sp.z && xa <= sp.w)) ka = m.key;
     }
     if ((unsigned)rb < (unsigned)m.rows && m.key > kb) {
-        const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + rb] : scanline_spans(S.pvx[id], S.pvy[id], m.n, yb, m.miny + m.rows - 1);
+        const short4 sp = (!SLOW || m.off != NO_TABLE) ? S.spans[m.off + rb] : poly_row_spans(S, id, m, yb);
         if ((xb >= sp.x && xb <= sp.y) || (xb >= sp.z && xb <= sp.w)) kb = m.key;
     }
 }
@@ -386,7 +404,10 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     if (tid < p.players * 40) S.car_body[tid / 40][tid % 40] = p.body[((size_t)e * p.players + tid / 40) * 40 + tid % 40];
     if (tid < (2 * CAR_W + 2 * CAR_H) / 4) reinterpret_cast<uint32_t*>(S.chk_x)[tid] = 0u;     // chk_x and chk_y are adjacent
     for (int i = tid; i < N_CELLS * MASK_WORDS; i += RASTER_THREADS) (&S.cell_mask[0][0])[i] = 0u;
-    if (tid == 255) { S.n_poly = 0; S.pool_used = 0; S.overflow = 0; }
+    if (tid == 255) {
+        S.n_poly = 0; S.pool_used = 0; S.overflow = 0;
+        S.tiles = tiles; S.env_spans = p.tile_spans + (size_t)e * CAR_MAX_TRACK * CAR_SPAN_ROWS;
+    }
     if (tid >= 240 && tid < 248) {      // HUD inputs (render_indicators_for_pygame :645-670)
         const int k = tid - 240;
         const float* b = p.body + (size_t)frame * 40;
@@ -420,11 +441,11 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
             int vx[8], vy[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) { vx[i] = (i < 5) ? T.mx[i] : 0; vy[i] = (i < 5) ? T.my[i] : 0; }
-            add_polygon(S, fm, vx, vy, 5, (order << 8) | G[G_ROAD0 + t % 3], false, 0, 0x80000000u | (unsigned)t);
+            add_polygon(S, fm, vx, vy, 5, (order << 8) | G[G_ROAD0 + t % 3], false, 0, 0x40000000u | (unsigned)t);
             if (T.flags & 2) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { vx[i] = T.kmx[i]; vy[i] = T.kmy[i]; }
-                add_polygon(S, fm, vx, vy, 4, ((order + 1u) << 8) | ((T.flags & 4) ? G[G_KERB_W] : G[G_KERB_R]), false, 0, 0x80010000u | (unsigned)t);
+                add_polygon(S, fm, vx, vy, 4, ((order + 1u) << 8) | ((T.flags & 4) ? G[G_KERB_W] : G[G_KERB_R]), false, 0, 0x40010000u | (unsigned)t);
             }
         } else if (tid >= RASTER_THREADS - p.players * per_car) {
             const int q = RASTER_THREADS - 1 - tid;
@@ -467,13 +488,7 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
             const int id = S.row_owner[i];
             const PolyMeta m = S.meta[id];
             if (m.off == NO_TABLE || i < (int)m.off || i >= (int)m.off + m.rows) continue;   // tail of a polygon that did not fit
-            const int r = i - (int)m.off;
-            if (m.pad & 0x80000000u) {      // road polygon: its rows were scanned once per reset (car_tile_spans_kernel)
-                const size_t base = ((size_t)e * CAR_MAX_TRACK + (m.pad & 0xFFFFu)) * CAR_SPAN_ROWS + (((m.pad >> 16) & 1u) ? CAR_SPAN_TILE_ROWS : 0);
-                S.spans[i] = p.tile_spans[base + r];
-            } else {
-                S.spans[i] = scanline_spans(S.pvx[id], S.pvy[id], m.n, m.miny + r, m.miny + m.rows - 1);
-            }
+            S.spans[i] = poly_row_spans(S, id, m, m.miny + (i - (int)m.off));   // road: copied from the per-reset tables
         }
     }
     __syncthreads();
