@@ -115,6 +115,7 @@ struct CarDev {
     // ---- per env: scanline span tables of the road polygons in road-map pixels (they depend on the track only, so they
     //      are built once per reset by car_tile_spans_kernel instead of once per frame): [n][CAR_MAX_TRACK][CAR_SPAN_ROWS] ----
     short4* tile_spans;
+    float2* tile_centres;     // [n][CAR_MAX_TRACK] tile centres (= CarTile::cx, cy), contiguous for the per-frame cull
     // ---- per frame (env * players + player): written by car_frame_setup_kernel, read by car_render_kernel ----
     FrameMap* frame_map;      // [n*players]
     uint16_t* frame_cand;     // [n*players][CAR_MAX_CAND] road tiles that can reach the window

@@ -292,6 +292,7 @@ __global__ void car_reset_kernel(CarDev p, int only_done) {
         t.flags = (uint8_t)(1 | (tiles[i].flags & 2) | ((i % 2 == 0) ? 4 : 0));
         t.pad = 0;
         t.cx = (float)x1; t.cy = (float)y1;
+        p.tile_centres[(size_t)e * CAR_MAX_TRACK + i] = make_float2(t.cx, t.cy);
         const double side = signd(b2 - b1);
         t.kx[0] = (float)(x1 + side * CR_TRACK_WIDTH * cos(b1)); t.ky[0] = (float)(y1 + side * CR_TRACK_WIDTH * sin(b1));
         t.kx[1] = (float)(x1 + side * (CR_TRACK_WIDTH + CR_BORDER) * cos(b1)); t.ky[1] = (float)(y1 + side * (CR_TRACK_WIDTH + CR_BORDER) * sin(b1));

@@ -359,7 +359,7 @@ car_frame_setup_kernel(CarDev p, int only_done, int which) {
     // ---- cull: road tiles whose centre, mapped to the screen, lies within the window grown by the tile's reach
     //      (farthest kerb corner 8.7 units = 15.4 px, plus the slack of the integer pipeline) ----
     const int n_track = p.n_track[e];
-    const CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
+    const float2* centres = p.tile_centres + (size_t)e * CAR_MAX_TRACK;
     uint16_t* cand = p.frame_cand + (size_t)frame * CAR_MAX_CAND;
     const double obs_scale = car_obs_scale();
     const float reach = 20.0f;
@@ -368,7 +368,8 @@ car_frame_setup_kernel(CarDev p, int only_done, int which) {
         const int t = t0 + lane;
         bool in = false;
         if (t < n_track) {
-            const float u = (float)(obs_scale * -(double)tiles[t].cx + 5000.0), v = (float)(obs_scale * -(double)tiles[t].cy + 5000.0);
+            const float2 tc = centres[t];                 // coalesced (CarTile is 116 bytes: one sector per lane otherwise)
+            const float u = (float)(obs_scale * -(double)tc.x + 5000.0), v = (float)(obs_scale * -(double)tc.y + 5000.0);
             float X, Y;
             map_to_screen(fm, u, v, X, Y);
             in = X > -reach && X < CAR_W + reach && Y > -reach && Y < CAR_H + reach;

@@ -248,7 +248,7 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
         d.frame_map = reinterpret_cast<FrameMap*>(fmraw);
     }
     ALLOC(d.frame_cand, nc * CAR_MAX_CAND); ALLOC(d.frame_ncand, nc);
-    ALLOC(d.tile_spans, n * CAR_MAX_TRACK * CAR_SPAN_ROWS);
+    ALLOC(d.tile_spans, n * CAR_MAX_TRACK * CAR_SPAN_ROWS); ALLOC(d.tile_centres, n * CAR_MAX_TRACK);
     if (P == 2) { ALLOC(d.contacts, n * CAR_MAX_CONTACTS); ALLOC(d.n_contacts, n); ALLOC(d.slow_list, n); ALLOC(d.slow_count, 1); }
     ALLOC(d.deferred, n);
     CarHullConst* kdev = nullptr;
