@@ -479,6 +479,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
         uint32_t* visited = p.visited + (size_t)ci * 16;
         const int n_track = p.n_track[e];
         const CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
+        const float2* centres = p.tile_centres + (size_t)e * CAR_MAX_TRACK;   // 8-byte stride instead of CarTile's 116
         int step_count = p.step_count[e];
         float inv_dt0 = p.inv_dt0[e];
         const float hull_lcx = K.hull_lcx, hull_lcy = K.hull_lcy;
@@ -577,7 +578,8 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                     if (dx * dx + dy * dy < 36.0f * 36.0f) {
                         const int t1 = min(n_track, (s + 1) * CAR_SAMPLE_STRIDE);
                         for (int t = s * CAR_SAMPLE_STRIDE; t < t1; ++t) {
-                            const float tx = tiles[t].cx - hp.x, ty = tiles[t].cy - hp.y;
+                            const float2 tc = centres[t];
+                            const float tx = tc.x - hp.x, ty = tc.y - hp.y;
                             if (tx * tx + ty * ty < 11.5f * 11.5f && n_cand < 48) cand[n_cand++] = t;
                         }
                     }
@@ -600,7 +602,8 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                 for (int q2 = 0; q2 < n_cand; ++q2) {
                     const int t = cand[q2];
                     const CarTile* Tp = tiles + t;
-                    const float tcx = Tp->cx, tcy = Tp->cy;
+                    const float2 tcen = centres[t];
+                    const float tcx = tcen.x, tcy = tcen.y;
                     bool near_w[4], any_near = false;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
