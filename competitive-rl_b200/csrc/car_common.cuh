@@ -31,12 +31,12 @@ constexpr int CAR_SPAN_KERB_ROWS = 16;      // ... and per kerb quad (larger pol
 constexpr int CAR_SPAN_ROWS = CAR_SPAN_TILE_ROWS + CAR_SPAN_KERB_ROWS;
 constexpr int CAR_MAX_CONTACTS = 8;         // touching car-car fixture pairs kept per env (of 48 possible)
 
-// A road tile, 116 bytes: for the physics the convex hull (CCW, fp32) of the reference's 5 listed
-// vertices; for the renderer the listed vertices and the kerb quad in ROAD-MAP PIXELS, i.e.
+// A road tile, 124 bytes: for the physics the convex hull (CCW, fp32) of the reference's 5 listed
+// vertices, with the edge normals the sensor-overlap test needs; for the renderer the listed vertices and the kerb quad in ROAD-MAP PIXELS, i.e.
 // (int)(obs_scale * -v + 5000) of the fp64 vertex as pygame truncates it (render_road_for_observation_map).
 struct CarTile {
     float px[5], py[5];       // hull vertices (n of them)
-    float kx[4], ky[4];       // kerb quad in world units (valid iff flags & 2)
+    float nx[5], ny[5];       // outward unit normals of the hull edges i -> i + 1 (nx = 3e38: degenerate edge)
     uint8_t n, flags;         // flags: 1 = exists, 2 = has kerb, 4 = white kerb (block_id even)
     uint16_t pad;
     float cx, cy;             // track point (x, y): centre used for culling

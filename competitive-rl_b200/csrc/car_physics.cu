@@ -289,15 +289,20 @@ __global__ void car_reset_kernel(CarDev p, int only_done) {
         }
         t.n = (uint8_t)convex_hull5(vx, vy, t.px, t.py);
         for (int k = t.n; k < 5; ++k) { t.px[k] = t.px[0]; t.py[k] = t.py[0]; }
+        for (int k = 0; k < 5; ++k) {      // edge normals exactly as max_separation derives them (same fp32 operations)
+            t.nx[k] = 3.0e38f; t.ny[k] = 0.f;
+            if (k < t.n) {
+                const int k2 = (k + 1 == t.n) ? 0 : k + 1;
+                const float ex = t.px[k2] - t.px[k], ey = t.py[k2] - t.py[k];
+                const float len = sqrtf(ex * ex + ey * ey);
+                if (!(len < 1e-12f)) { t.nx[k] = ey / len; t.ny[k] = -ex / len; }
+            }
+        }
         t.flags = (uint8_t)(1 | (tiles[i].flags & 2) | ((i % 2 == 0) ? 4 : 0));
         t.pad = 0;
         t.cx = (float)x1; t.cy = (float)y1;
         p.tile_centres[(size_t)e * CAR_MAX_TRACK + i] = make_float2(t.cx, t.cy);
         const double side = signd(b2 - b1);
-        t.kx[0] = (float)(x1 + side * CR_TRACK_WIDTH * cos(b1)); t.ky[0] = (float)(y1 + side * CR_TRACK_WIDTH * sin(b1));
-        t.kx[1] = (float)(x1 + side * (CR_TRACK_WIDTH + CR_BORDER) * cos(b1)); t.ky[1] = (float)(y1 + side * (CR_TRACK_WIDTH + CR_BORDER) * sin(b1));
-        t.kx[2] = (float)(x2 + side * (CR_TRACK_WIDTH + CR_BORDER) * cos(b2)); t.ky[2] = (float)(y2 + side * (CR_TRACK_WIDTH + CR_BORDER) * sin(b2));
-        t.kx[3] = (float)(x2 + side * CR_TRACK_WIDTH * cos(b2)); t.ky[3] = (float)(y2 + side * CR_TRACK_WIDTH * sin(b2));
         {
             const double osc = (10 / (100 / sqrt(96.0))) * 1.8;
             const double kdx[4] = {x1 + side * CR_TRACK_WIDTH * cos(b1), x1 + side * (CR_TRACK_WIDTH + CR_BORDER) * cos(b1),
@@ -381,6 +386,19 @@ __device__ float max_separation(const float* ax, const float* ay, int na, const 
         const float nx = ey / len, ny = -ex / len;
         float mn = 3.4e38f;
         for (int k = 0; k < nb; ++k) mn = fminf(mn, nx * (bx[k] - ax[i]) + ny * (by[k] - ay[i]));
+        best = fmaxf(best, mn);
+    }
+    return best;
+}
+
+// the same with the face normals of A given (nx[i] > 1e38: degenerate edge, skipped like len < 1e-12 above)
+__device__ __forceinline__ float max_separation_n(const float* ax, const float* ay, const float* nx, const float* ny, int na,
+                                                  const float* bx, const float* by, int nb) {
+    float best = -3.4e38f;
+    for (int i = 0; i < na; ++i) {
+        if (nx[i] > 1.0e38f) continue;
+        float mn = 3.4e38f;
+        for (int k = 0; k < nb; ++k) mn = fminf(mn, nx[i] * (bx[k] - ax[i]) + ny[i] * (by[k] - ay[i]));
         best = fmaxf(best, mn);
     }
     return best;
@@ -595,6 +613,17 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                     wx[k][0] = l0.x; wy[k][0] = l0.y; wx[k][1] = l1.x; wy[k][1] = l1.y;
                     wx[k][2] = l2.x; wy[k][2] = l2.y; wx[k][3] = l3.x; wy[k][3] = l3.y;
                 }
+                // face normals of the wheel boxes, once per wheel instead of once per (wheel, tile) pair
+                float wnx[4][4], wny[4][4];
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int i2 = (i + 1) & 3;
+                        const float ex = wx[k][i2] - wx[k][i], ey = wy[k][i2] - wy[k][i];
+                        const float len = sqrtf(ex * ex + ey * ey);
+                        wnx[k][i] = 3.0e38f; wny[k][i] = 0.f;
+                        if (!(len < 1e-12f)) { wnx[k][i] = ey / len; wny[k][i] = -ex / len; }
+                    }
                 // overlap tests, tile-major: each candidate tile is fetched once and tested against the four wheels
                 uint32_t now[4][16];
                 for (int k = 0; k < 4; ++k)
@@ -612,15 +641,15 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                         any_near = any_near || near_w[k];
                     }
                     if (!any_near) continue;
-                    float tpx[5], tpy[5];
+                    float tpx[5], tpy[5], tnx[5], tny[5];
 #pragma unroll
-                    for (int i = 0; i < 5; ++i) { tpx[i] = Tp->px[i]; tpy[i] = Tp->py[i]; }
+                    for (int i = 0; i < 5; ++i) { tpx[i] = Tp->px[i]; tpy[i] = Tp->py[i]; tnx[i] = Tp->nx[i]; tny[i] = Tp->ny[i]; }
                     const int tn = Tp->n;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (!near_w[k]) continue;
-                        const float s1 = max_separation(wx[k], wy[k], 4, tpx, tpy, tn);
-                        const float s2 = max_separation(tpx, tpy, tn, wx[k], wy[k], 4);
+                        const float s1 = max_separation_n(wx[k], wy[k], wnx[k], wny[k], 4, tpx, tpy, tn);
+                        const float s2 = max_separation_n(tpx, tpy, tnx, tny, tn, wx[k], wy[k], 4);
                         if (fmaxf(s1, s2) < 2.0f * B2_POLYGON_RADIUS) now[k][t >> 5] |= 1u << (t & 31);
                     }
                 }
