@@ -377,3 +377,41 @@ def test_autoreset_frame_matches_oracle():
             orcs[e].step(np.array([[0.0, 0.5]]))
             assert (o[e, 3].cpu().numpy() != orcs[e].observe()[0]).mean() <= 5e-2, (t, e)
     envs.close()
+
+
+def test_car_sharding_invariance():
+    """Tracks and spawn order come from an RNG keyed by the GLOBAL env index, and nothing in a step crosses envs: two
+    shards of 128 two-car envs reproduce one batch of 256 bit for bit -- states, rewards, dones, contacts, frames
+    (SURVEY.md section 8e)."""
+    N, T = 256, 60
+    whole = _make("cCarRacingDouble-v0", N, seed=77)
+    lo = _make("cCarRacingDouble-v0", N // 2, seed=77, first_env=0)
+    hi = _make("cCarRacingDouble-v0", N // 2, seed=77, first_env=N // 2)
+    ow = whole.reset()
+    assert torch.equal(ow, torch.cat([lo.reset(), hi.reset()]))
+    lengths = set()
+    for e in (0, 1, N // 2 - 1, N // 2, N - 1):
+        tw = whole.get_track(e)
+        ts = lo.get_track(e) if e < N // 2 else hi.get_track(e - N // 2)
+        assert np.array_equal(tw, ts), e
+        lengths.add(tw.tobytes())
+    assert len(lengths) == 5                                                  # tracks really differ between envs
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    touched = 0
+    for t in range(T):
+        a = torch.rand((N, 2, 2), generator=gen, device="cuda") * 2 - 1
+        a[:, :, 0] *= 0.3
+        ow, rw, dw, iw = whole.step(a)
+        ol, rl, dl, il = lo.step(a[:N // 2])
+        oh, rh, dh, ih = hi.step(a[N // 2:])
+        assert torch.equal(ow, torch.cat([ol, oh])), t
+        assert torch.equal(rw, torch.cat([rl, rh])) and torch.equal(dw, torch.cat([dl, dh]))
+        assert torch.equal(iw.rewards, torch.cat([il.rewards, ih.rewards]))
+        assert torch.equal(whole.get_state(), torch.cat([lo.get_state(), hi.get_state()])), t
+        cw, cl, ch = whole.get_contacts()[0], lo.get_contacts()[0], hi.get_contacts()[0]
+        assert np.array_equal(cw, np.concatenate([cl, ch]))
+        touched += int((cw > 0).sum())
+    assert touched > 0                                                        # the two-pass schedule was exercised
+    for e in (whole, lo, hi):
+        e.check()
+        e.close()
