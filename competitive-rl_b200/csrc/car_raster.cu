@@ -35,12 +35,14 @@ constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 constexpr int MAX_POLY = 240;              // 224 road polygons (tiles + kerbs) + 16 car fixtures of one frame (ids fit a byte)
 constexpr int POOL_ROWS = 2048;            // scanline span table shared by all polygons of a frame
-constexpr int CELL = 8, CELLS_X = CAR_W / CELL, N_CELLS = CELLS_X * (CAR_H / CELL);
+constexpr int CELL = 8, CELLS_X = CAR_W / CELL;
+constexpr int WALK_CELLS = CELLS_X * ((86 + CELL - 1) / CELL);   // cells with rows above the HUD bar (HUD_TOP = 86): 11 rows of 12
 constexpr int MASK_WORDS = (MAX_POLY + 31) / 32;   // per-cell bitmask over the polygon ids
 constexpr int CAR_WORD = MASK_WORDS - 1;   // ids CAR_WORD * 32 .. are the car fixtures (screen space); below: road (map space)
 constexpr int MAX_ROAD_POLY = CAR_WORD * 32;
 constexpr unsigned short NO_TABLE = 0xFFFFu;
 constexpr int HUD_TOP = 86;                // (int)(H - 4 * (H / 40.0)) = (int)86.4: first row of the black HUD bar
+constexpr int HUD_WARP = 5;                // the warp that paints the HUD (it has no other work unless a frame has > 160 road tiles)
 
 __constant__ float c_hull_poly[4][8][2] = {
     {{-60, +130}, {+60, +130}, {+60, +110}, {-60, +110}},
@@ -135,12 +137,13 @@ struct RasterSmem {
     const CarTile* tiles;                          // the env's tiles (road polygon vertices) and their span tables
     const short4* env_spans;
     PolyMeta meta[MAX_POLY];
-    uint32_t cell_mask[N_CELLS][MASK_WORDS];      // polygons whose screen bounding box touches the cell
+    uint32_t cell_mask[WALK_CELLS][MASK_WORDS];      // polygons whose screen bounding box touches the cell
     uint8_t chk_x[2 * CAR_W], chk_y[2 * CAR_H];   // is road-map column rx + i / row ry + i inside a checker square
     float car_body[CAR_MAX_PLAYERS][40];
     double hud_vals[8];
     FrameMap fm;
     int n_poly, pool_used, overflow;
+    int copy_next, hud_late;                       // ring -> observation chunk counter; 1 = an indicator reaches above the bar
 };
 
 // Register polygon (vx, vy)[n] of the frame: id, span-table rows, cell bins.  One thread per polygon.
@@ -203,7 +206,7 @@ __device__ __forceinline__ short4 poly_row_spans(const RasterSmem& S, int id, co
     return scanline_spans(S.pvx[id - MAX_ROAD_POLY], S.pvy[id - MAX_ROAD_POLY], m.n, V, m.miny + m.rows - 1);
 }
 
-// Pixels of the frame: a warp walks one 8x8 cell at a time, lane = (x, y) and (x, y + 4).  Background: black outside
+// Pixels of the frame above the HUD bar: a warp walks one 8x8 cell at a time, lane = (x, y) and (x, y + 4).  Background: black outside
 // the source crop, else grass / checker by road-map pixel; then the polygons binned to the cell, largest key wins.
 // SLOW (the span pool overflowed): polygons without a table get their spans recomputed per pixel.
 // one polygon against the two pixels of a lane; (xa, ya) / (xb, yb) in the polygon's coordinate system
@@ -225,7 +228,7 @@ __device__ __forceinline__ void test_polygon(const RasterSmem& S, int id, int xa
 
 template <bool SLOW>
 __device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, unsigned int g_grass, unsigned int g_check,
-                                           unsigned int g_hud, int warp, int lane) {
+                                           int warp, int lane) {
     uint8_t* img = S.img;
     const int n_words = (min(S.n_poly, MAX_ROAD_POLY) + 31) >> 5;
     const int lx = lane & 7, ly = lane >> 3;
@@ -236,11 +239,10 @@ __device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, un
     const int ldy = fm.cy0 + fm.isin * (lx - fm.bx) + fm.icos * (ly - fm.by);
     // cells warp, warp + 8, ...: 12 cells per row of cells, so +8 cells = +64 px in x, wrapping into the next row
     int cx = warp * CELL, cy = 0;
-    for (int cell = warp; cell < N_CELLS; cell += RASTER_WARPS, cx += RASTER_WARPS * CELL) {
+    for (int cell = warp; cell < WALK_CELLS; cell += RASTER_WARPS, cx += RASTER_WARPS * CELL) {
         if (cx >= CAR_W) { cx -= CAR_W; cy += CELL; }
         const int X = cx + lx, Ya = cy + ly, Yb = Ya + 4;
         uint8_t* pa = img + Ya * CAR_W + X;
-        if (cy >= HUD_TOP) { pa[0] = (uint8_t)g_hud; pa[4 * CAR_W] = (uint8_t)g_hud; continue; }   // whole cell under the HUD bar
         const int dxa = ldx + fm.icos * cx - fm.isin * cy, dya = ldy + fm.isin * cx + fm.icos * cy;
         const int dxb = dxa - 4 * fm.isin, dyb = dya + 4 * fm.icos;
         const int ua = (dxa >> 16) & 255, va = (dya >> 16) & 255, ub = (dxb >> 16) & 255, vb = (dyb >> 16) & 255;   // 0..191 (see above)
@@ -263,12 +265,8 @@ __device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, un
                 test_polygon<SLOW>(S, id, X, Ya, X, Yb, ka, kb);
             }
         }
-        if (cy + CELL > HUD_TOP) {                          // the row of cells the HUD bar starts in
-            if (Ya >= HUD_TOP) ka = g_hud;
-            if (Yb >= HUD_TOP) kb = g_hud;
-        }
-        pa[0] = (uint8_t)(ka & 255u);
-        pa[4 * CAR_W] = (uint8_t)(kb & 255u);
+        pa[0] = (uint8_t)(ka & 255u);                        // Ya <= 83
+        if (Yb < HUD_TOP) pa[4 * CAR_W] = (uint8_t)(kb & 255u);   // rows 86.. belong to the HUD bar (painted by the HUD warp)
     }
 }
 
@@ -385,6 +383,48 @@ car_frame_setup_kernel(CarDev p, int only_done, int which) {
     }
 }
 
+// HUD indicators and reward text (render_indicators_for_pygame :645-670), one warp, in paint order
+__device__ void paint_hud_indicators(const RasterSmem& S, const uint8_t* glyphs, const uint8_t* G, uint8_t* img, int lane) {
+    const double W = CAR_W, H = CAR_H, s = W / 40.0, h = H / 40.0;
+    hud_rect(img, 5 * s, H - h, s, h * (-0.02 * S.hud_vals[0]), G[G_BLUE], lane, 32);
+    __syncwarp();
+    for (int k = 0; k < 4; ++k) {
+        hud_rect(img, (7 + k) * s, H - h, s, h * (-0.01 * S.hud_vals[1 + k]), k < 2 ? G[G_BLUE] : G[G_BLUE2], lane, 32);
+        __syncwarp();
+    }
+    hud_rect(img, 20 * s, H - 2 * h, s * (10.0 * S.hud_vals[5]), 2 * h, G[G_GREEN], lane, 32);
+    __syncwarp();
+    hud_rect(img, 30 * s, H - 2 * h, s * (0.8 * S.hud_vals[6]), 2 * h, G[G_RED], lane, 32);
+    __syncwarp();
+    if (glyphs != nullptr) {     // draw_text("%05.0f" % reward) at (W/100, H - H/20): lane = one pixel of the 4x8 glyph cell
+        // "%05.0f": round half to even, sign kept for negative values, zero padded to width 5
+        const double rv = S.hud_vals[7];
+        double mag = rint(fabs(rv));
+        char digits[24];
+        int nd = 0;
+        if (mag == 0) digits[nd++] = 0;
+        while (mag >= 1 && nd < 20) { const double qd = floor(mag / 10.0); digits[nd++] = (char)(mag - qd * 10.0); mag = qd; }
+        const int neg = (rv < 0 || (rv == 0 && signbit(rv))) ? 1 : 0;
+        const int body = nd + neg;
+        int pen = (int)(W / 100);
+        const int y0 = (int)(H - H / 20);
+        const int pad = 5 > body ? 5 - body : 0;
+        const int gx = lane & 3, gy = lane >> 2;
+        for (int i = 0; i < body + pad; ++i) {
+            int gi;
+            if (neg && i == 0) gi = 10;
+            else if (i < neg + pad) gi = 0;
+            else gi = digits[nd - 1 - (i - neg - pad)];
+            if (glyphs[(gi * 8 + gy) * 4 + gx]) {
+                const int px = pen + gx, py = y0 + gy;
+                if (px >= 0 && px < CAR_W && py >= 0 && py < CAR_H) img[py * CAR_W + px] = G[G_TEXT];
+            }
+            pen += glyphs[11 * 8 * 4 + gi];
+            __syncwarp();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(RASTER_THREADS, 5)
 car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs, uint8_t* __restrict__ term_obs) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -401,12 +441,18 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     const double obs_scale = car_obs_scale();
     const int n_track = p.n_track[e];
     const CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
+    const int C = p.c;
+    uint8_t* ring = p.ring + (size_t)frame * C * CAR_PIX;
+    const bool fill_all = only_done != 0 || p.ring_pos[e] < 0;
+    const int newest = fill_all ? C - 1 : (p.ring_pos[e] + 1) % C;
+    uint8_t* out = obs + (size_t)frame * C * CAR_PIX;
+    uint8_t* tout = (term_obs != nullptr && !only_done && p.env_done[e]) ? term_obs + (size_t)frame * C * CAR_PIX : nullptr;
 
     if (tid < p.players * 40) S.car_body[tid / 40][tid % 40] = p.body[((size_t)e * p.players + tid / 40) * 40 + tid % 40];
     if (tid < (2 * CAR_W + 2 * CAR_H) / 4) reinterpret_cast<uint32_t*>(S.chk_x)[tid] = 0u;     // chk_x and chk_y are adjacent
-    for (int i = tid; i < N_CELLS * MASK_WORDS; i += RASTER_THREADS) (&S.cell_mask[0][0])[i] = 0u;
+    for (int i = tid; i < WALK_CELLS * MASK_WORDS; i += RASTER_THREADS) (&S.cell_mask[0][0])[i] = 0u;
     if (tid == 255) {
-        S.n_poly = 0; S.pool_used = 0; S.overflow = 0;
+        S.n_poly = 0; S.pool_used = 0; S.overflow = 0; S.copy_next = 0; S.hud_late = 0;
         S.tiles = tiles; S.env_spans = p.tile_spans + (size_t)e * CAR_MAX_TRACK * CAR_SPAN_ROWS;
     }
     if (tid >= 240 && tid < 248) {      // HUD inputs (render_indicators_for_pygame :645-670)
@@ -480,6 +526,47 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
             add_polygon(S, fm, vx, vy, n, (order << 8) | g, true, q, 0u);
         }
     }
+    // ---- meanwhile (nothing here touches what the polygon threads write): warp HUD_WARP paints the HUD bar -- rows 86..95,
+    //      which the pixel pass below never writes -- and every warp, as soon as it is free, copies chunks of the C - 1
+    //      older frames ring -> observation.  FrameStack: the new frame enters the ring; the observation is the ring
+    //      oldest -> newest.  After a reset (only_done pass, or the very first render) every slot holds the reset frame.
+    //      Output layout: [env][players * C][96][96]: player-major channel blocks (FlattenMultiAgentObservation
+    //      concatenates the players' stacks on the channel axis), oldest frame first within a player. ----
+    uint8_t* img = S.img;
+    __syncwarp();
+    if (warp == HUD_WARP) {
+        // the indicators are painted after the scene in the reference (render_indicators_for_pygame :645-670); they stay inside
+        // the bar unless a vertical one is taller than 7 px (speed >= 146, wheel omega >= 292): then they wait for the scene
+        const double H = CAR_H, h = H / 40.0;
+        bool late = false;
+        for (int k = 0; k < 5; ++k) {
+            const int Y = (int)(H - h), Hh = (int)(h * ((k == 0 ? -0.02 : -0.01) * S.hud_vals[k]));
+            late = late || min(Y, Y + Hh - 1) < HUD_TOP;
+        }
+        const uint32_t g4 = 0x01010101u * (uint32_t)G[G_HUD];
+        for (int q = lane; q < (CAR_H - HUD_TOP) * CAR_W / 16; q += 32) reinterpret_cast<uint4*>(img + HUD_TOP * CAR_W)[q] = make_uint4(g4, g4, g4, g4);
+        __syncwarp();
+        if (late) { if (lane == 0) S.hud_late = 1; }
+        else paint_hud_indicators(S, p.glyphs, G, img, lane);
+        __syncwarp();
+    }
+    if (!fill_all) {
+        constexpr int PER_SLOT = CAR_PIX / 16 / 64;                // chunks of 64 uint4 (two per lane) per frame: 9
+        const int n_chunks = (C - 1) * PER_SLOT;
+        for (;;) {
+            int ch = 0;
+            if (lane == 0) ch = atomicAdd(&S.copy_next, 1);
+            ch = __shfl_sync(0xffffffffu, ch, 0);
+            if (ch >= n_chunks) break;
+            const int sl = ch / PER_SLOT, q = (ch % PER_SLOT) * 64 + lane;       // slot sl of the output = the sl-th oldest frame
+            const int rs = (newest + 1 + sl) % C;
+            const uint4* rsrc = reinterpret_cast<const uint4*>(ring + (size_t)rs * CAR_PIX);
+            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)sl * CAR_PIX);
+            const uint4 v0 = rsrc[q], v1 = rsrc[q + 32];
+            dst[q] = v0; dst[q + 32] = v1;
+            if (tout) { uint4* tdst = reinterpret_cast<uint4*>(tout + (size_t)sl * CAR_PIX); tdst[q] = v0; tdst[q + 32] = v1; }
+        }
+    }
     __syncthreads();
     if (tid == 0 && S.overflow != 0) atomicAdd(p.overrun + (S.overflow == 2 ? 1 : 2), 1);   // [1] polygons dropped, [2] frames with a full span pool (slow path)
     // ---- span tables: one (polygon, row) per thread and pass ----
@@ -493,76 +580,14 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
         }
     }
     __syncthreads();
-    // ---- pixels ----
-    uint8_t* img = S.img;
-    if (S.overflow == 0) walk_cells<false>(S, fm, G[G_GRASS], G[G_CHECK], G[G_HUD], warp, lane);
-    else walk_cells<true>(S, fm, G[G_GRASS], G[G_CHECK], G[G_HUD], warp, lane);
+    // ---- pixels above the HUD bar ----
+    if (S.overflow == 0) walk_cells<false>(S, fm, G[G_GRASS], G[G_CHECK], warp, lane);
+    else walk_cells<true>(S, fm, G[G_GRASS], G[G_CHECK], warp, lane);
     __syncthreads();
-    // ---- HUD indicators and text (painted after the scene, in order, on top of the black bar that the pixel pass already
-    //      laid down) by warp 0, while the other warps copy the older frames of the stack ----
-    // FrameStack: the new frame enters the ring; the observation is the ring oldest -> newest.  After a reset
-    // (only_done pass, or the very first render) every slot holds the reset frame.
-    // output layout: [env][players * C][96][96]: player-major channel blocks (FlattenMultiAgentObservation
-    // concatenates the players' stacks on the channel axis), oldest frame first within a player
-    const int C = p.c;
-    uint8_t* ring = p.ring + (size_t)frame * C * CAR_PIX;
-    const bool fill_all = only_done != 0 || p.ring_pos[e] < 0;
-    const int newest = fill_all ? C - 1 : (p.ring_pos[e] + 1) % C;
-    uint8_t* out = obs + (size_t)frame * C * CAR_PIX;
-    uint8_t* tout = (term_obs != nullptr && !only_done && p.env_done[e]) ? term_obs + (size_t)frame * C * CAR_PIX : nullptr;
-    if (warp == 0) {
-        const double W = CAR_W, H = CAR_H, s = W / 40.0, h = H / 40.0;
-        hud_rect(img, 5 * s, H - h, s, h * (-0.02 * S.hud_vals[0]), G[G_BLUE], lane, 32);
-        __syncwarp();
-        for (int k = 0; k < 4; ++k) {
-            hud_rect(img, (7 + k) * s, H - h, s, h * (-0.01 * S.hud_vals[1 + k]), k < 2 ? G[G_BLUE] : G[G_BLUE2], lane, 32);
-            __syncwarp();
-        }
-        hud_rect(img, 20 * s, H - 2 * h, s * (10.0 * S.hud_vals[5]), 2 * h, G[G_GREEN], lane, 32);
-        __syncwarp();
-        hud_rect(img, 30 * s, H - 2 * h, s * (0.8 * S.hud_vals[6]), 2 * h, G[G_RED], lane, 32);
-        __syncwarp();
-        if (p.glyphs != nullptr) {     // draw_text("%05.0f" % reward) at (W/100, H - H/20): lane = one pixel of the 4x8 glyph cell
-            // "%05.0f": round half to even, sign kept for negative values, zero padded to width 5
-            const double rv = S.hud_vals[7];
-            double mag = rint(fabs(rv));
-            char digits[24];
-            int nd = 0;
-            if (mag == 0) digits[nd++] = 0;
-            while (mag >= 1 && nd < 20) { const double qd = floor(mag / 10.0); digits[nd++] = (char)(mag - qd * 10.0); mag = qd; }
-            const int neg = (rv < 0 || (rv == 0 && signbit(rv))) ? 1 : 0;
-            const int body = nd + neg;
-            int pen = (int)(W / 100);
-            const int y0 = (int)(H - H / 20);
-            const int pad = 5 > body ? 5 - body : 0;
-            const int gx = lane & 3, gy = lane >> 2;
-            for (int i = 0; i < body + pad; ++i) {
-                int gi;
-                if (neg && i == 0) gi = 10;
-                else if (i < neg + pad) gi = 0;
-                else gi = digits[nd - 1 - (i - neg - pad)];
-                if (p.glyphs[(gi * 8 + gy) * 4 + gx]) {
-                    const int px = pen + gx, py = y0 + gy;
-                    if (px >= 0 && px < CAR_W && py >= 0 && py < CAR_H) img[py * CAR_W + px] = G[G_TEXT];
-                }
-                pen += p.glyphs[11 * 8 * 4 + gi];
-                __syncwarp();
-            }
-        }
-    } else if (!fill_all) {
-        for (int sl = 0; sl < C - 1; ++sl) {                      // the C - 1 older frames, oldest first
-            const int rs = (newest + 1 + sl) % C;
-            const uint4* rsrc = reinterpret_cast<const uint4*>(ring + (size_t)rs * CAR_PIX);
-            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)sl * CAR_PIX);
-            uint4* tdst = tout ? reinterpret_cast<uint4*>(tout + (size_t)sl * CAR_PIX) : nullptr;
-            for (int q = tid - 32; q < CAR_PIX / 16; q += RASTER_THREADS - 32) {
-                const uint4 vv = rsrc[q];
-                dst[q] = vv;
-                if (tdst) tdst[q] = vv;
-            }
-        }
+    if (S.hud_late) {                                              // uniform over the CTA
+        if (warp == HUD_WARP) paint_hud_indicators(S, p.glyphs, G, img, lane);
+        __syncthreads();
     }
-    __syncthreads();
     const uint4* src = reinterpret_cast<const uint4*>(img);
     if (fill_all) {
         for (int sl = 0; sl < C; ++sl) {

@@ -415,3 +415,54 @@ def test_car_sharding_invariance():
     for e in (whole, lo, hi):
         e.check()
         e.close()
+
+
+def test_hud_bars_taller_than_the_bar_are_painted_over_the_scene():
+    """render_indicators_for_pygame paints after the scene, so a wheel-speed bar taller than the 7 rows between its base
+    and the top of the black HUD bar (wheel omega >= 292 rad/s: ~8 s of full throttle) covers scene pixels.  The raster
+    kernel paints the HUD early unless that happens; this drives the exception and checks those pixels against the
+    oracle's frame and against the bar geometry computed from the GPU's own state."""
+    import car_oracle as C
+    from competitive_rl_b200 import _native
+    N, T = 6, 440
+    rng = np.random.RandomState(11)
+    draws = np.zeros((N, 4, 24))
+    tracks = []
+    for e in range(N):
+        tr, bd, d = C.make_track(rng)
+        draws[e, :] = d
+        tracks.append((tr, bd))
+    birth = np.zeros((N, 4, 1), np.int32)
+    envs = _make("cCarRacing-v0", N, track_draws=draws, birth=birth)
+    glyphs = C.load_glyphs(_native.DEFAULT_CAR_GLYPHS)
+    orcs = [C.CarOracleEnv(1, 1, glyphs, render=False) for _ in range(N)]
+    envs.reset()
+    for e, o in enumerate(orcs):
+        o.reset(*tracks[e], [0])
+    a = np.tile(np.array([[0.0, 1.0]], np.float32), (N, 1))
+    checked, alive = 0, np.ones(N, bool)
+    for t in range(T):
+        obs, r, d, info = envs.step(a)
+        alive &= ~d.cpu().numpy().reshape(N).astype(bool)      # a car that left the playfield was auto-reset: drop the env
+        for e in range(N):
+            orcs[e].step(a[e].astype(np.float64))
+        if t < 400 or t % 8:
+            continue
+        sg, og = envs.get_state().cpu().numpy(), obs.cpu().numpy()
+        for e in np.nonzero(alive)[0]:
+            so, oo = orcs[e].get_state(), None
+            for k in (2, 3):                                   # rear wheels: bars at x = int((7 + k) * 2.4), 2 px wide
+                hh = int(2.4 * (-0.01 * sg[e, 0, 7 + 4 * k]))
+                top = 93 + hh - 1
+                if top >= 86:
+                    continue
+                x = int((7 + k) * 2.4)
+                patch = og[e, 3, top:91, x:x + 2]
+                assert (patch == og[e, 3, 89, x]).all() and og[e, 3, 89, x] not in (0, og[e, 3, top - 1, x]), (t, e, k)
+                if int(2.4 * (-0.01 * so[0, 7 + 4 * k])) == hh:
+                    oo = orcs[e].observe() if oo is None else oo
+                    assert np.array_equal(og[e, 3, top - 1:96, x - 1:x + 3], oo[0][top - 1:96, x - 1:x + 3]), (t, e, k)
+                    checked += 1
+    assert checked > 0
+    envs.check()
+    envs.close()
