@@ -403,7 +403,12 @@ __device__ void paint_hud_indicators(const RasterSmem& S, const uint8_t* glyphs,
         char digits[24];
         int nd = 0;
         if (mag == 0) digits[nd++] = 0;
-        while (mag >= 1 && nd < 20) { const double qd = floor(mag / 10.0); digits[nd++] = (char)(mag - qd * 10.0); mag = qd; }
+        if (mag < 2.0e9) {                                    // every reward in practice: integer digits (exact, no fp64 divisions)
+            unsigned int mi = (unsigned int)mag;
+            while (mi != 0u) { const unsigned int qi = mi / 10u; digits[nd++] = (char)(mi - qi * 10u); mi = qi; }
+        } else {
+            while (mag >= 1 && nd < 20) { const double qd = floor(mag / 10.0); digits[nd++] = (char)(mag - qd * 10.0); mag = qd; }
+        }
         const int neg = (rv < 0 || (rv == 0 && signbit(rv))) ? 1 : 0;
         const int body = nd + neg;
         int pen = (int)(W / 100);
@@ -430,7 +435,7 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     extern __shared__ __align__(16) uint8_t smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
     const int frame = blockIdx.x;                     // env * players + player
-    const int e = frame / p.players, pi = frame % p.players;
+    const int e = (p.players == 2) ? frame >> 1 : frame, pi = (p.players == 2) ? frame & 1 : 0;   // players is 1 or 2
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (only_done && !p.env_done[e]) return;
     if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
@@ -444,11 +449,12 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     const int C = p.c;
     uint8_t* ring = p.ring + (size_t)frame * C * CAR_PIX;
     const bool fill_all = only_done != 0 || p.ring_pos[e] < 0;
-    const int newest = fill_all ? C - 1 : (p.ring_pos[e] + 1) % C;
+    int newest = C - 1;
+    if (!fill_all) { newest = p.ring_pos[e] + 1; if (newest >= C) newest = 0; }
     uint8_t* out = obs + (size_t)frame * C * CAR_PIX;
     uint8_t* tout = (term_obs != nullptr && !only_done && p.env_done[e]) ? term_obs + (size_t)frame * C * CAR_PIX : nullptr;
 
-    if (tid < p.players * 40) S.car_body[tid / 40][tid % 40] = p.body[((size_t)e * p.players + tid / 40) * 40 + tid % 40];
+    if (tid < p.players * 40) (&S.car_body[0][0])[tid] = p.body[(size_t)e * p.players * 40 + tid];   // [player][40], contiguous on both sides
     if (tid < (2 * CAR_W + 2 * CAR_H) / 4) reinterpret_cast<uint32_t*>(S.chk_x)[tid] = 0u;     // chk_x and chk_y are adjacent
     for (int i = tid; i < WALK_CELLS * MASK_WORDS; i += RASTER_THREADS) (&S.cell_mask[0][0])[i] = 0u;
     if (tid == 255) {
@@ -559,7 +565,8 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
             ch = __shfl_sync(0xffffffffu, ch, 0);
             if (ch >= n_chunks) break;
             const int sl = ch / PER_SLOT, q = (ch % PER_SLOT) * 64 + lane;       // slot sl of the output = the sl-th oldest frame
-            const int rs = (newest + 1 + sl) % C;
+            int rs = newest + 1 + sl;                             // < 2 C
+            if (rs >= C) rs -= C;
             const uint4* rsrc = reinterpret_cast<const uint4*>(ring + (size_t)rs * CAR_PIX);
             uint4* dst = reinterpret_cast<uint4*>(out + (size_t)sl * CAR_PIX);
             const uint4 v0 = rsrc[q], v1 = rsrc[q + 32];
