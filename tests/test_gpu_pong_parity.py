@@ -213,3 +213,9 @@ def test_full_size_properties():
         assert torch.equal(o[1][:, :, :9], o[0][:, :, :9])
     assert not torch.equal(o[0][0, 3], first)
     envs.close()
+
+
+def test_survey_known_answer_rollout():
+    """SURVEY.md section 8(c) known-answer rollout (hand-derived from PongGame): the CUDA path through the C ABI."""
+    from test_oracle_golden import kat_rollout
+    kat_rollout(lambda serves: _make("cPongDouble-v0", 1, 84, None, serves))
