@@ -427,7 +427,8 @@ int crl_pong_check(crl_pong* h, void* stream) {
     int32_t flag = 0;
     CUDA_TRY(cudaMemcpyAsync(&flag, h->dev.serve_overrun, sizeof flag, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    if (flag) return fail(CRL_E_SERVES, "injected serve table exhausted");
+    if (flag & 2) return fail(CRL_E_INVALID, "an action outside {0, 1, 2} (cPongDouble: or 999) was passed to step; it was played as 1 (stay)");
+    if (flag & 1) return fail(CRL_E_SERVES, "injected serve table exhausted");
     return CRL_OK;
 }
 

@@ -39,7 +39,7 @@ __device__ __forceinline__ void ball_reset(const PongDev& p, int e, Game& g) {
     if (p.serves != nullptr) {
         int k = g.serve_count;
         if (k >= p.serves_k) {
-            *p.serve_overrun = 1;
+            atomicOr(p.serve_overrun, 1);
             k = p.serves_k - 1;
         }
         const double2 s = reinterpret_cast<const double2*>(p.serves)[(size_t)e * p.serves_k + k];
@@ -242,6 +242,15 @@ pong_step_kernel(PongDev p, const int32_t* __restrict__ actions, float* __restri
         a_right = a.y;
     } else {
         a_left = actions[e];
+    }
+    // The reference rejects anything else (assert action_space.contains, :42; BAT_DIRECTIONS[a], :124/:134).  A device
+    // kernel cannot raise: the step treats the action as "stay" and crl_pong_check reports it.
+    const bool ok_left = (unsigned)a_left <= 2u || (p.n_agents == 2 && a_left == CHEAT_CODES);
+    const bool ok_right = (unsigned)a_right <= 2u || (p.n_agents == 2 && a_right == CHEAT_CODES);
+    if (!ok_left || !ok_right) {
+        atomicOr(p.serve_overrun, 2);
+        if (!ok_left) a_left = 1;
+        if (!ok_right) a_right = 1;
     }
     RenderState buf0 = p.skipbuf[e], buf1 = p.skipbuf[(size_t)p.n + e];
     int total0 = 0, total1 = 0;

@@ -320,9 +320,18 @@ class CudaPongVecEnv(VecEnv):
     def _coerce_actions(self, actions):
         want = self._actions.shape
         if isinstance(actions, torch.Tensor):
-            a = actions
+            a = actions         # device-resident actions are validated on the device: see check()
         else:
-            a = torch.as_tensor(np.asarray(actions))
+            arr = np.asarray(actions)
+            # the reference raises on anything else: assert action_space.contains (cPong, base_pong_env.py:42),
+            # BAT_DIRECTIONS[a] IndexError (cPongDouble, :124/:134; Python's negative indices are not honoured here)
+            bad = (arr < 0) | (arr > 2)
+            if self.n_agents == 2:
+                bad &= arr != 999
+            if bad.any():
+                raise (IndexError if self.n_agents == 2 else AssertionError)(
+                    "invalid Pong action %r (valid: 0, 1, 2%s)" % (arr[bad].ravel()[0].item(), ", 999" if self.n_agents == 2 else ""))
+            a = torch.as_tensor(arr)
         if tuple(a.shape) != tuple(want):
             a = a.reshape(want)
         self._actions.copy_(a, non_blocking=True)   # casts to int32 and moves to the device

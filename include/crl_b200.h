@@ -141,7 +141,10 @@ int crl_pong_random_actions(int32_t* actions_dev, int32_t n_values, uint64_t see
 int crl_pong_get_stats(crl_pong* h, uint64_t* stats_host, void* stream);
 
 /* Number of kernel launches this library has issued from this process (bench.py's
- * gpu_launches) and a checked flag for serve-table overrun (synchronises). */
+ * gpu_launches), and the deferred error check (synchronises): CRL_E_SERVES after a
+ * serve-table overrun, CRL_E_INVALID after a step saw an action outside {0, 1, 2}
+ * (cPongDouble: or 999) -- the reference asserts / raises IndexError there
+ * (pong/base_pong_env.py:42, :124, :134); the device step plays it as 1 (stay). */
 uint64_t crl_launch_count(void);
 int crl_pong_check(crl_pong* h, void* stream);
 

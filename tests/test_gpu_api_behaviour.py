@@ -171,3 +171,36 @@ def test_evaluate_two_policies_in_batch_matches_host_bookkeeping():
     assert g0 == r0 and g1 == r1
     assert g0[0] + g0[1] + g0[2] >= EPISODES and g0[0] > g0[2]      # the rule-based bat beats a bat that never moves
     envs.close()
+
+
+def test_invalid_actions_are_rejected():
+    """The reference asserts action_space.contains (cPong-v0) / indexes BAT_DIRECTIONS (cPongDouble-v0): host actions are
+    rejected before the step; device-resident ones are played as "stay" and reported by check()."""
+    from competitive_rl_b200 import make_envs
+    from competitive_rl_b200._native import CrlError
+    single = make_envs("cPong-v0", num_envs=4, resized_dim=84, frame_stack=4, log_dir=None)
+    single.reset()
+    with pytest.raises(AssertionError):
+        single.step(np.array([0, 1, 2, 3]))
+    with pytest.raises(AssertionError):
+        single.step(np.array([0, 999, 2, 1]))                  # the cheat code exists only in the two-player env
+    single.step(np.array([0, 1, 2, 1]))
+    single.check()
+    single.close()
+    double = make_envs("cPongDouble-v0", num_envs=4, resized_dim=84, frame_stack=None, log_dir=None)
+    double.reset()
+    with pytest.raises(IndexError):
+        double.step(np.array([[0, 1], [2, 3], [1, 1], [1, 1]]))
+    double.step(np.array([[0, 999], [999, 2], [1, 1], [1, 1]]))
+    double.check()
+    s0 = double.get_state().clone()
+    double.step(torch.tensor([[1, 1], [1, 1], [7, 1], [1, -1]], dtype=torch.int32, device="cuda"))   # not validated on the host
+    twin = make_envs("cPongDouble-v0", num_envs=4, resized_dim=84, frame_stack=None, log_dir=None)
+    twin.reset()
+    twin.set_state(s0)
+    twin.step(np.ones((4, 2), np.int32))
+    assert torch.equal(double.get_state()[:, 4:6], twin.get_state()[:, 4:6])      # the bad actions moved no bat
+    with pytest.raises(CrlError, match="action outside"):
+        double.check()
+    double.close()
+    twin.close()
