@@ -22,6 +22,7 @@ EXPORTS = [
     "crl_car_create", "crl_car_destroy", "crl_car_load_glyphs", "crl_car_inject_tracks", "crl_car_load_tracks", "crl_car_reset",
     "crl_car_step", "crl_car_step_state", "crl_car_render_obs", "crl_car_get_state", "crl_car_get_track",
     "crl_car_random_actions", "crl_car_get_stats", "crl_car_get_contacts", "crl_car_check",
+    "crl_car_seed", "crl_car_step_host", "crl_car_set_elapsed",
 ]
 
 
@@ -37,6 +38,7 @@ class CarConfig(ctypes.Structure):
     _fields_ = [
         ("num_envs", ctypes.c_int32), ("num_players", ctypes.c_int32), ("frame_stack", ctypes.c_int32),
         ("action_repeat", ctypes.c_int32), ("max_episode_steps", ctypes.c_int32), ("device", ctypes.c_int32),
+        ("done_mode", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("seed", ctypes.c_uint64), ("first_env", ctypes.c_int64),
     ]
 
@@ -91,6 +93,9 @@ def load():
     L.crl_car_reset.argtypes = [vp, vp, vp]
     L.crl_car_step.argtypes = [vp] * 9
     L.crl_car_step_state.argtypes = [vp] * 7
+    L.crl_car_seed.argtypes = [vp, u64, vp]
+    L.crl_car_step_host.argtypes = [vp] * 10
+    L.crl_car_set_elapsed.argtypes = [vp, vp, vp]
     L.crl_car_render_obs.argtypes = [vp] * 4
     L.crl_car_get_state.argtypes = [vp, vp, vp]
     L.crl_car_get_track.argtypes = [vp, i32, ctypes.POINTER(i32), vp, i32, vp]

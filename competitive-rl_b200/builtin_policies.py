@@ -91,7 +91,8 @@ class DevicePolicy(object):
         net = LightActorCritic if use_light_model else ActorCritic
         self.model = net(shape, num_actions).to(self.device)
         if checkpoint_path:
-            state = torch.load(checkpoint_path, map_location=self.device, weights_only=False)
+            # the reference's checkpoint-*.pkl files hold {"model": state_dict, ...} of plain tensors: no pickled code is needed
+            state = torch.load(checkpoint_path, map_location=self.device, weights_only=True)
             self.model.load_state_dict(state["model"] if "model" in state else state)
         self.model.requires_grad_(False)
         self.stack = torch.zeros((num_envs, *shape), dtype=torch.float32, device=self.device)

@@ -6,14 +6,18 @@ Mirrors what make_envs builds for these ids (competitive_rl/make_envs.py:101-110
           obs (N, 2n, 96, 96) (player 0's stack, then player 1's), reward = player 0's,
           done = any car done (utils/atari_wrappers.py:308-334)
 stepped by a Dummy/Subproc vec-env with auto-reset (utils/dummy_vec_env.py:51-63).
-Car-car collisions are not modelled."""
+Car-car contacts of the two-car env are resolved on the device (csrc/car_contact.cuh).
+
+Buffer lifetime: the tensors returned by reset()/step() are owned by the env and rotate over `n_buffers` sets; what
+step t returned is overwritten by step t + n_buffers (the reference returns fresh copies).  Pass `copy=True` to get
+fresh tensors every step, or a larger `n_buffers` to keep a short rollout alive."""
 import ctypes
 
 import numpy as np
 import torch
 
 from . import _native, spaces
-from .vec_env import VecEnv, _EnvList
+from .vec_env import AlreadySteppingError, NotSteppingError, VecEnv, _EnvList
 
 
 class LazyCarInfos(object):
@@ -40,7 +44,8 @@ class LazyCarInfos(object):
         else:
             info = {k: {"num_steps": int(steps[i]), "reward": float(rew[i, k])} for k in range(self._env.players)}
         if done[i]:
-            info["terminal_observation"] = self._term[i]
+            t = self._term[i]
+            info["terminal_observation"] = t.cpu().numpy() if self._env.return_numpy else t
             if self._env.max_episode_steps:
                 info["TimeLimit.truncated"] = bool(trunc[i])
         return info
@@ -56,7 +61,7 @@ class CudaCarVecEnv(VecEnv):
 
     def __init__(self, env_id="cCarRacing-v0", num_envs=1, frame_stack=4, action_repeat=None, seed=0,
                  asynchronous=False, device=None, max_episode_steps=1000, first_env=0, track_draws=None, birth=None,
-                 glyphs="default", return_numpy=False, n_buffers=2):
+                 glyphs="default", return_numpy=False, n_buffers=2, copy=False, done_mode="any", stack_mode="stack"):
         if env_id not in ("cCarRacing-v0", "cCarRacingDouble-v0"):
             raise ValueError("unsupported env id %r" % (env_id,))
         if not torch.cuda.is_available():
@@ -64,7 +69,12 @@ class CudaCarVecEnv(VecEnv):
         self._lib = _native.load()
         self.env_id, self.players = env_id, 2 if env_id == "cCarRacingDouble-v0" else 1
         self.c = int(frame_stack) if frame_stack else 1
-        self.asynchronous, self.return_numpy = bool(asynchronous), bool(return_numpy)
+        self.asynchronous, self.return_numpy, self.copy = bool(asynchronous), bool(return_numpy), bool(copy)
+        if stack_mode not in ("stack",):
+            raise ValueError("stack_mode must be 'stack'")
+        self.stack_mode = stack_mode
+        if done_mode not in ("any", "car0"):
+            raise ValueError("done_mode must be 'any' (make_envs) or 'car0' (make_competitive_car_racing)")
         self.max_episode_steps = int(max_episode_steps or 0)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.index is None:
@@ -75,7 +85,8 @@ class CudaCarVecEnv(VecEnv):
         act_space = spaces.Box(-1, 1, (2,) if self.players == 1 else (self.players, 2), dtype=np.float32)
         VecEnv.__init__(self, n, obs_space, act_space)
         cfg = _native.CarConfig(n, self.players, int(frame_stack or 0), int(action_repeat or 0), self.max_episode_steps,
-                                int(self.device.index), int(seed) & (2 ** 64 - 1), int(first_env))
+                                int(self.device.index), 1 if done_mode == "car0" else 0, 0, int(seed) & (2 ** 64 - 1),
+                                int(first_env))
         h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             _native.check(self._lib.crl_car_create(ctypes.byref(cfg), ctypes.byref(h)))
@@ -106,6 +117,11 @@ class CudaCarVecEnv(VecEnv):
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    @property
+    def bytes_per_env_step(self):
+        """observation bytes written per env-step (36 864 / 73 728 with frame_stack 4)"""
+        return self.players * self.c * 96 * 96
+
     @staticmethod
     def _ptr(t):
         return ctypes.c_void_p(t.data_ptr())
@@ -116,12 +132,15 @@ class CudaCarVecEnv(VecEnv):
         d = np.ascontiguousarray(draws, np.float64)
         assert d.ndim == 3 and d.shape[0] == self.num_envs and d.shape[2] == 24
         b = None if birth is None else np.ascontiguousarray(birth, np.int32)
-        _native.check(self._lib.crl_car_inject_tracks(
-            self._h, d.ctypes.data, d.shape[1], None if b is None else b.ctypes.data, 0 if b is None else b.shape[1],
-            self._stream()))
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.crl_car_inject_tracks(
+                self._h, d.ctypes.data, d.shape[1], None if b is None else b.ctypes.data, 0 if b is None else b.shape[1],
+                self._stream()))
 
     def _out(self, t):
-        return t.cpu().numpy() if self.return_numpy else t
+        if self.return_numpy:
+            return t.cpu().numpy()
+        return t.clone() if self.copy else t
 
     def load_tracks(self, tracks):
         """CarRacing.reset(use_local_track=...) (car_racing_multi_players.py:376-381) for the whole vec-env: `tracks` is a
@@ -166,6 +185,8 @@ class CudaCarVecEnv(VecEnv):
         return self._out(b["obs"])
 
     def step_async(self, actions):
+        if self._waiting:
+            raise AlreadySteppingError()
         a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions, np.float32))
         self._actions.copy_(a.reshape(self._actions.shape), non_blocking=True)
         self._cur = (self._cur + 1) % len(self._sets)
@@ -177,8 +198,12 @@ class CudaCarVecEnv(VecEnv):
         self._waiting = True
 
     def step_wait(self):
+        if not self._waiting:
+            raise NotSteppingError()
         self._waiting = False
         b = self._sets[self._cur]
+        if self.copy:
+            b = {k: v.clone() for k, v in b.items()}
         done = b["done"].bool()
         rew = b["rew"][:, 0]          # FlattenMultiAgentObservation returns r[0]; single: the scalar reward
         infos = LazyCarInfos(self, b["steps"], b["rew"], b["done"], b["trunc"], b["term"])
@@ -189,7 +214,22 @@ class CudaCarVecEnv(VecEnv):
         return self._out(b["obs"]), rew, done, infos
 
     def seed(self, seed=None):
+        """VecEnv.seed: env i is seeded with seed + i (dummy_vec_env.py:65-69) and CarRacing.seed returns [seed]
+        (car_racing_multi_players.py:248-250).  Here one key re-seeds the whole batch: env i draws its tracks and
+        birth places from the Philox stream of (seed, first_env + i)."""
+        if seed is not None:
+            with torch.cuda.device(self.device):
+                _native.check(self._lib.crl_car_seed(self._h, int(seed) & (2 ** 64 - 1), self._stream()))
         return [[None if seed is None else seed + i] for i in range(self.num_envs)]
+
+    def set_elapsed(self, elapsed):
+        """Pre-age the envs: TimeLimit._elapsed_steps per env (int (N,)); spreads the truncations of a synchronously
+        reset batch over the steps, like a long-running rollout."""
+        t = torch.as_tensor(elapsed).to(self.device, torch.int32).contiguous()
+        assert tuple(t.shape) == (self.num_envs,)
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.crl_car_set_elapsed(self._h, self._ptr(t), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
 
     def get_state(self):
         s = torch.empty((self.num_envs * self.players, 24), dtype=torch.float64, device=self.device)

@@ -30,6 +30,7 @@ constexpr int CAR_SPAN_TILE_ROWS = 32;      // cached scanline rows per road til
 constexpr int CAR_SPAN_KERB_ROWS = 16;      // ... and per kerb quad (larger polygons are scanned in the render kernel)
 constexpr int CAR_SPAN_ROWS = CAR_SPAN_TILE_ROWS + CAR_SPAN_KERB_ROWS;
 constexpr int CAR_MAX_CONTACTS = 8;         // touching car-car fixture pairs kept per env (of 48 possible)
+constexpr int CAR_RAW_RING = 1024;          // raw points of the curve follower kept while it walks (last lap + tail)
 
 // A road tile, 124 bytes: for the physics the convex hull (CCW, fp32) of the reference's 5 listed
 // vertices, with the edge normals the sensor-overlap test needs; for the renderer the listed vertices and the kerb quad in ROAD-MAP PIXELS, i.e.
@@ -81,14 +82,22 @@ struct CarDev {
     int c;                    // frames per player in the observation (frame_stack or 1)
     int action_repeat;
     int max_episode_steps;    // gym TimeLimit of the registry entry (1000); 0 = none
+    int done_mode;            // 0 = any car done (FlattenMultiAgentObservation), 1 = car 0 only (make_competitive_car_racing)
     int64_t first_env;
     uint64_t seed;
+    // ---- per track SLOT: every env owns two, slot = env + n * sel[env] is the track it drives on, the other one
+    //      receives the NEXT track ahead of time (car_pregen_kernel on a side stream), so that an auto-reset is a
+    //      slot swap + car spawn instead of a serial 2500-step curve walk on the step's critical path ----
+    int32_t* n_track;         // [2n]
+    CarTile* tiles;           // [2n][CAR_MAX_TRACK]
+    float2* samples;          // [CAR_MAX_SAMPLES][2n] every 8th track point (transposed: coalesced per-thread scans)
+    double* start_pose;       // [2n][3] beta, x, y of track[0]
+    double* track_pts;        // [2n][CAR_MAX_TRACK][3] beta, x, y of the track (fp64, as generated)
     // ---- per env ----
-    int32_t* n_track;         // [n]
-    CarTile* tiles;           // [n][CAR_MAX_TRACK]
-    float2* samples;          // [CAR_MAX_SAMPLES][n] every 8th track point (transposed: coalesced per-thread scans)
-    double* start_pose;       // [n][3] beta, x, y of track[0]
-    double* track_pts;        // [n][CAR_MAX_TRACK][3] beta, x, y of the current track (fp64, as generated)
+    int32_t* sel;             // [n] which of its two slots env e currently drives on
+    int32_t* next_state;      // [n] the other slot: 0 = empty, 1 = being generated, 2 = holds the next track
+    int32_t* next_att0;       // [n] attempt_count before the next track was generated (restored when it is discarded)
+    double* raw_ring;         // [n][CAR_RAW_RING][3] scratch of the generator: the last raw points of the walk
     int32_t* step_count;      // [n] CarRacing.step_count
     int32_t* elapsed;         // [n] TimeLimit._elapsed_steps
     int32_t* reset_count;     // [n] resets so far (RNG / injection cursor)
@@ -112,10 +121,10 @@ struct CarDev {
     int32_t* slow_list;       // [n]
     int32_t* slow_count;      // [1]
     uint8_t* deferred;        // [n] 1 = on the slow list this step
-    // ---- per env: scanline span tables of the road polygons in road-map pixels (they depend on the track only, so they
-    //      are built once per reset by car_tile_spans_kernel instead of once per frame): [n][CAR_MAX_TRACK][CAR_SPAN_ROWS] ----
+    // ---- per slot: scanline span tables of the road polygons in road-map pixels (they depend on the track only, so they
+    //      are built once per track by the generator instead of once per frame): [2n][CAR_MAX_TRACK][CAR_SPAN_ROWS] ----
     short4* tile_spans;
-    float2* tile_centres;     // [n][CAR_MAX_TRACK] tile centres (= CarTile::cx, cy), contiguous for the per-frame cull
+    float2* tile_centres;     // [2n][CAR_MAX_TRACK] tile centres (= CarTile::cx, cy), contiguous for the per-frame cull
     // ---- per frame (env * players + player): written by car_frame_setup_kernel, read by car_render_kernel ----
     FrameMap* frame_map;      // [n*players]
     uint16_t* frame_cand;     // [n*players][CAR_MAX_CAND] road tiles that can reach the window
@@ -140,13 +149,16 @@ struct CarDev {
     unsigned long long* stats;   // [0] episodes, [1] sum length, [2] sum tiles visited (player 0)
 };
 
+__device__ __forceinline__ int car_slot(const CarDev& p, int e) { return e + p.n * p.sel[e]; }
+
 cudaError_t launch_car_reset(const CarDev& p, int only_done, cudaStream_t s);
+cudaError_t launch_car_pregen(const CarDev& p, cudaStream_t s);        // next tracks of the envs that have none (side stream)
+cudaError_t launch_car_discard_next(const CarDev& p, cudaStream_t s);  // forget pre-generated tracks (seed / injection changed)
 cudaError_t launch_car_step(const CarDev& p, int mode, const float* actions, float* rew, uint8_t* done, int32_t* num_steps,
                             uint8_t* truncated, cudaStream_t s);
 // which: 0 = every frame, 1 = envs not deferred to the slow stepping pass, 2 = deferred envs only; advance: move the frame ring on
 cudaError_t launch_car_render(const CarDev& p, int only_done, int which, int advance, uint8_t* obs, uint8_t* term_obs, cudaStream_t s);
 cudaError_t car_raster_init();
-cudaError_t launch_car_tile_spans(const CarDev& p, cudaStream_t s);   // after a full launch_car_reset (auto-reset: see car_frame_setup_kernel)
 size_t car_frame_map_bytes();
 void car_checker_table(int* out);
 cudaError_t launch_car_get_state(const CarDev& p, double* state, cudaStream_t s);

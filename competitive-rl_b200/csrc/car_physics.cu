@@ -16,6 +16,7 @@
 #include <math.h>
 
 #include "car_common.cuh"
+#include "car_spans.cuh"
 
 namespace crl {
 
@@ -70,11 +71,15 @@ __device__ __forceinline__ double signd(double v) { return (double)((v > 0) - (v
 namespace crl {
 
 // ------------------------------------------------------------------------------------------------
-// track generator (fp64): one walk of the curve follower; `emit_from/emit_to` select which raw points
-// are written out (second pass) -- the raw 2500-point walk is never stored.
+// track generator (fp64): one walk of the curve follower (_create_track :262-375), run by ONE lane.  The reference keeps
+// all raw points and slices track[i1 : i2 - 1] afterwards (i2 = last, i1 = previous crossing of start_alpha).  Here the
+// last CAR_RAW_RING raw points go to a ring in global memory (fire-and-forget stores off the dependent chain), which holds
+// the slice whenever the walk ends within a lap of the last crossing -- always, unless the follower got stuck; then
+// `emit_from/emit_to` select the raw points a second walk writes out.
 struct WalkResult { int n_raw, i1, i2; };
 
-__device__ WalkResult track_walk(const double* draws, int emit_from, int emit_to, double* out /* [][3] beta,x,y */) {
+__device__ WalkResult track_walk(const double* draws, double* ring /* [CAR_RAW_RING][3] or nullptr */, int emit_from, int emit_to,
+                                 double* out /* [][3] beta,x,y or nullptr */) {
     double cp_alpha[CAR_CHECKPOINTS], cp_x[CAR_CHECKPOINTS], cp_y[CAR_CHECKPOINTS];
     double start_alpha = 0.0;
     for (int c = 0; c < CAR_CHECKPOINTS; ++c) {
@@ -121,6 +126,10 @@ __device__ WalkResult track_walk(const double* draws, int emit_from, int emit_to
         y += p1y * CR_TRACK_DETAIL_STEP;
         // raw point n_raw = (alpha, prev_beta*0.5 + beta*0.5, x, y)
         if (n_raw >= 1 && alpha > start_alpha && prev_alpha <= start_alpha) { prev_cross = last_cross; last_cross = n_raw; }
+        if (ring != nullptr) {
+            double* o = ring + 3 * (n_raw & (CAR_RAW_RING - 1));
+            o[0] = prev_beta * 0.5 + beta * 0.5; o[1] = x; o[2] = y;
+        }
         if (out != nullptr && n_raw >= emit_from && n_raw < emit_to) {
             double* o = out + 3 * (n_raw - emit_from);
             o[0] = prev_beta * 0.5 + beta * 0.5; o[1] = x; o[2] = y;
@@ -172,83 +181,150 @@ __device__ int convex_hull5(const float* px, const float* py, float* ox, float* 
     return cnt;
 }
 
-__device__ void car_body_reset(const CarDev& p, int ci, double init_angle, double init_x, double init_y, int birth) {
+// Car.__init__ (car_dynamics.py:55-129) of car `ci` at the track start, by the 32 lanes of a warp
+__device__ void car_body_reset(const CarDev& p, int ci, double init_angle, double init_x, double init_y, int birth, int lane) {
     init_x -= birth % 2 * 5;
     init_y -= floor((double)(birth / 2)) * 10;
     float* b = p.body + (size_t)ci * 40;
     const CarHullConst* K = p.consts;
     const float a = (float)init_angle;
-    const Rot q = make_rot(a);
-    const F2 lc = rmul(q, f2(K->hull_lcx, K->hull_lcy));
-    b[0] = (float)init_x + lc.x; b[1] = (float)init_y + lc.y; b[2] = a; b[3] = b[4] = b[5] = 0.f; b[6] = 0.f; b[7] = 1.f;
-    for (int k = 0; k < 4; ++k) {   // wheels are NOT placed rotated (car_dynamics.py:90); the joints pull them in
+    if (lane == 0) {
+        const Rot q = make_rot(a);
+        const F2 lc = rmul(q, f2(K->hull_lcx, K->hull_lcy));
+        b[0] = (float)init_x + lc.x; b[1] = (float)init_y + lc.y; b[2] = a; b[3] = b[4] = b[5] = 0.f; b[6] = 0.f; b[7] = 1.f;
+    } else if (lane <= 4) {   // wheels are NOT placed rotated (car_dynamics.py:90); the joints pull them in
+        const int k = lane - 1;
         float* w = b + 8 * (k + 1);
         w[0] = (float)(init_x + c_wheelpos[k][0] * CR_SIZE); w[1] = (float)(init_y + c_wheelpos[k][1] * CR_SIZE);
         w[2] = a; w[3] = w[4] = w[5] = 0.f; w[6] = 0.f; w[7] = 1.f;
     }
-    float* j = p.joint + (size_t)ci * 24;
-    for (int i = 0; i < 24; ++i) j[i] = 0.f;
-    double* wd = p.wheel + (size_t)ci * 8;
-    for (int i = 0; i < 8; ++i) wd[i] = 0.0;
-    p.reward[2 * ci] = 0.0; p.reward[2 * ci + 1] = 0.0;
-    int32_t* cn = p.counters + 4 * ci;
-    cn[0] = cn[1] = cn[2] = cn[3] = 0;
-    for (int i = 0; i < 64; ++i) p.touching[(size_t)ci * 64 + i] = 0u;
-    for (int i = 0; i < 16; ++i) p.visited[(size_t)ci * 16 + i] = 0u;
+    if (lane < 24) p.joint[(size_t)ci * 24 + lane] = 0.f;
+    if (lane < 8) p.wheel[(size_t)ci * 8 + lane] = 0.0;
+    if (lane < 2) p.reward[2 * ci + lane] = 0.0;
+    if (lane < 4) p.counters[4 * ci + lane] = 0;
+    p.touching[(size_t)ci * 64 + lane] = 0u; p.touching[(size_t)ci * 64 + 32 + lane] = 0u;
+    if (lane < 16) p.visited[(size_t)ci * 16 + lane] = 0u;
 }
 
-// CarRacing.reset: new track (retry until an attempt succeeds, :499-507), cars at track[0] (:508-512)
-__global__ void car_reset_kernel(CarDev p, int only_done) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= p.n) return;
-    if (only_done && !p.env_done[e]) return;
-    double* pts = p.track_pts + (size_t)e * CAR_MAX_TRACK * 3;
-    CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
+// One tile of the track (:399-445): convex hull + edge normals for the physics, road-map pixels for the renderer
+__device__ void build_tile(const double* pts, int n, int i, uint8_t border_flag, CarTile* tiles, float2* centres) {
+    const double* p1 = pts + 3 * i;
+    const double* p2 = pts + 3 * ((i - 1 + n) % n);
+    const double b1 = p1[0], x1 = p1[1], y1 = p1[2], b2 = p2[0], x2 = p2[1], y2 = p2[2];
+    const double osc = (10 / (100 / sqrt(96.0))) * 1.8;
+    const double cb1 = cos(b1), sb1 = sin(b1), cb2 = cos(b2), sb2 = sin(b2);
+    const double dvx[5] = {x1 - CR_TRACK_WIDTH * cb1, x1 - CR_TRACK_WIDTH / 2 * cos(b1 - CR_PI / 2),
+                           x1 + CR_TRACK_WIDTH * cb1, x2 + CR_TRACK_WIDTH * cb2, x2 - CR_TRACK_WIDTH * cb2};
+    const double dvy[5] = {y1 - CR_TRACK_WIDTH * sb1, y1 - CR_TRACK_WIDTH / 2 * sin(b1 - CR_PI / 2),
+                           y1 + CR_TRACK_WIDTH * sb1, y2 + CR_TRACK_WIDTH * sb2, y2 - CR_TRACK_WIDTH * sb2};
+    float vx[5], vy[5];
+    CarTile t;
+    for (int k = 0; k < 5; ++k) {
+        vx[k] = (float)dvx[k]; vy[k] = (float)dvy[k];
+        // road-map pixels of the listed (fp64) vertices: obs_scale * -v + world_size / 2, truncated
+        t.mx[k] = (int16_t)(int)(osc * -dvx[k] + 5000.0);
+        t.my[k] = (int16_t)(int)(osc * -dvy[k] + 5000.0);
+    }
+    t.n = (uint8_t)convex_hull5(vx, vy, t.px, t.py);
+    for (int k = t.n; k < 5; ++k) { t.px[k] = t.px[0]; t.py[k] = t.py[0]; }
+    for (int k = 0; k < 5; ++k) {      // edge normals exactly as max_separation derives them (same fp32 operations)
+        t.nx[k] = 3.0e38f; t.ny[k] = 0.f;
+        if (k < t.n) {
+            const int k2 = (k + 1 == t.n) ? 0 : k + 1;
+            const float ex = t.px[k2] - t.px[k], ey = t.py[k2] - t.py[k];
+            const float len = sqrtf(ex * ex + ey * ey);
+            if (!(len < 1e-12f)) { t.nx[k] = ey / len; t.ny[k] = -ex / len; }
+        }
+    }
+    t.flags = (uint8_t)(1 | (border_flag & 2) | ((i % 2 == 0) ? 4 : 0));
+    t.pad = 0;
+    t.cx = (float)x1; t.cy = (float)y1;
+    centres[i] = make_float2(t.cx, t.cy);
+    const double side = signd(b2 - b1);
+    const double kdx[4] = {x1 + side * CR_TRACK_WIDTH * cb1, x1 + side * (CR_TRACK_WIDTH + CR_BORDER) * cb1,
+                           x2 + side * (CR_TRACK_WIDTH + CR_BORDER) * cb2, x2 + side * CR_TRACK_WIDTH * cb2};
+    const double kdy[4] = {y1 + side * CR_TRACK_WIDTH * sb1, y1 + side * (CR_TRACK_WIDTH + CR_BORDER) * sb1,
+                           y2 + side * (CR_TRACK_WIDTH + CR_BORDER) * sb2, y2 + side * CR_TRACK_WIDTH * sb2};
+    for (int k = 0; k < 4; ++k) {
+        t.kmx[k] = (int16_t)(int)(osc * -kdx[k] + 5000.0);
+        t.kmy[k] = (int16_t)(int)(osc * -kdy[k] + 5000.0);
+    }
+    tiles[i] = t;
+}
+
+// CarRacing.reset's track loop (:499-507) for env e into track slot `slot`, by one warp: lane 0 retries _create_track until
+// an attempt succeeds (the curve walk is a serial fp64 chain); the kerb flags, tiles, prefilter samples and span tables
+// that follow are spread over the lanes.  Returns the number of track points; 0 = failed 64 times (flagged);
+// -1 = (for_pregen only) the injected draw table has no attempt left, nothing was written or consumed.
+__device__ int generate_track_warp(const CarDev& p, int e, int slot, bool for_pregen, int lane) {
+    double* pts = p.track_pts + (size_t)slot * CAR_MAX_TRACK * 3;
+    CarTile* tiles = p.tiles + (size_t)slot * CAR_MAX_TRACK;
+    float2* centres = p.tile_centres + (size_t)slot * CAR_MAX_TRACK;
+    double* ring = p.raw_ring + (size_t)e * CAR_RAW_RING * 3;
     const uint64_t gi = (uint64_t)(p.first_env + e);
-    int n = 0;
+    int n = 0, ring_from = -1;
     if (p.fixed_tracks != nullptr && p.n_fixed > 0) {       // replay of a recorded track: no generation, no draws consumed
         const int k = (int)(gi % (uint64_t)p.n_fixed);
         n = min(max(p.fixed_counts[k], 0), CAR_MAX_TRACK);
         const double* src = p.fixed_tracks + (size_t)k * CAR_MAX_TRACK * 3;
-        for (int i = 0; i < 3 * n; ++i) pts[i] = src[i];
-    }
-    for (int guard = 0; guard < 64 && n == 0; ++guard) {
-        double draws[CAR_DRAWS];
-        const int att = p.attempt_count[e];
-        p.attempt_count[e] = att + 1;
-        if (p.track_draws != nullptr) {
-            int k = att;
-            if (k >= p.k_draws) { *p.overrun = 1; k = p.k_draws - 1; }
-            for (int i = 0; i < CAR_DRAWS; ++i) draws[i] = p.track_draws[((size_t)e * p.k_draws + k) * CAR_DRAWS + i];
-        } else {
-            for (int i = 0; i < CAR_DRAWS; i += 2) {   // noise ~ U(0, 2pi/12), rad ~ U(R/3, R), :268-270
-                uint32_t r[4];
-                philox4x32_10((uint32_t)att, (uint32_t)(i / 2), (uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)p.seed,
-                              (uint32_t)(p.seed >> 32) ^ 0xC0FFEEu, r);
-                const double u0 = (double)((((uint64_t)r[0] >> 5) << 26) | ((uint64_t)r[1] >> 6)) * (1.0 / 9007199254740992.0);
-                const double u1 = (double)((((uint64_t)r[2] >> 5) << 26) | ((uint64_t)r[3] >> 6)) * (1.0 / 9007199254740992.0);
-                draws[i] = 0.0 + (2 * CR_PI * 1 / CAR_CHECKPOINTS - 0.0) * u0;
-                draws[i + 1] = CR_TRACK_RAD / 3 + (CR_TRACK_RAD - CR_TRACK_RAD / 3) * u1;
+        for (int i = lane; i < 3 * n; i += 32) pts[i] = src[i];
+    } else {
+        if (lane == 0) {
+            for (int guard = 0; guard < 64 && n == 0; ++guard) {
+                double draws[CAR_DRAWS];
+                const int att = p.attempt_count[e];
+                if (p.track_draws != nullptr) {
+                    int k = att;
+                    if (k >= p.k_draws) {
+                        if (for_pregen) { n = -1; break; }          // the table is not ours to overrun ahead of time
+                        *p.overrun = 1; k = p.k_draws - 1;
+                    }
+                    for (int i = 0; i < CAR_DRAWS; ++i) draws[i] = p.track_draws[((size_t)e * p.k_draws + k) * CAR_DRAWS + i];
+                } else {
+                    for (int i = 0; i < CAR_DRAWS; i += 2) {   // noise ~ U(0, 2pi/12), rad ~ U(R/3, R), :268-270
+                        uint32_t r[4];
+                        philox4x32_10((uint32_t)att, (uint32_t)(i / 2), (uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)p.seed,
+                                      (uint32_t)(p.seed >> 32) ^ 0xC0FFEEu, r);
+                        const double u0 = (double)((((uint64_t)r[0] >> 5) << 26) | ((uint64_t)r[1] >> 6)) * (1.0 / 9007199254740992.0);
+                        const double u1 = (double)((((uint64_t)r[2] >> 5) << 26) | ((uint64_t)r[3] >> 6)) * (1.0 / 9007199254740992.0);
+                        draws[i] = 0.0 + (2 * CR_PI * 1 / CAR_CHECKPOINTS - 0.0) * u0;
+                        draws[i + 1] = CR_TRACK_RAD / 3 + (CR_TRACK_RAD - CR_TRACK_RAD / 3) * u1;
+                    }
+                }
+                p.attempt_count[e] = att + 1;
+                const WalkResult w = track_walk(draws, ring, 0, 0, nullptr);
+                if (w.i1 < 0 || w.i2 < 0) continue;               // "return False  # Failed"
+                const int cnt = (w.i2 - 1) - w.i1;                // track = track[i1:i2 - 1]
+                if (cnt <= 8 || cnt > CAR_MAX_TRACK) continue;
+                const double *first, *last;
+                if (w.n_raw - w.i1 <= CAR_RAW_RING) {             // the slice is still in the ring
+                    first = ring + 3 * (w.i1 & (CAR_RAW_RING - 1));
+                    last = ring + 3 * ((w.i1 + cnt - 1) & (CAR_RAW_RING - 1));
+                    ring_from = w.i1;
+                } else {                                          // follower wandered off after its last lap: walk again
+                    track_walk(draws, nullptr, w.i1, w.i1 + cnt, pts);
+                    first = pts; last = pts + 3 * (cnt - 1);
+                    ring_from = -1;
+                }
+                const double fb = first[0], fpx = cos(fb), fpy = sin(fb);
+                const double gx = fpx * (first[1] - last[1]), gy = fpy * (first[2] - last[2]);
+                if (sqrt(gx * gx + gy * gy) > CR_TRACK_DETAIL_STEP) continue;   // not well glued together
+                n = cnt;
             }
+            if (n == 0) *p.overrun = 2;   // cannot happen with sane draws; the env keeps its old track, flagged
         }
-        const WalkResult w = track_walk(draws, 0, 0, nullptr);
-        if (w.i1 < 0 || w.i2 < 0) continue;               // "return False  # Failed"
-        const int cnt = (w.i2 - 1) - w.i1;                // track = track[i1:i2 - 1]
-        if (cnt <= 8 || cnt > CAR_MAX_TRACK) continue;
-        track_walk(draws, w.i1, w.i1 + cnt, pts);
-        const double fb = pts[0], fpx = cos(fb), fpy = sin(fb);
-        const double gx = fpx * (pts[1] - pts[3 * (cnt - 1) + 1]), gy = fpy * (pts[2] - pts[3 * (cnt - 1) + 2]);
-        if (sqrt(gx * gx + gy * gy) > CR_TRACK_DETAIL_STEP) continue;   // not well glued together
-        n = cnt;
+        __syncwarp();
+        n = __shfl_sync(0xffffffffu, n, 0);
+        ring_from = __shfl_sync(0xffffffffu, ring_from, 0);
+        if (n <= 0) return n;
+        if (ring_from >= 0)
+            for (int i = lane; i < 3 * n; i += 32) pts[i] = ring[3 * ((ring_from + i / 3) & (CAR_RAW_RING - 1)) + i % 3];
     }
-    if (n == 0) {   // cannot happen with sane draws; keep the env valid with a flagged error
-        *p.overrun = 2;
-        return;
-    }
-    p.n_track[e] = n;
+    __syncwarp();
+    if (n <= 0) return 0;
+    if (lane == 0) p.n_track[slot] = n;
     // red-white border on hard turns (:383-397): border[] kept in tile.flags bit 1
-    for (int i = 0; i < n; ++i) tiles[i].flags = 1;
-    for (int i = 0; i < n; ++i) {
+    for (int i = lane; i < n; i += 32) {
         bool good = true;
         int oneside = 0;
         for (int neg = 0; neg < CR_BORDER_MIN_COUNT; ++neg) {
@@ -257,80 +333,102 @@ __global__ void car_reset_kernel(CarDev p, int only_done) {
             oneside += (b1 - b2 > 0) - (b1 - b2 < 0);
         }
         good = good && abs(oneside) == CR_BORDER_MIN_COUNT;
-        if (good) tiles[i].flags |= 2;
+        tiles[i].flags = good ? 3 : 1;
     }
+    __syncwarp();
     // "border[i - neg] |= border[i]" in place, i ascending (:394-396): the marks i = 0..2 put on the last tiles through the
-    // negative indices are seen again when the loop gets there, exactly like the reference's list
-    for (int i = 0; i < n; ++i)
-        if (tiles[i].flags & 2)
-            for (int neg = 0; neg < CR_BORDER_MIN_COUNT; ++neg) tiles[((i - neg) % n + n) % n].flags |= 2;
-    // tiles (:399-445)
-    for (int i = 0; i < n; ++i) {
-        const double* p1 = pts + 3 * i;
-        const double* p2 = pts + 3 * ((i - 1 + n) % n);
-        const double b1 = p1[0], x1 = p1[1], y1 = p1[2], b2 = p2[0], x2 = p2[1], y2 = p2[2];
-        float vx[5], vy[5];
-        vx[0] = (float)(x1 - CR_TRACK_WIDTH * cos(b1)); vy[0] = (float)(y1 - CR_TRACK_WIDTH * sin(b1));
-        vx[1] = (float)(x1 - CR_TRACK_WIDTH / 2 * cos(b1 - CR_PI / 2)); vy[1] = (float)(y1 - CR_TRACK_WIDTH / 2 * sin(b1 - CR_PI / 2));
-        vx[2] = (float)(x1 + CR_TRACK_WIDTH * cos(b1)); vy[2] = (float)(y1 + CR_TRACK_WIDTH * sin(b1));
-        vx[3] = (float)(x2 + CR_TRACK_WIDTH * cos(b2)); vy[3] = (float)(y2 + CR_TRACK_WIDTH * sin(b2));
-        vx[4] = (float)(x2 - CR_TRACK_WIDTH * cos(b2)); vy[4] = (float)(y2 - CR_TRACK_WIDTH * sin(b2));
-        CarTile t;
-        {   // road-map pixels of the listed (fp64) vertices: obs_scale * -v + world_size / 2, truncated
-            const double osc = (10 / (100 / sqrt(96.0))) * 1.8;
-            const double dvx[5] = {x1 - CR_TRACK_WIDTH * cos(b1), x1 - CR_TRACK_WIDTH / 2 * cos(b1 - CR_PI / 2),
-                                   x1 + CR_TRACK_WIDTH * cos(b1), x2 + CR_TRACK_WIDTH * cos(b2), x2 - CR_TRACK_WIDTH * cos(b2)};
-            const double dvy[5] = {y1 - CR_TRACK_WIDTH * sin(b1), y1 - CR_TRACK_WIDTH / 2 * sin(b1 - CR_PI / 2),
-                                   y1 + CR_TRACK_WIDTH * sin(b1), y2 + CR_TRACK_WIDTH * sin(b2), y2 - CR_TRACK_WIDTH * sin(b2)};
-            for (int k = 0; k < 5; ++k) {
-                t.mx[k] = (int16_t)(int)(osc * -dvx[k] + 5000.0);
-                t.my[k] = (int16_t)(int)(osc * -dvy[k] + 5000.0);
-            }
-        }
-        t.n = (uint8_t)convex_hull5(vx, vy, t.px, t.py);
-        for (int k = t.n; k < 5; ++k) { t.px[k] = t.px[0]; t.py[k] = t.py[0]; }
-        for (int k = 0; k < 5; ++k) {      // edge normals exactly as max_separation derives them (same fp32 operations)
-            t.nx[k] = 3.0e38f; t.ny[k] = 0.f;
-            if (k < t.n) {
-                const int k2 = (k + 1 == t.n) ? 0 : k + 1;
-                const float ex = t.px[k2] - t.px[k], ey = t.py[k2] - t.py[k];
-                const float len = sqrtf(ex * ex + ey * ey);
-                if (!(len < 1e-12f)) { t.nx[k] = ey / len; t.ny[k] = -ex / len; }
-            }
-        }
-        t.flags = (uint8_t)(1 | (tiles[i].flags & 2) | ((i % 2 == 0) ? 4 : 0));
-        t.pad = 0;
-        t.cx = (float)x1; t.cy = (float)y1;
-        p.tile_centres[(size_t)e * CAR_MAX_TRACK + i] = make_float2(t.cx, t.cy);
-        const double side = signd(b2 - b1);
-        {
-            const double osc = (10 / (100 / sqrt(96.0))) * 1.8;
-            const double kdx[4] = {x1 + side * CR_TRACK_WIDTH * cos(b1), x1 + side * (CR_TRACK_WIDTH + CR_BORDER) * cos(b1),
-                                   x2 + side * (CR_TRACK_WIDTH + CR_BORDER) * cos(b2), x2 + side * CR_TRACK_WIDTH * cos(b2)};
-            const double kdy[4] = {y1 + side * CR_TRACK_WIDTH * sin(b1), y1 + side * (CR_TRACK_WIDTH + CR_BORDER) * sin(b1),
-                                   y2 + side * (CR_TRACK_WIDTH + CR_BORDER) * sin(b2), y2 + side * CR_TRACK_WIDTH * sin(b2)};
-            for (int k = 0; k < 4; ++k) {
-                t.kmx[k] = (int16_t)(int)(osc * -kdx[k] + 5000.0);
-                t.kmy[k] = (int16_t)(int)(osc * -kdy[k] + 5000.0);
-            }
-        }
-        tiles[i] = t;
-    }
-    for (int i = n; i < CAR_MAX_TRACK; ++i) tiles[i].flags = 0;
-    for (int s = 0; s < CAR_MAX_SAMPLES; ++s) {
+    // negative indices are seen again when the loop gets there, exactly like the reference's list -- serial, lane 0
+    if (lane == 0)
+        for (int i = 0; i < n; ++i)
+            if (tiles[i].flags & 2)
+                for (int neg = 0; neg < CR_BORDER_MIN_COUNT; ++neg) tiles[((i - neg) % n + n) % n].flags |= 2;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) build_tile(pts, n, i, tiles[i].flags, tiles, centres);
+    for (int i = n + lane; i < CAR_MAX_TRACK; i += 32) tiles[i].flags = 0;
+    for (int s = lane; s < CAR_MAX_SAMPLES; s += 32) {
         const int i = s * CAR_SAMPLE_STRIDE;
-        p.samples[(size_t)s * p.n + e] = (i < n) ? make_float2((float)pts[3 * i + 1], (float)pts[3 * i + 2])
-                                                 : make_float2(1e30f, 1e30f);
+        p.samples[(size_t)s * (2 * p.n) + slot] = (i < n) ? make_float2((float)pts[3 * i + 1], (float)pts[3 * i + 2])
+                                                          : make_float2(1e30f, 1e30f);
     }
-    p.start_pose[3 * e] = pts[0]; p.start_pose[3 * e + 1] = pts[1]; p.start_pose[3 * e + 2] = pts[2];
+    if (lane < 3) p.start_pose[3 * slot + lane] = pts[lane];
+    __syncwarp();
+    build_tile_spans(p, slot, n, lane, 32);
+    return n;
+}
+
+// Claim the generation of env e's next track (next_state 0 -> 1), or wait for whoever holds it.  A holder is a resident
+// warp of car_pregen_kernel or car_reset_kernel, so it finishes on its own: the wait cannot deadlock.
+// Returns true when this warp has to generate.
+__device__ bool claim_next_track(const CarDev& p, int e, int lane, bool wait) {
+    int st = 0;
+    if (lane == 0) st = atomicCAS(p.next_state + e, 0, 1);
+    st = __shfl_sync(0xffffffffu, st, 0);
+    if (st == 0) return true;
+    if (wait && st == 1) {
+        if (lane == 0) {
+            volatile int32_t* flag = p.next_state + e;
+            while (*flag != 2) __nanosleep(500);
+        }
+        __syncwarp();
+    }
+    __threadfence();
+    return false;
+}
+
+__device__ void publish_next_track(const CarDev& p, int e, int lane, bool ok) {
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) *(volatile int32_t*)(p.next_state + e) = ok ? 2 : 0;
+}
+
+// Next track of every env that has none, one warp per env.  Runs on a side stream behind the step, so that the
+// auto-reset below finds the track ready: its inputs are only (seed, global env index, attempt_count).
+__global__ void __launch_bounds__(64) car_pregen_kernel(CarDev p) {
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= p.n) return;
+    if (*(volatile int32_t*)(p.next_state + e) != 0) return;
+    if (!claim_next_track(p, e, lane, false)) return;
+    if (lane == 0) p.next_att0[e] = p.attempt_count[e];
+    const int n = generate_track_warp(p, e, e + p.n * (1 - p.sel[e]), true, lane);
+    publish_next_track(p, e, lane, n > 0);
+}
+
+// A pre-generated track that will not be used (seed / injection tables / fixed tracks changed): give its attempts back.
+__global__ void car_discard_next_kernel(CarDev p) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.n) return;
+    if (p.next_state[e] == 2) p.attempt_count[e] = p.next_att0[e];
+    p.next_state[e] = 0;
+}
+
+// CarRacing.reset: new track (retry until an attempt succeeds, :499-507), cars at track[0] (:508-512).  One warp per env:
+// the track is normally waiting in the env's other slot (car_pregen_kernel) and the reset is a slot swap + spawn.
+__global__ void __launch_bounds__(64) car_reset_kernel(CarDev p, int only_done) {
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= p.n) return;
+    if (only_done && !p.env_done[e]) return;
+    const int next_slot = e + p.n * (1 - p.sel[e]);
+    bool have = true;
+    if (claim_next_track(p, e, lane, true)) {          // not pre-generated (first reset, or an episode shorter than the generator)
+        have = generate_track_warp(p, e, next_slot, false, lane) > 0;
+        __threadfence();
+    }
+    __syncwarp();
+    if (lane == 0) {
+        if (have) p.sel[e] = 1 - p.sel[e];             // a failed generation (flagged) keeps the old track
+        *(volatile int32_t*)(p.next_state + e) = 0;
+    }
+    const int slot = have ? next_slot : (next_slot >= p.n ? e : e + p.n);
     // cars: birth_place_indices = shuffle(arange(num_player)) (:508-512)
-    const int rc = p.reset_count[e];
-    p.reset_count[e] = rc + 1;
+    int rc = 0;
+    if (lane == 0) { rc = p.reset_count[e]; p.reset_count[e] = rc + 1; }
+    rc = __shfl_sync(0xffffffffu, rc, 0);
+    const uint64_t gi = (uint64_t)(p.first_env + e);
     int birth[CAR_MAX_PLAYERS] = {0, 1};
     if (p.players == 2) {
         if (p.birth != nullptr) {
             int k = rc;
-            if (k >= p.k_birth) { *p.overrun = 1; k = p.k_birth - 1; }
+            if (k >= p.k_birth) { if (lane == 0) *p.overrun = 1; k = p.k_birth - 1; }
             birth[0] = p.birth[((size_t)e * p.k_birth + k) * 2]; birth[1] = p.birth[((size_t)e * p.k_birth + k) * 2 + 1];
         } else {
             uint32_t r[4];
@@ -339,11 +437,14 @@ __global__ void car_reset_kernel(CarDev p, int only_done) {
             if (r[0] & 1u) { birth[0] = 1; birth[1] = 0; }
         }
     }
-    for (int k = 0; k < p.players; ++k) car_body_reset(p, e * p.players + k, pts[0], pts[1], pts[2], birth[k]);
-    p.step_count[e] = 0;
-    p.elapsed[e] = 0;
-    p.inv_dt0[e] = 0.f;
-    if (p.n_contacts != nullptr) p.n_contacts[e] = 0;
+    const double sp0 = p.start_pose[3 * slot], sp1 = p.start_pose[3 * slot + 1], sp2 = p.start_pose[3 * slot + 2];
+    for (int k = 0; k < p.players; ++k) car_body_reset(p, e * p.players + k, sp0, sp1, sp2, birth[k], lane);
+    if (lane == 0) {
+        p.step_count[e] = 0;
+        p.elapsed[e] = 0;
+        p.inv_dt0[e] = 0.f;
+        if (p.n_contacts != nullptr) p.n_contacts[e] = 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -495,9 +596,10 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
         car_done = cn[3] != 0;
         uint32_t* touching = p.touching + (size_t)ci * 64;
         uint32_t* visited = p.visited + (size_t)ci * 16;
-        const int n_track = p.n_track[e];
-        const CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
-        const float2* centres = p.tile_centres + (size_t)e * CAR_MAX_TRACK;   // 8-byte stride instead of CarTile's 116
+        const int slot = car_slot(p, e);
+        const int n_track = p.n_track[slot];
+        const CarTile* tiles = p.tiles + (size_t)slot * CAR_MAX_TRACK;
+        const float2* centres = p.tile_centres + (size_t)slot * CAR_MAX_TRACK;   // 8-byte stride instead of CarTile's 116
         int step_count = p.step_count[e];
         float inv_dt0 = p.inv_dt0[e];
         const float hull_lcx = K.hull_lcx, hull_lcy = K.hull_lcy;
@@ -591,7 +693,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                 int cand[48], n_cand = 0;
                 const int n_samp = (n_track + CAR_SAMPLE_STRIDE - 1) / CAR_SAMPLE_STRIDE;
                 for (int s = 0; s < n_samp; ++s) {
-                    const float2 sp = p.samples[(size_t)s * p.n + e];
+                    const float2 sp = p.samples[(size_t)s * (2 * p.n) + slot];
                     const float dx = sp.x - hp.x, dy = sp.y - hp.y;
                     if (dx * dx + dy * dy < 36.0f * 36.0f) {
                         const int t1 = min(n_track, (s + 1) * CAR_SAMPLE_STRIDE);
@@ -932,7 +1034,10 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
     // ---- env level: done = any(car done) (FlattenMultiAgentObservation.step, atari_wrappers.py:323-331),
     //      gym TimeLimit (register.py:14,21) ----
     bool any_done = car_done;
-    if (p.players == 2) any_done = any_done || __shfl_xor_sync(0xffffffffu, (int)car_done, 1) != 0;
+    if (p.players == 2) {   // done_mode 1: the env ends with car 0 (make_competitive_car_racing returns d[0], :29-33)
+        const bool other = __shfl_xor_sync(0xffffffffu, (int)car_done, 1) != 0;
+        if (p.done_mode == 0) any_done = any_done || other;
+    }
     if (active && player == 0) {
         const int steps = p.step_count[e] + env_steps;
         p.step_count[e] = steps;
@@ -986,7 +1091,17 @@ __global__ void car_random_actions_kernel(float* actions, int n_values, uint64_t
 }
 
 cudaError_t launch_car_reset(const CarDev& p, int only_done, cudaStream_t s) {
-    car_reset_kernel<<<(p.n + 63) / 64, 64, 0, s>>>(p, only_done);
+    car_reset_kernel<<<(p.n + 1) / 2, 64, 0, s>>>(p, only_done);     // one warp per env
+    return cudaGetLastError();
+}
+
+cudaError_t launch_car_pregen(const CarDev& p, cudaStream_t s) {
+    car_pregen_kernel<<<(p.n + 1) / 2, 64, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_car_discard_next(const CarDev& p, cudaStream_t s) {
+    car_discard_next_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,7 @@
 #include <math.h>
 
 #include "car_common.cuh"
+#include "car_spans.cuh"
 
 namespace crl {
 
@@ -74,44 +75,6 @@ __device__ __forceinline__ void map_to_screen(const FrameMap& m, float u, float 
     const float dx = (u - (float)m.rx) * 65536.f - (float)m.cx0, dy = (v - (float)m.ry) * 65536.f - (float)m.cy0;
     X = ((float)m.icos * dx + (float)m.isin * dy) * m.inv_det + (float)m.bx;
     Y = (-(float)m.isin * dx + (float)m.icos * dy) * m.inv_det + (float)m.by;
-}
-
-// C integer division a / b (b > 0, truncation towards zero).  For |a| < 2^24 the correctly rounded float quotient of
-// two integers truncates to the exact answer (a non-integer quotient is at least 1/b away from an integer, the
-// rounding error is below |a/b| * 2^-24), which is several times cheaper than the emulated 32-bit division.
-__device__ __forceinline__ int cdiv_trunc(int a, int b) {
-    if (abs(a) < (1 << 24)) return (int)__fdiv_rn((float)a, (float)b);
-    return a / b;
-}
-
-// pygame 1.9 draw_fillpoly, one scanline: x spans (inclusive) of polygon (vx, vy)[n] at row V.
-// Up to two spans (outlines with <= 8 vertices used here never give more); empty span = (1, 0).
-__device__ __forceinline__ short4 scanline_spans(const short* vx, const short* vy, int n, int V, int maxy) {
-    int xs[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
-    int m = 0;
-    int yp = vy[n - 1], xp = vx[n - 1];                   // previous vertex (edge i runs from vertex i - 1 to vertex i)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (i >= n) break;
-        const int yc = vy[i], xc = vx[i];
-        int y1 = yp, y2 = yc, x1 = xp, x2 = xc;
-        yp = yc; xp = xc;
-        if (y1 > y2) { int t = y1; y1 = y2; y2 = t; t = x1; x1 = x2; x2 = t; }
-        if (y1 != y2 && ((V >= y1 && V < y2) || (V == maxy && V > y1 && V <= y2))) {
-            const int x = cdiv_trunc((V - y1) * (x2 - x1), y2 - y1) + x1;      // C integer division
-            if (m == 0) xs[0] = x; else if (m == 1) xs[1] = x; else if (m == 2) xs[2] = x; else if (m == 3) xs[3] = x;
-            ++m;
-        }
-    }
-    // sort (unused slots hold INT_MAX): 4-element network
-#define CSWAP(a, b) { const int lo_ = min(xs[a], xs[b]), hi_ = max(xs[a], xs[b]); xs[a] = lo_; xs[b] = hi_; }
-    CSWAP(0, 1) CSWAP(2, 3) CSWAP(0, 2) CSWAP(1, 3) CSWAP(1, 2)
-#undef CSWAP
-    m = min(m, 4);
-    short4 r = make_short4(1, 0, 1, 0);
-    if (m >= 2) { r.x = (short)xs[0]; r.y = (short)xs[1]; }
-    if (m >= 4) { r.z = (short)xs[2]; r.w = (short)xs[3]; }
-    return r;
 }
 
 // pygame.draw.rect(screen, color, (x, y, w, h)) = polygon (l, t), (r, t), (r, b), (l, b), r = x + w - 1, b = y + h - 1
@@ -270,35 +233,6 @@ __device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, un
     }
 }
 
-// Scanline span tables of every road polygon (tile, kerb) of env e's track, in road-map pixels: they depend on the track
-// only, so they are scanned once per reset rather than once per frame in the render kernel.  `nthreads` threads, thread
-// `tid` of them; one (tile, table row) per thread and pass.
-__device__ void build_tile_spans(const CarDev& p, int e, int tid, int nthreads) {
-    const int n_track = p.n_track[e];
-    const CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
-    short4* out = p.tile_spans + (size_t)e * CAR_MAX_TRACK * CAR_SPAN_ROWS;
-    for (int item = tid; item < n_track * CAR_SPAN_ROWS; item += nthreads) {
-        const int t = item / CAR_SPAN_ROWS, slot = item % CAR_SPAN_ROWS;
-        const bool kerb = slot >= CAR_SPAN_TILE_ROWS;
-        const int r = kerb ? slot - CAR_SPAN_TILE_ROWS : slot;
-        const CarTile* T = tiles + t;
-        if (kerb && !(T->flags & 2)) continue;
-        const short* vx = kerb ? T->kmx : T->mx;
-        const short* vy = kerb ? T->kmy : T->my;
-        const int n = kerb ? 4 : 5;
-        int miny = vy[0], maxy = vy[0];
-        for (int i = 1; i < n; ++i) { miny = min(miny, (int)vy[i]); maxy = max(maxy, (int)vy[i]); }
-        if (r > maxy - miny) continue;
-        out[(size_t)t * CAR_SPAN_ROWS + slot] = scanline_spans(vx, vy, n, miny + r, maxy);
-    }
-}
-
-// all envs of the shard (crl_car_reset); the auto-reset pass builds the tables of the finished envs in
-// car_frame_setup_kernel instead (no extra launch on the step path)
-__global__ void __launch_bounds__(256) car_tile_spans_kernel(CarDev p) {
-    for (int e = blockIdx.x; e < p.n; e += gridDim.x) build_tile_spans(p, e, threadIdx.x, blockDim.x);
-}
-
 // Per-frame setup, one warp per (env, player) frame: camera and the integer screen -> road-map mapping (lane 0), then
 // the cull of the road tiles against the visible window (all lanes).  Kept out of the render kernel, where these
 // serial steps would stall a whole CTA.
@@ -311,7 +245,6 @@ car_frame_setup_kernel(CarDev p, int only_done, int which) {
     const int e = frame / p.players;
     if (only_done && !p.env_done[e]) return;
     if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
-    if (only_done && frame % p.players == 0) build_tile_spans(p, e, lane, 32);   // the env was just reset: new track
     const CarHullConst* K = p.consts;
     if (lane == 0) {
         // ---- camera_update("rgb_array"): hull.position + R(angle) * (0, 16) ----
@@ -356,8 +289,9 @@ car_frame_setup_kernel(CarDev p, int only_done, int which) {
     const FrameMap fm = s_fm[warp];
     // ---- cull: road tiles whose centre, mapped to the screen, lies within the window grown by the tile's reach
     //      (farthest kerb corner 8.7 units = 15.4 px, plus the slack of the integer pipeline) ----
-    const int n_track = p.n_track[e];
-    const float2* centres = p.tile_centres + (size_t)e * CAR_MAX_TRACK;
+    const int slot = car_slot(p, e);
+    const int n_track = p.n_track[slot];
+    const float2* centres = p.tile_centres + (size_t)slot * CAR_MAX_TRACK;
     uint16_t* cand = p.frame_cand + (size_t)frame * CAR_MAX_CAND;
     const double obs_scale = car_obs_scale();
     const float reach = 20.0f;
@@ -444,8 +378,9 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     const int* checker = K->checker;
     const FrameMap fm = p.frame_map[frame];           // written by car_frame_setup_kernel
     const double obs_scale = car_obs_scale();
-    const int n_track = p.n_track[e];
-    const CarTile* tiles = p.tiles + (size_t)e * CAR_MAX_TRACK;
+    const int slot = car_slot(p, e);
+    const int n_track = p.n_track[slot];
+    const CarTile* tiles = p.tiles + (size_t)slot * CAR_MAX_TRACK;
     const int C = p.c;
     uint8_t* ring = p.ring + (size_t)frame * C * CAR_PIX;
     const bool fill_all = only_done != 0 || p.ring_pos[e] < 0;
@@ -459,7 +394,7 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     for (int i = tid; i < WALK_CELLS * MASK_WORDS; i += RASTER_THREADS) (&S.cell_mask[0][0])[i] = 0u;
     if (tid == 255) {
         S.n_poly = 0; S.pool_used = 0; S.overflow = 0; S.copy_next = 0; S.hud_late = 0;
-        S.tiles = tiles; S.env_spans = p.tile_spans + (size_t)e * CAR_MAX_TRACK * CAR_SPAN_ROWS;
+        S.tiles = tiles; S.env_spans = p.tile_spans + (size_t)slot * CAR_MAX_TRACK * CAR_SPAN_ROWS;
     }
     if (tid >= 240 && tid < 248) {      // HUD inputs (render_indicators_for_pygame :645-670)
         const int k = tid - 240;
@@ -613,11 +548,6 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
             if (tdst) tdst[q] = vv;
         }
     }
-}
-
-cudaError_t launch_car_tile_spans(const CarDev& p, cudaStream_t s) {
-    car_tile_spans_kernel<<<min(p.n, 148 * 8), 256, 0, s>>>(p);
-    return cudaGetLastError();
 }
 
 __global__ void car_ring_advance_kernel(CarDev p, int only_done) {

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/crl_b200.h"
+#include "crl_host.h"
 #include "pong_common.cuh"
 
 using namespace crl;
@@ -135,7 +136,7 @@ uint64_t crl_launch_count(void) { return g_launches.load(); }
 
 int crl_pong_destroy(crl_pong* h) {
     if (!h) return CRL_OK;
-    cudaSetDevice(h->cfg.device);
+    CrlDeviceGuard guard(h->cfg.device);
     for (void* p : h->allocs) cudaFree(p);
     if (h->ev_state) cudaEventDestroy(h->ev_state);
     if (h->ev_copied) cudaEventDestroy(h->ev_copied);
@@ -161,7 +162,8 @@ int crl_pong_create(const crl_pong_config* cfg, crl_pong** out) {
         return fail(CRL_E_CUDA, "no CUDA device available (%s); this library has no CPU path",
                     cudaGetErrorString(e));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(CRL_E_INVALID, "device %d out of range", cfg->device);
-    CUDA_TRY(cudaSetDevice(cfg->device));
+    CrlDeviceGuard guard(cfg->device);
+    CUDA_TRY(guard.err);
     AreaTabs tabs;
     if (!build_tabs(cfg->resized_dim, &tabs))
         return fail(CRL_E_INVALID, "resized_dim %d needs more than %d taps per pixel", cfg->resized_dim, MAX_TAPS);
@@ -223,7 +225,7 @@ int crl_pong_create(const crl_pong_config* cfg, crl_pong** out) {
     d.tmpl = h->tmpl_dev;
 #undef ALLOC
     e = cudaMemcpy(h->tabs_dev, &tabs, sizeof tabs, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = pong_raster_init();
+    if (e == cudaSuccess) e = pong_raster_init(d.raster_grid);
     if (e == cudaSuccess) e = launch_pong_construct(d, 0);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -238,8 +240,9 @@ int crl_pong_create(const crl_pong_config* cfg, crl_pong** out) {
 #define CHECK_HANDLE(h)                                        \
     do {                                                       \
         if (!(h)) return fail(CRL_E_INVALID, "null handle");   \
-        CUDA_TRY(cudaSetDevice((h)->cfg.device));              \
-    } while (0)
+    } while (0);                                               \
+    CrlDeviceGuard crl_guard_((h)->cfg.device);                \
+    CUDA_TRY(crl_guard_.err)
 
 int crl_pong_load_atlas(crl_pong* h, const uint8_t* strips_host, size_t bytes, void* stream) {
     CHECK_HANDLE(h);
@@ -427,6 +430,10 @@ int crl_pong_check(crl_pong* h, void* stream) {
     int32_t flag = 0;
     CUDA_TRY(cudaMemcpyAsync(&flag, h->dev.serve_overrun, sizeof flag, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    if (flag != 0) {   // reported once: the flag is cleared so that later checks see later steps only
+        CUDA_TRY(cudaMemsetAsync(h->dev.serve_overrun, 0, sizeof flag, (cudaStream_t)stream));
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    }
     if (flag & 2) return fail(CRL_E_INVALID, "an action outside {0, 1, 2} (cPongDouble: or 999) was passed to step; it was played as 1 (stay)");
     if (flag & 1) return fail(CRL_E_SERVES, "injected serve table exhausted");
     return CRL_OK;

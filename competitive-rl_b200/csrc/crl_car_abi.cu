@@ -8,6 +8,7 @@
 
 #include "../../include/crl_b200.h"
 #include "car_common.cuh"
+#include "crl_host.h"
 
 using namespace crl;
 
@@ -33,7 +34,17 @@ struct crl_car {
     // crl_car_step of two-car envs: envs whose cars touch are stepped on a side stream while the others render
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fast = nullptr, ev_slow = nullptr;
+    // next tracks are generated ahead of time on this stream (car_pregen_kernel); at most one launch in flight
+    cudaStream_t pregen_stream = nullptr;
+    cudaEvent_t ev_pregen_go = nullptr, ev_pregen_done = nullptr;
+    bool pregen_in_flight = false;
     bool was_reset = false;
+    // crl_car_step_host staging
+    float* actions_stage = nullptr;
+    float* rew_stage = nullptr;
+    uint8_t* done_stage = nullptr;
+    int32_t* steps_stage = nullptr;
+    uint8_t* trunc_stage = nullptr;
 };
 
 // ---- car body mass data: b2PolygonShape::Set + ComputeMass + b2Body::ResetMassData, fp32 ----
@@ -190,14 +201,47 @@ cudaError_t car_alloc(crl_car* h, T** p, size_t count) {
     *p = (T*)q;
     return cudaMemset(q, 0, count * sizeof(T) + 16);
 }
+
+// Start generating the next track of every env that has none, behind everything queued on `s` so far, on the handle's
+// side stream -- unless the previous launch is still running (its successor will pick the newcomers up).  The main
+// stream never waits for the side stream: an env that finishes again before its next track is ready generates it
+// inside car_reset_kernel.  High stream priority: the few warps that have work live ~1.5 ms each (the curve walk is a
+// serial fp64 chain) and should start at once; the others exit immediately.
+int kick_pregen(crl_car* h, cudaStream_t s) {
+    if (h->pregen_in_flight) {
+        const cudaError_t q = cudaEventQuery(h->ev_pregen_done);
+        if (q == cudaErrorNotReady) return CRL_OK;
+        if (q != cudaSuccess) return crl_set_error(CRL_E_CUDA, "pregen: %s", cudaGetErrorString(q));
+        h->pregen_in_flight = false;
+    }
+    CUDA_TRY(cudaEventRecord(h->ev_pregen_go, s));
+    CUDA_TRY(cudaStreamWaitEvent(h->pregen_stream, h->ev_pregen_go, 0));
+    LAUNCH(launch_car_pregen(h->dev, h->pregen_stream), 1);
+    CUDA_TRY(cudaEventRecord(h->ev_pregen_done, h->pregen_stream));
+    h->pregen_in_flight = true;
+    return CRL_OK;
+}
+
+// The inputs of track generation changed (seed, injected tables, fixed tracks): tracks generated ahead are dropped
+// and their attempts given back, so that what follows does not depend on how far the side stream had got.
+int discard_pregen(crl_car* h, cudaStream_t s) {
+    CUDA_TRY(cudaStreamSynchronize(h->pregen_stream));
+    h->pregen_in_flight = false;
+    LAUNCH(launch_car_discard_next(h->dev, s), 1);
+    return CRL_OK;
+}
 }  // namespace
 
 extern "C" {
 
 int crl_car_destroy(crl_car* h) {
     if (!h) return CRL_OK;
-    cudaSetDevice(h->cfg.device);
+    CrlDeviceGuard guard(h->cfg.device);
+    if (h->pregen_stream) cudaStreamSynchronize(h->pregen_stream);
     for (void* p : h->allocs) cudaFree(p);
+    if (h->ev_pregen_go) cudaEventDestroy(h->ev_pregen_go);
+    if (h->ev_pregen_done) cudaEventDestroy(h->ev_pregen_done);
+    if (h->pregen_stream) cudaStreamDestroy(h->pregen_stream);
     if (h->ev_fast) cudaEventDestroy(h->ev_fast);
     if (h->ev_slow) cudaEventDestroy(h->ev_slow);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -212,12 +256,14 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     if (cfg->num_players != 1 && cfg->num_players != 2) return crl_set_error(CRL_E_INVALID, "num_players must be 1 or 2");
     if (cfg->frame_stack < 0 || cfg->frame_stack > CAR_MAX_STACK)
         return crl_set_error(CRL_E_INVALID, "frame_stack must be in [0, %d]", CAR_MAX_STACK);
+    if (cfg->done_mode != 0 && cfg->done_mode != 1) return crl_set_error(CRL_E_INVALID, "done_mode must be 0 (any car) or 1 (car 0)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
         return crl_set_error(CRL_E_CUDA, "no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
     if (cfg->device < 0 || cfg->device >= ndev) return crl_set_error(CRL_E_INVALID, "device %d out of range", cfg->device);
-    CUDA_TRY(cudaSetDevice(cfg->device));
+    CrlDeviceGuard guard(cfg->device);
+    CUDA_TRY(guard.err);
     crl_car* h = new crl_car();
     h->cfg = *cfg;
     CarDev& d = h->dev;
@@ -226,6 +272,7 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     d.n = cfg->num_envs; d.players = cfg->num_players; d.c = cfg->frame_stack > 0 ? cfg->frame_stack : 1;
     d.action_repeat = cfg->action_repeat > 0 ? cfg->action_repeat : 1;
     d.max_episode_steps = cfg->max_episode_steps;
+    d.done_mode = cfg->done_mode;
     d.first_env = cfg->first_env; d.seed = cfg->seed;
 #define ALLOC(ptr, count)                                                                   \
     do {                                                                                    \
@@ -235,8 +282,10 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
             return crl_set_error(CRL_E_CUDA, "cudaMalloc: %s", cudaGetErrorString(_e));      \
         }                                                                                   \
     } while (0)
-    ALLOC(d.n_track, n); ALLOC(d.tiles, n * CAR_MAX_TRACK); ALLOC(d.samples, n * CAR_MAX_SAMPLES);
-    ALLOC(d.start_pose, n * 3); ALLOC(d.track_pts, n * CAR_MAX_TRACK * 3); ALLOC(d.step_count, n); ALLOC(d.elapsed, n); ALLOC(d.reset_count, n);
+    ALLOC(d.n_track, 2 * n); ALLOC(d.tiles, 2 * n * CAR_MAX_TRACK); ALLOC(d.samples, 2 * n * CAR_MAX_SAMPLES);
+    ALLOC(d.start_pose, 2 * n * 3); ALLOC(d.track_pts, 2 * n * CAR_MAX_TRACK * 3);
+    ALLOC(d.sel, n); ALLOC(d.next_state, n); ALLOC(d.next_att0, n); ALLOC(d.raw_ring, n * CAR_RAW_RING * 3);
+    ALLOC(d.step_count, n); ALLOC(d.elapsed, n); ALLOC(d.reset_count, n);
     ALLOC(d.attempt_count, n); ALLOC(d.inv_dt0, n); ALLOC(d.env_done, n); ALLOC(d.ring_pos, n);
     ALLOC(d.body, nc * 40); ALLOC(d.joint, nc * 24); ALLOC(d.wheel, nc * 8); ALLOC(d.reward, nc * 2);
     ALLOC(d.counters, nc * 4); ALLOC(d.touching, nc * 64); ALLOC(d.visited, nc * 16);
@@ -248,7 +297,8 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
         d.frame_map = reinterpret_cast<FrameMap*>(fmraw);
     }
     ALLOC(d.frame_cand, nc * CAR_MAX_CAND); ALLOC(d.frame_ncand, nc);
-    ALLOC(d.tile_spans, n * CAR_MAX_TRACK * CAR_SPAN_ROWS); ALLOC(d.tile_centres, n * CAR_MAX_TRACK);
+    ALLOC(d.tile_spans, 2 * n * CAR_MAX_TRACK * CAR_SPAN_ROWS); ALLOC(d.tile_centres, 2 * n * CAR_MAX_TRACK);
+    ALLOC(h->actions_stage, nc * 2); ALLOC(h->rew_stage, nc); ALLOC(h->done_stage, n); ALLOC(h->steps_stage, n); ALLOC(h->trunc_stage, n);
     if (P == 2) { ALLOC(d.contacts, n * CAR_MAX_CONTACTS); ALLOC(d.n_contacts, n); ALLOC(d.slow_list, n); ALLOC(d.slow_count, 1); }
     ALLOC(d.deferred, n);
     CarHullConst* kdev = nullptr;
@@ -266,6 +316,17 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
         return crl_set_error(CRL_E_CUDA, "init: %s", cudaGetErrorString(e));
     }
     d.consts = kdev;
+    {
+        int lo = 0, hi = 0;
+        e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->pregen_stream, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pregen_go, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pregen_done, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            crl_car_destroy(h);
+            return crl_set_error(CRL_E_CUDA, "pregen stream: %s", cudaGetErrorString(e));
+        }
+    }
     *out = h;
     return CRL_OK;
 }
@@ -273,8 +334,9 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
 #define CHECK_HANDLE(h)                                               \
     do {                                                              \
         if (!(h)) return crl_set_error(CRL_E_INVALID, "null handle"); \
-        CUDA_TRY(cudaSetDevice((h)->cfg.device));                     \
-    } while (0)
+    } while (0);                                                      \
+    CrlDeviceGuard crl_guard_((h)->cfg.device);                       \
+    CUDA_TRY(crl_guard_.err)
 
 int crl_car_load_glyphs(crl_car* h, const uint8_t* glyphs_host, size_t bytes, void* stream) {
     CHECK_HANDLE(h);
@@ -296,6 +358,7 @@ int crl_car_inject_tracks(crl_car* h, const double* draws_host, int32_t k_draws,
     const size_t cnt = (size_t)h->dev.n * k_draws * CAR_DRAWS;
     CUDA_TRY(car_alloc(h, &dd, cnt));
     CUDA_TRY(cudaMemcpyAsync(dd, draws_host, cnt * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (int r = discard_pregen(h, s)) return r;
     h->dev.track_draws = dd; h->dev.k_draws = k_draws;
     if (birth_host && k_birth > 0) {
         int32_t* bb = nullptr;
@@ -313,6 +376,8 @@ int crl_car_inject_tracks(crl_car* h, const double* draws_host, int32_t k_draws,
 int crl_car_load_tracks(crl_car* h, const double* pts_host, const int32_t* counts_host, int32_t n_tracks, void* stream) {
     CHECK_HANDLE(h);
     cudaStream_t s = (cudaStream_t)stream;
+    if (int r = discard_pregen(h, s)) return r;
+    CUDA_TRY(cudaStreamSynchronize(s));
     if (n_tracks <= 0) {                       // back to generated tracks
         h->dev.fixed_tracks = nullptr; h->dev.fixed_counts = nullptr; h->dev.n_fixed = 0;
         return CRL_OK;
@@ -339,10 +404,9 @@ int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream) {
     CUDA_TRY(cudaMemsetAsync(h->dev.ring_pos, 0xFF, (size_t)h->dev.n * sizeof(int32_t), s));
     CUDA_TRY(cudaMemsetAsync(h->dev.env_done, 0, (size_t)h->dev.n, s));
     LAUNCH(launch_car_reset(h->dev, 0, s), 1);
-    LAUNCH(launch_car_tile_spans(h->dev, s), 1);
     LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, nullptr, s), 3);
     h->was_reset = true;
-    return CRL_OK;
+    return kick_pregen(h, s);
 }
 
 int crl_car_step_state(crl_car* h, const float* actions_dev, float* rew_dev, uint8_t* done_dev,
@@ -362,7 +426,7 @@ int crl_car_render_obs(crl_car* h, uint8_t* obs_dev, uint8_t* term_obs_dev, void
     LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, term_obs_dev, s), 3);   // post-step frame (terminal obs of finished envs)
     LAUNCH(launch_car_reset(h->dev, 1, s), 1);                                 // auto-reset of finished envs
     LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 3);        // their reset observation
-    return CRL_OK;
+    return kick_pregen(h, s);
 }
 
 int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* rew_dev, uint8_t* done_dev,
@@ -397,6 +461,39 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
     LAUNCH(launch_car_render(h->dev, 0, 2, 1, obs_dev, term_obs_dev, s), 3);   // frames of the listed envs; ring moves on
     LAUNCH(launch_car_reset(h->dev, 1, s), 1);                                 // auto-reset of finished envs
     LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 3);        // their reset observation
+    return kick_pregen(h, s);
+}
+
+int crl_car_seed(crl_car* h, uint64_t seed, void* stream) {
+    CHECK_HANDLE(h);
+    if (int r = discard_pregen(h, (cudaStream_t)stream)) return r;
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    h->dev.seed = seed;
+    return CRL_OK;
+}
+
+int crl_car_set_elapsed(crl_car* h, const int32_t* elapsed_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (!elapsed_dev) return crl_set_error(CRL_E_INVALID, "null buffer");
+    CUDA_TRY(cudaMemcpyAsync(h->dev.elapsed, elapsed_dev, (size_t)h->dev.n * sizeof(int32_t), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return CRL_OK;
+}
+
+int crl_car_step_host(crl_car* h, const float* actions_host, uint8_t* obs_dev, uint8_t* obs_host, float* rew_host,
+                      uint8_t* done_host, int32_t* num_steps_host, uint8_t* truncated_host, uint8_t* term_obs_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (!actions_host || !obs_dev || !rew_host || !done_host) return crl_set_error(CRL_E_INVALID, "null host buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)h->dev.n, nc = n * h->dev.players;
+    CUDA_TRY(cudaMemcpyAsync(h->actions_stage, actions_host, nc * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (int r = crl_car_step(h, h->actions_stage, obs_dev, h->rew_stage, h->done_stage, h->steps_stage, h->trunc_stage,
+                             term_obs_dev, stream)) return r;
+    CUDA_TRY(cudaMemcpyAsync(rew_host, h->rew_stage, nc * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(done_host, h->done_stage, n, cudaMemcpyDeviceToHost, s));
+    if (num_steps_host) CUDA_TRY(cudaMemcpyAsync(num_steps_host, h->steps_stage, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (truncated_host) CUDA_TRY(cudaMemcpyAsync(truncated_host, h->trunc_stage, n, cudaMemcpyDeviceToHost, s));
+    if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, obs_dev, nc * h->dev.c * CAR_PIX, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     return CRL_OK;
 }
 
@@ -411,14 +508,17 @@ int crl_car_get_track(crl_car* h, int32_t env, int32_t* n_out, double* pts_host,
     CHECK_HANDLE(h);
     if (env < 0 || env >= h->dev.n || !n_out) return crl_set_error(CRL_E_INVALID, "bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
-    int32_t n = 0;
-    CUDA_TRY(cudaMemcpyAsync(&n, h->dev.n_track + env, sizeof n, cudaMemcpyDeviceToHost, s));
+    int32_t n = 0, sel = 0;
+    CUDA_TRY(cudaMemcpyAsync(&sel, h->dev.sel + env, sizeof sel, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    const size_t slot = (size_t)env + (size_t)h->dev.n * (sel ? 1 : 0);
+    CUDA_TRY(cudaMemcpyAsync(&n, h->dev.n_track + slot, sizeof n, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     *n_out = n;
     if (pts_host) {
         const int m = n < max_points ? n : max_points;
         if (m > 0)
-            CUDA_TRY(cudaMemcpy(pts_host, h->dev.track_pts + (size_t)env * CAR_MAX_TRACK * 3, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(pts_host, h->dev.track_pts + slot * CAR_MAX_TRACK * 3, (size_t)m * 3 * sizeof(double), cudaMemcpyDeviceToHost));
     }
     return CRL_OK;
 }

@@ -107,6 +107,7 @@ struct PongDev {
     int text_stride;           // bytes per text_tab entry (multiple of 16)
     const void* fast_tabs;     // FastTabs<dim> image for the hot kernel (nullptr: dim not specialised)
     int fast_ok;               // atlas rows sharing a dst row with the arena are pure white
+    int raster_grid[2];        // persistent grid of the hot kernel on this handle's device: [0] 84x84, [1] 42x42
 };
 
 // ---- Philox4x32-10 (counter-based; streams keyed by seed and global env index) ----
@@ -139,7 +140,7 @@ cudaError_t launch_pong_build_tables(const PongDev& p, uint8_t* text_tab, uint8_
 cudaError_t launch_pong_raster(const PongDev& p, const FrameSpec* hist, uint8_t* obs0, uint8_t* obs1, cudaStream_t s);
 cudaError_t launch_pong_raster_generic(const PongDev& p, const FrameSpec* hist, const uint8_t* only_done,
                                        uint8_t* obs0, uint8_t* obs1, cudaStream_t s);
-cudaError_t pong_raster_init();
+cudaError_t pong_raster_init(int grid_out[2]);
 size_t pong_fast_tabs_bytes(int dim);
 bool pong_fast_tabs_fill(const AreaTabs& a, int text_stride, void* host_buf);   // false: geometry not supported
 cudaError_t launch_pong_build_bat_lut(int dim, void* fast_tabs_dev, cudaStream_t s);

@@ -509,10 +509,8 @@ cudaError_t launch_pong_build_bat_lut(int dim, void* fast_tabs_dev, cudaStream_t
     return cudaGetLastError();
 }
 
-static int g_grid[2] = {0, 0};
-
-// per-device: opt in to the dynamic shared memory size and size the persistent grid
-cudaError_t pong_raster_init() {
+// per device (called at handle creation): opt in to the dynamic shared memory size and size the persistent grid
+cudaError_t pong_raster_init(int g_grid[2]) {
     cudaError_t e;
     int dev = 0, sms = 0, nb = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -546,11 +544,11 @@ cudaError_t launch_pong_raster(const PongDev& p, const FrameSpec* hist, uint8_t*
     cudaError_t me = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), s);
     if (me != cudaSuccess) return me;
     if (p.dim == 84) {
-        const unsigned grid = (unsigned)min((long long)g_grid[0], want);
+        const unsigned grid = (unsigned)min((long long)p.raster_grid[0], want);
         pong_raster_fast_kernel<84><<<grid, FAST_WARPS * 32, fast_smem_bytes<84>(), s>>>(
             p, hist, obs0, obs1, reinterpret_cast<const FastTabs<84>*>(p.fast_tabs));
     } else {
-        const unsigned grid = (unsigned)min((long long)g_grid[1], want);
+        const unsigned grid = (unsigned)min((long long)p.raster_grid[1], want);
         pong_raster_fast_kernel<42><<<grid, FAST_WARPS * 32, fast_smem_bytes<42>(), s>>>(
             p, hist, obs0, obs1, reinterpret_cast<const FastTabs<42>*>(p.fast_tabs));
     }

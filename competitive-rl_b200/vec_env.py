@@ -216,7 +216,7 @@ class CudaPongVecEnv(VecEnv):
 
     def __init__(self, env_id="cPongDouble-v0", num_envs=1, resized_dim=42, frame_stack=None, seed=0,
                  asynchronous=False, device=None, max_num_rounds=21, atlas=None, serves=None, first_env=0,
-                 return_numpy=False, n_buffers=2):
+                 return_numpy=False, n_buffers=2, stack_mode="stack"):
         if env_id not in ("cPong-v0", "cPongDouble-v0"):
             raise ValueError("unsupported env id %r" % (env_id,))
         if not torch.cuda.is_available():
@@ -228,6 +228,9 @@ class CudaPongVecEnv(VecEnv):
         self.c = int(frame_stack) if frame_stack else 1
         self.asynchronous = bool(asynchronous)
         self.return_numpy = bool(return_numpy)
+        if stack_mode not in ("stack",):
+            raise ValueError("stack_mode must be 'stack'")
+        self.stack_mode = stack_mode
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -276,6 +279,16 @@ class CudaPongVecEnv(VecEnv):
         self.envs = _EnvList(self)
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def _store(self):
+        """the tensors the rasteriser writes (stack mode: the observations themselves)"""
+        return self._obs if self.n_agents == 2 else [self._obs[0], self._obs[0]]
+
+    @property
+    def bytes_per_env_step(self):
+        """observation bytes the rasteriser writes per env-step"""
+        return self.n_agents * self.c * self.dim * self.dim
+
     def _bind(self, k):
         b = self._sets[k]
         self._cur = k

@@ -38,7 +38,7 @@ extern "C" {
 #define CRL_E_STATE (-3)     /* call order violated (e.g. step before atlas/reset) */
 #define CRL_E_SERVES (-4)    /* injected serve table exhausted */
 
-#define CRL_ABI_VERSION 1
+#define CRL_ABI_VERSION 2
 #define CRL_PONG_ATLAS_BYTES (22 * 22 * 34 * 160 * 3)
 #define CRL_PONG_STATE_DOUBLES 10
 
@@ -167,6 +167,10 @@ typedef struct crl_car_config {
     int32_t action_repeat;      /* CarRacing(action_repeat=...), 0/None = 1 */
     int32_t max_episode_steps;  /* gym registry TimeLimit (car_racing/register.py:14,21): 1000; 0 = off */
     int32_t device;
+    int32_t done_mode;          /* two cars: 0 = env done when ANY car is (FlattenMultiAgentObservation.step,
+                                   utils/atari_wrappers.py:323-331, the make_envs path); 1 = when car 0 is
+                                   (make_competitive_car_racing returns d[0], make_competitive_car_racing.py:29-33) */
+    int32_t reserved;           /* must be 0 */
     uint64_t seed;              /* track / birth-place RNG (Philox) */
     int64_t first_env;          /* global index of env 0 of this shard */
 } crl_car_config;
@@ -194,6 +198,11 @@ int crl_car_inject_tracks(crl_car* h, const double* draws_host, int32_t k_draws,
 int crl_car_load_tracks(crl_car* h, const double* pts_host, const int32_t* counts_host, int32_t n_tracks, void* stream);
 int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream);
 
+/* VecEnv.seed(seed) (base_vec_env.py:163-176 -> CarRacing.seed, car_racing_multi_players.py:248-250): re-keys the
+ * track / birth-place RNG for the tracks generated from now on (env i uses the stream of its global index).  Tracks
+ * generated ahead of time under the old seed are dropped.  Synchronises. */
+int crl_car_seed(crl_car* h, uint64_t seed, void* stream);
+
 /* VecEnv.step with auto-reset.
  *   actions_dev     float32 [num_envs][num_players][2]  (steer, gas/brake), clipped like process_action
  *   rew_dev         float32 [num_envs][num_players]     per-car step reward (the Double wrapper returns [:, 0])
@@ -204,6 +213,18 @@ int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream);
  *                   info["terminal_observation"]. */
 int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* rew_dev, uint8_t* done_dev,
                  int32_t* num_steps_dev, uint8_t* truncated_dev, uint8_t* term_obs_dev, void* stream);
+
+/* Pre-age the envs: TimeLimit._elapsed_steps of every env (gym TimeLimit, car_racing/register.py:14,21), int32
+ * [num_envs] on the device.  A rollout whose envs were all reset together truncates them all on the same step; a
+ * long-running trainer sees them spread out, which is what this reproduces for measurements and tests. */
+int crl_car_set_elapsed(crl_car* h, const int32_t* elapsed_dev, void* stream);
+
+/* Host-buffer form of crl_car_step (what a numpy caller of the reference's VecEnv.step sees): copies the actions
+ * host->device, steps, copies rew / done / num_steps / truncated back and, when obs_host is non-NULL, the observation
+ * too.  obs_dev (and term_obs_dev, may be NULL) are device staging owned by the caller.  Synchronises the stream. */
+int crl_car_step_host(crl_car* h, const float* actions_host, uint8_t* obs_dev, uint8_t* obs_host, float* rew_host,
+                      uint8_t* done_host, int32_t* num_steps_host, uint8_t* truncated_host, uint8_t* term_obs_dev,
+                      void* stream);
 
 /* the two halves of crl_car_step: game core (no rendering, no auto-reset), then
  * render + auto-reset + render of the reset envs */

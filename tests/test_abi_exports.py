@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_native.EXPORTS) == names
-    assert _native.load().crl_abi_version() == 1
+    assert _native.load().crl_abi_version() == 2
 
 
 def test_no_cpu_fallback():
