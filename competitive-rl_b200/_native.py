@@ -18,11 +18,11 @@ EXPORTS = [
     "crl_pong_inject_serves", "crl_pong_seed", "crl_pong_reset", "crl_pong_step", "crl_pong_step_state",
     "crl_pong_render_obs", "crl_pong_render_obs_generic", "crl_pong_terminal_obs", "crl_pong_step_host",
     "crl_pong_get_state", "crl_pong_set_state", "crl_pong_render_raw", "crl_pong_random_actions",
-    "crl_launch_count", "crl_pong_check", "crl_pong_get_stats",
+    "crl_launch_count", "crl_pong_check", "crl_pong_get_stats", "crl_pong_ring_phase",
     "crl_car_create", "crl_car_destroy", "crl_car_load_glyphs", "crl_car_inject_tracks", "crl_car_load_tracks", "crl_car_reset",
     "crl_car_step", "crl_car_step_state", "crl_car_render_obs", "crl_car_get_state", "crl_car_get_track",
     "crl_car_random_actions", "crl_car_get_stats", "crl_car_get_contacts", "crl_car_check",
-    "crl_car_seed", "crl_car_step_host", "crl_car_set_elapsed",
+    "crl_car_seed", "crl_car_step_host", "crl_car_set_elapsed", "crl_car_set_state", "crl_car_ring_phase",
 ]
 
 
@@ -30,6 +30,7 @@ class PongConfig(ctypes.Structure):
     _fields_ = [
         ("num_envs", ctypes.c_int32), ("n_agents", ctypes.c_int32), ("resized_dim", ctypes.c_int32),
         ("frame_stack", ctypes.c_int32), ("max_num_rounds", ctypes.c_int32), ("device", ctypes.c_int32),
+        ("stack_mode", ctypes.c_int32), ("zero_on_done", ctypes.c_int32),
         ("seed", ctypes.c_uint64), ("first_env", ctypes.c_int64),
     ]
 
@@ -38,7 +39,7 @@ class CarConfig(ctypes.Structure):
     _fields_ = [
         ("num_envs", ctypes.c_int32), ("num_players", ctypes.c_int32), ("frame_stack", ctypes.c_int32),
         ("action_repeat", ctypes.c_int32), ("max_episode_steps", ctypes.c_int32), ("device", ctypes.c_int32),
-        ("done_mode", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("done_mode", ctypes.c_int32), ("stack_mode", ctypes.c_int32),
         ("seed", ctypes.c_uint64), ("first_env", ctypes.c_int64),
     ]
 
@@ -46,11 +47,38 @@ class CarConfig(ctypes.Structure):
 DEFAULT_CAR_GLYPHS = os.path.join(_HERE, "data", "car_hud_glyphs.npz")
 
 
-class CrlError(RuntimeError):
-    pass
-
-
 _lib = None
+_ext = None
+EXT_PATH = os.path.join(_HERE, "_crl_torch.so")
+
+
+def ext():
+    """The torch C++ extension of the host layer (csrc/crl_torch.cpp, built in-tree by build.py).  The vec-envs call the
+    library only through it; there is no ctypes or CPU fallback behind them: a missing extension is an ImportError."""
+    global _ext
+    if _ext is None:
+        if not os.path.exists(EXT_PATH) or not os.path.exists(LIB_PATH):
+            raise ImportError(
+                "%s not found: the CUDA extension is not built. Run `python competitive-rl_b200/build.py` "
+                "(there is no CPU fallback)." % (EXT_PATH if os.path.exists(LIB_PATH) else LIB_PATH))
+        import importlib.util
+        import sys
+        import torch  # noqa: F401  (loads libc10 / libtorch before the extension)
+        name = (__name__.rsplit(".", 1)[0] + "._crl_torch") if "." in __name__ else "_crl_torch"
+        spec = importlib.util.spec_from_file_location(name, EXT_PATH)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        sys.modules[name] = mod
+        _ext = mod
+    return _ext
+
+
+try:                      # one exception type whichever way the library was called
+    CrlError = ext().CrlError
+except ImportError:       # not built yet; the ctypes path below still reports errors
+
+    class CrlError(RuntimeError):
+        pass
 
 
 def load():
@@ -84,6 +112,7 @@ def load():
     L.crl_pong_render_raw.argtypes = [vp, i32, vp, vp, vp]
     L.crl_pong_random_actions.argtypes = [vp, i32, u64, u64, vp]
     L.crl_pong_check.argtypes = [vp, vp]
+    L.crl_pong_ring_phase.argtypes = [vp]
     L.crl_pong_get_stats.argtypes = [vp, vp, vp]
     L.crl_car_create.argtypes = [ctypes.POINTER(CarConfig), ctypes.POINTER(vp)]
     L.crl_car_destroy.argtypes = [vp]
@@ -96,6 +125,8 @@ def load():
     L.crl_car_seed.argtypes = [vp, u64, vp]
     L.crl_car_step_host.argtypes = [vp] * 10
     L.crl_car_set_elapsed.argtypes = [vp, vp, vp]
+    L.crl_car_set_state.argtypes = [vp, vp, vp]
+    L.crl_car_ring_phase.argtypes = [vp]
     L.crl_car_render_obs.argtypes = [vp] * 4
     L.crl_car_get_state.argtypes = [vp, vp, vp]
     L.crl_car_get_track.argtypes = [vp, i32, ctypes.POINTER(i32), vp, i32, vp]

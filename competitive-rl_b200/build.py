@@ -67,5 +67,39 @@ def build(force=False, verbose=False):
     return OUT
 
 
+EXT_SRC = os.path.join(CSRC, "crl_torch.cpp")
+EXT_NAME = "_crl_torch"
+EXT_OUT = os.path.join(HERE, EXT_NAME + ".so")
+
+
+def build_torch_ext(force=False, verbose=False):
+    """The host layer's torch C++ extension (csrc/crl_torch.cpp): g++ against torch's headers, linked to libcrl_b200.so
+    next to it (rpath $ORIGIN).  In-tree like the library, so it travels to the GPU box with the snapshot."""
+    build(force=False, verbose=verbose)
+    deps = [EXT_SRC, os.path.join(CSRC, "..", "..", "include", "crl_b200.h"), os.path.abspath(__file__)]
+    if not force and not _newer(EXT_OUT, deps):
+        return EXT_OUT
+    import sysconfig
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        import torch
+        from torch.utils import cpp_extension as ce
+    inc = ce.include_paths() + [sysconfig.get_paths()["include"], "/usr/local/cuda/include"]
+    libdir = ce.library_paths()[0]
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-deprecated-declarations",
+           "-DTORCH_EXTENSION_NAME=" + EXT_NAME, "-DTORCH_API_INCLUDE_EXTENSION_H",
+           "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)]
+    for i in inc:
+        cmd += ["-isystem", i]
+    cmd += [EXT_SRC, "-o", EXT_OUT, "-L" + libdir, "-L" + HERE, "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch", "-ltorch_python",
+            "-l:libcrl_b200.so", "-Wl,-rpath,$ORIGIN", "-Wl,-rpath," + libdir]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return EXT_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_torch_ext(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -57,7 +57,12 @@ class LazyCarInfos(object):
 
 class CudaCarVecEnv(VecEnv):
     """actions: float (N, 2) for cCarRacing-v0, (N, 2, 2) for cCarRacingDouble-v0 (steer, gas/brake in [-1, 1]).
-    step -> (obs uint8 (N, players*C, 96, 96), rew float32, done bool (N,), infos)."""
+    step -> (obs uint8 (N, players*C, 96, 96), rew float32, done bool (N,), infos).
+
+    stack_mode="ring" (opt-in): the observation is a strided VIEW of an (N, players, 2C, 96, 96) double-write ring -- shape
+    (N, C, 96, 96) for one car, (N, 2, C, 96, 96) for two (player axis kept: the two players' windows cannot be one
+    uniformly strided channel axis; `.flatten(1, 2)` materialises the reference's (N, 2C, 96, 96) layout).  A step then
+    writes each new frame twice and copies nothing; the view of step t is valid until step t + 1."""
 
     def __init__(self, env_id="cCarRacing-v0", num_envs=1, frame_stack=4, action_repeat=None, seed=0,
                  asynchronous=False, device=None, max_episode_steps=1000, first_env=0, track_draws=None, birth=None,
@@ -66,13 +71,14 @@ class CudaCarVecEnv(VecEnv):
             raise ValueError("unsupported env id %r" % (env_id,))
         if not torch.cuda.is_available():
             raise RuntimeError("CudaCarVecEnv needs a CUDA device: this simulator has no CPU path")
-        self._lib = _native.load()
+        ext = _native.ext()
+        self._lib = _native.load()          # the plain C ABI, for callers that drive it directly (bench.py, tests)
         self.env_id, self.players = env_id, 2 if env_id == "cCarRacingDouble-v0" else 1
         self.c = int(frame_stack) if frame_stack else 1
         self.asynchronous, self.return_numpy, self.copy = bool(asynchronous), bool(return_numpy), bool(copy)
-        if stack_mode not in ("stack",):
-            raise ValueError("stack_mode must be 'stack'")
-        self.stack_mode = stack_mode
+        if stack_mode not in ("stack", "ring"):
+            raise ValueError("stack_mode must be 'stack' or 'ring'")
+        self.stack_mode, self.ring = stack_mode, stack_mode == "ring"
         if done_mode not in ("any", "car0"):
             raise ValueError("done_mode must be 'any' (make_envs) or 'car0' (make_competitive_car_racing)")
         self.max_episode_steps = int(max_episode_steps or 0)
@@ -84,30 +90,27 @@ class CudaCarVecEnv(VecEnv):
         obs_space = spaces.Box(0, 255, (ch, 96, 96), dtype=np.uint8)
         act_space = spaces.Box(-1, 1, (2,) if self.players == 1 else (self.players, 2), dtype=np.float32)
         VecEnv.__init__(self, n, obs_space, act_space)
-        cfg = _native.CarConfig(n, self.players, int(frame_stack or 0), int(action_repeat or 0), self.max_episode_steps,
-                                int(self.device.index), 1 if done_mode == "car0" else 0, 0, int(seed) & (2 ** 64 - 1),
-                                int(first_env))
-        h = ctypes.c_void_p()
-        with torch.cuda.device(self.device):
-            _native.check(self._lib.crl_car_create(ctypes.byref(cfg), ctypes.byref(h)))
-        self._h = h
+        self._impl = ext.Car(n, self.players, int(frame_stack or 0), int(action_repeat or 0), self.max_episode_steps,
+                             int(self.device.index), 1 if done_mode == "car0" else 0, 1 if self.ring else 0,
+                             int(seed) & (2 ** 64 - 1), int(first_env))
+        self._h = ctypes.c_void_p(self._impl.raw_handle())
         if isinstance(glyphs, str) and glyphs == "default":
             g = np.load(_native.DEFAULT_CAR_GLYPHS)
             glyphs = np.concatenate([g["bitmaps"].reshape(-1), g["advance"].reshape(-1)]).astype(np.uint8)
         if glyphs is not None:
-            glyphs = np.ascontiguousarray(glyphs, np.uint8)
-            _native.check(self._lib.crl_car_load_glyphs(self._h, glyphs.ctypes.data, glyphs.nbytes, self._stream()))
+            self._impl.load_glyphs(torch.from_numpy(np.ascontiguousarray(glyphs, np.uint8)))
         if track_draws is not None:
             self.inject_tracks(track_draws, birth)
         dev = self.device
+        self._ring = torch.empty((n, self.players, 2 * self.c, 96, 96), dtype=torch.uint8, device=dev) if self.ring else None
         self._sets = []
         for _ in range(max(1, int(n_buffers))):
             self._sets.append(dict(
-                obs=torch.empty((n, ch, 96, 96), dtype=torch.uint8, device=dev),
+                obs=self._ring if self.ring else torch.empty((n, ch, 96, 96), dtype=torch.uint8, device=dev),
                 term=torch.zeros((n, ch, 96, 96), dtype=torch.uint8, device=dev),
                 rew=torch.zeros((n, self.players), dtype=torch.float32, device=dev),
-                done=torch.zeros((n,), dtype=torch.uint8, device=dev),
-                trunc=torch.zeros((n,), dtype=torch.uint8, device=dev),
+                done=torch.zeros((n,), dtype=torch.bool, device=dev),
+                trunc=torch.zeros((n,), dtype=torch.bool, device=dev),
                 steps=torch.zeros((n,), dtype=torch.int32, device=dev)))
         self._cur = 0
         self._actions = torch.zeros((n, self.players, 2), dtype=torch.float32, device=dev)
@@ -119,8 +122,14 @@ class CudaCarVecEnv(VecEnv):
 
     @property
     def bytes_per_env_step(self):
-        """observation bytes written per env-step (36 864 / 73 728 with frame_stack 4)"""
-        return self.players * self.c * 96 * 96
+        """observation bytes written per env-step (36 864 / 73 728 with frame_stack 4; the ring
+        writes each new frame twice whatever the stack depth)"""
+        return self.players * (2 if self.ring else self.c) * 96 * 96
+
+    @property
+    def _store(self):
+        """the buffer the rasteriser writes (the observation itself, or the ring)"""
+        return [self._sets[self._cur]["obs"]]
 
     @staticmethod
     def _ptr(t):
@@ -131,11 +140,16 @@ class CudaCarVecEnv(VecEnv):
         (N, Kb, players) = shuffled birth_place_indices per reset."""
         d = np.ascontiguousarray(draws, np.float64)
         assert d.ndim == 3 and d.shape[0] == self.num_envs and d.shape[2] == 24
-        b = None if birth is None else np.ascontiguousarray(birth, np.int32)
-        with torch.cuda.device(self.device):
-            _native.check(self._lib.crl_car_inject_tracks(
-                self._h, d.ctypes.data, d.shape[1], None if b is None else b.ctypes.data, 0 if b is None else b.shape[1],
-                self._stream()))
+        b = None if birth is None else torch.from_numpy(np.ascontiguousarray(birth, np.int32))
+        self._impl.inject_tracks(torch.from_numpy(d), b)
+
+    def _obs_of(self, b):
+        """what the caller sees of buffer set b: the observation tensor, or the ring's current window"""
+        if not self.ring:
+            return b["obs"]
+        k = self._impl.ring_phase()
+        v = self._ring[:, :, k + 1:k + 1 + self.c]
+        return v[:, 0] if self.players == 1 else v
 
     def _out(self, t):
         if self.return_numpy:
@@ -160,7 +174,7 @@ class CudaCarVecEnv(VecEnv):
             assert 9 <= len(t) <= 512, "a track has 9..512 points"
             pts[k, :len(t)] = t
             counts[k] = len(t)
-        _native.check(self._lib.crl_car_load_tracks(self._h, pts.ctypes.data, counts.ctypes.data, len(arrs), self._stream()))
+        self._impl.load_tracks(torch.from_numpy(pts), torch.from_numpy(counts), len(arrs))
 
     def record_track(self, env, path=None):
         """CarRacing.reset(record_track_to=...) (:447-451): the current track of `env` in the reference's JSON format
@@ -179,22 +193,23 @@ class CudaCarVecEnv(VecEnv):
     def reset(self):
         self._cur = (self._cur + 1) % len(self._sets)
         b = self._sets[self._cur]
-        with torch.cuda.device(self.device):
-            _native.check(self._lib.crl_car_reset(self._h, self._ptr(b["obs"]), self._stream()))
+        self._impl.reset(b["obs"])
         self._waiting = False
-        return self._out(b["obs"])
+        return self._out(self._obs_of(b))
 
     def step_async(self, actions):
         if self._waiting:
             raise AlreadySteppingError()
-        a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions, np.float32))
-        self._actions.copy_(a.reshape(self._actions.shape), non_blocking=True)
+        if isinstance(actions, torch.Tensor) and actions.dtype == torch.float32 and actions.device == self.device \
+                and actions.is_contiguous() and actions.numel() == self._actions.numel():
+            a = actions                      # consumed in place
+        else:
+            a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions, np.float32))
+            self._actions.copy_(a.reshape(self._actions.shape), non_blocking=True)
+            a = self._actions
         self._cur = (self._cur + 1) % len(self._sets)
         b = self._sets[self._cur]
-        with torch.cuda.device(self.device):
-            _native.check(self._lib.crl_car_step(
-                self._h, self._ptr(self._actions), self._ptr(b["obs"]), self._ptr(b["rew"]), self._ptr(b["done"]),
-                self._ptr(b["steps"]), self._ptr(b["trunc"]), self._ptr(b["term"]), self._stream()))
+        self._impl.step(a, b["obs"], b["rew"], b["done"], b["steps"], b["trunc"], b["term"])
         self._waiting = True
 
     def step_wait(self):
@@ -202,67 +217,67 @@ class CudaCarVecEnv(VecEnv):
             raise NotSteppingError()
         self._waiting = False
         b = self._sets[self._cur]
+        obs = self._obs_of(b)
         if self.copy:
-            b = {k: v.clone() for k, v in b.items()}
-        done = b["done"].bool()
+            b = {k: v.clone() for k, v in b.items() if k != "obs"}
+        done = b["done"]
         rew = b["rew"][:, 0]          # FlattenMultiAgentObservation returns r[0]; single: the scalar reward
         infos = LazyCarInfos(self, b["steps"], b["rew"], b["done"], b["trunc"], b["term"])
         if not self.asynchronous:     # DummyVecEnv buffers: (N, 1)
             rew, done = rew[:, None], done[:, None]
         if self.return_numpy:
             rew, done, infos = rew.cpu().numpy(), done.cpu().numpy(), list(infos)
-        return self._out(b["obs"]), rew, done, infos
+        return self._out(obs), rew, done, infos
 
     def seed(self, seed=None):
         """VecEnv.seed: env i is seeded with seed + i (dummy_vec_env.py:65-69) and CarRacing.seed returns [seed]
         (car_racing_multi_players.py:248-250).  Here one key re-seeds the whole batch: env i draws its tracks and
         birth places from the Philox stream of (seed, first_env + i)."""
         if seed is not None:
-            with torch.cuda.device(self.device):
-                _native.check(self._lib.crl_car_seed(self._h, int(seed) & (2 ** 64 - 1), self._stream()))
+            self._impl.seed(int(seed) & (2 ** 64 - 1))
         return [[None if seed is None else seed + i] for i in range(self.num_envs)]
 
     def set_elapsed(self, elapsed):
         """Pre-age the envs: TimeLimit._elapsed_steps per env (int (N,)); spreads the truncations of a synchronously
         reset batch over the steps, like a long-running rollout."""
-        t = torch.as_tensor(elapsed).to(self.device, torch.int32).contiguous()
+        t = torch.as_tensor(np.asarray(elapsed)).to(self.device, torch.int32).contiguous()
         assert tuple(t.shape) == (self.num_envs,)
-        with torch.cuda.device(self.device):
-            _native.check(self._lib.crl_car_set_elapsed(self._h, self._ptr(t), self._stream()))
-            torch.cuda.current_stream(self.device).synchronize()
+        self._impl.set_elapsed(t)
+        torch.cuda.current_stream(self.device).synchronize()
 
     def get_state(self):
         s = torch.empty((self.num_envs * self.players, 24), dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
-            _native.check(self._lib.crl_car_get_state(self._h, self._ptr(s), self._stream()))
+        self._impl.get_state(s)
         return s.reshape(self.num_envs, self.players, 24)
 
+    def set_state(self, state):
+        """Debug / tests: put every car into `state` (N, players, 24) as get_state() lays it out (see crl_car_set_state)."""
+        s = torch.as_tensor(state, dtype=torch.float64).to(self.device).reshape(self.num_envs * self.players, 24).contiguous()
+        self._impl.set_state(s)
+        torch.cuda.current_stream(self.device).synchronize()
+
     def get_track(self, env):
-        n = ctypes.c_int32(0)
-        pts = np.zeros((512, 3), np.float64)
-        _native.check(self._lib.crl_car_get_track(self._h, int(env), ctypes.byref(n), pts.ctypes.data, 512, self._stream()))
-        return pts[:n.value].copy()
+        return self._impl.get_track(int(env)).numpy()
 
     def episode_stats(self):
-        raw = (ctypes.c_uint64 * 8)()
-        _native.check(self._lib.crl_car_get_stats(self._h, raw, self._stream()))
+        raw = self._impl.stats()
         ep = int(raw[0])
-        return {"episodes": ep, "mean_length": raw[1] / ep if ep else 0.0, "mean_tiles": raw[2] / ep if ep else 0.0}
+        return {"episodes": ep, "mean_length": raw[1] / ep if ep else 0.0, "mean_tiles": raw[2] / ep if ep else 0.0,
+                "resets_without_pregenerated_track": int(raw[3]), "slow_path_frames": int(raw[4]),
+                "pregen_launches": int(raw[5])}
 
     def get_contacts(self):
         """(int32 [num_envs] touching car-car fixture pairs after the last step, contacts dropped so far)."""
-        counts = np.zeros((self.num_envs,), np.int32)
-        over = ctypes.c_int32(0)
-        _native.check(self._lib.crl_car_get_contacts(self._h, counts.ctypes.data, ctypes.byref(over), self._stream()))
-        return counts, int(over.value)
+        counts, over = self._impl.contacts()
+        return counts.numpy(), int(over)
 
     def check(self):
-        _native.check(self._lib.crl_car_check(self._h, self._stream()))
+        self._impl.check()
 
     def close(self):
-        if not self.closed and self._h:
+        if not self.closed and self._impl is not None:
             torch.cuda.synchronize(self.device)
-            self._lib.crl_car_destroy(self._h)
+            self._impl.close()
             self._h = None
         self.closed = True
 
@@ -273,8 +288,8 @@ class CudaCarVecEnv(VecEnv):
             pass
 
     def get_images(self, indices=None, **kwargs):
-        b = self._sets[self._cur]
-        return [np.repeat(b["obs"][i, self.c - 1].cpu().numpy()[:, :, None], 3, axis=2) for i in self._get_indices(indices)]
+        obs = self._obs_of(self._sets[self._cur]).reshape(self.num_envs, self.players, self.c, 96, 96)
+        return [np.repeat(obs[i, 0, self.c - 1].cpu().numpy()[:, :, None], 3, axis=2) for i in self._get_indices(indices)]
 
     def get_attr(self, attr_name, indices=None):
         return [getattr(self.envs[i], attr_name) for i in self._get_indices(indices)]

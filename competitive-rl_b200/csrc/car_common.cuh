@@ -82,6 +82,11 @@ struct CarDev {
     int c;                    // frames per player in the observation (frame_stack or 1)
     int action_repeat;
     int max_episode_steps;    // gym TimeLimit of the registry entry (1000); 0 = none
+    // stack_mode 1: the observation buffer is a double-write ring [n][players][2c][96][96]: the new frame goes to slots
+    // ring_phase and ring_phase + c, the observation is the strided view of slots ring_phase + 1 .. ring_phase + c
+    int ring_mode;
+    int ring_phase;           // host-tracked, advanced per step
+    int fill_all;             // 1 after reset(): every frame written goes to all slots
     int done_mode;            // 0 = any car done (FlattenMultiAgentObservation), 1 = car 0 only (make_competitive_car_racing)
     int64_t first_env;
     uint64_t seed;
@@ -143,6 +148,7 @@ struct CarDev {
     int n_fixed;
     int32_t* overrun;            // [0] device flag: an injection table ran out; [1] frames whose rasteriser dropped polygons;
                                  // [2] frames rasterised on the exact slow path (span pool full)
+                                 // [3] auto-resets that had to generate (or wait for) their track on the step's critical path
     // ---- constants ----
     const CarHullConst* consts;
     const uint8_t* glyphs;       // [CAR_GLYPH_BYTES]
@@ -162,6 +168,7 @@ cudaError_t car_raster_init();
 size_t car_frame_map_bytes();
 void car_checker_table(int* out);
 cudaError_t launch_car_get_state(const CarDev& p, double* state, cudaStream_t s);
+cudaError_t launch_car_set_state(const CarDev& p, const double* state, cudaStream_t s);
 cudaError_t launch_car_random_actions(float* actions, int n_values, uint64_t seed, uint64_t step, cudaStream_t s);
 
 }  // namespace crl

@@ -409,6 +409,8 @@ __global__ void __launch_bounds__(64) car_reset_kernel(CarDev p, int only_done) 
     if (only_done && !p.env_done[e]) return;
     const int next_slot = e + p.n * (1 - p.sel[e]);
     bool have = true;
+    const int st_before = *(volatile int32_t*)(p.next_state + e);
+    if (only_done && st_before != 2 && lane == 0) atomicAdd(p.overrun + 3, 1);   // an auto-reset that found no track waiting
     if (claim_next_track(p, e, lane, true)) {          // not pre-generated (first reset, or an episode shorter than the generator)
         have = generate_track_warp(p, e, next_slot, false, lane) > 0;
         __threadfence();
@@ -1081,6 +1083,40 @@ __global__ void car_get_state_kernel(CarDev p, double* state) {
     s[23] = p.counters[4 * ci];
 }
 
+// Put every car into a given state (debug / tests: renderer cross-checks on arbitrary states).  state[car][24] as
+// car_get_state_kernel writes it; used: hull x, y, angle, vx, vy, w; per wheel joint angle, omega, gas; reward.  The
+// wheels are placed on their joint anchors and move rigidly with the hull; joint impulses, contacts and the wheels'
+// tile sets are cleared; tiles visited so far are kept.
+__global__ void car_set_state_kernel(CarDev p, const double* state) {
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= p.n * p.players) return;
+    const double* s = state + (size_t)ci * 24;
+    const CarHullConst* K = p.consts;
+    float* b = p.body + (size_t)ci * 40;
+    const float a = (float)s[2];
+    const Rot q = make_rot(a);
+    const F2 org = f2((float)s[0], (float)s[1]);
+    const F2 com = org + rmul(q, f2(K->hull_lcx, K->hull_lcy));
+    const F2 v0 = f2((float)s[3], (float)s[4]);
+    const float w0 = (float)s[5];
+    b[0] = com.x; b[1] = com.y; b[2] = a; b[3] = v0.x; b[4] = v0.y; b[5] = w0; b[6] = 0.f; b[7] = 1.f;
+    double* wd = p.wheel + (size_t)ci * 8;
+    for (int k = 0; k < 4; ++k) {
+        float* w = b + 8 * (k + 1);
+        const F2 wp = org + rmul(q, f2((float)(c_wheelpos[k][0] * CR_SIZE), (float)(c_wheelpos[k][1] * CR_SIZE)));
+        const F2 vw = v0 + cross_sv(w0, wp - com);
+        w[0] = wp.x; w[1] = wp.y; w[2] = a + (float)s[6 + 4 * k]; w[3] = vw.x; w[4] = vw.y; w[5] = w0; w[6] = 0.f; w[7] = 1.f;
+        wd[k] = s[7 + 4 * k];
+        if (k >= 2) wd[4 + k - 2] = s[8 + 4 * k];
+    }
+    wd[6] = 0.0; wd[7] = 0.0;
+    float* j = p.joint + (size_t)ci * 24;
+    for (int i = 0; i < 24; ++i) j[i] = 0.f;
+    p.reward[2 * ci] = s[22]; p.reward[2 * ci + 1] = s[22];
+    for (int i = 0; i < 64; ++i) p.touching[(size_t)ci * 64 + i] = 0u;
+    if (p.n_contacts != nullptr && ci % p.players == 0) p.n_contacts[ci / p.players] = 0;
+}
+
 __global__ void car_random_actions_kernel(float* actions, int n_values, uint64_t seed, uint64_t step) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i * 4 >= n_values) return;
@@ -1115,6 +1151,12 @@ cudaError_t launch_car_step(const CarDev& p, int mode, const float* actions, flo
 cudaError_t launch_car_get_state(const CarDev& p, double* state, cudaStream_t s) {
     const int n_cars = p.n * p.players;
     car_get_state_kernel<<<(n_cars + 127) / 128, 128, 0, s>>>(p, state);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_car_set_state(const CarDev& p, const double* state, cudaStream_t s) {
+    const int n_cars = p.n * p.players;
+    car_set_state_kernel<<<(n_cars + 127) / 128, 128, 0, s>>>(p, state);
     return cudaGetLastError();
 }
 

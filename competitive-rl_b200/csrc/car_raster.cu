@@ -382,11 +382,16 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     const int n_track = p.n_track[slot];
     const CarTile* tiles = p.tiles + (size_t)slot * CAR_MAX_TRACK;
     const int C = p.c;
-    uint8_t* ring = p.ring + (size_t)frame * C * CAR_PIX;
-    const bool fill_all = only_done != 0 || p.ring_pos[e] < 0;
+    // stack mode: the frames live in an internal ring [frame][C] and the observation (C channels, oldest first) is
+    // rewritten every step.  Ring mode: the observation buffer itself is a double-write ring of 2C slots (the new frame
+    // goes to slots k and k + C, the caller looks at slots k+1 .. k+C), so nothing is copied.
+    const bool ringm = p.ring_mode != 0;
+    uint8_t* ring = ringm ? nullptr : p.ring + (size_t)frame * C * CAR_PIX;
+    const bool fill_all = only_done != 0 || (ringm ? p.fill_all != 0 : p.ring_pos[e] < 0);
     int newest = C - 1;
-    if (!fill_all) { newest = p.ring_pos[e] + 1; if (newest >= C) newest = 0; }
-    uint8_t* out = obs + (size_t)frame * C * CAR_PIX;
+    if (ringm) newest = p.ring_phase;
+    else if (!fill_all) { newest = p.ring_pos[e] + 1; if (newest >= C) newest = 0; }
+    uint8_t* out = obs + (size_t)frame * (ringm ? 2 * C : C) * CAR_PIX;
     uint8_t* tout = (term_obs != nullptr && !only_done && p.env_done[e]) ? term_obs + (size_t)frame * C * CAR_PIX : nullptr;
 
     if (tid < p.players * 40) (&S.car_body[0][0])[tid] = p.body[(size_t)e * p.players * 40 + tid];   // [player][40], contiguous on both sides
@@ -491,7 +496,7 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
         else paint_hud_indicators(S, p.glyphs, G, img, lane);
         __syncwarp();
     }
-    if (!fill_all) {
+    if (!fill_all && (!ringm || tout != nullptr)) {                // ring mode: only the terminal observation is materialised
         constexpr int PER_SLOT = CAR_PIX / 16 / 64;                // chunks of 64 uint4 (two per lane) per frame: 9
         const int n_chunks = (C - 1) * PER_SLOT;
         for (;;) {
@@ -501,11 +506,13 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
             if (ch >= n_chunks) break;
             const int sl = ch / PER_SLOT, q = (ch % PER_SLOT) * 64 + lane;       // slot sl of the output = the sl-th oldest frame
             int rs = newest + 1 + sl;                             // < 2 C
-            if (rs >= C) rs -= C;
-            const uint4* rsrc = reinterpret_cast<const uint4*>(ring + (size_t)rs * CAR_PIX);
-            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)sl * CAR_PIX);
+            if (!ringm && rs >= C) rs -= C;
+            const uint4* rsrc = reinterpret_cast<const uint4*>((ringm ? out : ring) + (size_t)rs * CAR_PIX);
             const uint4 v0 = rsrc[q], v1 = rsrc[q + 32];
-            dst[q] = v0; dst[q + 32] = v1;
+            if (!ringm) {
+                uint4* dst = reinterpret_cast<uint4*>(out + (size_t)sl * CAR_PIX);
+                dst[q] = v0; dst[q + 32] = v1;
+            }
             if (tout) { uint4* tdst = reinterpret_cast<uint4*>(tout + (size_t)sl * CAR_PIX); tdst[q] = v0; tdst[q + 32] = v1; }
         }
     }
@@ -531,15 +538,21 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
         __syncthreads();
     }
     const uint4* src = reinterpret_cast<const uint4*>(img);
-    if (fill_all) {
+    if (fill_all && ringm) {
+        for (int sl = 0; sl < 2 * C; ++sl) {
+            uint4* dst = reinterpret_cast<uint4*>(out + (size_t)sl * CAR_PIX);
+            for (int q = tid; q < CAR_PIX / 16; q += RASTER_THREADS) dst[q] = src[q];
+        }
+    } else if (fill_all) {
         for (int sl = 0; sl < C; ++sl) {
             uint4* rdst = reinterpret_cast<uint4*>(ring + (size_t)sl * CAR_PIX);
             uint4* dst = reinterpret_cast<uint4*>(out + (size_t)sl * CAR_PIX);
             for (int q = tid; q < CAR_PIX / 16; q += RASTER_THREADS) { const uint4 vv = src[q]; rdst[q] = vv; dst[q] = vv; }
         }
     } else {
-        uint4* rdst = reinterpret_cast<uint4*>(ring + (size_t)newest * CAR_PIX);
-        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(C - 1) * CAR_PIX);
+        // stack: internal ring slot + newest channel.  ring: slots k and k + C of the observation ring
+        uint4* rdst = reinterpret_cast<uint4*>((ringm ? out : ring) + (size_t)newest * CAR_PIX);
+        uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(ringm ? newest + C : C - 1) * CAR_PIX);
         uint4* tdst = tout ? reinterpret_cast<uint4*>(tout + (size_t)(C - 1) * CAR_PIX) : nullptr;
         for (int q = tid; q < CAR_PIX / 16; q += RASTER_THREADS) {
             const uint4 vv = src[q];
@@ -585,7 +598,7 @@ cudaError_t launch_car_render(const CarDev& p, int only_done, int which, int adv
     if (e != cudaSuccess) return e;
     car_render_kernel<<<p.n * p.players, RASTER_THREADS, sizeof(RasterSmem), s>>>(p, only_done, which, obs, term_obs);
     e = cudaGetLastError();
-    if (e != cudaSuccess || !advance) return e;
+    if (e != cudaSuccess || !advance || p.ring_mode) return e;   // ring mode: the phase is advanced on the host, per step
     car_ring_advance_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p, only_done);
     return cudaGetLastError();
 }

@@ -154,6 +154,8 @@ int crl_pong_create(const crl_pong_config* cfg, crl_pong** out) {
         return fail(CRL_E_INVALID, "resized_dim must be even and in [8, %d]", MAX_DIM);
     if (cfg->frame_stack < 0 || cfg->frame_stack > MAX_STACK)
         return fail(CRL_E_INVALID, "frame_stack must be in [0, %d]", MAX_STACK);
+    if (cfg->stack_mode != 0 && cfg->stack_mode != 1) return fail(CRL_E_INVALID, "stack_mode must be 0 (stack) or 1 (ring)");
+    if (cfg->stack_mode == 1 && cfg->frame_stack < 2) return fail(CRL_E_INVALID, "stack_mode ring needs frame_stack >= 2");
     if (cfg->max_num_rounds < 1 || cfg->max_num_rounds > ATLAS_SCORES - 1)
         return fail(CRL_E_INVALID, "max_num_rounds must be in [1, %d] (scoreboard atlas range)", ATLAS_SCORES - 1);
     int ndev = 0;
@@ -178,6 +180,8 @@ int crl_pong_create(const crl_pong_config* cfg, crl_pong** out) {
     d.dim = cfg->resized_dim;
     d.c = cfg->frame_stack > 0 ? cfg->frame_stack : 1;
     d.max_rounds = cfg->max_num_rounds;
+    d.ring = cfg->stack_mode == 1 ? 1 : 0;
+    d.zero_on_done = cfg->zero_on_done ? 1 : 0;
     d.first_env = cfg->first_env;
     d.seed = cfg->seed;
     const int dd = d.dim * d.dim;
@@ -192,7 +196,7 @@ int crl_pong_create(const crl_pong_config* cfg, crl_pong** out) {
         }                                                                        \
     } while (0)
     ALLOC(d.ball, n); ALLOC(d.vx, n); ALLOC(d.vy, n); ALLOC(d.bats, n); ALLOC(d.score, n);
-    ALLOC(d.num_steps, n); ALLOC(d.clip_steps, n); ALLOC(d.serve_count, n);
+    ALLOC(d.num_steps, n); ALLOC(d.clip_steps, n); ALLOC(d.serve_count, n); ALLOC(d.last_done, n);
     ALLOC(d.skipbuf, 2 * n); ALLOC(d.hist, d.c * n); ALLOC(d.term_hist, d.c * n);
     ALLOC(d.serve_overrun, 1);
     ALLOC(d.stats, 8);
@@ -312,7 +316,7 @@ int crl_pong_render_obs_generic(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_de
     CHECK_HANDLE(h);
     if (int r = need_ready(h, true)) return r;
     if (!obs0_dev || (h->dev.n_agents == 2 && !obs1_dev)) return fail(CRL_E_INVALID, "null observation buffer");
-    LAUNCH(launch_pong_raster_generic(h->dev, h->dev.hist, nullptr, obs0_dev, obs1_dev, (cudaStream_t)stream));
+    LAUNCH(launch_pong_raster_generic(h->dev, h->dev.hist, nullptr, h->dev.ring, obs0_dev, obs1_dev, (cudaStream_t)stream));
     return CRL_OK;
 }
 
@@ -321,6 +325,8 @@ int crl_pong_reset(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_dev, void* stre
     if (int r = need_ready(h, false)) return r;
     LAUNCH(launch_pong_reset(h->dev, (cudaStream_t)stream));
     h->was_reset = true;
+    h->dev.ring_phase = 0;
+    h->dev.fill_all = 1;      // until the next step: every ring is (re)written completely
     return crl_pong_render_obs(h, obs0_dev, obs1_dev, stream);
 }
 
@@ -330,6 +336,8 @@ int crl_pong_step_state(crl_pong* h, const int32_t* actions_dev, float* rew_dev,
     if (int r = need_ready(h, true)) return r;
     if (!actions_dev || !rew_dev || !done_dev || !num_steps_dev || !real_reward_dev)
         return fail(CRL_E_INVALID, "null step buffer");
+    h->dev.fill_all = 0;
+    if (h->dev.ring) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
     LAUNCH(launch_pong_step(h->dev, actions_dev, rew_dev, done_dev, num_steps_dev, real_reward_dev,
                             (cudaStream_t)stream));
     return CRL_OK;
@@ -346,7 +354,7 @@ int crl_pong_terminal_obs(crl_pong* h, const uint8_t* done_dev, uint8_t* term0_d
     CHECK_HANDLE(h);
     if (int r = need_ready(h, true)) return r;
     if (!done_dev || !term0_dev || (h->dev.n_agents == 2 && !term1_dev)) return fail(CRL_E_INVALID, "null buffer");
-    LAUNCH(launch_pong_raster_generic(h->dev, h->dev.term_hist, done_dev, term0_dev, term1_dev, (cudaStream_t)stream));
+    LAUNCH(launch_pong_raster_generic(h->dev, h->dev.term_hist, done_dev, 0, term0_dev, term1_dev, (cudaStream_t)stream));
     return CRL_OK;
 }
 
@@ -380,11 +388,17 @@ int crl_pong_step_host(crl_pong* h, const int32_t* actions_host, uint8_t* obs0_d
     CUDA_TRY(cudaEventRecord(h->ev_copied, cs));
     if (int r = crl_pong_render_obs(h, obs0_dev, obs1_dev, stream)) return r;
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_copied, 0));
-    const size_t ob = n * h->dev.c * h->dev.dim * h->dev.dim;
+    const size_t ob = n * (h->dev.ring ? 2 * h->dev.c : h->dev.c) * h->dev.dim * h->dev.dim;
     if (obs0_host) CUDA_TRY(cudaMemcpyAsync(obs0_host, obs0_dev, ob, cudaMemcpyDeviceToHost, s));
     if (obs1_host && h->dev.n_agents == 2) CUDA_TRY(cudaMemcpyAsync(obs1_host, obs1_dev, ob, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return CRL_OK;
+}
+
+int crl_pong_ring_phase(crl_pong* h) {
+    if (!h) return fail(CRL_E_INVALID, "null handle");
+    if (!h->dev.ring) return fail(CRL_E_STATE, "the handle was not created with stack_mode ring");
+    return h->dev.ring_phase;
 }
 
 int crl_pong_get_state(crl_pong* h, double* state_dev, void* stream) {

@@ -36,8 +36,8 @@ struct crl_car {
     cudaEvent_t ev_fast = nullptr, ev_slow = nullptr;
     // next tracks are generated ahead of time on this stream (car_pregen_kernel); at most one launch in flight
     cudaStream_t pregen_stream = nullptr;
-    cudaEvent_t ev_pregen_go = nullptr, ev_pregen_done = nullptr;
-    bool pregen_in_flight = false;
+    cudaEvent_t ev_pregen_go = nullptr;
+    uint64_t pregen_launches = 0;
     bool was_reset = false;
     // crl_car_step_host staging
     float* actions_stage = nullptr;
@@ -202,23 +202,18 @@ cudaError_t car_alloc(crl_car* h, T** p, size_t count) {
     return cudaMemset(q, 0, count * sizeof(T) + 16);
 }
 
-// Start generating the next track of every env that has none, behind everything queued on `s` so far, on the handle's
-// side stream -- unless the previous launch is still running (its successor will pick the newcomers up).  The main
-// stream never waits for the side stream: an env that finishes again before its next track is ready generates it
-// inside car_reset_kernel.  High stream priority: the few warps that have work live ~1.5 ms each (the curve walk is a
-// serial fp64 chain) and should start at once; the others exit immediately.
+// Generate the next track of every env that has none, behind everything queued on `s` so far, on the handle's side
+// stream.  Launched after every step: the host runs many steps ahead of the GPU, so "launch when the previous one has
+// finished" would batch ~80 steps' worth of resets into one burst of curve walks; a launch per step keeps it at the
+// handful of envs that just finished (the others' warps exit at once), and a launch that finds the previous one still
+// walking simply queues behind it.  The main stream never waits for the side stream: an env that finishes again before
+// its next track is ready generates it inside car_reset_kernel.  High stream priority: the few warps that have work
+// live ~1.5 ms each (the walk is a serial fp64 chain) and should start at once.
 int kick_pregen(crl_car* h, cudaStream_t s) {
-    if (h->pregen_in_flight) {
-        const cudaError_t q = cudaEventQuery(h->ev_pregen_done);
-        if (q == cudaErrorNotReady) return CRL_OK;
-        if (q != cudaSuccess) return crl_set_error(CRL_E_CUDA, "pregen: %s", cudaGetErrorString(q));
-        h->pregen_in_flight = false;
-    }
     CUDA_TRY(cudaEventRecord(h->ev_pregen_go, s));
     CUDA_TRY(cudaStreamWaitEvent(h->pregen_stream, h->ev_pregen_go, 0));
     LAUNCH(launch_car_pregen(h->dev, h->pregen_stream), 1);
-    CUDA_TRY(cudaEventRecord(h->ev_pregen_done, h->pregen_stream));
-    h->pregen_in_flight = true;
+    h->pregen_launches += 1;
     return CRL_OK;
 }
 
@@ -226,7 +221,6 @@ int kick_pregen(crl_car* h, cudaStream_t s) {
 // and their attempts given back, so that what follows does not depend on how far the side stream had got.
 int discard_pregen(crl_car* h, cudaStream_t s) {
     CUDA_TRY(cudaStreamSynchronize(h->pregen_stream));
-    h->pregen_in_flight = false;
     LAUNCH(launch_car_discard_next(h->dev, s), 1);
     return CRL_OK;
 }
@@ -240,7 +234,6 @@ int crl_car_destroy(crl_car* h) {
     if (h->pregen_stream) cudaStreamSynchronize(h->pregen_stream);
     for (void* p : h->allocs) cudaFree(p);
     if (h->ev_pregen_go) cudaEventDestroy(h->ev_pregen_go);
-    if (h->ev_pregen_done) cudaEventDestroy(h->ev_pregen_done);
     if (h->pregen_stream) cudaStreamDestroy(h->pregen_stream);
     if (h->ev_fast) cudaEventDestroy(h->ev_fast);
     if (h->ev_slow) cudaEventDestroy(h->ev_slow);
@@ -256,6 +249,8 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     if (cfg->num_players != 1 && cfg->num_players != 2) return crl_set_error(CRL_E_INVALID, "num_players must be 1 or 2");
     if (cfg->frame_stack < 0 || cfg->frame_stack > CAR_MAX_STACK)
         return crl_set_error(CRL_E_INVALID, "frame_stack must be in [0, %d]", CAR_MAX_STACK);
+    if (cfg->stack_mode != 0 && cfg->stack_mode != 1) return crl_set_error(CRL_E_INVALID, "stack_mode must be 0 (stack) or 1 (ring)");
+    if (cfg->stack_mode == 1 && cfg->frame_stack < 2) return crl_set_error(CRL_E_INVALID, "stack_mode ring needs frame_stack >= 2");
     if (cfg->done_mode != 0 && cfg->done_mode != 1) return crl_set_error(CRL_E_INVALID, "done_mode must be 0 (any car) or 1 (car 0)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -273,6 +268,7 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     d.action_repeat = cfg->action_repeat > 0 ? cfg->action_repeat : 1;
     d.max_episode_steps = cfg->max_episode_steps;
     d.done_mode = cfg->done_mode;
+    d.ring_mode = cfg->stack_mode == 1 ? 1 : 0;
     d.first_env = cfg->first_env; d.seed = cfg->seed;
 #define ALLOC(ptr, count)                                                                   \
     do {                                                                                    \
@@ -289,7 +285,8 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     ALLOC(d.attempt_count, n); ALLOC(d.inv_dt0, n); ALLOC(d.env_done, n); ALLOC(d.ring_pos, n);
     ALLOC(d.body, nc * 40); ALLOC(d.joint, nc * 24); ALLOC(d.wheel, nc * 8); ALLOC(d.reward, nc * 2);
     ALLOC(d.counters, nc * 4); ALLOC(d.touching, nc * 64); ALLOC(d.visited, nc * 16);
-    ALLOC(d.ring, nc * d.c * CAR_PIX); ALLOC(d.overrun, 4); ALLOC(d.stats, 8);
+    if (!d.ring_mode) ALLOC(d.ring, nc * d.c * CAR_PIX);
+    ALLOC(d.overrun, 4); ALLOC(d.stats, 8);
     ALLOC(d.contact_overflow, 1);
     {
         uint8_t* fmraw = nullptr;
@@ -321,7 +318,6 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
         e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->pregen_stream, cudaStreamNonBlocking, hi);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pregen_go, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pregen_done, cudaEventDisableTiming);
         if (e != cudaSuccess) {
             crl_car_destroy(h);
             return crl_set_error(CRL_E_CUDA, "pregen stream: %s", cudaGetErrorString(e));
@@ -403,6 +399,8 @@ int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaMemsetAsync(h->dev.ring_pos, 0xFF, (size_t)h->dev.n * sizeof(int32_t), s));
     CUDA_TRY(cudaMemsetAsync(h->dev.env_done, 0, (size_t)h->dev.n, s));
+    h->dev.ring_phase = 0;
+    h->dev.fill_all = 1;      // until the next step: every frame written goes to all slots of its ring
     LAUNCH(launch_car_reset(h->dev, 0, s), 1);
     LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, nullptr, s), 3);
     h->was_reset = true;
@@ -414,6 +412,8 @@ int crl_car_step_state(crl_car* h, const float* actions_dev, float* rew_dev, uin
     CHECK_HANDLE(h);
     if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
     if (!actions_dev || !rew_dev || !done_dev || !num_steps_dev || !truncated_dev) return crl_set_error(CRL_E_INVALID, "null step buffer");
+    h->dev.fill_all = 0;
+    if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
     LAUNCH(launch_car_step(h->dev, 0, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, (cudaStream_t)stream), 1);
     return CRL_OK;
 }
@@ -450,6 +450,8 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fast, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_slow, cudaEventDisableTiming));
     }
+    h->dev.fill_all = 0;
+    if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
     CUDA_TRY(cudaMemsetAsync(h->dev.slow_count, 0, sizeof(int32_t), s));
     LAUNCH(launch_car_step(h->dev, 1, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, s), 1);
     CUDA_TRY(cudaEventRecord(h->ev_fast, s));
@@ -492,7 +494,7 @@ int crl_car_step_host(crl_car* h, const float* actions_host, uint8_t* obs_dev, u
     CUDA_TRY(cudaMemcpyAsync(done_host, h->done_stage, n, cudaMemcpyDeviceToHost, s));
     if (num_steps_host) CUDA_TRY(cudaMemcpyAsync(num_steps_host, h->steps_stage, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     if (truncated_host) CUDA_TRY(cudaMemcpyAsync(truncated_host, h->trunc_stage, n, cudaMemcpyDeviceToHost, s));
-    if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, obs_dev, nc * h->dev.c * CAR_PIX, cudaMemcpyDeviceToHost, s));
+    if (obs_host) CUDA_TRY(cudaMemcpyAsync(obs_host, obs_dev, nc * (h->dev.ring_mode ? 2 : 1) * h->dev.c * CAR_PIX, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return CRL_OK;
 }
@@ -502,6 +504,20 @@ int crl_car_get_state(crl_car* h, double* state_dev, void* stream) {
     if (!state_dev) return crl_set_error(CRL_E_INVALID, "null buffer");
     LAUNCH(launch_car_get_state(h->dev, state_dev, (cudaStream_t)stream), 1);
     return CRL_OK;
+}
+
+int crl_car_set_state(crl_car* h, const double* state_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (!state_dev) return crl_set_error(CRL_E_INVALID, "null buffer");
+    if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before set_state");
+    LAUNCH(launch_car_set_state(h->dev, state_dev, (cudaStream_t)stream), 1);
+    return CRL_OK;
+}
+
+int crl_car_ring_phase(crl_car* h) {
+    if (!h) return crl_set_error(CRL_E_INVALID, "null handle");
+    if (!h->dev.ring_mode) return crl_set_error(CRL_E_STATE, "the handle was not created with stack_mode ring");
+    return h->dev.ring_phase;
 }
 
 int crl_car_get_track(crl_car* h, int32_t env, int32_t* n_out, double* pts_host, int32_t max_points, void* stream) {
@@ -536,6 +552,12 @@ int crl_car_get_stats(crl_car* h, uint64_t* stats_host, void* stream) {
     CUDA_TRY(cudaMemcpyAsync(raw, h->dev.stats, sizeof raw, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     for (int i = 0; i < 8; ++i) stats_host[i] = raw[i];
+    int32_t flags[4] = {0, 0, 0, 0};
+    CUDA_TRY(cudaMemcpyAsync(flags, h->dev.overrun, sizeof flags, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    stats_host[3] = (uint64_t)flags[3];
+    stats_host[4] = (uint64_t)flags[2];
+    stats_host[5] = h->pregen_launches;
     return CRL_OK;
 }
 

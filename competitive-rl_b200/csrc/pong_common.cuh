@@ -75,6 +75,14 @@ struct PongDev {
     int dim;            // resized_dim
     int c;              // frames per observation (frame_stack or 1)
     int max_rounds;
+    // stack_mode 1: the observation buffers are double-write rings [n][2c][dim][dim]: the newest frame goes to slots
+    // ring_phase and ring_phase + c, the observation is the strided view of slots ring_phase + 1 .. ring_phase + c
+    // (oldest -> newest), so a step writes 2 frames per agent instead of c.  Slot j holds hist[(j - ring_phase - 1) mod c].
+    int ring;
+    int ring_phase;     // slot the newest frame was written to by the current step (host-tracked, advanced per step)
+    int fill_all;       // 1 after reset(): every env's ring is rewritten completely by the next render
+    int zero_on_done;   // FrameStackTensor semantics (utils/utils.py:145-173): a reset clears the history to zero frames
+                        // instead of filling it with copies of the reset frame (FrameStack.reset)
     int64_t first_env;  // global index of env 0 (RNG streams are keyed by global index)
     uint64_t seed;
     // --- game state (PongGame fields) ---
@@ -86,6 +94,7 @@ struct PongDev {
     int32_t* num_steps;  // PongGame._num_steps
     int32_t* clip_steps; // ClipRewardEnv._steps
     int32_t* serve_count;
+    uint8_t* last_done;     // [n] done flag of the last step (ring mode: these envs' rings are rewritten completely)
     RenderState* skipbuf;   // [2][n]  MaxAndSkipEnv._obs_buffer as render states
     FrameSpec* hist;        // [c][n]  FrameStack deque, slot 0 = oldest
     FrameSpec* term_hist;   // [c][n]  deque at the terminal step (for terminal_observation)
@@ -138,7 +147,8 @@ cudaError_t launch_pong_random_actions(int32_t* actions, int n_values, uint64_t 
 
 cudaError_t launch_pong_build_tables(const PongDev& p, uint8_t* text_tab, uint8_t* tmpl, cudaStream_t s);
 cudaError_t launch_pong_raster(const PongDev& p, const FrameSpec* hist, uint8_t* obs0, uint8_t* obs1, cudaStream_t s);
-cudaError_t launch_pong_raster_generic(const PongDev& p, const FrameSpec* hist, const uint8_t* only_done,
+// ring = 1: obs* are 2c-slot rings, rewritten completely (terminal observations are always plain stacks: ring = 0)
+cudaError_t launch_pong_raster_generic(const PongDev& p, const FrameSpec* hist, const uint8_t* only_done, int ring,
                                        uint8_t* obs0, uint8_t* obs1, cudaStream_t s);
 cudaError_t pong_raster_init(int grid_out[2]);
 size_t pong_fast_tabs_bytes(int dim);

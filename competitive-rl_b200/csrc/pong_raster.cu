@@ -67,19 +67,22 @@ __global__ void pong_build_tables_kernel(PongDev p, uint8_t* text_tab, uint8_t* 
 // Used for terminal observations (rare) and as the in-library cross-check of the
 // fast kernel (tests/test_gpu_pong_parity.py).
 __global__ void pong_raster_generic_kernel(PongDev p, const FrameSpec* __restrict__ hist,
-                                           const uint8_t* __restrict__ only_done, uint8_t* obs0, uint8_t* obs1) {
+                                           const uint8_t* __restrict__ only_done, int ring, uint8_t* obs0, uint8_t* obs1) {
     const int dd = p.dim * p.dim;
-    const long long total = (long long)p.n * p.n_agents * p.c * dd;
+    // ring: every slot j of the 2c-slot ring is rewritten with the frame it must hold, hist[(j - ring_phase - 1) mod c]
+    const int slots = ring ? 2 * p.c : p.c;
+    const long long total = (long long)p.n * p.n_agents * slots * dd;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int pix = (int)(i % dd);
         long long f = i / dd;
-        const int slot = (int)(f % p.c);
-        f /= p.c;
+        const int pos = (int)(f % slots);
+        f /= slots;
         const int env = (int)(f % p.n), agent = (int)(f / p.n);
         if (only_done != nullptr && !only_done[env]) continue;
+        const int slot = ring ? ((pos - p.ring_phase - 1) % p.c + p.c) % p.c : pos;
         const FrameCtx c = make_ctx(hist[(size_t)slot * p.n + env], agent);
-        uint8_t* out = (agent ? obs1 : obs0) + ((size_t)env * p.c + slot) * dd;
+        uint8_t* out = (agent ? obs1 : obs0) + ((size_t)env * slots + pos) * dd;
         out[pix] = c.any_valid ? eval_pixel(p.tabs, c, p.atlas, pix / p.dim, pix % p.dim) : (uint8_t)0;
     }
 }
@@ -123,9 +126,9 @@ cudaError_t launch_pong_build_tables(const PongDev& p, uint8_t* text_tab, uint8_
     return cudaGetLastError();
 }
 
-cudaError_t launch_pong_raster_generic(const PongDev& p, const FrameSpec* hist, const uint8_t* only_done,
+cudaError_t launch_pong_raster_generic(const PongDev& p, const FrameSpec* hist, const uint8_t* only_done, int ring,
                                        uint8_t* obs0, uint8_t* obs1, cudaStream_t s) {
-    pong_raster_generic_kernel<<<148 * 16, 256, 0, s>>>(p, hist, only_done, obs0, obs1);
+    pong_raster_generic_kernel<<<148 * 16, 256, 0, s>>>(p, hist, only_done, ring, obs0, obs1);
     return cudaGetLastError();
 }
 

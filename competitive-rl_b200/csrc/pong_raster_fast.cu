@@ -231,7 +231,9 @@ pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
     // A ticket covers ~4 frames (one stack of 4, or 4 stacks of 1): one atomic per 28 KB written; one per 7 KB frame
     // makes the counter itself the bottleneck (2.7 TB/s in the probe).
     const long long n_stacks = (long long)p.n * p.n_agents;
-    const int per_ticket = max(1, 4 / p.c);
+    // frames a stack writes: c (plain stack), or the newest frame twice (ring; all 2c slots only after a reset)
+    const int per_ticket = max(1, 4 / (p.ring ? 2 : p.c));
+    const int out_slots = p.ring ? 2 * p.c : p.c;
     long long s = 0, s_end = 0;
     for (;;) {
         if (s >= s_end) {
@@ -243,17 +245,27 @@ pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
         }
         const long long s_cur = s++;
         const int env = (int)(s_cur / p.n_agents), agent = (int)(s_cur % p.n_agents);
-        uint8_t* out_stack = (agent ? obs1 : obs0) + (size_t)env * p.c * DD;
+        uint8_t* out_stack = (agent ? obs1 : obs0) + (size_t)env * out_slots * DD;
         FrameSpec my_spec = make_uint4(0u, 0u, 0u, 0u);
         if (lane < p.c) my_spec = hist[(size_t)lane * p.n + env];
+        // ring: only the newest frame is new, unless the env was just reset (its whole history changed)
+        const int first_slot = (p.ring && !p.fill_all && !p.last_done[env]) ? p.c - 1 : 0;
 
-        for (int slot = 0; slot < p.c; ++slot) {
+        for (int slot = first_slot; slot < p.c; ++slot) {
             FrameSpec f;
             f.x = __shfl_sync(0xffffffffu, my_spec.x, slot);
             f.y = __shfl_sync(0xffffffffu, my_spec.y, slot);
             f.z = __shfl_sync(0xffffffffu, my_spec.z, slot);
             f.w = __shfl_sync(0xffffffffu, my_spec.w, slot);
+            // plain stack: frame `slot` goes to channel `slot`.  Ring: to slot ring_phase + 1 + slot and to its double
+            // c slots before or after it, whichever exists (the newest frame: ring_phase + c and ring_phase)
             uint8_t* out8 = out_stack + (size_t)slot * DD;
+            uint8_t* out8b = nullptr;
+            if (p.ring) {
+                const int pos = p.ring_phase + 1 + slot;
+                out8 = out_stack + (size_t)pos * DD;
+                out8b = out_stack + (size_t)(pos >= p.c ? pos - p.c : pos + p.c) * DD;
+            }
 
             // ---- frame context (warp-uniform) ----
             const bool va = (f.y >> 16) & 1u, vb = (f.w >> 16) & 1u;
@@ -279,6 +291,10 @@ pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
                 memset(&z, 0, sizeof z);
                 V* out = reinterpret_cast<V*>(out8);
                 for (int k = lane; k < NCH; k += 32) st_stream(out + k, z);
+                if (out8b != nullptr) {
+                    V* outb = reinterpret_cast<V*>(out8b);
+                    for (int k = lane; k < NCH; k += 32) st_stream(outb + k, z);
+                }
                 continue;
             }
 
@@ -421,14 +437,28 @@ pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
             if (USE_TMA) {
                 fence_proxy_async_smem();    // generic-proxy writes -> visible to the async proxy
                 __syncwarp();
-                if (lane == 0) bulk_store(out8, sm8, DD);
+                if (lane == 0) {
+                    bulk_store(out8, sm8, DD);
+                    if (out8b != nullptr) bulk_store(out8b, sm8, DD);
+                }
                 pending = true;
             } else {
                 __syncwarp();
                 V* out = reinterpret_cast<V*>(out8);
+                if (out8b == nullptr) {
 #pragma unroll
-                for (int j = 0; j < (NCH + 31) / 32; ++j)
-                    if ((j + 1) * 32 <= NCH || lane + 32 * j < NCH) st_stream(out + lane + 32 * j, sm[lane + 32 * j]);
+                    for (int j = 0; j < (NCH + 31) / 32; ++j)
+                        if ((j + 1) * 32 <= NCH || lane + 32 * j < NCH) st_stream(out + lane + 32 * j, sm[lane + 32 * j]);
+                } else {
+                    V* outb = reinterpret_cast<V*>(out8b);
+#pragma unroll
+                    for (int j = 0; j < (NCH + 31) / 32; ++j)
+                        if ((j + 1) * 32 <= NCH || lane + 32 * j < NCH) {
+                            const V v = sm[lane + 32 * j];
+                            st_stream(out + lane + 32 * j, v);
+                            st_stream(outb + lane + 32 * j, v);
+                        }
+                }
                 __syncwarp();
             }
         }
@@ -539,7 +569,7 @@ cudaError_t launch_pong_raster(const PongDev& p, const FrameSpec* hist, uint8_t*
     if (n_stacks == 0) return cudaSuccess;
     const bool aligned = ((uintptr_t)obs0 % 16 == 0) && ((uintptr_t)obs1 % 16 == 0);
     if (p.fast_tabs == nullptr || !p.fast_ok || !aligned || (p.dim != 84 && p.dim != 42))
-        return launch_pong_raster_generic(p, hist, nullptr, obs0, obs1, s);
+        return launch_pong_raster_generic(p, hist, nullptr, p.ring, obs0, obs1, s);
     const long long want = (n_stacks + FAST_WARPS - 1) / FAST_WARPS;
     cudaError_t me = cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), s);
     if (me != cudaSuccess) return me;

@@ -198,7 +198,11 @@ __device__ __forceinline__ void env_reset(const PongDev& p, int e, Game& g) {
     p.clip_steps[e] = 0;
     const RenderState rs = snapshot(g);
     const FrameSpec spec = make_uint4(rs.x, rs.y, rs.x, rs.y);
-    for (int k = 0; k < p.c; ++k) p.hist[(size_t)k * p.n + e] = spec;
+    // FrameStackTensor.update (utils/utils.py:159-170): `obs *= mask` zeroes the history of a finished env before the
+    // reset observation is appended; valid bit 0 = the all-zero frame
+    const FrameSpec old = p.zero_on_done ? make_uint4(0u, 0u, 0u, 0u) : spec;
+    for (int k = 0; k + 1 < p.c; ++k) p.hist[(size_t)k * p.n + e] = old;
+    p.hist[(size_t)(p.c - 1) * p.n + e] = spec;
 }
 
 // PongGame.__init__: Ball.__init__ -> reset() (:312) then reset_game() (:211): two serves.
@@ -285,6 +289,7 @@ pong_step_kernel(PongDev p, const int32_t* __restrict__ actions, float* __restri
     reinterpret_cast<float2*>(rew)[e] =
         make_float2((float)((total0 > 0) - (total0 < 0)), (float)((total1 > 0) - (total1 < 0)));
     done_out[e] = done ? 1 : 0;
+    p.last_done[e] = done ? 1 : 0;
     if (done) {   // vec-env auto-reset: keep the terminal deque, then env.reset()
         atomicAdd(&p.stats[0], 1ull);
         atomicAdd(&p.stats[1], (unsigned long long)steps);

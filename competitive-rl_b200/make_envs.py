@@ -5,7 +5,15 @@ GPU-resident vectorised environment instead of a Dummy/Subproc vec-env of Python
               resized_dim=42, frame_stack=4, action_repeat=None)
 
 Extra keyword-only arguments: device, return_numpy, serves (validation mode), atlas,
-first_env (global index of env 0 when the batch is one shard of a multi-GPU job).
+first_env (global index of env 0 when the batch is one shard of a multi-GPU job), n_buffers / copy (see below),
+stack_mode ("stack" | "ring"), zero_on_done.
+
+BUFFER LIFETIME: unlike the reference's vec-envs, which return fresh numpy copies, the tensors returned by reset() and
+step() alias env-owned device buffers that rotate over `n_buffers` (default 2) sets: what step t returned is overwritten
+by step t + n_buffers (stack_mode="ring": the observation view by step t + 1).  A rollout that keeps references
+(`obs_list.append(obs)`, deferred reads of `infos`) must pass `copy=True` (fresh tensors every step) or a large enough
+`n_buffers`.  `infos[i]["terminal_observation"]` is rendered on first access from the episode-end frame specs of the
+LAST step: read it before stepping again.
 """
 import os
 import warnings
@@ -52,8 +60,9 @@ def make_envs(env_id="cPong-v0", seed=0, log_dir="data", num_envs=3, asynchronou
         os.makedirs(log_dir, exist_ok=True)
     if env_id in ("cPong-v0", "cPongDouble-v0"):
         s = spec(env_id)
+        kwargs.setdefault("max_num_rounds", s["kwargs"]["max_num_rounds"])   # gym registry kwarg (pong/register.py:13-22)
         return CudaPongVecEnv(env_id, num_envs, resized_dim=resized_dim, frame_stack=frame_stack, seed=seed,
-                              asynchronous=asynchronous, max_num_rounds=s["kwargs"]["max_num_rounds"], **kwargs)
+                              asynchronous=asynchronous, **kwargs)
     if env_id in ("cCarRacing-v0", "cCarRacingDouble-v0"):
         from .car_vec_env import CudaCarVecEnv
         s = spec(env_id)

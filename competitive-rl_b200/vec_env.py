@@ -211,26 +211,43 @@ class CudaPongVecEnv(VecEnv):
     rew:   `asynchronous=False` (DummyVecEnv convention): float32 (N, A);
            `asynchronous=True`  (SubprocVecEnv convention): (N, 2) for Double, (N,) for single
     done:  Dummy convention: bool (N, A); Subproc convention: bool (N,)
-    actions: Double: int (N, 2) in {0, 1, 2, 999}; single: int (N,) in {0, 1, 2}.
+    actions: Double: int (N, 2) in {0, 1, 2, 999}; single: int (N,) in {0, 1, 2}.  An int32 CUDA tensor is consumed
+             in place (no copy, no host sync).
+
+    BUFFER LIFETIME (differs from the reference, which returns fresh numpy copies every step): the tensors returned by
+    reset()/step() are owned by the env and rotate over `n_buffers` sets, so what step t returned is overwritten by
+    step t + n_buffers.  Keep rollouts alive with a larger `n_buffers`, or pass `copy=True` to get fresh tensors from
+    every call (one extra device copy of the observations per step).
+
+    stack_mode="ring" (opt-in): the observations are strided VIEWS `ring[:, k+1 : k+1+C]` of an (N, 2C, D, D) ring per
+    agent in which every new frame is stored twice (slots k and k + C), so a step writes 2 frames per agent instead of
+    C -- same values, half the HBM traffic (28 224 B instead of 56 448 B per env-step at 84x84x4).  The
+    view returned by step t is valid until step t + 1 only (its oldest slot is the next one overwritten).
+
+    zero_on_done=True: FrameStackTensor's stacking (utils/utils.py:145-173) instead of FrameStack's: after a done the
+    history is zeros and only the newest channel holds the reset observation.
     """
 
     def __init__(self, env_id="cPongDouble-v0", num_envs=1, resized_dim=42, frame_stack=None, seed=0,
                  asynchronous=False, device=None, max_num_rounds=21, atlas=None, serves=None, first_env=0,
-                 return_numpy=False, n_buffers=2, stack_mode="stack"):
+                 return_numpy=False, n_buffers=2, stack_mode="stack", zero_on_done=False, copy=False):
         if env_id not in ("cPong-v0", "cPongDouble-v0"):
             raise ValueError("unsupported env id %r" % (env_id,))
+        if stack_mode not in ("stack", "ring"):
+            raise ValueError("stack_mode must be 'stack' or 'ring'")
         if not torch.cuda.is_available():
             raise RuntimeError("CudaPongVecEnv needs a CUDA device: this simulator has no CPU path")
-        self._lib = _native.load()
+        ext = _native.ext()
+        self._lib = _native.load()          # the plain C ABI, for callers that drive it directly (bench.py, tests)
         self.env_id = env_id
         self.n_agents = 2 if env_id == "cPongDouble-v0" else 1
         self.dim = int(resized_dim)
         self.c = int(frame_stack) if frame_stack else 1
         self.asynchronous = bool(asynchronous)
         self.return_numpy = bool(return_numpy)
-        if stack_mode not in ("stack",):
-            raise ValueError("stack_mode must be 'stack'")
+        self.copy = bool(copy)
         self.stack_mode = stack_mode
+        self.ring = stack_mode == "ring"
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -244,32 +261,30 @@ class CudaPongVecEnv(VecEnv):
         VecEnv.__init__(self, n, obs_space, act_space)
         self.metadata = {"render.modes": ["human", "rgb_array"]}
 
-        cfg = _native.PongConfig(n, self.n_agents, self.dim, int(frame_stack or 0), int(max_num_rounds),
-                                 int(self.device.index), int(seed) & (2 ** 64 - 1), int(first_env))
-        h = ctypes.c_void_p()
-        with torch.cuda.device(self.device):
-            _native.check(self._lib.crl_pong_create(ctypes.byref(cfg), ctypes.byref(h)))
-        self._h = h
+        self._impl = ext.Pong(n, self.n_agents, self.dim, int(frame_stack or 0), int(max_num_rounds), int(self.device.index),
+                              1 if self.ring else 0, bool(zero_on_done), int(seed) & (2 ** 64 - 1), int(first_env))
+        self._h = ctypes.c_void_p(self._impl.raw_handle())
         if atlas is None:
             atlas = np.load(_native.DEFAULT_ATLAS)["strips"]
         atlas = np.ascontiguousarray(atlas, np.uint8)
         if atlas.shape != _native.ATLAS_SHAPE:
             raise ValueError("atlas must have shape %r" % (_native.ATLAS_SHAPE,))
-        _native.check(self._lib.crl_pong_load_atlas(self._h, atlas.ctypes.data, atlas.nbytes, self._stream()))
+        self._impl.load_atlas(torch.from_numpy(atlas))
         if serves is not None:
             self.inject_serves(serves)
 
         dev = self.device
         shape = (n, self.c, self.dim, self.dim)
-        # Output buffers are owned by the env and rotate over `n_buffers` sets: what step t
-        # returned stays valid until step t + n_buffers (the reference returns fresh copies).
+        # the ring (one per agent) carries the frame history, so there is exactly one; the small outputs still rotate
+        self._ring = [torch.empty((n, 2 * self.c, self.dim, self.dim), dtype=torch.uint8, device=dev)
+                      for _ in range(self.n_agents)] if self.ring else None
         self._sets = []
         for _ in range(max(1, int(n_buffers))):
             self._sets.append(dict(
-                obs=[torch.empty(shape, dtype=torch.uint8, device=dev) for _ in range(self.n_agents)],
+                obs=None if self.ring else [torch.empty(shape, dtype=torch.uint8, device=dev) for _ in range(self.n_agents)],
                 rew=torch.zeros((n, 2), dtype=torch.float32, device=dev),
                 real=torch.zeros((n, 2), dtype=torch.float32, device=dev),
-                done=torch.zeros((n,), dtype=torch.uint8, device=dev),
+                done=torch.zeros((n,), dtype=torch.bool, device=dev),
                 steps=torch.zeros((n,), dtype=torch.int32, device=dev)))
         self._cur = 0
         self._bind(0)
@@ -281,27 +296,31 @@ class CudaPongVecEnv(VecEnv):
     # ------------------------------------------------------------------ plumbing
     @property
     def _store(self):
-        """the tensors the rasteriser writes (stack mode: the observations themselves)"""
-        return self._obs if self.n_agents == 2 else [self._obs[0], self._obs[0]]
+        """the two buffers the rasteriser writes: the observations themselves, or the rings (single: agent 0's twice)"""
+        b = self._ring if self.ring else self._obs
+        return [b[0], b[1 if self.n_agents == 2 else 0]]
 
     @property
     def bytes_per_env_step(self):
         """observation bytes the rasteriser writes per env-step"""
-        return self.n_agents * self.c * self.dim * self.dim
+        return self.n_agents * (2 if self.ring else self.c) * self.dim * self.dim
 
     def _bind(self, k):
         b = self._sets[k]
         self._cur = k
-        self._obs, self._rew, self._real, self._done, self._steps = b["obs"], b["rew"], b["real"], b["done"], b["steps"]
+        self._rew, self._real, self._done, self._steps = b["rew"], b["real"], b["done"], b["steps"]
+        if not self.ring:
+            self._obs = b["obs"]
+
+    def _ring_views(self):
+        k = self._impl.ring_phase()
+        self._obs = [r[:, k + 1:k + 1 + self.c] for r in self._ring]
 
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _ptr(self, t):
         return ctypes.c_void_p(t.data_ptr())
-
-    def _obs_ptrs(self, obs):
-        return self._ptr(obs[0]), self._ptr(obs[1] if self.n_agents == 2 else obs[0])
 
     @staticmethod
     def _to_numpy(x):
@@ -311,7 +330,11 @@ class CudaPongVecEnv(VecEnv):
 
     def _fmt_obs(self):
         obs = tuple(self._obs) if self.n_agents == 2 else self._obs[0]
-        return self._to_numpy(obs) if self.return_numpy else obs
+        if self.return_numpy:
+            return self._to_numpy(obs)
+        if self.copy:
+            return tuple(o.clone() for o in obs) if self.n_agents == 2 else obs.clone()
+        return obs
 
     def inject_serves(self, serves):
         """Validation mode: serves[env, k] = (vx, vy) of the k-th serve since construction
@@ -319,21 +342,26 @@ class CudaPongVecEnv(VecEnv):
         s = np.ascontiguousarray(serves, np.float64)
         if s.ndim != 3 or s.shape[0] != self.num_envs or s.shape[2] != 2:
             raise ValueError("serves must have shape (num_envs, K, 2)")
-        _native.check(self._lib.crl_pong_inject_serves(self._h, s.ctypes.data, s.shape[1], self._stream()))
+        self._impl.inject_serves(torch.from_numpy(s))
 
     # ------------------------------------------------------------------ VecEnv protocol
     def reset(self):
         self._bind((self._cur + 1) % len(self._sets))
-        with torch.cuda.device(self.device):
-            p0, p1 = self._obs_ptrs(self._obs)
-            _native.check(self._lib.crl_pong_reset(self._h, p0, p1, self._stream()))
+        st = self._store
+        self._impl.reset(st[0], st[1] if self.n_agents == 2 else None)
+        if self.ring:
+            self._ring_views()
         self._waiting = False
         return self._fmt_obs()
 
     def _coerce_actions(self, actions):
         want = self._actions.shape
         if isinstance(actions, torch.Tensor):
-            a = actions         # device-resident actions are validated on the device: see check()
+            # device-resident actions are validated on the device: see check()
+            if actions.dtype == torch.int32 and actions.device == self.device and actions.is_contiguous() \
+                    and actions.numel() == self._actions.numel():
+                return actions
+            a = actions
         else:
             arr = np.asarray(actions)
             # the reference raises on anything else: assert action_space.contains (cPong, base_pong_env.py:42),
@@ -353,26 +381,27 @@ class CudaPongVecEnv(VecEnv):
     def step_async(self, actions):
         if self._waiting:
             raise AlreadySteppingError()
+        a = self._coerce_actions(actions)
         self._bind((self._cur + 1) % len(self._sets))
-        with torch.cuda.device(self.device):
-            a = self._coerce_actions(actions)
-            p0, p1 = self._obs_ptrs(self._obs)
-            _native.check(self._lib.crl_pong_step(
-                self._h, self._ptr(a), p0, p1, self._ptr(self._rew), self._ptr(self._done), self._ptr(self._steps),
-                self._ptr(self._real), self._stream()))
+        st = self._store
+        self._impl.step(a, st[0], st[1] if self.n_agents == 2 else None, self._rew, self._done, self._steps, self._real)
+        if self.ring:
+            self._ring_views()
         self._waiting = True
 
     def step_wait(self):
         if not self._waiting:
             raise NotSteppingError()
         self._waiting = False
-        done_b = self._done.bool()
-        infos = LazyInfos(self, self._steps, self._real, self._done)
+        done_b, rew_t, steps, real = self._done, self._rew, self._steps, self._real
+        if self.copy:
+            done_b, rew_t, steps, real = done_b.clone(), rew_t.clone(), steps.clone(), real.clone()
+        infos = LazyInfos(self, steps, real, done_b)
         if self.asynchronous:   # SubprocVecEnv: np.stack(rews) / np.stack(dones)
-            rew = self._rew if self.n_agents == 2 else self._rew[:, 0]
+            rew = rew_t if self.n_agents == 2 else rew_t[:, 0]
             done = done_b
         else:                   # DummyVecEnv: buf_rews (N, A) float32, buf_dones (N, A) bool
-            rew = self._rew[:, :self.n_agents]
+            rew = rew_t[:, :self.n_agents]
             done = done_b[:, None].expand(-1, self.n_agents)
         if self.return_numpy:
             rew = rew.cpu().numpy()
@@ -382,24 +411,23 @@ class CudaPongVecEnv(VecEnv):
             infos = list(infos) if not self.asynchronous else tuple(infos)
         return self._fmt_obs(), rew, done, infos
 
-    def _terminal_obs(self, done_u8):
-        with torch.cuda.device(self.device):
-            term = [torch.zeros_like(o) for o in self._obs]
-            p0, p1 = self._obs_ptrs(term)
-            _native.check(self._lib.crl_pong_terminal_obs(self._h, self._ptr(done_u8), p0, p1, self._stream()))
+    def _terminal_obs(self, done):
+        shape = (self.num_envs, self.c, self.dim, self.dim)
+        term = [torch.zeros(shape, dtype=torch.uint8, device=self.device) for _ in range(self.n_agents)]
+        self._impl.terminal_obs(done.to(torch.bool), term[0], term[1] if self.n_agents == 2 else None)
         return tuple(term) if self.n_agents == 2 else term[0]
 
     def seed(self, seed=None):
         # reference: [env.seed(seed + idx)] -> PongSinglePlayerEnv._seed is `pass` -> [None]*N
         if seed is not None:
-            _native.check(self._lib.crl_pong_seed(self._h, int(seed) & (2 ** 64 - 1)))
+            self._impl.seed(int(seed) & (2 ** 64 - 1))
         return [None] * self.num_envs
 
     def close(self):
-        if not self.closed and self._h:
+        if not self.closed and self._impl is not None:
             if torch.cuda.is_available():
                 torch.cuda.synchronize(self.device)
-            self._lib.crl_pong_destroy(self._h)
+            self._impl.close()
             self._h = None
         self.closed = True
 
@@ -414,46 +442,46 @@ class CudaPongVecEnv(VecEnv):
         """float64 (N, 10) device tensor: ball_x, ball_y, vx, vy, left_y, right_y, score_l, score_r,
         num_rounds, num_steps (the PongGame fields)."""
         s = torch.empty((self.num_envs, 10), dtype=torch.float64, device=self.device)
-        with torch.cuda.device(self.device):
-            _native.check(self._lib.crl_pong_get_state(self._h, self._ptr(s), self._stream()))
+        self._impl.get_state(s)
         return s
 
     def set_state(self, state):
         s = torch.as_tensor(state, dtype=torch.float64).to(self.device).contiguous()
         assert tuple(s.shape) == (self.num_envs, 10)
-        with torch.cuda.device(self.device):
-            _native.check(self._lib.crl_pong_set_state(self._h, self._ptr(s), self._stream()))
-            torch.cuda.current_stream(self.device).synchronize()
+        self._impl.set_state(s)
+        torch.cuda.current_stream(self.device).synchronize()
 
     def check(self):
-        """Raise if a device-side error flag (serve table overrun) is set. Synchronises."""
-        _native.check(self._lib.crl_pong_check(self._h, self._stream()))
+        """Raise if a device-side error flag is set (serve table overrun, invalid device action).  Synchronises; the flag
+        is cleared once reported."""
+        self._impl.check()
 
     def episode_stats(self):
         """Device-accumulated episode statistics of this shard as a dict (synchronises)."""
-        raw = (ctypes.c_uint64 * 8)()
-        _native.check(self._lib.crl_pong_get_stats(self._h, raw, self._stream()))
         from .distributed import stats_from_raw
-        return stats_from_raw(list(raw))
+        return stats_from_raw(list(self._impl.stats()))
 
     def render_obs_generic(self):
-        """Observations through the one-thread-per-pixel reference rasteriser (cross-check)."""
-        out = [torch.empty_like(o) for o in self._obs]
-        with torch.cuda.device(self.device):
-            p0, p1 = self._obs_ptrs(out)
-            _native.check(self._lib.crl_pong_render_obs_generic(self._h, p0, p1, self._stream()))
+        """Observations through the one-thread-per-pixel reference rasteriser (cross-check); ring mode: the views of a
+        completely rewritten scratch ring."""
+        if self.ring:
+            out = [torch.empty_like(r) for r in self._ring]
+        else:
+            out = [torch.empty_like(o) for o in self._obs]
+        self._impl.render_obs_generic(out[0], out[1] if self.n_agents == 2 else None)
+        if self.ring:
+            k = self._impl.ring_phase()
+            out = [r[:, k + 1:k + 1 + self.c] for r in out]
         return tuple(out) if self.n_agents == 2 else out[0]
 
     def get_images(self, indices=None, agent=0, **kwargs):
         """Raw 210x160x3 RGB frames (what the reference's env.render('rgb_array') returns)."""
         imgs = []
-        with torch.cuda.device(self.device):
-            for i in self._get_indices(indices):
-                f0 = torch.empty((210, 160, 3), dtype=torch.uint8, device=self.device)
-                f1 = torch.empty_like(f0)
-                _native.check(self._lib.crl_pong_render_raw(self._h, int(i), self._ptr(f0), self._ptr(f1),
-                                                            self._stream()))
-                imgs.append((f1 if agent == 1 else f0).cpu().numpy())
+        for i in self._get_indices(indices):
+            f0 = torch.empty((210, 160, 3), dtype=torch.uint8, device=self.device)
+            f1 = torch.empty_like(f0)
+            self._impl.render_raw(int(i), f0, f1)
+            imgs.append((f1 if agent == 1 else f0).cpu().numpy())
         return imgs
 
     def render(self, mode="human", *args, **kwargs):

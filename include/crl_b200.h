@@ -51,6 +51,15 @@ typedef struct crl_pong_config {
     int32_t frame_stack;    /* make_envs frame_stack; 0 = None (one channel) */
     int32_t max_num_rounds; /* gym registry kwarg, pong/register.py:13-22 (21) */
     int32_t device;         /* CUDA device ordinal */
+    int32_t stack_mode;     /* 0 = every step writes the full (C, dim, dim) stack per agent, like FrameStack._get_ob
+                               (utils/atari_wrappers.py:257-259).  1 = double-write ring: the observation buffers are
+                               uint8 [num_envs][2*C][dim][dim] rings OWNED BY THE CALLER ACROSS STEPS (same pointers every
+                               call); a step stores the newest frame at slots k and k + C, k = crl_pong_ring_phase(), and
+                               the observation is the view of slots k+1 .. k+C (oldest -> newest): 2 frames written
+                               instead of C.  Needs frame_stack >= 2. */
+    int32_t zero_on_done;   /* 1 = FrameStackTensor semantics (utils/utils.py:145-173): after a done the history is all
+                               zeros and only the newest frame is the reset observation, instead of FrameStack.reset's
+                               C copies (utils/atari_wrappers.py:246-250) */
     uint64_t seed;          /* serve RNG seed (Philox); ignored once serves are injected */
     int64_t first_env;      /* global index of env 0 of this shard: RNG streams are keyed by
                                global env index, so results do not depend on the sharding */
@@ -82,7 +91,7 @@ int crl_pong_inject_serves(crl_pong* h, const double* serves_host, int32_t k, vo
 int crl_pong_seed(crl_pong* h, uint64_t seed);
 
 /* VecEnv.reset(): obs{0,1}_dev receive uint8 [num_envs][C][dim][dim] per agent
- * (obs1_dev is ignored for n_agents == 1). */
+ * (obs1_dev is ignored for n_agents == 1).  stack_mode 1: [num_envs][2*C][dim][dim] rings, see crl_pong_config. */
 int crl_pong_reset(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_dev, void* stream);
 
 /* VecEnv.step(actions) == step_async + step_wait with auto-reset on done.
@@ -101,6 +110,9 @@ int crl_pong_step(crl_pong* h, const int32_t* actions_dev, uint8_t* obs0_dev, ui
 int crl_pong_step_state(crl_pong* h, const int32_t* actions_dev, float* rew_dev, uint8_t* done_dev,
                         int32_t* num_steps_dev, float* real_reward_dev, void* stream);
 int crl_pong_render_obs(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_dev, void* stream);
+/* stack_mode 1: slot k the last step wrote the newest frame to (and to k + C); the observation is slots k+1 .. k+C.
+ * Advanced by crl_pong_step / crl_pong_step_state, 0 after crl_pong_reset.  No device work, no synchronisation. */
+int crl_pong_ring_phase(crl_pong* h);
 /* same output through the one-thread-per-pixel reference rasteriser (cross-check) */
 int crl_pong_render_obs_generic(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_dev, void* stream);
 
@@ -170,7 +182,13 @@ typedef struct crl_car_config {
     int32_t done_mode;          /* two cars: 0 = env done when ANY car is (FlattenMultiAgentObservation.step,
                                    utils/atari_wrappers.py:323-331, the make_envs path); 1 = when car 0 is
                                    (make_competitive_car_racing returns d[0], make_competitive_car_racing.py:29-33) */
-    int32_t reserved;           /* must be 0 */
+    int32_t stack_mode;         /* 0 = every step writes the whole (players * C, 96, 96) observation (FrameStack._get_ob /
+                                   FlattenMultiAgentObservation, utils/atari_wrappers.py:257-259, 333-334).  1 = double-write
+                                   ring: obs_dev is uint8 [num_envs][players][2*C][96][96], owned by the caller ACROSS
+                                   steps (same pointer every call); a step stores each player's new frame at slots k and
+                                   k + C, k = crl_car_ring_phase(), and the player's stack is the view of slots
+                                   k+1 .. k+C (oldest -> newest).  Needs frame_stack >= 2.  term_obs_dev rows stay plain
+                                   [players * C][96][96] stacks. */
     uint64_t seed;              /* track / birth-place RNG (Philox) */
     int64_t first_env;          /* global index of env 0 of this shard */
 } crl_car_config;
@@ -235,11 +253,20 @@ int crl_car_render_obs(crl_car* h, uint8_t* obs_dev, uint8_t* term_obs_dev, void
 /* float64 [num_envs * num_players][24]: hull x, y, angle, vx, vy, w; per wheel: joint angle,
  * omega, gas, #tiles touched; reward; tiles visited. */
 int crl_car_get_state(crl_car* h, double* state_dev, void* stream);
+/* Debug / tests: put every car into the state described by float64 [num_envs * num_players][24] (layout of
+ * crl_car_get_state; used: hull pose and velocity, wheel joint angles, omega, gas, reward).  Wheels are placed on their
+ * joint anchors moving rigidly with the hull; joint impulses, car-car contacts and wheel tile sets are cleared. */
+int crl_car_set_state(crl_car* h, const double* state_dev, void* stream);
+/* stack_mode 1: slot k the last step wrote the new frames to (and to k + C).  0 after crl_car_reset. */
+int crl_car_ring_phase(crl_car* h);
 /* number of tiles of env `env`'s current track, and (if non-NULL) its track points float64 [n][3] beta, x, y */
 int crl_car_get_track(crl_car* h, int32_t env, int32_t* n_out, double* pts_host, int32_t max_points, void* stream);
 
 int crl_car_random_actions(float* actions_dev, int32_t n_values, uint64_t seed, uint64_t step, void* stream);
-int crl_car_get_stats(crl_car* h, uint64_t* stats_host, void* stream);   /* [0] episodes [1] sum length [2] sum tiles */
+/* [0] episodes [1] sum of episode lengths [2] sum of tiles visited (car 0) [3] auto-resets that found no track
+ * generated ahead and built it inside the step [4] frames rasterised on the exact slow path (span pool full)
+ * [5] launches of the ahead-of-time track generator so far */
+int crl_car_get_stats(crl_car* h, uint64_t* stats_host, void* stream);
 /* car-car contacts of cCarRacingDouble (what box2d-py's b2World::Step resolves between the fixtures of the two
  * cars, car_dynamics.py:63-68,94-96): int32 [num_envs] touching fixture pairs per env after the last step, and the
  * number of contacts dropped so far because an env had more than 8 touching pairs at once (either may be NULL). */
