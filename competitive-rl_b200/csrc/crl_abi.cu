@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -221,6 +222,7 @@ int crl_pong_create(const crl_pong_config* cfg, crl_pong** out) {
             }
             g_launches += 1;
             d.fast_tabs = h->fast_tabs_dev;
+            d.quad_ok = (pong_quad_ok(tabs) && getenv("CRL_PONG_NO_QUAD") == nullptr) ? 1 : 0;
         }
     }
     d.tabs = h->tabs_dev;

@@ -116,7 +116,9 @@ struct PongDev {
     int text_stride;           // bytes per text_tab entry (multiple of 16)
     const void* fast_tabs;     // FastTabs<dim> image for the hot kernel (nullptr: dim not specialised)
     int fast_ok;               // atlas rows sharing a dst row with the arena are pure white
-    int raster_grid[2];        // persistent grid of the hot kernel on this handle's device: [0] 84x84, [1] 42x42
+    int raster_grid[3];        // persistent grids of the hot kernels on this handle's device: [0] 84x84, [1] 42x42 one frame
+                               // per warp, [2] 42x42 four frames per warp
+    int quad_ok;               // the 42x42 geometry the four-frames-per-warp kernel relies on holds
 };
 
 // ---- Philox4x32-10 (counter-based; streams keyed by seed and global env index) ----
@@ -150,7 +152,8 @@ cudaError_t launch_pong_raster(const PongDev& p, const FrameSpec* hist, uint8_t*
 // ring = 1: obs* are 2c-slot rings, rewritten completely (terminal observations are always plain stacks: ring = 0)
 cudaError_t launch_pong_raster_generic(const PongDev& p, const FrameSpec* hist, const uint8_t* only_done, int ring,
                                        uint8_t* obs0, uint8_t* obs1, cudaStream_t s);
-cudaError_t pong_raster_init(int grid_out[2]);
+cudaError_t pong_raster_init(int grid_out[3]);
+bool pong_quad_ok(const AreaTabs& a);
 size_t pong_fast_tabs_bytes(int dim);
 bool pong_fast_tabs_fill(const AreaTabs& a, int text_stride, void* host_buf);   // false: geometry not supported
 cudaError_t launch_pong_build_bat_lut(int dim, void* fast_tabs_dev, cudaStream_t s);

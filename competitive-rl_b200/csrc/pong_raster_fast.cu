@@ -467,6 +467,298 @@ pong_raster_fast_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
 }
 
 // ---------------------------------------------------------------------------------
+// 42x42 (the make_envs default, what every built-in agent consumes): FOUR frames per warp.
+//
+// A 42x42 frame is 1 764 bytes, a quarter of the 84x84 one, but what has to be computed per frame (two bat strips, two
+// pooled ball positions, the scoreboard rows) is the same, so the one-frame-per-warp kernel above is bound by
+// instruction issue at 42x42 (518 warp-instructions per 1 764 bytes, 0.52 of the HBM roofline).  Here a warp owns a QUAD
+// of four frames that are adjacent in the output (with frame_stack 4: the stack of one (env, agent); with frame_stack
+// None: four consecutive envs) = 7 056 bytes = 441 16-byte vectors.  Lane group g = lane >> 3 works on frame g, so every
+// instruction of the patch phase serves four frames at once: per side the (frame A | frame B, row) items of the bat strips
+// (a bat touches <= 4 destination rows and exactly two destination columns -> one 16-bit store), per pooled ball the
+// <= 3 x 2 destination pixels.  The quad is then drained as one flat run of 16-byte st.global.cs (1 764 is not a multiple
+// of 16, 7 056 is), instead of 4-byte stores.  Arithmetic is the kernel's above, so the results are bit-identical.
+// Quads containing an unusual frame (both pool buffers zero, score combination outside text_tab) are evaluated exactly,
+// pixel by pixel, like pong_raster_generic_kernel does.
+// the tables of FastTabs the quad kernel keeps in shared memory (the bat LUT narrowed to the two columns a bat touches)
+template <int DIM> struct alignas(16) QuadTabs {
+    TapEnt<FastCfg<DIM>::TAPS> xe[DIM], ye[DIM];
+    float xlut[DIM][1 << FastCfg<DIM>::TAPS];
+    uint16_t bat2[2][DIM][1 << FastCfg<DIM>::TAPS];
+    uint8_t x_first[SCREEN_W], x_last[SCREEN_W], y_first[FIRST_PAD], y_last[FIRST_PAD];
+    uint32_t bat_c0[2], pad[2];
+};
+
+#ifndef CRL_QUAD_CTAS
+#define CRL_QUAD_CTAS 2      // measured: 3 CTAs per SM (80 registers, 108 B of spills) 0.236 ms per step, 2 CTAs 0.2 ms
+#endif
+#ifndef CRL_QUAD_WARPS
+#define CRL_QUAD_WARPS 10      // measured per 65 536-env step: 8 warps x 2 CTAs 0.202 ms, 10 x 2 (96 registers) 0.191 ms, 11 x 2 and 8 x 3 (80 registers, spills) 0.23 ms
+#endif
+constexpr int QUAD_WARPS = CRL_QUAD_WARPS;
+template <int DIM>
+__global__ void __launch_bounds__(QUAD_WARPS * 32, CRL_QUAD_CTAS)
+pong_raster_quad_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* __restrict__ obs0,
+                        uint8_t* __restrict__ obs1, const FastTabs<DIM>* __restrict__ gtabs) {
+    constexpr int TAPS = FastCfg<DIM>::TAPS, NP = 1 << TAPS;
+    constexpr int DD = DIM * DIM, QB = 4 * DD, NV = QB / 16, DW = DD / 4;
+    typedef QuadTabs<DIM> Tabs;
+    static_assert(QB % 16 == 0 && DD % 4 == 0, "a quad must be a whole number of 16-byte vectors");
+
+    extern __shared__ uint4 smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(smem_raw);
+    Tabs* Tw = reinterpret_cast<Tabs*>(smem);
+    const Tabs* T = Tw;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 3, sub = lane & 7;                 // frame of the quad, lane within its group
+    uint8_t* smq = smem + sizeof(Tabs) + (size_t)warp * QB;  // the warp's quad buffer (16-byte aligned)
+    uint8_t* sm8 = smq + g * DD;                             // this group's frame
+    const uint32_t* tm32 = reinterpret_cast<const uint32_t*>(p.tmpl);
+
+    auto load_templates = [&]() {
+        uint32_t* q32 = reinterpret_cast<uint32_t*>(smq);
+        for (int i = lane; i < DW; i += 32) {
+            const uint32_t v = tm32[i];
+            q32[i] = v; q32[DW + i] = v; q32[2 * DW + i] = v; q32[3 * DW + i] = v;
+        }
+    };
+    {   // CTA prologue: tables into shared memory, the template into every frame of every warp's quad buffer
+        const int tid = threadIdx.x, nt = blockDim.x;
+        for (int i = tid; i < DIM; i += nt) { Tw->xe[i] = gtabs->xe[i]; Tw->ye[i] = gtabs->ye[i]; }
+        for (int i = tid; i < DIM * NP; i += nt) (&Tw->xlut[0][0])[i] = (&gtabs->xlut[0][0])[i];
+        for (int i = tid; i < 2 * DIM * NP; i += nt) (&Tw->bat2[0][0][0])[i] = (uint16_t)(&gtabs->bat_lut[0][0][0])[i];
+        for (int i = tid; i < SCREEN_W; i += nt) { Tw->x_first[i] = gtabs->x_first[i]; Tw->x_last[i] = gtabs->x_last[i]; }
+        for (int i = tid; i < FIRST_PAD; i += nt) { Tw->y_first[i] = gtabs->y_first[i]; Tw->y_last[i] = gtabs->y_last[i]; }
+        if (tid < 2) Tw->bat_c0[tid] = gtabs->bat_c0[tid];
+        load_templates();
+    }
+    __syncthreads();
+
+    const int text_words = p.text_stride / 4;
+    const int cL = (int)T->bat_c0[0], cR = (int)T->bat_c0[1];
+    const int b_which = sub >> 2, b_row = sub & 3;           // bat items of one side: (frame A | B, row)
+    const int p_col = sub & 3, p_row = sub >> 2;             // ball pixels of one pooled frame: 4 x 2 window
+    // what the previous quad left patched in this group's frame (restored before the next patches)
+    int bat_off[2] = {-1, -1}, ball_off[2] = {-1, -1};
+    uint32_t bat_rest[2] = {0u, 0u}, ball_old[2] = {0u, 0u};
+    int cur_text = -1;
+
+    // 32-bit work indices (the host launches this kernel only when they fit)
+    const unsigned c = (unsigned)p.c, n_env = (unsigned)p.n;
+    const unsigned frames_per_agent = n_env * c;
+    const unsigned quads_per_agent = (frames_per_agent + 3u) / 4u;
+    const unsigned n_quads = quads_per_agent * (unsigned)p.n_agents;
+    const bool two = p.n_agents == 2;
+    constexpr unsigned PER_TICKET = 4;                       // one atomic per 28 KB written (see the kernel above)
+    // With few warps per SM (the quad buffers fill the shared memory) little hides a dependent global load: the next
+    // ticket is drawn while the current one is worked on, and the frame specs of a ticket's quads are pulled into L1
+    // (one prefetch per lane) as soon as the ticket is known.
+    auto frame_of = [&](unsigned F, unsigned& env, unsigned& slot) {
+        if (c == 4u) { env = F >> 2; slot = F & 3u; }
+        else if (c == 1u) { env = F; slot = 0u; }
+        else { env = F / c; slot = F - env * c; }
+    };
+    unsigned next_ticket = 0u;
+    if (lane == 0) next_ticket = (unsigned)atomicAdd(p.work_counter, (unsigned long long)PER_TICKET);
+    unsigned s = 0u, s_end = 0u;
+    for (;;) {
+        if (s >= s_end) {
+            s = __shfl_sync(0xffffffffu, next_ticket, 0);
+            if (s >= n_quads) break;
+            s_end = min(s + PER_TICKET, n_quads);
+            if (sub < PER_TICKET && s + sub < n_quads) {     // lane (g, sub): frame g of quad s + sub
+                const unsigned F_ = (two ? (s + sub) >> 1 : s + sub) * 4u + g;
+                if (F_ < frames_per_agent) {
+                    unsigned e_, sl_;
+                    frame_of(F_, e_, sl_);
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(hist + (size_t)sl_ * n_env + e_));
+                }
+            }
+            if (lane == 0) next_ticket = (unsigned)atomicAdd(p.work_counter, (unsigned long long)PER_TICKET);   // used a ticket later
+        }
+        const unsigned id = s++;
+        // agents interleaved, so that both observation buffers are written front to back in step
+        const int agent = two ? (int)(id & 1u) : 0;
+        const unsigned q = two ? (id >> 1) : id;
+        const unsigned F = q * 4u + g;
+        const bool valid = F < frames_per_agent;
+        unsigned env = 0u, slot = 0u;
+        if (valid) frame_of(F, env, slot);
+        uint8_t* out_quad = (agent ? obs1 : obs0) + (size_t)q * QB;
+        FrameSpec f = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) f = hist[(size_t)slot * n_env + env];
+        const FrameSpec f_raw = f;
+
+        // ---- frame context (uniform within the lane group) ----
+        const bool va = (f.y >> 16) & 1u, vb = (f.w >> 16) & 1u;
+        if (!va) { f.x = f.z; f.y = f.w; }
+        if (!vb) { f.z = f.x; f.w = f.y; }
+        const int pairA = (int)(f.y & 255u) * ATLAS_SCORES + (int)((f.y >> 8) & 255u);
+        const int pairB = (int)(f.w & 255u) * ATLAS_SCORES + (int)((f.w >> 8) & 255u);
+        int base = pairA, kind = 0;
+        bool text_ok = true;
+        if (pairA != pairB) {   // one point scored between the two pooled frames
+            const int d = pairB - pairA;
+            if (d == ATLAS_SCORES) kind = 1;
+            else if (d == 1 && (pairA % ATLAS_SCORES) != ATLAS_SCORES - 1) kind = 2;
+            else if (d == -ATLAS_SCORES) { base = pairB; kind = 1; }
+            else if (d == -1 && (pairB % ATLAS_SCORES) != ATLAS_SCORES - 1) { base = pairB; kind = 2; }
+            else text_ok = false;
+        }
+        const bool unusual = valid && (!(va || vb) || !text_ok);
+        if (__any_sync(0xffffffffu, unusual)) {
+            // ======== exact path: every pixel of the four frames from the atlas and the frame specs ========
+            __syncwarp();
+            for (int j = 0; j < 4; ++j) {
+                FrameSpec fj;
+                fj.x = __shfl_sync(0xffffffffu, f_raw.x, 8 * j); fj.y = __shfl_sync(0xffffffffu, f_raw.y, 8 * j);
+                fj.z = __shfl_sync(0xffffffffu, f_raw.z, 8 * j); fj.w = __shfl_sync(0xffffffffu, f_raw.w, 8 * j);
+                const FrameCtx cx = make_ctx(fj, agent);
+                for (int pix = lane; pix < DD; pix += 32)
+                    smq[j * DD + pix] = cx.any_valid ? eval_pixel(p.tabs, cx, p.atlas, pix / DIM, pix % DIM) : (uint8_t)0;
+            }
+            __syncwarp();
+            const int n_valid = (int)min(4u, frames_per_agent - q * 4u);
+            const uint32_t* q32 = reinterpret_cast<const uint32_t*>(smq);
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(out_quad);
+            for (int i = lane; i < n_valid * DW; i += 32) st_stream(o32 + i, q32[i]);
+            __syncwarp();
+            load_templates();                                 // back to the resident-template state
+            cur_text = -1;
+            bat_off[0] = bat_off[1] = ball_off[0] = ball_off[1] = -1;
+            __syncwarp();
+            continue;
+        }
+
+        const bool same = (f.x == f.z);
+        const int lyA = (f.x >> 16) & 255u, ryA = f.x >> 24, lyB = (f.z >> 16) & 255u, ryB = f.z >> 24;
+        const int vlA = agent ? ryA : lyA, vrA = agent ? lyA : ryA;   // view coordinates (agent 1: mirrored in x)
+        const int vlB = agent ? ryB : lyB, vrB = agent ? lyB : ryB;
+
+        // the scoreboard rows this frame needs: pull the table entry (L2-resident, 304 bytes) into L1 now, copy it below
+        const int text_id = (base * 3 + kind) * 2 + agent;
+        const bool reload_text = valid && text_id != cur_text;
+        const uint32_t* __restrict__ te = reinterpret_cast<const uint32_t*>(p.text_tab + (size_t)text_id * p.text_stride);
+        if (reload_text && sub * 128 < p.text_stride)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(te) + sub * 128));
+
+        // ======== restore what the previous quad patched ========
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            if (bat_off[r] >= 0) *reinterpret_cast<uint16_t*>(sm8 + bat_off[r]) = (uint16_t)bat_rest[r];
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            if (ball_off[r] >= 0) sm8[ball_off[r]] = (uint8_t)ball_old[r];   // after the bats: a ball pixel may lie on a strip
+        __syncwarp();
+
+        // vertical tap masks of the two pooled bats per view side (arena-clipped, as tap_bits wants them)
+        const int la0 = max(vlA, ARENA_TOP), la1 = min(vlA + BAT_H, ARENA_BOTTOM), lb0 = max(vlB, ARENA_TOP), lb1 = min(vlB + BAT_H, ARENA_BOTTOM);
+        const int ra0 = max(vrA, ARENA_TOP), ra1 = min(vrA + BAT_H, ARENA_BOTTOM), rb0 = max(vrB, ARENA_TOP), rb1 = min(vrB + BAT_H, ARENA_BOTTOM);
+        auto bat_vbits = [&](bool right, int sy0) -> uint32_t {
+            const int a0 = right ? ra0 : la0, a1 = right ? ra1 : la1, b0 = right ? rb0 : lb0, b1 = right ? rb1 : lb1;
+            uint32_t vbits = 0u;
+            if (a1 > a0) vbits |= tap_bits(((1u << (a1 - a0)) - 1u) << 8, a0, sy0);
+            if (b1 > b0) vbits |= tap_bits(((1u << (b1 - b0)) - 1u) << 8, b0, sy0);
+            return vbits;
+        };
+
+        // ======== ball pixels: round r = pooled frame r, lane = pixel of its 4 x 2 window; exact evaluation (values only:
+        //          nothing here touches the frame buffer, so the scoreboard prefetch above has time to land) ========
+        uint32_t ball_val[2] = {0u, 0u};
+        {
+            int ax0 = f.x & 255u, ax1 = min(ax0 + BALL_SIZE, SCREEN_W);
+            int ay0 = (f.x >> 8) & 255u, ay1 = min(ay0 + BALL_SIZE, ARENA_BOTTOM);
+            ay0 = max(ay0, ARENA_TOP);
+            int bx0 = f.z & 255u, bx1 = min(bx0 + BALL_SIZE, SCREEN_W);
+            int by0 = (f.z >> 8) & 255u, by1 = min(by0 + BALL_SIZE, ARENA_BOTTOM);
+            by0 = max(by0, ARENA_TOP);
+            if (agent) {
+                int t = SCREEN_W - ax1; ax1 = SCREEN_W - ax0; ax0 = t;
+                t = SCREEN_W - bx1; bx1 = SCREEN_W - bx0; bx0 = t;
+            }
+            const bool ea = valid && ax1 > ax0 && ay1 > ay0, eb = valid && bx1 > bx0 && by1 > by0 && !same;
+            const uint32_t axm = ((1u << (ax1 - ax0)) - 1u) << 8, aym = ((1u << (ay1 - ay0)) - 1u) << 8;
+            const uint32_t bxm = ((1u << (bx1 - bx0)) - 1u) << 8, bym = ((1u << (by1 - by0)) - 1u) << 8;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                ball_off[r] = -1;
+                const int mx0 = r ? bx0 : ax0, mx1 = r ? bx1 : ax1, my0 = r ? by0 : ay0, my1 = r ? by1 : ay1;
+                if (r ? eb : ea) {
+                    const int dx = (int)T->x_first[mx0] + p_col, dy = (int)T->y_first[my0] + p_row;
+                    if (dx <= (int)T->x_last[mx1 - 1] && dy <= (int)T->y_last[my1 - 1]) {
+                        const uint32_t xmeta = T->xe[dx].meta;
+                        const TapEnt<TAPS> Y = T->ye[dy];
+                        const int sx0 = xmeta & 255u, sy0 = Y.meta & 255u;
+                        const uint32_t xmask = (xmeta >> 8) & 255u, ymask = (Y.meta >> 8) & 255u;
+                        uint32_t pat = xmask * spread6((Y.meta >> 16) & 255u);   // border rows: all white
+                        if (ea) pat |= (tap_bits(axm, ax0, sx0) & xmask) * spread6(tap_bits(aym, ay0, sy0) & ymask);
+                        if (eb) pat |= (tap_bits(bxm, bx0, sx0) & xmask) * spread6(tap_bits(bym, by0, sy0) & ymask);
+                        const bool nl = (unsigned)(dx - cL) < 4u, nr = (unsigned)(dx - cR) < 4u;
+                        if (nl || nr) {                                   // a bat strip under this pixel: both frames' bats
+                            const uint32_t hb = tap_bits(((1u << BAT_W) - 1u) << 8, nr ? RIGHT_BAT_X : LEFT_BAT_X, sx0);
+                            pat |= (hb & xmask) * spread6(bat_vbits(nr, sy0) & ymask);
+                        }
+                        ball_val[r] = eval_from_pat_lut<TAPS>(T->xlut[dx], Y, pat);
+                        ball_off[r] = dy * DIM + dx;
+                    }
+                }
+            }
+        }
+
+        // ======== scoreboard rows of this frame's score pair(s), when the buffer holds another pair's ========
+        if (reload_text) {
+            uint32_t* d32 = reinterpret_cast<uint32_t*>(sm8);
+            for (int i = sub; i < text_words; i += 8) d32[i] = te[i];
+            cur_text = text_id;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            if (ball_off[r] >= 0) ball_old[r] = sm8[ball_off[r]];     // template / scoreboard value under the ball
+        __syncwarp();
+
+        // ======== bat strips: round r = view side r, lane = (frame A | B, row); one LUT entry (two pixels) per row ========
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            bat_off[r] = -1;
+            const int y0 = b_which ? (r ? vrB : vlB) : (r ? vrA : vlA);
+            const int c0 = max(y0, ARENA_TOP), c1 = min(y0 + BAT_H, ARENA_BOTTOM);   // white on white outside
+            if (valid && c1 > c0 && !(b_which && same)) {
+                const int dy = (int)T->y_first[c0] + b_row;
+                if (dy <= (int)T->y_last[c1 - 1]) {
+                    const uint32_t meta = T->ye[dy].meta;
+                    const uint32_t vbits = bat_vbits(r != 0, meta & 255u) & ((meta >> 8) & 255u);
+                    bat_off[r] = dy * DIM + (r ? cR : cL);
+                    bat_rest[r] = T->bat2[r][dy][0];
+                    *reinterpret_cast<uint16_t*>(sm8 + bat_off[r]) = T->bat2[r][dy][vbits];
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            if (ball_off[r] >= 0) sm8[ball_off[r]] = (uint8_t)ball_val[r];   // overrides the strip LUT where the ball is near
+        __syncwarp();
+
+        // ======== drain: the quad as one run of 16-byte streaming stores ========
+        if (q * 4u + 4u <= frames_per_agent) {
+            const uint4* q128 = reinterpret_cast<const uint4*>(smq);
+            uint4* out = reinterpret_cast<uint4*>(out_quad);
+#pragma unroll
+            for (int j = 0; j < (NV + 31) / 32; ++j)
+                if ((j + 1) * 32 <= NV || lane + 32 * j < NV) st_stream(out + lane + 32 * j, q128[lane + 32 * j]);
+        } else {                                             // the last, partial quad of a buffer
+            const int n_valid = (int)(frames_per_agent - q * 4u);
+            const uint32_t* q32 = reinterpret_cast<const uint32_t*>(smq);
+            uint32_t* o32 = reinterpret_cast<uint32_t*>(out_quad);
+            for (int i = lane; i < n_valid * DW; i += 32) st_stream(o32 + i, q32[i]);
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // host side
 template <int DIM>
 static bool fill_fast_tabs(const AreaTabs& a, FastTabs<DIM>* t) {
@@ -512,6 +804,38 @@ static bool fill_fast_tabs(const AreaTabs& a, FastTabs<DIM>* t) {
     return true;
 }
 
+// geometry the four-frames-per-warp kernel relies on: a bat touches at most 4 destination rows and only the first two
+// columns of its strip, whose byte offset is even in every row (16-bit store); a ball touches at most 3 x 2 pixels
+template <int DIM>
+static bool quad_geometry_ok(const AreaTabs& a) {
+    if (DIM % 2) return false;
+    for (int side = 0; side < 2; ++side) {
+        const int x0 = side ? RIGHT_BAT_X : LEFT_BAT_X;
+        const int c0 = (a.x_first[x0] / 4) * 4;
+        if (a.x_first[x0] != c0 || a.x_last[x0 + BAT_W - 1] > c0 + 1) return false;
+    }
+    for (int y = ARENA_TOP; y + 1 <= ARENA_BOTTOM; ++y) {
+        const int y1 = y + BAT_H < ARENA_BOTTOM ? y + BAT_H : ARENA_BOTTOM;
+        if (a.y_last[y1 - 1] - a.y_first[y] + 1 > 4) return false;
+    }
+    for (int x = 0; x < SCREEN_W; ++x) {
+        const int x1 = x + BALL_SIZE < SCREEN_W ? x + BALL_SIZE : SCREEN_W;
+        if (a.x_last[x1 - 1] - a.x_first[x] + 1 > 4) return false;
+    }
+    for (int y = ARENA_TOP; y < ARENA_BOTTOM; ++y) {
+        const int y1 = y + BALL_SIZE < ARENA_BOTTOM ? y + BALL_SIZE : ARENA_BOTTOM;
+        if (a.y_last[y1 - 1] - a.y_first[y] + 1 > 2) return false;
+    }
+    return true;
+}
+
+bool pong_quad_ok(const AreaTabs& a) { return a.dim == 42 && quad_geometry_ok<42>(a); }
+
+template <int DIM>
+static size_t quad_smem_bytes() {
+    return sizeof(QuadTabs<DIM>) + (size_t)QUAD_WARPS * 4 * DIM * DIM;
+}
+
 template <int DIM>
 static size_t fast_smem_bytes() {
     constexpr int FB = ((DIM * DIM + 15) / 16) * 16;
@@ -540,7 +864,7 @@ cudaError_t launch_pong_build_bat_lut(int dim, void* fast_tabs_dev, cudaStream_t
 }
 
 // per device (called at handle creation): opt in to the dynamic shared memory size and size the persistent grid
-cudaError_t pong_raster_init(int g_grid[2]) {
+cudaError_t pong_raster_init(int g_grid[3]) {
     cudaError_t e;
     int dev = 0, sms = 0, nb = 0;
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -561,6 +885,11 @@ cudaError_t pong_raster_init(int g_grid[2]) {
                                                       fast_smem_bytes<42>());
     if (e != cudaSuccess) return e;
     g_grid[1] = sms * max(nb, 1);
+    e = cudaFuncSetAttribute(pong_raster_quad_kernel<42>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)quad_smem_bytes<42>());
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, pong_raster_quad_kernel<42>, QUAD_WARPS * 32, quad_smem_bytes<42>());
+    if (e != cudaSuccess) return e;
+    g_grid[2] = sms * max(nb, 1);
     return cudaSuccess;
 }
 
@@ -577,6 +906,11 @@ cudaError_t launch_pong_raster(const PongDev& p, const FrameSpec* hist, uint8_t*
         const unsigned grid = (unsigned)min((long long)p.raster_grid[0], want);
         pong_raster_fast_kernel<84><<<grid, FAST_WARPS * 32, fast_smem_bytes<84>(), s>>>(
             p, hist, obs0, obs1, reinterpret_cast<const FastTabs<84>*>(p.fast_tabs));
+    } else if (p.quad_ok && !p.ring && (long long)p.n * p.c * p.n_agents < (1LL << 31)) {
+        const long long quads = (((long long)p.n * p.c + 3) / 4) * p.n_agents;
+        const unsigned grid = (unsigned)min((long long)p.raster_grid[2], (quads + 4 * QUAD_WARPS - 1) / (4 * QUAD_WARPS));
+        pong_raster_quad_kernel<42><<<grid, QUAD_WARPS * 32, quad_smem_bytes<42>(), s>>>(
+            p, hist, obs0, obs1, reinterpret_cast<const FastTabs<42>*>(p.fast_tabs));
     } else {
         const unsigned grid = (unsigned)min((long long)p.raster_grid[1], want);
         pong_raster_fast_kernel<42><<<grid, FAST_WARPS * 32, fast_smem_bytes<42>(), s>>>(

@@ -142,9 +142,11 @@ def test_obs_parity_vs_oracle(env_id, dim, fs, N, T, atlas):
 def test_fast_vs_generic_rasteriser_random_states(atlas):
     """Arbitrary (also unreachable) states: every ball/bat position class incl. ball above the arena,
     at the walls, overlapping bats; scores anywhere in the atlas."""
-    N = 8192
     rng = np.random.default_rng(11)
-    for env_id, dim, fs in [("cPongDouble-v0", 84, 4), ("cPongDouble-v0", 42, None), ("cPong-v0", 84, None)]:
+    # 42x42 runs the four-frames-per-warp kernel: full stacks, frame_stack None (four envs per quad), and sizes that
+    # leave a partial last quad (8190 * 3 and 8189 * 1 frames per agent are not multiples of 4)
+    for env_id, dim, fs, N in [("cPongDouble-v0", 84, 4, 8192), ("cPongDouble-v0", 42, None, 8192), ("cPong-v0", 84, None, 8192),
+                               ("cPongDouble-v0", 42, 4, 8192), ("cPong-v0", 42, 3, 8190), ("cPongDouble-v0", 42, None, 8189)]:
         envs = _make(env_id, N, dim, fs, None, seed=1)
         envs.reset()
         for it in range(3):
