@@ -105,7 +105,10 @@ class DevicePolicy(object):
         obs = torch.as_tensor(obs).to(self.device, dtype=torch.float32).reshape(self.num_envs, self.num_channels, *self.stack.shape[2:])
         self.stack = self.stack.roll(shifts=-self.num_channels, dims=1)
         self.stack[:, -self.num_channels:] = obs
-        return self.model(self.stack)[0]
+        # plain fp32 convolutions (cuDNN would otherwise take TF32 tensor-core paths on this GPU: the networks are tiny,
+        # and a greedy argmax over near-tied logits should not depend on the conv algorithm's precision)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return self.model(self.stack)[0]
 
     def __call__(self, obs):
         """-> int32 [num_envs] device tensor of greedy actions (Categorical(logits).probs.argmax, policy_serving.py:50-56)."""

@@ -24,8 +24,12 @@ class LazyCarInfos(object):
     """infos[i] -> {"num_steps": ..} (single) or {player: {"num_steps": .., "reward": ..}} (Double),
     plus "terminal_observation" / "TimeLimit.truncated" for finished envs."""
 
-    def __init__(self, env, num_steps, rewards, done, truncated, term):
-        self._env, self.num_steps, self.rewards, self.done, self.truncated = env, num_steps, rewards, done, truncated
+    def __init__(self, env, num_steps, rewards, done, trunc_bits, term):
+        self._env, self.num_steps, self.rewards, self.done = env, num_steps, rewards, done
+        # gym TimeLimit: the key exists only on the step the limit fired; its value is `not done` (always False with two
+        # cars, whose `done` is a dict -- a quirk of the reference stack this reproduces)
+        self.time_limit_hit = (trunc_bits & 2) != 0
+        self.truncated = (trunc_bits & 1) != 0
         self._term, self._host = term, None
 
     def __len__(self):
@@ -37,8 +41,8 @@ class LazyCarInfos(object):
     def __getitem__(self, i):
         if self._host is None:
             self._host = (self.num_steps.cpu().numpy(), self.rewards.cpu().numpy(), self.done.cpu().numpy(),
-                          self.truncated.cpu().numpy())
-        steps, rew, done, trunc = self._host
+                          self.truncated.cpu().numpy(), self.time_limit_hit.cpu().numpy())
+        steps, rew, done, trunc, hit = self._host
         if self._env.players == 1:
             info = {"num_steps": int(steps[i])}
         else:
@@ -46,8 +50,8 @@ class LazyCarInfos(object):
         if done[i]:
             t = self._term[i]
             info["terminal_observation"] = t.cpu().numpy() if self._env.return_numpy else t
-            if self._env.max_episode_steps:
-                info["TimeLimit.truncated"] = bool(trunc[i])
+        if hit[i]:
+            info["TimeLimit.truncated"] = bool(trunc[i])
         return info
 
     def __iter__(self):
@@ -110,7 +114,7 @@ class CudaCarVecEnv(VecEnv):
                 term=torch.zeros((n, ch, 96, 96), dtype=torch.uint8, device=dev),
                 rew=torch.zeros((n, self.players), dtype=torch.float32, device=dev),
                 done=torch.zeros((n,), dtype=torch.bool, device=dev),
-                trunc=torch.zeros((n,), dtype=torch.bool, device=dev),
+                trunc=torch.zeros((n,), dtype=torch.uint8, device=dev),
                 steps=torch.zeros((n,), dtype=torch.int32, device=dev)))
         self._cur = 0
         self._actions = torch.zeros((n, self.players, 2), dtype=torch.float32, device=dev)

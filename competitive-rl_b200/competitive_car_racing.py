@@ -81,9 +81,7 @@ class _Car0Infos(object):
         out.pop("reward", None)     # FlattenMultiAgentObservation's addition, not on this path
         if "terminal_observation" in full:
             out["terminal_observation"] = full["terminal_observation"][:self._infos._env.c]
-        if "TimeLimit.truncated" in full:
-            out["TimeLimit.truncated"] = full["TimeLimit.truncated"]
-        return out
+        return out          # "TimeLimit.truncated" sits beside the player keys in the reference's dict: i[0] does not carry it
 
     def __iter__(self):
         for i in range(len(self)):

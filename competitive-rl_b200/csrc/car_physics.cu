@@ -1045,11 +1045,17 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
         p.step_count[e] = steps;
         p.inv_dt0[e] = 1.0f / (1.0f / CR_FPS);
         int el = p.elapsed[e] + 1;
-        bool trunc = false;
-        if (p.max_episode_steps > 0 && el >= p.max_episode_steps) { trunc = !any_done; any_done = true; }
+        // gym TimeLimit.step: at the limit `info["TimeLimit.truncated"] = not done; done = True`.  With one car `done` is a
+        // bool; with two it is CarRacing's {player: bool} dict, which is truthy, so the reference's flag is always False
+        // there.  bit 1 = the limit was hit on this step (the key exists), bit 0 = its value.
+        int trunc = 0;
+        if (p.max_episode_steps > 0 && el >= p.max_episode_steps) {
+            trunc = 2 | ((p.players == 1 && !any_done) ? 1 : 0);
+            any_done = true;
+        }
         p.elapsed[e] = el;
         done_out[e] = any_done ? 1 : 0;
-        truncated_out[e] = trunc ? 1 : 0;
+        truncated_out[e] = (uint8_t)trunc;
         num_steps_out[e] = steps;
         p.env_done[e] = any_done ? 1 : 0;
         if (any_done) {

@@ -188,7 +188,7 @@ struct Car {
         check_rc(crl_car_step(handle(), dev_ptr<float>(actions, at::kFloat, dev(), 2 * cars(), "actions"),
                               dev_ptr<uint8_t>(obs, at::kByte, dev(), obs_numel, "obs"), dev_ptr<float>(rew, at::kFloat, dev(), cars(), "rew"),
                               dev_ptr<uint8_t>(done, at::kBool, dev(), n(), "done"), dev_ptr<int32_t>(num_steps, at::kInt, dev(), n(), "num_steps"),
-                              dev_ptr<uint8_t>(truncated, at::kBool, dev(), n(), "truncated"),
+                              dev_ptr<uint8_t>(truncated, at::kByte, dev(), n(), "truncated"),
                               opt_dev_ptr<uint8_t>(term, at::kByte, dev(), term_numel, "terminal observation"), stream_of(dev())));
     }
     int64_t ring_phase() {

@@ -226,7 +226,9 @@ int crl_car_seed(crl_car* h, uint64_t seed, void* stream);
  *   rew_dev         float32 [num_envs][num_players]     per-car step reward (the Double wrapper returns [:, 0])
  *   done_dev        uint8   [num_envs]                  any car done, or TimeLimit
  *   num_steps_dev   int32   [num_envs]                  info["num_steps"]
- *   truncated_dev   uint8   [num_envs]                  info["TimeLimit.truncated"]
+ *   truncated_dev   uint8   [num_envs]                  bit 1: the gym TimeLimit fired on this step (the key
+ *                                                       info["TimeLimit.truncated"] exists), bit 0: its value -- `not done`
+ *                                                       with one car; always False with two, whose `done` is a (truthy) dict
  *   term_obs_dev    may be NULL; else same layout as obs: rows of finished envs receive
  *                   info["terminal_observation"]. */
 int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* rew_dev, uint8_t* done_dev,

@@ -9,7 +9,7 @@ Restated third-party behaviour (not pinned by /root/reference):
     specifies the uint8 observation path, so this shim defaults to uint8 when
     `high == 255`; set GYM_SHIM_BOX_FLOAT32=1 to get gym's float32.
 """
-from . import envs, error, logger, spaces, utils  # noqa: F401
+from . import envs, error, logger, spaces, utils, wrappers  # noqa: F401
 from .core import Env, ObservationWrapper, RewardWrapper, Wrapper  # noqa: F401
 from .envs.registration import make, register, spec  # noqa: F401
 

@@ -34,4 +34,7 @@ def make(id, **kwargs):  # noqa: A002
         cls = getattr(importlib.import_module(mod), name)
     env = cls(**kw)
     env.spec = s
+    if s.max_episode_steps is not None:      # gym.envs.registration.EnvSpec.make wraps the env in TimeLimit
+        from ..wrappers import TimeLimit
+        env = TimeLimit(env, max_episode_steps=s.max_episode_steps)
     return env

@@ -129,7 +129,7 @@ def test_autoreset_timelimit_and_stack_layout():
             assert torch.equal(r[:, 0], info.rewards[:, 0])
         prev = o.clone()
     assert bool(d.all())                                                         # TimeLimit(30)
-    assert bool(info.truncated.bool().all())
+    assert bool(info.time_limit_hit.all()) and not bool(info.truncated.any())   # two cars: `not done` of a dict (see car_vec_env)
     assert int(info.num_steps[0]) == 30
     term = info.terminal_observation()
     assert torch.equal(o[:, 0], o[:, 3])                                         # already the reset observation
@@ -137,7 +137,7 @@ def test_autoreset_timelimit_and_stack_layout():
     assert any(len(envs.get_track(e)) != len(tracks0[e]) or not np.array_equal(envs.get_track(e), tracks0[e])
                for e in range(N))                                                # a new random track per reset
     i0 = info[0]
-    assert i0[0]["num_steps"] == 30 and "terminal_observation" in i0 and i0["TimeLimit.truncated"] is True
+    assert i0[0]["num_steps"] == 30 and "terminal_observation" in i0 and i0["TimeLimit.truncated"] is False
     envs.check()
     envs.close()
 
