@@ -322,6 +322,25 @@ int crl_pong_render_obs_generic(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_de
     return CRL_OK;
 }
 
+int crl_pong_render_obs_f32(crl_pong* h, int32_t terminal, const uint8_t* only_done_dev, float* obs0_dev, float* obs1_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (int r = need_ready(h, true)) return r;
+    if (h->dev.ring) return fail(CRL_E_STATE, "float32 observations are plain stacks: create the handle with stack_mode 0");
+    if (!obs0_dev || (h->dev.n_agents == 2 && !obs1_dev)) return fail(CRL_E_INVALID, "null observation buffer");
+    LAUNCH(launch_pong_raster_f32(h->dev, terminal ? h->dev.term_hist : h->dev.hist, only_done_dev, obs0_dev, obs1_dev, (cudaStream_t)stream));
+    return CRL_OK;
+}
+
+int crl_pong_reset_state(crl_pong* h, void* stream) {
+    CHECK_HANDLE(h);
+    if (int r = need_ready(h, false)) return r;
+    LAUNCH(launch_pong_reset(h->dev, (cudaStream_t)stream));
+    h->was_reset = true;
+    h->dev.ring_phase = 0;
+    h->dev.fill_all = 1;
+    return CRL_OK;
+}
+
 int crl_pong_reset(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_dev, void* stream) {
     CHECK_HANDLE(h);
     if (int r = need_ready(h, false)) return r;

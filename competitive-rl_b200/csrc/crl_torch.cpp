@@ -94,6 +94,25 @@ struct Pong {
                                dev_ptr<int32_t>(num_steps, at::kInt, dev(), n(), "num_steps"),
                                dev_ptr<float>(real_reward, at::kFloat, dev(), 2 * n(), "real_reward"), stream_of(dev())));
     }
+    // float32 observation mode (stock gym): game core, then the float rasteriser
+    void reset_f32(const at::Tensor& obs0, const c10::optional<at::Tensor>& obs1) {
+        check_rc(crl_pong_reset_state(handle(), stream_of(dev())));
+        render_f32(false, c10::nullopt, obs0, obs1);
+    }
+    void step_f32(const at::Tensor& actions, const at::Tensor& obs0, const c10::optional<at::Tensor>& obs1, const at::Tensor& rew,
+                  const at::Tensor& done, const at::Tensor& num_steps, const at::Tensor& real_reward) {
+        check_rc(crl_pong_step_state(handle(), dev_ptr<int32_t>(actions, at::kInt, dev(), n() * cfg.n_agents, "actions"),
+                                     dev_ptr<float>(rew, at::kFloat, dev(), 2 * n(), "rew"), dev_ptr<uint8_t>(done, at::kBool, dev(), n(), "done"),
+                                     dev_ptr<int32_t>(num_steps, at::kInt, dev(), n(), "num_steps"),
+                                     dev_ptr<float>(real_reward, at::kFloat, dev(), 2 * n(), "real_reward"), stream_of(dev())));
+        render_f32(false, c10::nullopt, obs0, obs1);
+    }
+    void render_f32(bool terminal, const c10::optional<at::Tensor>& only_done, const at::Tensor& obs0, const c10::optional<at::Tensor>& obs1) {
+        if (cfg.n_agents == 2) TORCH_CHECK(obs1.has_value(), "obs1: cPongDouble needs both agents' buffers");
+        check_rc(crl_pong_render_obs_f32(handle(), terminal ? 1 : 0, opt_dev_ptr<uint8_t>(only_done, at::kBool, dev(), n(), "done"),
+                                         dev_ptr<float>(obs0, at::kFloat, dev(), obs_numel, "obs0"),
+                                         opt_dev_ptr<float>(obs1, at::kFloat, dev(), obs_numel, "obs1"), stream_of(dev())));
+    }
     void render_obs_generic(const at::Tensor& obs0, const c10::optional<at::Tensor>& obs1) {
         check_rc(crl_pong_render_obs_generic(handle(), dev_ptr<uint8_t>(obs0, at::kByte, dev(), obs_numel, "obs0"), obs1_ptr(obs1, "obs1"),
                                              stream_of(dev())));
@@ -239,6 +258,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         .def("reset", &Pong::reset)
         .def("step", &Pong::step)
         .def("render_obs_generic", &Pong::render_obs_generic)
+        .def("reset_f32", &Pong::reset_f32)
+        .def("step_f32", &Pong::step_f32)
+        .def("render_f32", &Pong::render_f32)
         .def("terminal_obs", &Pong::terminal_obs)
         .def("ring_phase", &Pong::ring_phase)
         .def("get_state", &Pong::get_state)

@@ -41,6 +41,7 @@ constexpr int MAX_STACK = 8;
 // What one rendered game frame depends on: 8 bytes.
 //   x: ball_x | ball_y<<8 | left_y<<16 | right_y<<24
 //   y: score_left | score_right<<8 | valid<<16   (valid=0: the np.zeros MaxAndSkip buffer)
+//      | raw<<17 (the frame reset() returned: it bypasses MaxAndSkipEnv's buffers; only the float32 mode cares)
 typedef uint2 RenderState;
 
 // One preprocessed observation frame = max of two rendered frames (MaxAndSkipEnv
@@ -152,6 +153,8 @@ cudaError_t launch_pong_raster(const PongDev& p, const FrameSpec* hist, uint8_t*
 // ring = 1: obs* are 2c-slot rings, rewritten completely (terminal observations are always plain stacks: ring = 0)
 cudaError_t launch_pong_raster_generic(const PongDev& p, const FrameSpec* hist, const uint8_t* only_done, int ring,
                                        uint8_t* obs0, uint8_t* obs1, cudaStream_t s);
+cudaError_t launch_pong_raster_f32(const PongDev& p, const FrameSpec* hist, const uint8_t* only_done, float* obs0, float* obs1,
+                                   cudaStream_t s);
 cudaError_t pong_raster_init(int grid_out[3]);
 bool pong_quad_ok(const AreaTabs& a);
 size_t pong_fast_tabs_bytes(int dim);

@@ -88,6 +88,35 @@ __global__ void pong_raster_generic_kernel(PongDev p, const FrameSpec* __restric
 }
 
 // ---------------------------------------------------------------------------------
+// float32 observations, as a stock gym install produces them: Box without a dtype is float32
+// (pong/base_pong_env.py:22-24), so MaxAndSkipEnv pools float32 frames (utils/atari_wrappers.py:106-115) and WarpFrame's
+// cv2 calls take their float paths: the observation is the UNROUNDED fp32 area sum.  The exception are frames that come
+// from reset(): MaxAndSkipEnv.reset passes the raw uint8 array through un-pooled (:162-163), so those go through the
+// uint8 path and enter the float32 stack as rounded integers (frame spec bit 17).  One thread per destination pixel.
+__global__ void pong_raster_f32_kernel(PongDev p, const FrameSpec* __restrict__ hist, const uint8_t* __restrict__ only_done,
+                                       float* obs0, float* obs1) {
+    const int dd = p.dim * p.dim;
+    const long long total = (long long)p.n * p.n_agents * p.c * dd;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int pix = (int)(i % dd);
+        long long f = i / dd;
+        const int slot = (int)(f % p.c);
+        f /= p.c;
+        const int env = (int)(f % p.n), agent = (int)(f / p.n);
+        if (only_done != nullptr && !only_done[env]) continue;
+        const FrameSpec spec = hist[(size_t)slot * p.n + env];
+        const FrameCtx c = make_ctx(spec, agent);
+        float v = 0.f;
+        if (c.any_valid) {
+            if ((spec.y >> 17) & 1u) v = (float)eval_pixel(p.tabs, c, p.atlas, pix / p.dim, pix % p.dim);
+            else v = eval_pixel_sum<true>(p.tabs, c, p.atlas, pix / p.dim, pix % p.dim);
+        }
+        ((agent ? obs1 : obs0) + ((size_t)env * p.c + slot) * dd)[pix] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // Raw 210x160x3 export of one env's CURRENT game state (VecEnv.render / get_images,
 // utils/base_vec_env.py:189-216).  Not on the step path.
 __global__ void pong_raw_frame_kernel(PongDev p, int env, uint8_t* rgb0, uint8_t* rgb1) {
@@ -129,6 +158,12 @@ cudaError_t launch_pong_build_tables(const PongDev& p, uint8_t* text_tab, uint8_
 cudaError_t launch_pong_raster_generic(const PongDev& p, const FrameSpec* hist, const uint8_t* only_done, int ring,
                                        uint8_t* obs0, uint8_t* obs1, cudaStream_t s) {
     pong_raster_generic_kernel<<<148 * 16, 256, 0, s>>>(p, hist, only_done, ring, obs0, obs1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pong_raster_f32(const PongDev& p, const FrameSpec* hist, const uint8_t* only_done, float* obs0, float* obs1,
+                                   cudaStream_t s) {
+    pong_raster_f32_kernel<<<148 * 16, 256, 0, s>>>(p, hist, only_done, obs0, obs1);
     return cudaGetLastError();
 }
 

@@ -65,10 +65,22 @@ __device__ __forceinline__ int text_gray(const FrameCtx& c, const uint8_t* __res
     return (r * 9798 + g * 19235 + b * 3735 + 16384) >> 15;   // cv2 RGB2GRAY, 15-bit fixed point
 }
 
-// Exact value of destination pixel (dy, dx): cv2's INTER_AREA float path evaluated on
-// the analytically-described source frame.
-__device__ __forceinline__ uint8_t eval_pixel(const AreaTabs* __restrict__ T, const FrameCtx& c,
-                                              const uint8_t* __restrict__ atlas, int dy, int dx) {
+// the same pixel as cv2.cvtColor(float32 RGB -> GRAY) computes it (stock gym: float32 observation buffers):
+// fma(B, 0.114f, fma(R, 0.299f, G * 0.587f)) in fp32 -- pinned against cv2 4.13 on random and Pong-like images
+// (tests/test_oracle_cv2.py); pure white gives exactly 255.0f, so only the antialiased text pixels differ from text_gray
+__device__ __forceinline__ float text_gray_f32(const FrameCtx& c, const uint8_t* __restrict__ atlas, int sy, int sx) {
+    const int ax = (c.mirror && sy >= MIRROR_ROW) ? (SCREEN_W - 1 - sx) : sx;
+    const uint8_t* pa = atlas + ((size_t)(c.pairA * ATLAS_ROWS + sy) * SCREEN_W + ax) * 3;
+    const uint8_t* pb = atlas + ((size_t)(c.pairB * ATLAS_ROWS + sy) * SCREEN_W + ax) * 3;
+    const float r = (float)max((int)pa[0], (int)pb[0]), g = (float)max((int)pa[1], (int)pb[1]), b = (float)max((int)pa[2], (int)pb[2]);
+    return __fmaf_rn(b, 0.114f, __fmaf_rn(r, 0.299f, __fmul_rn(g, 0.587f)));
+}
+
+// Value of destination pixel (dy, dx) before rounding: cv2's INTER_AREA float sequence evaluated on the
+// analytically-described source frame.  FLOAT_GRAY: the gray conversion of the float32 path (see text_gray_f32).
+template <bool FLOAT_GRAY>
+__device__ __forceinline__ float eval_pixel_sum(const AreaTabs* __restrict__ T, const FrameCtx& c,
+                                                const uint8_t* __restrict__ atlas, int dy, int dx) {
     const int sx0 = T->x_src0[dx], nx = T->x_n[dx];
     const int sy0 = T->y_src0[dy], ny = T->y_n[dy];
     uint32_t hp[6], vp[6];
@@ -84,8 +96,10 @@ __device__ __forceinline__ uint8_t eval_pixel(const AreaTabs* __restrict__ T, co
         const int sy = sy0 + ty;
         float buf = 0.f;
         if (sy < ARENA_TOP) {
-            for (int tx = 0; tx < nx; ++tx)
-                buf = __fadd_rn(buf, __fmul_rn((float)text_gray(c, atlas, sy, sx0 + tx), T->x_a[dx][tx]));
+            for (int tx = 0; tx < nx; ++tx) {
+                const float gv = FLOAT_GRAY ? text_gray_f32(c, atlas, sy, sx0 + tx) : (float)text_gray(c, atlas, sy, sx0 + tx);
+                buf = __fadd_rn(buf, __fmul_rn(gv, T->x_a[dx][tx]));
+            }
         } else {
             uint32_t pat = 0u;
             if (sy >= ARENA_BOTTOM) {
@@ -101,7 +115,13 @@ __device__ __forceinline__ uint8_t eval_pixel(const AreaTabs* __restrict__ T, co
         const float term = __fmul_rn(T->y_b[dy][ty], buf);
         sum = (ty == 0) ? term : __fadd_rn(sum, term);
     }
-    const int v = __float2int_rn(sum);   // cvRound: round half to even
+    return sum;
+}
+
+// uint8 observation: saturate_cast<uchar>(cvRound(sum)), round half to even
+__device__ __forceinline__ uint8_t eval_pixel(const AreaTabs* __restrict__ T, const FrameCtx& c,
+                                              const uint8_t* __restrict__ atlas, int dy, int dx) {
+    const int v = __float2int_rn(eval_pixel_sum<false>(T, c, atlas, dy, dx));
     return (uint8_t)min(max(v, 0), 255);
 }
 

@@ -197,7 +197,7 @@ __device__ __forceinline__ void env_reset(const PongDev& p, int e, Game& g) {
     reset_game(p, e, g);
     p.clip_steps[e] = 0;
     const RenderState rs = snapshot(g);
-    const FrameSpec spec = make_uint4(rs.x, rs.y, rs.x, rs.y);
+    const FrameSpec spec = make_uint4(rs.x, rs.y | (1u << 17), rs.x, rs.y | (1u << 17));   // bit 17: reset()'s un-pooled frame
     // FrameStackTensor.update (utils/utils.py:159-170): `obs *= mask` zeroes the history of a finished env before the
     // reset observation is appended; valid bit 0 = the all-zero frame
     const FrameSpec old = p.zero_on_done ? make_uint4(0u, 0u, 0u, 0u) : spec;

@@ -224,17 +224,26 @@ class CudaPongVecEnv(VecEnv):
     C -- same values, half the HBM traffic (28 224 B instead of 56 448 B per env-step at 84x84x4).  The
     view returned by step t is valid until step t + 1 only (its oldest slot is the next one overwritten).
 
+    obs_dtype="float32": the observations a STOCK gym install of the reference produces (gym's Box defaults to float32,
+    SURVEY.md F7): unrounded fp32 area sums, rounded integers only in frames that came from reset().  A plain
+    one-thread-per-pixel rasteriser, 4x the bytes: for parity with such an install, not for throughput.
+
     zero_on_done=True: FrameStackTensor's stacking (utils/utils.py:145-173) instead of FrameStack's: after a done the
     history is zeros and only the newest channel holds the reset observation.
     """
 
     def __init__(self, env_id="cPongDouble-v0", num_envs=1, resized_dim=42, frame_stack=None, seed=0,
                  asynchronous=False, device=None, max_num_rounds=21, atlas=None, serves=None, first_env=0,
-                 return_numpy=False, n_buffers=2, stack_mode="stack", zero_on_done=False, copy=False):
+                 return_numpy=False, n_buffers=2, stack_mode="stack", zero_on_done=False, copy=False, obs_dtype="uint8"):
         if env_id not in ("cPong-v0", "cPongDouble-v0"):
             raise ValueError("unsupported env id %r" % (env_id,))
         if stack_mode not in ("stack", "ring"):
             raise ValueError("stack_mode must be 'stack' or 'ring'")
+        if obs_dtype not in ("uint8", "float32"):
+            raise ValueError("obs_dtype must be 'uint8' or 'float32'")
+        self.f32 = obs_dtype == "float32"
+        if self.f32 and stack_mode == "ring":
+            raise ValueError("obs_dtype='float32' needs stack_mode='stack'")
         if not torch.cuda.is_available():
             raise RuntimeError("CudaPongVecEnv needs a CUDA device: this simulator has no CPU path")
         ext = _native.ext()
@@ -252,7 +261,7 @@ class CudaPongVecEnv(VecEnv):
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
         n = int(num_envs)
-        box = spaces.Box(0, 255, (self.c, self.dim, self.dim), dtype=np.uint8)
+        box = spaces.Box(0, 255, (self.c, self.dim, self.dim), dtype=np.float32 if self.f32 else np.uint8)
         if self.n_agents == 2:
             obs_space = spaces.Tuple([box, box])
             act_space = spaces.Tuple([spaces.Discrete(3), spaces.Discrete(3)])
@@ -281,7 +290,8 @@ class CudaPongVecEnv(VecEnv):
         self._sets = []
         for _ in range(max(1, int(n_buffers))):
             self._sets.append(dict(
-                obs=None if self.ring else [torch.empty(shape, dtype=torch.uint8, device=dev) for _ in range(self.n_agents)],
+                obs=None if self.ring else [torch.empty(shape, dtype=torch.float32 if self.f32 else torch.uint8, device=dev)
+                                            for _ in range(self.n_agents)],
                 rew=torch.zeros((n, 2), dtype=torch.float32, device=dev),
                 real=torch.zeros((n, 2), dtype=torch.float32, device=dev),
                 done=torch.zeros((n,), dtype=torch.bool, device=dev),
@@ -303,7 +313,7 @@ class CudaPongVecEnv(VecEnv):
     @property
     def bytes_per_env_step(self):
         """observation bytes the rasteriser writes per env-step"""
-        return self.n_agents * (2 if self.ring else self.c) * self.dim * self.dim
+        return self.n_agents * (2 if self.ring else self.c) * self.dim * self.dim * (4 if self.f32 else 1)
 
     def _bind(self, k):
         b = self._sets[k]
@@ -348,7 +358,7 @@ class CudaPongVecEnv(VecEnv):
     def reset(self):
         self._bind((self._cur + 1) % len(self._sets))
         st = self._store
-        self._impl.reset(st[0], st[1] if self.n_agents == 2 else None)
+        (self._impl.reset_f32 if self.f32 else self._impl.reset)(st[0], st[1] if self.n_agents == 2 else None)
         if self.ring:
             self._ring_views()
         self._waiting = False
@@ -384,7 +394,8 @@ class CudaPongVecEnv(VecEnv):
         a = self._coerce_actions(actions)
         self._bind((self._cur + 1) % len(self._sets))
         st = self._store
-        self._impl.step(a, st[0], st[1] if self.n_agents == 2 else None, self._rew, self._done, self._steps, self._real)
+        (self._impl.step_f32 if self.f32 else self._impl.step)(a, st[0], st[1] if self.n_agents == 2 else None, self._rew,
+                                                                 self._done, self._steps, self._real)
         if self.ring:
             self._ring_views()
         self._waiting = True
@@ -413,8 +424,11 @@ class CudaPongVecEnv(VecEnv):
 
     def _terminal_obs(self, done):
         shape = (self.num_envs, self.c, self.dim, self.dim)
-        term = [torch.zeros(shape, dtype=torch.uint8, device=self.device) for _ in range(self.n_agents)]
-        self._impl.terminal_obs(done.to(torch.bool), term[0], term[1] if self.n_agents == 2 else None)
+        term = [torch.zeros(shape, dtype=torch.float32 if self.f32 else torch.uint8, device=self.device) for _ in range(self.n_agents)]
+        if self.f32:
+            self._impl.render_f32(True, done.to(torch.bool), term[0], term[1] if self.n_agents == 2 else None)
+        else:
+            self._impl.terminal_obs(done.to(torch.bool), term[0], term[1] if self.n_agents == 2 else None)
         return tuple(term) if self.n_agents == 2 else term[0]
 
     def seed(self, seed=None):

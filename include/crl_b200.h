@@ -110,6 +110,17 @@ int crl_pong_step(crl_pong* h, const int32_t* actions_dev, uint8_t* obs0_dev, ui
 int crl_pong_step_state(crl_pong* h, const int32_t* actions_dev, float* rew_dev, uint8_t* done_dev,
                         int32_t* num_steps_dev, float* real_reward_dev, void* stream);
 int crl_pong_render_obs(crl_pong* h, uint8_t* obs0_dev, uint8_t* obs1_dev, void* stream);
+/* float32 observations, as a STOCK gym install produces them: gym's Box without a dtype is float32
+ * (pong/base_pong_env.py:22-24), MaxAndSkipEnv pools float32 frames (utils/atari_wrappers.py:106-115) and cv2 takes its
+ * float paths, so an observation pixel is the UNROUNDED fp32 area sum -- except in frames that reset() returned, which
+ * bypass MaxAndSkipEnv un-pooled as uint8 (:162-163) and enter the stack as rounded integers.  Use instead of
+ * crl_pong_render_obs after crl_pong_step_state / crl_pong_reset_state: obs{0,1}_dev are float32
+ * [num_envs][C][dim][dim]; terminal != 0 renders info["terminal_observation"] of the envs flagged in only_done_dev
+ * (may be NULL = all) instead of the current observation.  One thread per pixel (not a tuned path), stack_mode 0 only. */
+int crl_pong_render_obs_f32(crl_pong* h, int32_t terminal, const uint8_t* only_done_dev, float* obs0_dev, float* obs1_dev,
+                            void* stream);
+/* VecEnv.reset() without rendering (for callers that render with crl_pong_render_obs_f32) */
+int crl_pong_reset_state(crl_pong* h, void* stream);
 /* stack_mode 1: slot k the last step wrote the newest frame to (and to k + C); the observation is slots k+1 .. k+C.
  * Advanced by crl_pong_step / crl_pong_step_state, 0 after crl_pong_reset.  No device work, no synchronisation. */
 int crl_pong_ring_phase(crl_pong* h);
