@@ -260,6 +260,13 @@ class CudaCarVecEnv(VecEnv):
         self._impl.set_state(s)
         torch.cuda.current_stream(self.device).synchronize()
 
+    def render_state(self):
+        """Debug / tests: render the CURRENT state (e.g. after set_state) as one more frame of the stack; returns the
+        newest frame of every player, uint8 (N, players, 96, 96)."""
+        b = self._sets[self._cur]
+        self._impl.render_state(b["obs"])
+        return self._obs_of(b).reshape(self.num_envs, self.players, self.c, 96, 96)[:, :, -1]
+
     def get_track(self, env):
         return self._impl.get_track(int(env)).numpy()
 

@@ -514,6 +514,15 @@ int crl_car_set_state(crl_car* h, const double* state_dev, void* stream) {
     return CRL_OK;
 }
 
+int crl_car_render_state(crl_car* h, uint8_t* obs_dev, void* stream) {
+    CHECK_HANDLE(h);
+    if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before rendering");
+    if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
+    if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
+    LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, nullptr, (cudaStream_t)stream), 3);
+    return CRL_OK;
+}
+
 int crl_car_ring_phase(crl_car* h) {
     if (!h) return crl_set_error(CRL_E_INVALID, "null handle");
     if (!h->dev.ring_mode) return crl_set_error(CRL_E_STATE, "the handle was not created with stack_mode ring");

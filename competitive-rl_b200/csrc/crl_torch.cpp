@@ -221,6 +221,9 @@ struct Car {
     void set_state(const at::Tensor& state) {
         check_rc(crl_car_set_state(handle(), dev_ptr<double>(state, at::kDouble, dev(), cars() * CRL_CAR_STATE_DOUBLES, "state"), stream_of(dev())));
     }
+    void render_state(const at::Tensor& obs) {
+        check_rc(crl_car_render_state(handle(), dev_ptr<uint8_t>(obs, at::kByte, dev(), obs_numel, "obs"), stream_of(dev())));
+    }
     at::Tensor get_track(int64_t env) {
         int32_t cnt = 0;
         at::Tensor pts = at::zeros({512, 3}, at::kDouble);
@@ -282,6 +285,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         .def("ring_phase", &Car::ring_phase)
         .def("get_state", &Car::get_state)
         .def("set_state", &Car::set_state)
+        .def("render_state", &Car::render_state)
         .def("get_track", &Car::get_track)
         .def("stats", &Car::stats)
         .def("contacts", &Car::contacts)

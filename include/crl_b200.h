@@ -270,6 +270,9 @@ int crl_car_get_state(crl_car* h, double* state_dev, void* stream);
  * crl_car_get_state; used: hull pose and velocity, wheel joint angles, omega, gas, reward).  Wheels are placed on their
  * joint anchors moving rigidly with the hull; joint impulses, car-car contacts and wheel tile sets are cleared. */
 int crl_car_set_state(crl_car* h, const double* state_dev, void* stream);
+/* Debug / tests: render every player's view of the CURRENT state as one more frame of the stack (what a step's rendering
+ * does, without the game core and without the auto-reset passes), e.g. after crl_car_set_state. */
+int crl_car_render_state(crl_car* h, uint8_t* obs_dev, void* stream);
 /* stack_mode 1: slot k the last step wrote the new frames to (and to k + C).  0 after crl_car_reset. */
 int crl_car_ring_phase(crl_car* h);
 /* number of tiles of env `env`'s current track, and (if non-NULL) its track points float64 [n][3] beta, x, y */

@@ -1844,6 +1844,43 @@ void car_oracle_step(CarEnv* e, const double* actions, double* step_rewards, int
 }
 
 void car_oracle_set_lazy_render(CarEnv* e, int lazy) { e->lazy_render = lazy; }
+
+/* Debug / tests (mirror of crl_car_set_state, same fp32 operations in the same order): put every car into the state
+ * state[car][24] laid out as car_oracle_get_state writes it.  Used: hull x, y, angle, vx, vy, w; per wheel joint angle,
+ * omega, gas; reward.  The wheels are placed on their joint anchors and move rigidly with the hull; joint impulses,
+ * car-car manifolds and the wheels' tile sets are cleared. */
+void car_oracle_set_state(CarEnv* e, const double* in) {
+    for (int k = 0; k < e->n_cars; ++k) {
+        Car* c = &e->car[k];
+        const double* s = in + 24 * k;
+        Body* h = &c->body[HULL_BODY];
+        const float a = (float)s[2];
+        const Rot q = rot(a);
+        const V2 org = v2((float)s[0], (float)s[1]);
+        const V2 com = vadd(org, rmul(q, h->local_center));
+        const V2 v0 = v2((float)s[3], (float)s[4]);
+        const float w0 = (float)s[5];
+        h->a = h->a0 = a; h->q = q; h->p = org; h->c = h->c0 = com; h->v = v0; h->w = w0; h->awake = 1; h->sleep_time = 0.f;
+        for (int w = 0; w < 4; ++w) {
+            Body* b = &c->body[BODY_OF_WHEEL[w]];
+            const V2 wp = vadd(org, rmul(q, v2((float)(WHEELPOS[w][0] * SIZE), (float)(WHEELPOS[w][1] * SIZE))));
+            const V2 d = vsub(wp, com);
+            b->a = b->a0 = a + (float)s[6 + 4 * w]; b->q = rot(b->a); b->p = wp; b->c = b->c0 = wp;
+            b->v = vadd(v0, v2(-w0 * d.y, w0 * d.x)); b->w = w0; b->awake = 1; b->sleep_time = 0.f;
+            c->omega[w] = s[7 + 4 * w];
+            if (w >= 2) c->gas[w] = s[8 + 4 * w];
+            c->n_touching[w] = 0;
+            memset(c->touching[w], 0, sizeof c->touching[w]);
+        }
+        for (int j = 0; j < 4; ++j) {
+            RevJoint* r = &c->joint[j];
+            r->impulse[0] = r->impulse[1] = r->impulse[2] = 0.f; r->motor_impulse = 0.f; r->limit_state = 0; r->motor_speed = 0.f;
+        }
+        for (int w = 0; w < 4; ++w) { c->brake[w] = 0.0; c->steer[w] = 0.0; }
+        c->reward = c->prev_reward = s[22];
+    }
+    memset(&e->contacts, 0, sizeof e->contacts);
+}
 /* touching car-car contacts / manifold points after the last step (diagnostics for the tests) */
 int car_oracle_env_contacts(const CarEnv* e, int* n_points) { return car_oracle_contact_count(&e->contacts, n_points); }
 const uint8_t* car_oracle_obs(CarEnv* e, int player) {

@@ -35,6 +35,7 @@ def lib():
         L.car_oracle_obs.argtypes = [vp, ctypes.c_int]
         L.car_oracle_get_state.argtypes = [vp, vp]
         L.car_oracle_set_lazy_render.argtypes = [vp, ctypes.c_int]
+        L.car_oracle_set_state.argtypes = [vp, vp]
         L.car_oracle_env_contacts.argtypes = [vp, vp]
         f = ctypes.c_float
         L.car_oracle_collide_fixtures.argtypes = [ctypes.c_int, f, f, f, ctypes.c_int, f, f, f, vp]
@@ -174,6 +175,11 @@ class CarOracleEnv(object):
         ns = ctypes.c_int(0)
         lib().car_oracle_step(self._h, _p(a), _p(rew), _p(done), ctypes.byref(ns))
         return self._obs(), rew, done.astype(bool), ns.value
+
+    def set_state(self, state):
+        """mirror of crl_car_set_state (tests: renderer cross-checks on arbitrary states)"""
+        s = np.ascontiguousarray(state, np.float64).reshape(self.n_cars, 24)
+        lib().car_oracle_set_state(self._h, _p(s))
 
     def get_state(self):
         s = np.zeros((self.n_cars, 24), np.float64)

@@ -466,3 +466,60 @@ def test_hud_bars_taller_than_the_bar_are_painted_over_the_scene():
     assert checked > 0
     envs.check()
     envs.close()
+
+
+@pytest.mark.parametrize("P", [1, 2])
+def test_renderer_on_arbitrary_states(P):
+    """crl_car_set_state + crl_car_render_state against the oracle's set_state + renderer: cars anywhere on (and off) the
+    track, any heading, speed (the camera turns into the velocity above 0.5), wheel angles, wheel speeds (HUD bars incl.
+    the tall-indicator case) and rewards (HUD text incl. negative values)."""
+    import car_oracle as C
+    from competitive_rl_b200 import _native
+    N = 24
+    rng = np.random.RandomState(77 + P)
+    draws = np.zeros((N, 2, 24))
+    tracks = []
+    for e in range(N):
+        tr, bd, d = C.make_track(rng)
+        draws[e, :] = d
+        tracks.append((tr, bd))
+    birth = np.tile(np.arange(P)[None, None], (N, 2, 1)).astype(np.int32)
+    envs = _make("cCarRacing-v0" if P == 1 else "cCarRacingDouble-v0", N, track_draws=draws, birth=birth)
+    glyphs = C.load_glyphs(_native.DEFAULT_CAR_GLYPHS)
+    orcs = [C.CarOracleEnv(P, 1, glyphs, render=False) for _ in range(N)]
+    envs.reset()
+    for e, o in enumerate(orcs):
+        o.reset(*tracks[e], list(range(P)))
+    mism = []
+    for it in range(3):
+        st = np.zeros((N, P, 24))
+        for e in range(N):
+            tr = tracks[e][0]
+            for k in range(P):
+                i = rng.randint(len(tr))
+                off = rng.uniform(-12, 12, 2) if rng.rand() < 0.8 else rng.uniform(-60, 60, 2)     # mostly near the road
+                st[e, k, 0:2] = tr[i, 2:4] + off
+                st[e, k, 2] = rng.uniform(-7, 7)
+                st[e, k, 3:5] = rng.uniform(-40, 40, 2) if rng.rand() < 0.7 else rng.uniform(-0.3, 0.3, 2)
+                st[e, k, 5] = rng.uniform(-3, 3)
+                for w in range(4):
+                    st[e, k, 6 + 4 * w] = rng.uniform(-0.4, 0.4) if w < 2 else 0.0
+                    st[e, k, 7 + 4 * w] = rng.uniform(0, 400) if rng.rand() < 0.3 else rng.uniform(0, 120)
+                    st[e, k, 8 + 4 * w] = rng.uniform(0, 1)
+                st[e, k, 22] = rng.uniform(-120, 950)
+            if P == 2 and rng.rand() < 0.5:          # the other car in view
+                st[e, 1, 0:2] = st[e, 0, 0:2] + rng.uniform(-8, 8, 2)
+        envs.set_state(st)
+        fr = envs.render_state().cpu().numpy()
+        sg = envs.get_state().cpu().numpy()
+        for e in range(N):
+            orcs[e].set_state(st[e])
+            so = orcs[e].get_state()
+            assert np.abs(sg[e][:, :6] - so[:, :6]).max() <= 1e-4, (it, e)
+            fo = orcs[e].observe()
+            for k in range(P):
+                mism.append(float((fr[e, k] != fo[k]).mean()))
+    print("arbitrary states: pixel mismatch mean %.6f max %.6f over %d frames" % (np.mean(mism), np.max(mism), len(mism)))
+    assert np.mean(mism) <= 5e-3 and np.max(mism) <= 5e-2, (np.mean(mism), np.max(mism))
+    envs.check()
+    envs.close()
