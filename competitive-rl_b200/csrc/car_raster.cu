@@ -337,11 +337,9 @@ __device__ void paint_hud_indicators(const RasterSmem& S, const uint8_t* glyphs,
         char digits[24];
         int nd = 0;
         if (mag == 0) digits[nd++] = 0;
-        if (mag < 2.0e9) {                                    // every reward in practice: integer digits (exact, no fp64 divisions)
-            unsigned int mi = (unsigned int)mag;
+        {   // integer digits (exact, no fp64 divisions); a reward is bounded by 1000 + 0.1 per step, far below 2^32
+            unsigned int mi = (unsigned int)fmin(mag, 4.0e9);
             while (mi != 0u) { const unsigned int qi = mi / 10u; digits[nd++] = (char)(mi - qi * 10u); mi = qi; }
-        } else {
-            while (mag >= 1 && nd < 20) { const double qd = floor(mag / 10.0); digits[nd++] = (char)(mag - qd * 10.0); mag = qd; }
         }
         const int neg = (rv < 0 || (rv == 0 && signbit(rv))) ? 1 : 0;
         const int body = nd + neg;
