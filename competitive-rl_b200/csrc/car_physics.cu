@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(64) car_reset_kernel(CarDev p, int only_done) 
 // per-step pipeline, one thread per car
 
 struct Joint {
-    F2 rA, rB;
+    F2 rA;
     float k00, k01, k02, k11, k12, k22;   // symmetric K (ex.x, ey.x, ez.x, ey.y, ez.y, ez.z)
     float motor_mass;
     float ix, iy, iz, motor_impulse, motor_speed;
@@ -505,6 +505,18 @@ __device__ __forceinline__ float max_separation_n(const float* ax, const float* 
         best = fmaxf(best, mn);
     }
     return best;
+}
+
+// max_separation_n(...) >= thr, i.e. some face of A keeps every vertex of B at least thr away (same arithmetic per face)
+__device__ __forceinline__ bool separated_by_face(const float* ax, const float* ay, const float* nx, const float* ny, int na,
+                                                  const float* bx, const float* by, int nb, float thr) {
+    for (int i = 0; i < na; ++i) {
+        if (nx[i] > 1.0e38f) continue;
+        float mn = 3.4e38f;
+        for (int k = 0; k < nb; ++k) mn = fminf(mn, nx[i] * (bx[k] - ax[i]) + ny[i] * (by[k] - ay[i]));
+        if (!(mn < thr)) return true;
+    }
+    return false;
 }
 
 // Can any fixture pair of the two cars be within contact reach?  The cars as oriented boxes in their hull frames (hull
@@ -752,9 +764,10 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (!near_w[k]) continue;
-                        const float s1 = max_separation_n(wx[k], wy[k], wnx[k], wny[k], 4, tpx, tpy, tn);
-                        const float s2 = max_separation_n(tpx, tpy, tnx, tny, tn, wx[k], wy[k], 4);
-                        if (fmaxf(s1, s2) < 2.0f * B2_POLYGON_RADIUS) now[k][t >> 5] |= 1u << (t & 31);
+                        // max(s1, s2) < 2 r  <=>  no face of either polygon separates them by 2 r or more: stop at the first that does
+                        if (!separated_by_face(wx[k], wy[k], wnx[k], wny[k], 4, tpx, tpy, tn, 2.0f * B2_POLYGON_RADIUS) &&
+                            !separated_by_face(tpx, tpy, tnx, tny, tn, wx[k], wy[k], 4, 2.0f * B2_POLYGON_RADIUS))
+                            now[k][t >> 5] |= 1u << (t & 31);
                     }
                 }
                 // contact events wheel by wheel (FrictionDetector._contact), BeginContact in ascending block id
@@ -839,14 +852,16 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                 for (int kk = 3; kk >= 0; --kk) {
                     Joint& j = J[kk];
                     const int bi = kk + 1;
-                    const Rot qA = make_rot(a[0]), qB = make_rot(a[bi]);
+                    // The wheel's anchor is its body origin = its centre of mass (localAnchorB = (0, 0), car_dynamics.py:101-110), so
+                    // Box2D's rB = R(aB) * (0 - 0) is (+-0, +-0): every term it enters only adds a signed zero.  Those terms
+                    // (and the sincosf of the wheel angle they need) are left out; results differ at most in the sign of a zero.
+                    const Rot qA = make_rot(a[0]);
                     j.rA = rmul(qA, f2((float)(c_wheelpos[kk][0] * CR_SIZE), (float)(c_wheelpos[kk][1] * CR_SIZE)) - f2(hull_lcx, hull_lcy));
-                    j.rB = rmul(qB, f2(0.f, 0.f) - f2(0.f, 0.f));
-                    j.k00 = mA + mB + j.rA.y * j.rA.y * iA + j.rB.y * j.rB.y * iB;
-                    j.k01 = -j.rA.y * j.rA.x * iA - j.rB.y * j.rB.x * iB;
-                    j.k02 = -j.rA.y * iA - j.rB.y * iB;
-                    j.k11 = mA + mB + j.rA.x * j.rA.x * iA + j.rB.x * j.rB.x * iB;
-                    j.k12 = j.rA.x * iA + j.rB.x * iB;
+                    j.k00 = mA + mB + j.rA.y * j.rA.y * iA;
+                    j.k01 = -j.rA.y * j.rA.x * iA;
+                    j.k02 = -j.rA.y * iA;
+                    j.k11 = mA + mB + j.rA.x * j.rA.x * iA;
+                    j.k12 = j.rA.x * iA;
                     j.k22 = iA + iB;
                     j.motor_mass = iA + iB;
                     if (j.motor_mass > 0.0f) j.motor_mass = 1.0f / j.motor_mass;
@@ -867,7 +882,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                     v[0] = v[0] - mA * P;
                     w[0] -= iA * (cross(j.rA, P) + j.motor_impulse + j.iz);
                     v[bi] = v[bi] + mB * P;
-                    w[bi] += iB * (cross(j.rB, P) + j.motor_impulse + j.iz);
+                    w[bi] += iB * (j.motor_impulse + j.iz);
                 }
                 const float max_motor_impulse = h * (float)(180 * 900 * CR_SIZE * CR_SIZE);
 #pragma unroll 1
@@ -888,7 +903,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                             wB += iB * impulse;
                         }
                         if (j.limit_state != 0) {
-                            const F2 Cdot1 = ((vB + cross_sv(wB, j.rB)) - vA) - cross_sv(wA, j.rA);
+                            const F2 Cdot1 = (vB - vA) - cross_sv(wA, j.rA);
                             const float Cdot2 = wB - wA;
                             float i0, i1, i2;
                             solve33(j, Cdot1.x, Cdot1.y, Cdot2, i0, i1, i2);
@@ -907,15 +922,14 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                             vA = vA - mA * P;
                             wA -= iA * (cross(j.rA, P) + i2);
                             vB = vB + mB * P;
-                            wB += iB * (cross(j.rB, P) + i2);
+                            wB += iB * i2;
                         } else {
-                            const F2 Cdot = ((vB + cross_sv(wB, j.rB)) - vA) - cross_sv(wA, j.rA);
+                            const F2 Cdot = (vB - vA) - cross_sv(wA, j.rA);
                             const F2 imp = solve22(j.k00, j.k01, j.k01, j.k11, f2(-Cdot.x, -Cdot.y));
                             j.ix += imp.x; j.iy += imp.y;
                             vA = vA - mA * imp;
                             wA -= iA * cross(j.rA, imp);
                             vB = vB + mB * imp;
-                            wB += iB * cross(j.rB, imp);
                         }
                         v[0] = vA; w[0] = wA; v[bi] = vB; w[bi] = wB;
                     }
@@ -974,20 +988,18 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                             aA -= iA * limit_impulse;
                             aB += iB * limit_impulse;
                         }
-                        const Rot qA = make_rot(aA), qB = make_rot(aB);
+                        const Rot qA = make_rot(aA);
                         const F2 rA = rmul(qA, f2((float)(c_wheelpos[kk][0] * CR_SIZE), (float)(c_wheelpos[kk][1] * CR_SIZE)) - f2(hull_lcx, hull_lcy));
-                        const F2 rB = rmul(qB, f2(0.f, 0.f) - f2(0.f, 0.f));
-                        const F2 C = ((cB + rB) - cA) - rA;
+                        const F2 C = (cB - cA) - rA;                                   // rB = (+-0, +-0), see above
                         const float position_error = sqrtf(dot(C, C));
-                        const float k00 = mA + mB + iA * rA.y * rA.y + iB * rB.y * rB.y;
-                        const float k01 = -iA * rA.x * rA.y - iB * rB.x * rB.y;
-                        const float k11 = mA + mB + iA * rA.x * rA.x + iB * rB.x * rB.x;
+                        const float k00 = mA + mB + iA * rA.y * rA.y;
+                        const float k01 = -iA * rA.x * rA.y;
+                        const float k11 = mA + mB + iA * rA.x * rA.x;
                         F2 imp = solve22(k00, k01, k01, k11, C);
                         imp = f2(-imp.x, -imp.y);
                         cA = cA - mA * imp;
                         aA -= iA * cross(rA, imp);
                         cB = cB + mB * imp;
-                        aB += iB * cross(rB, imp);
                         c[0] = cA; a[0] = aA; c[bi] = cB; a[bi] = aB;
                         ok = (position_error <= B2_LINEAR_SLOP && angular_error <= B2_ANGULAR_SLOP) && ok;
                     }
