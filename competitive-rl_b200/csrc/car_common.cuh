@@ -25,10 +25,10 @@ constexpr int CAR_SAMPLE_STRIDE = 8;        // every 8th track point feeds the c
 constexpr int CAR_MAX_SAMPLES = CAR_MAX_TRACK / CAR_SAMPLE_STRIDE;
 constexpr int CAR_MAX_STACK = 8;
 constexpr int CAR_GLYPH_BYTES = 11 * 8 * 4 + 11;
-constexpr int CAR_MAX_CAND = 176;           // road tiles of one frame that can reach the 96x96 window
-constexpr int CAR_SPAN_TILE_ROWS = 32;      // cached scanline rows per road tile polygon ...
-constexpr int CAR_SPAN_KERB_ROWS = 16;      // ... and per kerb quad (larger polygons are scanned in the render kernel)
-constexpr int CAR_SPAN_ROWS = CAR_SPAN_TILE_ROWS + CAR_SPAN_KERB_ROWS;
+// the painted road map of a track, kept as a sparse raster (car_spans.cuh): 16 x 16 px blocks of the 2048 x 2048 px window
+// of the reference's 10 000 x 10 000 px surface that starts at road-map pixel CAR_MAP_ORIGIN on both axes
+constexpr int CAR_MAP_BLOCK = 16, CAR_MAP_GRID = 128, CAR_MAP_ORIGIN = 5000 - 1032;
+constexpr int CAR_MAP_MAX_BLOCKS = 768;     // blocks a track may paint (standard tracks: 260-450); 192 KB per track slot
 constexpr int CAR_MAX_CONTACTS = 8;         // touching car-car fixture pairs kept per env (of 48 possible)
 constexpr int CAR_RAW_RING = 1024;          // raw points of the curve follower kept while it walks (last lap + tail)
 
@@ -126,14 +126,13 @@ struct CarDev {
     int32_t* slow_list;       // [n]
     int32_t* slow_count;      // [1]
     uint8_t* deferred;        // [n] 1 = on the slow list this step
-    // ---- per slot: scanline span tables of the road polygons in road-map pixels (they depend on the track only, so they
-    //      are built once per track by the generator instead of once per frame): [2n][CAR_MAX_TRACK][CAR_SPAN_ROWS] ----
-    short4* tile_spans;
-    float2* tile_centres;     // [2n][CAR_MAX_TRACK] tile centres (= CarTile::cx, cy), contiguous for the per-frame cull
+    // ---- per slot: the painted road map (it depends on the track only, so it is painted once per track by the generator
+    //      instead of once per frame): block index [2n][CAR_MAP_GRID][CAR_MAP_GRID], block pool [2n][CAR_MAP_MAX_BLOCKS][256] ----
+    uint16_t* map_index;
+    uint8_t* map_blocks;
+    float2* tile_centres;     // [2n][CAR_MAX_TRACK] tile centres (= CarTile::cx, cy), contiguous for the step kernel's candidate search
     // ---- per frame (env * players + player): written by car_frame_setup_kernel, read by car_render_kernel ----
     FrameMap* frame_map;      // [n*players]
-    uint16_t* frame_cand;     // [n*players][CAR_MAX_CAND] road tiles that can reach the window
-    int32_t* frame_ncand;     // [n*players]
     // ---- observation ring: [n][players][c][CAR_PIX] ----
     uint8_t* ring;
     // ---- validation mode ----
@@ -146,8 +145,8 @@ struct CarDev {
     const double* fixed_tracks;  // [n_fixed][CAR_MAX_TRACK][3] beta, x, y or nullptr
     const int32_t* fixed_counts; // [n_fixed]
     int n_fixed;
-    int32_t* overrun;            // [0] device flag: an injection table ran out; [1] frames whose rasteriser dropped polygons;
-                                 // [2] frames rasterised on the exact slow path (span pool full)
+    int32_t* overrun;            // [0] device flag: an injection table ran out; [1] road-map pixels / blocks dropped while painting a track
+                                 // (outside the 2048 px window, block pool full); [2] frames with a car polygon scanned per pixel (> 16 rows)
                                  // [3] auto-resets that had to generate (or wait for) their track on the step's critical path
     // ---- constants ----
     const CarHullConst* consts;

@@ -352,7 +352,7 @@ __device__ int generate_track_warp(const CarDev& p, int e, int slot, bool for_pr
     }
     if (lane < 3) p.start_pose[3 * slot + lane] = pts[lane];
     __syncwarp();
-    build_tile_spans(p, slot, n, lane, 32);
+    paint_road_map(p, slot, n, lane);
     return n;
 }
 

@@ -1,4 +1,4 @@
-// car_spans.cuh -- pygame 1.9 draw_fillpoly scanline rule and the per-track span tables of the road polygons.
+// car_spans.cuh -- pygame 1.9 draw_fillpoly scanline rule and the per-track road map painted with it.
 // Shared by the track generator (car_physics.cu: tables built once per track) and the rasteriser (car_raster.cu).
 #pragma once
 #include "car_common.cuh"
@@ -43,26 +43,93 @@ __device__ __forceinline__ short4 scanline_spans(const short* vx, const short* v
     return r;
 }
 
-// Scanline span tables of every road polygon (tile, kerb) of the track in `slot`, in road-map pixels: they depend on the
-// track only, so the generator scans them once per track rather than the render kernel once per frame.  `nthreads`
-// threads, thread `tid` of them; one (tile, table row) per thread and pass.
-__device__ inline void build_tile_spans(const CarDev& p, int slot, int n_track, int tid, int nthreads) {
-    const CarTile* tiles = p.tiles + (size_t)slot * CAR_MAX_TRACK;
-    short4* out = p.tile_spans + (size_t)slot * CAR_MAX_TRACK * CAR_SPAN_ROWS;
-    for (int item = tid; item < n_track * CAR_SPAN_ROWS; item += nthreads) {
-        const int t = item / CAR_SPAN_ROWS, slot_r = item % CAR_SPAN_ROWS;
-        const bool kerb = slot_r >= CAR_SPAN_TILE_ROWS;
-        const int r = kerb ? slot_r - CAR_SPAN_TILE_ROWS : slot_r;
-        const CarTile* T = tiles + t;
-        if (kerb && !(T->flags & 2)) continue;
-        const short* vx = kerb ? T->kmx : T->mx;
-        const short* vy = kerb ? T->kmy : T->my;
-        const int n = kerb ? 4 : 5;
-        int miny = vy[0], maxy = vy[0];
-        for (int i = 1; i < n; ++i) { miny = min(miny, (int)vy[i]); maxy = max(maxy, (int)vy[i]); }
-        if (r > maxy - miny) continue;
-        out[(size_t)t * CAR_SPAN_ROWS + slot_r] = scanline_spans(vx, vy, n, miny + r, maxy);
+// ------------------------------------------------------------------------------------------------
+// The road map.  The reference paints every road tile and kerb once per reset into a 10 000 x 10 000 px surface
+// (render_road_for_observation_map, car_racing_multi_players.py:732-755) and crops it per frame.  The painted part of that
+// surface depends on the track only, so it is kept per track slot as a sparse raster: the 2048 x 2048 px window
+// [CAR_MAP_ORIGIN, CAR_MAP_ORIGIN + 2048)^2 around the map centre (+-580 track units; a track stays within +-240) is cut
+// into 16 x 16 px blocks, `index[by][bx]` = 0 (nothing painted there), 0xFFFF (block dropped: pool full, flagged) or
+// 1 + the block's position in the slot's pool of 256-byte blocks.  A byte is 0 (background: grass / checker, decided per
+// frame) or the gray value of the last polygon painted over that pixel (never 0: road 102/104/107, kerbs 255/76).
+// One warp paints a track: polygons strictly in the reference's paint order (tile n-1 .. 0, each followed by its kerb),
+// lanes = scanlines of the polygon (pygame 1.9 draw_fillpoly, above), so a later polygon overwrites an earlier one.
+
+__device__ inline void paint_polygon_warp(uint16_t* index, uint8_t* blocks, int& n_blocks, const short* vx, const short* vy, int n,
+                                          uint8_t gray, int lane, int32_t* dropped) {
+    int miny = vy[0], maxy = vy[0];
+    for (int i = 1; i < n; ++i) { miny = min(miny, (int)vy[i]); maxy = max(maxy, (int)vy[i]); }
+    constexpr int HI = CAR_MAP_ORIGIN + CAR_MAP_GRID * CAR_MAP_BLOCK;
+    for (int r0 = miny; r0 <= maxy; r0 += 32) {
+        const int V = r0 + lane;
+        const bool active = V <= maxy;
+        short4 sp = make_short4(1, 0, 1, 0);
+        if (active) sp = scanline_spans(vx, vy, n, V, maxy);
+        const int by = (V - CAR_MAP_ORIGIN) >> 4;
+        const bool row_ok = active && by >= 0 && by < CAR_MAP_GRID;
+        if (active && !row_ok && (sp.x <= sp.y || sp.z <= sp.w)) atomicAdd(dropped, 1);
+        // x ranges clipped to the window; pixels outside it are dropped (flagged)
+        int x0[2] = {sp.x, sp.z}, x1[2] = {sp.y, sp.w};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (!row_ok) { x0[k] = 1; x1[k] = 0; continue; }
+            if (x0[k] <= x1[k] && (x0[k] < CAR_MAP_ORIGIN || x1[k] >= HI)) {
+                atomicAdd(dropped, 1);
+                x0[k] = max(x0[k], CAR_MAP_ORIGIN); x1[k] = min(x1[k], HI - 1);
+            }
+        }
+        // ---- blocks this row needs that do not exist yet: allocated one at a time by the whole warp ----
+        for (;;) {
+            int need = -1;
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+                if (need < 0 && x0[k] <= x1[k])
+                    for (int bx = (x0[k] - CAR_MAP_ORIGIN) >> 4; bx <= ((x1[k] - CAR_MAP_ORIGIN) >> 4); ++bx)
+                        if (__ldcg(index + by * CAR_MAP_GRID + bx) == 0) { need = by * CAR_MAP_GRID + bx; break; }
+            const unsigned m = __ballot_sync(0xffffffffu, need >= 0);
+            if (m == 0u) break;
+            const int cell = __shfl_sync(0xffffffffu, need, __ffs(m) - 1);
+            if (n_blocks >= CAR_MAP_MAX_BLOCKS) {
+                if (lane == 0) { __stcg(index + cell, (uint16_t)0xFFFFu); atomicAdd(dropped, 1); }
+            } else {
+                reinterpret_cast<uint2*>(blocks + (size_t)n_blocks * 256)[lane] = make_uint2(0u, 0u);
+                if (lane == 0) __stcg(index + cell, (uint16_t)(n_blocks + 1));
+                n_blocks += 1;
+            }
+            __syncwarp();
+        }
+        // ---- paint ----
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (x0[k] > x1[k]) continue;
+            const int ry = (V - CAR_MAP_ORIGIN) & 15;
+            for (int bx = (x0[k] - CAR_MAP_ORIGIN) >> 4; bx <= ((x1[k] - CAR_MAP_ORIGIN) >> 4); ++bx) {
+                const unsigned idx = __ldcg(index + by * CAR_MAP_GRID + bx);
+                if (idx == 0xFFFFu) continue;
+                uint8_t* row = blocks + (size_t)(idx - 1u) * 256 + ry * 16;
+                const int xa = max(x0[k] - CAR_MAP_ORIGIN - bx * 16, 0), xb = min(x1[k] - CAR_MAP_ORIGIN - bx * 16, 15);
+                for (int x = xa; x <= xb; ++x) row[x] = gray;
+            }
+        }
+        __syncwarp();
     }
+}
+
+// Road map of the track in `slot` (n_track tiles), by one warp.
+__device__ inline void paint_road_map(const CarDev& p, int slot, int n_track, int lane) {
+    const CarTile* tiles = p.tiles + (size_t)slot * CAR_MAX_TRACK;
+    uint16_t* index = p.map_index + (size_t)slot * CAR_MAP_GRID * CAR_MAP_GRID;
+    uint8_t* blocks = p.map_blocks + (size_t)slot * CAR_MAP_MAX_BLOCKS * 256;
+    const uint8_t* G = p.consts->gray;
+    for (int i = lane; i < CAR_MAP_GRID * CAR_MAP_GRID / 8; i += 32) __stcg(reinterpret_cast<uint4*>(index) + i, make_uint4(0u, 0u, 0u, 0u));
+    __syncwarp();
+    int n_blocks = 0;
+    for (int t = n_track - 1; t >= 0; --t) {
+        const CarTile* T = tiles + t;
+        paint_polygon_warp(index, blocks, n_blocks, T->mx, T->my, 5, G[G_ROAD0 + t % 3], lane, p.overrun + 1);
+        const uint8_t flags = T->flags;
+        if (flags & 2) paint_polygon_warp(index, blocks, n_blocks, T->kmx, T->kmy, 4, (flags & 4) ? G[G_KERB_W] : G[G_KERB_R], lane, p.overrun + 1);
+    }
+    __threadfence();
 }
 
 }  // namespace crl

@@ -293,8 +293,8 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
         ALLOC(fmraw, nc * car_frame_map_bytes());
         d.frame_map = reinterpret_cast<FrameMap*>(fmraw);
     }
-    ALLOC(d.frame_cand, nc * CAR_MAX_CAND); ALLOC(d.frame_ncand, nc);
-    ALLOC(d.tile_spans, 2 * n * CAR_MAX_TRACK * CAR_SPAN_ROWS); ALLOC(d.tile_centres, 2 * n * CAR_MAX_TRACK);
+    ALLOC(d.map_index, 2 * n * CAR_MAP_GRID * CAR_MAP_GRID); ALLOC(d.map_blocks, 2 * n * CAR_MAP_MAX_BLOCKS * 256);
+    ALLOC(d.tile_centres, 2 * n * CAR_MAX_TRACK);
     ALLOC(h->actions_stage, nc * 2); ALLOC(h->rew_stage, nc); ALLOC(h->done_stage, n); ALLOC(h->steps_stage, n); ALLOC(h->trunc_stage, n);
     if (P == 2) { ALLOC(d.contacts, n * CAR_MAX_CONTACTS); ALLOC(d.n_contacts, n); ALLOC(d.slow_list, n); ALLOC(d.slow_count, 1); }
     ALLOC(d.deferred, n);
@@ -588,7 +588,7 @@ int crl_car_check(crl_car* h, void* stream) {
     CUDA_TRY(cudaMemcpyAsync(flags, h->dev.overrun, sizeof flags, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     const int32_t flag = flags[0];
-    if (flags[1] != 0) return crl_set_error(CRL_E_STATE, "rasteriser dropped polygons in %d frame(s) (more road tiles in view than its tables hold)", flags[1]);
+    if (flags[1] != 0) return crl_set_error(CRL_E_STATE, "road map: %d span(s) / block(s) of a track could not be painted (outside the 2048 px map window or block pool full)", flags[1]);
     if (flag == 1) return crl_set_error(CRL_E_SERVES, "injected track-draw / birth-place table exhausted");
     if (flag == 2) return crl_set_error(CRL_E_STATE, "track generation failed 64 times in a row");
     return CRL_OK;
