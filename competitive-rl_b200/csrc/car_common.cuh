@@ -130,6 +130,7 @@ struct CarDev {
     //      instead of once per frame): block index [2n][CAR_MAP_GRID][CAR_MAP_GRID], block pool [2n][CAR_MAP_MAX_BLOCKS][256] ----
     uint16_t* map_index;
     uint8_t* map_blocks;
+    const uint8_t* chk;       // [2][2048] 0xFF where map column (axis 0) / row (axis 1) CAR_MAP_ORIGIN + i lies in a checker square (:733-746)
     float2* tile_centres;     // [2n][CAR_MAX_TRACK] tile centres (= CarTile::cx, cy), contiguous for the step kernel's candidate search
     // ---- per frame (env * players + player): written by car_frame_setup_kernel, read by car_render_kernel ----
     FrameMap* frame_map;      // [n*players]

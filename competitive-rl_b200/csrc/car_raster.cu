@@ -36,10 +36,10 @@ namespace crl {
 constexpr int RASTER_THREADS = 256;
 constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 constexpr int CAR_POLYS = 8 * CAR_MAX_PLAYERS;   // 4 wheels + 4 hull fixtures per car
-constexpr int POLY_ROWS = 16;              // span rows kept per car polygon (a fixture is <= 5.2 px across at obs_scale: <= 7 rows)
-constexpr int CELL = 8, CELLS_X = CAR_W / CELL;
+constexpr int POLY_ROWS = 8;               // span rows kept per car polygon (a fixture is <= 5.2 px across at obs_scale: <= 7 rows)
 constexpr int HUD_TOP = 86;                // (int)(H - 4 * (H / 40.0)) = (int)86.4: first row of the black HUD bar
-constexpr int WALK_CELLS = CELLS_X * ((HUD_TOP + CELL - 1) / CELL);   // cells with rows above the HUD bar: 11 rows of 12
+// the pixels above the HUD bar as quads of 4 horizontally adjacent pixels, row-major: a warp walks 32 consecutive quads at a time
+constexpr int QUADS_X = CAR_W / 4, WALK_QUADS = QUADS_X * HUD_TOP, WALK_GROUPS = (WALK_QUADS + 31) / 32;
 constexpr int HUD_WARP = 5;                // the warp that paints the HUD
 // The 96 x 86 px above the HUD bar, rotated by any angle, cover at most floor(sqrt(95^2 + 85^2)) + 2 = 129 consecutive
 // road-map columns / rows, i.e. at most 9 blocks of 16 per axis whatever the alignment (15 + 129 = 144).
@@ -57,7 +57,7 @@ struct FrameMap {
     int rx, ry;            // top-left of the 192x192 crop in the road map
     int obx, oby;          // first block (of the slot's block grid, may be < 0) of the staged window
     int bx, by;            // blit position of the rotated surface on the screen
-    int nbx, nby;          // blocks per axis of the staged window (<= CROP_BLOCKS)
+    int nbx, nby_mul;      // blocks per axis of the staged window (<= CROP_BLOCKS): nbx, nby | mul << 8 with b / nbx = (b * mul) >> 10
     int isin, icos;
     int cx0, cy0;          // dx = cx0 + icos*x - isin*y ; dy = cy0 + isin*x + icos*y   (16.16)
     float camx, camy;      // camera_offset (b2Vec2)
@@ -90,8 +90,7 @@ struct RasterSmem {
     short4 spans[CAR_POLYS][POLY_ROWS];
     short pvx[CAR_POLYS][8], pvy[CAR_POLYS][8];    // vertices of the car polygons
     PolyMeta meta[CAR_POLYS];
-    uint32_t cell_mask[WALK_CELLS];                // car polygons whose bounding box touches the cell
-    uint8_t chk_x[2 * CAR_W], chk_y[2 * CAR_H];    // is road-map column rx + i / row ry + i inside a checker square
+    uint32_t group_mask[WALK_GROUPS];              // car polygons whose bounding box touches the group of 32 quads
     float car_body[CAR_MAX_PLAYERS][40];
     double hud_vals[8];
     int copy_next, hud_late, slow;                 // ring -> observation chunk counter; 1 = an indicator reaches above the bar; 1 = a polygon with > POLY_ROWS rows
@@ -113,62 +112,55 @@ __device__ void add_polygon(RasterSmem& S, const int* vx, const int* vy, int n, 
 #pragma unroll
         for (int i = 0; i < 8; ++i) { S.pvx[id][i] = (short)max(-32000, min(32000, vx[i])); S.pvy[id][i] = (short)max(-32000, min(32000, vy[i])); }
         const uint32_t bit = 1u << id;
-        for (int cy = Y0 / CELL; cy <= Y1 / CELL; ++cy)
-            for (int cx = X0 / CELL; cx <= X1 / CELL; ++cx) atomicOr(&S.cell_mask[cy * CELLS_X + cx], bit);
+        for (int y = Y0; y <= Y1; ++y)
+            for (int g = (y * QUADS_X + (X0 >> 2)) >> 5; g <= (y * QUADS_X + (X1 >> 2)) >> 5; ++g) atomicOr(&S.group_mask[g], bit);
     }
     S.meta[id] = m;
 }
 
-// Pixels of the frame above the HUD bar: a warp walks one 8x8 cell at a time, lane = (x, y) and (x, y + 4).  The pixel's
-// road-map byte from the staged window, 0 = background (grass / checker by road-map pixel); then the car polygons binned
-// to the cell, largest key (paint order) wins.  SLOW: a polygon with more rows than its table holds is scanned per pixel.
+// Pixels of the frame above the HUD bar: lane = one quad (x .. x + 3, y).  The road-map byte of each pixel from the staged
+// window (background included); then the car polygons binned to the group, largest key (paint order << 8 | gray) wins.
+// SLOW: a polygon with more rows than its table holds is scanned per pixel.
 template <bool SLOW>
-__device__ __forceinline__ void test_polygon(const RasterSmem& S, int id, int x, int ya, int yb, unsigned int& ka, unsigned int& kb) {
+__device__ __forceinline__ void test_polygon(const RasterSmem& S, int id, int x, int y, unsigned int (&k)[4]) {
     const PolyMeta m = S.meta[id];
     const unsigned int key = m.key;
-    const int ra = ya - m.miny, rb = yb - m.miny;
-    if ((unsigned)ra < (unsigned)m.rows && key > ka) {
-        const short4 sp = (!SLOW || ra < POLY_ROWS) ? S.spans[id][ra] : scanline_spans(S.pvx[id], S.pvy[id], m.n, ya, m.miny + m.rows - 1);
-        if ((x >= sp.x && x <= sp.y) || (x >= sp.z && x <= sp.w)) ka = key;
-    }
-    if ((unsigned)rb < (unsigned)m.rows && key > kb) {
-        const short4 sp = (!SLOW || rb < POLY_ROWS) ? S.spans[id][rb] : scanline_spans(S.pvx[id], S.pvy[id], m.n, yb, m.miny + m.rows - 1);
-        if ((x >= sp.x && x <= sp.y) || (x >= sp.z && x <= sp.w)) kb = key;
-    }
+    const int r = y - m.miny;
+    if ((unsigned)r >= (unsigned)m.rows) return;
+    const short4 sp = (!SLOW || r < POLY_ROWS) ? S.spans[id][r] : scanline_spans(S.pvx[id], S.pvy[id], m.n, y, m.miny + m.rows - 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (key > k[i] && ((x + i >= sp.x && x + i <= sp.y) || (x + i >= sp.z && x + i <= sp.w))) k[i] = key;
 }
 
 template <bool SLOW>
-__device__ __forceinline__ void walk_cells(RasterSmem& S, const FrameMap& fm, unsigned int g_grass, unsigned int g_check,
-                                           int warp, int lane) {
-    uint8_t* img = S.img;
-    const int lx = lane & 7, ly = lane >> 3;
-    // dx = cx0 + icos * x - isin * y, dy = cy0 + isin * x + icos * y with (x, y) = (X - bx, Y - by): affine in the lane and
-    // in the cell.  No bounds test: the 96x96 window is the centre of the rotated 192x192 crop, whose inscribed circle
-    // (radius 96) contains it (half diagonal 68), so every screen pixel samples inside the crop.
-    const int ldx = fm.cx0 + fm.icos * (lx - fm.bx) - fm.isin * (ly - fm.by);
-    const int ldy = fm.cy0 + fm.isin * (lx - fm.bx) + fm.icos * (ly - fm.by);
-    // road-map pixel (rx + u, ry + v) sits at [v + offy][u + offx] of the staged window
+__device__ __forceinline__ void walk_quads(RasterSmem& S, const FrameMap& fm, int warp, int lane) {
+    uint32_t* img32 = reinterpret_cast<uint32_t*>(S.img);
+    // road-map pixel (rx + u, ry + v) sits at [v + offy][u + offx] of the staged window.  No bounds test: the 96x96 window
+    // is the centre of the rotated 192x192 crop, whose inscribed circle (radius 96) contains it (half diagonal 68), so
+    // every screen pixel samples inside the crop, and the staged blocks cover everything the rows above the HUD bar sample.
     const uint8_t* crop = S.crop + (fm.ry - CAR_MAP_ORIGIN - CAR_MAP_BLOCK * fm.oby) * CROP_DIM + (fm.rx - CAR_MAP_ORIGIN - CAR_MAP_BLOCK * fm.obx);
-    // cells warp, warp + 8, ...: 12 cells per row of cells, so +8 cells = +64 px in x, wrapping into the next row
-    int cx = warp * CELL, cy = 0;
-    for (int cell = warp; cell < WALK_CELLS; cell += RASTER_WARPS, cx += RASTER_WARPS * CELL) {
-        if (cx >= CAR_W) { cx -= CAR_W; cy += CELL; }
-        const int X = cx + lx, Ya = cy + ly, Yb = Ya + 4;
-        uint8_t* pa = img + Ya * CAR_W + X;
-        const int dxa = ldx + fm.icos * cx - fm.isin * cy, dya = ldy + fm.isin * cx + fm.icos * cy;
-        const int dxb = dxa - 4 * fm.isin, dyb = dya + 4 * fm.icos;
-        const int ua = (dxa >> 16) & 255, va = (dya >> 16) & 255, ub = (dxb >> 16) & 255, vb = (dyb >> 16) & 255;   // 0..191 (see above)
-        unsigned int ka = crop[va * CROP_DIM + ua], kb = crop[vb * CROP_DIM + ub];
-        if (ka == 0u) ka = (S.chk_x[ua] & S.chk_y[va]) ? g_check : g_grass;
-        if (kb == 0u) kb = (S.chk_x[ub] & S.chk_y[vb]) ? g_check : g_grass;
-        unsigned int bits = S.cell_mask[cell];              // car fixtures: screen coordinates
+    const int bdx = fm.cx0 - fm.icos * fm.bx + fm.isin * fm.by, bdy = fm.cy0 - fm.isin * fm.bx - fm.icos * fm.by;
+    for (int g = warp; g < WALK_GROUPS; g += RASTER_WARPS) {
+        const int q = g * 32 + lane;
+        if (q >= WALK_QUADS) break;                           // only lanes of the last group
+        const int y = (q * 2731) >> 16, x = (q - y * QUADS_X) * 4;     // q / 24 for q < 4096
+        // dx = cx0 + icos * (x - bx) - isin * (y - by), dy = cy0 + isin * (x - bx) + icos * (y - by)   (16.16)
+        int dx = bdx + fm.icos * x - fm.isin * y, dy = bdy + fm.isin * x + fm.icos * y;
+        unsigned int k[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int u = (dx >> 16) & 255, v = (dy >> 16) & 255;      // 0..191 (see above)
+            k[i] = crop[v * CROP_DIM + u];
+            dx += fm.icos; dy += fm.isin;
+        }
+        unsigned int bits = S.group_mask[g];                  // car fixtures: screen coordinates
         while (bits) {
             const int id = __ffs(bits) - 1;
             bits &= bits - 1u;
-            test_polygon<SLOW>(S, id, X, Ya, Yb, ka, kb);
+            test_polygon<SLOW>(S, id, x, y, k);
         }
-        pa[0] = (uint8_t)(ka & 255u);                        // Ya <= 83
-        if (Yb < HUD_TOP) pa[4 * CAR_W] = (uint8_t)(kb & 255u);   // rows 86.. belong to the HUD bar (painted by the HUD warp)
+        img32[q] = (k[0] & 255u) | ((k[1] & 255u) << 8) | ((k[2] & 255u) << 16) | (k[3] << 24);
     }
 }
 
@@ -228,7 +220,8 @@ car_frame_setup_kernel(CarDev p, int only_done, int which) {
     }
     m.obx = (m.rx + u0 - CAR_MAP_ORIGIN) >> 4; m.oby = (m.ry + v0 - CAR_MAP_ORIGIN) >> 4;
     m.nbx = min(((m.rx + u1 - CAR_MAP_ORIGIN) >> 4) - m.obx + 1, CROP_BLOCKS);
-    m.nby = min(((m.ry + v1 - CAR_MAP_ORIGIN) >> 4) - m.oby + 1, CROP_BLOCKS);
+    const int nby = min(((m.ry + v1 - CAR_MAP_ORIGIN) >> 4) - m.oby + 1, CROP_BLOCKS);
+    m.nby_mul = nby | (((1024 + m.nbx - 1) / m.nbx) << 8);
     p.frame_map[frame] = m;
 }
 
@@ -277,7 +270,7 @@ __device__ void paint_hud_indicators(const RasterSmem& S, const uint8_t* glyphs,
     }
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS, 5)
+__global__ void __launch_bounds__(RASTER_THREADS, 6)
 car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs, uint8_t* __restrict__ term_obs) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
@@ -288,7 +281,6 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
     const CarHullConst* K = p.consts;
     const uint8_t* G = K->gray;
-    const int* checker = K->checker;
     const FrameMap fm = p.frame_map[frame];           // written by car_frame_setup_kernel
     const double obs_scale = car_obs_scale();
     const int slot = car_slot(p, e);
@@ -306,8 +298,7 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     uint8_t* tout = (term_obs != nullptr && !only_done && p.env_done[e]) ? term_obs + (size_t)frame * C * CAR_PIX : nullptr;
 
     if (tid < p.players * 40) (&S.car_body[0][0])[tid] = p.body[(size_t)e * p.players * 40 + tid];   // [player][40], contiguous on both sides
-    if (tid < (2 * CAR_W + 2 * CAR_H) / 4) reinterpret_cast<uint32_t*>(S.chk_x)[tid] = 0u;     // chk_x and chk_y are adjacent
-    if (tid < WALK_CELLS) S.cell_mask[tid] = 0u;
+    if (tid < WALK_GROUPS) S.group_mask[tid] = 0u;
     if (tid >= 232 && tid < 232 + CAR_POLYS - p.players * 8) S.meta[p.players * 8 + tid - 232].rows = 0;   // polygons of an absent second car
     if (tid == 255) { S.copy_next = 0; S.hud_late = 0; S.slow = 0; }
     if (tid >= 240 && tid < 248) {      // HUD inputs (render_indicators_for_pygame :645-670)
@@ -323,14 +314,6 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
         S.hud_vals[k] = v;
     }
     __syncthreads();
-    // ---- checker squares (:733-746) are axis-aligned in the road map: mark the crop columns / rows that lie in one
-    //      (20 squares per axis, each ~29 px wide; the tables were cleared above) ----
-    if (tid >= 192 && tid < 192 + 40) {
-        const int q = tid - 192, is_y = q >= 20;
-        const int lo = checker[2 * q], hi = checker[2 * q + 1], base = is_y ? fm.ry : fm.rx;
-        uint8_t* tab = is_y ? S.chk_y : S.chk_x;
-        for (int v = max(lo - base, 0); v <= min(hi - base, 2 * CAR_W - 1); ++v) tab[v] = 1;
-    }
     // ---- car polygons, one thread each (Car.draw_for_pygame): for k in cars: wheels, then hull fixtures; b2Vec2 fp32
     //      arithmetic: path = -scale * (tmp * ((trans * v) - offset)) + (W/2, H/2), truncated to int by pygame.  Painted
     //      over the road in that order: higher key wins. ----
@@ -364,21 +347,27 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
         const uint8_t g = (part < 4) ? G[G_WHEEL] : ((ck == pi) ? G[G_OWN] : G[G_OTHER]);
         add_polygon(S, vx, vy, n, ((unsigned)(q + 1) << 8) | g, q);
     }
-    // ---- the road map under the window: 16 threads per 16 x 16 block, one 16-byte row each; blocks that hold no paint
-    //      (or lie outside the slot's grid) are staged as zeros ----
+    // ---- the road map under the window: 16 threads per 16 x 16 block, one 16-byte row each; where nothing was painted
+    //      (no block, or outside the slot's grid) the row is the background: grass / checker squares ----
     {
         const uint16_t* index = p.map_index + (size_t)slot * CAR_MAP_GRID * CAR_MAP_GRID;
         const uint4* blocks = reinterpret_cast<const uint4*>(p.map_blocks + (size_t)slot * CAR_MAP_MAX_BLOCKS * 256);
-        const int nb = fm.nbx * fm.nby, sub = tid & 15;
-        const int mul = (1024 + fm.nbx - 1) / fm.nbx;               // b / nbx = (b * mul) >> 10 for b < 100, nbx <= 10
+        const int nb = fm.nbx * (fm.nby_mul & 255), sub = tid & 15, mul = fm.nby_mul >> 8;
+        const uint32_t grass4 = 0x01010101u * G[G_GRASS], check4 = 0x01010101u * G[G_CHECK];
 #pragma unroll 2
         for (int bq = tid >> 4; bq < nb; bq += RASTER_THREADS / 16) {
             const int j = (bq * mul) >> 10, i = bq - j * fm.nbx;
             const int gx = fm.obx + i, gy = fm.oby + j;
+            const bool inside = (unsigned)gx < (unsigned)CAR_MAP_GRID && (unsigned)gy < (unsigned)CAR_MAP_GRID;
             unsigned int idx = 0u;
-            if ((unsigned)gx < (unsigned)CAR_MAP_GRID && (unsigned)gy < (unsigned)CAR_MAP_GRID) idx = index[gy * CAR_MAP_GRID + gx];
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (inside) idx = index[gy * CAR_MAP_GRID + gx];
+            uint4 v;
             if (idx != 0u && idx != 0xFFFFu) v = blocks[(idx - 1u) * 16 + sub];
+            else if (inside) {
+                const int my = gy * 16 + sub;
+                v = make_uint4(road_bg_word(p.chk, gx, my, 0, grass4, check4), road_bg_word(p.chk, gx, my, 1, grass4, check4),
+                               road_bg_word(p.chk, gx, my, 2, grass4, check4), road_bg_word(p.chk, gx, my, 3, grass4, check4));
+            } else v = make_uint4(grass4, grass4, grass4, grass4);      // the checker squares end well inside the window
             *reinterpret_cast<uint4*>(S.crop + (j * 16 + sub) * CROP_DIM + i * 16) = v;
         }
     }
@@ -430,14 +419,16 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     if (tid == 0 && S.slow != 0) atomicAdd(p.overrun + 2, 1);     // frames with a car polygon taller than its span table (scanned per pixel)
     // ---- span tables of the car polygons: one (polygon, row) per thread ----
     {
-        const int id = tid >> 4, r = tid & 15;
-        const PolyMeta m = S.meta[id];
-        if (r < m.rows) S.spans[id][r] = scanline_spans(S.pvx[id], S.pvy[id], m.n, m.miny + r, m.miny + m.rows - 1);
+        const int id = tid >> 3, r = tid & 7;
+        if (id < CAR_POLYS) {
+            const PolyMeta m = S.meta[id];
+            if (r < m.rows) S.spans[id][r] = scanline_spans(S.pvx[id], S.pvy[id], m.n, m.miny + r, m.miny + m.rows - 1);
+        }
     }
     __syncthreads();
     // ---- pixels above the HUD bar ----
-    if (S.slow == 0) walk_cells<false>(S, fm, G[G_GRASS], G[G_CHECK], warp, lane);
-    else walk_cells<true>(S, fm, G[G_GRASS], G[G_CHECK], warp, lane);
+    if (S.slow == 0) walk_quads<false>(S, fm, warp, lane);
+    else walk_quads<true>(S, fm, warp, lane);
     __syncthreads();
     if (S.hud_late) {                                              // uniform over the CTA
         if (warp == HUD_WARP) paint_hud_indicators(S, p.glyphs, G, img, lane);

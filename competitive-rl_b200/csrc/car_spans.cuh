@@ -49,13 +49,24 @@ __device__ __forceinline__ short4 scanline_spans(const short* vx, const short* v
 // surface depends on the track only, so it is kept per track slot as a sparse raster: the 2048 x 2048 px window
 // [CAR_MAP_ORIGIN, CAR_MAP_ORIGIN + 2048)^2 around the map centre (+-580 track units; a track stays within +-240) is cut
 // into 16 x 16 px blocks, `index[by][bx]` = 0 (nothing painted there), 0xFFFF (block dropped: pool full, flagged) or
-// 1 + the block's position in the slot's pool of 256-byte blocks.  A byte is 0 (background: grass / checker, decided per
-// frame) or the gray value of the last polygon painted over that pixel (never 0: road 102/104/107, kerbs 255/76).
+// 1 + the block's position in the slot's pool of 256-byte blocks.  A byte is the final gray value of that map pixel: a block
+// starts out as the background (grass, or the lighter checker squares of :733-746, which are axis-aligned in the map and the
+// same for every track: CarDev::chk) and takes the gray of the last polygon painted over each pixel.
 // One warp paints a track: polygons strictly in the reference's paint order (tile n-1 .. 0, each followed by its kerb),
 // lanes = scanlines of the polygon (pygame 1.9 draw_fillpoly, above), so a later polygon overwrites an earlier one.
 
+
+// 16 background pixels of map row `my`, columns 16 * bx .. 16 * bx + 15 (both relative to CAR_MAP_ORIGIN, inside the window):
+// words [w0, w0 + nw) of the row.  chk = [2][2048] bytes, 0xFF where the column (axis 0) / row (axis 1) lies in a checker square.
+__device__ __forceinline__ uint32_t road_bg_word(const uint8_t* chk, int bx, int my, int w, uint32_t grass4, uint32_t check4) {
+    const uint32_t fx = __ldg(reinterpret_cast<const uint32_t*>(chk) + bx * 4 + w);
+    const uint32_t fy = __ldg(chk + 2048 + my) ? 0xFFFFFFFFu : 0u;
+    const uint32_t f = fx & fy;
+    return (f & check4) | (~f & grass4);
+}
+
 __device__ inline void paint_polygon_warp(uint16_t* index, uint8_t* blocks, int& n_blocks, const short* vx, const short* vy, int n,
-                                          uint8_t gray, int lane, int32_t* dropped) {
+                                          uint8_t gray, int lane, int32_t* dropped, const uint8_t* chk, uint32_t grass4, uint32_t check4) {
     int miny = vy[0], maxy = vy[0];
     for (int i = 1; i < n; ++i) { miny = min(miny, (int)vy[i]); maxy = max(maxy, (int)vy[i]); }
     constexpr int HI = CAR_MAP_ORIGIN + CAR_MAP_GRID * CAR_MAP_BLOCK;
@@ -91,7 +102,9 @@ __device__ inline void paint_polygon_warp(uint16_t* index, uint8_t* blocks, int&
             if (n_blocks >= CAR_MAP_MAX_BLOCKS) {
                 if (lane == 0) { __stcg(index + cell, (uint16_t)0xFFFFu); atomicAdd(dropped, 1); }
             } else {
-                reinterpret_cast<uint2*>(blocks + (size_t)n_blocks * 256)[lane] = make_uint2(0u, 0u);
+                const int gx = cell & (CAR_MAP_GRID - 1), my = (cell / CAR_MAP_GRID) * 16 + (lane >> 1), w = (lane & 1) * 2;   // lane = half a row
+                reinterpret_cast<uint2*>(blocks + (size_t)n_blocks * 256)[lane] =
+                    make_uint2(road_bg_word(chk, gx, my, w, grass4, check4), road_bg_word(chk, gx, my, w + 1, grass4, check4));
                 if (lane == 0) __stcg(index + cell, (uint16_t)(n_blocks + 1));
                 n_blocks += 1;
             }
@@ -123,11 +136,14 @@ __device__ inline void paint_road_map(const CarDev& p, int slot, int n_track, in
     for (int i = lane; i < CAR_MAP_GRID * CAR_MAP_GRID / 8; i += 32) __stcg(reinterpret_cast<uint4*>(index) + i, make_uint4(0u, 0u, 0u, 0u));
     __syncwarp();
     int n_blocks = 0;
+    const uint32_t grass4 = 0x01010101u * G[G_GRASS], check4 = 0x01010101u * G[G_CHECK];
     for (int t = n_track - 1; t >= 0; --t) {
         const CarTile* T = tiles + t;
-        paint_polygon_warp(index, blocks, n_blocks, T->mx, T->my, 5, G[G_ROAD0 + t % 3], lane, p.overrun + 1);
+        paint_polygon_warp(index, blocks, n_blocks, T->mx, T->my, 5, G[G_ROAD0 + t % 3], lane, p.overrun + 1, p.chk, grass4, check4);
         const uint8_t flags = T->flags;
-        if (flags & 2) paint_polygon_warp(index, blocks, n_blocks, T->kmx, T->kmy, 4, (flags & 4) ? G[G_KERB_W] : G[G_KERB_R], lane, p.overrun + 1);
+        if (flags & 2)
+            paint_polygon_warp(index, blocks, n_blocks, T->kmx, T->kmy, 4, (flags & 4) ? G[G_KERB_W] : G[G_KERB_R], lane, p.overrun + 1, p.chk,
+                               grass4, check4);
     }
     __threadfence();
 }

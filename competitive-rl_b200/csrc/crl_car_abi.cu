@@ -306,6 +306,17 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     car_constants(&K);
     car_checker_table(K.checker);
     e = cudaMemcpy(kdev, &K, sizeof K, cudaMemcpyHostToDevice);
+    {   // checker squares as byte flags over the road-map window (the same bounds on both axes, kept per axis anyway)
+        std::vector<uint8_t> chk(2 * 2048, 0);
+        for (int axis = 0; axis < 2; ++axis)
+            for (int i = 0; i < 20; ++i)
+                for (int v = K.checker[(axis * 20 + i) * 2]; v <= K.checker[(axis * 20 + i) * 2 + 1]; ++v)
+                    if (v >= CAR_MAP_ORIGIN && v < CAR_MAP_ORIGIN + 2048) chk[axis * 2048 + v - CAR_MAP_ORIGIN] = 0xFF;
+        uint8_t* cdev = nullptr;
+        if (e == cudaSuccess) e = car_alloc(h, &cdev, chk.size());
+        if (e == cudaSuccess) e = cudaMemcpy(cdev, chk.data(), chk.size(), cudaMemcpyHostToDevice);
+        d.chk = cdev;
+    }
     if (e == cudaSuccess) e = cudaMemset(d.ring_pos, 0xFF, n * sizeof(int32_t));
     if (e == cudaSuccess) e = car_raster_init();
     if (e != cudaSuccess) {
