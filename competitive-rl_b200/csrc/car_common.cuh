@@ -134,6 +134,7 @@ struct CarDev {
     float2* tile_centres;     // [2n][CAR_MAX_TRACK] tile centres (= CarTile::cx, cy), contiguous for the step kernel's candidate search
     // ---- per frame (env * players + player): written by car_frame_setup_kernel, read by car_render_kernel ----
     FrameMap* frame_map;      // [n*players]
+    uint8_t* frame_aux;       // [n*players] FrameAux records (car polygon span tables, road-map block list)
     // ---- observation ring: [n][players][c][CAR_PIX] ----
     uint8_t* ring;
     // ---- validation mode ----
@@ -164,8 +165,11 @@ cudaError_t launch_car_step(const CarDev& p, int mode, const float* actions, flo
                             uint8_t* truncated, cudaStream_t s);
 // which: 0 = every frame, 1 = envs not deferred to the slow stepping pass, 2 = deferred envs only; advance: move the frame ring on
 cudaError_t launch_car_render(const CarDev& p, int only_done, int which, int advance, uint8_t* obs, uint8_t* term_obs, cudaStream_t s);
+// stack mode: the C - 1 frames that stay in the observation, ring -> obs; before the render passes of a step (not after a reset)
+cudaError_t launch_car_stack_shift(const CarDev& p, uint8_t* obs, cudaStream_t s);
 cudaError_t car_raster_init();
 size_t car_frame_map_bytes();
+size_t car_frame_aux_bytes();
 void car_checker_table(int* out);
 cudaError_t launch_car_get_state(const CarDev& p, double* state, cudaStream_t s);
 cudaError_t launch_car_set_state(const CarDev& p, const double* state, cudaStream_t s);

@@ -34,12 +34,11 @@ namespace crl {
 #define CR_TRACK_DETAIL_STEP (21.0 / 6.0)
 
 constexpr int RASTER_THREADS = 256;
-constexpr int RASTER_WARPS = RASTER_THREADS / 32;
 constexpr int CAR_POLYS = 8 * CAR_MAX_PLAYERS;   // 4 wheels + 4 hull fixtures per car
 constexpr int POLY_ROWS = 8;               // span rows kept per car polygon (a fixture is <= 5.2 px across at obs_scale: <= 7 rows)
 constexpr int HUD_TOP = 86;                // (int)(H - 4 * (H / 40.0)) = (int)86.4: first row of the black HUD bar
 // the pixels above the HUD bar as quads of 4 horizontally adjacent pixels, row-major: a warp walks 32 consecutive quads at a time
-constexpr int QUADS_X = CAR_W / 4, WALK_QUADS = QUADS_X * HUD_TOP, WALK_GROUPS = (WALK_QUADS + 31) / 32;
+constexpr int QUADS_X = CAR_W / 4, WALK_QUADS = QUADS_X * HUD_TOP;
 constexpr int HUD_WARP = 5;                // the warp that paints the HUD
 // The 96 x 86 px above the HUD bar, rotated by any angle, cover at most floor(sqrt(95^2 + 85^2)) + 2 = 129 consecutive
 // road-map columns / rows, i.e. at most 9 blocks of 16 per axis whatever the alignment (15 + 129 = 144).
@@ -81,91 +80,79 @@ __device__ __forceinline__ void hud_rect(uint8_t* img, double x, double y, doubl
     for (int q = tid; q < total; q += nthreads) img[(y0 + q / bw) * CAR_W + x0 + q % bw] = val;
 }
 
-// one car polygon of the frame (screen pixels): rows [miny, miny + rows) of its span table; key = paint order << 8 | gray
-struct __align__(8) PolyMeta { short miny, rows; unsigned short key; unsigned char n, pad; };
+// one car polygon of the frame (screen pixels): rows [miny, miny + rows) of its span table, gray value
+struct __align__(8) PolyMeta { short miny, rows; unsigned char gray, n, pad0, pad1; };
+
+// What car_frame_setup_kernel hands to the render kernel besides the FrameMap, per frame (1344 bytes): the car polygons
+// scan-converted with pygame's fill rule, and the block-pool positions of the road-map blocks under the window.
+struct __align__(16) FrameAux {
+    short4 spans[CAR_POLYS][POLY_ROWS];
+    PolyMeta meta[CAR_POLYS];
+    uint16_t blk[96];                              // [j * nbx + i]: CarDev::map_index entry of block (obx + i, oby + j); 0 = nothing painted
+};
 
 struct RasterSmem {
     uint8_t img[CAR_PIX];
     uint8_t crop[CROP_DIM * CROP_DIM];             // the road map under the visible window, [v][u] from block (obx, oby)
-    short4 spans[CAR_POLYS][POLY_ROWS];
-    short pvx[CAR_POLYS][8], pvy[CAR_POLYS][8];    // vertices of the car polygons
-    PolyMeta meta[CAR_POLYS];
-    uint32_t group_mask[WALK_GROUPS];              // car polygons whose bounding box touches the group of 32 quads
-    float car_body[CAR_MAX_PLAYERS][40];
+    FrameAux aux;
     double hud_vals[8];
-    int copy_next, hud_late, slow;                 // ring -> observation chunk counter; 1 = an indicator reaches above the bar; 1 = a polygon with > POLY_ROWS rows
+    int copy_next, hud_late;                       // ring -> terminal observation chunk counter; 1 = an indicator reaches above the bar
 };
 
-// Register car polygon `id` (vx, vy)[n] of the frame: vertices, span-table rows, cell bins.  One thread per polygon.
-__device__ void add_polygon(RasterSmem& S, const int* vx, const int* vy, int n, unsigned int key, int id) {
-    int minx = vx[0], maxx = vx[0], miny = vy[0], maxy = vy[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i)
-        if (i < n) { minx = min(minx, vx[i]); maxx = max(maxx, vx[i]); miny = min(miny, vy[i]); maxy = max(maxy, vy[i]); }
-    // vertices far off the screen are clamped (short storage); such a polygon cannot touch the window anyway
-    const int X0 = max(0, minx), X1 = min(CAR_W - 1, maxx), Y0 = max(0, miny), Y1 = min(HUD_TOP - 1, maxy);   // rows under the HUD bar are never walked
-    PolyMeta m;
-    m.miny = (short)max(-32000, min(32000, miny)); m.rows = 0; m.key = (unsigned short)key; m.n = (unsigned char)n; m.pad = 0;
-    if (X1 >= X0 && Y1 >= Y0 && maxy - miny < 30000) {
-        m.rows = (short)(maxy - miny + 1);
-        if (m.rows > POLY_ROWS) S.slow = 1;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { S.pvx[id][i] = (short)max(-32000, min(32000, vx[i])); S.pvy[id][i] = (short)max(-32000, min(32000, vy[i])); }
-        const uint32_t bit = 1u << id;
-        for (int y = Y0; y <= Y1; ++y)
-            for (int g = (y * QUADS_X + (X0 >> 2)) >> 5; g <= (y * QUADS_X + (X1 >> 2)) >> 5; ++g) atomicOr(&S.group_mask[g], bit);
-    }
-    S.meta[id] = m;
-}
-
-// Pixels of the frame above the HUD bar: lane = one quad (x .. x + 3, y).  The road-map byte of each pixel from the staged
-// window (background included); then the car polygons binned to the group, largest key (paint order << 8 | gray) wins.
-// SLOW: a polygon with more rows than its table holds is scanned per pixel.
-template <bool SLOW>
-__device__ __forceinline__ void test_polygon(const RasterSmem& S, int id, int x, int y, unsigned int (&k)[4]) {
-    const PolyMeta m = S.meta[id];
-    const unsigned int key = m.key;
-    const int r = y - m.miny;
-    if ((unsigned)r >= (unsigned)m.rows) return;
-    const short4 sp = (!SLOW || r < POLY_ROWS) ? S.spans[id][r] : scanline_spans(S.pvx[id], S.pvy[id], m.n, y, m.miny + m.rows - 1);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (key > k[i] && ((x + i >= sp.x && x + i <= sp.y) || (x + i >= sp.z && x + i <= sp.w))) k[i] = key;
-}
-
-template <bool SLOW>
-__device__ __forceinline__ void walk_quads(RasterSmem& S, const FrameMap& fm, int warp, int lane) {
+// Pixels of the frame above the HUD bar: lane = one quad (x .. x + 3, y), each pixel the road-map byte it samples from the
+// staged window (background included) -- unless a car polygon was painted there before the walk (img starts out as
+// CAR_UNPAINTED everywhere; no car pixel has that value).
+constexpr uint32_t CAR_UNPAINTED = 0xFFu;
+__device__ __forceinline__ void walk_quads(RasterSmem& S, const FrameMap& fm, int tid) {
     uint32_t* img32 = reinterpret_cast<uint32_t*>(S.img);
     // road-map pixel (rx + u, ry + v) sits at [v + offy][u + offx] of the staged window.  No bounds test: the 96x96 window
     // is the centre of the rotated 192x192 crop, whose inscribed circle (radius 96) contains it (half diagonal 68), so
     // every screen pixel samples inside the crop, and the staged blocks cover everything the rows above the HUD bar sample.
     const uint8_t* crop = S.crop + (fm.ry - CAR_MAP_ORIGIN - CAR_MAP_BLOCK * fm.oby) * CROP_DIM + (fm.rx - CAR_MAP_ORIGIN - CAR_MAP_BLOCK * fm.obx);
     const int bdx = fm.cx0 - fm.icos * fm.bx + fm.isin * fm.by, bdy = fm.cy0 - fm.isin * fm.bx - fm.icos * fm.by;
-    for (int g = warp; g < WALK_GROUPS; g += RASTER_WARPS) {
-        const int q = g * 32 + lane;
-        if (q >= WALK_QUADS) break;                           // only lanes of the last group
+#pragma unroll 1
+    for (int q = tid; q < WALK_QUADS; q += RASTER_THREADS) {
         const int y = (q * 2731) >> 16, x = (q - y * QUADS_X) * 4;     // q / 24 for q < 4096
         // dx = cx0 + icos * (x - bx) - isin * (y - by), dy = cy0 + isin * (x - bx) + icos * (y - by)   (16.16)
         int dx = bdx + fm.icos * x - fm.isin * y, dy = bdy + fm.isin * x + fm.icos * y;
         unsigned int k[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int u = (dx >> 16) & 255, v = (dy >> 16) & 255;      // 0..191 (see above)
+            const unsigned int u = __byte_perm((unsigned)dx, 0u, 0x4442), v = __byte_perm((unsigned)dy, 0u, 0x4442);   // (d >> 16) & 255: 0..191
             k[i] = crop[v * CROP_DIM + u];
             dx += fm.icos; dy += fm.isin;
         }
-        unsigned int bits = S.group_mask[g];                  // car fixtures: screen coordinates
-        while (bits) {
-            const int id = __ffs(bits) - 1;
-            bits &= bits - 1u;
-            test_polygon<SLOW>(S, id, x, y, k);
+        uint32_t w = k[0] | (k[1] << 8) | (k[2] << 16) | (k[3] << 24);
+        const uint32_t cars = img32[q];
+        if (cars != 0x01010101u * CAR_UNPAINTED) {
+            const uint32_t keep = __vcmpeq4(cars, 0x01010101u * CAR_UNPAINTED);      // 0xFF where no car pixel
+            w = (w & keep) | (cars & ~keep);
         }
-        img32[q] = (k[0] & 255u) | ((k[1] & 255u) << 8) | ((k[2] & 255u) << 16) | (k[3] << 24);
+        img32[q] = w;
     }
 }
 
-// Per-frame setup, one thread per (env, player) frame: camera, the integer screen -> road-map mapping and the blocks of
-// the road map under the visible window.  Kept out of the render kernel, where this serial fp64 chain would stall a CTA.
+// The car polygons (Car.draw_for_pygame, car_dynamics.py:284-298: for k in cars: wheels, then hull fixtures), by one warp,
+// before the road pixels are walked.  The four wheels of a car share one colour and so do its four hull fixtures, so
+// only the order of these layers matters: car 0 wheels < car 0 hull < car 1 wheels < car 1 hull.  lane = (polygon of the
+// layer, row of its span table).
+__device__ void paint_cars(RasterSmem& S, int players, int lane) {
+    uint8_t* img = S.img;
+    for (int layer = 0; layer < 2 * players; ++layer) {
+        const int id = layer * 4 + (lane >> 3), r = lane & 7;
+        const PolyMeta m = S.aux.meta[id];
+        const int y = m.miny + r;
+        if (r < m.rows && y >= 0 && y < HUD_TOP) {                    // rows under the HUD bar belong to the HUD
+            const short4 sp = S.aux.spans[id][r];
+            for (int x = max((int)sp.x, 0); x <= min((int)sp.y, CAR_W - 1); ++x) img[y * CAR_W + x] = m.gray;
+            for (int x = max((int)sp.z, 0); x <= min((int)sp.w, CAR_W - 1); ++x) img[y * CAR_W + x] = m.gray;
+        }
+        __syncwarp();
+    }
+}
+
+// Per-frame setup, part 1, one thread per (env, player) frame: camera and the integer screen -> road-map mapping (a serial
+// fp64 chain that would stall a whole CTA of the render kernel).
 __global__ void __launch_bounds__(128)
 car_frame_setup_kernel(CarDev p, int only_done, int which) {
     const int frame = blockIdx.x * blockDim.x + threadIdx.x;       // env * players + player
@@ -174,6 +161,8 @@ car_frame_setup_kernel(CarDev p, int only_done, int which) {
     if (only_done && !p.env_done[e]) return;
     if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
     const CarHullConst* K = p.consts;
+    const double obs_scale = car_obs_scale();
+    FrameMap m;
     // ---- camera_update("rgb_array"): hull.position + R(angle) * (0, 16) ----
     const float4 b0 = *reinterpret_cast<const float4*>(p.body + (size_t)frame * 40);     // cx, cy, angle, vx
     const float bvy = p.body[(size_t)frame * 40 + 4];
@@ -186,8 +175,6 @@ car_frame_setup_kernel(CarDev p, int only_done, int which) {
     const float fa = (float)angle;
     float fs, fc;
     sincosf(fa, &fs, &fc);
-    FrameMap m;
-    const double obs_scale = car_obs_scale();
     m.camx = hx + (fc * 0.0f - fs * 16.0f);
     m.camy = hy + (fs * 0.0f + fc * 16.0f);
     // ---- camera_view: crop rectangle, rotation, blit ----
@@ -223,6 +210,81 @@ car_frame_setup_kernel(CarDev p, int only_done, int which) {
     const int nby = min(((m.ry + v1 - CAR_MAP_ORIGIN) >> 4) - m.oby + 1, CROP_BLOCKS);
     m.nby_mul = nby | (((1024 + m.nbx - 1) / m.nbx) << 8);
     p.frame_map[frame] = m;
+}
+
+// Per-frame setup, part 2, 16 threads per frame: one car polygon each -- b2Vec2 fp32 arithmetic: path = -scale * (tmp *
+// ((trans * v) - offset)) + (W/2, H/2), truncated to int by pygame -- scan-converted with draw_fillpoly's rule, and the
+// pool positions of the road-map blocks under the window.
+__global__ void __launch_bounds__(128, 8)
+car_frame_aux_kernel(CarDev p, int only_done, int which) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int frame = gt >> 4, l = gt & 15;
+    if (frame >= p.n * p.players) return;
+    const int e = frame / p.players, pi = frame - e * p.players;
+    if (only_done && !p.env_done[e]) return;
+    if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
+    const CarHullConst* K = p.consts;
+    const double obs_scale = car_obs_scale();
+    const FrameMap& m = p.frame_map[frame];
+    FrameAux* aux = reinterpret_cast<FrameAux*>(p.frame_aux) + frame;
+    // ---- the road-map blocks under the window ----
+    {
+        const int slot = car_slot(p, e);
+        const uint16_t* index = p.map_index + (size_t)slot * CAR_MAP_GRID * CAR_MAP_GRID;
+        const int nb = m.nbx * (m.nby_mul & 255), mul = m.nby_mul >> 8;
+        for (int bq = l; bq < nb; bq += 16) {
+            const int j = (bq * mul) >> 10, i = bq - j * m.nbx;
+            const int gx = m.obx + i, gy = m.oby + j;
+            unsigned int idx = 0u;
+            if ((unsigned)gx < (unsigned)CAR_MAP_GRID && (unsigned)gy < (unsigned)CAR_MAP_GRID) idx = index[gy * CAR_MAP_GRID + gx];
+            aux->blk[bq] = (uint16_t)(idx == 0xFFFFu ? 0u : idx);   // a dropped block (flagged when painted) shows the background
+        }
+    }
+    // ---- car polygon l = car * 8 + part: parts 0..3 the wheels, 4..7 the hull fixtures ----
+    PolyMeta pm;
+    pm.miny = 0; pm.rows = 0; pm.gray = 0; pm.n = 0; pm.pad0 = pm.pad1 = 0;
+    const int ck = l >> 3, part = l & 7;
+    if (ck < p.players) {
+        const float* b = p.body + ((size_t)e * p.players + ck) * 40;
+        const float* body = (part < 4) ? b + 8 * (part + 1) : b;
+        float bs, bc;
+        sincosf(body[2], &bs, &bc);
+        float px = body[0], py = body[1];
+        if (part >= 4) { px = b[0] - (bc * K->hull_lcx - bs * K->hull_lcy); py = b[1] - (bs * K->hull_lcx + bc * K->hull_lcy); }
+        short vx[8], vy[8];
+        const int n = (part < 4) ? 4 : c_hull_count[part - 4];
+        const float hw = (float)(14 * CR_SIZE), hr = (float)(27 * CR_SIZE);
+        int minx = 0x7fffffff, maxx = -0x7fffffff, miny = 0x7fffffff, maxy = -0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            vx[i] = 0; vy[i] = 0;
+            if (i < n) {
+                float lx, ly;
+                if (part < 4) { lx = (i == 0 || i == 1) ? hw : -hw; ly = (i == 1 || i == 2) ? hr : -hr; }
+                else { lx = (float)(c_hull_poly[part - 4][i][0] * CR_SIZE); ly = (float)(c_hull_poly[part - 4][i][1] * CR_SIZE); }
+                const float wx = (bc * lx - bs * ly) + px, wy = (bs * lx + bc * ly) + py;
+                const float ox = wx - m.camx, oy = wy - m.camy;
+                const float rx2 = (m.tc * ox - m.ts * oy) + 0.0f, ry2 = (m.ts * ox + m.tc * oy) + 0.0f;
+                const float sxp = (float)((double)rx2 * -obs_scale) + (float)(CAR_W / 2.0);
+                const float syp = (float)((double)ry2 * -obs_scale) + (float)(CAR_H / 2.0);
+                // vertices far off the screen are clamped (short storage); such a polygon cannot touch the window anyway
+                const int ix = max(-32000, min(32000, (int)sxp)), iy = max(-32000, min(32000, (int)syp));
+                vx[i] = (short)ix; vy[i] = (short)iy;
+                minx = min(minx, ix); maxx = max(maxx, ix); miny = min(miny, iy); maxy = max(maxy, iy);
+            }
+        }
+        pm.gray = (part < 4) ? K->gray[G_WHEEL] : ((ck == pi) ? K->gray[G_OWN] : K->gray[G_OTHER]);
+        pm.n = (unsigned char)n;
+        pm.miny = (short)miny;
+        if (maxx >= 0 && minx < CAR_W && maxy >= 0 && miny < HUD_TOP) {         // can touch the rows above the HUD bar
+            int rows = maxy - miny + 1;
+            // a fixture is at most 5.3 px across at obs_scale (rigid polygons), i.e. <= 7 rows; anything taller is cut (flagged)
+            if (rows > POLY_ROWS) { atomicAdd(p.overrun + 2, 1); rows = POLY_ROWS; }
+            pm.rows = (short)rows;
+            for (int r = 0; r < rows; ++r) aux->spans[l][r] = scanline_spans(vx, vy, n, miny + r, maxy);
+        }
+    }
+    aux->meta[l] = pm;
 }
 
 // HUD indicators and reward text (render_indicators_for_pygame :645-670), one warp, in paint order
@@ -275,19 +337,21 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     extern __shared__ __align__(16) uint8_t smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
     const int frame = blockIdx.x;                     // env * players + player
-    const int e = (p.players == 2) ? frame >> 1 : frame, pi = (p.players == 2) ? frame & 1 : 0;   // players is 1 or 2
+    const int e = (p.players == 2) ? frame >> 1 : frame;          // players is 1 or 2
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (only_done && !p.env_done[e]) return;
     if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
     const CarHullConst* K = p.consts;
     const uint8_t* G = K->gray;
     const FrameMap fm = p.frame_map[frame];           // written by car_frame_setup_kernel
-    const double obs_scale = car_obs_scale();
     const int slot = car_slot(p, e);
     const int C = p.c;
-    // stack mode: the frames live in an internal ring [frame][C] and the observation (C channels, oldest first) is
-    // rewritten every step.  Ring mode: the observation buffer itself is a double-write ring of 2C slots (the new frame
-    // goes to slots k and k + C, the caller looks at slots k+1 .. k+C), so nothing is copied.
+    // stack mode: the frames live in an internal ring [frame][C]; the C - 1 that stay in the observation were moved
+    // ring -> observation by car_stack_shift_kernel, the new one goes to its ring slot and to channel C - 1.  Ring mode: the
+    // observation buffer itself is a double-write ring of 2C slots (the new frame goes to slots k and k + C, the caller
+    // looks at slots k+1 .. k+C), so nothing is ever moved.
+    // Output layout: [env][players * C][96][96]: player-major channel blocks (FlattenMultiAgentObservation concatenates
+    // the players' stacks on the channel axis), oldest frame first within a player.
     const bool ringm = p.ring_mode != 0;
     uint8_t* ring = ringm ? nullptr : p.ring + (size_t)frame * C * CAR_PIX;
     const bool fill_all = only_done != 0 || (ringm ? p.fill_all != 0 : p.ring_pos[e] < 0);
@@ -297,10 +361,14 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     uint8_t* out = obs + (size_t)frame * (ringm ? 2 * C : C) * CAR_PIX;
     uint8_t* tout = (term_obs != nullptr && !only_done && p.env_done[e]) ? term_obs + (size_t)frame * C * CAR_PIX : nullptr;
 
-    if (tid < p.players * 40) (&S.car_body[0][0])[tid] = p.body[(size_t)e * p.players * 40 + tid];   // [player][40], contiguous on both sides
-    if (tid < WALK_GROUPS) S.group_mask[tid] = 0u;
-    if (tid >= 232 && tid < 232 + CAR_POLYS - p.players * 8) S.meta[p.players * 8 + tid - 232].rows = 0;   // polygons of an absent second car
-    if (tid == 255) { S.copy_next = 0; S.hud_late = 0; S.slow = 0; }
+    // what the setup kernel prepared: car polygon span tables and the block list (84 x 16 bytes)
+    if (tid < (int)(sizeof(FrameAux) / 16))
+        reinterpret_cast<uint4*>(&S.aux)[tid] = reinterpret_cast<const uint4*>(reinterpret_cast<const FrameAux*>(p.frame_aux) + frame)[tid];
+    {   // every pixel starts out "no car here"; rows 86.. are the HUD warp's
+        const uint32_t f4 = 0x01010101u * CAR_UNPAINTED;
+        for (int q = tid; q < HUD_TOP * CAR_W / 16; q += RASTER_THREADS) reinterpret_cast<uint4*>(S.img)[q] = make_uint4(f4, f4, f4, f4);
+    }
+    if (tid == 255) { S.copy_next = 0; S.hud_late = 0; }
     if (tid >= 240 && tid < 248) {      // HUD inputs (render_indicators_for_pygame :645-670)
         const int k = tid - 240;
         const float* b = p.body + (size_t)frame * 40;
@@ -314,69 +382,32 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
         S.hud_vals[k] = v;
     }
     __syncthreads();
-    // ---- car polygons, one thread each (Car.draw_for_pygame): for k in cars: wheels, then hull fixtures; b2Vec2 fp32
-    //      arithmetic: path = -scale * (tmp * ((trans * v) - offset)) + (W/2, H/2), truncated to int by pygame.  Painted
-    //      over the road in that order: higher key wins. ----
-    if (tid >= RASTER_THREADS - p.players * 8) {
-        const int q = RASTER_THREADS - 1 - tid;
-        const int ck = q >> 3, part = q & 7;
-        const float* b = S.car_body[ck];
-        const float* body = (part < 4) ? b + 8 * (part + 1) : b;
-        float bs, bc;
-        sincosf(body[2], &bs, &bc);
-        float px = body[0], py = body[1];
-        if (part >= 4) { px = b[0] - (bc * K->hull_lcx - bs * K->hull_lcy); py = b[1] - (bs * K->hull_lcx + bc * K->hull_lcy); }
-        int vx[8], vy[8];
-        const int n = (part < 4) ? 4 : c_hull_count[part - 4];
-        const float hw = (float)(14 * CR_SIZE), hr = (float)(27 * CR_SIZE);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            vx[i] = 0; vy[i] = 0;
-            if (i < n) {
-                float lx, ly;
-                if (part < 4) { lx = (i == 0 || i == 1) ? hw : -hw; ly = (i == 1 || i == 2) ? hr : -hr; }
-                else { lx = (float)(c_hull_poly[part - 4][i][0] * CR_SIZE); ly = (float)(c_hull_poly[part - 4][i][1] * CR_SIZE); }
-                const float wx = (bc * lx - bs * ly) + px, wy = (bs * lx + bc * ly) + py;
-                const float ox = wx - fm.camx, oy = wy - fm.camy;
-                const float rx2 = (fm.tc * ox - fm.ts * oy) + 0.0f, ry2 = (fm.ts * ox + fm.tc * oy) + 0.0f;
-                const float sxp = (float)((double)rx2 * -obs_scale) + (float)(CAR_W / 2.0);
-                const float syp = (float)((double)ry2 * -obs_scale) + (float)(CAR_H / 2.0);
-                vx[i] = (int)sxp; vy[i] = (int)syp;
-            }
-        }
-        const uint8_t g = (part < 4) ? G[G_WHEEL] : ((ck == pi) ? G[G_OWN] : G[G_OTHER]);
-        add_polygon(S, vx, vy, n, ((unsigned)(q + 1) << 8) | g, q);
-    }
     // ---- the road map under the window: 16 threads per 16 x 16 block, one 16-byte row each; where nothing was painted
     //      (no block, or outside the slot's grid) the row is the background: grass / checker squares ----
     {
-        const uint16_t* index = p.map_index + (size_t)slot * CAR_MAP_GRID * CAR_MAP_GRID;
         const uint4* blocks = reinterpret_cast<const uint4*>(p.map_blocks + (size_t)slot * CAR_MAP_MAX_BLOCKS * 256);
         const int nb = fm.nbx * (fm.nby_mul & 255), sub = tid & 15, mul = fm.nby_mul >> 8;
         const uint32_t grass4 = 0x01010101u * G[G_GRASS], check4 = 0x01010101u * G[G_CHECK];
 #pragma unroll 2
         for (int bq = tid >> 4; bq < nb; bq += RASTER_THREADS / 16) {
             const int j = (bq * mul) >> 10, i = bq - j * fm.nbx;
-            const int gx = fm.obx + i, gy = fm.oby + j;
-            const bool inside = (unsigned)gx < (unsigned)CAR_MAP_GRID && (unsigned)gy < (unsigned)CAR_MAP_GRID;
-            unsigned int idx = 0u;
-            if (inside) idx = index[gy * CAR_MAP_GRID + gx];
+            const unsigned int idx = S.aux.blk[bq];
             uint4 v;
-            if (idx != 0u && idx != 0xFFFFu) v = blocks[(idx - 1u) * 16 + sub];
-            else if (inside) {
-                const int my = gy * 16 + sub;
-                v = make_uint4(road_bg_word(p.chk, gx, my, 0, grass4, check4), road_bg_word(p.chk, gx, my, 1, grass4, check4),
-                               road_bg_word(p.chk, gx, my, 2, grass4, check4), road_bg_word(p.chk, gx, my, 3, grass4, check4));
-            } else v = make_uint4(grass4, grass4, grass4, grass4);      // the checker squares end well inside the window
+            if (idx != 0u) v = blocks[(idx - 1u) * 16 + sub];
+            else {
+                const int gx = fm.obx + i, gy = fm.oby + j;
+                if ((unsigned)gx < (unsigned)CAR_MAP_GRID && (unsigned)gy < (unsigned)CAR_MAP_GRID) {
+                    const int my = gy * 16 + sub;
+                    v = make_uint4(road_bg_word(p.chk, gx, my, 0, grass4, check4), road_bg_word(p.chk, gx, my, 1, grass4, check4),
+                                   road_bg_word(p.chk, gx, my, 2, grass4, check4), road_bg_word(p.chk, gx, my, 3, grass4, check4));
+                } else v = make_uint4(grass4, grass4, grass4, grass4);  // the checker squares end well inside the window
+            }
             *reinterpret_cast<uint4*>(S.crop + (j * 16 + sub) * CROP_DIM + i * 16) = v;
         }
     }
-    // ---- meanwhile (nothing here touches what the polygon threads write): warp HUD_WARP paints the HUD bar -- rows 86..95,
-    //      which the pixel pass below never writes -- and every warp, as soon as it is free, copies chunks of the C - 1
-    //      older frames ring -> observation.  FrameStack: the new frame enters the ring; the observation is the ring
-    //      oldest -> newest.  After a reset (only_done pass, or the very first render) every slot holds the reset frame.
-    //      Output layout: [env][players * C][96][96]: player-major channel blocks (FlattenMultiAgentObservation
-    //      concatenates the players' stacks on the channel axis), oldest frame first within a player. ----
+    // ---- meanwhile: warp 0 paints the car polygons (the walk below keeps them), warp HUD_WARP the HUD bar -- rows 86..95,
+    //      which the walk never writes -- and a finished env's terminal observation gets its older frames ----
+    if (warp == 0) paint_cars(S, p.players, lane);
     uint8_t* img = S.img;
     __syncwarp();
     if (warp == HUD_WARP) {
@@ -395,7 +426,9 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
         else paint_hud_indicators(S, p.glyphs, G, img, lane);
         __syncwarp();
     }
-    if (!fill_all && (!ringm || tout != nullptr)) {                // ring mode: only the terminal observation is materialised
+    // The C - 1 older frames were moved ring -> observation by car_stack_shift_kernel before this launch (stack mode; a
+    // ring-mode observation needs no move at all).  Only the terminal observation of a finished env is assembled here.
+    if (!fill_all && tout != nullptr) {
         constexpr int PER_SLOT = CAR_PIX / 16 / 64;                // chunks of 64 uint4 (two per lane) per frame: 9
         const int n_chunks = (C - 1) * PER_SLOT;
         for (;;) {
@@ -408,27 +441,13 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
             if (!ringm && rs >= C) rs -= C;
             const uint4* rsrc = reinterpret_cast<const uint4*>((ringm ? out : ring) + (size_t)rs * CAR_PIX);
             const uint4 v0 = rsrc[q], v1 = rsrc[q + 32];
-            if (!ringm) {
-                uint4* dst = reinterpret_cast<uint4*>(out + (size_t)sl * CAR_PIX);
-                dst[q] = v0; dst[q + 32] = v1;
-            }
-            if (tout) { uint4* tdst = reinterpret_cast<uint4*>(tout + (size_t)sl * CAR_PIX); tdst[q] = v0; tdst[q + 32] = v1; }
-        }
-    }
-    __syncthreads();
-    if (tid == 0 && S.slow != 0) atomicAdd(p.overrun + 2, 1);     // frames with a car polygon taller than its span table (scanned per pixel)
-    // ---- span tables of the car polygons: one (polygon, row) per thread ----
-    {
-        const int id = tid >> 3, r = tid & 7;
-        if (id < CAR_POLYS) {
-            const PolyMeta m = S.meta[id];
-            if (r < m.rows) S.spans[id][r] = scanline_spans(S.pvx[id], S.pvy[id], m.n, m.miny + r, m.miny + m.rows - 1);
+            uint4* tdst = reinterpret_cast<uint4*>(tout + (size_t)sl * CAR_PIX);
+            tdst[q] = v0; tdst[q + 32] = v1;
         }
     }
     __syncthreads();
     // ---- pixels above the HUD bar ----
-    if (S.slow == 0) walk_quads<false>(S, fm, warp, lane);
-    else walk_quads<true>(S, fm, warp, lane);
+    walk_quads(S, fm, tid);
     __syncthreads();
     if (S.hud_late) {                                              // uniform over the CTA
         if (warp == HUD_WARP) paint_hud_indicators(S, p.glyphs, G, img, lane);
@@ -460,6 +479,42 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     }
 }
 
+// FrameStack in stack mode (atari_wrappers.py:222-259): the observation is the C newest frames, oldest first.  The C - 1
+// frames that stay are already known before the step: this kernel moves them from the internal ring to channels
+// 0 .. C-2 of every (env, player) -- pure bandwidth, so crl_car_step runs it on a side stream under the latency-bound
+// physics pass -- and the render kernel then only writes the new frame (ring slot + channel C-1).  Envs that were just
+// reset (ring_pos < 0) are skipped: their first render fills every channel.
+__global__ void __launch_bounds__(256) car_stack_shift_kernel(CarDev p, uint8_t* __restrict__ obs) {
+    constexpr int FRAME_V = CAR_PIX / 16;                           // uint4 per frame: 576
+    const int C = p.c, per_frame = (C - 1) * FRAME_V;
+    const size_t total = (size_t)p.n * p.players * per_frame;
+    const uint4* ring = reinterpret_cast<const uint4*>(p.ring);
+    uint4* out = reinterpret_cast<uint4*>(obs);
+    for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i0 < total; i0 += (size_t)gridDim.x * blockDim.x * 4) {
+        uint4 v[4];
+        size_t dst[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const size_t i = i0 + (size_t)k * gridDim.x * blockDim.x;
+            dst[k] = (size_t)-1;
+            if (i < total) {
+                const int frame = (int)(i / per_frame), r = (int)(i - (size_t)frame * per_frame);
+                const int sl = r / FRAME_V, q = r - sl * FRAME_V;
+                const int pos = p.ring_pos[p.players == 2 ? frame >> 1 : frame];
+                if (pos >= 0) {
+                    int rs = pos + 2 + sl;                          // the slot after the one the new frame will take = the oldest that stays
+                    rs -= (rs >= C) ? C : 0; rs -= (rs >= C) ? C : 0;
+                    v[k] = ring[((size_t)frame * C + rs) * FRAME_V + q];
+                    dst[k] = ((size_t)frame * C + sl) * FRAME_V + q;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (dst[k] != (size_t)-1) out[dst[k]] = v[k];
+    }
+}
+
 __global__ void car_ring_advance_kernel(CarDev p, int only_done) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.n) return;
@@ -484,13 +539,23 @@ void car_checker_table(int* out /* [2][20][2] */) {
 }
 
 size_t car_frame_map_bytes() { return sizeof(FrameMap); }
+size_t car_frame_aux_bytes() { return sizeof(FrameAux); }
 
 cudaError_t car_raster_init() {
     return cudaFuncSetAttribute(car_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RasterSmem));
 }
 
+cudaError_t launch_car_stack_shift(const CarDev& p, uint8_t* obs, cudaStream_t s) {
+    if (p.ring_mode || p.c < 2) return cudaSuccess;
+    const size_t total = (size_t)p.n * p.players * (p.c - 1) * (CAR_PIX / 16);
+    const int blocks = (int)((total + 256 * 4 - 1) / (256 * 4));
+    car_stack_shift_kernel<<<blocks, 256, 0, s>>>(p, obs);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_car_render(const CarDev& p, int only_done, int which, int advance, uint8_t* obs, uint8_t* term_obs, cudaStream_t s) {
     car_frame_setup_kernel<<<(p.n * p.players + 127) / 128, 128, 0, s>>>(p, only_done, which);
+    car_frame_aux_kernel<<<(p.n * p.players * 16 + 127) / 128, 128, 0, s>>>(p, only_done, which);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     car_render_kernel<<<p.n * p.players, RASTER_THREADS, sizeof(RasterSmem), s>>>(p, only_done, which, obs, term_obs);

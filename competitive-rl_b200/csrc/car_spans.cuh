@@ -18,7 +18,10 @@ __device__ __forceinline__ int cdiv_trunc(int a, int b) {
 __device__ __forceinline__ short4 scanline_spans(const short* vx, const short* vy, int n, int V, int maxy) {
     int xs[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
     int m = 0;
-    int yp = vy[n - 1], xp = vx[n - 1];                   // previous vertex (edge i runs from vertex i - 1 to vertex i)
+    int yp = vy[0], xp = vx[0];                           // previous vertex (edge i runs from vertex i - 1 to vertex i): the last one
+#pragma unroll
+    for (int i = 1; i < 8; ++i)                           // (static indices: a register array stays in registers)
+        if (i == n - 1) { yp = vy[i]; xp = vx[i]; }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         if (i >= n) break;

@@ -34,6 +34,9 @@ struct crl_car {
     // crl_car_step of two-car envs: envs whose cars touch are stepped on a side stream while the others render
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fast = nullptr, ev_slow = nullptr;
+    // stack mode: the C - 1 frames that stay in the observation are moved ring -> obs on this stream while the physics runs
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy_go = nullptr, ev_copy_done = nullptr;
     // next tracks are generated ahead of time on this stream (car_pregen_kernel); at most one launch in flight
     cudaStream_t pregen_stream = nullptr;
     cudaEvent_t ev_pregen_go = nullptr;
@@ -224,6 +227,28 @@ int discard_pregen(crl_car* h, cudaStream_t s) {
     LAUNCH(launch_car_discard_next(h->dev, s), 1);
     return CRL_OK;
 }
+
+// Stack mode: start moving the frames that stay in the observation (ring -> channels 0 .. C-2 of obs) on the copy stream,
+// behind everything queued on `s` so far; join_stack_shift makes `s` wait for it (before the first render pass).
+int fork_stack_shift(crl_car* h, uint8_t* obs_dev, cudaStream_t s) {
+    if (h->dev.ring_mode || h->dev.c < 2) return CRL_OK;
+    if (!h->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copy_go, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copy_done, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(h->ev_copy_go, s));
+    CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->ev_copy_go, 0));
+    LAUNCH(launch_car_stack_shift(h->dev, obs_dev, h->copy_stream), 1);
+    CUDA_TRY(cudaEventRecord(h->ev_copy_done, h->copy_stream));
+    return CRL_OK;
+}
+
+int join_stack_shift(crl_car* h, cudaStream_t s) {
+    if (h->dev.ring_mode || h->dev.c < 2) return CRL_OK;
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_copy_done, 0));
+    return CRL_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -238,6 +263,10 @@ int crl_car_destroy(crl_car* h) {
     if (h->ev_fast) cudaEventDestroy(h->ev_fast);
     if (h->ev_slow) cudaEventDestroy(h->ev_slow);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    if (h->ev_copy_go) cudaEventDestroy(h->ev_copy_go);
+    if (h->ev_copy_done) cudaEventDestroy(h->ev_copy_done);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
     return CRL_OK;
 }
@@ -292,6 +321,7 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
         uint8_t* fmraw = nullptr;
         ALLOC(fmraw, nc * car_frame_map_bytes());
         d.frame_map = reinterpret_cast<FrameMap*>(fmraw);
+        ALLOC(d.frame_aux, nc * car_frame_aux_bytes());
     }
     ALLOC(d.map_index, 2 * n * CAR_MAP_GRID * CAR_MAP_GRID); ALLOC(d.map_blocks, 2 * n * CAR_MAP_MAX_BLOCKS * 256);
     ALLOC(d.tile_centres, 2 * n * CAR_MAX_TRACK);
@@ -413,7 +443,7 @@ int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream) {
     h->dev.ring_phase = 0;
     h->dev.fill_all = 1;      // until the next step: every frame written goes to all slots of its ring
     LAUNCH(launch_car_reset(h->dev, 0, s), 1);
-    LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, nullptr, s), 3);
+    LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, nullptr, s), 4);
     h->was_reset = true;
     return kick_pregen(h, s);
 }
@@ -434,9 +464,10 @@ int crl_car_render_obs(crl_car* h, uint8_t* obs_dev, uint8_t* term_obs_dev, void
     if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
     if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
     cudaStream_t s = (cudaStream_t)stream;
-    LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, term_obs_dev, s), 3);   // post-step frame (terminal obs of finished envs)
+    if (!h->dev.ring_mode && h->dev.c >= 2) LAUNCH(launch_car_stack_shift(h->dev, obs_dev, s), 1);   // the frames that stay: ring -> obs
+    LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, term_obs_dev, s), 4);   // post-step frame (terminal obs of finished envs)
     LAUNCH(launch_car_reset(h->dev, 1, s), 1);                                 // auto-reset of finished envs
-    LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 3);        // their reset observation
+    LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 4);        // their reset observation
     return kick_pregen(h, s);
 }
 
@@ -444,8 +475,16 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
                  int32_t* num_steps_dev, uint8_t* truncated_dev, uint8_t* term_obs_dev, void* stream) {
     CHECK_HANDLE(h);
     if (h->dev.players == 1) {
+        if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
+        if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
+        cudaStream_t s1 = (cudaStream_t)stream;
+        if (int r = fork_stack_shift(h, obs_dev, s1)) return r;                    // under the physics pass
         if (int r = crl_car_step_state(h, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, stream)) return r;
-        return crl_car_render_obs(h, obs_dev, term_obs_dev, stream);
+        if (int r = join_stack_shift(h, s1)) return r;
+        LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, term_obs_dev, s1), 4);   // post-step frame (terminal obs of finished envs)
+        LAUNCH(launch_car_reset(h->dev, 1, s1), 1);                                 // auto-reset of finished envs
+        LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s1), 4);        // their reset observation
+        return kick_pregen(h, s1);
     }
     // Two-car envs.  The step kernel is one wave of latency-bound threads; lane pairs whose cars touch run the sequential
     // contact solver and take several times longer than the rest.  So: fast pass over the envs whose cars are apart
@@ -463,17 +502,19 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
     }
     h->dev.fill_all = 0;
     if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
+    if (int r = fork_stack_shift(h, obs_dev, s)) return r;                        // under the fast physics pass
     CUDA_TRY(cudaMemsetAsync(h->dev.slow_count, 0, sizeof(int32_t), s));
     LAUNCH(launch_car_step(h->dev, 1, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, s), 1);
     CUDA_TRY(cudaEventRecord(h->ev_fast, s));
     CUDA_TRY(cudaStreamWaitEvent(h->side_stream, h->ev_fast, 0));
     LAUNCH(launch_car_step(h->dev, 2, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, h->side_stream), 1);
     CUDA_TRY(cudaEventRecord(h->ev_slow, h->side_stream));
-    LAUNCH(launch_car_render(h->dev, 0, 1, 0, obs_dev, term_obs_dev, s), 2);   // frames of the envs stepped by the fast pass
+    if (int r = join_stack_shift(h, s)) return r;
+    LAUNCH(launch_car_render(h->dev, 0, 1, 0, obs_dev, term_obs_dev, s), 3);   // frames of the envs stepped by the fast pass
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_slow, 0));
-    LAUNCH(launch_car_render(h->dev, 0, 2, 1, obs_dev, term_obs_dev, s), 3);   // frames of the listed envs; ring moves on
+    LAUNCH(launch_car_render(h->dev, 0, 2, 1, obs_dev, term_obs_dev, s), 4);   // frames of the listed envs; ring moves on
     LAUNCH(launch_car_reset(h->dev, 1, s), 1);                                 // auto-reset of finished envs
-    LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 3);        // their reset observation
+    LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 4);        // their reset observation
     return kick_pregen(h, s);
 }
 
@@ -530,7 +571,8 @@ int crl_car_render_state(crl_car* h, uint8_t* obs_dev, void* stream) {
     if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before rendering");
     if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
     if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
-    LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, nullptr, (cudaStream_t)stream), 3);
+    if (!h->dev.ring_mode && h->dev.c >= 2) LAUNCH(launch_car_stack_shift(h->dev, obs_dev, (cudaStream_t)stream), 1);
+    LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, nullptr, (cudaStream_t)stream), 4);
     return CRL_OK;
 }
 
