@@ -118,6 +118,7 @@ struct CarDev {
     int32_t* counters;        // [n*players][4]: tile_visited_count, last_block, has_block, done
     uint32_t* touching;       // [n*players][4][16] wheel.tiles bitmasks
     uint32_t* visited;        // [n*players][16] tile.road_visited[car]
+    uint32_t* sensor_now;     // [n*players][4][16] tiles each wheel overlaps at the start of the step (car_sensor_kernel)
     // ---- car-car contacts (players == 2): [n][CAR_MAX_CONTACTS] records, [n] counts, one overflow counter ----
     CarContact* contacts;
     int32_t* n_contacts;
@@ -126,6 +127,11 @@ struct CarDev {
     int32_t* slow_list;       // [n]
     int32_t* slow_count;      // [1]
     uint8_t* deferred;        // [n] 1 = on the slow list this step
+    // envs that finished in this step, listed by the post-step render passes (collect_done = 1) so that the auto-reset
+    // kernels run over the list instead of launching a thread block per env
+    int32_t* done_list;       // [n]
+    int32_t* done_count;      // [1] cleared at the start of every step
+    int collect_done;
     // ---- per slot: the painted road map (it depends on the track only, so it is painted once per track by the generator
     //      instead of once per frame): block index [2n][CAR_MAP_GRID][CAR_MAP_GRID], block pool [2n][CAR_MAP_MAX_BLOCKS][256] ----
     uint16_t* map_index;
@@ -161,6 +167,7 @@ __device__ __forceinline__ int car_slot(const CarDev& p, int e) { return e + p.n
 cudaError_t launch_car_reset(const CarDev& p, int only_done, cudaStream_t s);
 cudaError_t launch_car_pregen(const CarDev& p, cudaStream_t s);        // next tracks of the envs that have none (side stream)
 cudaError_t launch_car_discard_next(const CarDev& p, cudaStream_t s);  // forget pre-generated tracks (seed / injection changed)
+cudaError_t launch_car_sensors(const CarDev& p, cudaStream_t s);      // wheel-tile overlaps, before launch_car_step
 cudaError_t launch_car_step(const CarDev& p, int mode, const float* actions, float* rew, uint8_t* done, int32_t* num_steps,
                             uint8_t* truncated, cudaStream_t s);
 // which: 0 = every frame, 1 = envs not deferred to the slow stepping pass, 2 = deferred envs only; advance: move the frame ring on

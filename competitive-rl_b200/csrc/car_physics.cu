@@ -403,10 +403,20 @@ __global__ void car_discard_next_kernel(CarDev p) {
 
 // CarRacing.reset: new track (retry until an attempt succeeds, :499-507), cars at track[0] (:508-512).  One warp per env:
 // the track is normally waiting in the env's other slot (car_pregen_kernel) and the reset is a slot swap + spawn.
+__device__ void car_reset_env(const CarDev& p, int e, int only_done, int lane);
+
+// only_done: the envs on the done list (grid-stride over the list, a warp per env); else every env, one warp each
 __global__ void __launch_bounds__(64) car_reset_kernel(CarDev p, int only_done) {
-    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (e >= p.n) return;
-    if (only_done && !p.env_done[e]) return;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (!only_done) {
+        if (w < p.n) car_reset_env(p, w, 0, lane);
+        return;
+    }
+    const int count = min(*p.done_count, p.n), n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = w; i < count; i += n_warps) car_reset_env(p, p.done_list[i], 1, lane);
+}
+
+__device__ void car_reset_env(const CarDev& p, int e, int only_done, int lane) {
     const int next_slot = e + p.n * (1 - p.sel[e]);
     bool have = true;
     const int st_before = *(volatile int32_t*)(p.next_state + e);
@@ -538,6 +548,76 @@ __device__ __forceinline__ bool cars_near(const float (*pose)[3], float hull_lcx
     return (step_count < 4) ? (t.x * t.x + t.y * t.y < 8.0f * 8.0f) : !separated;
 }
 
+// b2ContactManager::Collide for the tile sensors of ONE wheel: the road tiles whose fixture overlaps the wheel box (SAT
+// with the b2_polygonRadius skins), as a 512-bit set in now16[16] (global memory).  Candidates: every 8th track point
+// within 36 units of the hull (transposed array: coalesced), then tile centres within 11.5 of the hull and 9 of the wheel.
+__device__ void sensor_wheel_overlaps(const CarDev& p, int slot, int n_track, F2 hp, F2 wc, float wa, uint32_t* __restrict__ now16) {
+    const CarTile* tiles = p.tiles + (size_t)slot * CAR_MAX_TRACK;
+    const float2* centres = p.tile_centres + (size_t)slot * CAR_MAX_TRACK;
+    reinterpret_cast<uint4*>(now16)[0] = make_uint4(0u, 0u, 0u, 0u); reinterpret_cast<uint4*>(now16)[1] = make_uint4(0u, 0u, 0u, 0u);
+    reinterpret_cast<uint4*>(now16)[2] = make_uint4(0u, 0u, 0u, 0u); reinterpret_cast<uint4*>(now16)[3] = make_uint4(0u, 0u, 0u, 0u);
+    // wheel box in world coordinates and its face normals
+    float wx[4], wy[4], wnx[4], wny[4];
+    {
+        const Rot q = make_rot(wa);
+        const float hw = (float)(CR_WHEEL_W * CR_SIZE), hr = (float)(CR_WHEEL_R * CR_SIZE);
+        const F2 l0 = rmul(q, f2(-hw, -hr)) + wc, l1 = rmul(q, f2(+hw, -hr)) + wc;
+        const F2 l2 = rmul(q, f2(+hw, +hr)) + wc, l3 = rmul(q, f2(-hw, +hr)) + wc;
+        wx[0] = l0.x; wy[0] = l0.y; wx[1] = l1.x; wy[1] = l1.y; wx[2] = l2.x; wy[2] = l2.y; wx[3] = l3.x; wy[3] = l3.y;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int i2 = (i + 1) & 3;
+            const float ex = wx[i2] - wx[i], ey = wy[i2] - wy[i];
+            const float len = sqrtf(ex * ex + ey * ey);
+            wnx[i] = 3.0e38f; wny[i] = 0.f;
+            if (!(len < 1e-12f)) { wnx[i] = ey / len; wny[i] = -ex / len; }
+        }
+    }
+    const int n_samp = (n_track + CAR_SAMPLE_STRIDE - 1) / CAR_SAMPLE_STRIDE;
+    for (int s = 0; s < n_samp; ++s) {
+        const float2 sp = p.samples[(size_t)s * (2 * p.n) + slot];
+        const float dx = sp.x - hp.x, dy = sp.y - hp.y;
+        if (!(dx * dx + dy * dy < 36.0f * 36.0f)) continue;
+        const int t1 = min(n_track, (s + 1) * CAR_SAMPLE_STRIDE);
+        for (int t = s * CAR_SAMPLE_STRIDE; t < t1; ++t) {
+            const float2 tc = centres[t];
+            const float tx = tc.x - hp.x, ty = tc.y - hp.y;
+            if (!(tx * tx + ty * ty < 11.5f * 11.5f)) continue;
+            const float ddx = tc.x - wc.x, ddy = tc.y - wc.y;
+            if (!(ddx * ddx + ddy * ddy <= 9.0f * 9.0f)) continue;
+            const CarTile* Tp = tiles + t;
+            float tpx[5], tpy[5], tnx[5], tny[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) { tpx[i] = Tp->px[i]; tpy[i] = Tp->py[i]; tnx[i] = Tp->nx[i]; tny[i] = Tp->ny[i]; }
+            const int tn = Tp->n;
+            // max(s1, s2) < 2 r  <=>  no face of either polygon separates them by 2 r or more: stop at the first that does
+            if (!separated_by_face(wx, wy, wnx, wny, 4, tpx, tpy, tn, 2.0f * B2_POLYGON_RADIUS) &&
+                !separated_by_face(tpx, tpy, tnx, tny, tn, wx, wy, 4, 2.0f * B2_POLYGON_RADIUS))
+                now16[t >> 5] |= 1u << (t & 31);
+        }
+    }
+}
+
+// The tile-sensor overlaps of every wheel at the start of world.Step, one thread per (car, wheel), ahead of the step
+// kernel: they depend only on the poses the previous step left behind, and one thread per car would walk its four
+// wheels' candidates one after the other on the step's critical path.
+__global__ void __launch_bounds__(128) car_sensor_kernel(CarDev p) {
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ci = gt >> 2, k = gt & 3;
+    if (ci >= p.n * p.players) return;
+    const int e = ci / p.players;
+    const float* b = p.body + (size_t)ci * 40;
+    const Rot qh = make_rot(b[2]);
+    const F2 hp = f2(b[0], b[1]) - rmul(qh, f2(p.consts->hull_lcx, p.consts->hull_lcy));
+    const int slot = car_slot(p, e);
+    sensor_wheel_overlaps(p, slot, p.n_track[slot], hp, f2(b[8 * (k + 1)], b[8 * (k + 1) + 1]), b[8 * (k + 1) + 2],
+                          p.sensor_now + ((size_t)ci * 4 + k) * 16);
+}
+
+__device__ __noinline__ void sensor_car_overlaps(const CarDev& p, int ci, int slot, int n_track, F2 hp, const F2* c, const float* a) {
+    for (int k = 0; k < 4; ++k) sensor_wheel_overlaps(p, slot, n_track, hp, c[k + 1], a[k + 1], p.sensor_now + ((size_t)ci * 4 + k) * 16);
+}
+
 // mode 0: every car.  mode 1 (fast pass): two-car envs whose cars are near each other are only put on p.slow_list
 // (p.deferred[env] = 1) -- their contact solve is several times longer than a plain step and would hold up the whole
 // single-wave launch.  mode 2 (slow pass): the envs on p.slow_list, two lanes each.
@@ -612,8 +692,6 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
         uint32_t* visited = p.visited + (size_t)ci * 16;
         const int slot = car_slot(p, e);
         const int n_track = p.n_track[slot];
-        const CarTile* tiles = p.tiles + (size_t)slot * CAR_MAX_TRACK;
-        const float2* centres = p.tile_centres + (size_t)slot * CAR_MAX_TRACK;   // 8-byte stride instead of CarTile's 116
         int step_count = p.step_count[e];
         float inv_dt0 = p.inv_dt0[e];
         const float hull_lcx = K.hull_lcx, hull_lcy = K.hull_lcy;
@@ -701,75 +779,13 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
             // ================= world.Step(1/FPS, 180, 60) =================
             // ---- b2ContactManager::Collide: wheel-tile sensor contacts -> FrictionDetector._contact ----
             {
-                // candidate tiles: prefilter on every 8th track point (transposed array: coalesced), then tile centres
-                const Rot qh = make_rot(a[0]);
-                const F2 hp = c[0] - rmul(qh, f2(hull_lcx, hull_lcy));
-                int cand[48], n_cand = 0;
-                const int n_samp = (n_track + CAR_SAMPLE_STRIDE - 1) / CAR_SAMPLE_STRIDE;
-                for (int s = 0; s < n_samp; ++s) {
-                    const float2 sp = p.samples[(size_t)s * (2 * p.n) + slot];
-                    const float dx = sp.x - hp.x, dy = sp.y - hp.y;
-                    if (dx * dx + dy * dy < 36.0f * 36.0f) {
-                        const int t1 = min(n_track, (s + 1) * CAR_SAMPLE_STRIDE);
-                        for (int t = s * CAR_SAMPLE_STRIDE; t < t1; ++t) {
-                            const float2 tc = centres[t];
-                            const float tx = tc.x - hp.x, ty = tc.y - hp.y;
-                            if (tx * tx + ty * ty < 11.5f * 11.5f && n_cand < 48) cand[n_cand++] = t;
-                        }
-                    }
+                // the overlap sets of the four wheels come from car_sensor_kernel (poses at the start of the step); a further
+                // sub-step of the same action (action_repeat > 1) recomputes them here from the poses it now has
+                if (rep > 0) {
+                    const Rot qh = make_rot(a[0]);
+                    sensor_car_overlaps(p, ci, slot, n_track, c[0] - rmul(qh, f2(hull_lcx, hull_lcy)), c, a);
                 }
-                // wheel boxes in world coordinates
-                float wx[4][4], wy[4][4];
-                for (int k = 0; k < 4; ++k) {
-                    const int bi = k + 1;
-                    const Rot q = make_rot(a[bi]);
-                    const float hw = (float)(CR_WHEEL_W * CR_SIZE), hr = (float)(CR_WHEEL_R * CR_SIZE);
-                    const F2 l0 = rmul(q, f2(-hw, -hr)) + c[bi], l1 = rmul(q, f2(+hw, -hr)) + c[bi];
-                    const F2 l2 = rmul(q, f2(+hw, +hr)) + c[bi], l3 = rmul(q, f2(-hw, +hr)) + c[bi];
-                    wx[k][0] = l0.x; wy[k][0] = l0.y; wx[k][1] = l1.x; wy[k][1] = l1.y;
-                    wx[k][2] = l2.x; wy[k][2] = l2.y; wx[k][3] = l3.x; wy[k][3] = l3.y;
-                }
-                // face normals of the wheel boxes, once per wheel instead of once per (wheel, tile) pair
-                float wnx[4][4], wny[4][4];
-                for (int k = 0; k < 4; ++k)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int i2 = (i + 1) & 3;
-                        const float ex = wx[k][i2] - wx[k][i], ey = wy[k][i2] - wy[k][i];
-                        const float len = sqrtf(ex * ex + ey * ey);
-                        wnx[k][i] = 3.0e38f; wny[k][i] = 0.f;
-                        if (!(len < 1e-12f)) { wnx[k][i] = ey / len; wny[k][i] = -ex / len; }
-                    }
-                // overlap tests, tile-major: each candidate tile is fetched once and tested against the four wheels
-                uint32_t now[4][16];
-                for (int k = 0; k < 4; ++k)
-                    for (int wd = 0; wd < 16; ++wd) now[k][wd] = 0u;
-                for (int q2 = 0; q2 < n_cand; ++q2) {
-                    const int t = cand[q2];
-                    const CarTile* Tp = tiles + t;
-                    const float2 tcen = centres[t];
-                    const float tcx = tcen.x, tcy = tcen.y;
-                    bool near_w[4], any_near = false;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float ddx = tcx - c[k + 1].x, ddy = tcy - c[k + 1].y;
-                        near_w[k] = ddx * ddx + ddy * ddy <= 9.0f * 9.0f;
-                        any_near = any_near || near_w[k];
-                    }
-                    if (!any_near) continue;
-                    float tpx[5], tpy[5], tnx[5], tny[5];
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) { tpx[i] = Tp->px[i]; tpy[i] = Tp->py[i]; tnx[i] = Tp->nx[i]; tny[i] = Tp->ny[i]; }
-                    const int tn = Tp->n;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (!near_w[k]) continue;
-                        // max(s1, s2) < 2 r  <=>  no face of either polygon separates them by 2 r or more: stop at the first that does
-                        if (!separated_by_face(wx[k], wy[k], wnx[k], wny[k], 4, tpx, tpy, tn, 2.0f * B2_POLYGON_RADIUS) &&
-                            !separated_by_face(tpx, tpy, tnx, tny, tn, wx[k], wy[k], 4, 2.0f * B2_POLYGON_RADIUS))
-                            now[k][t >> 5] |= 1u << (t & 31);
-                    }
-                }
+                const uint32_t* now = p.sensor_now + (size_t)ci * 64;
                 // contact events wheel by wheel (FrictionDetector._contact), BeginContact in ascending block id
                 for (int k = 0; k < 4; ++k) {
                     uint32_t was_w[16];
@@ -778,9 +794,15 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
 #pragma unroll
                         for (int i = 0; i < 4; ++i) { const uint4 q4 = tw[i]; was_w[4 * i] = q4.x; was_w[4 * i + 1] = q4.y; was_w[4 * i + 2] = q4.z; was_w[4 * i + 3] = q4.w; }
                     }
+                    uint32_t now_k[16];
+                    {
+                        const uint4* nw = reinterpret_cast<const uint4*>(now + 16 * k);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { const uint4 q4 = nw[i]; now_k[4 * i] = q4.x; now_k[4 * i + 1] = q4.y; now_k[4 * i + 2] = q4.z; now_k[4 * i + 3] = q4.w; }
+                    }
 #pragma unroll
                     for (int wd = 0; wd < 16; ++wd) {
-                        const uint32_t was = was_w[wd], now_w = now[k][wd];
+                        const uint32_t was = was_w[wd], now_w = now_k[wd];
                         if (now_w == was) continue;                        // nothing begins or ends in these 32 tiles
                         uint32_t begins = now_w & ~was;
                         while (begins) {
@@ -1145,7 +1167,8 @@ __global__ void car_random_actions_kernel(float* actions, int n_values, uint64_t
 }
 
 cudaError_t launch_car_reset(const CarDev& p, int only_done, cudaStream_t s) {
-    car_reset_kernel<<<(p.n + 1) / 2, 64, 0, s>>>(p, only_done);     // one warp per env
+    const int blocks = only_done ? min((p.n + 1) / 2, 296) : (p.n + 1) / 2;   // a warp per env; auto-reset: over the done list
+    car_reset_kernel<<<blocks, 64, 0, s>>>(p, only_done);
     return cudaGetLastError();
 }
 
@@ -1163,6 +1186,11 @@ cudaError_t launch_car_step(const CarDev& p, int mode, const float* actions, flo
                             uint8_t* truncated, cudaStream_t s) {
     const int n_cars = p.n * p.players;
     car_step_kernel<<<(n_cars + 63) / 64, 64, 0, s>>>(p, mode, actions, rew, done, num_steps, truncated);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_car_sensors(const CarDev& p, cudaStream_t s) {
+    car_sensor_kernel<<<(p.n * p.players * 4 + 127) / 128, 128, 0, s>>>(p);
     return cudaGetLastError();
 }
 

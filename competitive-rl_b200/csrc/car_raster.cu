@@ -83,12 +83,14 @@ __device__ __forceinline__ void hud_rect(uint8_t* img, double x, double y, doubl
 // one car polygon of the frame (screen pixels): rows [miny, miny + rows) of its span table, gray value
 struct __align__(8) PolyMeta { short miny, rows; unsigned char gray, n, pad0, pad1; };
 
-// What car_frame_setup_kernel hands to the render kernel besides the FrameMap, per frame (1344 bytes): the car polygons
-// scan-converted with pygame's fill rule, and the block-pool positions of the road-map blocks under the window.
+// What car_frame_setup_kernel hands to the render kernel besides the FrameMap, per frame (1632 bytes): the car polygons
+// scan-converted with pygame's fill rule, the block-pool positions of the road-map blocks under the window, and the
+// checker flags of the window's columns and rows (background of blocks nothing was painted in).
 struct __align__(16) FrameAux {
     short4 spans[CAR_POLYS][POLY_ROWS];
     PolyMeta meta[CAR_POLYS];
     uint16_t blk[96];                              // [j * nbx + i]: CarDev::map_index entry of block (obx + i, oby + j); 0 = nothing painted
+    uint8_t chkx[CROP_DIM], chky[CROP_DIM];        // 0xFF where column / row i of the staged window lies in a checker square (CarDev::chk)
 };
 
 struct RasterSmem {
@@ -151,14 +153,26 @@ __device__ void paint_cars(RasterSmem& S, int players, int lane) {
     }
 }
 
+// The auto-reset passes (only_done) run over the frames of the envs on the done list: position i -> frame.  The render
+// kernel of such a pass is launched with DONE_PASS_CTAS blocks that stride over the list.
+constexpr int DONE_PASS_CTAS = 148 * 6;
+__device__ __forceinline__ int listed_frames(const CarDev& p, int only_done) {
+    return only_done ? min(*p.done_count, p.n) * p.players : p.n * p.players;
+}
+__device__ __forceinline__ int listed_frame(const CarDev& p, int only_done, int i) {
+    if (!only_done) return i;
+    const int k = i / p.players;
+    return p.done_list[k] * p.players + (i - k * p.players);
+}
+
 // Per-frame setup, part 1, one thread per (env, player) frame: camera and the integer screen -> road-map mapping (a serial
 // fp64 chain that would stall a whole CTA of the render kernel).
 __global__ void __launch_bounds__(128)
 car_frame_setup_kernel(CarDev p, int only_done, int which) {
-    const int frame = blockIdx.x * blockDim.x + threadIdx.x;       // env * players + player
-    if (frame >= p.n * p.players) return;
+    int frame = blockIdx.x * blockDim.x + threadIdx.x;             // env * players + player; auto-reset pass: position on the done list
+    if (frame >= listed_frames(p, only_done)) return;
+    frame = listed_frame(p, only_done, frame);
     const int e = frame / p.players;
-    if (only_done && !p.env_done[e]) return;
     if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
     const CarHullConst* K = p.consts;
     const double obs_scale = car_obs_scale();
@@ -218,10 +232,11 @@ car_frame_setup_kernel(CarDev p, int only_done, int which) {
 __global__ void __launch_bounds__(128, 8)
 car_frame_aux_kernel(CarDev p, int only_done, int which) {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const int frame = gt >> 4, l = gt & 15;
-    if (frame >= p.n * p.players) return;
+    int frame = gt >> 4;
+    const int l = gt & 15;
+    if (frame >= listed_frames(p, only_done)) return;
+    frame = listed_frame(p, only_done, frame);
     const int e = frame / p.players, pi = frame - e * p.players;
-    if (only_done && !p.env_done[e]) return;
     if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
     const CarHullConst* K = p.consts;
     const double obs_scale = car_obs_scale();
@@ -239,6 +254,13 @@ car_frame_aux_kernel(CarDev p, int only_done, int which) {
             if ((unsigned)gx < (unsigned)CAR_MAP_GRID && (unsigned)gy < (unsigned)CAR_MAP_GRID) idx = index[gy * CAR_MAP_GRID + gx];
             aux->blk[bq] = (uint16_t)(idx == 0xFFFFu ? 0u : idx);   // a dropped block (flagged when painted) shows the background
         }
+    }
+    // ---- checker flags of the window's columns and rows: 16-byte pieces, lanes 0..8 the columns, the rest + a second round the rows ----
+    for (int t = l; t < 2 * CROP_BLOCKS; t += 16) {
+        const int axis = t >= CROP_BLOCKS, k = axis ? t - CROP_BLOCKS : t, g = (axis ? m.oby : m.obx) + k;
+        uint4 f = make_uint4(0u, 0u, 0u, 0u);
+        if ((unsigned)g < (unsigned)CAR_MAP_GRID) f = __ldg(reinterpret_cast<const uint4*>(p.chk + axis * 2048) + g);
+        *reinterpret_cast<uint4*>((axis ? aux->chky : aux->chkx) + k * 16) = f;
     }
     // ---- car polygon l = car * 8 + part: parts 0..3 the wheels, 4..7 the hull fixtures ----
     PolyMeta pm;
@@ -336,11 +358,19 @@ __global__ void __launch_bounds__(RASTER_THREADS, 6)
 car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs, uint8_t* __restrict__ term_obs) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
-    const int frame = blockIdx.x;                     // env * players + player
-    const int e = (p.players == 2) ? frame >> 1 : frame;          // players is 1 or 2
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (only_done && !p.env_done[e]) return;
-    if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
+    const int n_listed = listed_frames(p, only_done);
+  for (int it = blockIdx.x; it < n_listed; it += gridDim.x) {        // a post-step pass has one CTA per frame: a single round
+    const int frame = listed_frame(p, only_done, it);  // env * players + player
+    const int e = (p.players == 2) ? frame >> 1 : frame;          // players is 1 or 2
+    if (which != 0 && (p.deferred[e] != 0) != (which == 2)) continue;
+    if (tid == 0 && (p.players == 1 || (frame & 1) == 0)) {
+        if (only_done) p.ring_pos[e] = p.c - 1;        // every ring slot holds the reset frame (nobody reads ring_pos in this pass)
+        else if (p.collect_done && p.env_done[e]) {    // finished in this step: onto the list the auto-reset passes run over
+            const int k = atomicAdd(p.done_count, 1);
+            if (k < p.n) p.done_list[k] = e;
+        }
+    }
     const CarHullConst* K = p.consts;
     const uint8_t* G = K->gray;
     const FrameMap fm = p.frame_map[frame];           // written by car_frame_setup_kernel
@@ -382,32 +412,32 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
         S.hud_vals[k] = v;
     }
     __syncthreads();
-    // ---- the road map under the window: 16 threads per 16 x 16 block, one 16-byte row each; where nothing was painted
-    //      (no block, or outside the slot's grid) the row is the background: grass / checker squares ----
-    {
+    // ---- three jobs side by side.  Warp 0 paints the car polygons (the walk below keeps them); warp HUD_WARP the HUD bar --
+    //      rows 86..95, which the walk never writes; the six other warps stage the road map under the window: 16 threads per
+    //      16 x 16 block, one 16-byte row each; where nothing was painted (no block, or outside the slot's grid) the row is
+    //      the background: grass / checker squares ----
+    if (warp == 0) paint_cars(S, p.players, lane);
+    else if (warp != HUD_WARP) {
         const uint4* blocks = reinterpret_cast<const uint4*>(p.map_blocks + (size_t)slot * CAR_MAP_MAX_BLOCKS * 256);
-        const int nb = fm.nbx * (fm.nby_mul & 255), sub = tid & 15, mul = fm.nby_mul >> 8;
+        const int st = tid - 32 - (warp > HUD_WARP ? 32 : 0);       // 0..191 over warps 1-4, 6, 7
+        const int nb = fm.nbx * (fm.nby_mul & 255), sub = st & 15, mul = fm.nby_mul >> 8;
         const uint32_t grass4 = 0x01010101u * G[G_GRASS], check4 = 0x01010101u * G[G_CHECK];
 #pragma unroll 2
-        for (int bq = tid >> 4; bq < nb; bq += RASTER_THREADS / 16) {
+        for (int bq = st >> 4; bq < nb; bq += 12) {
             const int j = (bq * mul) >> 10, i = bq - j * fm.nbx;
             const unsigned int idx = S.aux.blk[bq];
             uint4 v;
             if (idx != 0u) v = blocks[(idx - 1u) * 16 + sub];
             else {
-                const int gx = fm.obx + i, gy = fm.oby + j;
-                if ((unsigned)gx < (unsigned)CAR_MAP_GRID && (unsigned)gy < (unsigned)CAR_MAP_GRID) {
-                    const int my = gy * 16 + sub;
-                    v = make_uint4(road_bg_word(p.chk, gx, my, 0, grass4, check4), road_bg_word(p.chk, gx, my, 1, grass4, check4),
-                                   road_bg_word(p.chk, gx, my, 2, grass4, check4), road_bg_word(p.chk, gx, my, 3, grass4, check4));
-                } else v = make_uint4(grass4, grass4, grass4, grass4);  // the checker squares end well inside the window
+                uint4 f = *reinterpret_cast<const uint4*>(S.aux.chkx + i * 16);
+                const uint32_t fy = S.aux.chky[j * 16 + sub] ? 0xFFFFFFFFu : 0u;
+                f.x &= fy; f.y &= fy; f.z &= fy; f.w &= fy;
+                v = make_uint4((f.x & check4) | (~f.x & grass4), (f.y & check4) | (~f.y & grass4), (f.z & check4) | (~f.z & grass4),
+                               (f.w & check4) | (~f.w & grass4));
             }
             *reinterpret_cast<uint4*>(S.crop + (j * 16 + sub) * CROP_DIM + i * 16) = v;
         }
     }
-    // ---- meanwhile: warp 0 paints the car polygons (the walk below keeps them), warp HUD_WARP the HUD bar -- rows 86..95,
-    //      which the walk never writes -- and a finished env's terminal observation gets its older frames ----
-    if (warp == 0) paint_cars(S, p.players, lane);
     uint8_t* img = S.img;
     __syncwarp();
     if (warp == HUD_WARP) {
@@ -477,6 +507,8 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
             if (tdst) tdst[q] = vv;
         }
     }
+    __syncthreads();                                   // the shared-memory frame is reused by the next round
+  }
 }
 
 // FrameStack in stack mode (atari_wrappers.py:222-259): the observation is the C newest frames, oldest first.  The C - 1
@@ -515,14 +547,10 @@ __global__ void __launch_bounds__(256) car_stack_shift_kernel(CarDev p, uint8_t*
     }
 }
 
-__global__ void car_ring_advance_kernel(CarDev p, int only_done) {
+__global__ void car_ring_advance_kernel(CarDev p) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= p.n) return;
-    if (only_done) {
-        if (p.env_done[e]) p.ring_pos[e] = p.c - 1;
-    } else {
-        p.ring_pos[e] = p.ring_pos[e] < 0 ? p.c - 1 : (p.ring_pos[e] + 1) % p.c;
-    }
+    p.ring_pos[e] = p.ring_pos[e] < 0 ? p.c - 1 : (p.ring_pos[e] + 1) % p.c;
 }
 
 // road-map bounds of the checker squares: for even grid cells g = -20 + 2i the square polygon
@@ -558,10 +586,12 @@ cudaError_t launch_car_render(const CarDev& p, int only_done, int which, int adv
     car_frame_aux_kernel<<<(p.n * p.players * 16 + 127) / 128, 128, 0, s>>>(p, only_done, which);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    car_render_kernel<<<p.n * p.players, RASTER_THREADS, sizeof(RasterSmem), s>>>(p, only_done, which, obs, term_obs);
+    const int ctas = only_done ? min(p.n * p.players, DONE_PASS_CTAS) : p.n * p.players;
+    car_render_kernel<<<ctas, RASTER_THREADS, sizeof(RasterSmem), s>>>(p, only_done, which, obs, term_obs);
     e = cudaGetLastError();
-    if (e != cudaSuccess || !advance || p.ring_mode) return e;   // ring mode: the phase is advanced on the host, per step
-    car_ring_advance_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p, only_done);
+    // ring mode: the phase is advanced on the host, per step; an auto-reset pass sets ring_pos itself
+    if (e != cudaSuccess || !advance || p.ring_mode || only_done) return e;
+    car_ring_advance_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -313,7 +313,7 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     ALLOC(d.step_count, n); ALLOC(d.elapsed, n); ALLOC(d.reset_count, n);
     ALLOC(d.attempt_count, n); ALLOC(d.inv_dt0, n); ALLOC(d.env_done, n); ALLOC(d.ring_pos, n);
     ALLOC(d.body, nc * 40); ALLOC(d.joint, nc * 24); ALLOC(d.wheel, nc * 8); ALLOC(d.reward, nc * 2);
-    ALLOC(d.counters, nc * 4); ALLOC(d.touching, nc * 64); ALLOC(d.visited, nc * 16);
+    ALLOC(d.counters, nc * 4); ALLOC(d.touching, nc * 64); ALLOC(d.visited, nc * 16); ALLOC(d.sensor_now, nc * 64);
     if (!d.ring_mode) ALLOC(d.ring, nc * d.c * CAR_PIX);
     ALLOC(d.overrun, 4); ALLOC(d.stats, 8);
     ALLOC(d.contact_overflow, 1);
@@ -328,6 +328,7 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     ALLOC(h->actions_stage, nc * 2); ALLOC(h->rew_stage, nc); ALLOC(h->done_stage, n); ALLOC(h->steps_stage, n); ALLOC(h->trunc_stage, n);
     if (P == 2) { ALLOC(d.contacts, n * CAR_MAX_CONTACTS); ALLOC(d.n_contacts, n); ALLOC(d.slow_list, n); ALLOC(d.slow_count, 1); }
     ALLOC(d.deferred, n);
+    ALLOC(d.done_list, n); ALLOC(d.done_count, 1);
     CarHullConst* kdev = nullptr;
     ALLOC(kdev, 1);
 #undef ALLOC
@@ -455,6 +456,7 @@ int crl_car_step_state(crl_car* h, const float* actions_dev, float* rew_dev, uin
     if (!actions_dev || !rew_dev || !done_dev || !num_steps_dev || !truncated_dev) return crl_set_error(CRL_E_INVALID, "null step buffer");
     h->dev.fill_all = 0;
     if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
+    LAUNCH(launch_car_sensors(h->dev, (cudaStream_t)stream), 1);
     LAUNCH(launch_car_step(h->dev, 0, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, (cudaStream_t)stream), 1);
     return CRL_OK;
 }
@@ -465,9 +467,12 @@ int crl_car_render_obs(crl_car* h, uint8_t* obs_dev, uint8_t* term_obs_dev, void
     if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
     cudaStream_t s = (cudaStream_t)stream;
     if (!h->dev.ring_mode && h->dev.c >= 2) LAUNCH(launch_car_stack_shift(h->dev, obs_dev, s), 1);   // the frames that stay: ring -> obs
+    CUDA_TRY(cudaMemsetAsync(h->dev.done_count, 0, sizeof(int32_t), s));
+    h->dev.collect_done = 1;
     LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, term_obs_dev, s), 4);   // post-step frame (terminal obs of finished envs)
+    h->dev.collect_done = 0;
     LAUNCH(launch_car_reset(h->dev, 1, s), 1);                                 // auto-reset of finished envs
-    LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 4);        // their reset observation
+    LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 3);        // their reset observation
     return kick_pregen(h, s);
 }
 
@@ -481,9 +486,12 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
         if (int r = fork_stack_shift(h, obs_dev, s1)) return r;                    // under the physics pass
         if (int r = crl_car_step_state(h, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, stream)) return r;
         if (int r = join_stack_shift(h, s1)) return r;
+        CUDA_TRY(cudaMemsetAsync(h->dev.done_count, 0, sizeof(int32_t), s1));
+        h->dev.collect_done = 1;
         LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, term_obs_dev, s1), 4);   // post-step frame (terminal obs of finished envs)
+        h->dev.collect_done = 0;
         LAUNCH(launch_car_reset(h->dev, 1, s1), 1);                                 // auto-reset of finished envs
-        LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s1), 4);        // their reset observation
+        LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s1), 3);        // their reset observation
         return kick_pregen(h, s1);
     }
     // Two-car envs.  The step kernel is one wave of latency-bound threads; lane pairs whose cars touch run the sequential
@@ -504,17 +512,21 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
     if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
     if (int r = fork_stack_shift(h, obs_dev, s)) return r;                        // under the fast physics pass
     CUDA_TRY(cudaMemsetAsync(h->dev.slow_count, 0, sizeof(int32_t), s));
+    CUDA_TRY(cudaMemsetAsync(h->dev.done_count, 0, sizeof(int32_t), s));
+    LAUNCH(launch_car_sensors(h->dev, s), 1);
     LAUNCH(launch_car_step(h->dev, 1, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, s), 1);
     CUDA_TRY(cudaEventRecord(h->ev_fast, s));
     CUDA_TRY(cudaStreamWaitEvent(h->side_stream, h->ev_fast, 0));
     LAUNCH(launch_car_step(h->dev, 2, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, h->side_stream), 1);
     CUDA_TRY(cudaEventRecord(h->ev_slow, h->side_stream));
     if (int r = join_stack_shift(h, s)) return r;
+    h->dev.collect_done = 1;
     LAUNCH(launch_car_render(h->dev, 0, 1, 0, obs_dev, term_obs_dev, s), 3);   // frames of the envs stepped by the fast pass
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_slow, 0));
     LAUNCH(launch_car_render(h->dev, 0, 2, 1, obs_dev, term_obs_dev, s), 4);   // frames of the listed envs; ring moves on
+    h->dev.collect_done = 0;
     LAUNCH(launch_car_reset(h->dev, 1, s), 1);                                 // auto-reset of finished envs
-    LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 4);        // their reset observation
+    LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 3);        // their reset observation
     return kick_pregen(h, s);
 }
 
