@@ -167,13 +167,15 @@ __device__ __forceinline__ int car_slot(const CarDev& p, int e) { return e + p.n
 cudaError_t launch_car_reset(const CarDev& p, int only_done, cudaStream_t s);
 cudaError_t launch_car_pregen(const CarDev& p, cudaStream_t s);        // next tracks of the envs that have none (side stream)
 cudaError_t launch_car_discard_next(const CarDev& p, cudaStream_t s);  // forget pre-generated tracks (seed / injection changed)
-cudaError_t launch_car_sensors(const CarDev& p, cudaStream_t s);      // wheel-tile overlaps, before launch_car_step
+// wheel-tile overlaps, before launch_car_step; classify = 1: also the slow list of the two-pass schedule (slow_count cleared before)
+cudaError_t launch_car_sensors(const CarDev& p, int classify, cudaStream_t s);
 cudaError_t launch_car_step(const CarDev& p, int mode, const float* actions, float* rew, uint8_t* done, int32_t* num_steps,
                             uint8_t* truncated, cudaStream_t s);
 // which: 0 = every frame, 1 = envs not deferred to the slow stepping pass, 2 = deferred envs only; advance: move the frame ring on
 cudaError_t launch_car_render(const CarDev& p, int only_done, int which, int advance, uint8_t* obs, uint8_t* term_obs, cudaStream_t s);
 // stack mode: the C - 1 frames that stay in the observation, ring -> obs; before the render passes of a step (not after a reset)
 cudaError_t launch_car_stack_shift(const CarDev& p, uint8_t* obs, cudaStream_t s);
+cudaError_t launch_car_ring_advance(const CarDev& p, cudaStream_t s);
 cudaError_t car_raster_init();
 size_t car_frame_map_bytes();
 size_t car_frame_aux_bytes();

@@ -601,7 +601,7 @@ __device__ void sensor_wheel_overlaps(const CarDev& p, int slot, int n_track, F2
 // The tile-sensor overlaps of every wheel at the start of world.Step, one thread per (car, wheel), ahead of the step
 // kernel: they depend only on the poses the previous step left behind, and one thread per car would walk its four
 // wheels' candidates one after the other on the step's critical path.
-__global__ void __launch_bounds__(128) car_sensor_kernel(CarDev p) {
+__global__ void __launch_bounds__(128) car_sensor_kernel(CarDev p, int classify) {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int ci = gt >> 2, k = gt & 3;
     if (ci >= p.n * p.players) return;
@@ -610,6 +610,14 @@ __global__ void __launch_bounds__(128) car_sensor_kernel(CarDev p) {
     const Rot qh = make_rot(b[2]);
     const F2 hp = f2(b[0], b[1]) - rmul(qh, f2(p.consts->hull_lcx, p.consts->hull_lcy));
     const int slot = car_slot(p, e);
+    // two-car envs, two-pass stepping: the env whose cars are near each other goes on the slow list (see car_step_kernel)
+    if (classify && p.players == 2 && (gt & 7) == 0) {
+        const float* b1 = b + 40;
+        const float pose[10][3] = {{b[0], b[1], b[2]}, {}, {}, {}, {}, {b1[0], b1[1], b1[2]}, {}, {}, {}, {}};
+        const bool deferred = cars_near(pose, p.consts->hull_lcx, p.consts->hull_lcy, p.step_count[e]);
+        if (deferred) p.slow_list[atomicAdd(p.slow_count, 1)] = e;
+        p.deferred[e] = deferred ? 1 : 0;
+    }
     sensor_wheel_overlaps(p, slot, p.n_track[slot], hp, f2(b[8 * (k + 1)], b[8 * (k + 1) + 1]), b[8 * (k + 1) + 2],
                           p.sensor_now + ((size_t)ci * 4 + k) * 16);
 }
@@ -618,9 +626,10 @@ __device__ __noinline__ void sensor_car_overlaps(const CarDev& p, int ci, int sl
     for (int k = 0; k < 4; ++k) sensor_wheel_overlaps(p, slot, n_track, hp, c[k + 1], a[k + 1], p.sensor_now + ((size_t)ci * 4 + k) * 16);
 }
 
-// mode 0: every car.  mode 1 (fast pass): two-car envs whose cars are near each other are only put on p.slow_list
-// (p.deferred[env] = 1) -- their contact solve is several times longer than a plain step and would hold up the whole
-// single-wave launch.  mode 2 (slow pass): the envs on p.slow_list, two lanes each.
+// mode 0: every car.  mode 1 (fast pass): two-car envs whose cars are near each other are skipped: car_sensor_kernel put
+// them on p.slow_list (p.deferred[env] = 1) -- their contact solve is several times longer than a plain step and would
+// hold up the whole single-wave launch.  mode 2 (slow pass): the envs on p.slow_list, two lanes each; the two passes
+// touch disjoint envs and run side by side on two streams.
 __global__ void __launch_bounds__(64)
 car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __restrict__ rew, uint8_t* __restrict__ done_out,
                 int32_t* __restrict__ num_steps_out, uint8_t* __restrict__ truncated_out) {
@@ -645,15 +654,8 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
     float (*vel)[3] = sh_vel[threadIdx.x >> 1];
     bool deferred = false;
     if (active && p.players == 2 && mode != 2) {
-        if (mode == 1) {
-            const float* hb = p.body + (size_t)ci * 40;
-            pose[player * 5][0] = hb[0]; pose[player * 5][1] = hb[1]; pose[player * 5][2] = hb[2];
-            __syncwarp(pair_mask);
-            deferred = cars_near(pose, p.consts->hull_lcx, p.consts->hull_lcy, p.step_count[e]);
-            if (deferred && player == 0) p.slow_list[atomicAdd(p.slow_count, 1)] = e;
-            __syncwarp(pair_mask);
-        }
-        if (player == 0) p.deferred[e] = deferred ? 1 : 0;
+        if (mode == 1) deferred = p.deferred[e] != 0;       // decided by car_sensor_kernel from the poses at the start of the step
+        else if (player == 0) p.deferred[e] = 0;
     }
     active = active && !deferred;
     const unsigned warp_lanes = __ballot_sync(0xffffffffu, active);   // the lanes that run the per-car pipeline
@@ -1189,8 +1191,8 @@ cudaError_t launch_car_step(const CarDev& p, int mode, const float* actions, flo
     return cudaGetLastError();
 }
 
-cudaError_t launch_car_sensors(const CarDev& p, cudaStream_t s) {
-    car_sensor_kernel<<<(p.n * p.players * 4 + 127) / 128, 128, 0, s>>>(p);
+cudaError_t launch_car_sensors(const CarDev& p, int classify, cudaStream_t s) {
+    car_sensor_kernel<<<(p.n * p.players * 4 + 127) / 128, 128, 0, s>>>(p, classify);
     return cudaGetLastError();
 }
 

@@ -513,37 +513,41 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
 
 // FrameStack in stack mode (atari_wrappers.py:222-259): the observation is the C newest frames, oldest first.  The C - 1
 // frames that stay are already known before the step: this kernel moves them from the internal ring to channels
-// 0 .. C-2 of every (env, player) -- pure bandwidth, so crl_car_step runs it on a side stream under the latency-bound
-// physics pass -- and the render kernel then only writes the new frame (ring slot + channel C-1).  Envs that were just
+// 0 .. C-2 of every (env, player), and the render kernel then only writes the new frame (ring slot + channel C-1).  It is
+// pure DRAM traffic, and it neither reads what the render passes of the step write (the ring slot of the new frame is the
+// one slot it does not read) nor writes what they write, so crl_car_step runs it on a side stream NEXT TO the main render
+// pass, which is bound by instruction issue: a small persistent grid (two 192-thread blocks per SM, six 16-byte loads
+// in flight per thread) that leaves the registers and shared memory of the SMs to the render CTAs.  Envs that were just
 // reset (ring_pos < 0) are skipped: their first render fills every channel.
-__global__ void __launch_bounds__(256) car_stack_shift_kernel(CarDev p, uint8_t* __restrict__ obs) {
-    constexpr int FRAME_V = CAR_PIX / 16;                           // uint4 per frame: 576
-    const int C = p.c, per_frame = (C - 1) * FRAME_V;
-    const size_t total = (size_t)p.n * p.players * per_frame;
+constexpr int SHIFT_THREADS = 192, SHIFT_FRAME_V = CAR_PIX / 16;    // 576 uint4 per frame = 3 per thread
+__global__ void __launch_bounds__(SHIFT_THREADS) car_stack_shift_kernel(CarDev p, uint8_t* __restrict__ obs) {
+    const int C = p.c, n_units = p.n * p.players * (C - 1);         // unit = one frame that stays: (env, player, channel)
     const uint4* ring = reinterpret_cast<const uint4*>(p.ring);
     uint4* out = reinterpret_cast<uint4*>(obs);
-    for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x); i0 < total; i0 += (size_t)gridDim.x * blockDim.x * 4) {
-        uint4 v[4];
-        size_t dst[4];
+    for (int u0 = blockIdx.x; u0 < n_units; u0 += 2 * gridDim.x) {
+        uint4 v[2][3];
+        size_t dst[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const size_t i = i0 + (size_t)k * gridDim.x * blockDim.x;
+        for (int k = 0; k < 2; ++k) {
+            const int u = u0 + k * gridDim.x;
             dst[k] = (size_t)-1;
-            if (i < total) {
-                const int frame = (int)(i / per_frame), r = (int)(i - (size_t)frame * per_frame);
-                const int sl = r / FRAME_V, q = r - sl * FRAME_V;
+            if (u < n_units) {
+                const int frame = u / (C - 1), sl = u - frame * (C - 1);
                 const int pos = p.ring_pos[p.players == 2 ? frame >> 1 : frame];
                 if (pos >= 0) {
                     int rs = pos + 2 + sl;                          // the slot after the one the new frame will take = the oldest that stays
-                    rs -= (rs >= C) ? C : 0; rs -= (rs >= C) ? C : 0;
-                    v[k] = ring[((size_t)frame * C + rs) * FRAME_V + q];
-                    dst[k] = ((size_t)frame * C + sl) * FRAME_V + q;
+                    rs -= (rs >= C) ? C : 0;
+                    const uint4* src = ring + ((size_t)frame * C + rs) * SHIFT_FRAME_V + threadIdx.x;
+                    v[k][0] = __ldcs(src); v[k][1] = __ldcs(src + SHIFT_THREADS); v[k][2] = __ldcs(src + 2 * SHIFT_THREADS);
+                    dst[k] = ((size_t)frame * C + sl) * SHIFT_FRAME_V + threadIdx.x;
                 }
             }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (dst[k] != (size_t)-1) out[dst[k]] = v[k];
+        for (int k = 0; k < 2; ++k)
+            if (dst[k] != (size_t)-1) {
+                __stcs(out + dst[k], v[k][0]); __stcs(out + dst[k] + SHIFT_THREADS, v[k][1]); __stcs(out + dst[k] + 2 * SHIFT_THREADS, v[k][2]);
+            }
     }
 }
 
@@ -575,9 +579,15 @@ cudaError_t car_raster_init() {
 
 cudaError_t launch_car_stack_shift(const CarDev& p, uint8_t* obs, cudaStream_t s) {
     if (p.ring_mode || p.c < 2) return cudaSuccess;
-    const size_t total = (size_t)p.n * p.players * (p.c - 1) * (CAR_PIX / 16);
-    const int blocks = (int)((total + 256 * 4 - 1) / (256 * 4));
-    car_stack_shift_kernel<<<blocks, 256, 0, s>>>(p, obs);
+    const int n_units = p.n * p.players * (p.c - 1);
+    car_stack_shift_kernel<<<min((n_units + 1) / 2, 2 * 148), SHIFT_THREADS, 0, s>>>(p, obs);
+    return cudaGetLastError();
+}
+
+// stack mode: the frame ring moves on by one slot (after the render passes AND the stack shift of the step, which read ring_pos)
+cudaError_t launch_car_ring_advance(const CarDev& p, cudaStream_t s) {
+    if (p.ring_mode) return cudaSuccess;                        // ring mode: the phase is advanced on the host, per step
+    car_ring_advance_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -229,7 +229,7 @@ int discard_pregen(crl_car* h, cudaStream_t s) {
 }
 
 // Stack mode: start moving the frames that stay in the observation (ring -> channels 0 .. C-2 of obs) on the copy stream,
-// behind everything queued on `s` so far; join_stack_shift makes `s` wait for it (before the first render pass).
+// behind everything queued on `s` so far; join_stack_shift makes `s` wait for it (before the auto-reset pass).
 int fork_stack_shift(crl_car* h, uint8_t* obs_dev, cudaStream_t s) {
     if (h->dev.ring_mode || h->dev.c < 2) return CRL_OK;
     if (!h->copy_stream) {
@@ -456,7 +456,7 @@ int crl_car_step_state(crl_car* h, const float* actions_dev, float* rew_dev, uin
     if (!actions_dev || !rew_dev || !done_dev || !num_steps_dev || !truncated_dev) return crl_set_error(CRL_E_INVALID, "null step buffer");
     h->dev.fill_all = 0;
     if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
-    LAUNCH(launch_car_sensors(h->dev, (cudaStream_t)stream), 1);
+    LAUNCH(launch_car_sensors(h->dev, 0, (cudaStream_t)stream), 1);
     LAUNCH(launch_car_step(h->dev, 0, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, (cudaStream_t)stream), 1);
     return CRL_OK;
 }
@@ -483,21 +483,23 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
         if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
         if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
         cudaStream_t s1 = (cudaStream_t)stream;
-        if (int r = fork_stack_shift(h, obs_dev, s1)) return r;                    // under the physics pass
         if (int r = crl_car_step_state(h, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, stream)) return r;
-        if (int r = join_stack_shift(h, s1)) return r;
+        if (int r = fork_stack_shift(h, obs_dev, s1)) return r;                    // next to the render pass
         CUDA_TRY(cudaMemsetAsync(h->dev.done_count, 0, sizeof(int32_t), s1));
         h->dev.collect_done = 1;
-        LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, term_obs_dev, s1), 4);   // post-step frame (terminal obs of finished envs)
+        LAUNCH(launch_car_render(h->dev, 0, 0, 0, obs_dev, term_obs_dev, s1), 3);   // post-step frame (terminal obs of finished envs)
         h->dev.collect_done = 0;
+        if (int r = join_stack_shift(h, s1)) return r;                             // it reads ring_pos; the auto-reset pass rewrites whole stacks
+        LAUNCH(launch_car_ring_advance(h->dev, s1), 1);
         LAUNCH(launch_car_reset(h->dev, 1, s1), 1);                                 // auto-reset of finished envs
         LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s1), 3);        // their reset observation
         return kick_pregen(h, s1);
     }
     // Two-car envs.  The step kernel is one wave of latency-bound threads; lane pairs whose cars touch run the sequential
-    // contact solver and take several times longer than the rest.  So: fast pass over the envs whose cars are apart
-    // (the others are only listed), then the listed envs on a side stream WHILE the main stream renders the fast ones,
-    // then the frames of the listed envs.  Per env nothing changes; only the launch schedule does.
+    // contact solver and take several times longer than the rest.  So the sensor kernel lists the envs whose cars are near
+    // each other, the listed envs are stepped on a side stream (slow pass) WHILE the main stream steps the others (fast
+    // pass) and renders their frames; the frames of the listed envs follow.  Per env nothing changes; only the launch
+    // schedule does.  The frames that stay in the observation stack move ring -> obs on a third stream meanwhile.
     if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
     if (!actions_dev || !obs_dev || !rew_dev || !done_dev || !num_steps_dev || !truncated_dev) return crl_set_error(CRL_E_INVALID, "null step buffer");
     cudaStream_t s = (cudaStream_t)stream;
@@ -510,21 +512,24 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
     }
     h->dev.fill_all = 0;
     if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
-    if (int r = fork_stack_shift(h, obs_dev, s)) return r;                        // under the fast physics pass
     CUDA_TRY(cudaMemsetAsync(h->dev.slow_count, 0, sizeof(int32_t), s));
     CUDA_TRY(cudaMemsetAsync(h->dev.done_count, 0, sizeof(int32_t), s));
-    LAUNCH(launch_car_sensors(h->dev, s), 1);
-    LAUNCH(launch_car_step(h->dev, 1, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, s), 1);
+    LAUNCH(launch_car_sensors(h->dev, 1, s), 1);                               // wheel-tile overlaps + the slow list
     CUDA_TRY(cudaEventRecord(h->ev_fast, s));
     CUDA_TRY(cudaStreamWaitEvent(h->side_stream, h->ev_fast, 0));
     LAUNCH(launch_car_step(h->dev, 2, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, h->side_stream), 1);
     CUDA_TRY(cudaEventRecord(h->ev_slow, h->side_stream));
-    if (int r = join_stack_shift(h, s)) return r;
+    LAUNCH(launch_car_step(h->dev, 1, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, s), 1);
+    // the frames that stay in the stack: ring -> obs, next to the render passes (DRAM-bound beside issue-bound; the step
+    // kernels before it fill the register files, so it is not started under them)
+    if (int r = fork_stack_shift(h, obs_dev, s)) return r;
     h->dev.collect_done = 1;
     LAUNCH(launch_car_render(h->dev, 0, 1, 0, obs_dev, term_obs_dev, s), 3);   // frames of the envs stepped by the fast pass
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_slow, 0));
-    LAUNCH(launch_car_render(h->dev, 0, 2, 1, obs_dev, term_obs_dev, s), 4);   // frames of the listed envs; ring moves on
+    LAUNCH(launch_car_render(h->dev, 0, 2, 0, obs_dev, term_obs_dev, s), 3);   // frames of the listed envs
     h->dev.collect_done = 0;
+    if (int r = join_stack_shift(h, s)) return r;                             // it reads ring_pos; the auto-reset pass rewrites whole stacks
+    LAUNCH(launch_car_ring_advance(h->dev, s), 1);
     LAUNCH(launch_car_reset(h->dev, 1, s), 1);                                 // auto-reset of finished envs
     LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 3);        // their reset observation
     return kick_pregen(h, s);
