@@ -707,10 +707,23 @@ pong_raster_quad_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
         }
 
         // ======== scoreboard rows of this frame's score pair(s), when the buffer holds another pair's ========
-        if (reload_text) {
-            uint32_t* d32 = reinterpret_cast<uint32_t*>(sm8);
-            for (int i = sub; i < text_words; i += 8) d32[i] = te[i];
-            cur_text = text_id;
+        if (__any_sync(0xffffffffu, reload_text)) {
+            // The four frames of a quad are the four stack slots of one env (frame_stack 4): nearly always one score pair.
+            // Then the entry is fetched once by the whole warp (3 words per lane instead of 10 per lane of every group)
+            // and stored into the four frame buffers.
+            const int id0 = __shfl_sync(0xffffffffu, text_id, 0);
+            if (__all_sync(0xffffffffu, valid && text_id == id0)) {
+                uint32_t* q32 = reinterpret_cast<uint32_t*>(smq);
+                for (int i = lane; i < text_words; i += 32) {
+                    const uint32_t w = te[i];
+                    q32[i] = w; q32[DW + i] = w; q32[2 * DW + i] = w; q32[3 * DW + i] = w;
+                }
+                cur_text = text_id;
+            } else if (reload_text) {
+                uint32_t* d32 = reinterpret_cast<uint32_t*>(sm8);
+                for (int i = sub; i < text_words; i += 8) d32[i] = te[i];
+                cur_text = text_id;
+            }
         }
         __syncwarp();
 #pragma unroll
