@@ -379,6 +379,44 @@ def test_autoreset_frame_matches_oracle():
     envs.close()
 
 
+@pytest.mark.parametrize("stack_mode", ["stack", "ring"])
+def test_mass_autoreset_runs_over_the_done_list(stack_mode):
+    """Every env of a batch finishing in the same step (synchronous TimeLimit): the auto-reset passes run over the done
+    list with grids smaller than the list (2048 frames here, 888 render CTAs), so the strided rounds are exercised.
+    Each env must come back with its reset frame in every stack slot, on a new track, and a twin batch that reaches the
+    same point step by step through two smaller shards must agree bit for bit."""
+    N, L = 1024, 5
+    kw = dict(seed=21, max_episode_steps=L, stack_mode=stack_mode)
+    whole = _make("cCarRacingDouble-v0", N, **kw)
+    lo = _make("cCarRacingDouble-v0", 8, first_env=0, **kw)
+    hi = _make("cCarRacingDouble-v0", 8, first_env=N - 8, **kw)
+    whole.reset(); lo.reset(); hi.reset()
+    tracks0 = [whole.get_track(e) for e in (0, N - 1)]
+    a = torch.zeros((N, 2, 2), device="cuda")
+    a[:, :, 1] = 0.3
+    a[:, 0, 0] = 0.1
+    for t in range(L + 3):
+        o, r, d, info = whole.step(a)
+        ol, _, dl, _ = lo.step(a[:8])
+        oh, _, dh, _ = hi.step(a[N - 8:])
+        flat = lambda x: x.flatten(1, 2) if x.dim() == 5 else x      # ring mode keeps the player axis  # noqa: E731
+        o, ol, oh = flat(o), flat(ol), flat(oh)
+        assert torch.equal(o[:8], ol) and torch.equal(o[N - 8:], oh), t
+        assert bool(d.all()) == (t == L - 1) and torch.equal(d[:8], dl) and torch.equal(d[N - 8:], dh)
+        if t == L - 1:                                               # the step that ended every episode
+            assert torch.equal(o[:, 0], o[:, 3]) and torch.equal(o[:, 1], o[:, 3]) and torch.equal(o[:, 4], o[:, 7])
+            assert int(o[:, 3].float().std(dim=(1, 2)).min() > 0)       # a real frame in every env
+            term = flat(info.terminal_observation())
+            assert not torch.equal(term[:, 3], o[:, 3])
+            for k, e in enumerate((0, N - 1)):
+                tr = whole.get_track(e)
+                assert len(tr) != len(tracks0[k]) or not np.array_equal(tr, tracks0[k])
+    assert int(whole.episode_stats()["episodes"]) == N
+    for e in (whole, lo, hi):
+        e.check()
+        e.close()
+
+
 def test_car_sharding_invariance():
     """Tracks and spawn order come from an RNG keyed by the GLOBAL env index, and nothing in a step crosses envs: two
     shards of 128 two-car envs reproduce one batch of 256 bit for bit -- states, rewards, dones, contacts, frames
