@@ -551,7 +551,9 @@ __device__ __forceinline__ bool cars_near(const float (*pose)[3], float hull_lcx
 // b2ContactManager::Collide for the tile sensors of ONE wheel: the road tiles whose fixture overlaps the wheel box (SAT
 // with the b2_polygonRadius skins), as a 512-bit set in now16[16] (global memory).  Candidates: every 8th track point
 // within 36 units of the hull (transposed array: coalesced), then tile centres within 11.5 of the hull and 9 of the wheel.
-__device__ void sensor_wheel_overlaps(const CarDev& p, int slot, int n_track, F2 hp, F2 wc, float wa, uint32_t* __restrict__ now16) {
+// `near_samples`: bit s set = track point 8 s lies within 36 units of the hull (0 = not known: scanned here).
+__device__ void sensor_wheel_overlaps(const CarDev& p, int slot, int n_track, F2 hp, F2 wc, float wa, uint32_t* __restrict__ now16,
+                                      unsigned long long near_samples, bool have_near) {
     const CarTile* tiles = p.tiles + (size_t)slot * CAR_MAX_TRACK;
     const float2* centres = p.tile_centres + (size_t)slot * CAR_MAX_TRACK;
     reinterpret_cast<uint4*>(now16)[0] = make_uint4(0u, 0u, 0u, 0u); reinterpret_cast<uint4*>(now16)[1] = make_uint4(0u, 0u, 0u, 0u);
@@ -574,10 +576,42 @@ __device__ void sensor_wheel_overlaps(const CarDev& p, int slot, int n_track, F2
         }
     }
     const int n_samp = (n_track + CAR_SAMPLE_STRIDE - 1) / CAR_SAMPLE_STRIDE;
-    for (int s = 0; s < n_samp; ++s) {
-        const float2 sp = p.samples[(size_t)s * (2 * p.n) + slot];
-        const float dx = sp.x - hp.x, dy = sp.y - hp.y;
-        if (!(dx * dx + dy * dy < 36.0f * 36.0f)) continue;
+    if (!have_near) {
+        near_samples = 0ull;
+        for (int s = 0; s < n_samp; ++s) {
+            const float2 sp = p.samples[(size_t)s * (2 * p.n) + slot];
+            const float dx = sp.x - hp.x, dy = sp.y - hp.y;
+            if (dx * dx + dy * dy < 36.0f * 36.0f) near_samples |= 1ull << s;
+        }
+    }
+    // Candidates first (tile centre within 11.5 of the hull and 9 of the wheel: a few per wheel), tests second: the lanes of
+    // a warp reach their candidates at different points of the walk, and testing on the spot would run the test once per
+    // such point instead of once per round of "every lane's j-th candidate".  Up to six 10-bit tile ids in one word.
+    unsigned long long cand = 0ull;
+    int n_cand = 0;
+    auto test_tile = [&](int t) {
+        const CarTile* Tp = tiles + t;
+        float tpx[5], tpy[5], tnx[5], tny[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) { tpx[i] = Tp->px[i]; tpy[i] = Tp->py[i]; tnx[i] = Tp->nx[i]; tny[i] = Tp->ny[i]; }
+        const int tn = Tp->n;
+        // Cheap and safe reject: a tile face that keeps the wheel's centre more than the wheel's circumradius (0.6083)
+        // plus 2 r away keeps every wheel vertex 2 r away (the 0.0067 of slack dwarfs fp32 rounding), so the exact
+        // test below would find the same face separating.  Most candidates are the overlapped tile's neighbours.
+        bool far_face = false;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+            if (i < tn && !(tnx[i] > 1.0e38f) && tnx[i] * (wc.x - tpx[i]) + tny[i] * (wc.y - tpy[i]) - 0.615f >= 2.0f * B2_POLYGON_RADIUS)
+                far_face = true;
+        if (far_face) return;
+        // max(s1, s2) < 2 r  <=>  no face of either polygon separates them by 2 r or more: stop at the first that does
+        if (!separated_by_face(wx, wy, wnx, wny, 4, tpx, tpy, tn, 2.0f * B2_POLYGON_RADIUS) &&
+            !separated_by_face(tpx, tpy, tnx, tny, tn, wx, wy, 4, 2.0f * B2_POLYGON_RADIUS))
+            now16[t >> 5] |= 1u << (t & 31);
+    };
+    while (near_samples) {
+        const int s = __ffsll((long long)near_samples) - 1;
+        near_samples &= near_samples - 1ull;
         const int t1 = min(n_track, (s + 1) * CAR_SAMPLE_STRIDE);
         for (int t = s * CAR_SAMPLE_STRIDE; t < t1; ++t) {
             const float2 tc = centres[t];
@@ -585,17 +619,11 @@ __device__ void sensor_wheel_overlaps(const CarDev& p, int slot, int n_track, F2
             if (!(tx * tx + ty * ty < 11.5f * 11.5f)) continue;
             const float ddx = tc.x - wc.x, ddy = tc.y - wc.y;
             if (!(ddx * ddx + ddy * ddy <= 9.0f * 9.0f)) continue;
-            const CarTile* Tp = tiles + t;
-            float tpx[5], tpy[5], tnx[5], tny[5];
-#pragma unroll
-            for (int i = 0; i < 5; ++i) { tpx[i] = Tp->px[i]; tpy[i] = Tp->py[i]; tnx[i] = Tp->nx[i]; tny[i] = Tp->ny[i]; }
-            const int tn = Tp->n;
-            // max(s1, s2) < 2 r  <=>  no face of either polygon separates them by 2 r or more: stop at the first that does
-            if (!separated_by_face(wx, wy, wnx, wny, 4, tpx, tpy, tn, 2.0f * B2_POLYGON_RADIUS) &&
-                !separated_by_face(tpx, tpy, tnx, tny, tn, wx, wy, 4, 2.0f * B2_POLYGON_RADIUS))
-                now16[t >> 5] |= 1u << (t & 31);
+            if (n_cand < 6) { cand |= (unsigned long long)t << (10 * n_cand); ++n_cand; }
+            else test_tile(t);                                     // more candidates than the word holds: on the spot
         }
     }
+    for (int j = 0; j < n_cand; ++j) test_tile((int)((cand >> (10 * j)) & 1023ull));
 }
 
 // The tile-sensor overlaps of every wheel at the start of world.Step, one thread per (car, wheel), ahead of the step
@@ -618,12 +646,25 @@ __global__ void __launch_bounds__(128) car_sensor_kernel(CarDev p, int classify)
         if (deferred) p.slow_list[atomicAdd(p.slow_count, 1)] = e;
         p.deferred[e] = deferred ? 1 : 0;
     }
-    sensor_wheel_overlaps(p, slot, p.n_track[slot], hp, f2(b[8 * (k + 1)], b[8 * (k + 1) + 1]), b[8 * (k + 1) + 2],
-                          p.sensor_now + ((size_t)ci * 4 + k) * 16);
+    // the prefilter on every 8th track point depends on the hull only: the four wheel lanes of a car take a quarter of the
+    // (at most 64) points each and pool what they found
+    const int n_track = p.n_track[slot];
+    const int n_samp = (n_track + CAR_SAMPLE_STRIDE - 1) / CAR_SAMPLE_STRIDE;
+    unsigned long long near_samples = 0ull;
+    for (int s = k; s < n_samp; s += 4) {
+        const float2 sp = p.samples[(size_t)s * (2 * p.n) + slot];
+        const float dx = sp.x - hp.x, dy = sp.y - hp.y;
+        if (dx * dx + dy * dy < 36.0f * 36.0f) near_samples |= 1ull << s;
+    }
+    const unsigned car_lanes = 0xFu << (threadIdx.x & 28);            // the four lanes of this car: in range together
+    near_samples |= __shfl_xor_sync(car_lanes, near_samples, 1);
+    near_samples |= __shfl_xor_sync(car_lanes, near_samples, 2);
+    sensor_wheel_overlaps(p, slot, n_track, hp, f2(b[8 * (k + 1)], b[8 * (k + 1) + 1]), b[8 * (k + 1) + 2],
+                          p.sensor_now + ((size_t)ci * 4 + k) * 16, near_samples, true);
 }
 
 __device__ __noinline__ void sensor_car_overlaps(const CarDev& p, int ci, int slot, int n_track, F2 hp, const F2* c, const float* a) {
-    for (int k = 0; k < 4; ++k) sensor_wheel_overlaps(p, slot, n_track, hp, c[k + 1], a[k + 1], p.sensor_now + ((size_t)ci * 4 + k) * 16);
+    for (int k = 0; k < 4; ++k) sensor_wheel_overlaps(p, slot, n_track, hp, c[k + 1], a[k + 1], p.sensor_now + ((size_t)ci * 4 + k) * 16, 0ull, false);
 }
 
 // mode 0: every car.  mode 1 (fast pass): two-car envs whose cars are near each other are skipped: car_sensor_kernel put
