@@ -488,6 +488,53 @@ __device__ __forceinline__ F2 solve22(float a11, float a12, float a21, float a22
     return f2(det * (a22 * b.x - a12 * b.y), det * (a11 * b.y - a21 * b.x));
 }
 
+// One relaxation of a wheel joint inside a velocity iteration (b2RevoluteJoint::SolveVelocityConstraints: motor, then
+// the limit's 3 x 3 block or the plain 2 x 2 point constraint).  MAY_LIMIT = false: no lane of the warp has this joint
+// at its limit in this step (the limit state is fixed before the 180 iterations), so the branch and its code are
+// left out of the loop altogether.
+template <bool MAY_LIMIT>
+__device__ __forceinline__ void relax_joint(Joint& j, F2& vA, float& wA, F2& vB, float& wB, float mA, float iA, float mB, float iB,
+                                            float max_motor_impulse) {
+    {   // motor
+        const float Cdot = wB - wA - j.motor_speed;
+        float impulse = -j.motor_mass * Cdot;
+        const float old = j.motor_impulse;
+        j.motor_impulse = clampf(old + impulse, -max_motor_impulse, max_motor_impulse);
+        impulse = j.motor_impulse - old;
+        wA -= iA * impulse;
+        wB += iB * impulse;
+    }
+    if (MAY_LIMIT && j.limit_state != 0) {
+        const F2 Cdot1 = (vB - vA) - cross_sv(wA, j.rA);
+        const float Cdot2 = wB - wA;
+        float i0, i1, i2;
+        solve33(j, Cdot1.x, Cdot1.y, Cdot2, i0, i1, i2);
+        i0 = -i0; i1 = -i1; i2 = -i2;
+        const float ni = j.iz + i2;
+        const bool release = (j.limit_state == 1) ? (ni < 0.0f) : (ni > 0.0f);
+        if (release) {
+            const F2 rhs = f2(-Cdot1.x + j.iz * j.k02, -Cdot1.y + j.iz * j.k12);
+            const F2 red = solve22(j.k00, j.k01, j.k01, j.k11, rhs);
+            i0 = red.x; i1 = red.y; i2 = -j.iz;
+            j.ix += red.x; j.iy += red.y; j.iz = 0.0f;
+        } else {
+            j.ix += i0; j.iy += i1; j.iz += i2;
+        }
+        const F2 P = f2(i0, i1);
+        vA = vA - mA * P;
+        wA -= iA * (cross(j.rA, P) + i2);
+        vB = vB + mB * P;
+        wB += iB * i2;
+    } else {
+        const F2 Cdot = (vB - vA) - cross_sv(wA, j.rA);
+        const F2 imp = solve22(j.k00, j.k01, j.k01, j.k11, f2(-Cdot.x, -Cdot.y));
+        j.ix += imp.x; j.iy += imp.y;
+        vA = vA - mA * imp;
+        wA -= iA * cross(j.rA, imp);
+        vB = vB + mB * imp;
+    }
+}
+
 // polygons (with b2_polygonRadius skins) touch: max face separation below 2 * radius
 __device__ float max_separation(const float* ax, const float* ay, int na, const float* bx, const float* by, int nb) {
     float best = -3.4e38f;
@@ -708,6 +755,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
         bool awake[5];
         {
             const float* b = p.body + (size_t)ci * 40;
+#pragma unroll
             for (int i = 0; i < 5; ++i) {
                 c[i] = f2(b[8 * i], b[8 * i + 1]); a[i] = b[8 * i + 2]; v[i] = f2(b[8 * i + 3], b[8 * i + 4]);
                 w[i] = b[8 * i + 5]; sleep_t[i] = b[8 * i + 6]; awake[i] = b[8 * i + 7] != 0.f;
@@ -716,6 +764,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
         Joint J[4];
         {
             const float* j = p.joint + (size_t)ci * 24;
+#pragma unroll
             for (int k = 0; k < 4; ++k) {
                 J[k].ix = j[6 * k]; J[k].iy = j[6 * k + 1]; J[k].iz = j[6 * k + 2]; J[k].motor_impulse = j[6 * k + 3];
                 J[k].limit_state = (int)j[6 * k + 4]; J[k].motor_speed = j[6 * k + 5];
@@ -724,6 +773,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
         double omega[4], gas[2], brake, steer;
         {
             const double* wd = p.wheel + (size_t)ci * 8;
+#pragma unroll
             for (int k = 0; k < 4; ++k) omega[k] = wd[k];
             gas[0] = wd[4]; gas[1] = wd[5]; brake = wd[6]; steer = wd[7];
         }
@@ -747,6 +797,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
             if (a1 > 0) a2 = 0; else { a2 = a1; a1 = 0; }
             steer = -a0;
             const double g = fmin(fmax(fabs(a1), 0.0), 1.0);
+#pragma unroll
             for (int k = 0; k < 2; ++k) {
                 double diff = g - gas[k];
                 if (diff > 0.1) diff = 0.1;
@@ -759,8 +810,10 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
         const float h = 1.0f / CR_FPS;
         for (int rep = 0; rep < p.action_repeat; ++rep) {
             F2 force[5];
+#pragma unroll
             for (int i = 0; i < 5; ++i) force[i] = f2(0.f, 0.f);
             int n_touch[4];
+#pragma unroll
             for (int k = 0; k < 4; ++k) {
                 int cnt = 0;
                 for (int wd = 0; wd < 16; ++wd) cnt += __popc(touching[16 * k + wd]);
@@ -768,6 +821,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
             }
             if (!car_done) {
                 // ---- Car.step(1/FPS), car_dynamics.py:159-234 ----
+#pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int bi = k + 1;
                     const double joint_angle = (double)(a[bi] - a[0] - 0.0f);
@@ -830,6 +884,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                 }
                 const uint32_t* now = p.sensor_now + (size_t)ci * 64;
                 // contact events wheel by wheel (FrictionDetector._contact), BeginContact in ascending block id
+#pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     uint32_t was_w[16];
                     {
@@ -870,6 +925,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
             int n_con = 0;
             CarContact* recs = nullptr;
             if (p.players == 2) {
+#pragma unroll
                 for (int i = 0; i < 5; ++i) { pose[player * 5 + i][0] = c[i].x; pose[player * 5 + i][1] = c[i].y; pose[player * 5 + i][2] = a[i]; }
                 __syncwarp(pair_mask);
                 recs = p.contacts + (size_t)e * CAR_MAX_CONTACTS;
@@ -892,13 +948,16 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
             // The lanes arrive here diverged (different numbers of candidate tiles, contact events, gate outcomes); left
             // alone, each group would run the 180-iteration solver loops on its own.  Reconverge the warp first.
             __syncwarp(warp_lanes);
+            const unsigned awake_lanes = __ballot_sync(warp_lanes, any_awake);   // the lanes that run the solver loops
             if (any_awake) {
+#pragma unroll
                 for (int i = 0; i < 5; ++i)
                     if (!awake[i]) { awake[i] = true; sleep_t[i] = 0.f; }
                 const float dt_ratio = inv_dt0 * h;
                 const float mA = K.hull_inv_mass, iA = K.hull_inv_I, mB = K.wheel_inv_mass, iB = K.wheel_inv_I;
                 const F2 c0h = c[0];
                 (void)c0h;
+#pragma unroll
                 for (int i = 0; i < 5; ++i) {
                     const float im = (i == 0) ? mA : mB;
                     v[i] = v[i] + h * (im * force[i]);
@@ -907,13 +966,16 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                     w[i] *= 1.0f / (1.0f + h * 0.0f);
                 }
                 if (merged) {   // contact constraints are initialised and warm-started before the joints (b2Island::Solve)
+#pragma unroll
                     for (int i = 0; i < 5; ++i) { vel[player * 5 + i][0] = v[i].x; vel[player * 5 + i][1] = v[i].y; vel[player * 5 + i][2] = w[i]; }
                     __syncwarp(pair_mask);
                     if (player == 0) car_contacts_init(p.consts, recs, n_con, pose, vel, dt_ratio);
                     __syncwarp(pair_mask);
+#pragma unroll
                     for (int i = 0; i < 5; ++i) { v[i] = f2(vel[player * 5 + i][0], vel[player * 5 + i][1]); w[i] = vel[player * 5 + i][2]; }
                 }
                 // InitVelocityConstraints (+ warm start), joints 3, 2, 1, 0
+#pragma unroll
                 for (int kk = 3; kk >= 0; --kk) {
                     Joint& j = J[kk];
                     const int bi = kk + 1;
@@ -950,63 +1012,37 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                     w[bi] += iB * (j.motor_impulse + j.iz);
                 }
                 const float max_motor_impulse = h * (float)(180 * 900 * CR_SIZE * CR_SIZE);
-#pragma unroll 1
-                for (int it = 0; it < 6 * 30; ++it) {
+                // Which joints are at a limit in ANY lane of the warp: decided once (InitVelocityConstraints fixed the limit
+                // states), so that the 180 iterations run without the limit branch where no lane needs it.  Rear wheels
+                // (joints 2, 3) are held at angle 0 by their motors and only leave it under a contact; front wheels reach
+                // +-0.4 whenever the steering saturates.
+                unsigned lim = 0u;
 #pragma unroll
-                    for (int kk = 3; kk >= 0; --kk) {
-                        Joint& j = J[kk];
-                        const int bi = kk + 1;
-                        F2 vA = v[0], vB = v[bi];
-                        float wA = w[0], wB = w[bi];
-                        {   // motor
-                            const float Cdot = wB - wA - j.motor_speed;
-                            float impulse = -j.motor_mass * Cdot;
-                            const float old = j.motor_impulse;
-                            j.motor_impulse = clampf(old + impulse, -max_motor_impulse, max_motor_impulse);
-                            impulse = j.motor_impulse - old;
-                            wA -= iA * impulse;
-                            wB += iB * impulse;
-                        }
-                        if (j.limit_state != 0) {
-                            const F2 Cdot1 = (vB - vA) - cross_sv(wA, j.rA);
-                            const float Cdot2 = wB - wA;
-                            float i0, i1, i2;
-                            solve33(j, Cdot1.x, Cdot1.y, Cdot2, i0, i1, i2);
-                            i0 = -i0; i1 = -i1; i2 = -i2;
-                            const float ni = j.iz + i2;
-                            const bool release = (j.limit_state == 1) ? (ni < 0.0f) : (ni > 0.0f);
-                            if (release) {
-                                const F2 rhs = f2(-Cdot1.x + j.iz * j.k02, -Cdot1.y + j.iz * j.k12);
-                                const F2 red = solve22(j.k00, j.k01, j.k01, j.k11, rhs);
-                                i0 = red.x; i1 = red.y; i2 = -j.iz;
-                                j.ix += red.x; j.iy += red.y; j.iz = 0.0f;
-                            } else {
-                                j.ix += i0; j.iy += i1; j.iz += i2;
-                            }
-                            const F2 P = f2(i0, i1);
-                            vA = vA - mA * P;
-                            wA -= iA * (cross(j.rA, P) + i2);
-                            vB = vB + mB * P;
-                            wB += iB * i2;
-                        } else {
-                            const F2 Cdot = (vB - vA) - cross_sv(wA, j.rA);
-                            const F2 imp = solve22(j.k00, j.k01, j.k01, j.k11, f2(-Cdot.x, -Cdot.y));
-                            j.ix += imp.x; j.iy += imp.y;
-                            vA = vA - mA * imp;
-                            wA -= iA * cross(j.rA, imp);
-                            vB = vB + mB * imp;
-                        }
-                        v[0] = vA; w[0] = wA; v[bi] = vB; w[bi] = wB;
-                    }
-                    if (merged) {   // contacts after the joints of both cars
-                        for (int i = 0; i < 5; ++i) { vel[player * 5 + i][0] = v[i].x; vel[player * 5 + i][1] = v[i].y; vel[player * 5 + i][2] = w[i]; }
-                        __syncwarp(pair_mask);
-                        if (player == 0) car_contacts_solve_velocity(p.consts, recs, n_con, vel);
-                        __syncwarp(pair_mask);
-                        for (int i = 0; i < 5; ++i) { v[i] = f2(vel[player * 5 + i][0], vel[player * 5 + i][1]); w[i] = vel[player * 5 + i][2]; }
-                    }
+                for (int k = 0; k < 4; ++k)
+                    if (__ballot_sync(awake_lanes, J[k].limit_state != 0) != 0u) lim |= 1u << k;
+                auto contacts_after_joints = [&]() {   // merged island: contacts after the joints of both cars
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) { vel[player * 5 + i][0] = v[i].x; vel[player * 5 + i][1] = v[i].y; vel[player * 5 + i][2] = w[i]; }
+                    __syncwarp(pair_mask);
+                    if (player == 0) car_contacts_solve_velocity(p.consts, recs, n_con, vel);
+                    __syncwarp(pair_mask);
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) { v[i] = f2(vel[player * 5 + i][0], vel[player * 5 + i][1]); w[i] = vel[player * 5 + i][2]; }
+                };
+#define CRL_VELOCITY_ITERATIONS(REAR, FRONT)                                                                        \
+                _Pragma("unroll 1") for (int it = 0; it < 6 * 30; ++it) {                                            \
+                    relax_joint<REAR>(J[3], v[0], w[0], v[4], w[4], mA, iA, mB, iB, max_motor_impulse);              \
+                    relax_joint<REAR>(J[2], v[0], w[0], v[3], w[3], mA, iA, mB, iB, max_motor_impulse);              \
+                    relax_joint<FRONT>(J[1], v[0], w[0], v[2], w[2], mA, iA, mB, iB, max_motor_impulse);             \
+                    relax_joint<FRONT>(J[0], v[0], w[0], v[1], w[1], mA, iA, mB, iB, max_motor_impulse);             \
+                    if (merged) contacts_after_joints();                                                             \
                 }
+                if (lim == 0u) { CRL_VELOCITY_ITERATIONS(false, false) }
+                else if ((lim & 0xCu) == 0u) { CRL_VELOCITY_ITERATIONS(false, true) }
+                else { CRL_VELOCITY_ITERATIONS(true, true) }
+#undef CRL_VELOCITY_ITERATIONS
                 // integrate positions
+#pragma unroll
                 for (int i = 0; i < 5; ++i) {
                     const F2 tr = h * v[i];
                     if (dot(tr, tr) > B2_MAX_TRANSLATION * B2_MAX_TRANSLATION) v[i] = (B2_MAX_TRANSLATION / sqrtf(dot(tr, tr))) * v[i];
@@ -1021,12 +1057,14 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                 for (int it = 0; it < 2 * 30; ++it) {
                     bool ok = true;
                     if (merged) {   // contacts before the joints
+#pragma unroll
                         for (int i = 0; i < 5; ++i) { pose[player * 5 + i][0] = c[i].x; pose[player * 5 + i][1] = c[i].y; pose[player * 5 + i][2] = a[i]; }
                         __syncwarp(pair_mask);
                         int cok = 1;
                         if (player == 0) cok = car_contacts_solve_position(p.consts, recs, n_con, pose) ? 1 : 0;
                         __syncwarp(pair_mask);
                         ok = __shfl_sync(pair_mask, cok, threadIdx.x & 30) != 0;
+#pragma unroll
                         for (int i = 0; i < 5; ++i) { c[i] = f2(pose[player * 5 + i][0], pose[player * 5 + i][1]); a[i] = pose[player * 5 + i][2]; }
                     }
 #pragma unroll
@@ -1073,6 +1111,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                 }
                 // sleeping
                 float min_sleep = 3.4e38f;
+#pragma unroll
                 for (int i = 0; i < 5; ++i) {
                     if (w[i] * w[i] > B2_ANGULAR_SLEEP_TOL * B2_ANGULAR_SLEEP_TOL || dot(v[i], v[i]) > B2_LINEAR_SLEEP_TOL * B2_LINEAR_SLEEP_TOL) {
                         sleep_t[i] = 0.0f;
@@ -1084,6 +1123,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                 }
                 if (merged) min_sleep = fminf(min_sleep, __shfl_xor_sync(pair_mask, min_sleep, 1));
                 if (min_sleep >= B2_TIME_TO_SLEEP && position_solved)
+#pragma unroll
                     for (int i = 0; i < 5; ++i) { awake[i] = false; sleep_t[i] = 0.f; v[i] = f2(0.f, 0.f); w[i] = 0.f; }
             }
             inv_dt0 = 1.0f / h;
@@ -1093,16 +1133,19 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
         // ---- store ----
         {
             float* b = p.body + (size_t)ci * 40;
+#pragma unroll
             for (int i = 0; i < 5; ++i) {
                 b[8 * i] = c[i].x; b[8 * i + 1] = c[i].y; b[8 * i + 2] = a[i]; b[8 * i + 3] = v[i].x; b[8 * i + 4] = v[i].y;
                 b[8 * i + 5] = w[i]; b[8 * i + 6] = sleep_t[i]; b[8 * i + 7] = awake[i] ? 1.f : 0.f;
             }
             float* j = p.joint + (size_t)ci * 24;
+#pragma unroll
             for (int k = 0; k < 4; ++k) {
                 j[6 * k] = J[k].ix; j[6 * k + 1] = J[k].iy; j[6 * k + 2] = J[k].iz; j[6 * k + 3] = J[k].motor_impulse;
                 j[6 * k + 4] = (float)J[k].limit_state; j[6 * k + 5] = J[k].motor_speed;
             }
             double* wd = p.wheel + (size_t)ci * 8;
+#pragma unroll
             for (int k = 0; k < 4; ++k) wd[k] = omega[k];
             wd[4] = gas[0]; wd[5] = gas[1]; wd[6] = brake; wd[7] = steer;
             p.reward[2 * ci] = reward; p.reward[2 * ci + 1] = prev_reward;

@@ -658,6 +658,8 @@ int crl_car_check(crl_car* h, void* stream) {
     CUDA_TRY(cudaMemcpyAsync(flags, h->dev.overrun, sizeof flags, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     const int32_t flag = flags[0];
+    if (flag != 0 || flags[1] != 0)                                   // reported once: the flags are cleared ([2], [3] are statistics)
+        CUDA_TRY(cudaMemsetAsync(h->dev.overrun, 0, 2 * sizeof(int32_t), (cudaStream_t)stream));
     if (flags[1] != 0) return crl_set_error(CRL_E_STATE, "road map: %d span(s) / block(s) of a track could not be painted (outside the 2048 px map window or block pool full)", flags[1]);
     if (flag == 1) return crl_set_error(CRL_E_SERVES, "injected track-draw / birth-place table exhausted");
     if (flag == 2) return crl_set_error(CRL_E_STATE, "track generation failed 64 times in a row");
