@@ -406,22 +406,21 @@ def car_leg(cx, a, env_id, N, steps, stack_mode="stack"):
     torch = cx.torch
     lib = _native.load()
     players = 2 if "Double" in env_id else 1
-    envs = make_envs(env_id, num_envs=N, frame_stack=4, log_dir=None, seed=1, asynchronous=True, n_buffers=1,
+    envs = make_envs(env_id, num_envs=N, frame_stack=4, log_dir=None, seed=1, asynchronous=True, n_buffers=2,
                      first_env=cx.rank * N, stack_mode=stack_mode)
     envs.reset()
     rng = np.random.default_rng(7 + cx.rank)
     envs.set_elapsed(rng.integers(0, 1000, N))
     h = envs._h
     stream, sp = cx.stream, cx.sp
-    b = envs._sets[0]
-    obs = envs._store[0] if hasattr(envs, "_store") else b["obs"]
     actions = torch.zeros((N, players, 2), dtype=torch.float32, device=cx.dev)
     bytes_step = envs.bytes_per_env_step
     warm = 30
 
     def one(t):
+        b = envs.next_set()     # stack mode: the next observation buffer of the rotation the env registered with the library
         _native.check(lib.crl_car_random_actions(P(actions), actions.numel(), 7 + cx.rank, t, sp))
-        _native.check(lib.crl_car_step(h, P(actions), P(obs), P(b["rew"]), P(b["done"]), P(b["steps"]), P(b["trunc"]),
+        _native.check(lib.crl_car_step(h, P(actions), P(b["obs"]), P(b["rew"]), P(b["done"]), P(b["steps"]), P(b["trunc"]),
                                        P(b["term"]), sp))
 
     sampler = ClockSampler(cx.local)
@@ -455,10 +454,11 @@ def car_leg(cx, a, env_id, N, steps, stack_mode="stack"):
     for k in range(K):
         _native.check(lib.crl_car_random_actions(P(actions), actions.numel(), 7 + cx.rank, t, sp))
         t += 1
+        b = envs.next_set()
         sev[k][0].record(stream)
         _native.check(lib.crl_car_step_state(h, P(actions), P(b["rew"]), P(b["done"]), P(b["steps"]), P(b["trunc"]), sp))
         sev[k][1].record(stream)
-        _native.check(lib.crl_car_render_obs(h, P(obs), P(b["term"]), sp))
+        _native.check(lib.crl_car_render_obs(h, P(b["obs"]), P(b["term"]), sp))
         sev[k][2].record(stream)
     cx.barrier()
     phys = sum(e[0].elapsed_time(e[1]) for e in sev) / K
@@ -473,7 +473,8 @@ def car_leg(cx, a, env_id, N, steps, stack_mode="stack"):
     h_trunc = torch.zeros((N,), dtype=torch.uint8).pin_memory()
 
     def host_step():
-        _native.check(lib.crl_car_step_host(h, P(h_act), P(obs), None, P(h_rew), P(h_done), P(h_steps), P(h_trunc),
+        b = envs.next_set()
+        _native.check(lib.crl_car_step_host(h, P(h_act), P(b["obs"]), None, P(h_rew), P(h_done), P(h_steps), P(h_trunc),
                                             P(b["term"]), sp))
     for _ in range(3):
         host_step()
@@ -485,7 +486,7 @@ def car_leg(cx, a, env_id, N, steps, stack_mode="stack"):
     e2e_s = time.perf_counter() - t0
     envs.check()
     envs.close()
-    del envs, obs, b
+    del envs
     torch.cuda.empty_cache()
 
     ms, phys, rend, e2e_s, p50, p99, pmax = cx.max_over_ranks(

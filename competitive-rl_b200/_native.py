@@ -22,7 +22,7 @@ EXPORTS = [
     "crl_car_create", "crl_car_destroy", "crl_car_load_glyphs", "crl_car_inject_tracks", "crl_car_load_tracks", "crl_car_reset",
     "crl_car_step", "crl_car_step_state", "crl_car_render_obs", "crl_car_get_state", "crl_car_get_track",
     "crl_car_random_actions", "crl_car_get_stats", "crl_car_get_contacts", "crl_car_check",
-    "crl_car_seed", "crl_car_step_host", "crl_car_set_elapsed", "crl_car_set_state", "crl_car_ring_phase", "crl_car_render_state",
+    "crl_car_seed", "crl_car_step_host", "crl_car_set_elapsed", "crl_car_set_state", "crl_car_ring_phase", "crl_car_render_state", "crl_car_set_obs_rotation",
 ]
 
 
@@ -129,6 +129,7 @@ def load():
     L.crl_car_set_elapsed.argtypes = [vp, vp, vp]
     L.crl_car_set_state.argtypes = [vp, vp, vp]
     L.crl_car_ring_phase.argtypes = [vp]
+    L.crl_car_set_obs_rotation.argtypes = [vp, ctypes.POINTER(vp), i32, vp]
     L.crl_car_render_state.argtypes = [vp, vp, vp]
     L.crl_car_render_obs.argtypes = [vp] * 4
     L.crl_car_get_state.argtypes = [vp, vp, vp]

@@ -63,6 +63,10 @@ class CudaCarVecEnv(VecEnv):
     """actions: float (N, 2) for cCarRacing-v0, (N, 2, 2) for cCarRacingDouble-v0 (steer, gas/brake in [-1, 1]).
     step -> (obs uint8 (N, players*C, 96, 96), rew float32, done bool (N,), infos).
 
+    stack_mode="stack" (default): a fully materialised stack, as the reference returns it.  The env's observation buffers
+    form a rotation of C + max(1, n_buffers - 1) sets registered with the library, which writes every new frame straight
+    into the C buffers it will appear in, so no frame is copied from step to step.  "stack-shift" is the plain C-ABI mode
+    (any buffer per call; internal frame ring and a stack-shift kernel).
     stack_mode="ring" (opt-in): the observation is a strided VIEW of an (N, players, 2C, 96, 96) double-write ring -- shape
     (N, C, 96, 96) for one car, (N, 2, C, 96, 96) for two (player axis kept: the two players' windows cannot be one
     uniformly strided channel axis; `.flatten(1, 2)` materialises the reference's (N, 2C, 96, 96) layout).  A step then
@@ -80,8 +84,8 @@ class CudaCarVecEnv(VecEnv):
         self.env_id, self.players = env_id, 2 if env_id == "cCarRacingDouble-v0" else 1
         self.c = int(frame_stack) if frame_stack else 1
         self.asynchronous, self.return_numpy, self.copy = bool(asynchronous), bool(return_numpy), bool(copy)
-        if stack_mode not in ("stack", "ring"):
-            raise ValueError("stack_mode must be 'stack' or 'ring'")
+        if stack_mode not in ("stack", "ring", "stack-shift"):
+            raise ValueError("stack_mode must be 'stack', 'ring' or 'stack-shift'")
         self.stack_mode, self.ring = stack_mode, stack_mode == "ring"
         if done_mode not in ("any", "car0"):
             raise ValueError("done_mode must be 'any' (make_envs) or 'car0' (make_competitive_car_racing)")
@@ -107,8 +111,14 @@ class CudaCarVecEnv(VecEnv):
             self.inject_tracks(track_draws, birth)
         dev = self.device
         self._ring = torch.empty((n, self.players, 2 * self.c, 96, 96), dtype=torch.uint8, device=dev) if self.ring else None
+        # "stack": the observation buffers form a rotation the library knows (crl_car_set_obs_rotation), and every new
+        # frame is written straight into the C buffers it will appear in -- nothing is copied from step to step.  What a
+        # call returned stays intact for n_buffers - 1 further calls (at least one), as with the other modes.
+        # "stack-shift": caller-chosen buffer per call, internal frame ring + stack-shift kernel (the plain C-ABI mode).
+        self._rotation = stack_mode == "stack" and self.c >= 2
+        n_sets = self.c + max(1, int(n_buffers) - 1) if self._rotation else max(1, int(n_buffers))
         self._sets = []
-        for _ in range(max(1, int(n_buffers))):
+        for _ in range(n_sets):
             self._sets.append(dict(
                 obs=self._ring if self.ring else torch.empty((n, ch, 96, 96), dtype=torch.uint8, device=dev),
                 term=torch.zeros((n, ch, 96, 96), dtype=torch.uint8, device=dev),
@@ -117,6 +127,8 @@ class CudaCarVecEnv(VecEnv):
                 trunc=torch.zeros((n,), dtype=torch.uint8, device=dev),
                 steps=torch.zeros((n,), dtype=torch.int32, device=dev)))
         self._cur = 0
+        if self._rotation:
+            self._impl.set_obs_rotation([b["obs"] for b in self._sets])
         self._actions = torch.zeros((n, self.players, 2), dtype=torch.float32, device=dev)
         self._waiting, self.closed = False, False
         self.envs = _EnvList(self)
@@ -146,6 +158,12 @@ class CudaCarVecEnv(VecEnv):
         assert d.ndim == 3 and d.shape[0] == self.num_envs and d.shape[2] == 24
         b = None if birth is None else torch.from_numpy(np.ascontiguousarray(birth, np.int32))
         self._impl.inject_tracks(torch.from_numpy(d), b)
+
+    def next_set(self):
+        """For callers that drive the C ABI themselves (bench.py, tools): the buffer set the NEXT call must be given
+        (stack_mode "stack": the next observation buffer of the registered rotation)."""
+        self._cur = (self._cur + 1) % len(self._sets)
+        return self._sets[self._cur]
 
     def _obs_of(self, b):
         """what the caller sees of buffer set b: the observation tensor, or the ring's current window"""
@@ -263,6 +281,8 @@ class CudaCarVecEnv(VecEnv):
     def render_state(self):
         """Debug / tests: render the CURRENT state (e.g. after set_state) as one more frame of the stack; returns the
         newest frame of every player, uint8 (N, players, 96, 96)."""
+        if self._rotation:
+            self._cur = (self._cur + 1) % len(self._sets)
         b = self._sets[self._cur]
         self._impl.render_state(b["obs"])
         return self._obs_of(b).reshape(self.num_envs, self.players, self.c, 96, 96)[:, :, -1]

@@ -24,6 +24,7 @@ constexpr int CAR_DRAWS = 2 * CAR_CHECKPOINTS;   // np_random.uniform draws per 
 constexpr int CAR_SAMPLE_STRIDE = 8;        // every 8th track point feeds the contact prefilter
 constexpr int CAR_MAX_SAMPLES = CAR_MAX_TRACK / CAR_SAMPLE_STRIDE;
 constexpr int CAR_MAX_STACK = 8;
+constexpr int CAR_MAX_ROTATION = 16;       // registered observation buffers of the ahead-write stack mode
 constexpr int CAR_GLYPH_BYTES = 11 * 8 * 4 + 11;
 // the painted road map of a track, kept as a sparse raster (car_spans.cuh): 16 x 16 px blocks of the 2048 x 2048 px window
 // of the reference's 10 000 x 10 000 px surface that starts at road-map pixel CAR_MAP_ORIGIN on both axes
@@ -87,6 +88,12 @@ struct CarDev {
     int ring_mode;
     int ring_phase;           // host-tracked, advanced per step
     int fill_all;             // 1 after reset(): every frame written goes to all slots
+    // stack mode over a rotation of B >= C + 1 registered observation buffers (crl_car_set_obs_rotation): the k-th call
+    // after a reset returns buffer (k mod B), and every new frame is written straight into the C buffers it will appear
+    // in -- channel C-1 of the current one, C-2 of the next, ... -- so no frame is ever moved and no ring is kept
+    uint8_t* rot[CAR_MAX_ROTATION];
+    int rot_n;                // 0 = not registered
+    int rot_pos;              // host-tracked: index of the buffer the current call returns
     int done_mode;            // 0 = any car done (FlattenMultiAgentObservation), 1 = car 0 only (make_competitive_car_racing)
     int64_t first_env;
     uint64_t seed;

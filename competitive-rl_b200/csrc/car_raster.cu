@@ -382,13 +382,15 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     // looks at slots k+1 .. k+C), so nothing is ever moved.
     // Output layout: [env][players * C][96][96]: player-major channel blocks (FlattenMultiAgentObservation concatenates
     // the players' stacks on the channel axis), oldest frame first within a player.
-    const bool ringm = p.ring_mode != 0;
-    uint8_t* ring = ringm ? nullptr : p.ring + (size_t)frame * C * CAR_PIX;
-    const bool fill_all = only_done != 0 || (ringm ? p.fill_all != 0 : p.ring_pos[e] < 0);
+    // Ahead-write stack mode (a rotation of registered buffers): the new frame goes to channel C-1 of the current buffer,
+    // C-2 of the next, ... 0 of the C-1-th next; the current buffer already holds its older frames.
+    const bool ringm = p.ring_mode != 0, ahead = p.rot_n > 0;
+    uint8_t* ring = (ringm || ahead) ? nullptr : p.ring + (size_t)frame * C * CAR_PIX;
+    const bool fill_all = only_done != 0 || ((ringm || ahead) ? p.fill_all != 0 : p.ring_pos[e] < 0);
     int newest = C - 1;
     if (ringm) newest = p.ring_phase;
-    else if (!fill_all) { newest = p.ring_pos[e] + 1; if (newest >= C) newest = 0; }
-    uint8_t* out = obs + (size_t)frame * (ringm ? 2 * C : C) * CAR_PIX;
+    else if (!ahead && !fill_all) { newest = p.ring_pos[e] + 1; if (newest >= C) newest = 0; }
+    uint8_t* out = (ahead ? p.rot[p.rot_pos] : obs) + (size_t)frame * (ringm ? 2 * C : C) * CAR_PIX;
     uint8_t* tout = (term_obs != nullptr && !only_done && p.env_done[e]) ? term_obs + (size_t)frame * C * CAR_PIX : nullptr;
 
     // what the setup kernel prepared: car polygon span tables and the block list (84 x 16 bytes)
@@ -469,7 +471,8 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
             const int sl = ch / PER_SLOT, q = (ch % PER_SLOT) * 64 + lane;       // slot sl of the output = the sl-th oldest frame
             int rs = newest + 1 + sl;                             // < 2 C
             if (!ringm && rs >= C) rs -= C;
-            const uint4* rsrc = reinterpret_cast<const uint4*>((ringm ? out : ring) + (size_t)rs * CAR_PIX);
+            if (ahead) rs = sl;                                   // the current buffer already holds the frames that stay
+            const uint4* rsrc = reinterpret_cast<const uint4*>(((ringm || ahead) ? out : ring) + (size_t)rs * CAR_PIX);
             const uint4 v0 = rsrc[q], v1 = rsrc[q + 32];
             uint4* tdst = reinterpret_cast<uint4*>(tout + (size_t)sl * CAR_PIX);
             tdst[q] = v0; tdst[q + 32] = v1;
@@ -484,7 +487,21 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
         __syncthreads();
     }
     const uint4* src = reinterpret_cast<const uint4*>(img);
-    if (fill_all && ringm) {
+    if (ahead) {
+        uint4* tdst = (tout && !fill_all) ? reinterpret_cast<uint4*>(tout + (size_t)(C - 1) * CAR_PIX) : nullptr;
+        for (int j = 0; j < C; ++j) {                          // buffer j calls ahead: this frame is its channel C-1-j
+            int bi = p.rot_pos + j;
+            if (bi >= p.rot_n) bi -= p.rot_n;
+            uint8_t* buf = p.rot[bi] + (size_t)frame * C * CAR_PIX;
+            // after a reset every older slot holds the reset frame too: channels 0 .. C-1-j of that buffer
+            for (int ch = fill_all ? 0 : C - 1 - j; ch <= C - 1 - j; ++ch) {
+                uint4* dst = reinterpret_cast<uint4*>(buf + (size_t)ch * CAR_PIX);
+                for (int q = tid; q < CAR_PIX / 16; q += RASTER_THREADS) dst[q] = src[q];
+            }
+        }
+        if (tdst)
+            for (int q = tid; q < CAR_PIX / 16; q += RASTER_THREADS) tdst[q] = src[q];
+    } else if (fill_all && ringm) {
         for (int sl = 0; sl < 2 * C; ++sl) {
             uint4* dst = reinterpret_cast<uint4*>(out + (size_t)sl * CAR_PIX);
             for (int q = tid; q < CAR_PIX / 16; q += RASTER_THREADS) dst[q] = src[q];
@@ -578,7 +595,7 @@ cudaError_t car_raster_init() {
 }
 
 cudaError_t launch_car_stack_shift(const CarDev& p, uint8_t* obs, cudaStream_t s) {
-    if (p.ring_mode || p.c < 2) return cudaSuccess;
+    if (p.ring_mode || p.rot_n > 0 || p.c < 2) return cudaSuccess;
     const int n_units = p.n * p.players * (p.c - 1);
     car_stack_shift_kernel<<<min((n_units + 1) / 2, 2 * 148), SHIFT_THREADS, 0, s>>>(p, obs);
     return cudaGetLastError();
@@ -586,7 +603,7 @@ cudaError_t launch_car_stack_shift(const CarDev& p, uint8_t* obs, cudaStream_t s
 
 // stack mode: the frame ring moves on by one slot (after the render passes AND the stack shift of the step, which read ring_pos)
 cudaError_t launch_car_ring_advance(const CarDev& p, cudaStream_t s) {
-    if (p.ring_mode) return cudaSuccess;                        // ring mode: the phase is advanced on the host, per step
+    if (p.ring_mode || p.rot_n > 0) return cudaSuccess;         // ring mode: the phase is advanced on the host, per step
     car_ring_advance_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p);
     return cudaGetLastError();
 }
@@ -600,7 +617,7 @@ cudaError_t launch_car_render(const CarDev& p, int only_done, int which, int adv
     car_render_kernel<<<ctas, RASTER_THREADS, sizeof(RasterSmem), s>>>(p, only_done, which, obs, term_obs);
     e = cudaGetLastError();
     // ring mode: the phase is advanced on the host, per step; an auto-reset pass sets ring_pos itself
-    if (e != cudaSuccess || !advance || p.ring_mode || only_done) return e;
+    if (e != cudaSuccess || !advance || p.ring_mode || p.rot_n > 0 || only_done) return e;
     car_ring_advance_kernel<<<(p.n + 127) / 128, 128, 0, s>>>(p);
     return cudaGetLastError();
 }

@@ -228,10 +228,27 @@ int discard_pregen(crl_car* h, cudaStream_t s) {
     return CRL_OK;
 }
 
+// Ahead-write stack mode: the buffer of this call must be the next one of the registered rotation (any of them at a reset).
+int rotate_obs(crl_car* h, uint8_t* obs_dev, bool at_reset) {
+    CarDev& d = h->dev;
+    if (d.rot_n == 0) return CRL_OK;
+    if (at_reset) {
+        for (int i = 0; i < d.rot_n; ++i)
+            if (d.rot[i] == obs_dev) { d.rot_pos = i; return CRL_OK; }
+        return crl_set_error(CRL_E_INVALID, "obs_dev is not one of the %d buffers registered with crl_car_set_obs_rotation", d.rot_n);
+    }
+    const int next = (d.rot_pos + 1) % d.rot_n;
+    if (d.rot[next] != obs_dev)
+        return crl_set_error(CRL_E_INVALID, "obs_dev must be buffer %d of the registered rotation (the one after the last call's)", next);
+    d.rot_pos = next;
+    return CRL_OK;
+}
+bool moves_frames(const crl_car* h) { return !h->dev.ring_mode && h->dev.rot_n == 0 && h->dev.c >= 2; }   // internal ring + stack shift
+
 // Stack mode: start moving the frames that stay in the observation (ring -> channels 0 .. C-2 of obs) on the copy stream,
 // behind everything queued on `s` so far; join_stack_shift makes `s` wait for it (before the auto-reset pass).
 int fork_stack_shift(crl_car* h, uint8_t* obs_dev, cudaStream_t s) {
-    if (h->dev.ring_mode || h->dev.c < 2) return CRL_OK;
+    if (!moves_frames(h)) return CRL_OK;
     if (!h->copy_stream) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_copy_go, cudaEventDisableTiming));
@@ -245,7 +262,7 @@ int fork_stack_shift(crl_car* h, uint8_t* obs_dev, cudaStream_t s) {
 }
 
 int join_stack_shift(crl_car* h, cudaStream_t s) {
-    if (h->dev.ring_mode || h->dev.c < 2) return CRL_OK;
+    if (!moves_frames(h)) return CRL_OK;
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_copy_done, 0));
     return CRL_OK;
 }
@@ -439,6 +456,7 @@ int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream) {
     CHECK_HANDLE(h);
     if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
     cudaStream_t s = (cudaStream_t)stream;
+    if (int r = rotate_obs(h, obs_dev, true)) return r;
     CUDA_TRY(cudaMemsetAsync(h->dev.ring_pos, 0xFF, (size_t)h->dev.n * sizeof(int32_t), s));
     CUDA_TRY(cudaMemsetAsync(h->dev.env_done, 0, (size_t)h->dev.n, s));
     h->dev.ring_phase = 0;
@@ -466,7 +484,8 @@ int crl_car_render_obs(crl_car* h, uint8_t* obs_dev, uint8_t* term_obs_dev, void
     if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
     if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
     cudaStream_t s = (cudaStream_t)stream;
-    if (!h->dev.ring_mode && h->dev.c >= 2) LAUNCH(launch_car_stack_shift(h->dev, obs_dev, s), 1);   // the frames that stay: ring -> obs
+    if (int r = rotate_obs(h, obs_dev, false)) return r;
+    if (moves_frames(h)) LAUNCH(launch_car_stack_shift(h->dev, obs_dev, s), 1);   // the frames that stay: ring -> obs
     CUDA_TRY(cudaMemsetAsync(h->dev.done_count, 0, sizeof(int32_t), s));
     h->dev.collect_done = 1;
     LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, term_obs_dev, s), 4);   // post-step frame (terminal obs of finished envs)
@@ -483,6 +502,7 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
         if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
         if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
         cudaStream_t s1 = (cudaStream_t)stream;
+        if (int r = rotate_obs(h, obs_dev, false)) return r;
         if (int r = crl_car_step_state(h, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, stream)) return r;
         if (int r = fork_stack_shift(h, obs_dev, s1)) return r;                    // next to the render pass
         CUDA_TRY(cudaMemsetAsync(h->dev.done_count, 0, sizeof(int32_t), s1));
@@ -490,7 +510,7 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
         LAUNCH(launch_car_render(h->dev, 0, 0, 0, obs_dev, term_obs_dev, s1), 3);   // post-step frame (terminal obs of finished envs)
         h->dev.collect_done = 0;
         if (int r = join_stack_shift(h, s1)) return r;                             // it reads ring_pos; the auto-reset pass rewrites whole stacks
-        LAUNCH(launch_car_ring_advance(h->dev, s1), 1);
+        if (moves_frames(h)) LAUNCH(launch_car_ring_advance(h->dev, s1), 1);
         LAUNCH(launch_car_reset(h->dev, 1, s1), 1);                                 // auto-reset of finished envs
         LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s1), 3);        // their reset observation
         return kick_pregen(h, s1);
@@ -510,6 +530,7 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fast, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_slow, cudaEventDisableTiming));
     }
+    if (int r = rotate_obs(h, obs_dev, false)) return r;
     h->dev.fill_all = 0;
     if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
     CUDA_TRY(cudaMemsetAsync(h->dev.slow_count, 0, sizeof(int32_t), s));
@@ -529,7 +550,7 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
     LAUNCH(launch_car_render(h->dev, 0, 2, 0, obs_dev, term_obs_dev, s), 3);   // frames of the listed envs
     h->dev.collect_done = 0;
     if (int r = join_stack_shift(h, s)) return r;                             // it reads ring_pos; the auto-reset pass rewrites whole stacks
-    LAUNCH(launch_car_ring_advance(h->dev, s), 1);
+    if (moves_frames(h)) LAUNCH(launch_car_ring_advance(h->dev, s), 1);
     LAUNCH(launch_car_reset(h->dev, 1, s), 1);                                 // auto-reset of finished envs
     LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 3);        // their reset observation
     return kick_pregen(h, s);
@@ -587,9 +608,31 @@ int crl_car_render_state(crl_car* h, uint8_t* obs_dev, void* stream) {
     CHECK_HANDLE(h);
     if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before rendering");
     if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
+    if (int r = rotate_obs(h, obs_dev, false)) return r;
+    h->dev.fill_all = 0;
     if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
-    if (!h->dev.ring_mode && h->dev.c >= 2) LAUNCH(launch_car_stack_shift(h->dev, obs_dev, (cudaStream_t)stream), 1);
+    if (moves_frames(h)) LAUNCH(launch_car_stack_shift(h->dev, obs_dev, (cudaStream_t)stream), 1);
     LAUNCH(launch_car_render(h->dev, 0, 0, 1, obs_dev, nullptr, (cudaStream_t)stream), 4);
+    return CRL_OK;
+}
+
+int crl_car_set_obs_rotation(crl_car* h, uint8_t* const* obs_devs_host, int32_t count, void* stream) {
+    CHECK_HANDLE(h);
+    CarDev& d = h->dev;
+    if (count == 0) { d.rot_n = 0; d.rot_pos = 0; h->was_reset = false; return CRL_OK; }   // plain mode again, from the next reset on
+    if (d.ring_mode) return crl_set_error(CRL_E_STATE, "stack_mode ring has no use for a buffer rotation");
+    if (d.c < 2) return crl_set_error(CRL_E_STATE, "a buffer rotation needs frame_stack >= 2");
+    if (!obs_devs_host || count < d.c + 1 || count > CAR_MAX_ROTATION)
+        return crl_set_error(CRL_E_INVALID, "need frame_stack + 1 .. %d buffers, got %d", CAR_MAX_ROTATION, count);
+    for (int i = 0; i < count; ++i) {
+        if (!obs_devs_host[i]) return crl_set_error(CRL_E_INVALID, "null buffer %d", i);
+        for (int k = 0; k < i; ++k)
+            if (obs_devs_host[k] == obs_devs_host[i]) return crl_set_error(CRL_E_INVALID, "buffers %d and %d are the same", k, i);
+    }
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int i = 0; i < count; ++i) d.rot[i] = obs_devs_host[i];
+    d.rot_n = count; d.rot_pos = 0;
+    h->was_reset = false;                  // the stacks are rebuilt by the next reset
     return CRL_OK;
 }
 

@@ -210,6 +210,11 @@ struct Car {
                               dev_ptr<uint8_t>(truncated, at::kByte, dev(), n(), "truncated"),
                               opt_dev_ptr<uint8_t>(term, at::kByte, dev(), term_numel, "terminal observation"), stream_of(dev())));
     }
+    void set_obs_rotation(const std::vector<at::Tensor>& bufs) {
+        std::vector<uint8_t*> ptrs;
+        for (const at::Tensor& t : bufs) ptrs.push_back(dev_ptr<uint8_t>(t, at::kByte, dev(), obs_numel, "obs buffer of the rotation"));
+        check_rc(crl_car_set_obs_rotation(handle(), ptrs.data(), (int32_t)ptrs.size(), stream_of(dev())));
+    }
     int64_t ring_phase() {
         const int k = crl_car_ring_phase(handle());
         if (k < 0) check_rc(k);
@@ -283,6 +288,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         .def("reset", &Car::reset)
         .def("step", &Car::step)
         .def("ring_phase", &Car::ring_phase)
+        .def("set_obs_rotation", &Car::set_obs_rotation)
         .def("get_state", &Car::get_state)
         .def("set_state", &Car::set_state)
         .def("render_state", &Car::render_state)

@@ -275,6 +275,15 @@ int crl_car_set_state(crl_car* h, const double* state_dev, void* stream);
 int crl_car_render_state(crl_car* h, uint8_t* obs_dev, void* stream);
 /* stack_mode 1: slot k the last step wrote the new frames to (and to k + C).  0 after crl_car_reset. */
 int crl_car_ring_phase(crl_car* h);
+/* stack_mode 0 without moving frames (FrameStack, utils/atari_wrappers.py:222-259, as it is: a fully materialised
+ * [players * C][96][96] stack per env).  Register `count` >= frame_stack + 1 (<= 16) observation buffers of the usual
+ * layout; from then on crl_car_reset accepts any of them and the k-th crl_car_step / crl_car_render_obs /
+ * crl_car_render_state after it must be given the next one in rotation (CRL_E_INVALID otherwise).  Each new frame is
+ * written straight into the frame_stack buffers it will appear in (channel C-1 of the current one, C-2 of the next,
+ * ...), so the C-1 frames that stay are never copied and no internal ring is kept: the bytes a step writes are the
+ * observation bytes, and it reads none.  What a call returned stays intact for count - frame_stack further calls.
+ * count = 0 returns to the plain mode (caller-chosen buffer per call, internal ring + stack-shift kernel). */
+int crl_car_set_obs_rotation(crl_car* h, uint8_t* const* obs_devs_host, int32_t count, void* stream);
 /* number of tiles of env `env`'s current track, and (if non-NULL) its track points float64 [n][3] beta, x, y */
 int crl_car_get_track(crl_car* h, int32_t env, int32_t* n_out, double* pts_host, int32_t max_points, void* stream);
 

@@ -379,7 +379,7 @@ def test_autoreset_frame_matches_oracle():
     envs.close()
 
 
-@pytest.mark.parametrize("stack_mode", ["stack", "ring"])
+@pytest.mark.parametrize("stack_mode", ["stack", "stack-shift", "ring"])
 def test_mass_autoreset_runs_over_the_done_list(stack_mode):
     """Every env of a batch finishing in the same step (synchronous TimeLimit): the auto-reset passes run over the done
     list with grids smaller than the list (2048 frames here, 888 render CTAs), so the strided rounds are exercised.
@@ -413,6 +413,46 @@ def test_mass_autoreset_runs_over_the_done_list(stack_mode):
                 assert len(tr) != len(tracks0[k]) or not np.array_equal(tr, tracks0[k])
     assert int(whole.episode_stats()["episodes"]) == N
     for e in (whole, lo, hi):
+        e.check()
+        e.close()
+
+
+@pytest.mark.parametrize("env_id", ["cCarRacing-v0", "cCarRacingDouble-v0"])
+def test_three_stack_modes_return_the_same_observations(env_id):
+    """stack (frames written ahead into a rotation of registered buffers), stack-shift (internal ring + shift kernel) and
+    ring (strided view of a double-write ring) are three ways of producing the same FrameStack: identical observations,
+    terminal observations, rewards and dones over a rollout whose episodes end at different steps (pre-aged TimeLimit),
+    including what step t returned still being intact after step t + 1 (n_buffers = 2)."""
+    N, T = 48, 70
+    P = 2 if "Double" in env_id else 1
+    envs = {m: _make(env_id, N, seed=9, max_episode_steps=25, stack_mode=m, n_buffers=2) for m in ("stack", "stack-shift", "ring")}
+    flat = lambda x: x.flatten(1, 2) if x.dim() == 5 else x          # noqa: E731
+    o0 = {m: flat(e.reset()).clone() for m, e in envs.items()}
+    assert torch.equal(o0["stack"], o0["stack-shift"]) and torch.equal(o0["stack"], o0["ring"])
+    age = np.random.default_rng(0).integers(0, 25, N)
+    for e in envs.values():
+        e.set_elapsed(age)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    prev = None
+    n_done = 0
+    for t in range(T):
+        a = torch.rand((N, P, 2) if P == 2 else (N, 2), generator=gen, device="cuda") * 2 - 1
+        out = {m: e.step(a) for m, e in envs.items()}
+        o = {m: flat(out[m][0]) for m in envs}
+        assert torch.equal(o["stack"], o["stack-shift"]), t
+        assert torch.equal(o["stack"], o["ring"]), t
+        for m in ("stack-shift", "ring"):
+            assert torch.equal(out["stack"][1], out[m][1]) and torch.equal(out["stack"][2], out[m][2]), (t, m)
+        d = out["stack"][2].reshape(-1)                              # DummyVecEnv conventions: (N, 1)
+        if bool(d.any()):
+            n_done += int(d.sum())
+            tr = {m: flat(out[m][3].terminal_observation()) for m in envs}
+            assert torch.equal(tr["stack"][d], tr["stack-shift"][d]) and torch.equal(tr["stack"][d], tr["ring"][d]), t
+        if prev is not None:                                         # the previous step's tensor was not touched by this step
+            assert torch.equal(prev[0], prev[1]), t
+        prev = (out["stack"][0], out["stack"][0].clone())
+    assert n_done > 2 * N                                            # every env was reset a few times, at different steps
+    for e in envs.values():
         e.check()
         e.close()
 

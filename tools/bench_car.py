@@ -24,23 +24,31 @@ def run(env_id, n, steps, warmup, cpu_envs=0):
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     lib = _native.load()
     P = 2 if "Double" in env_id else 1
-    envs = make_envs(env_id, num_envs=n, frame_stack=4, log_dir=None, seed=1, asynchronous=True, n_buffers=1,
-                     first_env=rank * n)
+    envs = make_envs(env_id, num_envs=n, frame_stack=4, log_dir=None, seed=1, asynchronous=True, n_buffers=2,
+                     first_env=rank * n, stack_mode=os.environ.get("CRL_STACK_MODE", "stack"))
     envs.reset()
     dev = envs.device
     stream = torch.cuda.current_stream(dev)
     sp = ctypes.c_void_p(stream.cuda_stream)
     ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
-    b = envs._sets[0]
+
+    class Cur:                # the buffer set of the current call (stack mode: the next buffer of the env's registered rotation)
+        b = envs._sets[envs._cur]
+
+        def __getitem__(self, k):
+            return self.b[k]
+    b = Cur()
     actions = torch.zeros((n, P, 2), dtype=torch.float32, device=dev)
     h = envs._h
 
     def one_combined(t):      # the call the vec-env makes: crl_car_step (two-car envs: touching cars on a side stream)
+        b.b = envs.next_set()
         _native.check(lib.crl_car_random_actions(ptr(actions), actions.numel(), 7, t, sp))
         actions[:, :, 0].mul_(0.3)   # keep cars on the road for a realistic mix (still random)
         _native.check(lib.crl_car_step(h, ptr(actions), ptr(b["obs"]), ptr(b["rew"]), ptr(b["done"]), ptr(b["steps"]), ptr(b["trunc"]), None, sp))
 
     def one(t, ev=None):      # the two halves separately, for the per-kernel split
+        b.b = envs.next_set()
         _native.check(lib.crl_car_random_actions(ptr(actions), actions.numel(), 7, t, sp))
         actions[:, :, 0].mul_(0.3)
         if ev:

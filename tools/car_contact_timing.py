@@ -9,7 +9,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 lib = _native.load()
 for frac in (0.0, 0.03, 0.25, 1.0):
     birth = np.tile(np.arange(2)[None, None], (n, 4, 1)).astype(np.int32)
-    envs = make_envs("cCarRacingDouble-v0", num_envs=n, frame_stack=4, log_dir=None, seed=1, n_buffers=1)
+    envs = make_envs("cCarRacingDouble-v0", num_envs=n, frame_stack=4, log_dir=None, seed=1, n_buffers=1, stack_mode="stack-shift")
     envs.reset()
     s0 = envs.get_state().cpu().numpy()
     # which side is the other car on?  steer towards it for a fraction of the envs, away for the rest

@@ -26,7 +26,7 @@ def main():
     env_id = "cCarRacingDouble-v0" if a.double else "cCarRacing-v0"
     P_ = 2 if a.double else 1
     N = a.envs
-    envs = make_envs(env_id, num_envs=N, frame_stack=4, log_dir=None, seed=1, asynchronous=True, n_buffers=1)
+    envs = make_envs(env_id, num_envs=N, frame_stack=4, log_dir=None, seed=1, asynchronous=True, n_buffers=1, stack_mode="stack-shift")
     envs.reset()
     if a.age:
         envs.set_elapsed(np.random.default_rng(7).integers(0, 1000, N))

@@ -4,7 +4,7 @@ import torch
 from competitive_rl_b200 import _native, make_envs
 lib = _native.load()
 for env_id, n in [("cCarRacing-v0", 1024), ("cCarRacing-v0", 4096), ("cCarRacing-v0", 9472), ("cCarRacing-v0", 18944), ("cCarRacing-v0", 32768), ("cCarRacing-v0", 65536), ("cCarRacingDouble-v0", 16384)]:
-    envs = make_envs(env_id, num_envs=n, frame_stack=4, log_dir=None, seed=1, n_buffers=1)
+    envs = make_envs(env_id, num_envs=n, frame_stack=4, log_dir=None, seed=1, n_buffers=1, stack_mode="stack-shift")
     envs.reset()
     P = 2 if "Double" in env_id else 1
     stream = torch.cuda.current_stream(); sp = ctypes.c_void_p(stream.cuda_stream)

@@ -48,14 +48,14 @@ def main():
         N = a.envs or (16384 if a.double else 1024)
         env_id = "cCarRacingDouble-v0" if a.double else "cCarRacing-v0"
         PL = 2 if a.double else 1
-        envs = make_envs(env_id, num_envs=N, frame_stack=a.frame_stack, log_dir=None, seed=1, asynchronous=True, n_buffers=1,
+        envs = make_envs(env_id, num_envs=N, frame_stack=a.frame_stack, log_dir=None, seed=1, asynchronous=True, n_buffers=2,
                          stack_mode=a.stack_mode)
         envs.reset()
         if a.age:
             envs.set_elapsed(np.random.default_rng(7).integers(0, 1000, N))
-        b = envs._sets[0]
         actions = torch.zeros((N, PL, 2), dtype=torch.float32, device="cuda")
         for t in range(a.steps):
+            b = envs.next_set()              # stack mode: the next buffer of the rotation the env registered
             _native.check(lib.crl_car_random_actions(P(actions), actions.numel(), 7, t, sp))
             _native.check(lib.crl_car_step(envs._h, P(actions), P(b["obs"]), P(b["rew"]), P(b["done"]), P(b["steps"]), P(b["trunc"]),
                                            P(b["term"]), sp))
