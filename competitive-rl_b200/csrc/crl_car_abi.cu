@@ -331,7 +331,6 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     ALLOC(d.attempt_count, n); ALLOC(d.inv_dt0, n); ALLOC(d.env_done, n); ALLOC(d.ring_pos, n);
     ALLOC(d.body, nc * 40); ALLOC(d.joint, nc * 24); ALLOC(d.wheel, nc * 8); ALLOC(d.reward, nc * 2);
     ALLOC(d.counters, nc * 4); ALLOC(d.touching, nc * 64); ALLOC(d.visited, nc * 16); ALLOC(d.sensor_now, nc * 64);
-    if (!d.ring_mode) ALLOC(d.ring, nc * d.c * CAR_PIX);
     ALLOC(d.overrun, 4); ALLOC(d.stats, 8);
     ALLOC(d.contact_overflow, 1);
     {
@@ -457,6 +456,8 @@ int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream) {
     if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
     cudaStream_t s = (cudaStream_t)stream;
     if (int r = rotate_obs(h, obs_dev, true)) return r;
+    if (!h->dev.ring_mode && h->dev.rot_n == 0 && h->dev.ring == nullptr)   // the internal frame ring of the plain stack mode, on first use (1.2 GB at config 5)
+        CUDA_TRY(car_alloc(h, &h->dev.ring, (size_t)h->dev.n * h->dev.players * h->dev.c * CAR_PIX));
     CUDA_TRY(cudaMemsetAsync(h->dev.ring_pos, 0xFF, (size_t)h->dev.n * sizeof(int32_t), s));
     CUDA_TRY(cudaMemsetAsync(h->dev.env_done, 0, (size_t)h->dev.n, s));
     h->dev.ring_phase = 0;

@@ -457,6 +457,26 @@ def test_three_stack_modes_return_the_same_observations(env_id):
         e.close()
 
 
+def test_without_frame_stack_the_observation_is_the_newest_frame():
+    """frame_stack=None (make_car_racing without FrameStack): (N, players, 96, 96), equal to the newest channel of a stacked env."""
+    N = 6
+    plain = _make("cCarRacingDouble-v0", N, seed=4, frame_stack=None, max_episode_steps=9)
+    stacked = _make("cCarRacingDouble-v0", N, seed=4, frame_stack=4, max_episode_steps=9)
+    op, os_ = plain.reset(), stacked.reset()
+    assert tuple(op.shape) == (N, 2, 96, 96)
+    assert torch.equal(op[:, 0], os_[:, 3]) and torch.equal(op[:, 1], os_[:, 7])
+    a = torch.zeros((N, 2, 2), device="cuda")
+    a[:, :, 1] = 0.5
+    a[:, 1, 0] = -0.2
+    for t in range(20):                                              # two TimeLimit resets inside
+        op, rp, dp, _ = plain.step(a)
+        os_, rs, ds, _ = stacked.step(a)
+        assert torch.equal(op[:, 0], os_[:, 3]) and torch.equal(op[:, 1], os_[:, 7]), t
+        assert torch.equal(rp, rs) and torch.equal(dp, ds), t
+    plain.check(); stacked.check()
+    plain.close(); stacked.close()
+
+
 def test_car_sharding_invariance():
     """Tracks and spawn order come from an RNG keyed by the GLOBAL env index, and nothing in a step crosses envs: two
     shards of 128 two-car envs reproduce one batch of 256 bit for bit -- states, rewards, dones, contacts, frames
