@@ -153,16 +153,20 @@ __device__ void paint_cars(RasterSmem& S, int players, int lane) {
     }
 }
 
-// The auto-reset passes (only_done) run over the frames of the envs on the done list: position i -> frame.  The render
-// kernel of such a pass is launched with DONE_PASS_CTAS blocks that stride over the list.
-constexpr int DONE_PASS_CTAS = 148 * 6;
-__device__ __forceinline__ int listed_frames(const CarDev& p, int only_done) {
-    return only_done ? min(*p.done_count, p.n) * p.players : p.n * p.players;
+// Two kinds of passes run over a list of envs instead of over all of them: the auto-reset passes (only_done: the done
+// list the post-step render built) and the pass over the envs of the slow physics pass (which == 2: the slow list of the
+// sensor kernel).  Position i on the list -> frame; the render kernel of such a pass is launched with at most
+// LIST_PASS_CTAS blocks that stride over the list.
+constexpr int LIST_PASS_CTAS = 148 * 6;
+__device__ __forceinline__ int listed_frames(const CarDev& p, int only_done, int which) {
+    if (only_done) return min(*p.done_count, p.n) * p.players;
+    if (which == 2) return min(*p.slow_count, p.n) * p.players;
+    return p.n * p.players;
 }
-__device__ __forceinline__ int listed_frame(const CarDev& p, int only_done, int i) {
-    if (!only_done) return i;
+__device__ __forceinline__ int listed_frame(const CarDev& p, int only_done, int which, int i) {
+    if (!only_done && which != 2) return i;
     const int k = i / p.players;
-    return p.done_list[k] * p.players + (i - k * p.players);
+    return (only_done ? p.done_list[k] : p.slow_list[k]) * p.players + (i - k * p.players);
 }
 
 // Per-frame setup, part 1, one thread per (env, player) frame: camera and the integer screen -> road-map mapping (a serial
@@ -170,10 +174,10 @@ __device__ __forceinline__ int listed_frame(const CarDev& p, int only_done, int 
 __global__ void __launch_bounds__(128)
 car_frame_setup_kernel(CarDev p, int only_done, int which) {
     int frame = blockIdx.x * blockDim.x + threadIdx.x;             // env * players + player; auto-reset pass: position on the done list
-    if (frame >= listed_frames(p, only_done)) return;
-    frame = listed_frame(p, only_done, frame);
+    if (frame >= listed_frames(p, only_done, which)) return;
+    frame = listed_frame(p, only_done, which, frame);
     const int e = frame / p.players;
-    if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
+    if (which == 1 && p.deferred[e] != 0) return;                  // the envs of the slow physics pass come in their own pass (over the slow list)
     const CarHullConst* K = p.consts;
     const double obs_scale = car_obs_scale();
     FrameMap m;
@@ -234,10 +238,10 @@ car_frame_aux_kernel(CarDev p, int only_done, int which) {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     int frame = gt >> 4;
     const int l = gt & 15;
-    if (frame >= listed_frames(p, only_done)) return;
-    frame = listed_frame(p, only_done, frame);
+    if (frame >= listed_frames(p, only_done, which)) return;
+    frame = listed_frame(p, only_done, which, frame);
     const int e = frame / p.players, pi = frame - e * p.players;
-    if (which != 0 && (p.deferred[e] != 0) != (which == 2)) return;
+    if (which == 1 && p.deferred[e] != 0) return;                  // the envs of the slow physics pass come in their own pass (over the slow list)
     const CarHullConst* K = p.consts;
     const double obs_scale = car_obs_scale();
     const FrameMap& m = p.frame_map[frame];
@@ -359,11 +363,11 @@ car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs,
     extern __shared__ __align__(16) uint8_t smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_listed = listed_frames(p, only_done);
+    const int n_listed = listed_frames(p, only_done, which);
   for (int it = blockIdx.x; it < n_listed; it += gridDim.x) {        // a post-step pass has one CTA per frame: a single round
-    const int frame = listed_frame(p, only_done, it);  // env * players + player
+    const int frame = listed_frame(p, only_done, which, it);   // env * players + player
     const int e = (p.players == 2) ? frame >> 1 : frame;          // players is 1 or 2
-    if (which != 0 && (p.deferred[e] != 0) != (which == 2)) continue;
+    if (which == 1 && p.deferred[e] != 0) continue;              // the envs of the slow physics pass come in their own pass (over the slow list)
     if (tid == 0 && (p.players == 1 || (frame & 1) == 0)) {
         if (only_done) p.ring_pos[e] = p.c - 1;        // every ring slot holds the reset frame (nobody reads ring_pos in this pass)
         else if (p.collect_done && p.env_done[e]) {    // finished in this step: onto the list the auto-reset passes run over
@@ -613,7 +617,7 @@ cudaError_t launch_car_render(const CarDev& p, int only_done, int which, int adv
     car_frame_aux_kernel<<<(p.n * p.players * 16 + 127) / 128, 128, 0, s>>>(p, only_done, which);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    const int ctas = only_done ? min(p.n * p.players, DONE_PASS_CTAS) : p.n * p.players;
+    const int ctas = (only_done || which == 2) ? min(p.n * p.players, LIST_PASS_CTAS) : p.n * p.players;
     car_render_kernel<<<ctas, RASTER_THREADS, sizeof(RasterSmem), s>>>(p, only_done, which, obs, term_obs);
     e = cudaGetLastError();
     // ring mode: the phase is advanced on the host, per step; an auto-reset pass sets ring_pos itself
