@@ -37,6 +37,10 @@ struct crl_car {
     // stack mode: the C - 1 frames that stay in the observation are moved ring -> obs on this stream while the physics runs
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy_go = nullptr, ev_copy_done = nullptr;
+    // the sensor kernel of the NEXT step, started on its own stream as soon as this step's auto-resets are done
+    cudaStream_t sens_stream = nullptr;
+    cudaEvent_t ev_sens_go = nullptr, ev_sens_done = nullptr;
+    bool sensors_ahead = false;      // sensor_now (and, two-car envs, slow list / deferred) of the current poses are in flight or ready
     // next tracks are generated ahead of time on this stream (car_pregen_kernel); at most one launch in flight
     cudaStream_t pregen_stream = nullptr;
     cudaEvent_t ev_pregen_go = nullptr;
@@ -261,6 +265,48 @@ int fork_stack_shift(crl_car* h, uint8_t* obs_dev, cudaStream_t s) {
     return CRL_OK;
 }
 
+// The wheel-tile overlaps (and, two-car envs, the slow list) the NEXT step needs depend only on the poses this step leaves
+// behind: started on their own stream behind everything queued on `s` so far (the auto-reset spawns included), they run
+// under the auto-reset render passes instead of at the head of the next step.
+int sensors_ahead_of_next_step(crl_car* h, cudaStream_t s) {
+    if (!h->sens_stream) {
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&h->sens_stream, cudaStreamNonBlocking, hi));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_sens_go, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_sens_done, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(h->ev_sens_go, s));
+    CUDA_TRY(cudaStreamWaitEvent(h->sens_stream, h->ev_sens_go, 0));
+    if (h->dev.players == 2) CUDA_TRY(cudaMemsetAsync(h->dev.slow_count, 0, sizeof(int32_t), h->sens_stream));
+    LAUNCH(launch_car_sensors(h->dev, h->dev.players == 2 ? 1 : 0, h->sens_stream), 1);
+    CUDA_TRY(cudaEventRecord(h->ev_sens_done, h->sens_stream));
+    h->sensors_ahead = true;
+    return CRL_OK;
+}
+
+// At the head of a step: wait for the sensors started ahead, or run them now (first step, after set_state / reset, or
+// when the plain schedule of crl_car_step_state wants them without the slow list).
+int sensors_for_this_step(crl_car* h, int classify, cudaStream_t s) {
+    if (h->sensors_ahead) {
+        CUDA_TRY(cudaStreamWaitEvent(s, h->ev_sens_done, 0));
+        h->sensors_ahead = false;
+        if (classify || h->dev.players == 1) return CRL_OK;      // what was computed ahead is what this step wants
+    }
+    if (classify) CUDA_TRY(cudaMemsetAsync(h->dev.slow_count, 0, sizeof(int32_t), s));
+    LAUNCH(launch_car_sensors(h->dev, classify, s), 1);
+    return CRL_OK;
+}
+
+// Before anything that moves the cars between steps (reset, set_state): what was computed ahead no longer holds, and the
+// kernel computing it must not be reading the bodies while they are rewritten.
+int drop_sensors_ahead(crl_car* h, cudaStream_t s) {
+    if (!h->sensors_ahead) return CRL_OK;
+    CUDA_TRY(cudaStreamWaitEvent(s, h->ev_sens_done, 0));
+    h->sensors_ahead = false;
+    return CRL_OK;
+}
+
 int join_stack_shift(crl_car* h, cudaStream_t s) {
     if (!moves_frames(h)) return CRL_OK;
     CUDA_TRY(cudaStreamWaitEvent(s, h->ev_copy_done, 0));
@@ -281,6 +327,10 @@ int crl_car_destroy(crl_car* h) {
     if (h->ev_slow) cudaEventDestroy(h->ev_slow);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    if (h->sens_stream) cudaStreamSynchronize(h->sens_stream);
+    if (h->ev_sens_go) cudaEventDestroy(h->ev_sens_go);
+    if (h->ev_sens_done) cudaEventDestroy(h->ev_sens_done);
+    if (h->sens_stream) cudaStreamDestroy(h->sens_stream);
     if (h->ev_copy_go) cudaEventDestroy(h->ev_copy_go);
     if (h->ev_copy_done) cudaEventDestroy(h->ev_copy_done);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -456,6 +506,7 @@ int crl_car_reset(crl_car* h, uint8_t* obs_dev, void* stream) {
     if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
     cudaStream_t s = (cudaStream_t)stream;
     if (int r = rotate_obs(h, obs_dev, true)) return r;
+    if (int r = drop_sensors_ahead(h, s)) return r;
     if (!h->dev.ring_mode && h->dev.rot_n == 0 && h->dev.ring == nullptr)   // the internal frame ring of the plain stack mode, on first use (1.2 GB at config 5)
         CUDA_TRY(car_alloc(h, &h->dev.ring, (size_t)h->dev.n * h->dev.players * h->dev.c * CAR_PIX));
     CUDA_TRY(cudaMemsetAsync(h->dev.ring_pos, 0xFF, (size_t)h->dev.n * sizeof(int32_t), s));
@@ -475,7 +526,7 @@ int crl_car_step_state(crl_car* h, const float* actions_dev, float* rew_dev, uin
     if (!actions_dev || !rew_dev || !done_dev || !num_steps_dev || !truncated_dev) return crl_set_error(CRL_E_INVALID, "null step buffer");
     h->dev.fill_all = 0;
     if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
-    LAUNCH(launch_car_sensors(h->dev, 0, (cudaStream_t)stream), 1);
+    if (int r = sensors_for_this_step(h, 0, (cudaStream_t)stream)) return r;
     LAUNCH(launch_car_step(h->dev, 0, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, (cudaStream_t)stream), 1);
     return CRL_OK;
 }
@@ -513,6 +564,7 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
         if (int r = join_stack_shift(h, s1)) return r;                             // it reads ring_pos; the auto-reset pass rewrites whole stacks
         if (moves_frames(h)) LAUNCH(launch_car_ring_advance(h->dev, s1), 1);
         LAUNCH(launch_car_reset(h->dev, 1, s1), 1);                                 // auto-reset of finished envs
+        if (int r = sensors_ahead_of_next_step(h, s1)) return r;
         LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s1), 3);        // their reset observation
         return kick_pregen(h, s1);
     }
@@ -534,9 +586,8 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
     if (int r = rotate_obs(h, obs_dev, false)) return r;
     h->dev.fill_all = 0;
     if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
-    CUDA_TRY(cudaMemsetAsync(h->dev.slow_count, 0, sizeof(int32_t), s));
     CUDA_TRY(cudaMemsetAsync(h->dev.done_count, 0, sizeof(int32_t), s));
-    LAUNCH(launch_car_sensors(h->dev, 1, s), 1);                               // wheel-tile overlaps + the slow list
+    if (int r = sensors_for_this_step(h, 1, s)) return r;                      // wheel-tile overlaps + the slow list
     CUDA_TRY(cudaEventRecord(h->ev_fast, s));
     CUDA_TRY(cudaStreamWaitEvent(h->side_stream, h->ev_fast, 0));
     LAUNCH(launch_car_step(h->dev, 2, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, h->side_stream), 1);
@@ -553,6 +604,7 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
     if (int r = join_stack_shift(h, s)) return r;                             // it reads ring_pos; the auto-reset pass rewrites whole stacks
     if (moves_frames(h)) LAUNCH(launch_car_ring_advance(h->dev, s), 1);
     LAUNCH(launch_car_reset(h->dev, 1, s), 1);                                 // auto-reset of finished envs
+    if (int r = sensors_ahead_of_next_step(h, s)) return r;
     LAUNCH(launch_car_render(h->dev, 1, 0, 1, obs_dev, nullptr, s), 3);        // their reset observation
     return kick_pregen(h, s);
 }
@@ -601,6 +653,7 @@ int crl_car_set_state(crl_car* h, const double* state_dev, void* stream) {
     CHECK_HANDLE(h);
     if (!state_dev) return crl_set_error(CRL_E_INVALID, "null buffer");
     if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before set_state");
+    if (int r = drop_sensors_ahead(h, (cudaStream_t)stream)) return r;
     LAUNCH(launch_car_set_state(h->dev, state_dev, (cudaStream_t)stream), 1);
     return CRL_OK;
 }
