@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcrl_b200.so")
 
 CRL_OK = 0
+CRL_E_INVALID, CRL_E_CUDA, CRL_E_STATE, CRL_E_SERVES = -1, -2, -3, -4   # include/crl_b200.h
 ATLAS_SHAPE = (22, 22, 34, 160, 3)
 DEFAULT_ATLAS = os.path.join(_HERE, "data", "scoreboard_atlas.npz")
 

@@ -202,3 +202,38 @@ def test_invalid_actions_are_rejected():
         double.check()
     double.close()
     twin.close()
+
+
+def test_car_obs_rotation_is_checked_at_the_c_abi():
+    """crl_car_set_obs_rotation: too few / duplicate buffers are refused, and once a rotation is registered a call given
+    any buffer but the next one fails with CRL_E_INVALID instead of silently writing the wrong stack."""
+    from competitive_rl_b200 import _native, make_envs
+    lib = _native.load()
+    N = 4
+    envs = make_envs("cCarRacing-v0", num_envs=N, frame_stack=4, log_dir=None, seed=2, stack_mode="stack-shift")
+    h = envs._h
+    sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    bufs = [torch.zeros((N, 4, 96, 96), dtype=torch.uint8, device="cuda") for _ in range(5)]
+
+    def register(tensors):
+        arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+        return lib.crl_car_set_obs_rotation(h, arr, len(tensors), sp)
+
+    assert register(bufs[:4]) == _native.CRL_E_INVALID                       # needs frame_stack + 1 buffers
+    assert register(bufs[:4] + [bufs[0]]) == _native.CRL_E_INVALID           # the same buffer twice
+    assert register(bufs) == 0
+    b = envs._sets[0]
+    act = torch.zeros((N, 2), dtype=torch.float32, device="cuda")
+    step = lambda o: lib.crl_car_step(h, p(act), p(o), p(b["rew"]), p(b["done"]), p(b["steps"]), p(b["trunc"]), None, sp)  # noqa: E731
+    assert step(bufs[1]) == _native.CRL_E_STATE                              # the stacks are rebuilt by a reset first
+    assert lib.crl_car_reset(h, p(b["obs"]), sp) == _native.CRL_E_INVALID    # not a registered buffer
+    assert lib.crl_car_reset(h, p(bufs[3]), sp) == 0                         # any registered buffer may start the rotation
+    assert step(bufs[3]) == _native.CRL_E_INVALID and step(bufs[0]) == _native.CRL_E_INVALID
+    assert step(bufs[4]) == 0 and step(bufs[0]) == 0 and step(bufs[1]) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(bufs[1][:, 2], bufs[0][:, 3]) and torch.equal(bufs[1][:, 1], bufs[4][:, 3])   # the frames are where FrameStack puts them
+    assert torch.equal(bufs[1][:, 0], bufs[3][:, 3])                         # ... down to the reset frame
+    assert lib.crl_car_set_obs_rotation(h, None, 0, sp) == 0                 # back to the plain mode (after a reset)
+    assert lib.crl_car_reset(h, p(b["obs"]), sp) == 0 and step(b["obs"]) == 0
+    envs.close()
