@@ -129,10 +129,13 @@ struct CarDev {
     // ---- car-car contacts (players == 2): [n][CAR_MAX_CONTACTS] records, [n] counts, one overflow counter ----
     CarContact* contacts;
     int32_t* n_contacts;
+    int32_t* n_contacts_step;    // [n] contacts the last executed (sub-)step worked with: the diagnostic of crl_car_get_contacts
     int32_t* contact_overflow;
     // two-pass stepping of two-car envs (car_step_kernel modes 1 / 2): envs whose cars are near each other
-    int32_t* slow_list;       // [n]
+    int32_t* slow_list;       // [n] envs with a touching pair of fixtures this step (car_collide_kernel): merged islands
     int32_t* slow_count;      // [1]
+    int32_t* near_list;       // [n] envs whose cars are near each other (oriented-box gate of the sensor kernel)
+    int32_t* near_count;      // [1] = slow_count + 1: both cleared by one memset
     uint8_t* deferred;        // [n] 1 = on the slow list this step
     // envs that finished in this step, listed by the post-step render passes (collect_done = 1) so that the auto-reset
     // kernels run over the list instead of launching a thread block per env
@@ -176,6 +179,8 @@ cudaError_t launch_car_pregen(const CarDev& p, cudaStream_t s);        // next t
 cudaError_t launch_car_discard_next(const CarDev& p, cudaStream_t s);  // forget pre-generated tracks (seed / injection changed)
 // wheel-tile overlaps, before launch_car_step; classify = 1: also the slow list of the two-pass schedule (slow_count cleared before)
 cudaError_t launch_car_sensors(const CarDev& p, int classify, cudaStream_t s);
+// two-car envs: manifolds of the near envs, one thread per fixture pair; fills the slow list (after launch_car_sensors(classify = 1))
+cudaError_t launch_car_collide(const CarDev& p, cudaStream_t s);
 cudaError_t launch_car_step(const CarDev& p, int mode, const float* actions, float* rew, uint8_t* done, int32_t* num_steps,
                             uint8_t* truncated, cudaStream_t s);
 // which: 0 = every frame, 1 = envs not deferred to the slow stepping pass, 2 = deferred envs only; advance: move the frame ring on

@@ -685,13 +685,13 @@ __global__ void __launch_bounds__(128) car_sensor_kernel(CarDev p, int classify)
     const Rot qh = make_rot(b[2]);
     const F2 hp = f2(b[0], b[1]) - rmul(qh, f2(p.consts->hull_lcx, p.consts->hull_lcy));
     const int slot = car_slot(p, e);
-    // two-car envs, two-pass stepping: the env whose cars are near each other goes on the slow list (see car_step_kernel)
+    // two-car envs: the env whose cars are near each other goes on the near list (car_collide_kernel, then car_step_kernel)
     if (classify && p.players == 2 && (gt & 7) == 0) {
         const float* b1 = b + 40;
         const float pose[10][3] = {{b[0], b[1], b[2]}, {}, {}, {}, {}, {b1[0], b1[1], b1[2]}, {}, {}, {}, {}};
-        const bool deferred = cars_near(pose, p.consts->hull_lcx, p.consts->hull_lcy, p.step_count[e]);
-        if (deferred) p.slow_list[atomicAdd(p.slow_count, 1)] = e;
-        p.deferred[e] = deferred ? 1 : 0;
+        const bool near = cars_near(pose, p.consts->hull_lcx, p.consts->hull_lcy, p.step_count[e]);
+        if (near) p.near_list[atomicAdd(p.near_count, 1)] = e;       // car_collide_kernel decides whether they touch
+        else { p.deferred[e] = 0; p.n_contacts[e] = 0; }
     }
     // the prefilter on every 8th track point depends on the hull only: the four wheel lanes of a car take a quarter of the
     // (at most 64) points each and pool what they found
@@ -712,6 +712,89 @@ __global__ void __launch_bounds__(128) car_sensor_kernel(CarDev p, int classify)
 
 __device__ __noinline__ void sensor_car_overlaps(const CarDev& p, int ci, int slot, int n_track, F2 hp, const F2* c, const float* a) {
     for (int k = 0; k < 4; ++k) sensor_wheel_overlaps(p, slot, n_track, hp, c[k + 1], a[k + 1], p.sensor_now + ((size_t)ci * 4 + k) * 16, 0ull, false);
+}
+
+// b2ContactManager::Collide between the two cars of every env on the NEAR list (the oriented-box gate of the sensor
+// kernel), ahead of the step kernel and in parallel: one 64-thread block per env, one thread per allowed fixture pair
+// (48: hull-hull 16, wheel-hull 2 x 16).  Like the tile sensors, the manifolds depend only on the poses the previous
+// step left behind; inside the one-lane-per-car step kernel the 48 b2CollidePolygons calls ran one after the other and
+// were the longest part of the slow physics pass (0.32 of 0.64 ms at config 5).  Same arithmetic and the same canonical
+// record order as car_contacts_collide (which stays for the further sub-steps of action_repeat > 1).  Envs that come out
+// with a touching pair go on the slow list (merged island: sequential contact pass); the others are stepped by the fast pass.
+__global__ void __launch_bounds__(64) car_collide_kernel(CarDev p) {
+    __shared__ Xf s_xf[10];
+    __shared__ F2 s_wc[16];
+    __shared__ int s_cnt0, s_nold;
+    __shared__ uint8_t s_old_pair[CAR_MAX_CONTACTS], s_old_count[CAR_MAX_CONTACTS];
+    __shared__ uint32_t s_old_id[CAR_MAX_CONTACTS][2];
+    __shared__ float s_old_ni[CAR_MAX_CONTACTS][2], s_old_ti[CAR_MAX_CONTACTS][2];
+    const CarHullConst* K = p.consts;
+    const int t = threadIdx.x;
+    const int n_near = min(*p.near_count, p.n);
+    for (int li = blockIdx.x; li < n_near; li += gridDim.x) {
+        const int e = p.near_list[li];
+        CarContact* recs = p.contacts + (size_t)e * CAR_MAX_CONTACTS;
+        if (t < 10) {
+            const float* b = p.body + ((size_t)e * 2 + t / 5) * 40 + 8 * (t % 5);
+            s_xf[t] = xf_of(f2(b[0], b[1]), b[2], body_lc(K, t));
+        }
+        if (t == 32) s_nold = min(max(p.n_contacts[e], 0), CAR_MAX_CONTACTS);
+        if (t >= 48 && t < 48 + CAR_MAX_CONTACTS) {          // the previous step's records: what the warm start needs of them
+            const CarContact* o = recs + (t - 48);
+            s_old_pair[t - 48] = o->pair; s_old_count[t - 48] = o->count;
+            s_old_id[t - 48][0] = o->id[0]; s_old_id[t - 48][1] = o->id[1];
+            s_old_ni[t - 48][0] = o->ni[0]; s_old_ni[t - 48][1] = o->ni[1];
+            s_old_ti[t - 48][0] = o->ti[0]; s_old_ti[t - 48][1] = o->ti[1];
+        }
+        __syncthreads();
+        if (t < 16) {      // world centroids of the 8 fixtures of each car
+            const int car = t >> 3, f = t & 7;
+            const int b = 5 * car + (f < 4 ? 0 : f - 3), sh = f < 4 ? f : 4;
+            s_wc[t] = xf_mul(s_xf[b], f2(K->fix_cx[sh], K->fix_cy[sh]));
+        }
+        __syncthreads();
+        CarContact m;
+        m.count = 0;
+        int ba = 0, bb = 5;
+        if (t < 48) {
+            const int fa = t < 32 ? t >> 3 : 4 + ((t - 32) >> 2), fb = t < 32 ? t & 7 : (t - 32) & 3;
+            ba = fa < 4 ? 0 : fa - 3; bb = 5 + (fb < 4 ? 0 : fb - 3);
+            const int sa = fa < 4 ? fa : 4, sb = fb < 4 ? fb : 4;
+            // quick reject of pairs farther apart than their bounding circles plus 0.15 (see car_contacts_collide)
+            const F2 d = s_wc[8 + fb] - s_wc[fa];
+            const float reach = K->fix_cradius[sa] + K->fix_cradius[sb] + 0.15f;
+            if (!(dot(d, d) > reach * reach)) collide_polygons(&m, poly_ref(K, sa), s_xf[ba], poly_ref(K, sb), s_xf[bb]);
+        }
+        const bool touching = m.count != 0;
+        const unsigned ball = __ballot_sync(0xffffffffu, touching);
+        if (t == 0) s_cnt0 = __popc(ball);
+        __syncthreads();
+        const int rank = (t < 32 ? 0 : s_cnt0) + __popc(ball & ((1u << (t & 31)) - 1u));   // canonical order = pair index
+        int n_new = s_cnt0;
+        if (t >= 32) n_new += __popc(ball);
+        n_new = __shfl_sync(0xffffffffu, n_new, 0);                                        // warp 1 holds the total
+        if (touching) {
+            if (rank >= CAR_MAX_CONTACTS) atomicAdd(p.contact_overflow, 1);
+            else {
+                m.pair = (uint8_t)t; m.ia = (uint8_t)ba; m.ib = (uint8_t)bb; m.vcount = m.count;
+                for (int i = 0; i < m.count; ++i) { m.ni[i] = 0.f; m.ti[i] = 0.f; }
+                for (int o = 0; o < s_nold; ++o) {
+                    if (s_old_pair[o] != t) continue;
+                    for (int i = 0; i < m.count; ++i)
+                        for (int j = 0; j < s_old_count[o]; ++j)
+                            if (s_old_id[o][j] == m.id[i]) { m.ni[i] = s_old_ni[o][j]; m.ti[i] = s_old_ti[o][j]; break; }
+                }
+                recs[rank] = m;
+            }
+        }
+        if (t == 32) {                                       // a thread of warp 1: it knows the total
+            const int kept = min(n_new, CAR_MAX_CONTACTS);
+            p.n_contacts[e] = kept;
+            p.deferred[e] = kept > 0 ? 1 : 0;
+            if (kept > 0) p.slow_list[atomicAdd(p.slow_count, 1)] = e;
+        }
+        __syncthreads();
+    }
 }
 
 // mode 0: every car.  mode 1 (fast pass): two-car envs whose cars are near each other are skipped: car_sensor_kernel put
@@ -929,17 +1012,22 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                 for (int i = 0; i < 5; ++i) { pose[player * 5 + i][0] = c[i].x; pose[player * 5 + i][1] = c[i].y; pose[player * 5 + i][2] = a[i]; }
                 __syncwarp(pair_mask);
                 recs = p.contacts + (size_t)e * CAR_MAX_CONTACTS;
-                const bool near_each_other = cars_near(pose, hull_lcx, hull_lcy, step_count);
-                if (near_each_other) {
-                    if (player == 0) {
-                        n_con = car_contacts_collide(p.consts, pose, recs, p.n_contacts[e], p.contact_overflow);
-                        p.n_contacts[e] = n_con;
+                if (rep == 0) {
+                    n_con = p.n_contacts[e];       // car_sensor_kernel (far: 0) / car_collide_kernel, from the poses at the start of the step
+                } else {                           // a further sub-step of the same action: from the poses it now has
+                    const bool near_each_other = cars_near(pose, hull_lcx, hull_lcy, step_count);
+                    if (near_each_other) {
+                        if (player == 0) {
+                            n_con = car_contacts_collide(p.consts, pose, recs, p.n_contacts[e], p.contact_overflow);
+                            p.n_contacts[e] = n_con;
+                        }
+                        n_con = __shfl_sync(pair_mask, n_con, threadIdx.x & 30);
+                    } else if (player == 0) {
+                        p.n_contacts[e] = 0;
                     }
-                    n_con = __shfl_sync(pair_mask, n_con, threadIdx.x & 30);
-                } else if (player == 0) {
-                    p.n_contacts[e] = 0;
                 }
             }
+            if (p.players == 2 && player == 0) p.n_contacts_step[e] = n_con;   // what crl_car_get_contacts reports (n_contacts is rewritten ahead of the next step)
             const bool merged = n_con > 0;
             // ---- b2Island::Solve for this car's island (bodies: hull + 4 wheels; joints relaxed in the
             //      order wheel 3, 2, 1, 0 -- the island order b2World::Solve's DFS produces) ----
@@ -1277,6 +1365,12 @@ cudaError_t launch_car_step(const CarDev& p, int mode, const float* actions, flo
 
 cudaError_t launch_car_sensors(const CarDev& p, int classify, cudaStream_t s) {
     car_sensor_kernel<<<(p.n * p.players * 4 + 127) / 128, 128, 0, s>>>(p, classify);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_car_collide(const CarDev& p, cudaStream_t s) {
+    if (p.players != 2) return cudaSuccess;
+    car_collide_kernel<<<min(p.n, 148 * 16), 64, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -278,23 +278,26 @@ int sensors_ahead_of_next_step(crl_car* h, cudaStream_t s) {
     }
     CUDA_TRY(cudaEventRecord(h->ev_sens_go, s));
     CUDA_TRY(cudaStreamWaitEvent(h->sens_stream, h->ev_sens_go, 0));
-    if (h->dev.players == 2) CUDA_TRY(cudaMemsetAsync(h->dev.slow_count, 0, sizeof(int32_t), h->sens_stream));
+    if (h->dev.players == 2) CUDA_TRY(cudaMemsetAsync(h->dev.slow_count, 0, 2 * sizeof(int32_t), h->sens_stream));   // slow + near counts
     LAUNCH(launch_car_sensors(h->dev, h->dev.players == 2 ? 1 : 0, h->sens_stream), 1);
+    if (h->dev.players == 2) LAUNCH(launch_car_collide(h->dev, h->sens_stream), 1);     // manifolds of the near envs -> slow list
     CUDA_TRY(cudaEventRecord(h->ev_sens_done, h->sens_stream));
     h->sensors_ahead = true;
     return CRL_OK;
 }
 
-// At the head of a step: wait for the sensors started ahead, or run them now (first step, after set_state / reset, or
-// when the plain schedule of crl_car_step_state wants them without the slow list).
-int sensors_for_this_step(crl_car* h, int classify, cudaStream_t s) {
+// At the head of a step: wait for the sensors (and, two-car envs, the manifolds and the slow list) started ahead, or run
+// them now (first step, after set_state / reset).
+int sensors_for_this_step(crl_car* h, cudaStream_t s) {
     if (h->sensors_ahead) {
         CUDA_TRY(cudaStreamWaitEvent(s, h->ev_sens_done, 0));
         h->sensors_ahead = false;
-        if (classify || h->dev.players == 1) return CRL_OK;      // what was computed ahead is what this step wants
+        return CRL_OK;
     }
-    if (classify) CUDA_TRY(cudaMemsetAsync(h->dev.slow_count, 0, sizeof(int32_t), s));
-    LAUNCH(launch_car_sensors(h->dev, classify, s), 1);
+    const int two = h->dev.players == 2 ? 1 : 0;
+    if (two) CUDA_TRY(cudaMemsetAsync(h->dev.slow_count, 0, 2 * sizeof(int32_t), s));
+    LAUNCH(launch_car_sensors(h->dev, two, s), 1);
+    if (two) LAUNCH(launch_car_collide(h->dev, s), 1);
     return CRL_OK;
 }
 
@@ -392,7 +395,7 @@ int crl_car_create(const crl_car_config* cfg, crl_car** out) {
     ALLOC(d.map_index, 2 * n * CAR_MAP_GRID * CAR_MAP_GRID); ALLOC(d.map_blocks, 2 * n * CAR_MAP_MAX_BLOCKS * 256);
     ALLOC(d.tile_centres, 2 * n * CAR_MAX_TRACK);
     ALLOC(h->actions_stage, nc * 2); ALLOC(h->rew_stage, nc); ALLOC(h->done_stage, n); ALLOC(h->steps_stage, n); ALLOC(h->trunc_stage, n);
-    if (P == 2) { ALLOC(d.contacts, n * CAR_MAX_CONTACTS); ALLOC(d.n_contacts, n); ALLOC(d.slow_list, n); ALLOC(d.slow_count, 1); }
+    if (P == 2) { ALLOC(d.contacts, n * CAR_MAX_CONTACTS); ALLOC(d.n_contacts, n); ALLOC(d.n_contacts_step, n); ALLOC(d.slow_list, n); ALLOC(d.slow_count, 2); d.near_count = d.slow_count + 1; ALLOC(d.near_list, n); }
     ALLOC(d.deferred, n);
     ALLOC(d.done_list, n); ALLOC(d.done_count, 1);
     CarHullConst* kdev = nullptr;
@@ -526,7 +529,7 @@ int crl_car_step_state(crl_car* h, const float* actions_dev, float* rew_dev, uin
     if (!actions_dev || !rew_dev || !done_dev || !num_steps_dev || !truncated_dev) return crl_set_error(CRL_E_INVALID, "null step buffer");
     h->dev.fill_all = 0;
     if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
-    if (int r = sensors_for_this_step(h, 0, (cudaStream_t)stream)) return r;
+    if (int r = sensors_for_this_step(h, (cudaStream_t)stream)) return r;
     LAUNCH(launch_car_step(h->dev, 0, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, (cudaStream_t)stream), 1);
     return CRL_OK;
 }
@@ -587,7 +590,7 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
     h->dev.fill_all = 0;
     if (h->dev.ring_mode) h->dev.ring_phase = (h->dev.ring_phase + 1) % h->dev.c;
     CUDA_TRY(cudaMemsetAsync(h->dev.done_count, 0, sizeof(int32_t), s));
-    if (int r = sensors_for_this_step(h, 1, s)) return r;                      // wheel-tile overlaps + the slow list
+    if (int r = sensors_for_this_step(h, s)) return r;                         // wheel-tile overlaps, manifolds, the slow list
     CUDA_TRY(cudaEventRecord(h->ev_fast, s));
     CUDA_TRY(cudaStreamWaitEvent(h->side_stream, h->ev_fast, 0));
     LAUNCH(launch_car_step(h->dev, 2, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, h->side_stream), 1);
@@ -741,7 +744,7 @@ int crl_car_get_contacts(crl_car* h, int32_t* counts_host, int32_t* overflow_hos
     CHECK_HANDLE(h);
     cudaStream_t s = (cudaStream_t)stream;
     if (counts_host) {
-        if (h->dev.n_contacts) CUDA_TRY(cudaMemcpyAsync(counts_host, h->dev.n_contacts, (size_t)h->dev.n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (h->dev.n_contacts_step) CUDA_TRY(cudaMemcpyAsync(counts_host, h->dev.n_contacts_step, (size_t)h->dev.n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
         else memset(counts_host, 0, (size_t)h->dev.n * sizeof(int32_t));
     }
     if (overflow_host) CUDA_TRY(cudaMemcpyAsync(overflow_host, h->dev.contact_overflow, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
