@@ -358,7 +358,7 @@ __device__ void paint_hud_indicators(const RasterSmem& S, const uint8_t* glyphs,
     }
 }
 
-__global__ void __launch_bounds__(RASTER_THREADS, 6)
+__global__ void __launch_bounds__(RASTER_THREADS, 7)
 car_render_kernel(CarDev p, int only_done, int which, uint8_t* __restrict__ obs, uint8_t* __restrict__ term_obs) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     RasterSmem& S = *reinterpret_cast<RasterSmem*>(smem_raw);
