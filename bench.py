@@ -501,6 +501,7 @@ def car_leg(cx, a, env_id, N, steps, stack_mode="stack"):
         "n_gpus": cx.world, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "scaling": "weak",
         "step_latency_ms": {"p50": p50, "p99": p99, "max": pmax},
         "episodes_finished": finished, "resets_per_step": finished / steps,
+        "resets_without_pregenerated_track": int(stats1["resets_without_pregenerated_track"]),   # auto-resets that had to build their track inside the step
         "config": {"workload": "%s, %d envs per GPU x %d GPU(s), frame_stack 4, action_repeat 1, uniform random actions "
                                "(device Philox), TimeLimit 1000 with envs pre-aged uniformly over [0, 1000): auto-resets "
                                "(terminal observation + new track + reset frame) inside the timed region on every step"

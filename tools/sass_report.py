@@ -13,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "competitive-rl_b200", "libcrl_b200.so")
 KERNELS = ["pong_step_kernel", "pong_raster_fast_kernelILi84", "pong_raster_fast_kernelILi42", "pong_raster_quad_kernelILi42",
-           "car_step_kernel", "car_sensor_kernel", "car_render_kernel", "car_frame_setup_kernel", "car_frame_aux_kernel",
+           "car_step_kernel", "car_sensor_kernel", "car_collide_kernel", "car_render_kernel", "car_frame_setup_kernel", "car_frame_aux_kernel",
            "car_stack_shift_kernel", "car_reset_kernel", "car_pregen_kernel"]
 
 
