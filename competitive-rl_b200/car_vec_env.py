@@ -294,7 +294,7 @@ class CudaCarVecEnv(VecEnv):
         raw = self._impl.stats()
         ep = int(raw[0])
         return {"episodes": ep, "mean_length": raw[1] / ep if ep else 0.0, "mean_tiles": raw[2] / ep if ep else 0.0,
-                "resets_without_pregenerated_track": int(raw[3]), "slow_path_frames": int(raw[4]),
+                "resets_without_pregenerated_track": int(raw[3]), "cut_car_polygons": int(raw[4]),
                 "pregen_launches": int(raw[5])}
 
     def get_contacts(self):

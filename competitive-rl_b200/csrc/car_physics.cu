@@ -1,6 +1,7 @@
-// car_physics.cu -- cCarRacing game core: track generation + reset (one thread per env) and the
-// per-step pipeline (one thread per car): action decode, wheel model, sensor contacts / tile
-// reward, Box2D-style joint solver, done / TimeLimit logic.
+// car_physics.cu -- cCarRacing game core: track generation + reset (one warp per env, the next track ahead of time),
+// the wheel-tile sensor overlaps (one thread per wheel) and the car-car manifolds (one thread per fixture pair) ahead of
+// the step, and the per-step pipeline (one thread per car): action decode, wheel model, contact events / tile reward,
+// Box2D-style joint + contact solver, done / TimeLimit logic.
 //
 // Replaces (paths relative to /root/reference/competitive_rl/):
 //   car_racing/car_racing_multi_players.py  _create_track (262-452), reset (454-525), process_action (527-540),
@@ -9,7 +10,7 @@
 //   car_racing/register.py                  max_episode_steps=1000 (gym TimeLimit) (8-26)
 //   box2d-py 2.3 (un-vendored)              b2World::Step(1/50, 180, 60): b2Island::Solve + b2RevoluteJoint,
 //                                           polygon mass data, sensor overlap -- restated from the published
-//                                           algorithm (parity vs a real Box2D is unpinned, DESIGN.md section 10)
+//                                           algorithm (parity vs a real Box2D is unpinned, DESIGN.md section 9)
 //
 // Arithmetic: solver in fp32 exactly as Box2D (b2 float32), un-fused (-fmad=false); the Python-level
 // wheel model and the track generator in fp64 like the reference's Python floats.

@@ -289,7 +289,7 @@ int crl_car_get_track(crl_car* h, int32_t env, int32_t* n_out, double* pts_host,
 
 int crl_car_random_actions(float* actions_dev, int32_t n_values, uint64_t seed, uint64_t step, void* stream);
 /* [0] episodes [1] sum of episode lengths [2] sum of tiles visited (car 0) [3] auto-resets that found no track
- * generated ahead and built it inside the step [4] frames with a car polygon taller than its span table (scanned per pixel)
+ * generated ahead and built it inside the step [4] car fixture polygons taller than their 8-row span table (cut; impossible for rigid fixtures at obs_scale)
  * [5] launches of the ahead-of-time track generator so far */
 int crl_car_get_stats(crl_car* h, uint64_t* stats_host, void* stream);
 /* car-car contacts of cCarRacingDouble (what box2d-py's b2World::Step resolves between the fixtures of the two

@@ -349,7 +349,7 @@ def test_replayed_track_matches_reference_fixture():
 
 
 def test_autoreset_frame_matches_oracle():
-    """The observation an env shows right after its auto-reset (new track, new span tables) against the oracle's
+    """The observation an env shows right after its auto-reset (new track, new road map) against the oracle's
     rendering of that new track -- and the frames of the following steps."""
     import car_oracle as C
     from competitive_rl_b200 import _native
