@@ -313,6 +313,90 @@ car_frame_aux_kernel(CarDev p, int only_done, int which) {
     aux->meta[l] = pm;
 }
 
+// The same for passes over few frames (the auto-reset and slow-list passes, small batches), where what counts is the
+// length of one thread's chain, not the instruction total: 128 threads per frame, thread (polygon, row) -- lane i of a
+// polygon's eight computes vertex i, the eight exchange them by shuffles, and each scan-converts ONE row.  Twice the
+// instructions per frame, a third of the latency.
+constexpr int AUX_ROW_THREADS = 128;
+__global__ void __launch_bounds__(2 * AUX_ROW_THREADS)
+car_frame_aux_rows_kernel(CarDev p, int only_done, int which) {
+    int frame = blockIdx.x * 2 + (threadIdx.x >> 7);
+    const int t = threadIdx.x & (AUX_ROW_THREADS - 1);
+    if (frame >= listed_frames(p, only_done, which)) return;
+    frame = listed_frame(p, only_done, which, frame);
+    const int e = frame / p.players, pi = frame - e * p.players;
+    if (which == 1 && p.deferred[e] != 0) return;
+    const CarHullConst* K = p.consts;
+    const double obs_scale = car_obs_scale();
+    const FrameMap& m = p.frame_map[frame];
+    FrameAux* aux = reinterpret_cast<FrameAux*>(p.frame_aux) + frame;
+    {   // the road-map blocks under the window
+        const int nb = m.nbx * (m.nby_mul & 255), mul = m.nby_mul >> 8;
+        if (t < nb) {
+            const int slot = car_slot(p, e);
+            const uint16_t* index = p.map_index + (size_t)slot * CAR_MAP_GRID * CAR_MAP_GRID;
+            const int j = (t * mul) >> 10, i = t - j * m.nbx;
+            const int gx = m.obx + i, gy = m.oby + j;
+            unsigned int idx = 0u;
+            if ((unsigned)gx < (unsigned)CAR_MAP_GRID && (unsigned)gy < (unsigned)CAR_MAP_GRID) idx = index[gy * CAR_MAP_GRID + gx];
+            aux->blk[t] = (uint16_t)(idx == 0xFFFFu ? 0u : idx);
+        }
+    }
+    if (t >= AUX_ROW_THREADS - 2 * CROP_BLOCKS) {   // checker flags of the window's columns and rows, in 16-byte pieces
+        const int q = t - (AUX_ROW_THREADS - 2 * CROP_BLOCKS);
+        const int axis = q >= CROP_BLOCKS, k = axis ? q - CROP_BLOCKS : q, g = (axis ? m.oby : m.obx) + k;
+        uint4 f = make_uint4(0u, 0u, 0u, 0u);
+        if ((unsigned)g < (unsigned)CAR_MAP_GRID) f = __ldg(reinterpret_cast<const uint4*>(p.chk + axis * 2048) + g);
+        *reinterpret_cast<uint4*>((axis ? aux->chky : aux->chkx) + k * 16) = f;
+    }
+    // car polygon id = car * 8 + part (parts 0..3 the wheels, 4..7 the hull fixtures), row r of its span table
+    const int id = t >> 3, r = t & 7;
+    const int ck = id >> 3, part = id & 7;
+    PolyMeta pm;
+    pm.miny = 0; pm.rows = 0; pm.gray = 0; pm.n = 0; pm.pad0 = pm.pad1 = 0;
+    if (ck < p.players) {                                           // uniform over the warp (four polygons of one car)
+        const float* b = p.body + ((size_t)e * p.players + ck) * 40;
+        const float* body = (part < 4) ? b + 8 * (part + 1) : b;
+        float bs, bc;
+        sincosf(body[2], &bs, &bc);
+        float px = body[0], py = body[1];
+        if (part >= 4) { px = b[0] - (bc * K->hull_lcx - bs * K->hull_lcy); py = b[1] - (bs * K->hull_lcx + bc * K->hull_lcy); }
+        const int n = (part < 4) ? 4 : c_hull_count[part - 4];
+        int ix = 0, iy = 0;
+        if (r < n) {                                                // vertex r of the polygon
+            const float hw = (float)(14 * CR_SIZE), hr = (float)(27 * CR_SIZE);
+            float lx, ly;
+            if (part < 4) { lx = (r == 0 || r == 1) ? hw : -hw; ly = (r == 1 || r == 2) ? hr : -hr; }
+            else { lx = (float)(c_hull_poly[part - 4][r][0] * CR_SIZE); ly = (float)(c_hull_poly[part - 4][r][1] * CR_SIZE); }
+            const float wx = (bc * lx - bs * ly) + px, wy = (bs * lx + bc * ly) + py;
+            const float ox = wx - m.camx, oy = wy - m.camy;
+            const float rx2 = (m.tc * ox - m.ts * oy) + 0.0f, ry2 = (m.ts * ox + m.tc * oy) + 0.0f;
+            const float sxp = (float)((double)rx2 * -obs_scale) + (float)(CAR_W / 2.0);
+            const float syp = (float)((double)ry2 * -obs_scale) + (float)(CAR_H / 2.0);
+            ix = max(-32000, min(32000, (int)sxp)); iy = max(-32000, min(32000, (int)syp));
+        }
+        short vx[8], vy[8];
+        int minx = 0x7fffffff, maxx = -0x7fffffff, miny = 0x7fffffff, maxy = -0x7fffffff;
+        const int lane0 = threadIdx.x & 24;                         // first lane of this polygon's eight within the warp
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int gx = __shfl_sync(0xffffffffu, ix, lane0 + i), gy = __shfl_sync(0xffffffffu, iy, lane0 + i);
+            vx[i] = (short)gx; vy[i] = (short)gy;
+            if (i < n) { minx = min(minx, gx); maxx = max(maxx, gx); miny = min(miny, gy); maxy = max(maxy, gy); }
+        }
+        pm.gray = (part < 4) ? K->gray[G_WHEEL] : ((ck == pi) ? K->gray[G_OWN] : K->gray[G_OTHER]);
+        pm.n = (unsigned char)n;
+        pm.miny = (short)miny;
+        if (maxx >= 0 && minx < CAR_W && maxy >= 0 && miny < HUD_TOP) {
+            int rows = maxy - miny + 1;
+            if (rows > POLY_ROWS) { if (r == 0) atomicAdd(p.overrun + 2, 1); rows = POLY_ROWS; }
+            pm.rows = (short)rows;
+            if (r < rows) aux->spans[id][r] = scanline_spans(vx, vy, n, miny + r, maxy);
+        }
+    }
+    if (r == 0) aux->meta[id] = pm;
+}
+
 // HUD indicators and reward text (render_indicators_for_pygame :645-670), one warp, in paint order
 __device__ void paint_hud_indicators(const RasterSmem& S, const uint8_t* glyphs, const uint8_t* G, uint8_t* img, int lane) {
     const double W = CAR_W, H = CAR_H, s = W / 40.0, h = H / 40.0;
@@ -614,7 +698,11 @@ cudaError_t launch_car_ring_advance(const CarDev& p, cudaStream_t s) {
 
 cudaError_t launch_car_render(const CarDev& p, int only_done, int which, int advance, uint8_t* obs, uint8_t* term_obs, cudaStream_t s) {
     car_frame_setup_kernel<<<(p.n * p.players + 127) / 128, 128, 0, s>>>(p, only_done, which);
-    car_frame_aux_kernel<<<(p.n * p.players * 16 + 127) / 128, 128, 0, s>>>(p, only_done, which);
+    // few frames (list passes, small batches): the latency of one thread's chain counts, not the instruction total
+    if (only_done || which == 2 || p.n * p.players <= 4096)
+        car_frame_aux_rows_kernel<<<(p.n * p.players + 1) / 2, 2 * AUX_ROW_THREADS, 0, s>>>(p, only_done, which);
+    else
+        car_frame_aux_kernel<<<(p.n * p.players * 16 + 127) / 128, 128, 0, s>>>(p, only_done, which);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int ctas = (only_done || which == 2) ? min(p.n * p.players, LIST_PASS_CTAS) : p.n * p.players;
