@@ -171,13 +171,7 @@ __device__ __forceinline__ int listed_frame(const CarDev& p, int only_done, int 
 
 // Per-frame setup, part 1, one thread per (env, player) frame: camera and the integer screen -> road-map mapping (a serial
 // fp64 chain that would stall a whole CTA of the render kernel).
-__global__ void __launch_bounds__(128)
-car_frame_setup_kernel(CarDev p, int only_done, int which) {
-    int frame = blockIdx.x * blockDim.x + threadIdx.x;             // env * players + player; auto-reset pass: position on the done list
-    if (frame >= listed_frames(p, only_done, which)) return;
-    frame = listed_frame(p, only_done, which, frame);
-    const int e = frame / p.players;
-    if (which == 1 && p.deferred[e] != 0) return;                  // the envs of the slow physics pass come in their own pass (over the slow list)
+__device__ FrameMap car_frame_map_of(const CarDev& p, int frame) {
     const CarHullConst* K = p.consts;
     const double obs_scale = car_obs_scale();
     FrameMap m;
@@ -227,7 +221,17 @@ car_frame_setup_kernel(CarDev p, int only_done, int which) {
     m.nbx = min(((m.rx + u1 - CAR_MAP_ORIGIN) >> 4) - m.obx + 1, CROP_BLOCKS);
     const int nby = min(((m.ry + v1 - CAR_MAP_ORIGIN) >> 4) - m.oby + 1, CROP_BLOCKS);
     m.nby_mul = nby | (((1024 + m.nbx - 1) / m.nbx) << 8);
-    p.frame_map[frame] = m;
+    return m;
+}
+
+__global__ void __launch_bounds__(128)
+car_frame_setup_kernel(CarDev p, int only_done, int which) {
+    int frame = blockIdx.x * blockDim.x + threadIdx.x;             // env * players + player; auto-reset pass: position on the done list
+    if (frame >= listed_frames(p, only_done, which)) return;
+    frame = listed_frame(p, only_done, which, frame);
+    const int e = frame / p.players;
+    if (which == 1 && p.deferred[e] != 0) return;                  // the envs of the slow physics pass come in their own pass (over the slow list)
+    p.frame_map[frame] = car_frame_map_of(p, frame);
 }
 
 // Per-frame setup, part 2, 16 threads per frame: one car polygon each -- b2Vec2 fp32 arithmetic: path = -scale * (tmp *
@@ -328,7 +332,11 @@ car_frame_aux_rows_kernel(CarDev p, int only_done, int which) {
     if (which == 1 && p.deferred[e] != 0) return;
     const CarHullConst* K = p.consts;
     const double obs_scale = car_obs_scale();
-    const FrameMap& m = p.frame_map[frame];
+    // part 1 (camera, screen -> road-map mapping) by the first thread of the frame's 128: no separate launch for these passes
+    __shared__ FrameMap s_fm[2];
+    if (t == 0) { s_fm[threadIdx.x >> 7] = car_frame_map_of(p, frame); p.frame_map[frame] = s_fm[threadIdx.x >> 7]; }
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 7)), "r"(AUX_ROW_THREADS));   // the frame's four warps only
+    const FrameMap& m = s_fm[threadIdx.x >> 7];
     FrameAux* aux = reinterpret_cast<FrameAux*>(p.frame_aux) + frame;
     {   // the road-map blocks under the window
         const int nb = m.nbx * (m.nby_mul & 255), mul = m.nby_mul >> 8;
@@ -697,12 +705,14 @@ cudaError_t launch_car_ring_advance(const CarDev& p, cudaStream_t s) {
 }
 
 cudaError_t launch_car_render(const CarDev& p, int only_done, int which, int advance, uint8_t* obs, uint8_t* term_obs, cudaStream_t s) {
-    car_frame_setup_kernel<<<(p.n * p.players + 127) / 128, 128, 0, s>>>(p, only_done, which);
-    // few frames (list passes, small batches): the latency of one thread's chain counts, not the instruction total
+    // few frames (list passes, small batches): the latency of one thread's chain counts, not the instruction total --
+    // one kernel for both parts of the setup, a thread per (polygon, row)
     if (only_done || which == 2 || p.n * p.players <= 4096)
         car_frame_aux_rows_kernel<<<(p.n * p.players + 1) / 2, 2 * AUX_ROW_THREADS, 0, s>>>(p, only_done, which);
-    else
+    else {
+        car_frame_setup_kernel<<<(p.n * p.players + 127) / 128, 128, 0, s>>>(p, only_done, which);
         car_frame_aux_kernel<<<(p.n * p.players * 16 + 127) / 128, 128, 0, s>>>(p, only_done, which);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int ctas = (only_done || which == 2) ? min(p.n * p.players, LIST_PASS_CTAS) : p.n * p.players;
