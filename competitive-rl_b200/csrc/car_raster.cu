@@ -234,6 +234,34 @@ car_frame_setup_kernel(CarDev p, int only_done, int which) {
     p.frame_map[frame] = car_frame_map_of(p, frame);
 }
 
+// Car.draw_for_pygame (car_dynamics.py:284-298) for one fixture polygon: `part` 0..3 = the wheels, 4..7 = the hull fixtures
+// of the car whose bodies start at `b`.  FixturePose = where the fixture's body sits; fixture_vertex = vertex i pushed through
+// path = -scale * (tmp * ((trans * v) - offset)) + (W/2, H/2) in b2Vec2 fp32 arithmetic and truncated to int like pygame
+// (clamped for the short storage: a polygon that far off the screen cannot touch the window anyway).
+struct FixturePose { float bs, bc, px, py; int n; };
+__device__ __forceinline__ FixturePose fixture_pose(const CarHullConst* K, const float* b, int part) {
+    const float* body = (part < 4) ? b + 8 * (part + 1) : b;
+    FixturePose f;
+    sincosf(body[2], &f.bs, &f.bc);
+    f.px = body[0]; f.py = body[1];
+    if (part >= 4) { f.px = b[0] - (f.bc * K->hull_lcx - f.bs * K->hull_lcy); f.py = b[1] - (f.bs * K->hull_lcx + f.bc * K->hull_lcy); }
+    f.n = (part < 4) ? 4 : c_hull_count[part - 4];
+    return f;
+}
+__device__ __forceinline__ void fixture_vertex(const FixturePose& f, const FrameMap& m, int part, int i, int& ix, int& iy) {
+    const float hw = (float)(14 * CR_SIZE), hr = (float)(27 * CR_SIZE);
+    const double obs_scale = car_obs_scale();
+    float lx, ly;
+    if (part < 4) { lx = (i == 0 || i == 1) ? hw : -hw; ly = (i == 1 || i == 2) ? hr : -hr; }
+    else { lx = (float)(c_hull_poly[part - 4][i][0] * CR_SIZE); ly = (float)(c_hull_poly[part - 4][i][1] * CR_SIZE); }
+    const float wx = (f.bc * lx - f.bs * ly) + f.px, wy = (f.bs * lx + f.bc * ly) + f.py;
+    const float ox = wx - m.camx, oy = wy - m.camy;
+    const float rx2 = (m.tc * ox - m.ts * oy) + 0.0f, ry2 = (m.ts * ox + m.tc * oy) + 0.0f;
+    const float sxp = (float)((double)rx2 * -obs_scale) + (float)(CAR_W / 2.0);
+    const float syp = (float)((double)ry2 * -obs_scale) + (float)(CAR_H / 2.0);
+    ix = max(-32000, min(32000, (int)sxp)); iy = max(-32000, min(32000, (int)syp));
+}
+
 // Per-frame setup, part 2, 16 threads per frame: one car polygon each -- b2Vec2 fp32 arithmetic: path = -scale * (tmp *
 // ((trans * v) - offset)) + (W/2, H/2), truncated to int by pygame -- scan-converted with draw_fillpoly's rule, and the
 // pool positions of the road-map blocks under the window.
@@ -247,7 +275,6 @@ car_frame_aux_kernel(CarDev p, int only_done, int which) {
     const int e = frame / p.players, pi = frame - e * p.players;
     if (which == 1 && p.deferred[e] != 0) return;                  // the envs of the slow physics pass come in their own pass (over the slow list)
     const CarHullConst* K = p.consts;
-    const double obs_scale = car_obs_scale();
     const FrameMap& m = p.frame_map[frame];
     FrameAux* aux = reinterpret_cast<FrameAux*>(p.frame_aux) + frame;
     // ---- the road-map blocks under the window ----
@@ -275,30 +302,16 @@ car_frame_aux_kernel(CarDev p, int only_done, int which) {
     pm.miny = 0; pm.rows = 0; pm.gray = 0; pm.n = 0; pm.pad0 = pm.pad1 = 0;
     const int ck = l >> 3, part = l & 7;
     if (ck < p.players) {
-        const float* b = p.body + ((size_t)e * p.players + ck) * 40;
-        const float* body = (part < 4) ? b + 8 * (part + 1) : b;
-        float bs, bc;
-        sincosf(body[2], &bs, &bc);
-        float px = body[0], py = body[1];
-        if (part >= 4) { px = b[0] - (bc * K->hull_lcx - bs * K->hull_lcy); py = b[1] - (bs * K->hull_lcx + bc * K->hull_lcy); }
+        const FixturePose fp = fixture_pose(K, p.body + ((size_t)e * p.players + ck) * 40, part);
+        const int n = fp.n;
         short vx[8], vy[8];
-        const int n = (part < 4) ? 4 : c_hull_count[part - 4];
-        const float hw = (float)(14 * CR_SIZE), hr = (float)(27 * CR_SIZE);
         int minx = 0x7fffffff, maxx = -0x7fffffff, miny = 0x7fffffff, maxy = -0x7fffffff;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             vx[i] = 0; vy[i] = 0;
             if (i < n) {
-                float lx, ly;
-                if (part < 4) { lx = (i == 0 || i == 1) ? hw : -hw; ly = (i == 1 || i == 2) ? hr : -hr; }
-                else { lx = (float)(c_hull_poly[part - 4][i][0] * CR_SIZE); ly = (float)(c_hull_poly[part - 4][i][1] * CR_SIZE); }
-                const float wx = (bc * lx - bs * ly) + px, wy = (bs * lx + bc * ly) + py;
-                const float ox = wx - m.camx, oy = wy - m.camy;
-                const float rx2 = (m.tc * ox - m.ts * oy) + 0.0f, ry2 = (m.ts * ox + m.tc * oy) + 0.0f;
-                const float sxp = (float)((double)rx2 * -obs_scale) + (float)(CAR_W / 2.0);
-                const float syp = (float)((double)ry2 * -obs_scale) + (float)(CAR_H / 2.0);
-                // vertices far off the screen are clamped (short storage); such a polygon cannot touch the window anyway
-                const int ix = max(-32000, min(32000, (int)sxp)), iy = max(-32000, min(32000, (int)syp));
+                int ix, iy;
+                fixture_vertex(fp, m, part, i, ix, iy);
                 vx[i] = (short)ix; vy[i] = (short)iy;
                 minx = min(minx, ix); maxx = max(maxx, ix); miny = min(miny, iy); maxy = max(maxy, iy);
             }
@@ -331,7 +344,6 @@ car_frame_aux_rows_kernel(CarDev p, int only_done, int which) {
     const int e = frame / p.players, pi = frame - e * p.players;
     if (which == 1 && p.deferred[e] != 0) return;
     const CarHullConst* K = p.consts;
-    const double obs_scale = car_obs_scale();
     // part 1 (camera, screen -> road-map mapping) by the first thread of the frame's 128: no separate launch for these passes
     __shared__ FrameMap s_fm[2];
     if (t == 0) { s_fm[threadIdx.x >> 7] = car_frame_map_of(p, frame); p.frame_map[frame] = s_fm[threadIdx.x >> 7]; }
@@ -363,26 +375,10 @@ car_frame_aux_rows_kernel(CarDev p, int only_done, int which) {
     PolyMeta pm;
     pm.miny = 0; pm.rows = 0; pm.gray = 0; pm.n = 0; pm.pad0 = pm.pad1 = 0;
     if (ck < p.players) {                                           // uniform over the warp (four polygons of one car)
-        const float* b = p.body + ((size_t)e * p.players + ck) * 40;
-        const float* body = (part < 4) ? b + 8 * (part + 1) : b;
-        float bs, bc;
-        sincosf(body[2], &bs, &bc);
-        float px = body[0], py = body[1];
-        if (part >= 4) { px = b[0] - (bc * K->hull_lcx - bs * K->hull_lcy); py = b[1] - (bs * K->hull_lcx + bc * K->hull_lcy); }
-        const int n = (part < 4) ? 4 : c_hull_count[part - 4];
+        const FixturePose fp = fixture_pose(K, p.body + ((size_t)e * p.players + ck) * 40, part);
+        const int n = fp.n;
         int ix = 0, iy = 0;
-        if (r < n) {                                                // vertex r of the polygon
-            const float hw = (float)(14 * CR_SIZE), hr = (float)(27 * CR_SIZE);
-            float lx, ly;
-            if (part < 4) { lx = (r == 0 || r == 1) ? hw : -hw; ly = (r == 1 || r == 2) ? hr : -hr; }
-            else { lx = (float)(c_hull_poly[part - 4][r][0] * CR_SIZE); ly = (float)(c_hull_poly[part - 4][r][1] * CR_SIZE); }
-            const float wx = (bc * lx - bs * ly) + px, wy = (bs * lx + bc * ly) + py;
-            const float ox = wx - m.camx, oy = wy - m.camy;
-            const float rx2 = (m.tc * ox - m.ts * oy) + 0.0f, ry2 = (m.ts * ox + m.tc * oy) + 0.0f;
-            const float sxp = (float)((double)rx2 * -obs_scale) + (float)(CAR_W / 2.0);
-            const float syp = (float)((double)ry2 * -obs_scale) + (float)(CAR_H / 2.0);
-            ix = max(-32000, min(32000, (int)sxp)); iy = max(-32000, min(32000, (int)syp));
-        }
+        if (r < n) fixture_vertex(fp, m, part, r, ix, iy);          // vertex r of the polygon
         short vx[8], vy[8];
         int minx = 0x7fffffff, maxx = -0x7fffffff, miny = 0x7fffffff, maxy = -0x7fffffff;
         const int lane0 = threadIdx.x & 24;                         // first lane of this polygon's eight within the warp
