@@ -477,6 +477,30 @@ def test_without_frame_stack_the_observation_is_the_newest_frame():
     plain.close(); stacked.close()
 
 
+@pytest.mark.parametrize("frame_stack", [2, 8])
+def test_stack_depths_two_and_eight(frame_stack):
+    """The buffer rotation with the smallest and the largest stack depth (3 and 9 registered buffers) against the
+    stack-shift mode, through two rounds of TimeLimit resets."""
+    N = 12
+    a_env = _make("cCarRacingDouble-v0", N, seed=3, frame_stack=frame_stack, max_episode_steps=11, stack_mode="stack")
+    b_env = _make("cCarRacingDouble-v0", N, seed=3, frame_stack=frame_stack, max_episode_steps=11, stack_mode="stack-shift")
+    assert torch.equal(a_env.reset(), b_env.reset())
+    age = np.arange(N) % 11
+    a_env.set_elapsed(age); b_env.set_elapsed(age)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(3 * frame_stack + 25):
+        act = torch.rand((N, 2, 2), generator=gen, device="cuda") * 2 - 1
+        oa, ra, da, ia = a_env.step(act)
+        ob, rb, db, ib = b_env.step(act)
+        assert tuple(oa.shape) == (N, 2 * frame_stack, 96, 96)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), t
+        if bool(da.any()):
+            d = da.reshape(-1)
+            assert torch.equal(ia.terminal_observation()[d], ib.terminal_observation()[d]), t
+    a_env.check(); b_env.check()
+    a_env.close(); b_env.close()
+
+
 def test_car_sharding_invariance():
     """Tracks and spawn order come from an RNG keyed by the GLOBAL env index, and nothing in a step crosses envs: two
     shards of 128 two-car envs reproduce one batch of 256 bit for bit -- states, rewards, dones, contacts, frames
