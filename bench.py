@@ -484,13 +484,33 @@ def car_leg(cx, a, env_id, N, steps, stack_mode="stack"):
         host_step()
     cx.barrier()
     e2e_s = time.perf_counter() - t0
+
+    # ---- the Python API: envs.step(device actions) through the torch C++ extension (what a trainer calls) ----
+    K3 = min(steps, 200)
+    for k in range(5):
+        _native.check(lib.crl_car_random_actions(P(actions), actions.numel(), 7 + cx.rank, t + k, sp))
+        envs.step(actions if players == 2 else actions.view(N, 2))
+    cx.barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(stream)
+    for k in range(K3):
+        _native.check(lib.crl_car_random_actions(P(actions), actions.numel(), 7 + cx.rank, t + 5 + k, sp))
+        envs.step(actions if players == 2 else actions.view(N, 2))
+    a1.record(stream)
+    # ... and the C-ABI call over the next K3 steps of the same rollout (the workload drifts as episodes age: compare like with like)
+    for k in range(K3):
+        one(t + 5 + K3 + k)
+    a2 = torch.cuda.Event(enable_timing=True)
+    a2.record(stream)
+    cx.barrier()
+    api_ms, abi_ms = a0.elapsed_time(a1), a1.elapsed_time(a2)
     envs.check()
     envs.close()
     del envs
     torch.cuda.empty_cache()
 
-    ms, phys, rend, e2e_s, p50, p99, pmax = cx.max_over_ranks(
-        [ms, phys, rend, e2e_s, lat[len(lat) // 2], lat[min(len(lat) - 1, int(len(lat) * 0.99))], lat[-1]])
+    ms, phys, rend, e2e_s, p50, p99, pmax, api_ms, abi_ms = cx.max_over_ranks(
+        [ms, phys, rend, e2e_s, lat[len(lat) // 2], lat[min(len(lat) - 1, int(len(lat) * 0.99))], lat[-1], api_ms, abi_ms])
     finished = int(cx.sum_over_ranks([finished])[0])
     peak, peak_src = measured_peak()
     total = N * cx.world
@@ -521,6 +541,11 @@ def car_leg(cx, a, env_id, N, steps, stack_mode="stack"):
                 "d2h_bytes_per_step": (h_rew.numel() * 4 + 2 * N + 4 * N) * cx.world,
                 "note": "crl_car_step_host: pinned host actions in; rewards, dones, num_steps, truncated out; observations "
                         "stay in HBM"},
+        "api_step": {"value": total * K3 / (api_ms / 1e3), "unit": UNIT, "ms_per_step": api_ms / K3,
+                     "ratio_to_c_abi_same_phase": abi_ms / api_ms,
+                     "note": "envs.step(float32 device tensor) -> (obs, rew, done, infos) through the torch C++ extension, "
+                             "device-timed over %d steps; the ratio compares it with crl_car_step over the next %d steps of the "
+                             "same rollout (the workload drifts as the episodes age)" % (K3, K3)},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     if cx.rank == 0 and not a.no_cpu_baseline and cx.world == 1:

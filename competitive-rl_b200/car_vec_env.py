@@ -28,9 +28,16 @@ class LazyCarInfos(object):
         self._env, self.num_steps, self.rewards, self.done = env, num_steps, rewards, done
         # gym TimeLimit: the key exists only on the step the limit fired; its value is `not done` (always False with two
         # cars, whose `done` is a dict -- a quirk of the reference stack this reproduces)
-        self.time_limit_hit = (trunc_bits & 2) != 0
-        self.truncated = (trunc_bits & 1) != 0
+        self._trunc_bits = trunc_bits          # decoded on first use: nothing is launched per step for what nobody reads
         self._term, self._host = term, None
+
+    @property
+    def time_limit_hit(self):
+        return (self._trunc_bits & 2) != 0
+
+    @property
+    def truncated(self):
+        return (self._trunc_bits & 1) != 0
 
     def __len__(self):
         return self._env.num_envs
