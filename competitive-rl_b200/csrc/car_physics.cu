@@ -466,16 +466,23 @@ __device__ void car_reset_env(const CarDev& p, int e, int only_done, int lane) {
 struct Joint {
     F2 rA;
     float k00, k01, k02, k11, k12, k22;   // symmetric K (ex.x, ey.x, ez.x, ey.y, ez.y, ez.z)
+    float c33x, c33y, c33z, det33;        // b2Mat33::Solve33: cross(ey, ez) and 1 / det, the same every iteration of a step
     float motor_mass;
     float ix, iy, iz, motor_impulse, motor_speed;
     int limit_state;
 };
 
+// the part of Solve33 that does not depend on the right-hand side (same operations in the same order as Box2D's)
+__device__ __forceinline__ void solve33_prepare(Joint& j) {
+    const float ex0 = j.k00, ex1 = j.k01, ex2 = j.k02, ey0 = j.k01, ey1 = j.k11, ey2 = j.k12, ez0 = j.k02, ez1 = j.k12, ez2 = j.k22;
+    j.c33x = ey1 * ez2 - ey2 * ez1; j.c33y = ey2 * ez0 - ey0 * ez2; j.c33z = ey0 * ez1 - ey1 * ez0;
+    float det = ex0 * j.c33x + ex1 * j.c33y + ex2 * j.c33z;
+    if (det != 0.0f) det = 1.0f / det;
+    j.det33 = det;
+}
 __device__ __forceinline__ void solve33(const Joint& j, float b0, float b1, float b2, float& o0, float& o1, float& o2) {
     const float ex0 = j.k00, ex1 = j.k01, ex2 = j.k02, ey0 = j.k01, ey1 = j.k11, ey2 = j.k12, ez0 = j.k02, ez1 = j.k12, ez2 = j.k22;
-    const float cx = ey1 * ez2 - ey2 * ez1, cy = ey2 * ez0 - ey0 * ez2, cz = ey0 * ez1 - ey1 * ez0;
-    float det = ex0 * cx + ex1 * cy + ex2 * cz;
-    if (det != 0.0f) det = 1.0f / det;
+    const float cx = j.c33x, cy = j.c33y, cz = j.c33z, det = j.det33;
     o0 = det * (b0 * cx + b1 * cy + b2 * cz);
     const float bx = b1 * ez2 - b2 * ez1, by = b2 * ez0 - b0 * ez2, bz = b0 * ez1 - b1 * ez0;
     o1 = det * (ex0 * bx + ex1 * by + ex2 * bz);
@@ -1079,6 +1086,7 @@ car_step_kernel(CarDev p, int mode, const float* __restrict__ actions, float* __
                     j.k11 = mA + mB + j.rA.x * j.rA.x * iA;
                     j.k12 = j.rA.x * iA;
                     j.k22 = iA + iB;
+                    solve33_prepare(j);
                     j.motor_mass = iA + iB;
                     if (j.motor_mass > 0.0f) j.motor_mass = 1.0f / j.motor_mass;
                     const float joint_angle = a[bi] - a[0] - 0.0f;
