@@ -34,7 +34,8 @@ struct crl_car {
     // crl_car_step of two-car envs: envs whose cars touch are stepped on a side stream while the others render
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_fast = nullptr, ev_slow = nullptr;
-    // stack mode: the C - 1 frames that stay in the observation are moved ring -> obs on this stream while the physics runs
+    // plain stack mode without a registered buffer rotation ("stack-shift"): the C - 1 frames that stay in the observation
+    // are moved ring -> obs on this stream beside the render passes
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy_go = nullptr, ev_copy_done = nullptr;
     // the sensor kernel of the NEXT step, started on its own stream as soon as this step's auto-resets are done
@@ -555,9 +556,9 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
     CHECK_HANDLE(h);
     if (h->dev.players == 1) {
         if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
-        if (!obs_dev) return crl_set_error(CRL_E_INVALID, "null observation buffer");
+        if (!actions_dev || !obs_dev || !rew_dev || !done_dev || !num_steps_dev || !truncated_dev) return crl_set_error(CRL_E_INVALID, "null step buffer");
         cudaStream_t s1 = (cudaStream_t)stream;
-        if (int r = rotate_obs(h, obs_dev, false)) return r;
+        if (int r = rotate_obs(h, obs_dev, false)) return r;      // after the argument checks: a refused call leaves the rotation where it was
         if (int r = crl_car_step_state(h, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, stream)) return r;
         if (int r = fork_stack_shift(h, obs_dev, s1)) return r;                    // next to the render pass
         CUDA_TRY(cudaMemsetAsync(h->dev.done_count, 0, sizeof(int32_t), s1));
@@ -575,7 +576,8 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
     // contact solver and take several times longer than the rest.  So the sensor kernel lists the envs whose cars are near
     // each other, the listed envs are stepped on a side stream (slow pass) WHILE the main stream steps the others (fast
     // pass) and renders their frames; the frames of the listed envs follow.  Per env nothing changes; only the launch
-    // schedule does.  The frames that stay in the observation stack move ring -> obs on a third stream meanwhile.
+    // schedule does.  (Without a registered buffer rotation the frames that stay in the observation stack move ring -> obs
+    // on a third stream meanwhile.)
     if (!h->was_reset) return crl_set_error(CRL_E_STATE, "reset must be called before step");
     if (!actions_dev || !obs_dev || !rew_dev || !done_dev || !num_steps_dev || !truncated_dev) return crl_set_error(CRL_E_INVALID, "null step buffer");
     cudaStream_t s = (cudaStream_t)stream;
@@ -596,8 +598,8 @@ int crl_car_step(crl_car* h, const float* actions_dev, uint8_t* obs_dev, float* 
     LAUNCH(launch_car_step(h->dev, 2, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, h->side_stream), 1);
     CUDA_TRY(cudaEventRecord(h->ev_slow, h->side_stream));
     LAUNCH(launch_car_step(h->dev, 1, actions_dev, rew_dev, done_dev, num_steps_dev, truncated_dev, s), 1);
-    // the frames that stay in the stack: ring -> obs, next to the render passes (DRAM-bound beside issue-bound; the step
-    // kernels before it fill the register files, so it is not started under them)
+    // "stack-shift" only: the frames that stay in the stack, ring -> obs, next to the render passes (DRAM-bound beside
+    // issue-bound; the step kernels before it fill the register files, so it is not started under them)
     if (int r = fork_stack_shift(h, obs_dev, s)) return r;
     h->dev.collect_done = 1;
     LAUNCH(launch_car_render(h->dev, 0, 1, 0, obs_dev, term_obs_dev, s), 3);   // frames of the envs stepped by the fast pass
