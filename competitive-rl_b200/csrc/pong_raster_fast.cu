@@ -502,6 +502,7 @@ pong_raster_quad_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
                         uint8_t* __restrict__ obs1, const FastTabs<DIM>* __restrict__ gtabs) {
     constexpr int TAPS = FastCfg<DIM>::TAPS, NP = 1 << TAPS;
     constexpr int DD = DIM * DIM, QB = 4 * DD, NV = QB / 16, DW = DD / 4;
+    constexpr int TEXT_WORDS_MAX = 96 * DD / (42 * 42);      // pong_fast_tabs_fill refuses longer scoreboard entries (96 * 4 bytes at 42 x 42)
     typedef QuadTabs<DIM> Tabs;
     static_assert(QB % 16 == 0 && DD % 4 == 0, "a quad must be a whole number of 16-byte vectors");
 
@@ -711,17 +712,31 @@ pong_raster_quad_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
             // The four frames of a quad are the four stack slots of one env (frame_stack 4): nearly always one score pair.
             // Then the entry is fetched once by the whole warp (3 words per lane instead of 10 per lane of every group)
             // and stored into the four frame buffers.
+            // All loads of an entry are issued before its first store (fixed trip counts, no branch between them): one
+            // round trip to L1 / L2 per reload instead of one per chunk of a copy loop.
             const int id0 = __shfl_sync(0xffffffffu, text_id, 0);
             if (__all_sync(0xffffffffu, valid && text_id == id0)) {
                 uint32_t* q32 = reinterpret_cast<uint32_t*>(smq);
-                for (int i = lane; i < text_words; i += 32) {
-                    const uint32_t w = te[i];
-                    q32[i] = w; q32[DW + i] = w; q32[2 * DW + i] = w; q32[3 * DW + i] = w;
+                uint32_t w[(TEXT_WORDS_MAX + 31) / 32];
+                int wi[(TEXT_WORDS_MAX + 31) / 32];
+#pragma unroll
+                for (int k = 0; k < (TEXT_WORDS_MAX + 31) / 32; ++k) {
+                    wi[k] = min(lane + 32 * k, text_words - 1);      // past the end: the last word again (same value, same place)
+                    w[k] = te[wi[k]];
+                }
+#pragma unroll
+                for (int k = 0; k < (TEXT_WORDS_MAX + 31) / 32; ++k) {
+                    q32[wi[k]] = w[k]; q32[DW + wi[k]] = w[k]; q32[2 * DW + wi[k]] = w[k]; q32[3 * DW + wi[k]] = w[k];
                 }
                 cur_text = text_id;
             } else if (reload_text) {
                 uint32_t* d32 = reinterpret_cast<uint32_t*>(sm8);
-                for (int i = sub; i < text_words; i += 8) d32[i] = te[i];
+                uint32_t w[(TEXT_WORDS_MAX + 7) / 8];
+#pragma unroll
+                for (int k = 0; k < (TEXT_WORDS_MAX + 7) / 8; ++k) w[k] = te[min(sub + 8 * k, text_words - 1)];
+#pragma unroll
+                for (int k = 0; k < (TEXT_WORDS_MAX + 7) / 8; ++k)
+                    if (sub + 8 * k < text_words) d32[sub + 8 * k] = w[k];
                 cur_text = text_id;
             }
         }
