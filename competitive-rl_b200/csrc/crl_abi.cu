@@ -188,6 +188,7 @@ int crl_pong_create(const crl_pong_config* cfg, crl_pong** out) {
     const int dd = d.dim * d.dim;
     d.text_stride = ((tabs.text_rows * d.dim + 15) / 16) * 16;
     if (d.text_stride > ((dd + 15) / 16) * 16) d.text_stride = ((dd + 15) / 16) * 16;
+    d.text_w0 = 0; d.text_w1 = d.text_stride / 4;
 #define ALLOC(ptr, count)                                                        \
     do {                                                                         \
         cudaError_t _e = dev_alloc(h, &(ptr), (count));                          \
@@ -273,6 +274,23 @@ int crl_pong_load_atlas(crl_pong* h, const uint8_t* strips_host, size_t bytes, v
     CUDA_TRY(cudaMemcpyAsync(h->atlas_dev, strips_host, bytes, cudaMemcpyHostToDevice, s));
     LAUNCH(launch_pong_build_tables(h->dev, h->text_tab_dev, h->tmpl_dev, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    {   // The words of a scoreboard entry that differ between entries (any score pair, kind, agent) or from the template: the
+        // score digits cover a few of the rows above the arena only, and the rest of an entry never needs copying.
+        const int tw = h->dev.text_stride / 4;
+        const size_t n_ent = (size_t)ATLAS_SCORES * ATLAS_SCORES * 3 * 2;
+        std::vector<uint32_t> tt(n_ent * tw), tm(tw);
+        CUDA_TRY(cudaMemcpy(tt.data(), h->text_tab_dev, tt.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(tm.data(), h->tmpl_dev, tm.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        int w0 = tw, w1 = 0;
+        for (int w = 0; w < tw; ++w) {
+            bool differs = tm[w] != tt[w];
+            for (size_t e = 1; e < n_ent && !differs; ++e) differs = tt[e * tw + w] != tt[w];
+            if (differs) { if (w < w0) w0 = w; w1 = w + 1; }
+        }
+        if (w1 <= w0) w0 = w1 = 0;
+        if (getenv("CRL_PONG_TEXT_FULL") != nullptr) { w0 = 0; w1 = tw; }   // A/B switch: copy whole entries
+        h->dev.text_w0 = w0; h->dev.text_w1 = w1;
+    }
     h->atlas_loaded = true;
     return CRL_OK;
 }

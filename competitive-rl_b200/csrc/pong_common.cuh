@@ -115,6 +115,8 @@ struct PongDev {
     const uint8_t* text_tab;   // [22*22*3][2 agents][text_stride] preprocessed rows above the arena
     const uint8_t* tmpl;       // [dim*dim (+pad)] rect-free frame (score 0:0)
     int text_stride;           // bytes per text_tab entry (multiple of 16)
+    int text_w0, text_w1;      // 32-bit words [w0, w1) of an entry that differ between entries or from tmpl (host scan after the tables
+                               // are built; until then the whole entry): all the 42x42 quad kernel copies on a score change
     const void* fast_tabs;     // FastTabs<dim> image for the hot kernel (nullptr: dim not specialised)
     int fast_ok;               // atlas rows sharing a dst row with the arena are pure white
     int raster_grid[3];        // persistent grids of the hot kernels on this handle's device: [0] 84x84, [1] 42x42 one frame

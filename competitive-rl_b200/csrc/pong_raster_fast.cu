@@ -25,6 +25,8 @@
 //      the next frame.
 // HBM traffic = the observation bytes, written once; ~100 B/env of state are read.
 // The grid is persistent: SMs x resident CTAs, warps stride over the stacks.
+#include <type_traits>
+
 #include "pong_raster_dev.cuh"
 
 namespace crl {
@@ -535,7 +537,9 @@ pong_raster_quad_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
     }
     __syncthreads();
 
-    const int text_words = p.text_stride / 4;
+    // the words of a scoreboard entry that can differ from what a frame buffer holds (PongDev::text_w0 / text_w1: the rows
+    // with the score digits), clipped to what the copy loops below are sized for
+    const int text_w0 = p.text_w0, text_nw = min(p.text_w1, min(p.text_stride / 4, TEXT_WORDS_MAX)) - p.text_w0;
     const int cL = (int)T->bat_c0[0], cR = (int)T->bat_c0[1];
     const int b_which = sub >> 2, b_row = sub & 3;           // bat items of one side: (frame A | B, row)
     const int p_col = sub & 3, p_row = sub >> 2;             // ball pixels of one pooled frame: 4 x 2 window
@@ -715,28 +719,40 @@ pong_raster_quad_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
             // All loads of an entry are issued before its first store (fixed trip counts, no branch between them): one
             // round trip to L1 / L2 per reload instead of one per chunk of a copy loop.
             const int id0 = __shfl_sync(0xffffffffu, text_id, 0);
-            if (__all_sync(0xffffffffu, valid && text_id == id0)) {
+            if (text_nw <= 0) {                              // every entry equals the template
+                if (reload_text) cur_text = text_id;
+            } else if (__all_sync(0xffffffffu, valid && text_id == id0)) {
                 uint32_t* q32 = reinterpret_cast<uint32_t*>(smq);
-                uint32_t w[(TEXT_WORDS_MAX + 31) / 32];
-                int wi[(TEXT_WORDS_MAX + 31) / 32];
+                auto copy_warp = [&](auto KC) {
+                    constexpr int K = decltype(KC)::value;
+                    uint32_t w[K];
+                    int wi[K];
 #pragma unroll
-                for (int k = 0; k < (TEXT_WORDS_MAX + 31) / 32; ++k) {
-                    wi[k] = min(lane + 32 * k, text_words - 1);      // past the end: the last word again (same value, same place)
-                    w[k] = te[wi[k]];
-                }
+                    for (int k = 0; k < K; ++k) {
+                        wi[k] = text_w0 + min(lane + 32 * k, text_nw - 1);   // past the end: the last word again (same value, same place)
+                        w[k] = te[wi[k]];
+                    }
 #pragma unroll
-                for (int k = 0; k < (TEXT_WORDS_MAX + 31) / 32; ++k) {
-                    q32[wi[k]] = w[k]; q32[DW + wi[k]] = w[k]; q32[2 * DW + wi[k]] = w[k]; q32[3 * DW + wi[k]] = w[k];
-                }
+                    for (int k = 0; k < K; ++k) {
+                        q32[wi[k]] = w[k]; q32[DW + wi[k]] = w[k]; q32[2 * DW + wi[k]] = w[k]; q32[3 * DW + wi[k]] = w[k];
+                    }
+                };
+                if (text_nw <= 64) copy_warp(std::integral_constant<int, 2>{});
+                else copy_warp(std::integral_constant<int, (TEXT_WORDS_MAX + 31) / 32>{});
                 cur_text = text_id;
             } else if (reload_text) {
                 uint32_t* d32 = reinterpret_cast<uint32_t*>(sm8);
-                uint32_t w[(TEXT_WORDS_MAX + 7) / 8];
+                auto copy_group = [&](auto KC) {
+                    constexpr int K = decltype(KC)::value;
+                    uint32_t w[K];
 #pragma unroll
-                for (int k = 0; k < (TEXT_WORDS_MAX + 7) / 8; ++k) w[k] = te[min(sub + 8 * k, text_words - 1)];
+                    for (int k = 0; k < K; ++k) w[k] = te[text_w0 + min(sub + 8 * k, text_nw - 1)];
 #pragma unroll
-                for (int k = 0; k < (TEXT_WORDS_MAX + 7) / 8; ++k)
-                    if (sub + 8 * k < text_words) d32[sub + 8 * k] = w[k];
+                    for (int k = 0; k < K; ++k)
+                        if (sub + 8 * k < text_nw) d32[text_w0 + sub + 8 * k] = w[k];
+                };
+                if (text_nw <= 48) copy_group(std::integral_constant<int, 6>{});
+                else copy_group(std::integral_constant<int, (TEXT_WORDS_MAX + 7) / 8>{});
                 cur_text = text_id;
             }
         }
