@@ -714,7 +714,7 @@ pong_raster_quad_kernel(PongDev p, const FrameSpec* __restrict__ hist, uint8_t* 
         // ======== scoreboard rows of this frame's score pair(s), when the buffer holds another pair's ========
         if (__any_sync(0xffffffffu, reload_text)) {
             // The four frames of a quad are the four stack slots of one env (frame_stack 4): one score pair in about half the
-            // quads; then the entry is fetched once by the whole warp (3 words per lane instead of 10 per lane of every group)
+            // quads; then the entry is fetched once by the whole warp (2-3 words per lane instead of 6-12 per lane of every group)
             // and stored into the four frame buffers.
             // All loads of an entry are issued before its first store (fixed trip counts, no branch between them): one
             // round trip to L1 / L2 per reload instead of one per chunk of a copy loop.
